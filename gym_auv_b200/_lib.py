@@ -1,0 +1,203 @@
+"""ctypes binding of the C ABI in include/auv_b200.h (libauv_b200.so, built in-tree by
+``gym_auv_b200/build.py``).  There is NO fallback: if the shared library is missing or
+its ABI version differs, importing the compute path raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libauv_b200.so")
+ABI_VERSION = 3
+N_STATS = 16
+STAT_NAMES = [
+    "episodes",
+    "reward",
+    "reward_sq",
+    "progress",
+    "collisions",
+    "reached_goal",
+    "timesteps",
+    "cross_track_error",
+    "pathlength",
+    "steps",
+]
+
+OBSERVE_STEP = 0
+OBSERVE_RESET = 1
+REWARDER_IDS = {"colav": 0, "pathfollow": 1}
+CULL_IDS = {"reference": 0, "exact": 1}
+
+_vp = C.c_void_p
+
+
+class AuvConfig(C.Structure):
+    _fields_ = [
+        ("t_step_size", C.c_double),
+        ("thrust_max_auv", C.c_double),
+        ("moment_max_auv", C.c_double),
+        ("vessel_width", C.c_double),
+        ("look_ahead_distance", C.c_double),
+        ("sensor_range", C.c_double),
+        ("min_goal_distance", C.c_double),
+        ("min_path_progress", C.c_double),
+        ("min_cumulative_reward", C.c_double),
+        ("max_timesteps", C.c_int32),
+        ("sensor_interval_load_obstacles", C.c_int32),
+        ("n_sensors", C.c_int32),
+        ("n_sectors", C.c_int32),
+        ("use_lidar", C.c_int32),
+        ("sensor_log_transform", C.c_int32),
+        ("sensor_use_velocity_observations", C.c_int32),
+        ("rewarder", C.c_int32),
+        ("test_mode", C.c_int32),
+        ("cull_mode", C.c_int32),
+        ("auto_reset", C.c_int32),
+        ("reserved0", C.c_int32),
+    ]
+
+
+class AuvRayTable(C.Structure):
+    _fields_ = [("cos_sin", _vp), ("weight", _vp), ("sector", _vp), ("weight_sum", C.c_double)]
+
+
+class AuvPathBank(C.Structure):
+    _fields_ = [
+        ("n_paths", C.c_int32),
+        ("n_knots", C.c_int32),
+        ("poly_off", _vp),
+        ("poly_xy", _vp),
+        ("poly_cum", _vp),
+        ("blk_off", _vp),
+        ("blk_chord", _vp),
+        ("blk_dev", _vp),
+        ("origin", _vp),
+        ("knots", _vp),
+        ("coef", _vp),
+        ("length", _vp),
+        ("end_xy", _vp),
+    ]
+
+
+class AuvScenarioPool(C.Structure):
+    _fields_ = [
+        ("n_scenarios", C.c_int32),
+        ("k_moving", C.c_int32),
+        ("k_static", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("path_id", _vp),
+        ("vessel_init", _vp),
+        ("mov_start", _vp),
+        ("mov_width", _vp),
+        ("mov_track", _vp),
+        ("mov_pos0", _vp),
+        ("mov_disp0", _vp),
+        ("mov_counter0", _vp),
+        ("vel_table", _vp),
+        ("st_pos", _vp),
+        ("st_radius", _vp),
+    ]
+
+
+class AuvBatch(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32),
+        ("mask_words", C.c_int32),
+        ("env_offset", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("scn_id", _vp),
+        ("episode", _vp),
+        ("state", _vp),
+        ("step_counter", _vp),
+        ("t_step", _vp),
+        ("cum_reward", _vp),
+        ("max_progress", _vp),
+        ("cte_sum", _vp),
+        ("nearby_mask", _vp),
+        ("mov_pos", _vp),
+        ("mov_disp", _vp),
+        ("mov_counter", _vp),
+    ]
+
+
+class AuvStepOut(C.Structure):
+    _fields_ = [
+        ("obs", _vp),
+        ("reward", _vp),
+        ("done", _vp),
+        ("collision", _vp),
+        ("reached_goal", _vp),
+        ("goal_distance", _vp),
+        ("progress", _vp),
+        ("lidar_dist", _vp),
+        ("windows", _vp),
+        ("nav", _vp),
+        ("terminal_obs", _vp),
+        ("stats", _vp),
+        ("seg_tests", _vp),
+    ]
+
+
+EXPORTS = [
+    "auv_abi_version",
+    "auv_last_error",
+    "auv_obs_dim",
+    "auv_obstacle_update",
+    "auv_vessel_step",
+    "auv_observe",
+    "auv_reset",
+    "auv_step",
+    "auv_step_host",
+    "auv_fma_probe",
+]
+
+_lib = None
+
+
+class AuvLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libauv_b200.so (once).  Raises AuvLibraryError if it is absent or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AuvLibraryError(
+            f"{LIB_PATH} not found: build it with `python -m gym_auv_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise AuvLibraryError(f"{LIB_PATH} does not export {name}")
+    lib.auv_abi_version.restype = C.c_int
+    lib.auv_last_error.restype = C.c_char_p
+    lib.auv_obs_dim.argtypes = [C.POINTER(AuvConfig)]
+    P = C.POINTER
+    lib.auv_obstacle_update.argtypes = [P(AuvConfig), P(AuvScenarioPool), P(AuvBatch), _vp]
+    lib.auv_vessel_step.argtypes = [P(AuvConfig), P(AuvBatch), _vp, _vp]
+    lib.auv_observe.argtypes = [
+        P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), P(AuvStepOut), C.c_int, _vp,
+    ]
+    lib.auv_reset.argtypes = [P(AuvConfig), P(AuvScenarioPool), P(AuvBatch), _vp, _vp]
+    lib.auv_step.argtypes = [
+        P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, P(AuvStepOut), _vp,
+    ]
+    lib.auv_step_host.argtypes = [
+        P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, _vp, P(AuvStepOut),
+        _vp, _vp, _vp, _vp,
+    ]
+    lib.auv_fma_probe.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, P(C.c_double)]
+    ver = lib.auv_abi_version()
+    if ver != ABI_VERSION:
+        raise AuvLibraryError(f"ABI mismatch: library {ver}, binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().auv_last_error().decode("utf-8", "replace")
+        raise AuvLibraryError(f"{what} failed (rc={rc}): {msg}")

@@ -1,0 +1,77 @@
+// auv_device.cuh -- small device helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define AUV_PI 3.14159265358979323846
+#define AUV_FULL 0xffffffffu
+
+namespace auv {
+
+// geomutils.py:4-5  princip(angle) = ((angle + pi) % (2 pi)) - pi  with Python's floored
+// modulo (result of % has the sign of the divisor) => value in [-pi, pi).
+__device__ __forceinline__ double princip(double a) {
+  const double two_pi = 2.0 * AUV_PI;
+  double m = fmod(a + AUV_PI, two_pi);
+  if (m < 0.0) m += two_pi;
+  return m - AUV_PI;
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(AUV_FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(AUV_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(AUV_FULL, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+// lexicographic (d2, idx) arg-min over the warp; result valid in every lane
+__device__ __forceinline__ void warp_argmin(double& d2, int& idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double od = __shfl_xor_sync(AUV_FULL, d2, o);
+    int oi = __shfl_xor_sync(AUV_FULL, idx, o);
+    if (od < d2 || (od == d2 && oi < idx)) {
+      d2 = od;
+      idx = oi;
+    }
+  }
+}
+
+// distance from the origin-relative point (qx,qy) to segment (ax,ay)-(bx,by), FP32
+__device__ __forceinline__ float pt_seg_dist_f(float qx, float qy, float ax, float ay, float bx,
+                                               float by) {
+  float ex = bx - ax, ey = by - ay;
+  float wx = qx - ax, wy = qy - ay;
+  float len2 = ex * ex + ey * ey;
+  float t = wx * ex + wy * ey;
+  t = len2 > 0.f ? fminf(fmaxf(t / len2, 0.f), 1.f) : 0.f;
+  float dx = wx - t * ex, dy = wy - t * ey;
+  return sqrtf(dx * dx + dy * dy);
+}
+
+// circle -> regular n-gon side count of buffer(r).boundary.simplify(0.3)
+// (obstacles.py:101-106; closed form SURVEY.md App. A.5, pinned against a literal
+// Douglas-Peucker in oracle/geos_lite.py): n = 64/m, m the largest power of two <= 32
+// with r (1 - cos(m pi / 64)) <= 0.3.
+__device__ __forceinline__ int ngon_sides(double r) {
+  // 1 - cos(m*pi/64) for m = 32, 16, 8, 4, 2
+  if (r * 1.0 <= 0.3) return 2;
+  if (r * 0.29289321881345248 <= 0.3) return 4;
+  if (r * 0.07612046748871326 <= 0.3) return 8;
+  if (r * 0.01921471959676957 <= 0.3) return 16;
+  if (r * 0.00481527332780311 <= 0.3) return 32;
+  return 64;
+}
+
+}  // namespace auv

@@ -1,0 +1,174 @@
+"""Host-side construction of the path bank (reset-time work).
+
+A path is what ``gym_auv.objects.path.Path.__init__`` builds (path.py:19-40): three
+rounds of chord-length re-parametrisation through SciPy PCHIP resampled at 1000
+points, plus the 0.1 m polyline that ``LineString.project`` runs on.  The bank stores,
+per distinct path, exactly the tables the device needs:
+
+  * PPoly knots [1000] and coefficients [999][2][4] (FP64)      -> Path.__call__, get_direction
+  * polyline vertices [n][2] and chord-length prefix sums [n]     -> LineString.project
+  * one (chord, deviation) capsule per 32 consecutive segments    -> two-level exact search
+  * length, end point, origin
+
+Construction stays on the host with SciPy (the reference does the same); only
+evaluation and projection are on the per-step path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+from scipy import interpolate
+
+PATH_BLOCK = 32  # must equal AUV_PATH_BLOCK in include/auv_b200.h
+N_KNOTS = 1000
+
+
+@dataclass
+class PathTable:
+    """One path, host arrays (FP64 unless noted)."""
+
+    knots: np.ndarray  # [1000]
+    coef: np.ndarray  # [999, 2, 4]
+    poly: np.ndarray  # [n, 2]
+    cum: np.ndarray  # [n]
+    blk_chord: np.ndarray  # [nblk, 4] float32, relative to origin
+    blk_dev: np.ndarray  # [nblk] float32
+    origin: np.ndarray  # [2]
+    length: float
+    end: np.ndarray  # [2]
+    spline: object  # scipy PPoly (host-side evaluation for scenario generation)
+
+    def __call__(self, s):
+        return self.spline(s)
+
+    def direction(self, s):
+        d = self.spline.derivative()(s)
+        return np.arctan2(d[1], d[0])
+
+
+def _chord_lengths(pts: np.ndarray) -> np.ndarray:
+    seg = np.sqrt(np.sum(np.diff(pts, axis=1) ** 2, axis=0))
+    return np.concatenate([[0.0], np.cumsum(seg)])
+
+
+def build_path(waypoints) -> PathTable:
+    """waypoints: array [2, n_wp] (x row, y row) as passed to the reference's Path()."""
+    pts = np.array(waypoints, dtype=np.float64)
+    if pts.ndim != 2 or pts.shape[0] != 2 or pts.shape[1] < 2:
+        raise ValueError(f"waypoints must have shape [2, n>=2], got {pts.shape}")
+    spline = None
+    arc = None
+    for _ in range(3):
+        arc = _chord_lengths(pts)
+        spline = interpolate.PchipInterpolator(arc, pts, axis=1)
+        pts = spline(np.linspace(arc[0], arc[-1], N_KNOTS))
+    length = float(arc[-1])
+    n_poly = int(10 * length)
+    if n_poly < 2:
+        raise ValueError("path shorter than 0.2 m")
+    poly = np.ascontiguousarray(spline(np.linspace(0, length, n_poly)).T)  # [n, 2]
+    seglen = np.sqrt(np.sum(np.diff(poly, axis=0) ** 2, axis=1))
+    cum = np.concatenate([[0.0], np.cumsum(seglen)])
+    # PPoly.c has shape [4, 999, 2] (power, interval, axis) -> [999, 2, 4]
+    coef = np.ascontiguousarray(np.transpose(spline.c, (1, 2, 0)))
+    origin = poly[0].copy()
+
+    nseg = n_poly - 1
+    nblk = (nseg + PATH_BLOCK - 1) // PATH_BLOCK
+    first = np.arange(nblk) * PATH_BLOCK
+    last = np.minimum(first + PATH_BLOCK, nseg)  # vertex index of the block's last vertex
+    rel = poly - origin
+    chord = np.concatenate([rel[first], rel[last]], axis=1).astype(np.float32)  # [nblk, 4]
+    # max deviation of the block's vertices from its (float32-rounded) chord, in FP64
+    idx = np.minimum(first[:, None] + np.arange(PATH_BLOCK + 1)[None, :], last[:, None])
+    v = rel[idx]  # [nblk, 33, 2]
+    a = chord[:, None, 0:2].astype(np.float64)
+    b = chord[:, None, 2:4].astype(np.float64)
+    e = b - a
+    len2 = np.sum(e * e, axis=2)
+    w = v - a
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.where(len2 > 0, np.sum(w * e, axis=2) / len2, 0.0)
+    t = np.clip(t, 0.0, 1.0)
+    d = np.sqrt(np.sum((w - t[..., None] * e) ** 2, axis=2))
+    extent = float(np.abs(rel).max()) + 1.0
+    dev = d.max(axis=1) + 8.0 * np.finfo(np.float32).eps * extent
+    blk_dev = np.nextafter(dev.astype(np.float32), np.float32(np.inf))
+    return PathTable(
+        knots=np.ascontiguousarray(spline.x),
+        coef=coef,
+        poly=poly,
+        cum=cum,
+        blk_chord=chord,
+        blk_dev=blk_dev,
+        origin=origin,
+        length=length,
+        end=np.array(spline(length), dtype=np.float64),
+        spline=spline,
+    )
+
+
+class PathBank:
+    """A list of PathTable concatenated into the flat arrays of ``AuvPathBank``."""
+
+    def __init__(self, tables: Sequence[PathTable]):
+        if len(tables) == 0:
+            raise ValueError("empty path bank")
+        self.tables: List[PathTable] = list(tables)
+        self.n_paths = len(tables)
+        self.poly_off = np.zeros(self.n_paths + 1, dtype=np.int32)
+        self.blk_off = np.zeros(self.n_paths + 1, dtype=np.int32)
+        for i, t in enumerate(tables):
+            self.poly_off[i + 1] = self.poly_off[i] + len(t.poly)
+            self.blk_off[i + 1] = self.blk_off[i] + len(t.blk_dev)
+        self.poly_xy = np.concatenate([t.poly for t in tables], axis=0)
+        self.poly_cum = np.concatenate([t.cum for t in tables])
+        self.blk_chord = np.concatenate([t.blk_chord for t in tables], axis=0)
+        self.blk_dev = np.concatenate([t.blk_dev for t in tables])
+        self.origin = np.stack([t.origin for t in tables])
+        self.knots = np.stack([t.knots for t in tables])
+        self.coef = np.stack([t.coef for t in tables])
+        self.length = np.array([t.length for t in tables], dtype=np.float64)
+        self.end_xy = np.stack([t.end for t in tables])
+
+    @classmethod
+    def from_waypoints(cls, waypoint_list) -> "PathBank":
+        return cls([build_path(w) for w in waypoint_list])
+
+    def device_arrays(self, device):
+        import torch
+
+        def dev(a, dtype):
+            return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device)
+
+        return dict(
+            poly_off=dev(self.poly_off, torch.int32),
+            poly_xy=dev(self.poly_xy, torch.float64),
+            poly_cum=dev(self.poly_cum, torch.float64),
+            blk_off=dev(self.blk_off, torch.int32),
+            blk_chord=dev(self.blk_chord, torch.float32),
+            blk_dev=dev(self.blk_dev, torch.float32),
+            origin=dev(self.origin, torch.float64),
+            knots=dev(self.knots, torch.float64),
+            coef=dev(self.coef, torch.float64),
+            length=dev(self.length, torch.float64),
+            end_xy=dev(self.end_xy, torch.float64),
+        )
+
+
+def random_curve_waypoints(rng, nwaypoints: int, length: float = 400.0) -> np.ndarray:
+    """Waypoints of ``RandomCurveThroughOrigin`` (path.py:96-120): start on a circle of
+    radius length/2, end = -start, nwaypoints//2 rounds each inserting two jittered points
+    (the jitter is a scalar added to BOTH coordinates) around the origin.  Returns [2, n]."""
+    angle_init = 2 * np.pi * (rng.rand() - 0.5)
+    start = np.array([0.5 * length * np.cos(angle_init), 0.5 * length * np.sin(angle_init)])
+    end = -start
+    wps = np.vstack([start, end])
+    half = nwaypoints // 2
+    for k in range(half):
+        p1 = (half - k) * start / (half + 1) + length / (half + 1) * (rng.rand() - 0.5)
+        p2 = (half - k) * end / (half + 1) + length / (half + 1) * (rng.rand() - 0.5)
+        wps = np.vstack([wps[: k + 1, :], p1, np.array([0.0, 0.0]), p2, wps[-1 * k - 1 :, :]])
+    return np.transpose(wps)

@@ -1,0 +1,387 @@
+"""AUVVecEnv -- the batched, VecEnv-shaped entry point added in front of the reference's
+gym.Env contract.
+
+``step(actions[N,2]) -> (obs[N,D], reward[N], done[N], info)`` runs one full
+``BaseEnvironment.step`` (environment.py:292-366) for N envs on one B200 through the
+C ABI in ``include/auv_b200.h``; finished envs are auto-reset inside the same call
+(stable-baselines VecEnv semantics: the returned obs of a done env is the first obs of
+its next episode, the last obs of the finished one is in ``info["terminal_observation"]``).
+
+PyTorch is used for device memory and streams only; all arithmetic is in
+``libauv_b200.so``.  There is no CPU fallback: constructing an env without CUDA raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import Config
+from .scenarios import ScenarioSet
+from .spaces import Box
+
+
+def sector_partition(isensor: int, n_sensors: int, n_sectors: int, c: float = 0.1) -> int:
+    """utils/sector_partitioning.py:4-9."""
+    a, b = n_sensors, n_sectors
+
+    def sigma(x):
+        return b / (1 + np.exp((-x + a / 2) / (c * a)))
+
+    return int(np.floor(sigma(isensor) - sigma(0)))
+
+
+def ray_table(n_sensors: int, n_sectors: int):
+    """Per-ray constants: body angles (vessel.py:63-68), reward weights
+    (rewarder.py:203-205, gamma_theta = 10), sector ids."""
+    d = 2 * np.pi / n_sensors
+    ang = np.array([-np.pi + (i + 1) * d for i in range(n_sensors)], dtype=np.float64)
+    cos_sin = np.stack([np.cos(ang), np.sin(ang)], axis=1)
+    weight = 1.0 / (1.0 + np.abs(10.0 * ang))
+    wsum = 0.0
+    for w in weight:
+        wsum += float(w)
+    sector = np.array([sector_partition(i, n_sensors, n_sectors) for i in range(n_sensors)], dtype=np.uint8)
+    return ang, cos_sin, weight.astype(np.float32), wsum, sector
+
+
+def make_auv_config(cfg: Config, rewarder: str, test_mode: bool, auto_reset: bool, cull_mode: str) -> _lib.AuvConfig:
+    v, e, s = cfg.vessel, cfg.episode, cfg.simulation
+    if cfg.vessel.sensor_use_feasibility_pooling:
+        raise NotImplementedError(
+            "sensor_use_feasibility_pooling is broken in the reference at HEAD (SURVEY.md quirk #7)"
+        )
+    return _lib.AuvConfig(
+        t_step_size=float(s.t_step_size),
+        thrust_max_auv=float(v.thrust_max_auv),
+        moment_max_auv=float(v.moment_max_auv),
+        vessel_width=float(v.vessel_width),
+        look_ahead_distance=float(v.look_ahead_distance),
+        sensor_range=float(v.sensor_range),
+        min_goal_distance=float(e.min_goal_distance),
+        min_path_progress=float(e.min_path_progress),
+        min_cumulative_reward=float(e.min_cumulative_reward),
+        max_timesteps=int(e.max_timesteps),
+        sensor_interval_load_obstacles=int(v.sensor_interval_load_obstacles),
+        n_sensors=int(v.n_sensors),
+        n_sectors=int(v.n_sectors),
+        use_lidar=int(bool(v.use_lidar)),
+        sensor_log_transform=int(bool(v.sensor_log_transform)),
+        sensor_use_velocity_observations=int(bool(v.sensor_use_velocity_observations)),
+        rewarder=_lib.REWARDER_IDS[rewarder],
+        test_mode=int(bool(test_mode)),
+        cull_mode=_lib.CULL_IDS[cull_mode],
+        auto_reset=int(bool(auto_reset)),
+        reserved0=0,
+    )
+
+
+class AUVVecEnv:
+    """N gym-auv environments stepped together on one GPU.
+
+    Parameters
+    ----------
+    scenarios : ScenarioSet   pool of M scenarios (env i starts on scenario
+                              (env_offset + i) % M and moves on by N at every reset)
+    num_envs  : N
+    config    : gym_auv_b200.Config (reference field names)
+    device    : torch device (must be CUDA)
+    test_mode : as BaseEnvironment(test_mode=...) (environment.py:32,380-382)
+    auto_reset: VecEnv semantics (default) or manual ``reset_envs``
+    debug     : also record per-ray distances, culling windows and FP64 navigation values
+    """
+
+    def __init__(
+        self,
+        scenarios: ScenarioSet,
+        num_envs: int,
+        config: Optional[Config] = None,
+        device="cuda:0",
+        test_mode: bool = False,
+        auto_reset: bool = True,
+        cull_mode: str = "reference",
+        debug: bool = False,
+        env_offset: int = 0,
+    ):
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("AUVVecEnv needs a CUDA device: the step path has no CPU fallback")
+        self.lib = _lib.load()
+        self.config = config.copy() if config is not None else Config()
+        self.scenarios = scenarios
+        scenarios.validate()
+        self.num_envs = N = int(num_envs)
+        self.test_mode = test_mode
+        self.debug = debug
+        self.env_offset = int(env_offset)
+        self.cfg = make_auv_config(self.config, scenarios.rewarder, test_mode, auto_reset, cull_mode)
+        self.obs_dim = self.lib.auv_obs_dim(C.byref(self.cfg))
+        self.n_sensors = R = int(self.config.vessel.n_sensors)
+        dev = self.device
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
+
+        # ---- ray table
+        self.sensor_angles, cos_sin, weight, wsum, sector = ray_table(R, int(self.config.vessel.n_sectors))
+        self._ray = dict(cos_sin=t(cos_sin, torch.float64), weight=t(weight, torch.float32), sector=t(sector, torch.uint8))
+        self.sector_index = sector
+        self.rays = _lib.AuvRayTable(
+            self._ray["cos_sin"].data_ptr(), self._ray["weight"].data_ptr(), self._ray["sector"].data_ptr(), wsum
+        )
+
+        # ---- path bank
+        bank = scenarios.bank
+        self._bank = bank.device_arrays(dev)
+        b = self._bank
+        self.paths = _lib.AuvPathBank(
+            bank.n_paths, bank.knots.shape[1], b["poly_off"].data_ptr(), b["poly_xy"].data_ptr(),
+            b["poly_cum"].data_ptr(), b["blk_off"].data_ptr(), b["blk_chord"].data_ptr(), b["blk_dev"].data_ptr(),
+            b["origin"].data_ptr(), b["knots"].data_ptr(), b["coef"].data_ptr(), b["length"].data_ptr(),
+            b["end_xy"].data_ptr(),
+        )
+
+        # ---- scenario pool
+        M, Km, Ks = scenarios.n_scenarios, scenarios.k_moving, scenarios.k_static
+        self.k_moving, self.k_static = Km, Ks
+        pos0, disp0, counter0 = scenarios.initial_obstacle_state(float(self.config.simulation.t_step_size))
+        vel = scenarios.vel_table if len(scenarios.vel_table) else np.zeros((1, 2))
+        self._pool = dict(
+            path_id=t(scenarios.path_id, torch.int32),
+            vessel_init=t(scenarios.vessel_init, torch.float64),
+            mov_start=t(scenarios.mov_start, torch.float64),
+            mov_width=t(scenarios.mov_width, torch.float64),
+            mov_track=t(scenarios.mov_track, torch.int32),
+            mov_pos0=t(pos0, torch.float64),
+            mov_disp0=t(disp0, torch.float64),
+            mov_counter0=t(counter0, torch.float64),
+            vel_table=t(vel, torch.float64),
+            st_pos=t(scenarios.st_pos, torch.float64),
+            st_radius=t(scenarios.st_radius, torch.float64),
+        )
+        p = self._pool
+        self.pool = _lib.AuvScenarioPool(
+            M, Km, Ks, 0, p["path_id"].data_ptr(), p["vessel_init"].data_ptr(), p["mov_start"].data_ptr(),
+            p["mov_width"].data_ptr(), p["mov_track"].data_ptr(), p["mov_pos0"].data_ptr(), p["mov_disp0"].data_ptr(),
+            p["mov_counter0"].data_ptr(), p["vel_table"].data_ptr(), p["st_pos"].data_ptr(), p["st_radius"].data_ptr(),
+        )
+
+        # ---- mutable batch state
+        mw = max(1, (Km + Ks + 31) // 32)
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        self._st = dict(
+            scn_id=((torch.arange(N, device=dev, dtype=torch.int64) + self.env_offset) % M).to(torch.int32),
+            episode=z(N, torch.int32),
+            state=z((6, N), torch.float64),
+            step_counter=z(N, torch.int32),
+            t_step=z(N, torch.int32),
+            cum_reward=z(N, torch.float64),
+            max_progress=z(N, torch.float64),
+            cte_sum=z(N, torch.float64),
+            nearby_mask=z((N, mw), torch.int32),
+            mov_pos=z((N, max(Km, 1), 2), torch.float64),
+            mov_disp=z((N, max(Km, 1), 2), torch.float64),
+            mov_counter=z((N, max(Km, 1)), torch.float64),
+        )
+        s = self._st
+        self.batch = _lib.AuvBatch(
+            N, mw, self.env_offset, 0, s["scn_id"].data_ptr(), s["episode"].data_ptr(), s["state"].data_ptr(),
+            s["step_counter"].data_ptr(), s["t_step"].data_ptr(), s["cum_reward"].data_ptr(),
+            s["max_progress"].data_ptr(), s["cte_sum"].data_ptr(), s["nearby_mask"].data_ptr(),
+            s["mov_pos"].data_ptr(), s["mov_disp"].data_ptr(), s["mov_counter"].data_ptr(),
+        )
+
+        # ---- outputs
+        K = Km + Ks
+        self._out = dict(
+            obs=z((N, self.obs_dim), torch.float32),
+            reward=z(N, torch.float32),
+            done=z(N, torch.uint8),
+            collision=z(N, torch.uint8),
+            reached_goal=z(N, torch.uint8),
+            goal_distance=z(N, torch.float32),
+            progress=z(N, torch.float32),
+            terminal_obs=z((N, self.obs_dim), torch.float32),
+            stats=z(_lib.N_STATS, torch.float64),
+            seg_tests=z(1, torch.int64),
+        )
+        if debug:
+            self._out["lidar_dist"] = z((N, max(R, 1)), torch.float32)
+            self._out["windows"] = z((N, max(K, 1), 2), torch.int32)
+            self._out["nav"] = z((N, 8), torch.float64)
+        o = self._out
+        ptr = lambda k: o[k].data_ptr() if k in o else None
+        self.out = _lib.AuvStepOut(
+            ptr("obs"), ptr("reward"), ptr("done"), ptr("collision"), ptr("reached_goal"), ptr("goal_distance"),
+            ptr("progress"), ptr("lidar_dist"), ptr("windows"), ptr("nav"), ptr("terminal_obs"), ptr("stats"),
+            ptr("seg_tests") if debug else None,
+        )
+        self.actions_dev = z((N, 2), torch.float32)
+        self._pinned = None
+        self.total_steps = 0
+
+        self.action_space = Box(low=np.array([-1, -0.15]), high=np.array([1, 0.15]), dtype=np.float32)
+        self.observation_space = Box(low=-np.ones(self.obs_dim), high=np.ones(self.obs_dim), dtype=np.float32)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _refs(self):
+        return C.byref(self.cfg), C.byref(self.rays), C.byref(self.paths), C.byref(self.pool), C.byref(self.batch)
+
+    # ------------------------------------------------------------------ gym/VecEnv API
+    def reset(self) -> torch.Tensor:
+        """Reset every env (BaseEnvironment.reset, environment.py:176-245)."""
+        cfg, rays, paths, pool, batch = self._refs()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.auv_reset(cfg, pool, batch, None, self._stream()), "auv_reset")
+            _lib.check(
+                self.lib.auv_observe(cfg, rays, paths, pool, batch, C.byref(self.out), _lib.OBSERVE_RESET, self._stream()),
+                "auv_observe",
+            )
+        return self._out["obs"]
+
+    def reset_envs(self, mask: torch.Tensor, scenario_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Reset the envs where mask != 0 (optionally onto explicit scenario ids)."""
+        mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        if scenario_ids is not None:
+            sel = mask.bool()
+            self._st["scn_id"][sel] = scenario_ids.to(self.device, torch.int32)[sel]
+        cfg, rays, paths, pool, batch = self._refs()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.auv_reset(cfg, pool, batch, C.c_void_p(mask.data_ptr()), self._stream()), "auv_reset")
+            # observe everything in RESET mode would clobber live envs' max_progress only
+            # with identical values; obs of untouched envs is simply recomputed
+            _lib.check(
+                self.lib.auv_observe(cfg, rays, paths, pool, batch, C.byref(self.out), _lib.OBSERVE_RESET, self._stream()),
+                "auv_observe",
+            )
+        return self._out["obs"]
+
+    def step(self, actions: torch.Tensor):
+        """actions: [N, 2] float32 CUDA tensor (thrust, steer) -- environment.py:101-106."""
+        if actions.shape != (self.num_envs, 2):
+            raise ValueError(f"actions must have shape ({self.num_envs}, 2), got {tuple(actions.shape)}")
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        cfg, rays, paths, pool, batch = self._refs()
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.auv_step(cfg, rays, paths, pool, batch, C.c_void_p(a.data_ptr()), C.byref(self.out), self._stream()),
+                "auv_step",
+            )
+        self.total_steps += 1
+        return self._out["obs"], self._out["reward"], self._out["done"], self.info()
+
+    def step_host(self, actions: np.ndarray):
+        """NumPy in / NumPy out: the call a CPU-side VecEnv consumer makes (the e2e
+        path).  Copies actions H2D and obs/reward/done D2H through pinned buffers."""
+        N = self.num_envs
+        if self._pinned is None:
+            self._pinned = dict(
+                act=torch.zeros((N, 2), dtype=torch.float32).pin_memory(),
+                obs=torch.zeros((N, self.obs_dim), dtype=torch.float32).pin_memory(),
+                reward=torch.zeros(N, dtype=torch.float32).pin_memory(),
+                done=torch.zeros(N, dtype=torch.uint8).pin_memory(),
+            )
+        pin = self._pinned
+        pin["act"].numpy()[...] = actions
+        cfg, rays, paths, pool, batch = self._refs()
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.auv_step_host(
+                    cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
+                    C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.c_void_p(pin["obs"].data_ptr()),
+                    C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()), self._stream(),
+                ),
+                "auv_step_host",
+            )
+        self.total_steps += 1
+        return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy()
+
+    @property
+    def h2d_bytes_per_step(self) -> int:
+        return self.num_envs * 2 * 4
+
+    @property
+    def d2h_bytes_per_step(self) -> int:
+        return self.num_envs * (self.obs_dim * 4 + 4 + 1)
+
+    def info(self) -> Dict[str, torch.Tensor]:
+        o = self._out
+        return dict(
+            collision=o["collision"],
+            reached_goal=o["reached_goal"],
+            goal_distance=o["goal_distance"],
+            progress=o["progress"],
+            terminal_observation=o["terminal_obs"],
+        )
+
+    # ------------------------------------------------------------------ staged entry points
+    def obstacle_update(self):
+        cfg, _, _, pool, batch = self._refs()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.auv_obstacle_update(cfg, pool, batch, self._stream()), "auv_obstacle_update")
+
+    def vessel_step(self, actions: torch.Tensor):
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        cfg, _, _, _, batch = self._refs()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.auv_vessel_step(cfg, batch, C.c_void_p(a.data_ptr()), self._stream()), "auv_vessel_step")
+
+    def observe(self, mode=_lib.OBSERVE_STEP):
+        cfg, rays, paths, pool, batch = self._refs()
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.auv_observe(cfg, rays, paths, pool, batch, C.byref(self.out), mode, self._stream()),
+                "auv_observe",
+            )
+        return self._out["obs"]
+
+    # ------------------------------------------------------------------ attributes the reference driver reads
+    @property
+    def state(self) -> torch.Tensor:
+        """[6, N] FP64 vessel state x, y, psi, u, v, r."""
+        return self._st["state"]
+
+    def get_attr(self, name: str):
+        """SubprocVecEnv.get_attr-shaped access to per-env counters (scripts/run.py:415-426)."""
+        table = dict(
+            t_step=self._st["t_step"], cumulative_reward=self._st["cum_reward"], episode=self._st["episode"],
+            step_counter=self._st["step_counter"], max_progress=self._st["max_progress"], scn_id=self._st["scn_id"],
+            nearby_mask=self._st["nearby_mask"], mov_pos=self._st["mov_pos"], mov_counter=self._st["mov_counter"],
+        )
+        if name in table:
+            return table[name]
+        if name in self._out:
+            return self._out[name]
+        raise AttributeError(name)
+
+    def episode_stats(self, reduce: bool = True) -> Dict[str, float]:
+        """Per-episode means in the keys of ``env.history`` (environment.py:476-489).
+        With ``torch.distributed`` initialised and reduce=True the accumulators are summed
+        over ranks first -- the only collective on this path."""
+        st = self._out["stats"].clone()
+        st[9] = float(self.total_steps) * self.num_envs
+        if reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(st, op=torch.distributed.ReduceOp.SUM)
+        v = st.cpu().numpy()
+        n = max(v[0], 1.0)
+        mean_r = v[1] / n
+        return dict(
+            episodes=float(v[0]),
+            reward=float(mean_r),
+            reward_std=float(np.sqrt(max(v[2] / n - mean_r * mean_r, 0.0))),
+            progress=float(v[3] / n),
+            collision=float(v[4] / n),
+            reached_goal=float(v[5] / n),
+            timesteps=float(v[6] / n),
+            duration=float(v[6] / n * self.config.simulation.t_step_size),
+            cross_track_error=float(v[7] / n),
+            pathlength=float(v[8] / n),
+            steps=float(v[9]),
+        )
+
+    def close(self):
+        pass

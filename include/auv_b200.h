@@ -1,0 +1,225 @@
+/*
+ * auv_b200.h -- C ABI of the B200-native batched gym-auv step path.
+ *
+ * This is the drop-in boundary for the reference's per-step hot path.  The reference
+ * (krisbrud/gym-auv) is pure Python: its "FFI" for this path is the gym.Env method
+ * surface, so each entry point below names the Python interface it replaces
+ * (file:line under gym_auv/ in the reference):
+ *
+ *   auv_obstacle_update   <- BaseEnvironment._update            environment.py:386-392
+ *                            BaseObstacle.update                objects/obstacles.py:44-51
+ *                            VesselObstacle._update             objects/obstacles.py:195-215
+ *   auv_vessel_step       <- Vessel.step                        objects/vessel/vessel.py:226-247
+ *                            odesolver45                        objects/vessel/odesolver.py:2-47
+ *                            Vessel._state_dot                  objects/vessel/vessel.py:561-570
+ *   auv_observe           <- BaseEnvironment.observe            environment.py:247-290
+ *                            Vessel.navigate / Vessel.perceive  vessel.py:461-541 / 249-368
+ *                            find_rays_to_simulate_for_obstacles, simulate_sensor
+ *                                                               objects/vessel/sensor.py:74-97,140-159
+ *                            ColavRewarder/PathFollowRewarder.calculate
+ *                                                               objects/rewarder.py:167-241,78-140
+ *                            BaseEnvironment._isdone            environment.py:375-384
+ *                            BaseEnvironment.reset (auto-reset) environment.py:176-245
+ *   auv_step              <- BaseEnvironment.step               environment.py:292-366
+ *   auv_step_host         <- the same, called the way a NumPy VecEnv consumer does
+ *                            (SubprocVecEnv.step, scripts/run.py:296): host buffers in/out.
+ *
+ * Rules of the ABI: plain C, plain pointers and sizes, no torch types.  Every pointer in
+ * AuvPathBank / AuvScenarioPool / AuvBatch / AuvStepOut is a DEVICE pointer owned by the
+ * caller (PyTorch owns the allocations; this library never allocates device memory except
+ * the small staging buffers of auv_step_host).  Calls are asynchronous on the given
+ * cudaStream_t (passed as void*; NULL = legacy default stream).  Functions return 0 on
+ * success, a negative AUV_E* code for bad arguments, or a positive cudaError_t value; the
+ * message is available from auv_last_error().  Nothing throws across the boundary.
+ */
+#ifndef AUV_B200_H
+#define AUV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AUV_ABI_VERSION 3
+
+#define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
+#define AUV_ENOTSUP (-2) /* feature not built */
+
+#define AUV_REWARDER_COLAV 0      /* rewarder.py:143-241 */
+#define AUV_REWARDER_PATHFOLLOW 1 /* rewarder.py:56-140  */
+
+#define AUV_CULL_REFERENCE 0 /* replicate sensor.py:93 seam arithmetic exactly (default) */
+#define AUV_CULL_EXACT 1     /* wrap both window ends: every obstacle in range is seen   */
+
+#define AUV_MAX_RAYS 1024
+#define AUV_MAX_OBSTACLES 1024 /* moving + static slots per env */
+#define AUV_PATH_BLOCK 32     /* polyline segments per projection block */
+
+/* gym_auv/config.py field names (EpisodeConfig/SimulationConfig/VesselConfig).  POD. */
+typedef struct AuvConfig {
+  double t_step_size;           /* SimulationConfig.t_step_size            config.py:28  */
+  double thrust_max_auv;        /* VesselConfig.thrust_max_auv             config.py:39  */
+  double moment_max_auv;        /* VesselConfig.moment_max_auv             config.py:40  */
+  double vessel_width;          /* VesselConfig.vessel_width               config.py:41  */
+  double look_ahead_distance;   /* VesselConfig.look_ahead_distance        config.py:45  */
+  double sensor_range;          /* VesselConfig.sensor_range               config.py:64  */
+  double min_goal_distance;     /* EpisodeConfig.min_goal_distance         config.py:20  */
+  double min_path_progress;     /* EpisodeConfig.min_path_progress         config.py:23  */
+  double min_cumulative_reward; /* EpisodeConfig.min_cumulative_reward     config.py:16  */
+  int32_t max_timesteps;        /* EpisodeConfig.max_timesteps             config.py:19  */
+  int32_t sensor_interval_load_obstacles; /*                               config.py:56  */
+  int32_t n_sensors;            /* n_sensors_per_sector * n_sectors        config.py:75  */
+  int32_t n_sectors;            /*                                         config.py:58  */
+  int32_t use_lidar;            /*                                         config.py:52  */
+  int32_t sensor_log_transform; /*                                         config.py:65  */
+  int32_t sensor_use_velocity_observations; /* appends 2*n_sensors zeros   config.py:60  */
+  int32_t rewarder;             /* AUV_REWARDER_*                                       */
+  int32_t test_mode;            /* BaseEnvironment(test_mode=...)    environment.py:32  */
+  int32_t cull_mode;            /* AUV_CULL_*                                           */
+  int32_t auto_reset;           /* VecEnv semantics: reset done envs inside the step    */
+  int32_t reserved0;
+} AuvConfig;
+
+/* Per-ray constants, built once on the host from the config (vessel.py:63-68,
+ * rewarder.py:203-205, utils/sector_partitioning.py:4-9). */
+typedef struct AuvRayTable {
+  const double* cos_sin; /* [n_sensors][2]  cos/sin of body angle -pi+(i+1)*2pi/R       */
+  const float* weight;   /* [n_sensors]     1/(1+|10*angle_i|)                          */
+  const uint8_t* sector; /* [n_sensors]     sector index of ray i                       */
+  double weight_sum;     /* sum_i weight[i] (FP64, sequential order)                    */
+} AuvRayTable;
+
+/* Path bank: every distinct path (objects/path.py:19-40) tabulated once; envs refer to a
+ * path by id.  Polyline = the 0.1 m LineString of path.py:38-40 (FP64), its chord-length
+ * prefix sums, and per 32-segment block a chord + max deviation used as an exact
+ * two-level search structure for LineString.project (path.py:93).  PCHIP pieces are
+ * scipy PPoly coefficients (path.py:26). */
+typedef struct AuvPathBank {
+  int32_t n_paths;
+  int32_t n_knots;         /* 1000 */
+  const int32_t* poly_off; /* [n_paths+1] first polyline vertex of each path            */
+  const double* poly_xy;   /* [total_vertices][2]                                       */
+  const double* poly_cum;  /* [total_vertices] chord-length prefix sum at each vertex   */
+  const int32_t* blk_off;  /* [n_paths+1] first block of each path                      */
+  const float* blk_chord;  /* [total_blocks][4] ax,ay,bx,by relative to origin[path]    */
+  const float* blk_dev;    /* [total_blocks] max vertex deviation from chord + fp pad   */
+  const double* origin;    /* [n_paths][2]                                              */
+  const double* knots;     /* [n_paths][n_knots]                                        */
+  const double* coef;      /* [n_paths][n_knots-1][2][4]  (x: c0..c3, y: c0..c3)        */
+  const double* length;    /* [n_paths]   Path.length                                   */
+  const double* end_xy;    /* [n_paths][2] Path.end                                     */
+} AuvPathBank;
+
+/* Scenario pool: the read-only part of what a scenario plug-in's _generate() produces
+ * (envs/movingobstacles.py:28-95, envs/testscenario.py) for M scenarios, plus the state
+ * a freshly reset env starts from.  Obstacle slot order: moving first, then static
+ * circles (append order of movingobstacles.py:51-90).  width/radius <= 0 marks an
+ * unused slot. */
+typedef struct AuvScenarioPool {
+  int32_t n_scenarios;
+  int32_t k_moving;
+  int32_t k_static;
+  int32_t reserved0;
+  const int32_t* path_id;      /* [M]                                                   */
+  const double* vessel_init;   /* [M][3] x, y, psi                                      */
+  const double* mov_start;     /* [M][k_moving][2]  trajectory[0] (wrap target)         */
+  const double* mov_width;     /* [M][k_moving]                                         */
+  const int32_t* mov_track;    /* [M][k_moving][4]  vel_off, vel_len, vel_stride, 0     */
+  const double* mov_pos0;      /* [M][k_moving][2]  position right after reset()        */
+  const double* mov_disp0;     /* [M][k_moving][2]  last (dx,dy) right after reset()    */
+  const double* mov_counter0;  /* [M][k_moving]     waypoint_counter after reset()      */
+  const double* vel_table;     /* [n_vel][2] per-second velocities obstacles.py:160-172 */
+  const double* st_pos;        /* [M][k_static][2]                                      */
+  const double* st_radius;     /* [M][k_static]                                         */
+} AuvScenarioPool;
+
+/* Mutable per-env state (SoA).  N = n_envs. */
+typedef struct AuvBatch {
+  int32_t n_envs;
+  int32_t mask_words;     /* ceil((k_moving+k_static)/32)                               */
+  int32_t env_offset;     /* global index of env 0 (multi-GPU shards), used by reset    */
+  int32_t reserved0;
+  int32_t* scn_id;        /* [N]   scenario each env currently runs                     */
+  int32_t* episode;       /* [N]   BaseEnvironment.episode                              */
+  double* state;          /* [6][N] x, y, psi, u, v, r   (Vessel._state)                */
+  int32_t* step_counter;  /* [N]   Vessel._step_counter                                 */
+  int32_t* t_step;        /* [N]   BaseEnvironment.t_step                               */
+  double* cum_reward;     /* [N]   BaseEnvironment.cumulative_reward                    */
+  double* max_progress;   /* [N]   Vessel._max_progress                                 */
+  double* cte_sum;        /* [N]   sum |cross_track_error|*100 over the episode         */
+  uint32_t* nearby_mask;  /* [N][mask_words] Vessel._nearby_obstacles membership        */
+  double* mov_pos;        /* [N][k_moving][2]                                           */
+  double* mov_disp;       /* [N][k_moving][2]                                           */
+  double* mov_counter;    /* [N][k_moving]                                              */
+} AuvBatch;
+
+/* Outputs of one step / observe (all optional except obs/reward/done). */
+typedef struct AuvStepOut {
+  float* obs;            /* [N][obs_dim]  obs_dim = 6 (+ n_sensors (+ 2 n_sensors))     */
+  float* reward;         /* [N]                                                         */
+  uint8_t* done;         /* [N]                                                         */
+  uint8_t* collision;    /* [N] info["collision"]                                       */
+  uint8_t* reached_goal; /* [N] info["reached_goal"]                                    */
+  float* goal_distance;  /* [N] info["goal_distance"]                                   */
+  float* progress;       /* [N] info["progress"]                                        */
+  float* lidar_dist;     /* [N][n_sensors] or NULL: latest distance measurements        */
+  int32_t* windows;      /* [N][K][2] or NULL: culling (a, b) per obstacle slot (debug) */
+  double* nav;           /* [N][8] or NULL: s, chi, y_e, s_la, la_err, head_err,
+                                          goal_dist, progress (FP64, debug/parity)      */
+  float* terminal_obs;   /* [N][obs_dim] or NULL: last obs of a finished episode        */
+  double* stats;         /* [AUV_N_STATS] or NULL: episode-statistic accumulators       */
+  unsigned long long* seg_tests; /* [1] or NULL: reference-semantics ray/segment tests  */
+} AuvStepOut;
+
+/* indices into AuvStepOut.stats (mirrors env.history keys, environment.py:476-489) */
+#define AUV_STAT_EPISODES 0
+#define AUV_STAT_REWARD 1
+#define AUV_STAT_REWARD_SQ 2
+#define AUV_STAT_PROGRESS 3
+#define AUV_STAT_COLLISIONS 4
+#define AUV_STAT_REACHED_GOAL 5
+#define AUV_STAT_TIMESTEPS 6
+#define AUV_STAT_CROSS_TRACK 7
+#define AUV_STAT_PATHLENGTH 8
+#define AUV_STAT_STEPS 9
+#define AUV_N_STATS 16
+
+/* observe modes */
+#define AUV_OBSERVE_STEP 0  /* observe + reward + done (+ auto-reset): tail of step()    */
+#define AUV_OBSERVE_RESET 1 /* observe only: what reset() returns (no reward/done)       */
+
+int auv_abi_version(void);
+const char* auv_last_error(void);
+int auv_obs_dim(const AuvConfig* cfg);
+
+int auv_obstacle_update(const AuvConfig* cfg, const AuvScenarioPool* pool, AuvBatch* batch,
+                        void* stream);
+int auv_vessel_step(const AuvConfig* cfg, AuvBatch* batch, const float* actions /*[N][2]*/,
+                    void* stream);
+int auv_observe(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode,
+                void* stream);
+/* Put envs [0,N) whose reset_mask[e] != 0 (or all when NULL) into the post-reset() state
+ * of scenario scn_id[e] (does not compute the observation: call auv_observe(RESET)). */
+int auv_reset(const AuvConfig* cfg, const AuvScenarioPool* pool, AuvBatch* batch,
+              const uint8_t* reset_mask, void* stream);
+/* One full env.step() for the whole batch: update -> vessel -> observe/reward/done. */
+int auv_step(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+             const AuvScenarioPool* pool, AuvBatch* batch, const float* actions,
+             AuvStepOut* out, void* stream);
+/* Same with HOST buffers: actions_host -> device, step, obs/reward/done -> host.  The
+ * device staging lives in `out` / `actions_dev`; host pointers should be pinned. */
+int auv_step_host(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                  const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
+                  float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
+                  uint8_t* done_host, void* stream);
+/* Measured FP32 FMA peak helper (roofline denominator): runs `iters` dependent FMAs per
+ * thread on a full grid; the caller times it with CUDA events. Returns flop count. */
+int auv_fma_probe(float* sink, int blocks, int threads, int iters, void* stream,
+                  double* flops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUV_B200_H */

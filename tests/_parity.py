@@ -1,0 +1,148 @@
+"""Shared harness: run the same injected scenarios through the CPU oracle and the CUDA
+path and compare.  Tolerances follow BASELINE.json north_star: collision / done /
+reached_goal / culling windows / sector indices bit-exact (conditioned on the oracle's
+margin to the threshold being above the FP32 error band), vessel state, LiDAR ranges
+and rewards within a stated tolerance."""
+from __future__ import annotations
+
+import numpy as np
+
+RANGE_RTOL = 1e-4  # LiDAR ranges: |d_gpu - d_ref| <= RANGE_ATOL + RANGE_RTOL * d_ref
+RANGE_ATOL = 1e-4
+STATE_TOL = 1e-9   # vessel state is integrated in FP64 on the GPU
+REWARD_RTOL = 1e-4
+REWARD_ATOL = 1e-4
+OBS_ATOL = 2e-5    # closeness in [0,1] (FP32 log)
+COLLISION_BAND = 2e-4  # |min d - vessel_width| below this: FP32 may legitimately differ
+
+
+def oracle_cfg(config, **extra):
+    v, e, s = config.vessel, config.episode, config.simulation
+    d = dict(
+        min_cumulative_reward=e.min_cumulative_reward, max_timesteps=e.max_timesteps,
+        min_goal_distance=e.min_goal_distance, min_path_progress=e.min_path_progress,
+        t_step_size=s.t_step_size, thrust_max_auv=v.thrust_max_auv, moment_max_auv=v.moment_max_auv,
+        vessel_width=v.vessel_width, look_ahead_distance=v.look_ahead_distance, use_lidar=v.use_lidar,
+        sensor_interval_load_obstacles=v.sensor_interval_load_obstacles,
+        n_sensors_per_sector=v.n_sensors_per_sector, n_sectors=v.n_sectors, sensor_range=v.sensor_range,
+        sensor_log_transform=v.sensor_log_transform,
+        sensor_use_velocity_observations=v.sensor_use_velocity_observations,
+    )
+    d.update(extra)
+    return d
+
+
+def rollout_oracle(scn, config, actions, test_mode=True):
+    """actions: [T, M, 2].  Returns dict of arrays [T(+1), M, ...] (stops an env at done)."""
+    from oracle.sim import OracleEnv
+
+    T, M = actions.shape[0], scn.n_scenarios
+    R = config.vessel.n_sensors if config.vessel.use_lidar else 0
+    out = dict(
+        obs0=[], obs=np.full((T, M, 6 + R), np.nan), reward=np.full((T, M), np.nan),
+        done=np.zeros((T, M), bool), collision=np.zeros((T, M), bool), reached=np.zeros((T, M), bool),
+        state=np.full((T, M, 6), np.nan), dists=np.full((T, M, max(R, 1)), np.nan),
+        progress=np.full((T, M), np.nan), goal_distance=np.full((T, M), np.nan),
+        min_dist=np.full((T, M), np.inf), alive=np.zeros((T, M), bool), s=np.full((T, M), np.nan),
+        windows=[[None] * M for _ in range(T)], n_tests=np.zeros(M, np.int64), mov_pos=[[None] * M for _ in range(T)],
+    )
+    for m in range(M):
+        env = OracleEnv(scn.describe(m), oracle_cfg(config), test_mode=test_mode)
+        out["obs0"].append(env.observe() if False else None)
+        env2_obs0 = None
+        for t in range(T):
+            obs, rew, done, info = env.step(actions[t, m])
+            out["alive"][t, m] = True
+            out["obs"][t, m] = obs
+            out["reward"][t, m] = rew
+            out["done"][t, m] = done
+            out["collision"][t, m] = info["collision"]
+            out["reached"][t, m] = info["reached_goal"]
+            out["state"][t, m] = env.vessel.state
+            out["progress"][t, m] = info["progress"]
+            out["goal_distance"][t, m] = info["goal_distance"]
+            out["s"][t, m] = env.vessel.nav["vessel_arclength"]
+            if R:
+                out["dists"][t, m] = env.vessel.dists
+                out["min_dist"][t, m] = env.vessel.dists.min()
+            out["mov_pos"][t][m] = np.array([o.position for o in env.obstacles if not o.static])
+            if done:
+                break
+        out["n_tests"][m] = env.vessel.n_tests
+    return out
+
+
+def rollout_gpu(scn, config, actions, test_mode=True, device="cuda:0", cull_mode="reference"):
+    import torch
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    T, M = actions.shape[0], scn.n_scenarios
+    env = AUVVecEnv(scn, M, config, device=device, test_mode=test_mode, auto_reset=False, debug=True,
+                    cull_mode=cull_mode)
+    obs0 = env.reset().cpu().numpy().copy()
+    R = config.vessel.n_sensors if config.vessel.use_lidar else 0
+    out = dict(obs0=obs0, obs=[], reward=[], done=[], collision=[], reached=[], state=[], dists=[], progress=[],
+               goal_distance=[], s=[], windows=[], mov_pos=[])
+    a = torch.as_tensor(actions, dtype=torch.float32, device=device)
+    for t in range(T):
+        obs, rew, done, info = env.step(a[t])
+        out["obs"].append(obs.cpu().numpy().copy())
+        out["reward"].append(rew.cpu().numpy().copy())
+        out["done"].append(done.cpu().numpy().astype(bool))
+        out["collision"].append(info["collision"].cpu().numpy().astype(bool))
+        out["reached"].append(info["reached_goal"].cpu().numpy().astype(bool))
+        out["state"].append(env.state.cpu().numpy().T.copy())
+        out["progress"].append(info["progress"].cpu().numpy().copy())
+        out["goal_distance"].append(info["goal_distance"].cpu().numpy().copy())
+        out["s"].append(env.get_attr("nav")[:, 0].cpu().numpy().copy())
+        if R:
+            out["dists"].append(env.get_attr("lidar_dist").cpu().numpy().copy())
+        out["windows"].append(env.get_attr("windows").cpu().numpy().copy())
+        out["mov_pos"].append(env.get_attr("mov_pos").cpu().numpy().copy())
+    for k in ("obs", "reward", "done", "collision", "reached", "state", "dists", "progress", "goal_distance", "s",
+              "windows", "mov_pos"):
+        if out[k]:
+            out[k] = np.stack(out[k])
+    out["seg_tests"] = int(env.get_attr("seg_tests").item())
+    return out, env
+
+
+def compare(ref, gpu, config, label=""):
+    """Assert parity; returns a small report dict."""
+    alive = ref["alive"]
+    width = config.vessel.vessel_width
+    rep = dict(label=label, env_steps=int(alive.sum()))
+    # state (FP64 on both sides)
+    ds = np.abs(gpu["state"] - ref["state"])[alive]
+    rep["state_max_abs"] = float(ds.max())
+    assert ds.max() <= STATE_TOL * max(1.0, float(np.abs(ref["state"][alive]).max())), (label, ds.max())
+    # arclength / progress
+    d_s = np.abs(gpu["s"] - ref["s"])[alive]
+    rep["arclength_max_abs"] = float(d_s.max())
+    assert d_s.max() <= 1e-7, (label, "arclength", d_s.max())
+    if config.vessel.use_lidar:
+        dr, dg = ref["dists"][alive], gpu["dists"][alive]
+        err = np.abs(dg - dr)
+        tol = RANGE_ATOL + RANGE_RTOL * dr
+        rep["range_max_abs"] = float(err.max())
+        rep["range_max_rel"] = float((err / np.maximum(dr, 1e-9))[dr > 1e-3].max()) if (dr > 1e-3).any() else 0.0
+        bad = err > tol
+        assert not bad.any(), (label, "ranges", int(bad.sum()), float(err.max()), np.argwhere(bad)[:5], dr[bad][:5], dg[bad][:5])
+    # bit-exact flags, conditioned on margin
+    margin = np.abs(ref["min_dist"] - width)
+    decisive = alive & (margin > COLLISION_BAND)
+    rep["collision_decisive"] = int(decisive.sum())
+    rep["collision_skipped_in_band"] = int((alive & ~decisive).sum())
+    assert np.array_equal(gpu["collision"][decisive], ref["collision"][decisive]), (label, "collision")
+    assert np.array_equal(gpu["reached"][alive], ref["reached"][alive]), (label, "reached_goal")
+    assert np.array_equal(gpu["done"][decisive], ref["done"][decisive]), (label, "done")
+    # rewards
+    rr, rg = ref["reward"][decisive], gpu["reward"][decisive]
+    rerr = np.abs(rg - rr)
+    rep["reward_max_abs"] = float(rerr.max()) if rerr.size else 0.0
+    assert np.all(rerr <= REWARD_ATOL + REWARD_RTOL * np.abs(rr)), (label, "reward", rerr.max())
+    # observations
+    oerr = np.abs(gpu["obs"] - ref["obs"])[alive]
+    rep["obs_max_abs"] = float(oerr.max())
+    assert oerr.max() <= max(OBS_ATOL, RANGE_RTOL), (label, "obs", oerr.max())
+    return rep
