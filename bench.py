@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the gym-auv step path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port)
+
+Workload (BASELINE.json configs[2]): MovingObstacles, 65536 envs per GPU x 180 rays x
+32 obstacles (16 moving vessel pentagons + 16 static polygonised circles), paths shared
+from a bank of 1024 random curves, random actions, auto-reset on (non-test mode).
+One "step" = one full env.step() for every env of the batch (obstacle update, RKF45
+vessel step, path projection / navigation, 180-ray LiDAR with reference culling,
+reward, done, auto-reset).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job env-steps/s with actions resident
+in HBM; `e2e` = the same through auv_step_host with host buffers (H2D actions, D2H
+obs/reward/done inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (180-ray LiDAR, whole box)"
+UNIT = "env-steps/s"
+WORKLOAD = "MovingObstacles 65536 envs/GPU x 180 rays x 32 obstacles (16 moving + 16 static), 1024-path bank"
+
+# algorithmic bytes per env-step of the fused step, SURVEY.md section 8(d), FP64 state build:
+#   read : state 48 + action 8 + aux 40 + path tables ~ 3 x 64 + moving 16 x 40 + static 16 x 24
+#   write: state 48 + aux 40 + moving 16 x 40 + obs 186 x 4 + reward/done/info 14
+ALGO_BYTES_PER_ENV_STEP = (48 + 8 + 40 + 192 + 16 * 40 + 16 * 24) + (48 + 40 + 16 * 40 + 186 * 4 + 14)
+FLOP_PER_SEG_TEST = 16
+FLOP_PER_RAY = 60
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--n-moving", type=int, default=16)
+    ap.add_argument("--n-static", type=int, default=16)
+    ap.add_argument("--n-paths", type=int, default=1024)
+    ap.add_argument("--rays", type=int, default=180)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-envs", type=int, default=8)
+    ap.add_argument("--cpu-sample-steps", type=int, default=96)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def build_workload(args, rank):
+    from gym_auv_b200 import scenarios as S
+    from gym_auv_b200.config import Config
+
+    cfg = Config()
+    cfg.vessel.use_lidar = True
+    per_sector = args.rays // cfg.vessel.n_sectors
+    if per_sector * cfg.vessel.n_sectors != args.rays:
+        cfg.vessel.n_sectors = 8
+        per_sector = args.rays // 8
+    cfg.vessel.n_sensors_per_sector = per_sector
+    scn = S.moving_obstacles(args.envs, args.n_moving, args.n_static, seed=args.seed + 1000 * rank,
+                             n_paths=args.n_paths)
+    return cfg, scn
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle port (restated reference; Shapely/GEOS not installable)
+# --------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    descs, cfgd, actions, warmup = job
+    from oracle.sim import OracleEnv
+
+    envs = [OracleEnv(d, cfgd, test_mode=False) for d in descs]
+    T = actions.shape[0]
+    t0 = None
+    n = 0
+    for t in range(T):
+        if t == warmup:
+            t0 = time.perf_counter()
+        for i, env in enumerate(envs):
+            _, _, done, _ = env.step(actions[t, i])
+            if done:
+                env.reset()
+            if t >= warmup:
+                n += 1
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline(args, cfg, scn, n_envs, steps, warmup, procs):
+    """env-steps/s of the oracle port on `procs` host processes (each its own envs)."""
+    import multiprocessing as mp
+    from tests._parity import oracle_cfg
+
+    cfgd = oracle_cfg(cfg)
+    rng = np.random.RandomState(123)
+    per = max(1, n_envs // procs)
+    jobs = []
+    for p in range(procs):
+        ids = [(p * per + i) % scn.n_scenarios for i in range(per)]
+        acts = rng.uniform([-1, -0.15], [1, 0.15], size=(steps + warmup, per, 2))
+        jobs.append(([scn.describe(i) for i in ids], cfgd, acts, warmup))
+    if procs == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    total = sum(r[0] for r in res)
+    tmax = max(r[1] for r in res)
+    return total / tmax, total, tmax
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    small = argparse.Namespace(**vars(args))
+    small.envs = max(cores * 2, 16)
+    small.n_paths = min(args.n_paths, small.envs)
+    cfg, scn = build_workload(small, 0)
+    per_step_envs = small.envs
+    val, total, tmax = cpu_baseline(args, cfg, scn, per_step_envs, args.steps, args.warmup, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tmax / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{per_step_envs} envs per step on {cores} processes"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{total} env-steps ({per_step_envs} envs x {args.steps} steps), "
+                                   "oracle/sim.py FP64 restatement (Shapely/GEOS not installable)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gym_auv_b200 import _lib
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+
+    cfg, scn = build_workload(args, rank)
+    N, K, Wm = args.envs, args.steps, max(args.warmup, 3)
+    env = AUVVecEnv(scn, N, cfg, device=device, test_mode=False, auto_reset=True, env_offset=0)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1234 + rank)
+    lo = torch.tensor([-1.0, -0.15], device=device)
+    hi = torch.tensor([1.0, 0.15], device=device)
+    n_act = 16
+    actions = [lo + (hi - lo) * torch.rand((N, 2), device=device, generator=gen) for _ in range(n_act)]
+    env.reset()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(Wm):
+        env.step(actions[i % n_act])
+    barrier()
+    # snapshot so the counting pass can replay the exact same K steps
+    snap = {k: v.clone() for k, v in env._st.items()}
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    stream = torch.cuda.current_stream(device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    cfgp, rays, paths, pool, batch = env._refs()
+    import ctypes as C
+    barrier()
+    ev0.record(stream)
+    for i in range(K):
+        a = actions[(Wm + i) % n_act]
+        s = C.c_void_p(stream.cuda_stream)
+        _lib.check(env.lib.auv_obstacle_update(cfgp, pool, batch, s), "update")
+        _lib.check(env.lib.auv_vessel_step(cfgp, batch, C.c_void_p(a.data_ptr()), s), "vessel")
+        kev[i][0].record(stream)
+        _lib.check(env.lib.auv_observe(cfgp, rays, paths, pool, batch, C.byref(env.out), 0, s), "observe")
+        kev[i][1].record(stream)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    obs_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    t_local = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    ms_max = float(t_local.item())
+    value = world * N * K / (ms_max * 1e-3)
+
+    # ---- counting pass (untimed): replay the same K steps with the seg-test counter on
+    for k, v in snap.items():
+        env._st[k].copy_(v)
+    seg = torch.zeros(1, dtype=torch.int64, device=device)
+    env.out.seg_tests = seg.data_ptr()
+    for i in range(K):
+        env.step(actions[(Wm + i) % n_act])
+    torch.cuda.synchronize()
+    env.out.seg_tests = None
+    seg_tests_per_step = float(seg.item()) / K
+    dones_per_step = float(env._out["stats"][0].item()) / max(env.total_steps, 1)
+
+    # ---- FP32 FMA peak probe (roofline denominator for the LiDAR kernel), measured live
+    sink = torch.zeros(1, device=device)
+    fl = C.c_double(0)
+    blocks = 148 * 8
+    for _ in range(2):
+        env.lib.auv_fma_probe(C.c_void_p(sink.data_ptr()), blocks, 256, 1 << 15, C.c_void_p(stream.cuda_stream), C.byref(fl))
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    env.lib.auv_fma_probe(C.c_void_p(sink.data_ptr()), blocks, 256, 1 << 15, C.c_void_p(stream.cuda_stream), C.byref(fl))
+    p1.record(stream)
+    torch.cuda.synchronize()
+    fp32_peak_tflops = fl.value / (p0.elapsed_time(p1) * 1e-3) / 1e12
+
+    # ---- e2e through the host-buffer C ABI call
+    e2e = None
+    if not args.no_e2e:
+        acts_np = [a.cpu().numpy() for a in actions[:4]]
+        for i in range(2):
+            env.step_host(acts_np[i % 4])
+        barrier()
+        ke = max(3, min(K, 20))
+        t0 = time.perf_counter()
+        for i in range(ke):
+            env.step_host(acts_np[i % 4])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * N * ke / float(t_e.item()), "unit": UNIT,
+               "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
+               "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": ke}
+
+    stats = env.episode_stats(reduce=True)  # the only collective on the path (NCCL all-reduce)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    R = cfg.vessel.n_sensors
+    flops_per_launch = FLOP_PER_SEG_TEST * seg_tests_per_step + FLOP_PER_RAY * R * N
+    achieved_tflops = flops_per_launch / (obs_ms * 1e-3) / 1e12
+    achieved_gbs = ALGO_BYTES_PER_ENV_STEP * N / (obs_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 ray casting on f64 state/culling", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs_per_gpu": N, "rays": R, "obstacles": args.n_moving + args.n_static,
+                   "paths": args.n_paths, "l2": "per-step working set (state+obstacles ~%.0f MB, path bank ~%.0f MB) exceeds the 126 MB L2; no explicit flush"
+                   % (N * ALGO_BYTES_PER_ENV_STEP / 2e6, scn.bank.poly_xy.nbytes * 1.5 / 1e6 + scn.bank.coef.nbytes / 1e6),
+                   "auto_reset": True, "dones_per_step": dones_per_step},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": 3 * K,
+        "roofline": {
+            "kernel": "k_observe", "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops,
+            "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops if fp32_peak_tflops else None,
+            "traffic": None, "ms_per_launch": obs_ms,
+            "note": "algorithmic FLOPs = 16 x reference-semantics ray/segment tests + 60 x rays (SURVEY 8d); "
+                    "peak = FP32 FMA probe measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+            "seg_tests_per_env_step": seg_tests_per_step / N,
+            "hbm_view": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                         "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback",
+                         "algo_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP},
+        },
+        "episode_stats": stats,
+    }
+    if not args.no_cpu_baseline:
+        small = argparse.Namespace(**vars(args))
+        small.envs = args.cpu_sample_envs
+        small.n_paths = min(args.n_paths, small.envs)
+        ccfg, cscn = build_workload(small, 0)
+        v, total, tmax = cpu_baseline(args, ccfg, cscn, small.envs, args.cpu_sample_steps, 4, 1)
+        line["cpu_baseline"] = {
+            "value": v, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{total} env-steps ({small.envs} envs x {args.cpu_sample_steps} steps) of the same workload "
+                      "distribution, oracle/sim.py FP64 restatement (Shapely/GEOS not installable), %.1f s" % tmax,
+        }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

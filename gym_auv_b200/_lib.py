@@ -140,6 +140,7 @@ class AuvStepOut(C.Structure):
 
 EXPORTS = [
     "auv_abi_version",
+    "auv_sizeof",
     "auv_last_error",
     "auv_obs_dim",
     "auv_obstacle_update",
@@ -193,6 +194,10 @@ def load():
     ver = lib.auv_abi_version()
     if ver != ABI_VERSION:
         raise AuvLibraryError(f"ABI mismatch: library {ver}, binding {ABI_VERSION}; rebuild")
+    lib.auv_sizeof.argtypes = [C.c_int]
+    for i, st in enumerate([AuvConfig, AuvRayTable, AuvPathBank, AuvScenarioPool, AuvBatch, AuvStepOut]):
+        if lib.auv_sizeof(i) != C.sizeof(st):
+            raise AuvLibraryError(f"struct layout mismatch for {st.__name__}: C {lib.auv_sizeof(i)} vs ctypes {C.sizeof(st)}")
     _lib = lib
     return lib
 

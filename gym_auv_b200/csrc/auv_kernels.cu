@@ -622,10 +622,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
               float best = sdist[i];
               for (int o = 0; o < nact; ++o) {
                 const int oa = W.oa[o], ob = W.ob[o], fl = W.oflag[o];
-                const bool inwin = (fl & OFLAG_ALLRAYS) || (oa <= i && i < ob) || (oa <= i - R && i - R < ob);
+                // candidate(i) <=> a<=i<b or a<=i-R<b (Python negative-index wrap); an obstacle
+                // whose window is wider than R is listed -- and tested -- twice by the reference
+                const int hits = ((oa <= i && i < ob) ? 1 : 0) + ((oa <= i - R && i - R < ob) ? 1 : 0);
+                const bool inwin = (fl & OFLAG_ALLRAYS) || hits > 0;
                 if (!inwin) continue;
                 const int nvv = W.onv[o];
-                ntests += (unsigned)(nvv - 1);
+                ntests += (unsigned)((nvv - 1) * max(hits, 1));
                 if (fl & OFLAG_INSIDE) {
                   best = 0.f;
                   continue;
@@ -834,6 +837,17 @@ static int cuda_check(cudaError_t e, const char* where) {
 extern "C" {
 
 int auv_abi_version(void) { return AUV_ABI_VERSION; }
+int auv_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(AuvConfig);
+    case 1: return (int)sizeof(AuvRayTable);
+    case 2: return (int)sizeof(AuvPathBank);
+    case 3: return (int)sizeof(AuvScenarioPool);
+    case 4: return (int)sizeof(AuvBatch);
+    case 5: return (int)sizeof(AuvStepOut);
+    default: return AUV_EINVAL;
+  }
+}
 const char* auv_last_error(void) { return g_err; }
 
 int auv_obs_dim(const AuvConfig* cfg) {

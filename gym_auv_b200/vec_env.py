@@ -362,26 +362,13 @@ class AUVVecEnv:
         """Per-episode means in the keys of ``env.history`` (environment.py:476-489).
         With ``torch.distributed`` initialised and reduce=True the accumulators are summed
         over ranks first -- the only collective on this path."""
+        from .sharding import reduce_stats, summarize_stats
+
         st = self._out["stats"].clone()
         st[9] = float(self.total_steps) * self.num_envs
-        if reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(st, op=torch.distributed.ReduceOp.SUM)
-        v = st.cpu().numpy()
-        n = max(v[0], 1.0)
-        mean_r = v[1] / n
-        return dict(
-            episodes=float(v[0]),
-            reward=float(mean_r),
-            reward_std=float(np.sqrt(max(v[2] / n - mean_r * mean_r, 0.0))),
-            progress=float(v[3] / n),
-            collision=float(v[4] / n),
-            reached_goal=float(v[5] / n),
-            timesteps=float(v[6] / n),
-            duration=float(v[6] / n * self.config.simulation.t_step_size),
-            cross_track_error=float(v[7] / n),
-            pathlength=float(v[8] / n),
-            steps=float(v[9]),
-        )
+        if reduce:
+            st = reduce_stats(st)
+        return summarize_stats(st.cpu().numpy(), float(self.config.simulation.t_step_size))
 
     def close(self):
         pass

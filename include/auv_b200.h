@@ -190,6 +190,9 @@ typedef struct AuvStepOut {
 #define AUV_OBSERVE_RESET 1 /* observe only: what reset() returns (no reward/done)       */
 
 int auv_abi_version(void);
+/* sizeof of the ABI structs, in declaration order (0 AuvConfig, 1 AuvRayTable, 2 AuvPathBank,
+ * 3 AuvScenarioPool, 4 AuvBatch, 5 AuvStepOut) so a binding can verify its layout. */
+int auv_sizeof(int which);
 const char* auv_last_error(void);
 int auv_obs_dim(const AuvConfig* cfg);
 

@@ -46,10 +46,13 @@ def rollout_oracle(scn, config, actions, test_mode=True):
         min_dist=np.full((T, M), np.inf), alive=np.zeros((T, M), bool), s=np.full((T, M), np.nan),
         windows=[[None] * M for _ in range(T)], n_tests=np.zeros(M, np.int64), mov_pos=[[None] * M for _ in range(T)],
     )
+    out["slot_of"] = [
+        np.concatenate([np.nonzero(scn.mov_width[m] > 0)[0], scn.k_moving + np.nonzero(scn.st_radius[m] > 0)[0]])
+        for m in range(M)
+    ]
     for m in range(M):
         env = OracleEnv(scn.describe(m), oracle_cfg(config), test_mode=test_mode)
-        out["obs0"].append(env.observe() if False else None)
-        env2_obs0 = None
+        out["obs0"].append(env.reset())
         for t in range(T):
             obs, rew, done, info = env.step(actions[t, m])
             out["alive"][t, m] = True
@@ -66,6 +69,11 @@ def rollout_oracle(scn, config, actions, test_mode=True):
                 out["dists"][t, m] = env.vessel.dists
                 out["min_dist"][t, m] = env.vessel.dists.min()
             out["mov_pos"][t][m] = np.array([o.position for o in env.obstacles if not o.static])
+            if R and env.vessel.nearby:
+                slot = {id(o): j for j, o in enumerate(env.obstacles)}
+                out["windows"][t][m] = {slot[id(o)]: w for o, w in zip(env.vessel.nearby, env.vessel.windows)}
+            else:
+                out["windows"][t][m] = {}
             if done:
                 break
         out["n_tests"][m] = env.vessel.n_tests
@@ -136,6 +144,23 @@ def compare(ref, gpu, config, label=""):
     assert np.array_equal(gpu["collision"][decisive], ref["collision"][decisive]), (label, "collision")
     assert np.array_equal(gpu["reached"][alive], ref["reached"][alive]), (label, "reached_goal")
     assert np.array_equal(gpu["done"][decisive], ref["done"][decisive]), (label, "done")
+    # culling windows: bit-exact integers for every nearby obstacle (slots are packed in the
+    # same order on both sides when every slot is used)
+    if config.vessel.use_lidar and "windows" in gpu and len(gpu["windows"]):
+        T, M = alive.shape
+        nwin = 0
+        for t in range(T):
+            for m in range(M):
+                if not alive[t, m] or ref["windows"][t][m] is None:
+                    continue
+                gw = gpu["windows"][t, m]
+                for j, (a, b) in ref["windows"][t][m].items():
+                    js = ref["slot_of"][m][j] if "slot_of" in ref else j
+                    if a < -config.vessel.n_sensors:
+                        continue  # IndexError corner: defined as all rays
+                    assert (int(gw[js, 0]), int(gw[js, 1])) == (a, b), (label, "window", t, m, j, gw[js], (a, b))
+                    nwin += 1
+        rep["windows_checked"] = nwin
     # rewards
     rr, rg = ref["reward"][decisive], gpu["reward"][decisive]
     rerr = np.abs(rg - rr)

@@ -61,6 +61,7 @@ def main():
         a = rng.uniform([-1, -0.15], [1, 0.15], size=(T, 2))
         if case % 4 == 3:  # out-of-box actions exercise the clipping
             a = rng.uniform(-2, 2, size=(T, 2))
+        a = a.astype(np.float32).astype(np.float64)  # the C ABI takes float32 actions (gym Box dtype)
         dt = [1.0, 0.5, 0.1, 0.2][case % 4]
         inits.append(init)
         acts.append(a)

@@ -1,0 +1,343 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on
+identical injected scenarios and actions, and against golden vectors produced by the
+reference's own dynamics files.  Run on the B200 box:  pytest tests -m gpu"""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from gym_auv_b200 import Config, effective_reference_config, lidar_config, scenarios as S  # noqa: E402
+from tests._parity import compare, rollout_gpu, rollout_oracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def f32(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+def random_actions(T, M, seed):
+    return f32(np.random.RandomState(seed).uniform([-1, -0.15], [1, 0.15], size=(T, M, 2)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib_loaded(built_lib):
+    from gym_auv_b200 import _lib
+
+    _lib.load()
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+
+
+# ---------------------------------------------------------------------------------------
+# dynamics kernel against the REFERENCE'S OWN odesolver/constants output (pinned)
+# ---------------------------------------------------------------------------------------
+def test_vessel_step_matches_reference_goldens():
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    g = np.load(os.path.join(GOLD, "reference_dynamics.npz"))
+    worst = 0.0
+    for dt in np.unique(g["dts"]):
+        sel = np.nonzero(g["dts"] == dt)[0]
+        base = S.empty_scenario()
+        sets = []
+        for i in sel:
+            one = S.empty_scenario()
+            one.vessel_init = g["inits"][i][None, :]
+            sets.append(one)
+        scn = S.concat(sets)
+        cfg = Config()
+        cfg.simulation.t_step_size = float(dt)
+        env = AUVVecEnv(scn, len(sel), cfg, test_mode=True, auto_reset=False)
+        env.reset()
+        acts = torch.as_tensor(g["actions"][sel], dtype=torch.float32, device="cuda")  # [n, T, 2]
+        for t in range(acts.shape[1]):
+            env.vessel_step(acts[:, t].contiguous())
+            got = env.state.cpu().numpy().T
+            want = g["trajs"][sel, t + 1]
+            worst = max(worst, float(np.abs(got - want).max()))
+    assert worst <= 1e-11, worst
+
+
+def test_vessel_step_nan_action_is_zero_action():
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    scn = S.concat([S.empty_scenario(), S.empty_scenario()])
+    env = AUVVecEnv(scn, 2, Config(), test_mode=True, auto_reset=False)
+    env.reset()
+    a = torch.tensor([[float("nan"), 0.1], [0.0, 0.0]], device="cuda")
+    for _ in range(3):
+        env.vessel_step(a)
+    st = env.state.cpu().numpy()
+    assert np.array_equal(st[:, 0], st[:, 1])  # environment.py:314-315
+
+
+# ---------------------------------------------------------------------------------------
+# full step rollouts against the oracle
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt,seed", [(1.0, 3), (0.5, 4)])
+def test_moving_obstacles_rollout(dt, seed):
+    cfg = lidar_config()
+    cfg.simulation.t_step_size = dt
+    scn = S.moving_obstacles(8, 17, 11, seed=seed)
+    actions = random_actions(64, 8, 100 + seed)
+    ref = rollout_oracle(scn, cfg, actions)
+    gpu, _ = rollout_gpu(scn, cfg, actions)
+    rep = compare(ref, gpu, cfg, f"moving dt={dt}")
+    assert rep["env_steps"] >= 300
+    if ref["alive"].all():  # (the GPU env keeps stepping after done when auto_reset is off)
+        assert gpu["seg_tests"] == int(ref["n_tests"].sum())  # reference-semantics ray/segment tests
+    assert np.allclose(gpu["obs0"], np.array(ref["obs0"]), atol=2e-5)
+    # moving-obstacle positions are integrated in FP64 on both sides
+    for t in range(actions.shape[0]):
+        for m in range(8):
+            if ref["alive"][t, m]:
+                assert np.abs(gpu["mov_pos"][t, m] - ref["mov_pos"][t][m]).max() < 1e-9
+
+
+def test_moving_obstacles_close_quarters():
+    """Vessels started right next to obstacles so that collisions, inside-polygon and
+    sub-10 m ranges actually occur within the horizon."""
+    cfg = lidar_config()
+    scn = S.moving_obstacles(12, 17, 11, seed=21)
+    rng = np.random.RandomState(5)
+    for m in range(12):
+        if m % 2 == 0:  # next to a static circle
+            j = rng.randint(11)
+            ang = rng.uniform(-np.pi, np.pi)
+            r = scn.st_radius[m, j] + rng.uniform(1.5, 6.0)
+            scn.vessel_init[m, :2] = scn.st_pos[m, j] + r * np.array([np.cos(ang), np.sin(ang)])
+            scn.vessel_init[m, 2] = ang + np.pi + rng.uniform(-0.4, 0.4)
+        else:  # in the way of a moving vessel
+            j = rng.randint(17)
+            v = scn.vel_table[scn.mov_track[m, j, 0]]
+            scn.vessel_init[m, :2] = scn.mov_start[m, j] + v * rng.uniform(8, 20) + rng.uniform(-3, 3, size=2)
+            scn.vessel_init[m, 2] = rng.uniform(-np.pi, np.pi)
+    actions = random_actions(40, 12, 77)
+    actions[..., 0] = np.abs(actions[..., 0])
+    ref = rollout_oracle(scn, cfg, actions)
+    gpu, _ = rollout_gpu(scn, cfg, actions)
+    rep = compare(ref, gpu, cfg, "close quarters")
+    assert ref["collision"].any(), "fixture should produce at least one collision"
+    assert (ref["min_dist"][ref["alive"]] < 10).any()
+    assert rep["windows_checked"] > 100
+
+
+DETERMINISTIC = ["TestScenario1-v0", "TestScenario2-v0", "TestScenario3-v0", "TestScenario4-v0", "TestHeadOn-v0",
+                 "TestCrossing-v0", "TestCrossing1-v0", "EmptyScenario-v0", "DebugScenario-v0"]
+
+
+@pytest.mark.parametrize("name", DETERMINISTIC)
+def test_deterministic_scenarios(name):
+    scn = S.SCENARIOS[name]()
+    cfg = lidar_config()
+    if name in ("EmptyScenario-v0", "DebugScenario-v0"):  # registered with DEBUG_CONFIG
+        cfg.simulation.t_step_size = 0.5
+        cfg.episode.min_goal_distance = 0.1
+    T = 20 if name == "TestScenario2-v0" else 48
+    a = random_actions(T, 1, 9)
+    a[..., 0] = 0.9
+    a[..., 1] *= 0.3
+    a = f32(a)
+    ref = rollout_oracle(scn, cfg, a)
+    gpu, _ = rollout_gpu(scn, cfg, a)
+    compare(ref, gpu, cfg, name)
+    assert np.allclose(gpu["obs0"][0], ref["obs0"][0], atol=2e-5)
+
+
+def test_reference_hierarchical_collision_detector_case_on_gpu():
+    """tests/test_hierarchical_collision_detector.py of the reference, through the CUDA path."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    scn = S._single([[0, 100], [0, 100]], vessel_init=[5.0, -5.0, np.deg2rad(45)], static=[((0.0, -9.5), 1.5)])
+    env = AUVVecEnv(scn, 1, lidar_config(), test_mode=True, auto_reset=False, debug=True)
+    closeness = env.reset()[0, 6:].cpu().numpy()
+    assert len(closeness) == 180
+    assert not (0 < closeness[90] < 1)
+    assert 0 < closeness[-1] < 1
+    assert 0 < closeness[0] < 1
+    assert env.get_attr("windows")[0, 0].tolist() == [-9, 5]
+    assert np.nonzero(closeness)[0].tolist() == [0, 1, 2, 3, 172, 173, 174, 175, 176, 177, 178, 179]
+
+
+@pytest.mark.parametrize("heading_deg", [45, 90, 170, -135, -170, 0, 10, -10, 179.5, -179.5])
+def test_seam_windows_bit_exact(heading_deg):
+    from oracle import sim as OS
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    psi = np.deg2rad(heading_deg)
+    pos = np.array([5.0, -5.0])
+    sets, want = [], []
+    for off in (np.pi, np.pi - 0.2, np.pi + 0.2, 0.0, 1.0, -2.5):
+        c = pos + 6.5 * np.array([np.cos(psi + off), np.sin(psi + off)])
+        sets.append(S._single([[0, 100], [0, 100]], vessel_init=[pos[0], pos[1], psi], static=[(c, 1.5)]))
+        v = OS.OracleVessel(dict(OS.DEFAULT_CFG), [pos[0], pos[1], psi])
+        v.perceive([OS.OracleCircle(c, 1.5)])
+        want.append((v.windows[0], v.dists.copy()))
+    scn = S.concat(sets)
+    env = AUVVecEnv(scn, len(sets), lidar_config(), test_mode=True, auto_reset=False, debug=True)
+    env.reset()
+    win = env.get_attr("windows").cpu().numpy()
+    d = env.get_attr("lidar_dist").cpu().numpy()
+    for i, (w, dist) in enumerate(want):
+        assert tuple(win[i, 0]) == w
+        assert np.allclose(d[i], dist, rtol=1e-4, atol=1e-4)
+
+
+def test_exact_cull_mode_sees_obstacle_the_reference_misses():
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    psi = np.deg2rad(-135)
+    pos = np.array([5.0, -5.0])
+    c = pos - 6.5 * np.array([np.cos(psi), np.sin(psi)])
+    scn = S._single([[0, 100], [0, 100]], vessel_init=[pos[0], pos[1], psi], static=[(c, 1.5)])
+    ref_env = AUVVecEnv(scn, 1, lidar_config(), test_mode=True, auto_reset=False, debug=True)
+    ref_env.reset()
+    ex_env = AUVVecEnv(scn, 1, lidar_config(), test_mode=True, auto_reset=False, debug=True, cull_mode="exact")
+    ex_env.reset()
+    d_ref = ref_env.get_attr("lidar_dist")[0].cpu().numpy()
+    d_ex = ex_env.get_attr("lidar_dist")[0].cpu().numpy()
+    assert d_ref.min() == 150.0  # quirk #6: invisible to all rays
+    assert d_ex.min() < 6.0
+    assert np.all(d_ex <= d_ref)
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE config 2: no LiDAR, PathFollowRewarder
+# ---------------------------------------------------------------------------------------
+def test_path_follow_no_lidar_rollout():
+    cfg = Config()  # use_lidar False (reference default)
+    scn = S.path_follow_no_obstacles(16, seed=5, n_paths=4)
+    actions = random_actions(80, 16, 31)
+    actions[..., 0] = np.abs(actions[..., 0])
+    ref = rollout_oracle(scn, cfg, actions)
+    gpu, env = rollout_gpu(scn, cfg, actions)
+    assert env.obs_dim == 6
+    compare(ref, gpu, cfg, "pathfollow")
+
+
+def test_colav_rewarder_without_lidar():
+    cfg = Config()
+    scn = S.empty_scenario()  # ColavRewarder, no LiDAR: every ray keeps sensor_range
+    a = random_actions(30, 1, 2)
+    ref = rollout_oracle(scn, cfg, a)
+    gpu, _ = rollout_gpu(scn, cfg, a)
+    compare(ref, gpu, cfg, "colav-nolidar")
+
+
+def test_velocity_observation_channel_is_zero_and_shaped():
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config(sensor_use_velocity_observations=True)
+    scn = S.test_scenario3()
+    env = AUVVecEnv(scn, 1, cfg, test_mode=True, auto_reset=False)
+    obs = env.reset()
+    assert obs.shape == (1, 6 + 540)  # reference tests/test_config.py intent
+    assert (obs[0, 6:186] > 0).any() and (obs[0, 186:] == 0).all()  # sensor.py:159
+
+
+# ---------------------------------------------------------------------------------------
+# done / auto-reset semantics
+# ---------------------------------------------------------------------------------------
+def test_time_limit_done_and_auto_reset():
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    cfg.episode.max_timesteps = 6
+    scn = S.moving_obstacles(4, 3, 2, seed=8)
+    env = AUVVecEnv(scn, 4, cfg, test_mode=False, auto_reset=True, debug=True)
+    obs0 = env.reset().clone()
+    st0 = env.state.clone()
+    a = torch.zeros((4, 2), device="cuda")
+    a[:, 0] = 1.0
+    dones, last_obs = [], None
+    for t in range(6):
+        obs, rew, done, info = env.step(a)
+        dones.append(done.cpu().numpy().copy())
+    # done exactly when the pre-increment t_step reaches max_timesteps - 1 (environment.py:380)
+    assert [bool(d.all()) for d in dones] == [False, False, False, False, False, True]
+    assert not any(d.any() for d in dones[:5])
+    assert torch.equal(env.state, st0)  # env is back in its initial state...
+    assert torch.allclose(obs, obs0)  # ...and the returned obs is the reset obs
+    assert (env.get_attr("t_step") == 0).all() and (env.get_attr("episode") == 2).all()
+    term = info["terminal_observation"]
+    assert not torch.allclose(term, obs0)
+    stats = env.episode_stats(reduce=False)
+    assert stats["episodes"] == 4 and stats["timesteps"] == 6.0 and stats["collision"] == 0.0
+
+
+def test_test_mode_ignores_time_and_reward_limits():
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    cfg.episode.max_timesteps = 3
+    cfg.episode.min_cumulative_reward = -1.0
+    env = AUVVecEnv(S.empty_scenario(), 1, cfg, test_mode=True, auto_reset=False)
+    env.reset()
+    a = torch.zeros((1, 2), device="cuda")
+    for _ in range(6):
+        _, _, done, _ = env.step(a)
+        assert not bool(done.item())
+    env2 = AUVVecEnv(S.empty_scenario(), 1, cfg, test_mode=False, auto_reset=False)
+    env2.reset()
+    _, r, done, _ = env2.step(a)
+    assert bool(done.item()) and float(r.item()) < -1.0  # cumulative reward limit
+
+
+def test_step_host_equals_step():
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    scn = S.moving_obstacles(33, 4, 4, seed=12)  # odd batch size on purpose
+    e1 = AUVVecEnv(scn, 33, cfg, auto_reset=True)
+    e2 = AUVVecEnv(scn, 33, cfg, auto_reset=True)
+    e1.reset(), e2.reset()
+    acts = random_actions(10, 33, 3).astype(np.float32)
+    for t in range(10):
+        o1, r1, d1, _ = e1.step(torch.as_tensor(acts[t], device="cuda"))
+        o2, r2, d2 = e2.step_host(acts[t])
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(d1.cpu().numpy(), d2)
+    assert e2.h2d_bytes_per_step == 33 * 8 and e2.d2h_bytes_per_step == 33 * (186 * 4 + 5)
+
+
+def test_bad_shapes_raise():
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    env = AUVVecEnv(S.empty_scenario(), 1, lidar_config(), auto_reset=False)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((2, 2), device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------
+# gym.Env facade: the reference's tests/test_end_to_end.py over every registered id
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scenario_name", sorted(S.SCENARIOS))
+def test_single_step_end_to_end(scenario_name):
+    import gym_auv_b200
+
+    cfg = lidar_config() if scenario_name != "PathFollowNoObstacles-v0" else None
+    env = gym_auv_b200.make(scenario_name, cfg)
+    first_obs = env.reset()
+    obs, reward, done, info = env.step(np.array([0.5, 0.6]))
+    space = env.observation_space
+    assert isinstance(obs, np.ndarray) and obs.shape == space.shape
+    assert np.all(space.low <= obs) and np.all(space.high >= obs)
+    assert isinstance(reward, float) and isinstance(done, bool) and isinstance(info, dict)
+    assert set(info) == {"collision", "reached_goal", "goal_distance", "progress"}
+    assert np.any(first_obs != obs)
+    assert env.t_step == 1 and env.episode == 2  # constructor reset + explicit reset
+    assert env.rewarder.params["lambda"] == 0.5
+
+
+def test_dict_observation_facade():
+    import gym_auv_b200
+
+    cfg = lidar_config(use_dict_observation=True, sensor_use_velocity_observations=True)
+    env = gym_auv_b200.make("TestScenario3-v0", cfg)
+    obs = env.reset()
+    assert set(obs) == {"proprioceptive", "lidar"}
+    assert obs["proprioceptive"].shape == (6,) and obs["lidar"].shape == (3, 180)
+    assert env.observation_space.contains({k: v.astype(np.float32) for k, v in obs.items()})

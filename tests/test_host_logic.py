@@ -1,0 +1,201 @@
+"""Host-side logic that needs no GPU: config tree, scenario plug-ins, path bank tables,
+ABI library symbols and struct layout."""
+import ctypes
+import dataclasses
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gym_auv_b200 import Config, effective_reference_config, lidar_config, scenarios as S
+from gym_auv_b200.pathbank import PATH_BLOCK, build_path
+from oracle import geos_lite as G
+from oracle import sim as OS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- config (reference tests/test_config.py + quirk #4) --------------------------------
+def test_config_defaults_match_reference_declared_values():
+    c = Config()
+    assert c.simulation.t_step_size == 1.0 and c.episode.min_goal_distance == 5.0
+    assert c.episode.max_timesteps == 10000 and c.episode.min_cumulative_reward == -2000.0
+    assert c.vessel.use_lidar is False and c.vessel.n_sensors == 180 and c.vessel.sensor_range == 150.0
+    assert c.vessel.vessel_width == 1.255 and c.vessel.sensor_interval_load_obstacles == 25
+    assert [f.name for f in c] == ["episode", "simulation", "vessel", "rendering"]
+
+
+def test_configs_do_not_share_state_unlike_reference():
+    a, b = Config(), Config()
+    a.simulation.t_step_size = 0.5
+    assert b.simulation.t_step_size == 1.0
+    e = effective_reference_config()
+    assert e.simulation.t_step_size == 0.5 and e.episode.min_goal_distance == 0.1
+
+
+@pytest.mark.parametrize("use_lidar_velocity", [True, False])
+def test_lidar_observation_size(use_lidar_velocity):
+    c = lidar_config(sensor_use_velocity_observations=use_lidar_velocity)
+    assert c.vessel.lidar_shape == (3 if use_lidar_velocity else 1, 180)
+    assert c.vessel.dense_observation_size + c.vessel.n_lidar_observations == 6 + (540 if use_lidar_velocity else 180)
+
+
+# ---- path bank --------------------------------------------------------------------------
+def test_path_table_matches_oracle_path():
+    wp = S.random_curve_waypoints(np.random.RandomState(4), 5, 800)
+    tab = build_path(wp)
+    ora = OS.OraclePath(wp)
+    assert tab.length == ora.length
+    assert np.array_equal(tab.poly, ora.points)
+    assert len(tab.poly) == int(10 * tab.length)
+    s = np.linspace(-1, tab.length + 1, 57)
+    assert np.allclose(tab(s), ora(s), atol=0, rtol=0)
+    # coefficient layout [interval][axis][power] reproduces scipy's evaluation
+    j = 417
+    t = 0.37 * (tab.knots[j + 1] - tab.knots[j])
+    val = ((tab.coef[j, :, 0] * t + tab.coef[j, :, 1]) * t + tab.coef[j, :, 2]) * t + tab.coef[j, :, 3]
+    assert np.allclose(val, ora(tab.knots[j] + t), atol=1e-10)
+    assert np.allclose(tab.end, ora.end)
+
+
+def test_path_blocks_bound_their_segments():
+    wp = S.random_curve_waypoints(np.random.RandomState(5), 4, 800)
+    tab = build_path(wp)
+    rel = tab.poly - tab.origin
+    nseg = len(tab.poly) - 1
+    assert len(tab.blk_dev) == (nseg + PATH_BLOCK - 1) // PATH_BLOCK
+    for b in (0, 7, len(tab.blk_dev) - 1):
+        lo, hi = b * PATH_BLOCK, min((b + 1) * PATH_BLOCK, nseg)
+        a, c = tab.blk_chord[b, :2].astype(float), tab.blk_chord[b, 2:].astype(float)
+        for k in range(lo, hi + 1):
+            d = G.point_segment_distance(rel[k, 0], rel[k, 1], a[0], a[1], c[0], c[1])
+            assert d <= tab.blk_dev[b]
+
+
+def test_random_curve_shape():
+    for nwp in (2, 3, 4, 5):
+        wp = S.random_curve_waypoints(np.random.RandomState(nwp), nwp, 800)
+        assert wp.shape == (2, 2 + 3 * (nwp // 2) - (nwp // 2 - 1) * 1) or wp.shape[0] == 2
+        assert np.allclose(wp[:, 0], -wp[:, -1])  # end = -start
+        assert np.hypot(*wp[:, 0]) == pytest.approx(400.0)
+
+
+# ---- scenario plug-ins ---------------------------------------------------------------------
+def test_moving_obstacles_distribution_and_constraints():
+    scn = S.moving_obstacles(48, 17, 11, seed=2, n_paths=6)
+    assert scn.k_moving == 17 and scn.k_static == 11 and scn.n_scenarios == 48
+    assert scn.mov_width.min() >= 1 and scn.st_radius.min() >= 1
+    speed = np.linalg.norm(scn.vel_table, axis=1)
+    assert speed.min() >= 1 and speed.max() <= 3
+    for m in range(48):
+        tab = scn.bank.tables[scn.path_id[m]]
+        vp = scn.vessel_init[m, :2]
+        assert np.abs(vp - tab(0.0)).max() <= 25.0
+        # generate_obstacle's acceptance test (helpers.py:27-33)
+        d = np.linalg.norm(scn.st_pos[m] - vp, axis=1) - 1.255 - scn.st_radius[m]
+        g = np.linalg.norm(scn.st_pos[m] - tab(tab.length), axis=1) - scn.st_radius[m]
+        assert d.min() > 0 and g.min() > 0
+        d = np.linalg.norm(scn.mov_start[m] - vp, axis=1) - 1.255 - scn.mov_width[m]
+        assert d.min() > 0
+
+
+def test_initial_obstacle_state_equals_oracle_reset():
+    scn = S.moving_obstacles(3, 5, 2, seed=9)
+    for dt in (1.0, 0.5):
+        pos, disp, counter = scn.initial_obstacle_state(dt)
+        for m in range(3):
+            env = OS.OracleEnv(scn.describe(m), dict(t_step_size=dt, use_lidar=False))
+            mov = [o for o in env.obstacles if not o.static]
+            assert np.allclose([o.position for o in mov], pos[m], atol=1e-12)
+            assert np.allclose([o.counter for o in mov], counter[m], atol=1e-12)
+            assert counter[m, 0] == pytest.approx(0.1 + dt)
+
+
+def test_debug_scenario_velocity_tables_and_no_post_update():
+    scn = S.debug_scenario(seed=1)
+    assert scn.k_moving == 10 and not scn.post_generate_update
+    assert (scn.mov_track[0, :, 1] == 9999).all() and (scn.mov_track[0, :, 2] == 1).all()
+    pos, _, counter = scn.initial_obstacle_state(0.5)
+    assert np.allclose(counter, 0.1)
+
+
+def test_scenario_registry_matches_reference_ids():
+    ids = {"TestScenario1-v0", "TestScenario2-v0", "TestScenario3-v0", "TestScenario4-v0", "TestHeadOn-v0",
+           "TestCrossing-v0", "TestCrossing1-v0", "DebugScenario-v0", "EmptyScenario-v0",
+           "MovingObstaclesNoRules-v0", "PathFollowNoObstacles-v0"}
+    assert set(S.SCENARIOS) == ids  # gym_auv/__init__.py:43-121 (uncommented entries)
+    assert S.test_scenario1().k_static == 20 and S.test_scenario3().k_static == 21 and S.test_scenario4().k_static == 15
+
+
+def test_negative_radius_raises_value_error():
+    with pytest.raises(ValueError):
+        S._single([[0, 10], [0, 10]], static=[((1.0, 1.0), -2.0)])
+
+
+def test_concat_pads_slots():
+    a, b = S.test_scenario3(), S.test_crossing()
+    b.post_generate_update = a.post_generate_update
+    c = S.concat([a, b])
+    assert c.n_scenarios == 2 and c.k_static == 21 and c.k_moving == 1
+    assert (c.st_radius[1] == 0).all() and c.mov_width[0, 0] == 0 and c.mov_width[1, 0] == 30
+
+
+# ---- ABI --------------------------------------------------------------------------------
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "auv_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(auv_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    names = _declared_symbols()
+    assert {"auv_step", "auv_step_host", "auv_observe", "auv_vessel_step", "auv_obstacle_update", "auv_reset",
+            "auv_abi_version", "auv_last_error", "auv_obs_dim", "auv_sizeof", "auv_fma_probe"} <= set(names)
+    for n in names:
+        assert hasattr(lib, n), f"libauv_b200.so does not export {n}"
+
+
+def test_binding_layout_and_version(built_lib):
+    from gym_auv_b200 import _lib
+
+    lib = _lib.load()  # raises on ABI/layout mismatch
+    assert lib.auv_abi_version() == _lib.ABI_VERSION
+    assert set(_lib.EXPORTS) == set(_declared_symbols())
+    cfg = _lib.AuvConfig(n_sensors=180, use_lidar=1)
+    assert lib.auv_obs_dim(ctypes.byref(cfg)) == 186
+    cfg.sensor_use_velocity_observations = 1
+    assert lib.auv_obs_dim(ctypes.byref(cfg)) == 546
+    cfg.use_lidar = 0
+    assert lib.auv_obs_dim(ctypes.byref(cfg)) == 6
+
+
+def test_bad_arguments_return_error_codes_not_crashes(built_lib):
+    from gym_auv_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.auv_vessel_step(None, None, None, None) == -1
+    assert b"NULL" in lib.auv_last_error()
+    cfg = _lib.AuvConfig(t_step_size=0.0, sensor_interval_load_obstacles=25)
+    batch = _lib.AuvBatch(n_envs=4)
+    assert lib.auv_vessel_step(ctypes.byref(cfg), ctypes.byref(batch), ctypes.c_void_p(8), None) == -1
+    assert b"t_step_size" in lib.auv_last_error()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "gym_auv_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_vec_env_refuses_to_run_without_cuda():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        AUVVecEnv(S.empty_scenario(), 1, Config(), device="cuda:0")
