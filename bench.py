@@ -251,24 +251,27 @@ def run_ours(args):
         sampler.start()
     stream = torch.cuda.current_stream(device)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     cfgp, rays, paths, pool, batch = env._refs()
     import ctypes as C
+    timer = env.lib.auv_timer_create(K)
+    assert timer, "auv_timer_create failed"
     barrier()
     ev0.record(stream)
     for i in range(K):
         a = actions[(Wm + i) % n_act]
-        s = C.c_void_p(stream.cuda_stream)
-        _lib.check(env.lib.auv_obstacle_update(cfgp, pool, batch, s), "update")
-        _lib.check(env.lib.auv_vessel_step(cfgp, batch, C.c_void_p(a.data_ptr()), s), "vessel")
-        kev[i][0].record(stream)
-        _lib.check(env.lib.auv_observe(cfgp, rays, paths, pool, batch, C.byref(env.out), 0, s), "observe")
-        kev[i][1].record(stream)
+        _lib.check(env.lib.auv_step_timed(cfgp, rays, paths, pool, batch, C.c_void_p(a.data_ptr()), C.byref(env.out),
+                                          C.c_void_p(stream.cuda_stream), timer, i), "auv_step_timed")
     ev1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
-    obs_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    kms = np.zeros((K, 3), dtype=np.float32)
+    for i in range(K):
+        _lib.check(env.lib.auv_timer_read(timer, i, kms[i].ctypes.data_as(C.POINTER(C.c_float))), "auv_timer_read")
+    env.lib.auv_timer_destroy(timer)
+    kernel_ms = {"k_obstacle_update": float(kms[:, 0].mean()), "k_vessel_nav": float(kms[:, 1].mean()),
+                 "k_observe": float(kms[:, 2].mean())}
+    obs_ms = kernel_ms["k_observe"]
     t_local = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
@@ -351,7 +354,7 @@ def run_ours(args):
         "roofline": {
             "kernel": "k_observe", "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops,
             "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops if fp32_peak_tflops else None,
-            "traffic": None, "ms_per_launch": obs_ms,
+            "traffic": None, "ms_per_launch": obs_ms, "kernel_ms": kernel_ms,
             "note": "algorithmic FLOPs = 16 x reference-semantics ray/segment tests + 60 x rays (SURVEY 8d); "
                     "peak = FP32 FMA probe measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
             "seg_tests_per_env_step": seg_tests_per_step / N,

@@ -7,8 +7,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libauv_b200.so")
-ABI_VERSION = 3
+LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
+ABI_VERSION = 4
+NAV_W = 12
 N_STATS = 16
 STAT_NAMES = [
     "episodes",
@@ -71,6 +72,9 @@ class AuvPathBank(C.Structure):
         ("blk_off", _vp),
         ("blk_chord", _vp),
         ("blk_dev", _vp),
+        ("sb_off", _vp),
+        ("sb_chord", _vp),
+        ("sb_dev", _vp),
         ("origin", _vp),
         ("knots", _vp),
         ("coef", _vp),
@@ -117,6 +121,7 @@ class AuvBatch(C.Structure):
         ("mov_pos", _vp),
         ("mov_disp", _vp),
         ("mov_counter", _vp),
+        ("nav", _vp),
     ]
 
 
@@ -131,7 +136,6 @@ class AuvStepOut(C.Structure):
         ("progress", _vp),
         ("lidar_dist", _vp),
         ("windows", _vp),
-        ("nav", _vp),
         ("terminal_obs", _vp),
         ("stats", _vp),
         ("seg_tests", _vp),
@@ -145,11 +149,16 @@ EXPORTS = [
     "auv_obs_dim",
     "auv_obstacle_update",
     "auv_vessel_step",
+    "auv_navigate",
     "auv_observe",
     "auv_reset",
     "auv_step",
     "auv_step_host",
     "auv_fma_probe",
+    "auv_timer_create",
+    "auv_timer_destroy",
+    "auv_step_timed",
+    "auv_timer_read",
 ]
 
 _lib = None
@@ -182,6 +191,7 @@ def load():
     lib.auv_observe.argtypes = [
         P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), P(AuvStepOut), C.c_int, _vp,
     ]
+    lib.auv_navigate.argtypes = [P(AuvConfig), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp]
     lib.auv_reset.argtypes = [P(AuvConfig), P(AuvScenarioPool), P(AuvBatch), _vp, _vp]
     lib.auv_step.argtypes = [
         P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, P(AuvStepOut), _vp,
@@ -190,6 +200,15 @@ def load():
         P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, _vp, P(AuvStepOut),
         _vp, _vp, _vp, _vp,
     ]
+    lib.auv_timer_create.argtypes = [C.c_int]
+    lib.auv_timer_create.restype = _vp
+    lib.auv_timer_destroy.argtypes = [_vp]
+    lib.auv_timer_destroy.restype = None
+    lib.auv_step_timed.argtypes = [
+        P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, P(AuvStepOut), _vp,
+        _vp, C.c_int,
+    ]
+    lib.auv_timer_read.argtypes = [_vp, C.c_int, P(C.c_float)]
     lib.auv_fma_probe.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, P(C.c_double)]
     ver = lib.auv_abi_version()
     if ver != ABI_VERSION:

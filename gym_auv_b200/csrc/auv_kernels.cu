@@ -90,24 +90,12 @@ __device__ __forceinline__ S6 state_dot(const S6& s, double tau_u, double tau_r)
   out.v = y.v + (EXPR(v));             \
   out.r = y.r + (EXPR(r));
 
-__global__ void __launch_bounds__(128) k_vessel_step(AuvConfig cfg, AuvBatch batch,
-                                                      const float* __restrict__ actions) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = batch.n_envs;
-  if (e >= n) return;
-  float2 a = reinterpret_cast<const float2*>(actions)[e];
+// one Fehlberg step for one env (vessel.py:226-247): returns the 5th-order solution q
+__device__ __forceinline__ S6 vessel_rk_step(const AuvConfig& cfg, const S6& y, float2 a) {
   if (isnan(a.x) || isnan(a.y)) a = make_float2(0.f, 0.f);  // environment.py:314-315
   const double tau_u = fmin(fmax((double)a.x, 0.0), 1.0) * cfg.thrust_max_auv;
   const double tau_r = fmin(fmax((double)a.y, -1.0), 1.0) * cfg.moment_max_auv;
   const double h = cfg.t_step_size;
-  double* st = batch.state;
-  S6 y;
-  y.x = st[e];
-  y.y = st[n + e];
-  y.psi = st[2 * n + e];
-  y.u = st[3 * n + e];
-  y.v = st[4 * n + e];
-  y.r = st[5 * n + e];
   S6 t, k1, k2, k3, k4, k5, k6, q;
   k1 = state_dot(y, tau_u, tau_r);
 #define E2(c) h * k1.c / 4.0
@@ -132,19 +120,43 @@ __global__ void __launch_bounds__(128) k_vessel_step(AuvConfig cfg, AuvBatch bat
      2.0 * k6.c / 55.0)
   S6_AXPY(q, y, EQ)
   q.psi = princip(q.psi);
+  return q;
+}
+
+__device__ __forceinline__ S6 load_state(const double* st, int n, int e) {
+  S6 y;
+  y.x = st[e];
+  y.y = st[n + e];
+  y.psi = st[2 * n + e];
+  y.u = st[3 * n + e];
+  y.v = st[4 * n + e];
+  y.r = st[5 * n + e];
+  return y;
+}
+__device__ __forceinline__ void store_state(double* st, int n, int e, const S6& q) {
   st[e] = q.x;
   st[n + e] = q.y;
   st[2 * n + e] = q.psi;
   st[3 * n + e] = q.u;
   st[4 * n + e] = q.v;
   st[5 * n + e] = q.r;
+}
+
+// Vessel.step only (staged entry point auv_vessel_step)
+__global__ void __launch_bounds__(128) k_vessel_step(AuvConfig cfg, AuvBatch batch,
+                                                      const float* __restrict__ actions) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = batch.n_envs;
+  if (e >= n) return;
+  const S6 q = vessel_rk_step(cfg, load_state(batch.state, n, e), reinterpret_cast<const float2*>(actions)[e]);
+  store_state(batch.state, n, e, q);
   batch.step_counter[e] += 1;
 }
 
 // ------------------------------------------------------------------------------------
 // reset of one env, executed by one warp    environment.py:202-212, vessel.py:189-224
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void reset_env_warp(const AuvScenarioPool& pool, AuvBatch& batch, int e,
+__device__ __forceinline__ void reset_env_warp(const AuvScenarioPool& pool, const AuvBatch& batch, int e,
                                                int scn, int lane) {
   const int n = batch.n_envs;
   const int km = pool.k_moving;
@@ -184,13 +196,23 @@ __global__ void __launch_bounds__(256) k_reset(AuvScenarioPool pool, AuvBatch ba
 }
 
 // ------------------------------------------------------------------------------------
-// Path projection + navigation features (warp-cooperative)
+// Path projection + navigation features, ONE THREAD per env (FP64)
 //   path.py:61-93 (PCHIP eval, LineString.project), vessel.py:461-541 (navigate)
+// The result is the env's navigation record nav[e][AUV_NAV_W] in HBM; the warp-per-env
+// LiDAR kernel reads it back (one 96 B coalesced load).
 // ------------------------------------------------------------------------------------
-struct Nav {
-  double s, chi, y_e, s_la, la_err, head_err, goal_dist, progress;
-  bool reached;
-};
+#define NAV_S 0
+#define NAV_CHI 1
+#define NAV_YE 2
+#define NAV_SLA 3
+#define NAV_LA_ERR 4
+#define NAV_HEAD_ERR 5
+#define NAV_GOAL 6
+#define NAV_PROGRESS 7
+#define NAV_COSPSI 8
+#define NAV_SINPSI 9
+#define NAV_REACHED 10
+#define NAV_COS_HEAD_ERR 11
 
 // scipy PPoly evaluation (extrapolate=True): interval j with x[j] <= s < x[j+1], clamped.
 __device__ __forceinline__ void pchip_eval(const AuvPathBank& pb, int pid, double s, double& px,
@@ -210,70 +232,87 @@ __device__ __forceinline__ void pchip_eval(const AuvPathBank& pb, int pid, doubl
   dy = (3.0 * c[4] * t + 2.0 * c[5]) * t + c[6];
 }
 
-// GEOS LengthIndexOfPoint::indexOf restated as an exact two-level search: a block of 32
-// consecutive 0.1 m segments lies inside the capsule (chord, dev); blocks whose capsule
-// lower bound exceeds the best capsule upper bound cannot hold the minimum.  Candidate
-// blocks are refined in FP64 in path order with a strict '<' so the FIRST minimum wins.
-__device__ __forceinline__ double project_warp(const AuvPathBank& pb, int pid, double px, double py,
-                                               int lane) {
+// exact squared distance from P to segment AB (GEOS Distance::pointToSegment, squared;
+// the r<=0 / r>=1 tests are done on the numerator, no division)
+__device__ __forceinline__ double seg_d2(double px, double py, double2 A, double2 B) {
+  const double ex = B.x - A.x, ey = B.y - A.y;
+  const double wx = px - A.x, wy = py - A.y;
+  const double len2 = ex * ex + ey * ey;
+  const double num = wx * ex + wy * ey;
+  if (len2 == 0.0 || num <= 0.0) return wx * wx + wy * wy;
+  if (num >= len2) {
+    const double zx = px - B.x, zy = py - B.y;
+    return zx * zx + zy * zy;
+  }
+  const double cr = wx * ey - wy * ex;
+  return cr * cr / len2;
+}
+
+// GEOS LengthIndexOfPoint::indexOf (LineString.project) restated as an exact three-level
+// search.  Level 2 = superblocks of 32 blocks, level 1 = blocks of 32 segments; each node is
+// a capsule (chord, max deviation) that contains its part of the polyline, so
+//   dist(P, node) in [dc - dev, dc + dev],  dc = dist(P, chord)   (FP32, padded).
+// Pass A finds an upper bound over superblocks, pass B tightens it over the blocks of the
+// surviving superblocks, pass C refines in FP64 every block whose lower bound does not
+// exceed it.  The arg-min is lexicographic in (distance, segment index), which is GEOS's
+// "first minimum wins" independent of visiting order.
+__device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid, double px, double py) {
   const int v0 = pb.poly_off[pid];
   const int nseg = pb.poly_off[pid + 1] - v0 - 1;
   const int b0 = pb.blk_off[pid];
   const int nblk = pb.blk_off[pid + 1] - b0;
+  const int s0 = pb.sb_off[pid];
+  const int nsb = pb.sb_off[pid + 1] - s0;
   const double ox = pb.origin[2 * pid], oy = pb.origin[2 * pid + 1];
   const float qx = (float)(px - ox), qy = (float)(py - oy);
   const float pad = 1e-6f * (fabsf(qx) + fabsf(qy)) + 1e-6f;
   const float4* chord = reinterpret_cast<const float4*>(pb.blk_chord) + b0;
   const float* dev = pb.blk_dev + b0;
+  const float4* sbc = reinterpret_cast<const float4*>(pb.sb_chord) + s0;
+  const float* sbd = pb.sb_dev + s0;
+  const float up = 1.f + 4e-6f, dn = 1.f - 4e-6f;
   float ub = INFINITY;
-  for (int b = lane; b < nblk; b += 32) {
-    const float4 ch = chord[b];
-    const float dc = pt_seg_dist_f(qx, qy, ch.x, ch.y, ch.z, ch.w);
-    ub = fminf(ub, dc * (1.f + 4e-6f) + dev[b] + pad);
+  for (int sb = 0; sb < nsb; ++sb) {
+    const float4 ch = sbc[sb];
+    ub = fminf(ub, pt_seg_dist_f(qx, qy, ch.x, ch.y, ch.z, ch.w) * up + sbd[sb] + pad);
   }
-  ub = warp_min(ub);
+  // pass B: tighten over blocks of surviving superblocks; remember which survive
+  unsigned long long live = 0ull;  // up to 64 superblocks tracked exactly, the rest are always visited
+  for (int sb = 0; sb < nsb; ++sb) {
+    const float4 ch = sbc[sb];
+    const float lb = pt_seg_dist_f(qx, qy, ch.x, ch.y, ch.z, ch.w) * dn - sbd[sb] - pad;
+    if (lb > ub) continue;
+    if (sb < 64) live |= 1ull << sb;
+    const int be = min(nblk, (sb + 1) * 32);
+    for (int b = sb * 32; b < be; ++b) {
+      const float4 c4 = chord[b];
+      ub = fminf(ub, pt_seg_dist_f(qx, qy, c4.x, c4.y, c4.z, c4.w) * up + dev[b] + pad);
+    }
+  }
+  // pass C: exact refine
+  const double2* poly = reinterpret_cast<const double2*>(pb.poly_xy) + v0;
   double best_d2 = INFINITY;
   int best_seg = 0;
-  const double2* poly = reinterpret_cast<const double2*>(pb.poly_xy) + v0;
-  for (int base = 0; base < nblk; base += 32) {
-    const int b = base + lane;
-    bool cand = false;
-    if (b < nblk) {
-      const float4 ch = chord[b];
-      const float dc = pt_seg_dist_f(qx, qy, ch.x, ch.y, ch.z, ch.w);
-      cand = dc * (1.f - 4e-6f) - dev[b] - pad <= ub;
-    }
-    unsigned m = __ballot_sync(AUV_FULL, cand);
-    while (m) {
-      const int bb = base + __ffs(m) - 1;
-      m &= m - 1;
-      const int seg = bb * AUV_PATH_BLOCK + lane;
-      double d2 = INFINITY;
-      if (seg < nseg) {
-        const double2 A = poly[seg], B = poly[seg + 1];
-        const double ex = B.x - A.x, ey = B.y - A.y;
-        const double wx = px - A.x, wy = py - A.y;
-        const double len2 = ex * ex + ey * ey;
-        const double num = wx * ex + wy * ey;
-        if (len2 == 0.0 || num <= 0.0) {
-          d2 = wx * wx + wy * wy;
-        } else if (num >= len2) {
-          const double zx = px - B.x, zy = py - B.y;
-          d2 = zx * zx + zy * zy;
-        } else {
-          const double cr = wx * ey - wy * ex;
-          d2 = cr * cr / len2;
+  for (int sb = 0; sb < nsb; ++sb) {
+    if (sb < 64 && !((live >> sb) & 1ull)) continue;
+    const int be = min(nblk, (sb + 1) * 32);
+    for (int b = sb * 32; b < be; ++b) {
+      const float4 c4 = chord[b];
+      if (pt_seg_dist_f(qx, qy, c4.x, c4.y, c4.z, c4.w) * dn - dev[b] - pad > ub) continue;
+      const int se = min(nseg, (b + 1) * AUV_PATH_BLOCK);
+      double2 A = poly[b * AUV_PATH_BLOCK];
+      for (int k = b * AUV_PATH_BLOCK; k < se; ++k) {
+        const double2 B = poly[k + 1];
+        const double d2 = seg_d2(px, py, A, B);
+        if (d2 < best_d2) {  // segments are visited in increasing k: strict '<' keeps the first
+          best_d2 = d2;
+          best_seg = k;
         }
-      }
-      int idx = seg;
-      warp_argmin(d2, idx);
-      if (d2 < best_d2) {
-        best_d2 = d2;
-        best_seg = idx;
+        A = B;
       }
     }
   }
-  // segmentNearestMeasure of the winning segment (uniform across the warp)
+  // segmentNearestMeasure of the winning segment
   const double2 A = poly[best_seg], B = poly[best_seg + 1];
   const double start = pb.poly_cum[v0 + best_seg];
   const double ex = B.x - A.x, ey = B.y - A.y;
@@ -286,30 +325,62 @@ __device__ __forceinline__ double project_warp(const AuvPathBank& pb, int pid, d
   return start + seglen;
 }
 
-__device__ __forceinline__ Nav navigate_warp(const AuvConfig& cfg, const AuvPathBank& pb, int pid,
-                                             double px, double py, double psi, int lane) {
-  Nav nv;
-  nv.s = project_warp(pb, pid, px, py, lane);
+// Vessel.navigate (vessel.py:461-541) for env e; writes nav[e][:] and max_progress[e].
+__device__ __forceinline__ void navigate_thread(const AuvConfig& cfg, const AuvPathBank& pb,
+                                                const AuvBatch& batch, int pid, int e, double px,
+                                                double py, double psi) {
+  const double s = project_thread(pb, pid, px, py);
   const double L = pb.length[pid];
-  nv.s_la = fmin(L, nv.s + cfg.look_ahead_distance);
-  // lanes 0/1 evaluate the spline at s / s_la in parallel, then broadcast
-  double ex = 0, ey = 0, dx = 0, dy = 0;
-  if (lane < 2) pchip_eval(pb, pid, lane == 0 ? nv.s : nv.s_la, ex, ey, dx, dy);
-  const double p_x = __shfl_sync(AUV_FULL, ex, 0), p_y = __shfl_sync(AUV_FULL, ey, 0);
-  const double d_x = __shfl_sync(AUV_FULL, dx, 0), d_y = __shfl_sync(AUV_FULL, dy, 0);
-  const double l_x = __shfl_sync(AUV_FULL, ex, 1), l_y = __shfl_sync(AUV_FULL, ey, 1);
-  const double ldx = __shfl_sync(AUV_FULL, dx, 1), ldy = __shfl_sync(AUV_FULL, dy, 1);
-  nv.chi = atan2(d_y, d_x);
+  const double s_la = fmin(L, s + cfg.look_ahead_distance);
+  double p_x, p_y, d_x, d_y, l_x, l_y, ldx, ldy;
+  pchip_eval(pb, pid, s, p_x, p_y, d_x, d_y);
+  pchip_eval(pb, pid, s_la, l_x, l_y, ldx, ldy);
+  const double chi = atan2(d_y, d_x);
   double sc, cc;
-  sincos(nv.chi, &sc, &cc);
-  nv.y_e = -sc * (p_x - px) + cc * (p_y - py);
-  nv.la_err = princip(atan2(ldy, ldx) - psi);
-  nv.head_err = princip(atan2(l_y - py, l_x - px) - psi);
-  nv.progress = nv.s / L;
+  sincos(chi, &sc, &cc);
+  const double y_e = -sc * (p_x - px) + cc * (p_y - py);
+  const double la_err = princip(atan2(ldy, ldx) - psi);
+  const double head_err = princip(atan2(l_y - py, l_x - px) - psi);
+  const double progress = s / L;
   const double gx = pb.end_xy[2 * pid] - px, gy = pb.end_xy[2 * pid + 1] - py;
-  nv.goal_dist = sqrt(gx * gx + gy * gy);
-  nv.reached = (nv.goal_dist <= cfg.min_goal_distance) || (nv.progress >= cfg.min_path_progress);
-  return nv;
+  const double goal = sqrt(gx * gx + gy * gy);
+  const bool reached = (goal <= cfg.min_goal_distance) || (progress >= cfg.min_path_progress);
+  double sp, cp;
+  sincos(psi, &sp, &cp);
+  double* o = batch.nav + (long long)e * AUV_NAV_W;
+  o[NAV_S] = s;
+  o[NAV_CHI] = chi;
+  o[NAV_YE] = y_e;
+  o[NAV_SLA] = s_la;
+  o[NAV_LA_ERR] = la_err;
+  o[NAV_HEAD_ERR] = head_err;
+  o[NAV_GOAL] = goal;
+  o[NAV_PROGRESS] = progress;
+  o[NAV_COSPSI] = cp;
+  o[NAV_SINPSI] = sp;
+  o[NAV_REACHED] = reached ? 1.0 : 0.0;
+  o[NAV_COS_HEAD_ERR] = cos(head_err);
+  batch.max_progress[e] = fmax(progress, batch.max_progress[e]);  // vessel.py:507
+}
+
+// Vessel.step fused with Vessel.navigate (DYN) or navigate only (reset / staged observe):
+// the state never leaves registers between the RK step and the projection.
+template <bool DYN>
+__global__ void __launch_bounds__(128) k_vessel_nav(const __grid_constant__ AuvConfig cfg,
+                                                     const __grid_constant__ AuvPathBank paths,
+                                                     const __grid_constant__ AuvScenarioPool pool,
+                                                     const __grid_constant__ AuvBatch batch,
+                                                     const float* __restrict__ actions) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = batch.n_envs;
+  if (e >= n) return;
+  S6 y = load_state(batch.state, n, e);
+  if (DYN) {
+    y = vessel_rk_step(cfg, y, reinterpret_cast<const float2*>(actions)[e]);
+    store_state(batch.state, n, e, y);
+    batch.step_counter[e] += 1;
+  }
+  navigate_thread(cfg, paths, batch, pool.path_id[batch.scn_id[e]], e, y.x, y.y, y.psi);
 }
 
 // ------------------------------------------------------------------------------------
@@ -336,17 +407,11 @@ struct __align__(16) WarpScratch {
 __constant__ double c_pent[5][2] = {{-7.0 / 9.0, -0.5}, {-7.0 / 9.0, 0.5}, {2.0 / 9.0, 0.5},
                                     {11.0 / 9.0, 0.0},  {2.0 / 9.0, -0.5}};
 
-// culling window (sensor.py:22-97), FP64:  a = floor((pi+beta-delta)/dth) - 1,
-// b = ceil((pi+beta+delta)/dth) mod R (Python modulo); candidate(i) <=> a<=i<b or a<=i-R<b
-__device__ __forceinline__ void cull_window(double cx, double cy, double rho, double psi, int R,
-                                            int mode, int& a, int& b, bool& allrays) {
-  const double dth = 2.0 * AUV_PI / (double)R;
-  const double dist = fmax(1e-8, sqrt(cx * cx + cy * cy));
-  const double ratio = rho / dist;
-  const double delta = ratio <= 1.0 ? asin(ratio) : AUV_PI;
-  const double beta = atan2(cy, cx) - psi;
-  const int lo = (int)floor((AUV_PI + (beta - delta)) / dth);
-  const int hi = (int)ceil((AUV_PI + (beta + delta)) / dth);
+// culling window (sensor.py:22-97):  a = floor((pi+beta-delta)/dth) - 1,
+// b = ceil((pi+beta+delta)/dth) mod R (Python modulo); candidate(i) <=> a<=i<b or a<=i-R<b.
+// lo/hi are the raw floor/ceil values.
+__device__ __forceinline__ void window_from_bounds(int lo, int hi, int R, int mode, int& a, int& b,
+                                                   bool& allrays) {
   allrays = false;
   if (mode == AUV_CULL_EXACT) {
     // every ray whose index is in [lo-1, hi) modulo R
@@ -373,6 +438,40 @@ __device__ __forceinline__ void cull_window(double cx, double cy, double rho, do
   if (a < -R) allrays = true;  // IndexError in the reference: defined as all rays
 }
 
+__device__ __noinline__ void cull_bounds_f64(double cx, double cy, double rho, double psi, double dth,
+                                             int& lo, int& hi) {
+  const double dist = fmax(1e-8, sqrt(cx * cx + cy * cy));
+  const double ratio = rho / dist;
+  const double delta = ratio <= 1.0 ? asin(ratio) : AUV_PI;  // np.arcsin -> nan -> pi
+  const double beta = atan2(cy, cx) - psi;
+  lo = (int)floor((AUV_PI + (beta - delta)) / dth);
+  hi = (int)ceil((AUV_PI + (beta + delta)) / dth);
+}
+
+// FP32 fast path; falls back to FP64 whenever a quotient is within GUARD of an integer or
+// the asin argument is near 1, so the integers are always those of the FP64 formula.
+__device__ __forceinline__ void cull_bounds(double cx, double cy, double rho, double psi, int R,
+                                            int& lo, int& hi) {
+  const double dth = 2.0 * AUV_PI / (double)R;
+  const float fx = (float)cx, fy = (float)cy, fr = (float)rho;
+  const float dist = fmaxf(1e-8f, sqrtf(fx * fx + fy * fy));
+  const float ratio = fr / dist;
+  bool exact = ratio > 0.98f;  // asin' blows up near 1 and the <=1 decision itself is a threshold
+  if (!exact) {
+    const float inv = (float)(1.0 / dth);
+    const float delta = asinf(ratio);
+    const float beta = atan2f(fy, fx) - (float)psi;
+    const float qlo = ((float)AUV_PI + (beta - delta)) * inv;
+    const float qhi = ((float)AUV_PI + (beta + delta)) * inv;
+    const float flo = floorf(qlo), chi = ceilf(qhi);
+    const float GUARD = 4e-4f;  // >> atan2f/asinf error (~1e-6 rad) / dth + ulp(360)
+    exact = (qlo - flo < GUARD) || (flo + 1.f - qlo < GUARD) || (chi - qhi < GUARD) || (qhi - (chi - 1.f) < GUARD);
+    lo = (int)flo;
+    hi = (int)chi;
+  }
+  if (exact) cull_bounds_f64(cx, cy, rho, psi, dth, lo, hi);
+}
+
 struct ObserveArgs {
   AuvConfig cfg;
   AuvRayTable rays;
@@ -384,7 +483,18 @@ struct ObserveArgs {
   int obs_dim;
 };
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+// pentagon vertex k of a vessel obstacle, relative to the own-ship: base (bx,by) is the
+// rotation centre (area centroid) in vessel-relative coordinates
+__device__ __forceinline__ void pent_vertex(int k, double bx, double by, double w, double hx, double hy,
+                                            double& vx, double& vy) {
+  vx = bx + w * (hx * c_pent[k][0] - hy * c_pent[k][1]);
+  vy = by + w * (hy * c_pent[k][0] + hx * c_pent[k][1]);
+}
+
+#ifndef AUV_OBSERVE_MIN_BLOCKS
+#define AUV_OBSERVE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
     k_observe(const __grid_constant__ ObserveArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_unit[64][2];  // cos/sin(2 pi k / 64)
@@ -405,7 +515,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
   const int e = blockIdx.x * WARPS_PER_BLOCK + wib;
   const int n = A.batch.n_envs;
   if (e >= n) return;
-  AuvBatch batch = A.batch;  // local copy (reset helper takes a non-const ref)
+  const AuvBatch& batch = A.batch;
   const AuvScenarioPool& pool = A.pool;
   const AuvConfig& cfg = A.cfg;
   const int km = pool.k_moving, ks = pool.k_static, K = km + ks;
@@ -416,14 +526,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 
   for (int pass = 0; pass < 2; ++pass) {
     const int scn = batch.scn_id[e];
-    const double px = batch.state[e], py = batch.state[n + e], psi = batch.state[2 * n + e];
-    const double vu = batch.state[3 * n + e], vv = batch.state[4 * n + e], vr = batch.state[5 * n + e];
+    // navigation record written by k_vessel_nav (or by lane 0 below after an auto-reset)
+    double navv = 0.0;
+    if (lane < AUV_NAV_W) navv = batch.nav[(long long)e * AUV_NAV_W + lane];
+    double stv = 0.0;  // lanes 0..5: x, y, psi, u, v, r
+    if (lane < 6) stv = batch.state[(long long)lane * n + e];
+    const double px = __shfl_sync(AUV_FULL, stv, 0), py = __shfl_sync(AUV_FULL, stv, 1);
+    const double psi = __shfl_sync(AUV_FULL, stv, 2);
     const int step_counter = batch.step_counter[e];
-
-    // ---------------- navigate ----------------
-    const Nav nv = navigate_warp(cfg, A.paths, pool.path_id[scn], px, py, psi, lane);
-    const double maxprog_prev = batch.max_progress[e];
-    const double maxprog = fmax(nv.progress, maxprog_prev);
 
     float* obs = A.out.obs + (long long)e * A.obs_dim;
     bool collision = false;
@@ -432,118 +542,128 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 
     if (cfg.use_lidar) {
       // ---------------- perceive ----------------
-      for (int i = lane; i < rpad; i += 32) sdist[i] = rangef;
       const bool refresh = (step_counter % cfg.sensor_interval_load_obstacles) == 0;
-      double spsi, cpsi;
-      sincos(psi, &spsi, &cpsi);
+      const double cpsi = __shfl_sync(AUV_FULL, navv, NAV_COSPSI), spsi = __shfl_sync(AUV_FULL, navv, NAV_SINPSI);
       bool any_active = false;
       for (int base = 0; base < K; base += 32) {
         const int j = base + lane;
+        unsigned word = 0u;
+        if (!refresh) {
+          word = batch.nearby_mask[(long long)e * batch.mask_words + (base >> 5)];
+          if (word == 0u) {
+            if (A.out.windows != nullptr && j < K)
+              reinterpret_cast<int2*>(A.out.windows)[(long long)e * K + j] = make_int2(0, 0);
+            continue;  // nothing of this chunk is on the nearby list: no loads at all
+          }
+        }
+        // only obstacles that are (or may become) nearby are loaded
+        const bool want = j < K && (refresh || ((word >> lane) & 1u));
         bool valid = false;
         bool pent = false;
         double cx = 0, cy = 0, rho = 0, geo = 0, hx = 1.0, hy = 0.0;
         int nv_cnt = 0;  // vertices incl. closing one
-        if (j < km) {
-          const long long ps = (long long)scn * km + j, pe = (long long)e * km + j;
-          const double w = pool.mov_width[ps];
-          if (w > 0.0) {
-            valid = true;
-            pent = true;
-            geo = w;
+        if (want) {
+          if (j < km) {
+            const long long ps = (long long)scn * km + j, pe = (long long)e * km + j;
+            const double w = pool.mov_width[ps];
             const double2 pos = reinterpret_cast<const double2*>(batch.mov_pos)[pe];
             const double2 dsp = reinterpret_cast<const double2*>(batch.mov_disp)[pe];
-            const double dl = sqrt(dsp.x * dsp.x + dsp.y * dsp.y);
-            if (dl > 0.0) {
-              hx = dsp.x / dl;
-              hy = dsp.y / dl;
+            if (w > 0.0) {
+              valid = true;
+              pent = true;
+              geo = w;
+              const double dl2 = dsp.x * dsp.x + dsp.y * dsp.y;
+              if (dl2 > 0.0) {
+                const double inv = rsqrt(dl2);
+                hx = dsp.x * inv;
+                hy = dsp.y * inv;
+              }
+              // enclosing circle of the min-rotated rectangle (obstacles.py:230-262; App. A.3)
+              cx = (pos.x - px) + 5.0 * w / 18.0 + (2.0 * w / 9.0) * hx;
+              cy = (pos.y - py) + (2.0 * w / 9.0) * hy;
+              rho = w * 1.1180339887498949;  // sqrt(5)/2
+              nv_cnt = 6;
             }
-            // enclosing circle of the min-rotated rectangle (obstacles.py:230-262; App. A.3)
-            cx = (pos.x - px) + 5.0 * w / 18.0 + (2.0 * w / 9.0) * hx;
-            cy = (pos.y - py) + (2.0 * w / 9.0) * hy;
-            rho = w * 1.1180339887498949;  // sqrt(5)/2
-            nv_cnt = 6;
-          }
-        } else if (j < K) {
-          const long long ps = (long long)scn * ks + (j - km);
-          const double r = pool.st_radius[ps];
-          if (r > 0.0) {
-            valid = true;
-            geo = r;
+          } else {
+            const long long ps = (long long)scn * ks + (j - km);
+            const double r = pool.st_radius[ps];
             const double2 c = reinterpret_cast<const double2*>(pool.st_pos)[ps];
-            cx = c.x - px;
-            cy = c.y - py;
-            rho = r;
-            nv_cnt = ngon_sides(r) + 1;
+            if (r > 0.0) {
+              valid = true;
+              geo = r;
+              cx = c.x - px;
+              cy = c.y - py;
+              rho = r;
+              nv_cnt = ngon_sides(r) + 1;
+            }
           }
         }
-        // pentagon vertices relative to the vessel (needed for inside / nearby tests)
-        // V_k = centroid + R(heading) (P_k - centroid) + pos - p0
+        // rotation centre of the pentagon, vessel-relative: V_k = b + w R(heading) P'_k
         const double bx0 = cx - (2.0 * geo / 9.0) * hx, by0 = cy - (2.0 * geo / 9.0) * hy;
 
         // ---- nearby list: refreshed every sensor_interval_load_obstacles vessel steps
-        unsigned word;
         if (refresh) {
           bool near = false;
           if (valid) {
-            float dmin = INFINITY;
-            bool inside = false;
-            const int ne = nv_cnt - 1;
-            float pxv, pyv;
-            {  // vertex 0
+            // cheap conservative pre-tests on the enclosing circle (exact test only in between)
+            const double dc = sqrt(cx * cx + cy * cy);
+            if (dc - rho - cfg.vessel_width >= range + 1e-6) {
+              near = false;  // boundary lies inside the circle: distance >= dc - rho
+            } else if (pent && dc + rho - cfg.vessel_width < range - 1e-6) {
+              near = true;  // filled polygon: distance <= dc + rho
+            } else {
+              float dmin = INFINITY;
+              const int ne = nv_cnt - 1;
               double vx, vy;
               if (pent) {
-                vx = bx0 + geo * (hx * c_pent[0][0] - hy * c_pent[0][1]);
-                vy = by0 + geo * (hy * c_pent[0][0] + hx * c_pent[0][1]);
+                pent_vertex(0, bx0, by0, geo, hx, hy, vx, vy);
               } else {
                 vx = cx + geo;
                 vy = cy;
               }
-              pxv = (float)vx;
-              pyv = (float)vy;
-            }
-            bool allpos = true, allneg = true;
-            for (int k = 1; k <= ne; ++k) {
-              const int kk = (k == ne) ? 0 : k;
-              double vx, vy;
-              if (pent) {
-                vx = bx0 + geo * (hx * c_pent[kk][0] - hy * c_pent[kk][1]);
-                vy = by0 + geo * (hy * c_pent[kk][0] + hx * c_pent[kk][1]);
-              } else {
-                const int ui = kk * (64 / ne);
-                vx = cx + geo * s_unit[ui][0];
-                vy = cy + geo * s_unit[ui][1];
+              float pxv = (float)vx, pyv = (float)vy;
+              bool allpos = true, allneg = true;
+              for (int k = 1; k <= ne; ++k) {
+                const int kk = (k == ne) ? 0 : k;
+                if (pent) {
+                  pent_vertex(kk, bx0, by0, geo, hx, hy, vx, vy);
+                } else {
+                  const int ui = kk * (64 / ne);
+                  vx = cx + geo * s_unit[ui][0];
+                  vy = cy + geo * s_unit[ui][1];
+                }
+                const float qx = (float)vx, qy = (float)vy;
+                dmin = fminf(dmin, pt_seg_dist_f(0.f, 0.f, pxv, pyv, qx, qy));
+                const float cr = pxv * qy - pyv * qx;  // cross(prev, cur) about the vessel
+                allpos = allpos && (cr >= 0.f);
+                allneg = allneg && (cr <= 0.f);
+                pxv = qx;
+                pyv = qy;
               }
-              const float qx = (float)vx, qy = (float)vy;
-              dmin = fminf(dmin, pt_seg_dist_f(0.f, 0.f, pxv, pyv, qx, qy));
-              const float cr = pxv * qy - pyv * qx;  // cross(prev, cur) about the vessel
-              allpos = allpos && (cr >= 0.f);
-              allneg = allneg && (cr <= 0.f);
-              pxv = qx;
-              pyv = qy;
+              const bool inside = pent && (allpos || allneg);
+              const double dist = inside ? 0.0 : (double)dmin;
+              near = (dist - cfg.vessel_width) < range;  // vessel.py:269-270
             }
-            inside = pent && (allpos || allneg);
-            const double dist = inside ? 0.0 : (double)dmin;
-            near = (dist - cfg.vessel_width) < range;  // vessel.py:269-270
           }
           word = __ballot_sync(AUV_FULL, near);
           if (lane == 0) batch.nearby_mask[(long long)e * batch.mask_words + (base >> 5)] = word;
-        } else {
-          word = batch.nearby_mask[(long long)e * batch.mask_words + (base >> 5)];
         }
         const bool active = valid && ((word >> lane) & 1u);
 
         int wa = 0, wb = 0;
         bool allrays = false, inside = false;
         if (active) {
-          cull_window(cx, cy, rho, psi, R, cfg.cull_mode, wa, wb, allrays);
-          if (pent) {  // filled polygon: is the vessel inside?  (range 0)
+          int lo, hi;
+          cull_bounds(cx, cy, rho, psi, R, lo, hi);
+          window_from_bounds(lo, hi, R, cfg.cull_mode, wa, wb, allrays);
+          if (pent && cx * cx + cy * cy <= rho * rho) {
+            // filled polygon: is the vessel inside?  (range 0)
             bool allpos = true, allneg = true;
-            double pvx = bx0 + geo * (hx * c_pent[4][0] - hy * c_pent[4][1]);
-            double pvy = by0 + geo * (hy * c_pent[4][0] + hx * c_pent[4][1]);
+            double pvx, pvy, vx, vy;
+            pent_vertex(4, bx0, by0, geo, hx, hy, pvx, pvy);
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-              const double vx = bx0 + geo * (hx * c_pent[k][0] - hy * c_pent[k][1]);
-              const double vy = by0 + geo * (hy * c_pent[k][0] + hx * c_pent[k][1]);
+              pent_vertex(k, bx0, by0, geo, hx, hy, vx, vy);
               const double cr = pvx * vy - pvy * vx;
               allpos = allpos && (cr >= 0.0);
               allneg = allneg && (cr <= 0.0);
@@ -561,7 +681,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
         // ---- stage active obstacles in batches bounded by the vertex budget
         unsigned rem = __ballot_sync(AUV_FULL, active);
         while (rem) {
-          any_active = true;
+          if (!any_active) {
+            for (int i = lane; i < rpad; i += 32) sdist[i] = rangef;
+            any_active = true;
+          }
           const bool mine = (rem >> lane) & 1u;
           const int cnt = mine ? nv_cnt : 0;
           const int incl = warp_incl_scan(cnt, lane);
@@ -570,8 +693,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
           const int nact = __popc(tk);
           if (take) {
             const int ci = __popc(tk & ((1u << lane) - 1u));
-            W.ocxd[ci] = cx;
-            W.ocyd[ci] = cy;
+            W.ocxd[ci] = pent ? bx0 : cx;  // pentagon: rotation centre; circle: centre
+            W.ocyd[ci] = pent ? by0 : cy;
             W.ogeo[ci] = geo;
             W.ohx[ci] = hx;
             W.ohy[ci] = hy;
@@ -593,13 +716,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
             const double g = W.ogeo[i];
             if (W.oflag[i] & OFLAG_PENTAGON) {
               if (lane < 6) {
-                const int kk = lane == 5 ? 0 : lane;
-                const double h_x = W.ohx[i], h_y = W.ohy[i];
-                const double b_x = W.ocxd[i] - (2.0 * g / 9.0) * h_x;
-                const double b_y = W.ocyd[i] - (2.0 * g / 9.0) * h_y;
-                W.verts[off + lane] =
-                    make_float2((float)(b_x + g * (h_x * c_pent[kk][0] - h_y * c_pent[kk][1])),
-                                (float)(b_y + g * (h_y * c_pent[kk][0] + h_x * c_pent[kk][1])));
+                double vx, vy;
+                pent_vertex(lane == 5 ? 0 : lane, W.ocxd[i], W.ocyd[i], g, W.ohx[i], W.ohy[i], vx, vy);
+                W.verts[off + lane] = make_float2((float)vx, (float)vy);
               }
             } else {
               const int ne = nvv - 1;
@@ -661,55 +780,50 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
         }
       }
       // ---- closeness / collision / penalty  (vessel.py:88-95,356-359; rewarder.py:199-214)
-      const float inv_log = 1.f / log1pf(rangef);
-      for (int i0 = 0; i0 < R; i0 += 32) {
-        const int i = i0 + lane;
-        if (i < R) {
-          const float d = any_active ? sdist[i] : rangef;
-          float cl;
-          if (!any_active) {
-            cl = 0.f;  // vessel.py:275-305: no nearby obstacles => closeness 0
-          } else if (d >= rangef) {
-            cl = 0.f;  // 1 - log(1+range)/log(1+range) is exactly 0 in the reference
-          } else if (cfg.sensor_log_transform) {
-            cl = 1.f - fminf(fmaxf(log1pf(d) * inv_log, 0.f), 1.f);
-          } else {
-            cl = 1.f - fminf(fmaxf(d / rangef, 0.f), 1.f);
-          }
-          obs[6 + i] = fminf(fmaxf(cl, -1.f), 1.f);
-          if (cfg.sensor_use_velocity_observations) {
-            obs[6 + R + i] = 0.f;  // sensor.py:159: speed channel is (0,0) at HEAD
-            obs[6 + 2 * R + i] = 0.f;
-          }
-          if (A.out.lidar_dist != nullptr) A.out.lidar_dist[(long long)e * R + i] = d;
-          collision = collision || (any_active && d < widthf);
-          pen_sum += A.rays.weight[i] * rangef * __expf(-0.1f * d);
+      if (!any_active) {
+        // vessel.py:275-305: no nearby obstacles => every range = sensor_range, closeness 0
+        for (int i = lane; i < R; i += 32) {
+          obs[6 + i] = 0.f;
+          if (A.out.lidar_dist != nullptr) A.out.lidar_dist[(long long)e * R + i] = rangef;
         }
+        pen_sum = (float)(A.rays.weight_sum * range * exp(-0.1 * range));
+      } else {
+        const float inv_log = 1.f / log1pf(rangef);
+        for (int i0 = 0; i0 < R; i0 += 32) {
+          const int i = i0 + lane;
+          if (i < R) {
+            const float d = sdist[i];
+            float cl;
+            if (d >= rangef) {
+              cl = 0.f;  // 1 - log(1+range)/log(1+range) is exactly 0 in the reference
+            } else if (cfg.sensor_log_transform) {
+              cl = 1.f - fminf(fmaxf(log1pf(d) * inv_log, 0.f), 1.f);
+            } else {
+              cl = 1.f - fminf(fmaxf(d / rangef, 0.f), 1.f);
+            }
+            obs[6 + i] = fminf(fmaxf(cl, -1.f), 1.f);
+            if (A.out.lidar_dist != nullptr) A.out.lidar_dist[(long long)e * R + i] = d;
+            collision = collision || (d < widthf);
+            pen_sum += A.rays.weight[i] * rangef * __expf(-0.1f * d);
+          }
+        }
+        collision = __any_sync(AUV_FULL, collision);
+        pen_sum = warp_sum(pen_sum);
       }
-      collision = __any_sync(AUV_FULL, collision);
-      pen_sum = warp_sum(pen_sum);
+      if (cfg.sensor_use_velocity_observations)  // sensor.py:159: speed channel is (0,0) at HEAD
+        for (int i = lane; i < 2 * R; i += 32) obs[6 + R + i] = 0.f;
     }
 
     // ---------------- navigation part of the observation (vessel.py:518-539) ----------
-    if (lane == 0) {
-      obs[0] = (float)fmin(fmax(vu, -1.0), 1.0);
-      obs[1] = (float)fmin(fmax(vv, -1.0), 1.0);
-      obs[2] = (float)fmin(fmax(vr, -1.0), 1.0);
-      obs[3] = (float)fmin(fmax(nv.la_err, -1.0), 1.0);
-      obs[4] = (float)fmin(fmax(nv.head_err, -1.0), 1.0);
-      obs[5] = (float)fmin(fmax(nv.y_e / 100.0, -1.0), 1.0);
-      batch.max_progress[e] = maxprog;
-      if (A.out.nav != nullptr) {
-        double* o = A.out.nav + 8ll * e;
-        o[0] = nv.s;
-        o[1] = nv.chi;
-        o[2] = nv.y_e;
-        o[3] = nv.s_la;
-        o[4] = nv.la_err;
-        o[5] = nv.head_err;
-        o[6] = nv.goal_dist;
-        o[7] = nv.progress;
-      }
+    {
+      // obs[0..5] = u, v, r, look-ahead heading error, heading error, cross-track/100
+      double val = __shfl_sync(AUV_FULL, stv, (lane + 3) & 31);  // lanes 0..2 <- u, v, r
+      const double la = __shfl_sync(AUV_FULL, navv, NAV_LA_ERR), he = __shfl_sync(AUV_FULL, navv, NAV_HEAD_ERR);
+      const double ye = __shfl_sync(AUV_FULL, navv, NAV_YE);
+      if (lane == 3) val = la;
+      if (lane == 4) val = he;
+      if (lane == 5) val = ye / 100.0;
+      if (lane < 6) obs[lane] = (float)fmin(fmax(val, -1.0), 1.0);
     }
     if (A.out.seg_tests != nullptr) {
       unsigned long long t = ntests;
@@ -717,30 +831,38 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
       for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(AUV_FULL, t, o);
       if (lane == 0 && t) atomicAdd(A.out.seg_tests, t);
     }
+    const double progress = __shfl_sync(AUV_FULL, navv, NAV_PROGRESS);
+    const double goal_dist = __shfl_sync(AUV_FULL, navv, NAV_GOAL);
+    const bool reached = __shfl_sync(AUV_FULL, navv, NAV_REACHED) != 0.0;
     if (mode == AUV_OBSERVE_RESET) {
       if (lane == 0 && pass == 0) {  // explicit reset observe: info mirrors a fresh env
         if (A.out.collision) A.out.collision[e] = collision;
-        if (A.out.reached_goal) A.out.reached_goal[e] = nv.reached;
-        if (A.out.goal_distance) A.out.goal_distance[e] = (float)nv.goal_dist;
-        if (A.out.progress) A.out.progress[e] = (float)nv.progress;
+        if (A.out.reached_goal) A.out.reached_goal[e] = reached;
+        if (A.out.goal_distance) A.out.goal_distance[e] = (float)goal_dist;
+        if (A.out.progress) A.out.progress[e] = (float)progress;
       }
       return;
     }
 
     // ---------------- reward (rewarder.py) + done (environment.py:375-384) ------------
+    const double vu = __shfl_sync(AUV_FULL, stv, 3), vv = __shfl_sync(AUV_FULL, stv, 4);
+    const double vr = __shfl_sync(AUV_FULL, stv, 5);
+    const double y_e = __shfl_sync(AUV_FULL, navv, NAV_YE);
+    const double cos_he = __shfl_sync(AUV_FULL, navv, NAV_COS_HEAD_ERR);
+    const double maxprog = batch.max_progress[e];  // already includes this step (k_vessel_nav)
     const double speed = sqrt(vu * vu + vv * vv);
     double reward;
     if (collision) {
       reward = -10000.0 * (1.0 - 0.5);
     } else {
-      const double cte = nv.y_e / 100.0;
-      double path_reward = (1.0 + cos(nv.head_err) * speed / 2.0) * (1.0 + exp(-5.0 * fabs(cte))) - 1.0;
+      const double cte = y_e / 100.0;
+      double path_reward = (1.0 + cos_he * speed / 2.0) * (1.0 + (double)__expf((float)(-5.0 * fabs(cte)))) - 1.0;
       const double living = 0.5 * (2.0 * 0.05 + 1.0);
       if (cfg.rewarder == AUV_REWARDER_COLAV) {
         // without LiDAR every ray keeps its reset value sensor_range (vessel.py:206-208)
         const double closeness_reward =
             cfg.use_lidar ? -(double)pen_sum / A.rays.weight_sum : -range * exp(-0.1 * range);
-        if (nv.progress < maxprog) path_reward = fmin(path_reward, 0.0);
+        if (progress < maxprog) path_reward = fmin(path_reward, 0.0);
         const double slow = speed < 0.04 ? -2.0 : 0.0;
         reward = 0.5 * path_reward + 0.5 * closeness_reward - living - 10.0 * fabs(vr) + slow;
         if (reward < 0.0) reward *= 2.0;
@@ -751,10 +873,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     }
     const double cum = batch.cum_reward[e] + reward;
     const int t_step = batch.t_step[e];
-    const bool done = collision || nv.reached ||
+    const bool done = collision || reached ||
                       (!cfg.test_mode && t_step >= cfg.max_timesteps - 1) ||
                       (!cfg.test_mode && cum < cfg.min_cumulative_reward);
-    const double cte_sum = batch.cte_sum[e] + fabs(nv.y_e);
+    const double cte_sum = batch.cte_sum[e] + fabs(y_e);
     if (lane == 0) {
       batch.cum_reward[e] = cum;
       batch.t_step[e] = t_step + 1;
@@ -762,9 +884,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
       A.out.reward[e] = (float)reward;
       A.out.done[e] = done;
       if (A.out.collision) A.out.collision[e] = collision;
-      if (A.out.reached_goal) A.out.reached_goal[e] = nv.reached;
-      if (A.out.goal_distance) A.out.goal_distance[e] = (float)nv.goal_dist;
-      if (A.out.progress) A.out.progress[e] = (float)nv.progress;
+      if (A.out.reached_goal) A.out.reached_goal[e] = reached;
+      if (A.out.goal_distance) A.out.goal_distance[e] = (float)goal_dist;
+      if (A.out.progress) A.out.progress[e] = (float)progress;
     }
     if (!(done && cfg.auto_reset)) return;
 
@@ -779,9 +901,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
       atomicAdd(st + AUV_STAT_EPISODES, 1.0);
       atomicAdd(st + AUV_STAT_REWARD, cum);
       atomicAdd(st + AUV_STAT_REWARD_SQ, cum * cum);
-      atomicAdd(st + AUV_STAT_PROGRESS, nv.progress);
+      atomicAdd(st + AUV_STAT_PROGRESS, progress);
       atomicAdd(st + AUV_STAT_COLLISIONS, collision ? 1.0 : 0.0);
-      atomicAdd(st + AUV_STAT_REACHED_GOAL, nv.reached ? 1.0 : 0.0);
+      atomicAdd(st + AUV_STAT_REACHED_GOAL, reached ? 1.0 : 0.0);
       atomicAdd(st + AUV_STAT_TIMESTEPS, (double)(t_step + 1));
       atomicAdd(st + AUV_STAT_CROSS_TRACK, cte_sum / (double)(t_step + 1));
       atomicAdd(st + AUV_STAT_PATHLENGTH, A.paths.length[pool.path_id[scn]]);
@@ -789,6 +911,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     __syncwarp();
     const int next = (int)(((long long)scn + n) % pool.n_scenarios);
     reset_env_warp(pool, batch, e, next, lane);
+    if (lane == 0) {  // navigation of the fresh episode (rare: one lane, FP64)
+      const double* vi = pool.vessel_init + 3ll * next;
+      navigate_thread(cfg, A.paths, batch, pool.path_id[next], e, vi[0], vi[1], vi[2]);
+    }
+    __syncwarp();
     mode = AUV_OBSERVE_RESET;
   }
 }
@@ -904,13 +1031,13 @@ int auv_reset(const AuvConfig* cfg, const AuvScenarioPool* pool, AuvBatch* batch
   return cuda_check(cudaGetLastError(), "k_reset");
 }
 
-int auv_observe(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
-                const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode,
-                void* stream) {
+static int check_observe_args(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                              const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode) {
   if (int rc = check_cfg(cfg)) return rc;
   if (!paths || !pool || !batch || !out) return set_err(AUV_EINVAL, "NULL argument");
   if (cfg->use_lidar && !rays) return set_err(AUV_EINVAL, "rays is NULL with use_lidar");
   if (!out->obs) return set_err(AUV_EINVAL, "out.obs is NULL");
+  if (!batch->nav) return set_err(AUV_EINVAL, "batch.nav is NULL");
   if (mode == AUV_OBSERVE_STEP && (!out->reward || !out->done))
     return set_err(AUV_EINVAL, "out.reward/out.done is NULL");
   if (batch->n_envs <= 0) return set_err(AUV_EINVAL, "n_envs must be > 0");
@@ -918,6 +1045,23 @@ int auv_observe(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank
     return set_err(AUV_EINVAL, "too many obstacle slots");
   if (batch->mask_words * 32 < pool->k_moving + pool->k_static)
     return set_err(AUV_EINVAL, "mask_words too small");
+  return 0;
+}
+
+static int launch_vessel_nav(const AuvConfig* cfg, const AuvPathBank* paths, const AuvScenarioPool* pool,
+                             AuvBatch* batch, const float* actions, void* stream) {
+  const int threads = 128;
+  const int blocks = (batch->n_envs + threads - 1) / threads;
+  if (actions)
+    auv::k_vessel_nav<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, actions);
+  else
+    auv::k_vessel_nav<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, nullptr);
+  return cuda_check(cudaGetLastError(), "k_vessel_nav");
+}
+
+static int launch_observe(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                          const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode,
+                          void* stream) {
   auv::ObserveArgs args;
   args.cfg = *cfg;
   if (rays) args.rays = *rays; else memset(&args.rays, 0, sizeof(args.rays));
@@ -942,12 +1086,80 @@ int auv_observe(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank
   return cuda_check(cudaGetLastError(), "k_observe");
 }
 
+int auv_navigate(const AuvConfig* cfg, const AuvPathBank* paths, const AuvScenarioPool* pool,
+                 AuvBatch* batch, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  if (!paths || !pool || !batch) return set_err(AUV_EINVAL, "NULL argument");
+  if (!batch->nav) return set_err(AUV_EINVAL, "batch.nav is NULL");
+  if (batch->n_envs <= 0) return set_err(AUV_EINVAL, "n_envs must be > 0");
+  return launch_vessel_nav(cfg, paths, pool, batch, nullptr, stream);
+}
+
+int auv_observe(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode,
+                void* stream) {
+  if (int rc = check_observe_args(cfg, rays, paths, pool, batch, out, mode)) return rc;
+  if (int rc = launch_vessel_nav(cfg, paths, pool, batch, nullptr, stream)) return rc;
+  return launch_observe(cfg, rays, paths, pool, batch, out, mode, stream);
+}
+
 int auv_step(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
              const AuvScenarioPool* pool, AuvBatch* batch, const float* actions, AuvStepOut* out,
              void* stream) {
+  if (!actions) return set_err(AUV_EINVAL, "actions is NULL");
+  if (int rc = check_observe_args(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP)) return rc;
   if (int rc = auv_obstacle_update(cfg, pool, batch, stream)) return rc;
-  if (int rc = auv_vessel_step(cfg, batch, actions, stream)) return rc;
-  return auv_observe(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, stream);
+  if (int rc = launch_vessel_nav(cfg, paths, pool, batch, actions, stream)) return rc;  // Vessel.step + navigate
+  return launch_observe(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, stream);
+}
+
+struct AuvTimer {
+  int capacity;
+  cudaEvent_t* ev;  // [capacity][4]
+};
+
+AuvTimer* auv_timer_create(int capacity) {
+  if (capacity <= 0) return nullptr;
+  AuvTimer* t = new AuvTimer;
+  t->capacity = capacity;
+  t->ev = new cudaEvent_t[(size_t)capacity * 4];
+  for (int i = 0; i < capacity * 4; ++i)
+    if (cudaEventCreate(&t->ev[i]) != cudaSuccess) {
+      for (int k = 0; k < i; ++k) cudaEventDestroy(t->ev[k]);
+      delete[] t->ev;
+      delete t;
+      return nullptr;
+    }
+  return t;
+}
+void auv_timer_destroy(AuvTimer* t) {
+  if (!t) return;
+  for (int i = 0; i < t->capacity * 4; ++i) cudaEventDestroy(t->ev[i]);
+  delete[] t->ev;
+  delete t;
+}
+int auv_step_timed(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                   const AuvScenarioPool* pool, AuvBatch* batch, const float* actions, AuvStepOut* out,
+                   void* stream, AuvTimer* t, int slot) {
+  if (!t || slot < 0 || slot >= t->capacity) return set_err(AUV_EINVAL, "bad timer/slot");
+  if (!actions) return set_err(AUV_EINVAL, "actions is NULL");
+  if (int rc = check_observe_args(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaEvent_t* e = t->ev + 4 * slot;
+  cudaEventRecord(e[0], s);
+  if (int rc = auv_obstacle_update(cfg, pool, batch, stream)) return rc;
+  cudaEventRecord(e[1], s);
+  if (int rc = launch_vessel_nav(cfg, paths, pool, batch, actions, stream)) return rc;
+  cudaEventRecord(e[2], s);
+  if (int rc = launch_observe(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, stream)) return rc;
+  return cuda_check(cudaEventRecord(e[3], s), "cudaEventRecord");
+}
+int auv_timer_read(AuvTimer* t, int slot, float* ms) {
+  if (!t || !ms || slot < 0 || slot >= t->capacity) return set_err(AUV_EINVAL, "bad timer/slot");
+  cudaEvent_t* e = t->ev + 4 * slot;
+  for (int k = 0; k < 3; ++k)
+    if (int rc = cuda_check(cudaEventElapsedTime(&ms[k], e[k], e[k + 1]), "cudaEventElapsedTime")) return rc;
+  return 0;
 }
 
 int auv_step_host(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,

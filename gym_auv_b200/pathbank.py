@@ -22,6 +22,7 @@ import numpy as np
 from scipy import interpolate
 
 PATH_BLOCK = 32  # must equal AUV_PATH_BLOCK in include/auv_b200.h
+PATH_SUPER = 32  # blocks per superblock, AUV_PATH_SUPER
 N_KNOTS = 1000
 
 
@@ -35,6 +36,8 @@ class PathTable:
     cum: np.ndarray  # [n]
     blk_chord: np.ndarray  # [nblk, 4] float32, relative to origin
     blk_dev: np.ndarray  # [nblk] float32
+    sb_chord: np.ndarray  # [nsb, 4] float32
+    sb_dev: np.ndarray  # [nsb] float32
     origin: np.ndarray  # [2]
     length: float
     end: np.ndarray  # [2]
@@ -51,6 +54,31 @@ class PathTable:
 def _chord_lengths(pts: np.ndarray) -> np.ndarray:
     seg = np.sqrt(np.sum(np.diff(pts, axis=1) ** 2, axis=0))
     return np.concatenate([[0.0], np.cumsum(seg)])
+
+
+def _capsules(rel: np.ndarray, nseg: int, span: int):
+    """One (chord, deviation) capsule per `span` consecutive segments: chord = first/last
+    vertex (rounded to float32), deviation = max distance of the covered vertices from the
+    ROUNDED chord (FP64) plus a float32 rounding allowance, rounded up."""
+    n = (nseg + span - 1) // span
+    first = np.arange(n) * span
+    last = np.minimum(first + span, nseg)
+    chord = np.concatenate([rel[first], rel[last]], axis=1).astype(np.float32)
+    a = chord[:, 0:2].astype(np.float64)
+    b = chord[:, 2:4].astype(np.float64)
+    e = b - a
+    len2 = np.sum(e * e, axis=1)
+    dev = np.zeros(n)
+    for k in range(span + 1):  # loop over the offset inside the node keeps memory O(n)
+        v = rel[np.minimum(first + k, last)]
+        w = v - a
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = np.where(len2 > 0, np.sum(w * e, axis=1) / len2, 0.0)
+        t = np.clip(t, 0.0, 1.0)
+        dev = np.maximum(dev, np.sqrt(np.sum((w - t[:, None] * e) ** 2, axis=1)))
+    extent = float(np.abs(rel).max()) + 1.0
+    dev = dev + 8.0 * np.finfo(np.float32).eps * extent
+    return chord, np.nextafter(dev.astype(np.float32), np.float32(np.inf))
 
 
 def build_path(waypoints) -> PathTable:
@@ -76,33 +104,18 @@ def build_path(waypoints) -> PathTable:
     origin = poly[0].copy()
 
     nseg = n_poly - 1
-    nblk = (nseg + PATH_BLOCK - 1) // PATH_BLOCK
-    first = np.arange(nblk) * PATH_BLOCK
-    last = np.minimum(first + PATH_BLOCK, nseg)  # vertex index of the block's last vertex
     rel = poly - origin
-    chord = np.concatenate([rel[first], rel[last]], axis=1).astype(np.float32)  # [nblk, 4]
-    # max deviation of the block's vertices from its (float32-rounded) chord, in FP64
-    idx = np.minimum(first[:, None] + np.arange(PATH_BLOCK + 1)[None, :], last[:, None])
-    v = rel[idx]  # [nblk, 33, 2]
-    a = chord[:, None, 0:2].astype(np.float64)
-    b = chord[:, None, 2:4].astype(np.float64)
-    e = b - a
-    len2 = np.sum(e * e, axis=2)
-    w = v - a
-    with np.errstate(divide="ignore", invalid="ignore"):
-        t = np.where(len2 > 0, np.sum(w * e, axis=2) / len2, 0.0)
-    t = np.clip(t, 0.0, 1.0)
-    d = np.sqrt(np.sum((w - t[..., None] * e) ** 2, axis=2))
-    extent = float(np.abs(rel).max()) + 1.0
-    dev = d.max(axis=1) + 8.0 * np.finfo(np.float32).eps * extent
-    blk_dev = np.nextafter(dev.astype(np.float32), np.float32(np.inf))
+    blk_chord, blk_dev = _capsules(rel, nseg, PATH_BLOCK)
+    sb_chord, sb_dev = _capsules(rel, nseg, PATH_BLOCK * PATH_SUPER)
     return PathTable(
         knots=np.ascontiguousarray(spline.x),
         coef=coef,
         poly=poly,
         cum=cum,
-        blk_chord=chord,
+        blk_chord=blk_chord,
         blk_dev=blk_dev,
+        sb_chord=sb_chord,
+        sb_dev=sb_dev,
         origin=origin,
         length=length,
         end=np.array(spline(length), dtype=np.float64),
@@ -120,9 +133,13 @@ class PathBank:
         self.n_paths = len(tables)
         self.poly_off = np.zeros(self.n_paths + 1, dtype=np.int32)
         self.blk_off = np.zeros(self.n_paths + 1, dtype=np.int32)
+        self.sb_off = np.zeros(self.n_paths + 1, dtype=np.int32)
         for i, t in enumerate(tables):
             self.poly_off[i + 1] = self.poly_off[i] + len(t.poly)
             self.blk_off[i + 1] = self.blk_off[i] + len(t.blk_dev)
+            self.sb_off[i + 1] = self.sb_off[i] + len(t.sb_dev)
+        self.sb_chord = np.concatenate([t.sb_chord for t in tables], axis=0)
+        self.sb_dev = np.concatenate([t.sb_dev for t in tables])
         self.poly_xy = np.concatenate([t.poly for t in tables], axis=0)
         self.poly_cum = np.concatenate([t.cum for t in tables])
         self.blk_chord = np.concatenate([t.blk_chord for t in tables], axis=0)
@@ -150,6 +167,9 @@ class PathBank:
             blk_off=dev(self.blk_off, torch.int32),
             blk_chord=dev(self.blk_chord, torch.float32),
             blk_dev=dev(self.blk_dev, torch.float32),
+            sb_off=dev(self.sb_off, torch.int32),
+            sb_chord=dev(self.sb_chord, torch.float32),
+            sb_dev=dev(self.sb_dev, torch.float32),
             origin=dev(self.origin, torch.float64),
             knots=dev(self.knots, torch.float64),
             coef=dev(self.coef, torch.float64),

@@ -138,7 +138,7 @@ class AUVVecEnv:
         self.paths = _lib.AuvPathBank(
             bank.n_paths, bank.knots.shape[1], b["poly_off"].data_ptr(), b["poly_xy"].data_ptr(),
             b["poly_cum"].data_ptr(), b["blk_off"].data_ptr(), b["blk_chord"].data_ptr(), b["blk_dev"].data_ptr(),
-            b["origin"].data_ptr(), b["knots"].data_ptr(), b["coef"].data_ptr(), b["length"].data_ptr(),
+            b["sb_off"].data_ptr(), b["sb_chord"].data_ptr(), b["sb_dev"].data_ptr(), b["origin"].data_ptr(), b["knots"].data_ptr(), b["coef"].data_ptr(), b["length"].data_ptr(),
             b["end_xy"].data_ptr(),
         )
 
@@ -183,13 +183,14 @@ class AUVVecEnv:
             mov_pos=z((N, max(Km, 1), 2), torch.float64),
             mov_disp=z((N, max(Km, 1), 2), torch.float64),
             mov_counter=z((N, max(Km, 1)), torch.float64),
+            nav=z((N, _lib.NAV_W), torch.float64),
         )
         s = self._st
         self.batch = _lib.AuvBatch(
             N, mw, self.env_offset, 0, s["scn_id"].data_ptr(), s["episode"].data_ptr(), s["state"].data_ptr(),
             s["step_counter"].data_ptr(), s["t_step"].data_ptr(), s["cum_reward"].data_ptr(),
             s["max_progress"].data_ptr(), s["cte_sum"].data_ptr(), s["nearby_mask"].data_ptr(),
-            s["mov_pos"].data_ptr(), s["mov_disp"].data_ptr(), s["mov_counter"].data_ptr(),
+            s["mov_pos"].data_ptr(), s["mov_disp"].data_ptr(), s["mov_counter"].data_ptr(), s["nav"].data_ptr(),
         )
 
         # ---- outputs
@@ -209,12 +210,11 @@ class AUVVecEnv:
         if debug:
             self._out["lidar_dist"] = z((N, max(R, 1)), torch.float32)
             self._out["windows"] = z((N, max(K, 1), 2), torch.int32)
-            self._out["nav"] = z((N, 8), torch.float64)
         o = self._out
         ptr = lambda k: o[k].data_ptr() if k in o else None
         self.out = _lib.AuvStepOut(
             ptr("obs"), ptr("reward"), ptr("done"), ptr("collision"), ptr("reached_goal"), ptr("goal_distance"),
-            ptr("progress"), ptr("lidar_dist"), ptr("windows"), ptr("nav"), ptr("terminal_obs"), ptr("stats"),
+            ptr("progress"), ptr("lidar_dist"), ptr("windows"), ptr("terminal_obs"), ptr("stats"),
             ptr("seg_tests") if debug else None,
         )
         self.actions_dev = z((N, 2), torch.float32)
@@ -330,6 +330,14 @@ class AUVVecEnv:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.auv_vessel_step(cfg, batch, C.c_void_p(a.data_ptr()), self._stream()), "auv_vessel_step")
 
+    def navigate(self):
+        """Vessel.navigate for every env -> nav record [N, 12] (s, chi, y_e, s_la, look-ahead
+        heading error, heading error, goal distance, progress, cos psi, sin psi, reached, ...)."""
+        cfg, _, paths, pool, batch = self._refs()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.auv_navigate(cfg, paths, pool, batch, self._stream()), "auv_navigate")
+        return self._st["nav"]
+
     def observe(self, mode=_lib.OBSERVE_STEP):
         cfg, rays, paths, pool, batch = self._refs()
         with torch.cuda.device(self.device):
@@ -351,6 +359,7 @@ class AUVVecEnv:
             t_step=self._st["t_step"], cumulative_reward=self._st["cum_reward"], episode=self._st["episode"],
             step_counter=self._st["step_counter"], max_progress=self._st["max_progress"], scn_id=self._st["scn_id"],
             nearby_mask=self._st["nearby_mask"], mov_pos=self._st["mov_pos"], mov_counter=self._st["mov_counter"],
+            nav=self._st["nav"],
         )
         if name in table:
             return table[name]

@@ -12,6 +12,8 @@
  *   auv_vessel_step       <- Vessel.step                        objects/vessel/vessel.py:226-247
  *                            odesolver45                        objects/vessel/odesolver.py:2-47
  *                            Vessel._state_dot                  objects/vessel/vessel.py:561-570
+ *   auv_navigate          <- Vessel.navigate                    objects/vessel/vessel.py:461-541
+ *                            Path.get_closest_arclength etc.    objects/path.py:61-93
  *   auv_observe           <- BaseEnvironment.observe            environment.py:247-290
  *                            Vessel.navigate / Vessel.perceive  vessel.py:461-541 / 249-368
  *                            find_rays_to_simulate_for_obstacles, simulate_sensor
@@ -41,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 3
+#define AUV_ABI_VERSION 4
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -55,6 +57,8 @@ extern "C" {
 #define AUV_MAX_RAYS 1024
 #define AUV_MAX_OBSTACLES 1024 /* moving + static slots per env */
 #define AUV_PATH_BLOCK 32     /* polyline segments per projection block */
+#define AUV_PATH_SUPER 32     /* blocks per projection superblock */
+#define AUV_NAV_W 12          /* doubles per env in AuvBatch.nav */
 
 /* gym_auv/config.py field names (EpisodeConfig/SimulationConfig/VesselConfig).  POD. */
 typedef struct AuvConfig {
@@ -92,8 +96,9 @@ typedef struct AuvRayTable {
 
 /* Path bank: every distinct path (objects/path.py:19-40) tabulated once; envs refer to a
  * path by id.  Polyline = the 0.1 m LineString of path.py:38-40 (FP64), its chord-length
- * prefix sums, and per 32-segment block a chord + max deviation used as an exact
- * two-level search structure for LineString.project (path.py:93).  PCHIP pieces are
+ * prefix sums, and per 32-segment block (and per 32-block superblock) a chord + max
+ * deviation used as an exact hierarchical search structure for LineString.project
+ * (path.py:93).  PCHIP pieces are
  * scipy PPoly coefficients (path.py:26). */
 typedef struct AuvPathBank {
   int32_t n_paths;
@@ -104,6 +109,9 @@ typedef struct AuvPathBank {
   const int32_t* blk_off;  /* [n_paths+1] first block of each path                      */
   const float* blk_chord;  /* [total_blocks][4] ax,ay,bx,by relative to origin[path]    */
   const float* blk_dev;    /* [total_blocks] max vertex deviation from chord + fp pad   */
+  const int32_t* sb_off;   /* [n_paths+1] first superblock (32 blocks) of each path     */
+  const float* sb_chord;   /* [total_superblocks][4]                                    */
+  const float* sb_dev;     /* [total_superblocks]                                       */
   const double* origin;    /* [n_paths][2]                                              */
   const double* knots;     /* [n_paths][n_knots]                                        */
   const double* coef;      /* [n_paths][n_knots-1][2][4]  (x: c0..c3, y: c0..c3)        */
@@ -152,6 +160,9 @@ typedef struct AuvBatch {
   double* mov_pos;        /* [N][k_moving][2]                                           */
   double* mov_disp;       /* [N][k_moving][2]                                           */
   double* mov_counter;    /* [N][k_moving]                                              */
+  double* nav;            /* [N][AUV_NAV_W] Vessel._last_navi_state_dict: s, chi, y_e, s_la,
+                             look_ahead_heading_error, heading_error, goal_distance, progress,
+                             cos psi, sin psi, reached_goal, cos(heading_error)            */
 } AuvBatch;
 
 /* Outputs of one step / observe (all optional except obs/reward/done). */
@@ -165,8 +176,6 @@ typedef struct AuvStepOut {
   float* progress;       /* [N] info["progress"]                                        */
   float* lidar_dist;     /* [N][n_sensors] or NULL: latest distance measurements        */
   int32_t* windows;      /* [N][K][2] or NULL: culling (a, b) per obstacle slot (debug) */
-  double* nav;           /* [N][8] or NULL: s, chi, y_e, s_la, la_err, head_err,
-                                          goal_dist, progress (FP64, debug/parity)      */
   float* terminal_obs;   /* [N][obs_dim] or NULL: last obs of a finished episode        */
   double* stats;         /* [AUV_N_STATS] or NULL: episode-statistic accumulators       */
   unsigned long long* seg_tests; /* [1] or NULL: reference-semantics ray/segment tests  */
@@ -200,6 +209,9 @@ int auv_obstacle_update(const AuvConfig* cfg, const AuvScenarioPool* pool, AuvBa
                         void* stream);
 int auv_vessel_step(const AuvConfig* cfg, AuvBatch* batch, const float* actions /*[N][2]*/,
                     void* stream);
+/* Vessel.navigate for every env (fills AuvBatch.nav / max_progress); auv_observe calls it. */
+int auv_navigate(const AuvConfig* cfg, const AuvPathBank* paths, const AuvScenarioPool* pool,
+                 AuvBatch* batch, void* stream);
 int auv_observe(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                 const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode,
                 void* stream);
@@ -217,6 +229,17 @@ int auv_step_host(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBa
                   const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
                   float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
                   uint8_t* done_host, void* stream);
+/* Per-kernel CUDA-event timing of a step on the launching stream (used by bench.py for the
+ * roofline of the dominant kernel).  A timer holds `capacity` slots of 4 events. */
+typedef struct AuvTimer AuvTimer;
+AuvTimer* auv_timer_create(int capacity);
+void auv_timer_destroy(AuvTimer* t);
+/* auv_step with events recorded around k_obstacle_update, k_vessel_nav and k_observe. */
+int auv_step_timed(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                   const AuvScenarioPool* pool, AuvBatch* batch, const float* actions,
+                   AuvStepOut* out, void* stream, AuvTimer* t, int slot);
+/* after the stream is synchronised: ms[0..2] = obstacle_update, vessel_nav, observe */
+int auv_timer_read(AuvTimer* t, int slot, float* ms);
 /* Measured FP32 FMA peak helper (roofline denominator): runs `iters` dependent FMAs per
  * thread on a full grid; the caller times it with CUDA events. Returns flop count. */
 int auv_fma_probe(float* sink, int blocks, int threads, int iters, void* stream,
