@@ -272,6 +272,8 @@ def run_ours(args):
     kernel_ms = {"k_obstacle_update": float(kms[:, 0].mean()), "k_vessel_nav": float(kms[:, 1].mean()),
                  "k_observe": float(kms[:, 2].mean())}
     obs_ms = kernel_ms["k_observe"]
+    kernel_ms["k_observe_min_med_max"] = [float(kms[:, 2].min()), float(np.median(kms[:, 2])), float(kms[:, 2].max())]
+    kernel_ms["k_observe_per_step"] = [round(float(x), 4) for x in kms[:, 2]]
     t_local = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)

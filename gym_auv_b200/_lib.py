@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
-ABI_VERSION = 4
+ABI_VERSION = 5
 NAV_W = 12
 N_STATS = 16
 STAT_NAMES = [
@@ -59,7 +59,7 @@ class AuvConfig(C.Structure):
 
 
 class AuvRayTable(C.Structure):
-    _fields_ = [("cos_sin", _vp), ("weight", _vp), ("sector", _vp), ("weight_sum", C.c_double)]
+    _fields_ = [("cos_sin", _vp), ("weight", _vp), ("sector", _vp), ("unit64", _vp), ("weight_sum", C.c_double)]
 
 
 class AuvPathBank(C.Structure):

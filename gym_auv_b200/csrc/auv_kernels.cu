@@ -271,22 +271,44 @@ __device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid,
   const float4* sbc = reinterpret_cast<const float4*>(pb.sb_chord) + s0;
   const float* sbd = pb.sb_dev + s0;
   const float up = 1.f + 4e-6f, dn = 1.f - 4e-6f;
+  // All node loops below issue their loads in groups of U before any arithmetic, so a
+  // thread has U independent L2 requests in flight instead of one (the kernel is bound by
+  // load latency, not by FP64 issue: profiles/r1b).
+  constexpr int U = 8;
   float ub = INFINITY;
-  for (int sb = 0; sb < nsb; ++sb) {
-    const float4 ch = sbc[sb];
-    ub = fminf(ub, pt_seg_dist_f(qx, qy, ch.x, ch.y, ch.z, ch.w) * up + sbd[sb] + pad);
+  for (int g0 = 0; g0 < nsb; g0 += U) {
+    float4 ch[U];
+    float dv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = min(g0 + u, nsb - 1);
+      ch[u] = sbc[i];
+      dv[u] = sbd[i];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      ub = fminf(ub, pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * up + dv[u] + pad);
   }
   // pass B: tighten over blocks of surviving superblocks; remember which survive
   unsigned long long live = 0ull;  // up to 64 superblocks tracked exactly, the rest are always visited
   for (int sb = 0; sb < nsb; ++sb) {
-    const float4 ch = sbc[sb];
-    const float lb = pt_seg_dist_f(qx, qy, ch.x, ch.y, ch.z, ch.w) * dn - sbd[sb] - pad;
+    const float4 c0 = sbc[sb];
+    const float lb = pt_seg_dist_f(qx, qy, c0.x, c0.y, c0.z, c0.w) * dn - sbd[sb] - pad;
     if (lb > ub) continue;
     if (sb < 64) live |= 1ull << sb;
-    const int be = min(nblk, (sb + 1) * 32);
-    for (int b = sb * 32; b < be; ++b) {
-      const float4 c4 = chord[b];
-      ub = fminf(ub, pt_seg_dist_f(qx, qy, c4.x, c4.y, c4.z, c4.w) * up + dev[b] + pad);
+    const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
+    for (int g0 = sb * AUV_PATH_SUPER; g0 < be; g0 += U) {
+      float4 ch[U];
+      float dv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = min(g0 + u, be - 1);
+        ch[u] = chord[i];
+        dv[u] = dev[i];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        ub = fminf(ub, pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * up + dv[u] + pad);
     }
   }
   // pass C: exact refine
@@ -295,20 +317,40 @@ __device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid,
   int best_seg = 0;
   for (int sb = 0; sb < nsb; ++sb) {
     if (sb < 64 && !((live >> sb) & 1ull)) continue;
-    const int be = min(nblk, (sb + 1) * 32);
-    for (int b = sb * 32; b < be; ++b) {
-      const float4 c4 = chord[b];
-      if (pt_seg_dist_f(qx, qy, c4.x, c4.y, c4.z, c4.w) * dn - dev[b] - pad > ub) continue;
-      const int se = min(nseg, (b + 1) * AUV_PATH_BLOCK);
-      double2 A = poly[b * AUV_PATH_BLOCK];
-      for (int k = b * AUV_PATH_BLOCK; k < se; ++k) {
-        const double2 B = poly[k + 1];
-        const double d2 = seg_d2(px, py, A, B);
-        if (d2 < best_d2) {  // segments are visited in increasing k: strict '<' keeps the first
-          best_d2 = d2;
-          best_seg = k;
+    const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
+    for (int g0 = sb * AUV_PATH_SUPER; g0 < be; g0 += U) {
+      float4 ch[U];
+      float dv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = min(g0 + u, be - 1);
+        ch[u] = chord[i];
+        dv[u] = dev[i];
+      }
+      unsigned cand = 0u;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (g0 + u < be && pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * dn - dv[u] - pad <= ub)
+          cand |= 1u << u;
+      while (cand) {  // blocks in increasing order
+        const int b = g0 + __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int se = min(nseg, (b + 1) * AUV_PATH_BLOCK);
+        for (int k0 = b * AUV_PATH_BLOCK; k0 < se; k0 += U) {
+          double2 v[U + 1];
+#pragma unroll
+          for (int u = 0; u <= U; ++u) v[u] = poly[min(k0 + u, se)];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (k0 + u < se) {
+              const double d2 = seg_d2(px, py, v[u], v[u + 1]);
+              if (d2 < best_d2) {  // segments are visited in increasing k: strict '<' keeps the first
+                best_d2 = d2;
+                best_seg = k0 + u;
+              }
+            }
+          }
         }
-        A = B;
       }
     }
   }
@@ -386,14 +428,14 @@ __global__ void __launch_bounds__(128) k_vessel_nav(const __grid_constant__ AuvC
 // ------------------------------------------------------------------------------------
 // LiDAR
 // ------------------------------------------------------------------------------------
-constexpr int VMAX = 448;          // staged vertices per warp per batch (float2)
-constexpr int WARPS_PER_BLOCK = 8;
+constexpr int VMAX = 320;          // staged vertices per warp per batch (float2)
+#ifndef AUV_WARPS_PER_BLOCK
+#define AUV_WARPS_PER_BLOCK 4
+#endif
+constexpr int WARPS_PER_BLOCK = AUV_WARPS_PER_BLOCK;  // envs per CTA (warps never synchronise with each other)
 
 struct __align__(16) WarpScratch {
   float2 verts[VMAX];
-  double ocxd[32], ocyd[32];  // enclosing-circle centre, vessel-relative (FP64)
-  double ogeo[32];            // radius (circle) or width (vessel obstacle)
-  double ohx[32], ohy[32];    // unit heading of a vessel obstacle
   float ocx[32], ocy[32], orho[32];
   int oa[32], ob[32], ovoff[32], onv[32], oflag[32];
 };
@@ -481,6 +523,9 @@ struct ObserveArgs {
   AuvStepOut out;
   int mode;
   int obs_dim;
+  float pen_clear;  // sum_i w_i * range * exp(-0.1 range): penalty sum when every ray reads sensor_range
+  float pen_clear_ray;     // range * exp(-0.1 range)
+  double clear_closeness;  // -range * exp(-0.1 range): closeness reward with no LiDAR at all
 };
 
 // pentagon vertex k of a vessel obstacle, relative to the own-ship: base (bx,by) is the
@@ -491,13 +536,69 @@ __device__ __forceinline__ void pent_vertex(int k, double bx, double by, double 
   vy = by + w * (hy * c_pent[k][0] + hx * c_pent[k][1]);
 }
 
-#ifndef AUV_OBSERVE_MIN_BLOCKS
-#define AUV_OBSERVE_MIN_BLOCKS 4
+// Point.distance(obstacle.boundary) from the own-ship (vessel.py:269): min over the edges
+// of the polygonised circle (ring) or 0 / min over edges for the filled vessel pentagon.
+// FP32 on vessel-relative vertices formed in FP64.  Cold (only on nearby-list refresh and
+// only for obstacles whose enclosing circle straddles the range limit).
+__device__ __forceinline__ double boundary_distance(bool pent, double cx, double cy, double bx0, double by0,
+                                                 double geo, double hx, double hy, int nv_cnt,
+                                                 const double2* __restrict__ unit) {
+  float dmin = INFINITY;
+  const int ne = nv_cnt - 1;
+  double vx, vy;
+  if (pent) {
+    pent_vertex(0, bx0, by0, geo, hx, hy, vx, vy);
+  } else {
+    vx = cx + geo;
+    vy = cy;
+  }
+  float pxv = (float)vx, pyv = (float)vy;
+  bool allpos = true, allneg = true;
+  for (int k = 1; k <= ne; ++k) {
+    const int kk = (k == ne) ? 0 : k;
+    if (pent) {
+      pent_vertex(kk, bx0, by0, geo, hx, hy, vx, vy);
+    } else {
+      const double2 un = __ldg(&unit[kk * (64 / ne)]);
+      vx = cx + geo * un.x;
+      vy = cy + geo * un.y;
+    }
+    const float qx = (float)vx, qy = (float)vy;
+    dmin = fminf(dmin, pt_seg_dist_f(0.f, 0.f, pxv, pyv, qx, qy));
+    const float cr = pxv * qy - pyv * qx;  // cross(prev, cur) about the vessel
+    allpos = allpos && (cr >= 0.f);
+    allneg = allneg && (cr <= 0.f);
+    pxv = qx;
+    pyv = qy;
+  }
+  const bool inside = pent && (allpos || allneg);
+  return inside ? 0.0 : (double)dmin;
+}
+
+// is the own-ship (origin) inside the convex vessel pentagon?  FP64.
+__device__ __forceinline__ bool vessel_inside_pentagon(double bx0, double by0, double geo, double hx, double hy) {
+  bool allpos = true, allneg = true;
+  double pvx, pvy, vx, vy;
+  pent_vertex(4, bx0, by0, geo, hx, hy, pvx, pvy);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    pent_vertex(k, bx0, by0, geo, hx, hy, vx, vy);
+    const double cr = pvx * vy - pvy * vx;
+    allpos = allpos && (cr >= 0.0);
+    allneg = allneg && (cr <= 0.0);
+    pvx = vx;
+    pvy = vy;
+  }
+  return allpos || allneg;
+}
+
+#ifndef AUV_OBSERVE_WARPS_PER_SM
+#define AUV_OBSERVE_WARPS_PER_SM 20  // 96 registers/thread: spills cost more than occupancy gains (profiles/r1c)
 #endif
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_WARPS_PER_SM / WARPS_PER_BLOCK)
     k_observe(const __grid_constant__ ObserveArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double s_unit[64][2];  // cos/sin(2 pi k / 64)
+  const double2* __restrict__ s_unit = reinterpret_cast<const double2*>(A.rays.unit64);  // cos/sin(2 pi k/64)
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int R = A.cfg.n_sensors;
@@ -505,13 +606,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
   const size_t per_warp = sizeof(WarpScratch) + sizeof(float) * rpad;
   WarpScratch& W = *reinterpret_cast<WarpScratch*>(smem_raw + per_warp * wib);
   float* sdist = reinterpret_cast<float*>(smem_raw + per_warp * wib + sizeof(WarpScratch));
-  if (threadIdx.x < 64) {
-    double s, c;
-    sincospi((double)threadIdx.x / 32.0, &s, &c);
-    s_unit[threadIdx.x][0] = c;
-    s_unit[threadIdx.x][1] = s;
-  }
-  __syncthreads();
   const int e = blockIdx.x * WARPS_PER_BLOCK + wib;
   const int n = A.batch.n_envs;
   if (e >= n) return;
@@ -525,15 +619,26 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
   int mode = A.mode;
 
   for (int pass = 0; pass < 2; ++pass) {
-    const int scn = batch.scn_id[e];
-    // navigation record written by k_vessel_nav (or by lane 0 below after an auto-reset)
-    double navv = 0.0;
+    // Every per-env scalar is fetched up front by a different lane (three independent
+    // 1-sector loads in flight together) and broadcast by shuffle when needed:
+    //   navv: lanes 0..11 = navigation record written by k_vessel_nav (or by lane 0 below
+    //         after an auto-reset);  stv: lanes 0..5 = x, y, psi, u, v, r;
+    //   auxv: lane 0 cum_reward, 1 cte_sum, 2 max_progress, 3 t_step, 4 step_counter, 5 scn_id
+    double navv = 0.0, stv = 0.0, auxv = 0.0;
     if (lane < AUV_NAV_W) navv = batch.nav[(long long)e * AUV_NAV_W + lane];
-    double stv = 0.0;  // lanes 0..5: x, y, psi, u, v, r
     if (lane < 6) stv = batch.state[(long long)lane * n + e];
+    if (lane == 0) auxv = batch.cum_reward[e];
+    if (lane == 1) auxv = batch.cte_sum[e];
+    if (lane == 2) auxv = batch.max_progress[e];
+    if (lane == 3) auxv = (double)batch.t_step[e];
+    if (lane == 4) auxv = (double)batch.step_counter[e];
+    if (lane == 5) auxv = (double)batch.scn_id[e];
+    unsigned mask0 = 0u;  // first word of the nearby list (covers K <= 32, the common case)
+    if (cfg.use_lidar) mask0 = batch.nearby_mask[(long long)e * batch.mask_words];
+    const int scn = (int)__shfl_sync(AUV_FULL, auxv, 5);
     const double px = __shfl_sync(AUV_FULL, stv, 0), py = __shfl_sync(AUV_FULL, stv, 1);
     const double psi = __shfl_sync(AUV_FULL, stv, 2);
-    const int step_counter = batch.step_counter[e];
+    const int step_counter = (int)__shfl_sync(AUV_FULL, auxv, 4);
 
     float* obs = A.out.obs + (long long)e * A.obs_dim;
     bool collision = false;
@@ -543,13 +648,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
     if (cfg.use_lidar) {
       // ---------------- perceive ----------------
       const bool refresh = (step_counter % cfg.sensor_interval_load_obstacles) == 0;
+      const double dth_d = 2.0 * AUV_PI / (double)R;
       const double cpsi = __shfl_sync(AUV_FULL, navv, NAV_COSPSI), spsi = __shfl_sync(AUV_FULL, navv, NAV_SINPSI);
       bool any_active = false;
       for (int base = 0; base < K; base += 32) {
         const int j = base + lane;
         unsigned word = 0u;
         if (!refresh) {
-          word = batch.nearby_mask[(long long)e * batch.mask_words + (base >> 5)];
+          word = base == 0 ? mask0 : batch.nearby_mask[(long long)e * batch.mask_words + (base >> 5)];
           if (word == 0u) {
             if (A.out.windows != nullptr && j < K)
               reinterpret_cast<int2*>(A.out.windows)[(long long)e * K + j] = make_int2(0, 0);
@@ -609,39 +715,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
             const double dc = sqrt(cx * cx + cy * cy);
             if (dc - rho - cfg.vessel_width >= range + 1e-6) {
               near = false;  // boundary lies inside the circle: distance >= dc - rho
-            } else if (pent && dc + rho - cfg.vessel_width < range - 1e-6) {
-              near = true;  // filled polygon: distance <= dc + rho
+            } else if (dc + rho - cfg.vessel_width < range - 1e-6) {
+              near = true;  // the boundary lies inside the circle: distance <= dc + rho
             } else {
-              float dmin = INFINITY;
-              const int ne = nv_cnt - 1;
-              double vx, vy;
-              if (pent) {
-                pent_vertex(0, bx0, by0, geo, hx, hy, vx, vy);
-              } else {
-                vx = cx + geo;
-                vy = cy;
-              }
-              float pxv = (float)vx, pyv = (float)vy;
-              bool allpos = true, allneg = true;
-              for (int k = 1; k <= ne; ++k) {
-                const int kk = (k == ne) ? 0 : k;
-                if (pent) {
-                  pent_vertex(kk, bx0, by0, geo, hx, hy, vx, vy);
-                } else {
-                  const int ui = kk * (64 / ne);
-                  vx = cx + geo * s_unit[ui][0];
-                  vy = cy + geo * s_unit[ui][1];
-                }
-                const float qx = (float)vx, qy = (float)vy;
-                dmin = fminf(dmin, pt_seg_dist_f(0.f, 0.f, pxv, pyv, qx, qy));
-                const float cr = pxv * qy - pyv * qx;  // cross(prev, cur) about the vessel
-                allpos = allpos && (cr >= 0.f);
-                allneg = allneg && (cr <= 0.f);
-                pxv = qx;
-                pyv = qy;
-              }
-              const bool inside = pent && (allpos || allneg);
-              const double dist = inside ? 0.0 : (double)dmin;
+              const double dist = boundary_distance(pent, cx, cy, bx0, by0, geo, hx, hy, nv_cnt, s_unit);
               near = (dist - cfg.vessel_width) < range;  // vessel.py:269-270
             }
           }
@@ -657,20 +734,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
           cull_bounds(cx, cy, rho, psi, R, lo, hi);
           window_from_bounds(lo, hi, R, cfg.cull_mode, wa, wb, allrays);
           if (pent && cx * cx + cy * cy <= rho * rho) {
-            // filled polygon: is the vessel inside?  (range 0)
-            bool allpos = true, allneg = true;
-            double pvx, pvy, vx, vy;
-            pent_vertex(4, bx0, by0, geo, hx, hy, pvx, pvy);
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-              pent_vertex(k, bx0, by0, geo, hx, hy, vx, vy);
-              const double cr = pvx * vy - pvy * vx;
-              allpos = allpos && (cr >= 0.0);
-              allneg = allneg && (cr <= 0.0);
-              pvx = vx;
-              pvy = vy;
-            }
-            inside = allpos || allneg;
+            inside = vessel_inside_pentagon(bx0, by0, geo, hx, hy);  // range 0, SURVEY A.5
           }
         }
         if (A.out.windows != nullptr && j < K) {
@@ -693,11 +757,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
           const int nact = __popc(tk);
           if (take) {
             const int ci = __popc(tk & ((1u << lane) - 1u));
-            W.ocxd[ci] = pent ? bx0 : cx;  // pentagon: rotation centre; circle: centre
-            W.ocyd[ci] = pent ? by0 : cy;
-            W.ogeo[ci] = geo;
-            W.ohx[ci] = hx;
-            W.ohy[ci] = hy;
             W.ocx[ci] = (float)cx;
             W.ocy[ci] = (float)cy;
             W.orho[ci] = (float)rho;
@@ -710,24 +769,34 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
           }
           rem &= ~tk;
           __syncwarp();
-          // vertices: vessel-relative, formed in FP64, stored FP32
-          for (int i = 0; i < nact; ++i) {
-            const int nvv = W.onv[i], off = W.ovoff[i];
-            const double g = W.ogeo[i];
-            if (W.oflag[i] & OFLAG_PENTAGON) {
-              if (lane < 6) {
-                double vx, vy;
-                pent_vertex(lane == 5 ? 0 : lane, W.ocxd[i], W.ocyd[i], g, W.ohx[i], W.ohy[i], vx, vy);
-                W.verts[off + lane] = make_float2((float)vx, (float)vy);
+          // vertices: vessel-relative, formed in FP64, stored FP32.  The owning lane's
+          // FP64 parameters are broadcast by shuffle (no FP64 staging in shared memory).
+          {
+            const double bcx = pent ? bx0 : cx, bcy = pent ? by0 : cy;  // rotation centre | circle centre
+            unsigned todo = tk;
+            int i = 0;
+            while (todo) {
+              const int src = __ffs(todo) - 1;
+              todo &= todo - 1;
+              const double ox = __shfl_sync(AUV_FULL, bcx, src), oy = __shfl_sync(AUV_FULL, bcy, src);
+              const double g = __shfl_sync(AUV_FULL, geo, src);
+              const int nvv = W.onv[i], off = W.ovoff[i];
+              if (W.oflag[i] & OFLAG_PENTAGON) {
+                const double h_x = __shfl_sync(AUV_FULL, hx, src), h_y = __shfl_sync(AUV_FULL, hy, src);
+                if (lane < 6) {
+                  double vx, vy;
+                  pent_vertex(lane == 5 ? 0 : lane, ox, oy, g, h_x, h_y, vx, vy);
+                  W.verts[off + lane] = make_float2((float)vx, (float)vy);
+                }
+              } else {
+                const int ne = nvv - 1;
+                const int stride = 64 / ne;
+                for (int k = lane; k < nvv; k += 32) {
+                  const double2 un = __ldg(&s_unit[(k == ne ? 0 : k) * stride]);
+                  W.verts[off + k] = make_float2((float)(ox + g * un.x), (float)(oy + g * un.y));
+                }
               }
-            } else {
-              const int ne = nvv - 1;
-              const int stride = 64 / ne;
-              for (int k = lane; k < nvv; k += 32) {
-                const int ui = (k == ne ? 0 : k) * stride;
-                W.verts[off + k] = make_float2((float)(W.ocxd[i] + g * s_unit[ui][0]),
-                                               (float)(W.ocyd[i] + g * s_unit[ui][1]));
-              }
+              ++i;
             }
           }
           __syncwarp();
@@ -738,6 +807,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
               const double2 cs = reinterpret_cast<const double2*>(A.rays.cos_sin)[i];
               const float c = (float)(cs.x * cpsi - cs.y * spsi);
               const float s = (float)(cs.y * cpsi + cs.x * spsi);
+              const float theta = (float)((-AUV_PI + (double)(i + 1) * dth_d) + psi);  // world angle of ray i
               float best = sdist[i];
               for (int o = 0; o < nact; ++o) {
                 const int oa = W.oa[o], ob = W.ob[o], fl = W.oflag[o];
@@ -758,6 +828,36 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
                 const float slack = rho * 1e-5f + 1e-4f;
                 if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > best) continue;
                 const float2* vp = W.verts + W.ovoff[o];
+                if (!(fl & OFLAG_PENTAGON) && nvv > 16) {
+                  // Regular n-gon inscribed in the enclosing circle (n = 16/32/64): the ray's
+                  // line meets the circle at polar angles theta+g and theta+pi-g (g =
+                  // asin(-hc/r)); between circle and polygon lies the circular segment of
+                  // exactly one edge, so the polygon crossing is on the edge whose angular span
+                  // contains that angle.  The neighbour on the nearer side is tested too, which
+                  // absorbs the FP32 error of asinf near grazing incidence.
+                  const int nn = nvv - 1;
+                  const float g = asinf(fminf(fmaxf(-hc / rho, -1.f), 1.f));
+                  const float invd = (float)nn * 0.15915494309189535f;
+#pragma unroll
+                  for (int sol = 0; sol < 2; ++sol) {
+                    const float p = (sol == 0 ? theta + g : theta + 3.14159265358979f - g) * invd;
+                    const float kf = floorf(p);
+                    const int k0 = (int)kf & (nn - 1);
+                    const int k1 = (p - kf < 0.5f ? k0 - 1 : k0 + 1) & (nn - 1);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                      const int k = q == 0 ? k0 : k1;
+                      const float2 va = vp[k], vb = vp[k + 1];
+                      const float ya = va.y * c - va.x * s, yb = vb.y * c - vb.x * s;
+                      if ((ya <= 0.f && yb >= 0.f) || (ya >= 0.f && yb <= 0.f)) {
+                        const float xa = va.x * c + va.y * s, xb = vb.x * c + vb.y * s;
+                        const float t = xa + (xb - xa) * (ya / (ya - yb));
+                        if (t >= 0.f && t <= rangef) best = fminf(best, t);
+                      }
+                    }
+                  }
+                  continue;
+                }
                 float2 v = vp[0];
                 float xp = v.x * c + v.y * s;
                 float yp = v.y * c - v.x * s;
@@ -786,25 +886,29 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
           obs[6 + i] = 0.f;
           if (A.out.lidar_dist != nullptr) A.out.lidar_dist[(long long)e * R + i] = rangef;
         }
-        pen_sum = (float)(A.rays.weight_sum * range * exp(-0.1 * range));
+        pen_sum = A.pen_clear;
       } else {
         const float inv_log = 1.f / log1pf(rangef);
         for (int i0 = 0; i0 < R; i0 += 32) {
           const int i = i0 + lane;
           if (i < R) {
             const float d = sdist[i];
+            const float w = A.rays.weight[i];
             float cl;
             if (d >= rangef) {
               cl = 0.f;  // 1 - log(1+range)/log(1+range) is exactly 0 in the reference
-            } else if (cfg.sensor_log_transform) {
-              cl = 1.f - fminf(fmaxf(log1pf(d) * inv_log, 0.f), 1.f);
+              pen_sum += w * A.pen_clear_ray;  // range * exp(-0.1 range), no transcendental
             } else {
-              cl = 1.f - fminf(fmaxf(d / rangef, 0.f), 1.f);
+              if (cfg.sensor_log_transform) {
+                cl = 1.f - fminf(fmaxf(log1pf(d) * inv_log, 0.f), 1.f);
+              } else {
+                cl = 1.f - fminf(fmaxf(d / rangef, 0.f), 1.f);
+              }
+              pen_sum += w * rangef * __expf(-0.1f * d);
             }
             obs[6 + i] = fminf(fmaxf(cl, -1.f), 1.f);
             if (A.out.lidar_dist != nullptr) A.out.lidar_dist[(long long)e * R + i] = d;
             collision = collision || (d < widthf);
-            pen_sum += A.rays.weight[i] * rangef * __expf(-0.1f * d);
           }
         }
         collision = __any_sync(AUV_FULL, collision);
@@ -849,7 +953,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
     const double vr = __shfl_sync(AUV_FULL, stv, 5);
     const double y_e = __shfl_sync(AUV_FULL, navv, NAV_YE);
     const double cos_he = __shfl_sync(AUV_FULL, navv, NAV_COS_HEAD_ERR);
-    const double maxprog = batch.max_progress[e];  // already includes this step (k_vessel_nav)
+    const double maxprog = __shfl_sync(AUV_FULL, auxv, 2);  // already includes this step (k_vessel_nav)
     const double speed = sqrt(vu * vu + vv * vv);
     double reward;
     if (collision) {
@@ -861,7 +965,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
       if (cfg.rewarder == AUV_REWARDER_COLAV) {
         // without LiDAR every ray keeps its reset value sensor_range (vessel.py:206-208)
         const double closeness_reward =
-            cfg.use_lidar ? -(double)pen_sum / A.rays.weight_sum : -range * exp(-0.1 * range);
+            cfg.use_lidar ? -(double)pen_sum / A.rays.weight_sum : A.clear_closeness;
         if (progress < maxprog) path_reward = fmin(path_reward, 0.0);
         const double slow = speed < 0.04 ? -2.0 : 0.0;
         reward = 0.5 * path_reward + 0.5 * closeness_reward - living - 10.0 * fabs(vr) + slow;
@@ -871,12 +975,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_MIN_BLOCKS)
         reward = path_reward - living - 10.0 * fabs(vr) + slow;
       }
     }
-    const double cum = batch.cum_reward[e] + reward;
-    const int t_step = batch.t_step[e];
+    const double cum = __shfl_sync(AUV_FULL, auxv, 0) + reward;
+    const int t_step = (int)__shfl_sync(AUV_FULL, auxv, 3);
     const bool done = collision || reached ||
                       (!cfg.test_mode && t_step >= cfg.max_timesteps - 1) ||
                       (!cfg.test_mode && cum < cfg.min_cumulative_reward);
-    const double cte_sum = batch.cte_sum[e] + fabs(y_e);
+    const double cte_sum = __shfl_sync(AUV_FULL, auxv, 1) + fabs(y_e);
     if (lane == 0) {
       batch.cum_reward[e] = cum;
       batch.t_step[e] = t_step + 1;
@@ -1050,7 +1154,7 @@ static int check_observe_args(const AuvConfig* cfg, const AuvRayTable* rays, con
 
 static int launch_vessel_nav(const AuvConfig* cfg, const AuvPathBank* paths, const AuvScenarioPool* pool,
                              AuvBatch* batch, const float* actions, void* stream) {
-  const int threads = 128;
+  const int threads = 64;  // small CTAs: 65536 envs are only ~7 CTAs per SM, balance matters
   const int blocks = (batch->n_envs + threads - 1) / threads;
   if (actions)
     auv::k_vessel_nav<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, actions);
@@ -1071,6 +1175,9 @@ static int launch_observe(const AuvConfig* cfg, const AuvRayTable* rays, const A
   args.out = *out;
   args.mode = mode;
   args.obs_dim = auv_obs_dim(cfg);
+  args.pen_clear = (float)((rays ? rays->weight_sum : 1.0) * cfg->sensor_range * exp(-0.1 * cfg->sensor_range));
+  args.clear_closeness = -cfg->sensor_range * exp(-0.1 * cfg->sensor_range);
+  args.pen_clear_ray = (float)(-args.clear_closeness);
   const int rpad = cfg->use_lidar ? ((cfg->n_sensors + 31) & ~31) : 32;
   const size_t smem = (sizeof(auv::WarpScratch) + sizeof(float) * rpad) * auv::WARPS_PER_BLOCK;
   static size_t configured = 0;

@@ -125,10 +125,14 @@ class AUVVecEnv:
 
         # ---- ray table
         self.sensor_angles, cos_sin, weight, wsum, sector = ray_table(R, int(self.config.vessel.n_sectors))
-        self._ray = dict(cos_sin=t(cos_sin, torch.float64), weight=t(weight, torch.float32), sector=t(sector, torch.uint8))
+        k64 = np.arange(64) * (2 * np.pi / 64)
+        unit64 = np.stack([np.cos(k64), np.sin(k64)], axis=1)
+        unit64[np.abs(unit64) < 1e-15] = 0.0
+        self._ray = dict(cos_sin=t(cos_sin, torch.float64), weight=t(weight, torch.float32),
+                         sector=t(sector, torch.uint8), unit64=t(unit64, torch.float64))
         self.sector_index = sector
         self.rays = _lib.AuvRayTable(
-            self._ray["cos_sin"].data_ptr(), self._ray["weight"].data_ptr(), self._ray["sector"].data_ptr(), wsum
+            self._ray["cos_sin"].data_ptr(), self._ray["weight"].data_ptr(), self._ray["sector"].data_ptr(), self._ray["unit64"].data_ptr(), wsum
         )
 
         # ---- path bank

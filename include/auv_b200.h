@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 4
+#define AUV_ABI_VERSION 5
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -91,6 +91,8 @@ typedef struct AuvRayTable {
   const double* cos_sin; /* [n_sensors][2]  cos/sin of body angle -pi+(i+1)*2pi/R       */
   const float* weight;   /* [n_sensors]     1/(1+|10*angle_i|)                          */
   const uint8_t* sector; /* [n_sensors]     sector index of ray i                       */
+  const double* unit64;  /* [64][2] cos/sin(2 pi k / 64): vertices of buffer(r) (quadsegs 16,
+                            obstacles.py:101-106)                                          */
   double weight_sum;     /* sum_i weight[i] (FP64, sequential order)                    */
 } AuvRayTable;
 
