@@ -384,10 +384,17 @@ def run_ours(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version
+    # banner, torchrun children) are diverted to stderr for the whole run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

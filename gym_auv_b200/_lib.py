@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
-ABI_VERSION = 5
+ABI_VERSION = 6
 NAV_W = 12
 N_STATS = 16
 STAT_NAMES = [
@@ -88,7 +88,7 @@ class AuvScenarioPool(C.Structure):
         ("n_scenarios", C.c_int32),
         ("k_moving", C.c_int32),
         ("k_static", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("n_world", C.c_int32),
         ("path_id", _vp),
         ("vessel_init", _vp),
         ("mov_start", _vp),
@@ -100,6 +100,9 @@ class AuvScenarioPool(C.Structure):
         ("vel_table", _vp),
         ("st_pos", _vp),
         ("st_radius", _vp),
+        ("world_circle", _vp),
+        ("world_voff", _vp),
+        ("world_verts", _vp),
     ]
 
 

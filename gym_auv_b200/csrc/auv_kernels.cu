@@ -443,6 +443,7 @@ struct __align__(16) WarpScratch {
 #define OFLAG_INSIDE 2
 #define OFLAG_ALLRAYS 4
 #define OFLAG_PENTAGON 8
+#define OFLAG_WORLD 16
 
 // body-frame pentagon of VesselObstacle relative to its area centroid (5w/18, 0), in
 // units of w     obstacles.py:175-181
@@ -536,6 +537,29 @@ __device__ __forceinline__ void pent_vertex(int k, double bx, double by, double 
   vy = by + w * (hy * c_pent[k][0] + hx * c_pent[k][1]);
 }
 
+// ---- shared static world polygons (PolygonObstacle, obstacles.py:116-127): FILLED.
+// distance from the own-ship to the filled polygon / crossing-number inside test, on
+// vessel-relative FP32 vertices formed in FP64.  Cold (nearby refresh / own-ship within
+// the enclosing circle only).
+__device__ __forceinline__ double world_polygon_distance(const double2* __restrict__ v, int nv, double px,
+                                                         double py, bool& inside) {
+  float dmin = INFINITY;
+  bool in = false;
+  float ax = (float)(v[0].x - px), ay = (float)(v[0].y - py);
+  for (int k = 1; k < nv; ++k) {
+    const float bx = (float)(v[k].x - px), by = (float)(v[k].y - py);
+    dmin = fminf(dmin, pt_seg_dist_f(0.f, 0.f, ax, ay, bx, by));
+    if ((ay > 0.f) != (by > 0.f)) {  // edge straddles the +x axis through the own-ship
+      const float xint = ax + (0.f - ay) * (bx - ax) / (by - ay);
+      if (xint > 0.f) in = !in;
+    }
+    ax = bx;
+    ay = by;
+  }
+  inside = in;
+  return in ? 0.0 : (double)dmin;
+}
+
 // Point.distance(obstacle.boundary) from the own-ship (vessel.py:269): min over the edges
 // of the polygonised circle (ring) or 0 / min over edges for the filled vessel pentagon.
 // FP32 on vessel-relative vertices formed in FP64.  Cold (only on nearby-list refresh and
@@ -613,6 +637,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_WARPS_PER_SM
   const AuvScenarioPool& pool = A.pool;
   const AuvConfig& cfg = A.cfg;
   const int km = pool.k_moving, ks = pool.k_static, K = km + ks;
+  const int S = K + pool.n_world;  // obstacle slots: moving, static circles, shared world polygons
   const double range = cfg.sensor_range;
   const float rangef = (float)range;
   const float widthf = (float)cfg.vessel_width;
@@ -633,8 +658,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_WARPS_PER_SM
     if (lane == 3) auxv = (double)batch.t_step[e];
     if (lane == 4) auxv = (double)batch.step_counter[e];
     if (lane == 5) auxv = (double)batch.scn_id[e];
-    unsigned mask0 = 0u;  // first word of the nearby list (covers K <= 32, the common case)
-    if (cfg.use_lidar) mask0 = batch.nearby_mask[(long long)e * batch.mask_words];
+    unsigned maskv = 0u;  // lane w holds word w of the nearby list (<= 32 words = 1024 slots)
+    if (cfg.use_lidar && lane < batch.mask_words) maskv = batch.nearby_mask[(long long)e * batch.mask_words + lane];
     const int scn = (int)__shfl_sync(AUV_FULL, auxv, 5);
     const double px = __shfl_sync(AUV_FULL, stv, 0), py = __shfl_sync(AUV_FULL, stv, 1);
     const double psi = __shfl_sync(AUV_FULL, stv, 2);
@@ -651,25 +676,36 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_WARPS_PER_SM
       const double dth_d = 2.0 * AUV_PI / (double)R;
       const double cpsi = __shfl_sync(AUV_FULL, navv, NAV_COSPSI), spsi = __shfl_sync(AUV_FULL, navv, NAV_SINPSI);
       bool any_active = false;
-      for (int base = 0; base < K; base += 32) {
+      for (int base = 0; base < S; base += 32) {
         const int j = base + lane;
         unsigned word = 0u;
         if (!refresh) {
-          word = base == 0 ? mask0 : batch.nearby_mask[(long long)e * batch.mask_words + (base >> 5)];
+          word = __shfl_sync(AUV_FULL, maskv, base >> 5);
           if (word == 0u) {
-            if (A.out.windows != nullptr && j < K)
-              reinterpret_cast<int2*>(A.out.windows)[(long long)e * K + j] = make_int2(0, 0);
+            if (A.out.windows != nullptr && j < S)
+              reinterpret_cast<int2*>(A.out.windows)[(long long)e * S + j] = make_int2(0, 0);
             continue;  // nothing of this chunk is on the nearby list: no loads at all
           }
         }
         // only obstacles that are (or may become) nearby are loaded
-        const bool want = j < K && (refresh || ((word >> lane) & 1u));
+        const bool want = j < S && (refresh || ((word >> lane) & 1u));
         bool valid = false;
-        bool pent = false;
+        bool pent = false, world = false;
         double cx = 0, cy = 0, rho = 0, geo = 0, hx = 1.0, hy = 0.0;
         int nv_cnt = 0;  // vertices incl. closing one
+        int vbase = 0;   // world polygon: first vertex
         if (want) {
-          if (j < km) {
+          if (j >= K) {
+            const int wi = j - K;
+            const double* c3 = pool.world_circle + 3ll * wi;
+            vbase = pool.world_voff[wi];
+            nv_cnt = pool.world_voff[wi + 1] - vbase;
+            valid = nv_cnt >= 4;
+            world = true;
+            cx = c3[0] - px;
+            cy = c3[1] - py;
+            rho = c3[2];
+          } else if (j < km) {
             const long long ps = (long long)scn * km + j, pe = (long long)e * km + j;
             const double w = pool.mov_width[ps];
             const double2 pos = reinterpret_cast<const double2*>(batch.mov_pos)[pe];
@@ -718,7 +754,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_WARPS_PER_SM
             } else if (dc + rho - cfg.vessel_width < range - 1e-6) {
               near = true;  // the boundary lies inside the circle: distance <= dc + rho
             } else {
-              const double dist = boundary_distance(pent, cx, cy, bx0, by0, geo, hx, hy, nv_cnt, s_unit);
+              bool in_dummy;
+              const double dist =
+                  world ? world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + vbase, nv_cnt,
+                                                 px, py, in_dummy)
+                        : boundary_distance(pent, cx, cy, bx0, by0, geo, hx, hy, nv_cnt, s_unit);
               near = (dist - cfg.vessel_width) < range;  // vessel.py:269-270
             }
           }
@@ -735,11 +775,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_WARPS_PER_SM
           window_from_bounds(lo, hi, R, cfg.cull_mode, wa, wb, allrays);
           if (pent && cx * cx + cy * cy <= rho * rho) {
             inside = vessel_inside_pentagon(bx0, by0, geo, hx, hy);  // range 0, SURVEY A.5
+          } else if (world && cx * cx + cy * cy <= rho * rho) {
+            world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + vbase, nv_cnt, px, py, inside);
           }
         }
-        if (A.out.windows != nullptr && j < K) {
+        if (A.out.windows != nullptr && j < S) {
           int2 wv = active ? make_int2(wa, wb) : make_int2(0, 0);
-          reinterpret_cast<int2*>(A.out.windows)[(long long)e * K + j] = wv;
+          reinterpret_cast<int2*>(A.out.windows)[(long long)e * S + j] = wv;
         }
 
         // ---- stage active obstacles in batches bounded by the vertex budget
@@ -764,8 +806,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_WARPS_PER_SM
             W.ob[ci] = wb;
             W.ovoff[ci] = incl - cnt;
             W.onv[ci] = nv_cnt;
-            W.oflag[ci] = (pent ? (OFLAG_FILLED | OFLAG_PENTAGON) : 0) | (inside ? OFLAG_INSIDE : 0) |
-                          (allrays ? OFLAG_ALLRAYS : 0);
+            W.oflag[ci] = (pent ? (OFLAG_FILLED | OFLAG_PENTAGON) : 0) | (world ? (OFLAG_FILLED | OFLAG_WORLD) : 0) |
+                          (inside ? OFLAG_INSIDE : 0) | (allrays ? OFLAG_ALLRAYS : 0);
           }
           rem &= ~tk;
           __syncwarp();
@@ -781,7 +823,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_WARPS_PER_SM
               const double ox = __shfl_sync(AUV_FULL, bcx, src), oy = __shfl_sync(AUV_FULL, bcy, src);
               const double g = __shfl_sync(AUV_FULL, geo, src);
               const int nvv = W.onv[i], off = W.ovoff[i];
-              if (W.oflag[i] & OFLAG_PENTAGON) {
+              if (W.oflag[i] & OFLAG_WORLD) {
+                const int vb = __shfl_sync(AUV_FULL, vbase, src);
+                const double2* wv = reinterpret_cast<const double2*>(pool.world_verts) + vb;
+                for (int k = lane; k < nvv; k += 32) {
+                  const double2 q = wv[k];
+                  W.verts[off + k] = make_float2((float)(q.x - px), (float)(q.y - py));
+                }
+              } else if (W.oflag[i] & OFLAG_PENTAGON) {
                 const double h_x = __shfl_sync(AUV_FULL, hx, src), h_y = __shfl_sync(AUV_FULL, hy, src);
                 if (lane < 6) {
                   double vx, vy;
@@ -828,7 +877,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_WARPS_PER_SM
                 const float slack = rho * 1e-5f + 1e-4f;
                 if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > best) continue;
                 const float2* vp = W.verts + W.ovoff[o];
-                if (!(fl & OFLAG_PENTAGON) && nvv > 16) {
+                if (!(fl & (OFLAG_PENTAGON | OFLAG_WORLD)) && nvv > 16) {
                   // Regular n-gon inscribed in the enclosing circle (n = 16/32/64): the ray's
                   // line meets the circle at polar angles theta+g and theta+pi-g (g =
                   // asin(-hc/r)); between circle and polygon lies the circular segment of
@@ -1145,10 +1194,13 @@ static int check_observe_args(const AuvConfig* cfg, const AuvRayTable* rays, con
   if (mode == AUV_OBSERVE_STEP && (!out->reward || !out->done))
     return set_err(AUV_EINVAL, "out.reward/out.done is NULL");
   if (batch->n_envs <= 0) return set_err(AUV_EINVAL, "n_envs must be > 0");
-  if (pool->k_moving + pool->k_static > AUV_MAX_OBSTACLES)
+  if (pool->n_world < 0) return set_err(AUV_EINVAL, "n_world < 0");
+  if (pool->k_moving + pool->k_static + pool->n_world > AUV_MAX_OBSTACLES)
     return set_err(AUV_EINVAL, "too many obstacle slots");
-  if (batch->mask_words * 32 < pool->k_moving + pool->k_static)
-    return set_err(AUV_EINVAL, "mask_words too small");
+  if (batch->mask_words * 32 < pool->k_moving + pool->k_static + pool->n_world || batch->mask_words > 32)
+    return set_err(AUV_EINVAL, "mask_words must cover all slots and be <= 32");
+  if (pool->n_world > 0 && (!pool->world_circle || !pool->world_voff || !pool->world_verts))
+    return set_err(AUV_EINVAL, "world arrays are NULL");
   return 0;
 }
 

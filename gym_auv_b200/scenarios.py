@@ -41,7 +41,9 @@ class ScenarioSet:
     rewarder: str = "colav"
     post_generate_update: bool = False  # scenario's _generate() ends with self._update()
     name: str = ""
+    world_polygons: List[np.ndarray] = field(default_factory=list)  # static land shared by all scenarios
     _bank: Optional[PathBank] = field(default=None, repr=False)
+    _world: Optional[object] = field(default=None, repr=False)
 
     @property
     def n_scenarios(self) -> int:
@@ -60,6 +62,14 @@ class ScenarioSet:
         if self._bank is None:
             self._bank = PathBank.from_waypoints(self.waypoints)
         return self._bank
+
+    @property
+    def world(self):
+        if self._world is None:
+            from .polygons import World
+
+            self._world = World(self.world_polygons)
+        return self._world
 
     def validate(self):
         if np.any(self.st_radius < 0):
@@ -100,6 +110,7 @@ class ScenarioSet:
             static=st,
             rewarder=self.rewarder,
             post_generate_update=self.post_generate_update,
+            polygons=[np.asarray(p, dtype=np.float64) for p in self.world_polygons],
         )
 
 
@@ -432,6 +443,17 @@ def concat(sets: List[ScenarioSet]) -> ScenarioSet:
         raise ValueError("cannot concat scenario sets with different post_generate_update")
     out._bank = PathBank(tables)
     return out
+
+
+def land_scenarios(n_scenarios: int, n_polygons: int = 512, n_moving: int = 0, n_static: int = 0, seed: int = 0,
+                   n_paths: Optional[int] = None, extent: float = 6000.0) -> ScenarioSet:
+    """BASELINE config 4 shape: MovingObstacles-style scenarios inside one shared world of
+    static land polygons (synthetic; envs/realworld.py's data files are not shipped)."""
+    from .polygons import random_land
+
+    scn = moving_obstacles(n_scenarios, n_moving, n_static, seed=seed, n_paths=n_paths, name="LandPolygons")
+    scn.world_polygons = random_land(n_polygons, extent, seed=seed + 77, keep_clear=scn.vessel_init[:, :2])
+    return scn
 
 
 # registry: scenario id -> (builder, rewarder default); mirrors gym_auv/__init__.py:43-121

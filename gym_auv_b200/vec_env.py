@@ -164,15 +164,26 @@ class AUVVecEnv:
             st_pos=t(scenarios.st_pos, torch.float64),
             st_radius=t(scenarios.st_radius, torch.float64),
         )
+        world = scenarios.world
+        self.n_world = Pw = world.n
+        if Pw:
+            self._pool.update(
+                world_circle=t(world.circle, torch.float64), world_voff=t(world.voff, torch.int32),
+                world_verts=t(world.verts, torch.float64),
+            )
         p = self._pool
+        wptr = lambda k: p[k].data_ptr() if k in p else None
         self.pool = _lib.AuvScenarioPool(
-            M, Km, Ks, 0, p["path_id"].data_ptr(), p["vessel_init"].data_ptr(), p["mov_start"].data_ptr(),
+            M, Km, Ks, Pw, p["path_id"].data_ptr(), p["vessel_init"].data_ptr(), p["mov_start"].data_ptr(),
             p["mov_width"].data_ptr(), p["mov_track"].data_ptr(), p["mov_pos0"].data_ptr(), p["mov_disp0"].data_ptr(),
             p["mov_counter0"].data_ptr(), p["vel_table"].data_ptr(), p["st_pos"].data_ptr(), p["st_radius"].data_ptr(),
+            wptr("world_circle"), wptr("world_voff"), wptr("world_verts"),
         )
 
         # ---- mutable batch state
-        mw = max(1, (Km + Ks + 31) // 32)
+        mw = max(1, (Km + Ks + Pw + 31) // 32)
+        if mw > 32:
+            raise ValueError("at most 1024 obstacle slots (moving + static + world polygons) per env")
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
         self._st = dict(
             scn_id=((torch.arange(N, device=dev, dtype=torch.int64) + self.env_offset) % M).to(torch.int32),
@@ -198,7 +209,7 @@ class AUVVecEnv:
         )
 
         # ---- outputs
-        K = Km + Ks
+        K = Km + Ks + Pw
         self._out = dict(
             obs=z((N, self.obs_dim), torch.float32),
             reward=z(N, torch.float32),

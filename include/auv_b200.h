@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 5
+#define AUV_ABI_VERSION 6
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -130,7 +130,7 @@ typedef struct AuvScenarioPool {
   int32_t n_scenarios;
   int32_t k_moving;
   int32_t k_static;
-  int32_t reserved0;
+  int32_t n_world;             /* shared static polygons (PolygonObstacle), 0 = none     */
   const int32_t* path_id;      /* [M]                                                   */
   const double* vessel_init;   /* [M][3] x, y, psi                                      */
   const double* mov_start;     /* [M][k_moving][2]  trajectory[0] (wrap target)         */
@@ -142,12 +142,18 @@ typedef struct AuvScenarioPool {
   const double* vel_table;     /* [n_vel][2] per-second velocities obstacles.py:160-172 */
   const double* st_pos;        /* [M][k_static][2]                                      */
   const double* st_radius;     /* [M][k_static]                                         */
+  /* static land polygons shared by every scenario of the pool (obstacles.py:116-127):
+   * filled, enclosing circle = cached enclosing_circle_of_shape (obstacles.py:235-262).
+   * Slots K .. K+n_world-1 of the nearby list / windows output. */
+  const double* world_circle;  /* [n_world][3] cx, cy, rho                              */
+  const int32_t* world_voff;   /* [n_world+1] first vertex of each closed ring          */
+  const double* world_verts;   /* [total][2]  rings, last vertex repeats the first      */
 } AuvScenarioPool;
 
 /* Mutable per-env state (SoA).  N = n_envs. */
 typedef struct AuvBatch {
   int32_t n_envs;
-  int32_t mask_words;     /* ceil((k_moving+k_static)/32)                               */
+  int32_t mask_words;     /* ceil((k_moving+k_static+n_world)/32), <= 32               */
   int32_t env_offset;     /* global index of env 0 (multi-GPU shards), used by reset    */
   int32_t reserved0;
   int32_t* scn_id;        /* [N]   scenario each env currently runs                     */
@@ -177,7 +183,7 @@ typedef struct AuvStepOut {
   float* goal_distance;  /* [N] info["goal_distance"]                                   */
   float* progress;       /* [N] info["progress"]                                        */
   float* lidar_dist;     /* [N][n_sensors] or NULL: latest distance measurements        */
-  int32_t* windows;      /* [N][K][2] or NULL: culling (a, b) per obstacle slot (debug) */
+  int32_t* windows;      /* [N][K+n_world][2] or NULL: culling (a, b) per slot (debug)  */
   float* terminal_obs;   /* [N][obs_dim] or NULL: last obs of a finished episode        */
   double* stats;         /* [AUV_N_STATS] or NULL: episode-statistic accumulators       */
   unsigned long long* seg_tests; /* [1] or NULL: reference-semantics ray/segment tests  */

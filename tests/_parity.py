@@ -47,7 +47,8 @@ def rollout_oracle(scn, config, actions, test_mode=True):
         windows=[[None] * M for _ in range(T)], n_tests=np.zeros(M, np.int64), mov_pos=[[None] * M for _ in range(T)],
     )
     out["slot_of"] = [
-        np.concatenate([np.nonzero(scn.mov_width[m] > 0)[0], scn.k_moving + np.nonzero(scn.st_radius[m] > 0)[0]])
+        np.concatenate([np.nonzero(scn.mov_width[m] > 0)[0], scn.k_moving + np.nonzero(scn.st_radius[m] > 0)[0],
+                        scn.k_moving + scn.k_static + np.arange(len(scn.world_polygons))]).astype(int)
         for m in range(M)
     ]
     for m in range(M):

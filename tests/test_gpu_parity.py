@@ -205,6 +205,49 @@ def test_exact_cull_mode_sees_obstacle_the_reference_misses():
 
 
 # ---------------------------------------------------------------------------------------
+# static land polygons (PolygonObstacle, BASELINE config 4 shape)
+# ---------------------------------------------------------------------------------------
+def test_land_polygons_rollout():
+    from gym_auv_b200.polygons import random_land, star_polygon
+
+    cfg = lidar_config()
+    scn = S.moving_obstacles(8, 3, 2, seed=41)
+    rng = np.random.RandomState(4)
+    # a dense little world around the vessels: ~40 star polygons (non-convex) within 400 m
+    polys = []
+    for m in range(8):
+        for _ in range(5):
+            ang, dist = rng.uniform(-np.pi, np.pi), rng.uniform(25, 300)
+            c = scn.vessel_init[m, :2] + dist * np.array([np.cos(ang), np.sin(ang)])
+            polys.append(star_polygon(rng, c, min(rng.uniform(8, 60), dist - 8), int(rng.randint(8, 65))))
+    # one vessel starts INSIDE a polygon (filled => range 0 => collision on the first step)
+    polys.append(star_polygon(rng, scn.vessel_init[7, :2] + 1.0, 30.0, 12) * 1.0)
+    scn.world_polygons = polys
+    actions = random_actions(30, 8, 55)
+    actions[..., 0] = np.abs(actions[..., 0])
+    ref = rollout_oracle(scn, cfg, actions)
+    gpu, env = rollout_gpu(scn, cfg, actions)
+    rep = compare(ref, gpu, cfg, "land polygons")
+    assert env.n_world == len(polys) and rep["windows_checked"] > 200
+    assert ref["collision"][0, 7] and gpu["collision"][0, 7]  # inside the filled polygon
+    assert gpu["dists"][0, 7].min() == 0.0
+    assert (ref["min_dist"][ref["alive"]] < 150).mean() > 0.5
+    if ref["alive"].all():
+        assert gpu["seg_tests"] == int(ref["n_tests"].sum())
+
+
+def test_land_polygons_512_world_sample_vs_oracle():
+    """Config-4-sized shared world (512 polygons = 16 extra mask words per env)."""
+    cfg = lidar_config()
+    scn = S.land_scenarios(6, n_polygons=512, n_moving=2, n_static=2, seed=9, extent=2500.0)
+    actions = random_actions(10, 6, 5)
+    ref = rollout_oracle(scn, cfg, actions)
+    gpu, env = rollout_gpu(scn, cfg, actions)
+    compare(ref, gpu, cfg, "land 512")
+    assert env.n_world == 512
+
+
+# ---------------------------------------------------------------------------------------
 # BASELINE config 2: no LiDAR, PathFollowRewarder
 # ---------------------------------------------------------------------------------------
 def test_path_follow_no_lidar_rollout():
