@@ -54,6 +54,10 @@ def parse():
     ap.add_argument("--n-paths", type=int, default=1024)
     ap.add_argument("--rays", type=int, default=180)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--workload", default="moving", choices=["moving", "land", "pathfollow"],
+                    help="moving = BASELINE config 3 (headline); land = config 4 shape (shared world of "
+                         "--n-polygons static land polygons); pathfollow = config 2 (no LiDAR, PathFollowRewarder)")
+    ap.add_argument("--n-polygons", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-envs", type=int, default=8)
@@ -121,14 +125,20 @@ def build_workload(args, rank):
     from gym_auv_b200.config import Config
 
     cfg = Config()
+    if getattr(args, "workload", "moving") == "pathfollow":
+        return cfg, S.path_follow_no_obstacles(args.envs, seed=args.seed + 1000 * rank, n_paths=args.n_paths)
     cfg.vessel.use_lidar = True
     per_sector = args.rays // cfg.vessel.n_sectors
     if per_sector * cfg.vessel.n_sectors != args.rays:
         cfg.vessel.n_sectors = 8
         per_sector = args.rays // 8
     cfg.vessel.n_sensors_per_sector = per_sector
-    scn = S.moving_obstacles(args.envs, args.n_moving, args.n_static, seed=args.seed + 1000 * rank,
-                             n_paths=args.n_paths)
+    if getattr(args, "workload", "moving") == "land":
+        scn = S.land_scenarios(args.envs, n_polygons=args.n_polygons, n_moving=args.n_moving, n_static=args.n_static,
+                               seed=args.seed + 1000 * rank, n_paths=args.n_paths)
+    else:
+        scn = S.moving_obstacles(args.envs, args.n_moving, args.n_static, seed=args.seed + 1000 * rank,
+                                 n_paths=args.n_paths)
     return cfg, scn
 
 
@@ -225,6 +235,7 @@ def run_ours(args):
 
     cfg, scn = build_workload(args, rank)
     N, K, Wm = args.envs, args.steps, max(args.warmup, 3)
+    R = cfg.vessel.n_sensors
     env = AUVVecEnv(scn, N, cfg, device=device, test_mode=False, auto_reset=True, env_offset=0)
     gen = torch.Generator(device=device)
     gen.manual_seed(1234 + rank)
@@ -338,15 +349,17 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    R = cfg.vessel.n_sensors
-    flops_per_launch = FLOP_PER_SEG_TEST * seg_tests_per_step + FLOP_PER_RAY * R * N
+    flops_per_launch = FLOP_PER_SEG_TEST * seg_tests_per_step + FLOP_PER_RAY * (R if cfg.vessel.use_lidar else 0) * N
     achieved_tflops = flops_per_launch / (obs_ms * 1e-3) / 1e12
     achieved_gbs = ALGO_BYTES_PER_ENV_STEP * N / (obs_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 ray casting on f64 state/culling", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": N, "rays": R, "obstacles": args.n_moving + args.n_static,
+        "config": {"workload": WORKLOAD if args.workload == "moving" and N == 65536 and R == 180 else
+                   f"{args.workload}: {N} envs/GPU x {R if cfg.vessel.use_lidar else 0} rays x {args.n_moving}+{args.n_static} obstacles"
+                   + (f" + {args.n_polygons} shared land polygons" if args.workload == "land" else ""),
+                   "envs_per_gpu": N, "rays": R, "obstacles": args.n_moving + args.n_static,
                    "paths": args.n_paths, "l2": "per-step working set (state+obstacles ~%.0f MB, path bank ~%.0f MB) exceeds the 126 MB L2; no explicit flush"
                    % (N * ALGO_BYTES_PER_ENV_STEP / 2e6, scn.bank.poly_xy.nbytes * 1.5 / 1e6 + scn.bank.coef.nbytes / 1e6),
                    "auto_reset": True, "dones_per_step": dones_per_step},
