@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
-ABI_VERSION = 6
+ABI_VERSION = 7
 NAV_W = 12
 N_STATS = 16
 STAT_NAMES = [
@@ -43,6 +43,7 @@ class AuvConfig(C.Structure):
         ("min_goal_distance", C.c_double),
         ("min_path_progress", C.c_double),
         ("min_cumulative_reward", C.c_double),
+        ("feasibility_width_multiplier", C.c_double),
         ("max_timesteps", C.c_int32),
         ("sensor_interval_load_obstacles", C.c_int32),
         ("n_sensors", C.c_int32),
@@ -140,6 +141,8 @@ class AuvStepOut(C.Structure):
         ("lidar_dist", _vp),
         ("windows", _vp),
         ("terminal_obs", _vp),
+        ("sector_min_dist", _vp),
+        ("sector_feasible_dist", _vp),
         ("stats", _vp),
         ("seg_tests", _vp),
     ]

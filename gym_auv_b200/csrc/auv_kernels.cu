@@ -515,6 +515,62 @@ __device__ __forceinline__ void cull_bounds(double cx, double cy, double rho, do
   if (exact) cull_bounds_f64(cx, cy, rho, psi, dth, lo, hi);
 }
 
+// LidarPreprocessor._feasibility_pooling (sensor.py:251-296) for one sector: the largest
+// range d such that no opening wider than `width` exists among the rays that see farther
+// than d + width.  m[0..n) are the sector's ranges (shared memory), FP64 arithmetic on the
+// FP32 ranges.  Candidates are visited in increasing range order (np.argsort; ties are
+// equal values so their order cannot change the result).
+__device__ __forceinline__ float feasibility_pooling(const float* m, int n, double width, double theta) {
+  // every FP64 operation is an explicit round-to-nearest intrinsic: the algorithm is a chain
+  // of threshold tests on accumulated sums, so FMA contraction would change its decisions
+  const double span = __dmul_rn(theta, (double)(n - 1));
+  const double half = span / 2.0, quarter = span / 4.0;
+  float prev = -1.f;
+  int prev_cnt = 0;  // how many rays with value == prev have been consumed already
+  float maxv = 0.f;
+  for (int i = 0; i < n; ++i) maxv = fmaxf(maxv, m[i]);
+  for (int it = 0; it < n; ++it) {
+    // next value in sorted order: smallest > prev, or another copy of prev
+    int same = 0;
+    float next = INFINITY;
+    for (int i = 0; i < n; ++i) {
+      const float v = m[i];
+      if (v == prev) ++same;
+      else if (v > prev) next = fminf(next, v);
+    }
+    float cur;
+    if (prev_cnt < same) {
+      cur = prev;
+      ++prev_cnt;
+    } else {
+      cur = next;
+      prev = next;
+      prev_cnt = 1;
+    }
+    const double dcur = (double)cur;
+    const double d = __dmul_rn(dcur, theta), hd = __dmul_rn(0.5, d), ht = __dmul_rn(0.5, theta);
+    const double thr = __dadd_rn(dcur, width);
+    double ow = 0.0, os = 0.0, ostart = -half;
+    bool found = false;
+    for (int i = 0; i < n; ++i) {
+      if ((double)m[i] > thr) {
+        ow = __dadd_rn(ow, d);
+        os = __dadd_rn(os, theta);
+        if (ow > width && fabs(__dadd_rn(ostart, os / 2.0)) < quarter) found = true;
+      } else {
+        ow = __dadd_rn(ow, hd);
+        os = __dadd_rn(os, ht);
+        if (ow > width && fabs(__dadd_rn(ostart, os / 2.0)) < quarter) found = true;
+        ow = 0.0;
+        os = 0.0;
+        ostart = __dadd_rn(-half, __dmul_rn((double)i, theta));
+      }
+    }
+    if (!found) return fmaxf(0.f, cur);
+  }
+  return fmaxf(0.f, maxv);
+}
+
 struct ObserveArgs {
   AuvConfig cfg;
   AuvRayTable rays;
@@ -526,6 +582,7 @@ struct ObserveArgs {
   int obs_dim;
   float pen_clear;  // sum_i w_i * range * exp(-0.1 range): penalty sum when every ray reads sensor_range
   float pen_clear_ray;     // range * exp(-0.1 range)
+  double feas_width;       // vessel_width * feasibility_width_multiplier (sensor.py:166-168)
   double clear_closeness;  // -range * exp(-0.1 range): closeness reward with no LiDAR at all
 };
 
@@ -963,6 +1020,49 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_WARPS_PER_SM
         collision = __any_sync(AUV_FULL, collision);
         pen_sum = warp_sum(pen_sum);
       }
+      // ---- optional sector pooling (utils/sector_partitioning.py; sensor.py:215-296)
+      if (A.out.sector_min_dist != nullptr || A.out.sector_feasible_dist != nullptr) {
+        const int ns = cfg.n_sectors;
+        __syncwarp();
+        if (!any_active)
+          for (int i = lane; i < rpad; i += 32) sdist[i] = rangef;
+        float* ssec = reinterpret_cast<float*>(W.verts);  // vertex staging is free again: reuse
+        if (lane < 32) ssec[lane] = rangef;
+        __syncwarp();
+        // min-pooling: segmented warp-shuffle reduction keyed by the ray's sector id
+        for (int i0 = 0; i0 < R; i0 += 32) {
+          const int i = i0 + lane;
+          float d = i < R ? sdist[i] : INFINITY;
+          const int sid = i < R ? (int)A.rays.sector[i] : -1 - lane;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float od = __shfl_down_sync(AUV_FULL, d, o);
+            const int os = __shfl_down_sync(AUV_FULL, sid, o);
+            if (lane + o < 32 && os == sid) d = fminf(d, od);
+          }
+          const int ps = __shfl_up_sync(AUV_FULL, sid, 1);
+          const bool head = i < R && (lane == 0 || ps != sid);
+          if (head && sid < 32) ssec[sid] = fminf(ssec[sid], d);  // one head per sector per iteration
+          __syncwarp();
+        }
+        if (A.out.sector_min_dist != nullptr && lane < ns)
+          A.out.sector_min_dist[(long long)e * ns + lane] = ssec[lane];
+        if (A.out.sector_feasible_dist != nullptr) {
+          // lane s pools sector s (sectors are contiguous ray ranges)
+          float res = rangef;
+          if (lane < ns) {
+            int lo = 0, hi = R;
+            for (int i = 0; i < R; ++i) {  // sector table is monotone
+              const int sd = A.rays.sector[i];
+              if (sd < lane) lo = i + 1;
+              if (sd <= lane) hi = i + 1;
+            }
+            res = hi > lo ? feasibility_pooling(sdist + lo, hi - lo, A.feas_width, dth_d) : rangef;
+          }
+          if (lane < ns) A.out.sector_feasible_dist[(long long)e * ns + lane] = res;
+        }
+        __syncwarp();
+      }
       if (cfg.sensor_use_velocity_observations)  // sensor.py:159: speed channel is (0,0) at HEAD
         for (int i = lane; i < 2 * R; i += 32) obs[6 + R + i] = 0.f;
     }
@@ -1147,6 +1247,8 @@ static int check_cfg(const AuvConfig* cfg) {
   if (!(cfg->t_step_size > 0.0)) return set_err(AUV_EINVAL, "t_step_size must be > 0");
   if (cfg->sensor_interval_load_obstacles <= 0)
     return set_err(AUV_EINVAL, "sensor_interval_load_obstacles must be > 0");
+  if (cfg->use_lidar && (cfg->n_sectors <= 0 || cfg->n_sectors > 32))
+    return set_err(AUV_EINVAL, "n_sectors must be in 1..32");
   return 0;
 }
 
@@ -1230,6 +1332,7 @@ static int launch_observe(const AuvConfig* cfg, const AuvRayTable* rays, const A
   args.pen_clear = (float)((rays ? rays->weight_sum : 1.0) * cfg->sensor_range * exp(-0.1 * cfg->sensor_range));
   args.clear_closeness = -cfg->sensor_range * exp(-0.1 * cfg->sensor_range);
   args.pen_clear_ray = (float)(-args.clear_closeness);
+  args.feas_width = cfg->vessel_width * cfg->feasibility_width_multiplier;
   const int rpad = cfg->use_lidar ? ((cfg->n_sensors + 31) & ~31) : 32;
   const size_t smem = (sizeof(auv::WarpScratch) + sizeof(float) * rpad) * auv::WARPS_PER_BLOCK;
   static size_t configured = 0;

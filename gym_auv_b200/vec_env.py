@@ -64,6 +64,7 @@ def make_auv_config(cfg: Config, rewarder: str, test_mode: bool, auto_reset: boo
         min_goal_distance=float(e.min_goal_distance),
         min_path_progress=float(e.min_path_progress),
         min_cumulative_reward=float(e.min_cumulative_reward),
+        feasibility_width_multiplier=float(v.feasibility_width_multiplier),
         max_timesteps=int(e.max_timesteps),
         sensor_interval_load_obstacles=int(v.sensor_interval_load_obstacles),
         n_sensors=int(v.n_sensors),
@@ -92,6 +93,8 @@ class AUVVecEnv:
     test_mode : as BaseEnvironment(test_mode=...) (environment.py:32,380-382)
     auto_reset: VecEnv semantics (default) or manual ``reset_envs``
     debug     : also record per-ray distances, culling windows and FP64 navigation values
+    sector_outputs : also produce per-sector min-pooled and feasibility-pooled ranges
+                     (get_attr("sector_min_dist") / get_attr("sector_feasible_dist"))
     """
 
     def __init__(
@@ -105,6 +108,7 @@ class AUVVecEnv:
         cull_mode: str = "reference",
         debug: bool = False,
         env_offset: int = 0,
+        sector_outputs: bool = False,
     ):
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -222,6 +226,10 @@ class AUVVecEnv:
             stats=z(_lib.N_STATS, torch.float64),
             seg_tests=z(1, torch.int64),
         )
+        if sector_outputs and self.config.vessel.use_lidar:
+            ns = int(self.config.vessel.n_sectors)
+            self._out["sector_min_dist"] = z((N, ns), torch.float32)
+            self._out["sector_feasible_dist"] = z((N, ns), torch.float32)
         if debug:
             self._out["lidar_dist"] = z((N, max(R, 1)), torch.float32)
             self._out["windows"] = z((N, max(K, 1), 2), torch.int32)
@@ -229,7 +237,8 @@ class AUVVecEnv:
         ptr = lambda k: o[k].data_ptr() if k in o else None
         self.out = _lib.AuvStepOut(
             ptr("obs"), ptr("reward"), ptr("done"), ptr("collision"), ptr("reached_goal"), ptr("goal_distance"),
-            ptr("progress"), ptr("lidar_dist"), ptr("windows"), ptr("terminal_obs"), ptr("stats"),
+            ptr("progress"), ptr("lidar_dist"), ptr("windows"), ptr("terminal_obs"), ptr("sector_min_dist"),
+            ptr("sector_feasible_dist"), ptr("stats"),
             ptr("seg_tests") if debug else None,
         )
         self.actions_dev = z((N, 2), torch.float32)

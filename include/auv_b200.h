@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 6
+#define AUV_ABI_VERSION 7
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -71,6 +71,7 @@ typedef struct AuvConfig {
   double min_goal_distance;     /* EpisodeConfig.min_goal_distance         config.py:20  */
   double min_path_progress;     /* EpisodeConfig.min_path_progress         config.py:23  */
   double min_cumulative_reward; /* EpisodeConfig.min_cumulative_reward     config.py:16  */
+  double feasibility_width_multiplier; /* VesselConfig.feasibility_width_multiplier config.py:42 */
   int32_t max_timesteps;        /* EpisodeConfig.max_timesteps             config.py:19  */
   int32_t sensor_interval_load_obstacles; /*                               config.py:56  */
   int32_t n_sensors;            /* n_sensors_per_sector * n_sectors        config.py:75  */
@@ -185,6 +186,10 @@ typedef struct AuvStepOut {
   float* lidar_dist;     /* [N][n_sensors] or NULL: latest distance measurements        */
   int32_t* windows;      /* [N][K+n_world][2] or NULL: culling (a, b) per slot (debug)  */
   float* terminal_obs;   /* [N][obs_dim] or NULL: last obs of a finished episode        */
+  float* sector_min_dist;      /* [N][n_sectors] or NULL: closest range per sector (sector map of
+                                  utils/sector_partitioning.py:4-9), warp-shuffle min-pooling    */
+  float* sector_feasible_dist; /* [N][n_sectors] or NULL: LidarPreprocessor._feasibility_pooling
+                                  (sensor.py:251-296) per sector                                  */
   double* stats;         /* [AUV_N_STATS] or NULL: episode-statistic accumulators       */
   unsigned long long* seg_tests; /* [1] or NULL: reference-semantics ray/segment tests  */
 } AuvStepOut;

@@ -464,3 +464,56 @@ class OracleEnv:
         self.cross_track_errors.append(abs(v.nav["cross_track_error"]) * 100)
         self.t_step += 1
         return obs, reward, done, info
+
+
+# ---------------------------------------------------------------------------------
+# Sector pooling (sensor.py:215-296; utils/sector_partitioning.py).  The wiring of
+# LidarPreprocessor is broken in the reference at HEAD; the static
+# pooling method itself is self-contained and restated here literally.
+# ---------------------------------------------------------------------------------
+
+
+def feasibility_pooling(measurements, width, theta):
+    """LidarPreprocessor._feasibility_pooling (sensor.py:251-296)."""
+    measurements = np.asarray(measurements, dtype=np.float64)
+    n = measurements.shape[0]
+    for idx in np.argsort(measurements):
+        surviving = measurements > measurements[idx] + width
+        d = measurements[idx] * theta
+        opening_width = 0
+        opening_span = 0
+        opening_start = -theta * (n - 1) / 2
+        found = False
+        for isensor, ok in enumerate(surviving):
+            if ok:
+                opening_width += d
+                opening_span += theta
+                if opening_width > width:
+                    if abs(opening_start + opening_span / 2) < theta * (n - 1) / 4:
+                        found = True
+            else:
+                opening_width += 0.5 * d
+                opening_span += 0.5 * theta
+                if opening_width > width:
+                    if abs(opening_start + opening_span / 2) < theta * (n - 1) / 4:
+                        found = True
+                opening_width = 0
+                opening_span = 0
+                opening_start = -theta * (n - 1) / 2 + isensor * theta
+        if not found:
+            return max(0, measurements[idx])
+    return max(0, np.max(measurements))
+
+
+def sector_pool(dists, n_sectors=9, vessel_width=1.255, width_multiplier=5.0):
+    """(min-pooled, feasibility-pooled) ranges per sector for one ray vector."""
+    dists = np.asarray(dists, dtype=np.float64)
+    n = len(dists)
+    table = M.sector_table(n, n_sectors)
+    theta = 2 * math.pi / n
+    mins, feas = [], []
+    for s in range(n_sectors):
+        m = dists[table == s]
+        mins.append(m.min())
+        feas.append(feasibility_pooling(m, vessel_width * width_multiplier, theta))
+    return np.array(mins), np.array(feas)

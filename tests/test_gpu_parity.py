@@ -282,6 +282,41 @@ def test_velocity_observation_channel_is_zero_and_shaped():
 
 
 # ---------------------------------------------------------------------------------------
+# sector pooling (utils/sector_partitioning.py + LidarPreprocessor._feasibility_pooling)
+# ---------------------------------------------------------------------------------------
+def test_sector_pooling_outputs():
+    from oracle.sim import sector_pool
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    scn = S.moving_obstacles(24, 17, 11, seed=33)
+    rng = np.random.RandomState(8)
+    for m in range(0, 24, 2):  # half of the envs start close to a static obstacle
+        j = rng.randint(11)
+        ang = rng.uniform(-np.pi, np.pi)
+        scn.vessel_init[m, :2] = scn.st_pos[m, j] + (scn.st_radius[m, j] + rng.uniform(3, 40)) * np.array(
+            [np.cos(ang), np.sin(ang)])
+    env = AUVVecEnv(scn, 24, cfg, test_mode=True, auto_reset=False, debug=True, sector_outputs=True)
+    env.reset()
+    a = torch.as_tensor(random_actions(6, 24, 3), dtype=torch.float32, device="cuda")
+    checked = 0
+    for t in range(6):
+        env.step(a[t])
+        d = env.get_attr("lidar_dist").cpu().numpy()
+        smin = env.get_attr("sector_min_dist").cpu().numpy()
+        sfeas = env.get_attr("sector_feasible_dist").cpu().numpy()
+        for m in range(24):
+            want_min, want_feas = sector_pool(d[m], 9, cfg.vessel.vessel_width, cfg.vessel.feasibility_width_multiplier)
+            assert np.array_equal(smin[m], want_min.astype(np.float32))  # pooling is exact on the same ranges
+            assert np.array_equal(sfeas[m], want_feas.astype(np.float32))
+            checked += int((want_min < 150).sum())
+    assert checked > 50
+    # sector index table is the reference's, bit-exact
+    g = np.load(os.path.join(GOLD, "reference_dynamics.npz"))
+    assert np.array_equal(env.sector_index, g["sectors_180"].astype(np.uint8))
+
+
+# ---------------------------------------------------------------------------------------
 # done / auto-reset semantics
 # ---------------------------------------------------------------------------------------
 def test_time_limit_done_and_auto_reset():
