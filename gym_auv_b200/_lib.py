@@ -8,7 +8,10 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
-ABI_VERSION = 7
+ABI_VERSION = 9
+REC_BYTES = 80
+MAX_POLY_VERTS = 192
+STATUS_REC_OVERFLOW = 1
 NAV_W = 12
 N_STATS = 16
 STAT_NAMES = [
@@ -104,6 +107,9 @@ class AuvScenarioPool(C.Structure):
         ("world_circle", _vp),
         ("world_voff", _vp),
         ("world_verts", _vp),
+        ("reset_obs", _vp),
+        ("reset_max_progress", _vp),
+        ("reset_mask", _vp),
     ]
 
 
@@ -126,6 +132,11 @@ class AuvBatch(C.Structure):
         ("mov_disp", _vp),
         ("mov_counter", _vp),
         ("nav", _vp),
+        ("rec", _vp),
+        ("rec_cnt", _vp),
+        ("status", _vp),
+        ("rec_cap", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 
@@ -197,7 +208,7 @@ def load():
     lib.auv_observe.argtypes = [
         P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), P(AuvStepOut), C.c_int, _vp,
     ]
-    lib.auv_navigate.argtypes = [P(AuvConfig), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp]
+    lib.auv_navigate.argtypes = [P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp]
     lib.auv_reset.argtypes = [P(AuvConfig), P(AuvScenarioPool), P(AuvBatch), _vp, _vp]
     lib.auv_step.argtypes = [
         P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, P(AuvStepOut), _vp,

@@ -1,21 +1,30 @@
-// auv_kernels.cu -- hand-written sm_100a kernels for the gym-auv step path.
+// auv_kernels.cu -- hand-written sm_100a kernels for the gym-auv step path + the C ABI.
 //
 // Kernel inventory (reference file:line each one replaces is in include/auv_b200.h):
-//   k_obstacle_update  one thread per (env, moving-obstacle slot)            HBM-bound
-//   k_vessel_step      one thread per env, FP64 RKF45 state in registers     HBM-bound
-//   k_observe          one WARP per env: path projection (two-level exact search),
-//                      PCHIP evaluation, nearby filter, reference-exact culling windows,
-//                      obstacle vertices staged in shared memory, lanes-over-rays
-//                      ray/segment casting, closeness, collision, reward (warp reduce),
-//                      done, episode stats and in-kernel auto-reset.        FP32-pipe bound
-//   k_reset            explicit host-requested reset of flagged envs
+//   k_obstacle_update  thread per (env, moving-obstacle slot)                        HBM
+//   k_vessel_nav<DYN>  thread per env, FP64: RKF45 vessel step (DYN) -> path projection
+//                      (exact hierarchical LineString.project) -> navigation record ->
+//                      obstacle culling: nearby list (every 25 steps), enclosing circles,
+//                      reference-exact ray windows, inside tests -> compact per-env
+//                      obstacle records in HBM                                latency / FP64
+//   k_lidar            WARP per env, lanes over rays: per-env scalars and obstacle records
+//                      arrive in one round trip, vertices are staged in shared memory (formed
+//                      in FP64 relative to the vessel), ray/segment casting (analytic edge pick
+//                      for polygonised circles), closeness, collision, obs, warp-reduced
+//                      reward, done, counters, sector pooling, and the VecEnv auto-reset of
+//                      finished envs as a COPY of the scenario's cached first observation
+//                      (no navigation / culling / casting on reset)              FP32 issue
+//   k_vessel_step / k_reset   staged entry points (Vessel.step only / explicit reset)
 //   k_fma_probe        FP32 FMA peak micro-benchmark (roofline denominator)
 //
-// Precision plan: everything that is cheap and threshold-sensitive is FP64 (vessel
-// state, RK step, obstacle positions, vessel-relative obstacle centres, culling-window
-// integers, path projection refine, navigation scalars, reward scalars); the O(rays x
-// segments) ray casting is FP32 on vessel-relative vertices that were formed in FP64.
+// Precision plan: everything cheap and threshold-sensitive is FP64 (vessel state, RK step,
+// obstacle positions, vessel-relative obstacle centres, culling-window integers via an FP32
+// fast path with FP64 fallback, projection refine, navigation and reward scalars); the
+// O(rays x segments) casting is FP32 on vessel-relative vertices formed in FP64.
 #include "auv_device.cuh"
+#include "auv_dynamics.cuh"
+#include "auv_geometry.cuh"
+#include "auv_navigate.cuh"
 #include "../../include/auv_b200.h"
 
 #include <math.h>
@@ -54,94 +63,6 @@ __global__ void __launch_bounds__(256) k_obstacle_update(AuvConfig cfg, AuvScena
   batch.mov_counter[gid] = counter;
 }
 
-// ------------------------------------------------------------------------------------
-// k_vessel_step     vessel.py:226-247,561-578; odesolver.py:2-47; constants.py:33-72
-// ------------------------------------------------------------------------------------
-struct S6 {
-  double x, y, psi, u, v, r;
-};
-
-__device__ __forceinline__ S6 state_dot(const S6& s, double tau_u, double tau_r) {
-  // M = [[25.8,0,0],[0,33.8,1.0948],[0,1.0948,2.76]]   (constants.py:33-36)
-  constexpr double m11 = 33.8, m12 = 23.8 * 0.046, m22 = 2.76;
-  constexpr double det = m11 * m22 - m12 * m12;
-  constexpr double i00 = 1.0 / 25.8, i11 = m22 / det, i12 = -m12 / det, i22 = m11 / det;
-  double sp, cp;
-  sincos(princip(s.psi), &sp, &cp);
-  S6 d;
-  d.x = cp * s.u - sp * s.v;
-  d.y = sp * s.u + cp * s.v;
-  d.psi = s.r;
-  // tau - D nu - N(nu) nu   (constants.py:39-43, 63-72)
-  const double f1 = (tau_u - 2.0 * s.u) - 2.0 * s.u;
-  const double f2 = (0.0 - (7.0 * s.v - 2.5425 * s.r)) - (7.0 * s.v + (23.8 * s.u + 0.1) * s.r);
-  const double f3 = (tau_r - (-2.5425 * s.v + 1.422 * s.r)) - (0.1 * s.v + (23.8 * 0.046 * s.u + 0.5) * s.r);
-  d.u = i00 * f1;
-  d.v = i11 * f2 + i12 * f3;
-  d.r = i12 * f2 + i22 * f3;
-  return d;
-}
-
-#define S6_AXPY(out, y, EXPR)          \
-  out.x = y.x + (EXPR(x));             \
-  out.y = y.y + (EXPR(y));             \
-  out.psi = y.psi + (EXPR(psi));       \
-  out.u = y.u + (EXPR(u));             \
-  out.v = y.v + (EXPR(v));             \
-  out.r = y.r + (EXPR(r));
-
-// one Fehlberg step for one env (vessel.py:226-247): returns the 5th-order solution q
-__device__ __forceinline__ S6 vessel_rk_step(const AuvConfig& cfg, const S6& y, float2 a) {
-  if (isnan(a.x) || isnan(a.y)) a = make_float2(0.f, 0.f);  // environment.py:314-315
-  const double tau_u = fmin(fmax((double)a.x, 0.0), 1.0) * cfg.thrust_max_auv;
-  const double tau_r = fmin(fmax((double)a.y, -1.0), 1.0) * cfg.moment_max_auv;
-  const double h = cfg.t_step_size;
-  S6 t, k1, k2, k3, k4, k5, k6, q;
-  k1 = state_dot(y, tau_u, tau_r);
-#define E2(c) h * k1.c / 4.0
-  S6_AXPY(t, y, E2)
-  k2 = state_dot(t, tau_u, tau_r);
-#define E3(c) 3.0 * h * k1.c / 32.0 + 9.0 * h * k2.c / 32.0
-  S6_AXPY(t, y, E3)
-  k3 = state_dot(t, tau_u, tau_r);
-#define E4(c) 1932.0 * h * k1.c / 2197.0 - 7200.0 * h * k2.c / 2197.0 + 7296.0 * h * k3.c / 2197.0
-  S6_AXPY(t, y, E4)
-  k4 = state_dot(t, tau_u, tau_r);
-#define E5(c) 439.0 * h * k1.c / 216.0 - 8.0 * h * k2.c + 3680.0 * h * k3.c / 513.0 - 845.0 * h * k4.c / 4104.0
-  S6_AXPY(t, y, E5)
-  k5 = state_dot(t, tau_u, tau_r);
-#define E6(c)                                                                               \
-  -8.0 * h * k1.c / 27.0 + 2 * h * k2.c - 3544.0 * h * k3.c / 2565 + 1859.0 * h * k4.c / 4104.0 - \
-      11.0 * h * k5.c / 40.0
-  S6_AXPY(t, y, E6)
-  k6 = state_dot(t, tau_u, tau_r);
-#define EQ(c)                                                                                   \
-  h*(16.0 * k1.c / 135.0 + 6656.0 * k3.c / 12825.0 + 28561.0 * k4.c / 56430.0 - 9.0 * k5.c / 50.0 + \
-     2.0 * k6.c / 55.0)
-  S6_AXPY(q, y, EQ)
-  q.psi = princip(q.psi);
-  return q;
-}
-
-__device__ __forceinline__ S6 load_state(const double* st, int n, int e) {
-  S6 y;
-  y.x = st[e];
-  y.y = st[n + e];
-  y.psi = st[2 * n + e];
-  y.u = st[3 * n + e];
-  y.v = st[4 * n + e];
-  y.r = st[5 * n + e];
-  return y;
-}
-__device__ __forceinline__ void store_state(double* st, int n, int e, const S6& q) {
-  st[e] = q.x;
-  st[n + e] = q.y;
-  st[2 * n + e] = q.psi;
-  st[3 * n + e] = q.u;
-  st[4 * n + e] = q.v;
-  st[5 * n + e] = q.r;
-}
-
 // Vessel.step only (staged entry point auv_vessel_step)
 __global__ void __launch_bounds__(128) k_vessel_step(AuvConfig cfg, AuvBatch batch,
                                                       const float* __restrict__ actions) {
@@ -154,1023 +75,639 @@ __global__ void __launch_bounds__(128) k_vessel_step(AuvConfig cfg, AuvBatch bat
 }
 
 // ------------------------------------------------------------------------------------
-// reset of one env, executed by one warp    environment.py:202-212, vessel.py:189-224
+// Obstacle records: what the culling stage hands to the ray-casting stage (HBM scratch
+// owned by the caller, AuvBatch.rec: [N][rec_cap] records of AUV_REC_BYTES bytes).
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void reset_env_warp(const AuvScenarioPool& pool, const AuvBatch& batch, int e,
-                                               int scn, int lane) {
+struct __align__(16) ObstRec {
+  double cx, cy;         // vessel-relative anchor: circle centre | pentagon rotation centre
+  double geo;            // radius | width
+  double hx, hy;         // unit heading of a vessel obstacle
+  float ecx, ecy, rho;   // enclosing circle, vessel-relative (sensor.py:22-38)
+  int a, b;              // culling window (sensor.py:41-97)
+  int flags;             // OFLAG_*
+  int nv;                // boundary vertices incl. the closing one
+  int vbase;             // world polygon: first vertex in pool.world_verts
+};
+static_assert(sizeof(ObstRec) == AUV_REC_BYTES, "ObstRec layout");
+
+// reset of one env's mutable state by ONE thread   environment.py:202-212, vessel.py:189-224
+__device__ __forceinline__ void reset_env_thread(const AuvScenarioPool& pool, const AuvBatch& batch, int e,
+                                                 int scn) {
   const int n = batch.n_envs;
   const int km = pool.k_moving;
-  if (lane == 0) {
-    batch.scn_id[e] = scn;
-    batch.episode[e] += 1;
-    const double* vi = pool.vessel_init + 3ll * scn;
-    batch.state[e] = vi[0];
-    batch.state[n + e] = vi[1];
-    batch.state[2 * n + e] = vi[2];
-    batch.state[3 * n + e] = 0.0;
-    batch.state[4 * n + e] = 0.0;
-    batch.state[5 * n + e] = 0.0;
-    batch.step_counter[e] = 0;
-    batch.t_step[e] = 0;
-    batch.cum_reward[e] = 0.0;
-    batch.max_progress[e] = 0.0;
-    batch.cte_sum[e] = 0.0;
-  }
-  for (int j = lane; j < km; j += 32) {
+  batch.scn_id[e] = scn;
+  batch.episode[e] += 1;
+  const double* vi = pool.vessel_init + 3ll * scn;
+  batch.state[e] = vi[0];
+  batch.state[n + e] = vi[1];
+  batch.state[2 * n + e] = vi[2];
+  batch.state[3 * n + e] = 0.0;
+  batch.state[4 * n + e] = 0.0;
+  batch.state[5 * n + e] = 0.0;
+  batch.step_counter[e] = 0;
+  batch.t_step[e] = 0;
+  batch.cum_reward[e] = 0.0;
+  batch.max_progress[e] = 0.0;
+  batch.cte_sum[e] = 0.0;
+  for (int j = 0; j < km; ++j) {
     const long long ps = (long long)scn * km + j, pe = (long long)e * km + j;
     reinterpret_cast<double2*>(batch.mov_pos)[pe] = reinterpret_cast<const double2*>(pool.mov_pos0)[ps];
     reinterpret_cast<double2*>(batch.mov_disp)[pe] = reinterpret_cast<const double2*>(pool.mov_disp0)[ps];
     batch.mov_counter[pe] = pool.mov_counter0[ps];
   }
-  for (int w = lane; w < batch.mask_words; w += 32) batch.nearby_mask[(long long)e * batch.mask_words + w] = 0u;
-  __syncwarp();
+  for (int w = 0; w < batch.mask_words; ++w) batch.nearby_mask[(long long)e * batch.mask_words + w] = 0u;
 }
 
-__global__ void __launch_bounds__(256) k_reset(AuvScenarioPool pool, AuvBatch batch,
+// explicit reset (auv_reset): envs flagged in reset_mask (or all) go back to scenario scn_id[e]
+__global__ void __launch_bounds__(128) k_reset(AuvScenarioPool pool, AuvBatch batch,
                                                const uint8_t* __restrict__ reset_mask) {
-  const int lane = threadIdx.x & 31;
-  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= batch.n_envs) return;
   if (reset_mask != nullptr && reset_mask[e] == 0) return;
-  reset_env_warp(pool, batch, e, batch.scn_id[e], lane);
+  reset_env_thread(pool, batch, e, batch.scn_id[e]);
 }
 
 // ------------------------------------------------------------------------------------
-// Path projection + navigation features, ONE THREAD per env (FP64)
-//   path.py:61-93 (PCHIP eval, LineString.project), vessel.py:461-541 (navigate)
-// The result is the env's navigation record nav[e][AUV_NAV_W] in HBM; the warp-per-env
-// LiDAR kernel reads it back (one 96 B coalesced load).
+// Culling stage ("hierarchical collision detector"), one thread per env.
+//   vessel.py:266-273 nearby list, sensor.py:22-97 windows, obstacles.py:108-113,230-262
+//   enclosing circles.  Emits rec[e][0..cnt) and rec_cnt[e].
 // ------------------------------------------------------------------------------------
-#define NAV_S 0
-#define NAV_CHI 1
-#define NAV_YE 2
-#define NAV_SLA 3
-#define NAV_LA_ERR 4
-#define NAV_HEAD_ERR 5
-#define NAV_GOAL 6
-#define NAV_PROGRESS 7
-#define NAV_COSPSI 8
-#define NAV_SINPSI 9
-#define NAV_REACHED 10
-#define NAV_COS_HEAD_ERR 11
+struct SlotGeom {
+  bool valid, pent, world;
+  double cx, cy, rho, geo, hx, hy;
+  int nv, vbase;
+};
 
-// scipy PPoly evaluation (extrapolate=True): interval j with x[j] <= s < x[j+1], clamped.
-__device__ __forceinline__ void pchip_eval(const AuvPathBank& pb, int pid, double s, double& px,
-                                           double& py, double& dx, double& dy) {
-  const int nk = pb.n_knots;
-  const double* kn = pb.knots + (long long)pid * nk;
-  const double L = kn[nk - 1];
-  int j = (int)((s / L) * (nk - 1));
-  j = max(0, min(nk - 2, j));
-  while (j > 0 && s < kn[j]) --j;
-  while (j < nk - 2 && s >= kn[j + 1]) ++j;
-  const double t = s - kn[j];
-  const double* c = pb.coef + ((long long)pid * (nk - 1) + j) * 8;
-  px = ((c[0] * t + c[1]) * t + c[2]) * t + c[3];
-  py = ((c[4] * t + c[5]) * t + c[6]) * t + c[7];
-  dx = (3.0 * c[0] * t + 2.0 * c[1]) * t + c[2];
-  dy = (3.0 * c[4] * t + 2.0 * c[5]) * t + c[6];
-}
-
-// exact squared distance from P to segment AB (GEOS Distance::pointToSegment, squared;
-// the r<=0 / r>=1 tests are done on the numerator, no division)
-__device__ __forceinline__ double seg_d2(double px, double py, double2 A, double2 B) {
-  const double ex = B.x - A.x, ey = B.y - A.y;
-  const double wx = px - A.x, wy = py - A.y;
-  const double len2 = ex * ex + ey * ey;
-  const double num = wx * ex + wy * ey;
-  if (len2 == 0.0 || num <= 0.0) return wx * wx + wy * wy;
-  if (num >= len2) {
-    const double zx = px - B.x, zy = py - B.y;
-    return zx * zx + zy * zy;
-  }
-  const double cr = wx * ey - wy * ex;
-  return cr * cr / len2;
-}
-
-// GEOS LengthIndexOfPoint::indexOf (LineString.project) restated as an exact three-level
-// search.  Level 2 = superblocks of 32 blocks, level 1 = blocks of 32 segments; each node is
-// a capsule (chord, max deviation) that contains its part of the polyline, so
-//   dist(P, node) in [dc - dev, dc + dev],  dc = dist(P, chord)   (FP32, padded).
-// Pass A finds an upper bound over superblocks, pass B tightens it over the blocks of the
-// surviving superblocks, pass C refines in FP64 every block whose lower bound does not
-// exceed it.  The arg-min is lexicographic in (distance, segment index), which is GEOS's
-// "first minimum wins" independent of visiting order.
-__device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid, double px, double py) {
-  const int v0 = pb.poly_off[pid];
-  const int nseg = pb.poly_off[pid + 1] - v0 - 1;
-  const int b0 = pb.blk_off[pid];
-  const int nblk = pb.blk_off[pid + 1] - b0;
-  const int s0 = pb.sb_off[pid];
-  const int nsb = pb.sb_off[pid + 1] - s0;
-  const double ox = pb.origin[2 * pid], oy = pb.origin[2 * pid + 1];
-  const float qx = (float)(px - ox), qy = (float)(py - oy);
-  const float pad = 1e-6f * (fabsf(qx) + fabsf(qy)) + 1e-6f;
-  const float4* chord = reinterpret_cast<const float4*>(pb.blk_chord) + b0;
-  const float* dev = pb.blk_dev + b0;
-  const float4* sbc = reinterpret_cast<const float4*>(pb.sb_chord) + s0;
-  const float* sbd = pb.sb_dev + s0;
-  const float up = 1.f + 4e-6f, dn = 1.f - 4e-6f;
-  // All node loops below issue their loads in groups of U before any arithmetic, so a
-  // thread has U independent L2 requests in flight instead of one (the kernel is bound by
-  // load latency, not by FP64 issue: profiles/r1b).
-  constexpr int U = 8;
-  float ub = INFINITY;
-  for (int g0 = 0; g0 < nsb; g0 += U) {
-    float4 ch[U];
-    float dv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = min(g0 + u, nsb - 1);
-      ch[u] = sbc[i];
-      dv[u] = sbd[i];
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      ub = fminf(ub, pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * up + dv[u] + pad);
-  }
-  // pass B: tighten over blocks of surviving superblocks; remember which survive
-  unsigned long long live = 0ull;  // up to 64 superblocks tracked exactly, the rest are always visited
-  for (int sb = 0; sb < nsb; ++sb) {
-    const float4 c0 = sbc[sb];
-    const float lb = pt_seg_dist_f(qx, qy, c0.x, c0.y, c0.z, c0.w) * dn - sbd[sb] - pad;
-    if (lb > ub) continue;
-    if (sb < 64) live |= 1ull << sb;
-    const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
-    for (int g0 = sb * AUV_PATH_SUPER; g0 < be; g0 += U) {
-      float4 ch[U];
-      float dv[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = min(g0 + u, be - 1);
-        ch[u] = chord[i];
-        dv[u] = dev[i];
+__device__ __forceinline__ SlotGeom load_slot(const AuvScenarioPool& pool, const AuvBatch& batch, int e, int scn,
+                                              int j, double px, double py) {
+  SlotGeom g;
+  g.valid = g.pent = g.world = false;
+  g.cx = g.cy = g.rho = g.geo = 0.0;
+  g.hx = 1.0;
+  g.hy = 0.0;
+  g.nv = g.vbase = 0;
+  const int km = pool.k_moving, ks = pool.k_static, K = km + ks;
+  if (j >= K) {  // shared world polygon (PolygonObstacle): cached enclosing circle
+    const int wi = j - K;
+    const double* c3 = pool.world_circle + 3ll * wi;
+    g.vbase = pool.world_voff[wi];
+    g.nv = pool.world_voff[wi + 1] - g.vbase;
+    g.valid = g.nv >= 4;
+    g.world = true;
+    g.cx = c3[0] - px;
+    g.cy = c3[1] - py;
+    g.rho = c3[2];
+  } else if (j < km) {  // VesselObstacle: pentagon, enclosing circle of its min-rotated rectangle
+    const long long ps = (long long)scn * km + j, pe = (long long)e * km + j;
+    const double w = pool.mov_width[ps];
+    if (w > 0.0) {
+      const double2 pos = reinterpret_cast<const double2*>(batch.mov_pos)[pe];
+      const double2 dsp = reinterpret_cast<const double2*>(batch.mov_disp)[pe];
+      g.valid = g.pent = true;
+      g.geo = w;
+      const double dl2 = dsp.x * dsp.x + dsp.y * dsp.y;
+      if (dl2 > 0.0) {
+        const double inv = rsqrt(dl2);
+        g.hx = dsp.x * inv;
+        g.hy = dsp.y * inv;
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        ub = fminf(ub, pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * up + dv[u] + pad);
+      // obstacles.py:230-262, SURVEY App. A.3: centre = c + R(th)((w/2,0) - c) + pos, c = (5w/18, 0)
+      g.cx = (pos.x - px) + 5.0 * w / 18.0 + (2.0 * w / 9.0) * g.hx;
+      g.cy = (pos.y - py) + (2.0 * w / 9.0) * g.hy;
+      g.rho = w * 1.1180339887498949;  // sqrt(5)/2
+      g.nv = 6;
+    }
+  } else {  // CircularObstacle: ring = regular n-gon, enclosing circle = (position, radius)
+    const long long ps = (long long)scn * ks + (j - km);
+    const double r = pool.st_radius[ps];
+    if (r > 0.0) {
+      const double2 c = reinterpret_cast<const double2*>(pool.st_pos)[ps];
+      g.valid = true;
+      g.geo = r;
+      g.cx = c.x - px;
+      g.cy = c.y - py;
+      g.rho = r;
+      g.nv = ngon_sides(r) + 1;
     }
   }
-  // pass C: exact refine
-  const double2* poly = reinterpret_cast<const double2*>(pb.poly_xy) + v0;
-  double best_d2 = INFINITY;
-  int best_seg = 0;
-  for (int sb = 0; sb < nsb; ++sb) {
-    if (sb < 64 && !((live >> sb) & 1ull)) continue;
-    const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
-    for (int g0 = sb * AUV_PATH_SUPER; g0 < be; g0 += U) {
-      float4 ch[U];
-      float dv[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = min(g0 + u, be - 1);
-        ch[u] = chord[i];
-        dv[u] = dev[i];
-      }
-      unsigned cand = 0u;
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (g0 + u < be && pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * dn - dv[u] - pad <= ub)
-          cand |= 1u << u;
-      while (cand) {  // blocks in increasing order
-        const int b = g0 + __ffs(cand) - 1;
-        cand &= cand - 1;
-        const int se = min(nseg, (b + 1) * AUV_PATH_BLOCK);
-        for (int k0 = b * AUV_PATH_BLOCK; k0 < se; k0 += U) {
-          double2 v[U + 1];
-#pragma unroll
-          for (int u = 0; u <= U; ++u) v[u] = poly[min(k0 + u, se)];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (k0 + u < se) {
-              const double d2 = seg_d2(px, py, v[u], v[u + 1]);
-              if (d2 < best_d2) {  // segments are visited in increasing k: strict '<' keeps the first
-                best_d2 = d2;
-                best_seg = k0 + u;
-              }
-            }
-          }
+  return g;
+}
+
+__device__ __forceinline__ void cull_env_thread(const AuvConfig& cfg, const AuvScenarioPool& pool,
+                                                const AuvBatch& batch, const double2* __restrict__ unit64,
+                                                int* __restrict__ windows_out, int e, int scn, double px,
+                                                double py, double psi, int step_counter) {
+  const int R = cfg.n_sensors;
+  const int S = pool.k_moving + pool.k_static + pool.n_world;
+  const bool refresh = (step_counter % cfg.sensor_interval_load_obstacles) == 0;
+  const double range = cfg.sensor_range, width = cfg.vessel_width;
+  ObstRec* rec = reinterpret_cast<ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
+  int cnt = 0;
+  for (int base = 0; base < S; base += 32) {
+    unsigned word;
+    unsigned* mw = batch.nearby_mask + (long long)e * batch.mask_words + (base >> 5);
+    if (refresh) {
+      // ---- nearby list: {o : dist(p0, o.boundary) - width < range}   vessel.py:266-273
+      word = 0u;
+      const int jend = min(S, base + 32);
+      for (int j = base; j < jend; ++j) {
+        const SlotGeom g = load_slot(pool, batch, e, scn, j, px, py);
+        if (!g.valid) continue;
+        bool near;
+        const double dc = sqrt(g.cx * g.cx + g.cy * g.cy);
+        if (dc - g.rho - width >= range + 1e-6) {
+          near = false;  // the boundary lies inside the enclosing circle: distance >= dc - rho
+        } else if (dc + g.rho - width < range - 1e-6) {
+          near = true;  // ... and distance <= dc + rho
+        } else {
+          const double bx0 = g.cx - (2.0 * g.geo / 9.0) * g.hx, by0 = g.cy - (2.0 * g.geo / 9.0) * g.hy;
+          bool in_dummy;
+          const double dist =
+              g.world ? world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + g.vbase, g.nv,
+                                               px, py, in_dummy)
+                      : boundary_distance(g.pent, g.cx, g.cy, bx0, by0, g.geo, g.hx, g.hy, g.nv, unit64);
+          near = (dist - width) < range;
         }
+        if (near) word |= 1u << (j - base);
       }
+      *mw = word;
+    } else {
+      word = *mw;
+    }
+    if (windows_out != nullptr) {
+      const int jend = min(S, base + 32);
+      for (int j = base; j < jend; ++j)
+        if (!((word >> (j - base)) & 1u))
+          reinterpret_cast<int2*>(windows_out)[(long long)e * S + j] = make_int2(0, 0);
+    }
+    // ---- one record per nearby obstacle
+    while (word) {
+      const int j = base + __ffs(word) - 1;
+      word &= word - 1;
+      const SlotGeom g = load_slot(pool, batch, e, scn, j, px, py);
+      int wa = 0, wb = 0;
+      bool allrays = false, inside = false;
+      if (g.valid) {
+        int lo, hi;
+        cull_bounds(g.cx, g.cy, g.rho, psi, R, lo, hi);
+        window_from_bounds(lo, hi, R, cfg.cull_mode, wa, wb, allrays);
+      }
+      if (windows_out != nullptr)
+        reinterpret_cast<int2*>(windows_out)[(long long)e * S + j] = g.valid ? make_int2(wa, wb) : make_int2(0, 0);
+      if (!g.valid) continue;
+      const double bx0 = g.cx - (2.0 * g.geo / 9.0) * g.hx, by0 = g.cy - (2.0 * g.geo / 9.0) * g.hy;
+      if (g.cx * g.cx + g.cy * g.cy <= g.rho * g.rho) {  // filled boundaries: own-ship inside => range 0
+        if (g.pent)
+          inside = vessel_inside_pentagon(bx0, by0, g.geo, g.hx, g.hy);
+        else if (g.world)
+          world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + g.vbase, g.nv, px, py, inside);
+      }
+      if (cnt >= batch.rec_cap) {  // cannot happen when rec_cap >= number of slots
+        if (batch.status != nullptr) atomicOr(batch.status, AUV_STATUS_REC_OVERFLOW);
+        continue;
+      }
+      ObstRec r;
+      r.cx = g.pent ? bx0 : g.cx;
+      r.cy = g.pent ? by0 : g.cy;
+      r.geo = g.geo;
+      r.hx = g.hx;
+      r.hy = g.hy;
+      r.ecx = (float)g.cx;
+      r.ecy = (float)g.cy;
+      r.rho = (float)g.rho;
+      r.a = wa;
+      r.b = wb;
+      r.flags = (g.pent ? (OFLAG_FILLED | OFLAG_PENTAGON) : 0) | (g.world ? (OFLAG_FILLED | OFLAG_WORLD) : 0) |
+                (inside ? OFLAG_INSIDE : 0) | (allrays ? OFLAG_ALLRAYS : 0);
+      r.nv = g.nv;
+      r.vbase = g.vbase;
+      rec[cnt++] = r;
     }
   }
-  // segmentNearestMeasure of the winning segment
-  const double2 A = poly[best_seg], B = poly[best_seg + 1];
-  const double start = pb.poly_cum[v0 + best_seg];
-  const double ex = B.x - A.x, ey = B.y - A.y;
-  const double len2 = ex * ex + ey * ey;
-  if (len2 == 0.0) return start;
-  const double r = ((px - A.x) * ex + (py - A.y) * ey) / len2;
-  if (r <= 0.0) return start;
-  const double seglen = sqrt(len2);
-  if (r <= 1.0) return start + r * seglen;
-  return start + seglen;
+  batch.rec_cnt[e] = cnt;
 }
 
-// Vessel.navigate (vessel.py:461-541) for env e; writes nav[e][:] and max_progress[e].
-__device__ __forceinline__ void navigate_thread(const AuvConfig& cfg, const AuvPathBank& pb,
-                                                const AuvBatch& batch, int pid, int e, double px,
-                                                double py, double psi) {
-  const double s = project_thread(pb, pid, px, py);
-  const double L = pb.length[pid];
-  const double s_la = fmin(L, s + cfg.look_ahead_distance);
-  double p_x, p_y, d_x, d_y, l_x, l_y, ldx, ldy;
-  pchip_eval(pb, pid, s, p_x, p_y, d_x, d_y);
-  pchip_eval(pb, pid, s_la, l_x, l_y, ldx, ldy);
-  const double chi = atan2(d_y, d_x);
-  double sc, cc;
-  sincos(chi, &sc, &cc);
-  const double y_e = -sc * (p_x - px) + cc * (p_y - py);
-  const double la_err = princip(atan2(ldy, ldx) - psi);
-  const double head_err = princip(atan2(l_y - py, l_x - px) - psi);
-  const double progress = s / L;
-  const double gx = pb.end_xy[2 * pid] - px, gy = pb.end_xy[2 * pid + 1] - py;
-  const double goal = sqrt(gx * gx + gy * gy);
-  const bool reached = (goal <= cfg.min_goal_distance) || (progress >= cfg.min_path_progress);
-  double sp, cp;
-  sincos(psi, &sp, &cp);
-  double* o = batch.nav + (long long)e * AUV_NAV_W;
-  o[NAV_S] = s;
-  o[NAV_CHI] = chi;
-  o[NAV_YE] = y_e;
-  o[NAV_SLA] = s_la;
-  o[NAV_LA_ERR] = la_err;
-  o[NAV_HEAD_ERR] = head_err;
-  o[NAV_GOAL] = goal;
-  o[NAV_PROGRESS] = progress;
-  o[NAV_COSPSI] = cp;
-  o[NAV_SINPSI] = sp;
-  o[NAV_REACHED] = reached ? 1.0 : 0.0;
-  o[NAV_COS_HEAD_ERR] = cos(head_err);
-  batch.max_progress[e] = fmax(progress, batch.max_progress[e]);  // vessel.py:507
-}
-
-// Vessel.step fused with Vessel.navigate (DYN) or navigate only (reset / staged observe):
-// the state never leaves registers between the RK step and the projection.
+// Vessel.step fused with Vessel.navigate and the culling stage (DYN), or navigate + culling
+// only (reset / staged observe): the state never leaves registers in between.
 template <bool DYN>
-__global__ void __launch_bounds__(128) k_vessel_nav(const __grid_constant__ AuvConfig cfg,
-                                                     const __grid_constant__ AuvPathBank paths,
-                                                     const __grid_constant__ AuvScenarioPool pool,
-                                                     const __grid_constant__ AuvBatch batch,
-                                                     const float* __restrict__ actions) {
+__global__ void __launch_bounds__(64) k_vessel_nav(const __grid_constant__ AuvConfig cfg,
+                                                    const __grid_constant__ AuvPathBank paths,
+                                                    const __grid_constant__ AuvScenarioPool pool,
+                                                    const __grid_constant__ AuvBatch batch,
+                                                    const double2* __restrict__ unit64,
+                                                    int* __restrict__ windows_out,
+                                                    const float* __restrict__ actions) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = batch.n_envs;
   if (e >= n) return;
   S6 y = load_state(batch.state, n, e);
+  int step_counter = batch.step_counter[e];
   if (DYN) {
     y = vessel_rk_step(cfg, y, reinterpret_cast<const float2*>(actions)[e]);
     store_state(batch.state, n, e, y);
-    batch.step_counter[e] += 1;
+    batch.step_counter[e] = ++step_counter;
   }
-  navigate_thread(cfg, paths, batch, pool.path_id[batch.scn_id[e]], e, y.x, y.y, y.psi);
+  const int scn = batch.scn_id[e];
+  navigate_thread(cfg, paths, batch, pool.path_id[scn], e, y.x, y.y, y.psi);
+  if (cfg.use_lidar) cull_env_thread(cfg, pool, batch, unit64, windows_out, e, scn, y.x, y.y, y.psi, step_counter);
 }
 
 // ------------------------------------------------------------------------------------
-// LiDAR
+// k_lidar: CTA per env, thread per ray
 // ------------------------------------------------------------------------------------
-constexpr int VMAX = 320;          // staged vertices per warp per batch (float2)
-#ifndef AUV_WARPS_PER_BLOCK
-#define AUV_WARPS_PER_BLOCK 4
+constexpr int VMAX = 192;  // staged vertices per warp per round (float2)
+constexpr int RROUND = 6;  // records per round: 6 x 80 B = 30 lanes x 16 B, one coalesced load
+#ifndef AUV_LIDAR_WARPS
+#define AUV_LIDAR_WARPS 8  // envs per CTA (the warps of a CTA never synchronise with each other)
 #endif
-constexpr int WARPS_PER_BLOCK = AUV_WARPS_PER_BLOCK;  // envs per CTA (warps never synchronise with each other)
 
-struct __align__(16) WarpScratch {
-  float2 verts[VMAX];
-  float ocx[32], ocy[32], orho[32];
-  int oa[32], ob[32], ovoff[32], onv[32], oflag[32];
-};
-#define OFLAG_FILLED 1
-#define OFLAG_INSIDE 2
-#define OFLAG_ALLRAYS 4
-#define OFLAG_PENTAGON 8
-#define OFLAG_WORLD 16
-
-// body-frame pentagon of VesselObstacle relative to its area centroid (5w/18, 0), in
-// units of w     obstacles.py:175-181
-__constant__ double c_pent[5][2] = {{-7.0 / 9.0, -0.5}, {-7.0 / 9.0, 0.5}, {2.0 / 9.0, 0.5},
-                                    {11.0 / 9.0, 0.0},  {2.0 / 9.0, -0.5}};
-
-// culling window (sensor.py:22-97):  a = floor((pi+beta-delta)/dth) - 1,
-// b = ceil((pi+beta+delta)/dth) mod R (Python modulo); candidate(i) <=> a<=i<b or a<=i-R<b.
-// lo/hi are the raw floor/ceil values.
-__device__ __forceinline__ void window_from_bounds(int lo, int hi, int R, int mode, int& a, int& b,
-                                                   bool& allrays) {
-  allrays = false;
-  if (mode == AUV_CULL_EXACT) {
-    // every ray whose index is in [lo-1, hi) modulo R
-    if (hi - (lo - 1) >= R) {
-      allrays = true;
-      a = 0;
-      b = R;
-    } else {
-      int s = (lo - 1) % R;
-      if (s < 0) s += R;
-      a = s;
-      b = s + (hi - (lo - 1));
-      if (b > R) {  // wraps: express as a negative start
-        a -= R;
-        b -= R;
-      }
-    }
-    return;
-  }
-  a = lo - 1;
-  int m = hi % R;
-  if (m < 0) m += R;
-  b = m;
-  if (a < -R) allrays = true;  // IndexError in the reference: defined as all rays
-}
-
-__device__ __noinline__ void cull_bounds_f64(double cx, double cy, double rho, double psi, double dth,
-                                             int& lo, int& hi) {
-  const double dist = fmax(1e-8, sqrt(cx * cx + cy * cy));
-  const double ratio = rho / dist;
-  const double delta = ratio <= 1.0 ? asin(ratio) : AUV_PI;  // np.arcsin -> nan -> pi
-  const double beta = atan2(cy, cx) - psi;
-  lo = (int)floor((AUV_PI + (beta - delta)) / dth);
-  hi = (int)ceil((AUV_PI + (beta + delta)) / dth);
-}
-
-// FP32 fast path; falls back to FP64 whenever a quotient is within GUARD of an integer or
-// the asin argument is near 1, so the integers are always those of the FP64 formula.
-__device__ __forceinline__ void cull_bounds(double cx, double cy, double rho, double psi, int R,
-                                            int& lo, int& hi) {
-  const double dth = 2.0 * AUV_PI / (double)R;
-  const float fx = (float)cx, fy = (float)cy, fr = (float)rho;
-  const float dist = fmaxf(1e-8f, sqrtf(fx * fx + fy * fy));
-  const float ratio = fr / dist;
-  bool exact = ratio > 0.98f;  // asin' blows up near 1 and the <=1 decision itself is a threshold
-  if (!exact) {
-    const float inv = (float)(1.0 / dth);
-    const float delta = asinf(ratio);
-    const float beta = atan2f(fy, fx) - (float)psi;
-    const float qlo = ((float)AUV_PI + (beta - delta)) * inv;
-    const float qhi = ((float)AUV_PI + (beta + delta)) * inv;
-    const float flo = floorf(qlo), chi = ceilf(qhi);
-    const float GUARD = 4e-4f;  // >> atan2f/asinf error (~1e-6 rad) / dth + ulp(360)
-    exact = (qlo - flo < GUARD) || (flo + 1.f - qlo < GUARD) || (chi - qhi < GUARD) || (qhi - (chi - 1.f) < GUARD);
-    lo = (int)flo;
-    hi = (int)chi;
-  }
-  if (exact) cull_bounds_f64(cx, cy, rho, psi, dth, lo, hi);
-}
-
-// LidarPreprocessor._feasibility_pooling (sensor.py:251-296) for one sector: the largest
-// range d such that no opening wider than `width` exists among the rays that see farther
-// than d + width.  m[0..n) are the sector's ranges (shared memory), FP64 arithmetic on the
-// FP32 ranges.  Candidates are visited in increasing range order (np.argsort; ties are
-// equal values so their order cannot change the result).
-__device__ __forceinline__ float feasibility_pooling(const float* m, int n, double width, double theta) {
-  // every FP64 operation is an explicit round-to-nearest intrinsic: the algorithm is a chain
-  // of threshold tests on accumulated sums, so FMA contraction would change its decisions
-  const double span = __dmul_rn(theta, (double)(n - 1));
-  const double half = span / 2.0, quarter = span / 4.0;
-  float prev = -1.f;
-  int prev_cnt = 0;  // how many rays with value == prev have been consumed already
-  float maxv = 0.f;
-  for (int i = 0; i < n; ++i) maxv = fmaxf(maxv, m[i]);
-  for (int it = 0; it < n; ++it) {
-    // next value in sorted order: smallest > prev, or another copy of prev
-    int same = 0;
-    float next = INFINITY;
-    for (int i = 0; i < n; ++i) {
-      const float v = m[i];
-      if (v == prev) ++same;
-      else if (v > prev) next = fminf(next, v);
-    }
-    float cur;
-    if (prev_cnt < same) {
-      cur = prev;
-      ++prev_cnt;
-    } else {
-      cur = next;
-      prev = next;
-      prev_cnt = 1;
-    }
-    const double dcur = (double)cur;
-    const double d = __dmul_rn(dcur, theta), hd = __dmul_rn(0.5, d), ht = __dmul_rn(0.5, theta);
-    const double thr = __dadd_rn(dcur, width);
-    double ow = 0.0, os = 0.0, ostart = -half;
-    bool found = false;
-    for (int i = 0; i < n; ++i) {
-      if ((double)m[i] > thr) {
-        ow = __dadd_rn(ow, d);
-        os = __dadd_rn(os, theta);
-        if (ow > width && fabs(__dadd_rn(ostart, os / 2.0)) < quarter) found = true;
-      } else {
-        ow = __dadd_rn(ow, hd);
-        os = __dadd_rn(os, ht);
-        if (ow > width && fabs(__dadd_rn(ostart, os / 2.0)) < quarter) found = true;
-        ow = 0.0;
-        os = 0.0;
-        ostart = __dadd_rn(-half, __dmul_rn((double)i, theta));
-      }
-    }
-    if (!found) return fmaxf(0.f, cur);
-  }
-  return fmaxf(0.f, maxv);
-}
-
-struct ObserveArgs {
+struct LidarArgs {
   AuvConfig cfg;
   AuvRayTable rays;
   AuvPathBank paths;
   AuvScenarioPool pool;
   AuvBatch batch;
   AuvStepOut out;
-  int mode;
+  int mode;       // AUV_OBSERVE_STEP | AUV_OBSERVE_RESET
   int obs_dim;
-  float pen_clear;  // sum_i w_i * range * exp(-0.1 range): penalty sum when every ray reads sensor_range
-  float pen_clear_ray;     // range * exp(-0.1 range)
+  float pen_clear_ray;     // range * exp(-0.1 range): penalty term of a ray that reads sensor_range
+  double clear_closeness;  // -range * exp(-0.1 range): closeness reward when every ray is clear
   double feas_width;       // vessel_width * feasibility_width_multiplier (sensor.py:166-168)
-  double clear_closeness;  // -range * exp(-0.1 range): closeness reward with no LiDAR at all
 };
 
-// pentagon vertex k of a vessel obstacle, relative to the own-ship: base (bx,by) is the
-// rotation centre (area centroid) in vessel-relative coordinates
-__device__ __forceinline__ void pent_vertex(int k, double bx, double by, double w, double hx, double hy,
-                                            double& vx, double& vy) {
-  vx = bx + w * (hx * c_pent[k][0] - hy * c_pent[k][1]);
-  vy = by + w * (hy * c_pent[k][0] + hx * c_pent[k][1]);
-}
+struct __align__(16) WarpSmem {
+  float2 verts[VMAX];
+  ObstRec rec[RROUND];
+  int voff[RROUND + 1];
+  int pad;
+};
+// lanes of the per-env scalar pack (one register per lane, read back by shuffle)
+#define SC_STATE 12
+#define SC_CUM 18
+#define SC_CTE 19
+#define SC_MAXPROG 20
+#define SC_TSTEP 21
+#define SC_SCN 22
+#define SC_CNT 23
 
-// ---- shared static world polygons (PolygonObstacle, obstacles.py:116-127): FILLED.
-// distance from the own-ship to the filled polygon / crossing-number inside test, on
-// vessel-relative FP32 vertices formed in FP64.  Cold (nearby refresh / own-ship within
-// the enclosing circle only).
-__device__ __forceinline__ double world_polygon_distance(const double2* __restrict__ v, int nv, double px,
-                                                         double py, bool& inside) {
-  float dmin = INFINITY;
-  bool in = false;
-  float ax = (float)(v[0].x - px), ay = (float)(v[0].y - py);
-  for (int k = 1; k < nv; ++k) {
-    const float bx = (float)(v[k].x - px), by = (float)(v[k].y - py);
-    dmin = fminf(dmin, pt_seg_dist_f(0.f, 0.f, ax, ay, bx, by));
-    if ((ay > 0.f) != (by > 0.f)) {  // edge straddles the +x axis through the own-ship
-      const float xint = ax + (0.f - ay) * (bx - ax) / (by - ay);
-      if (xint > 0.f) in = !in;
-    }
-    ax = bx;
-    ay = by;
-  }
-  inside = in;
-  return in ? 0.0 : (double)dmin;
-}
-
-// Point.distance(obstacle.boundary) from the own-ship (vessel.py:269): min over the edges
-// of the polygonised circle (ring) or 0 / min over edges for the filled vessel pentagon.
-// FP32 on vessel-relative vertices formed in FP64.  Cold (only on nearby-list refresh and
-// only for obstacles whose enclosing circle straddles the range limit).
-__device__ __forceinline__ double boundary_distance(bool pent, double cx, double cy, double bx0, double by0,
-                                                 double geo, double hx, double hy, int nv_cnt,
-                                                 const double2* __restrict__ unit) {
-  float dmin = INFINITY;
-  const int ne = nv_cnt - 1;
-  double vx, vy;
-  if (pent) {
-    pent_vertex(0, bx0, by0, geo, hx, hy, vx, vy);
-  } else {
-    vx = cx + geo;
-    vy = cy;
-  }
-  float pxv = (float)vx, pyv = (float)vy;
-  bool allpos = true, allneg = true;
-  for (int k = 1; k <= ne; ++k) {
-    const int kk = (k == ne) ? 0 : k;
-    if (pent) {
-      pent_vertex(kk, bx0, by0, geo, hx, hy, vx, vy);
-    } else {
-      const double2 un = __ldg(&unit[kk * (64 / ne)]);
-      vx = cx + geo * un.x;
-      vy = cy + geo * un.y;
-    }
-    const float qx = (float)vx, qy = (float)vy;
-    dmin = fminf(dmin, pt_seg_dist_f(0.f, 0.f, pxv, pyv, qx, qy));
-    const float cr = pxv * qy - pyv * qx;  // cross(prev, cur) about the vessel
-    allpos = allpos && (cr >= 0.f);
-    allneg = allneg && (cr <= 0.f);
-    pxv = qx;
-    pyv = qy;
-  }
-  const bool inside = pent && (allpos || allneg);
-  return inside ? 0.0 : (double)dmin;
-}
-
-// is the own-ship (origin) inside the convex vessel pentagon?  FP64.
-__device__ __forceinline__ bool vessel_inside_pentagon(double bx0, double by0, double geo, double hx, double hy) {
-  bool allpos = true, allneg = true;
-  double pvx, pvy, vx, vy;
-  pent_vertex(4, bx0, by0, geo, hx, hy, pvx, pvy);
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    pent_vertex(k, bx0, by0, geo, hx, hy, vx, vy);
-    const double cr = pvx * vy - pvy * vx;
-    allpos = allpos && (cr >= 0.0);
-    allneg = allneg && (cr <= 0.0);
-    pvx = vx;
-    pvy = vy;
-  }
-  return allpos || allneg;
-}
-
-#ifndef AUV_OBSERVE_WARPS_PER_SM
-#define AUV_OBSERVE_WARPS_PER_SM 20  // 96 registers/thread: spills cost more than occupancy gains (profiles/r1c)
-#endif
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUV_OBSERVE_WARPS_PER_SM / WARPS_PER_BLOCK)
-    k_observe(const __grid_constant__ ObserveArgs A) {
+__global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32) k_lidar(const __grid_constant__ LidarArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const double2* __restrict__ s_unit = reinterpret_cast<const double2*>(A.rays.unit64);  // cos/sin(2 pi k/64)
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int R = A.cfg.n_sensors;
-  const int rpad = (R + 31) & ~31;
-  const size_t per_warp = sizeof(WarpScratch) + sizeof(float) * rpad;
-  WarpScratch& W = *reinterpret_cast<WarpScratch*>(smem_raw + per_warp * wib);
-  float* sdist = reinterpret_cast<float*>(smem_raw + per_warp * wib + sizeof(WarpScratch));
-  const int e = blockIdx.x * WARPS_PER_BLOCK + wib;
-  const int n = A.batch.n_envs;
-  if (e >= n) return;
-  const AuvBatch& batch = A.batch;
-  const AuvScenarioPool& pool = A.pool;
   const AuvConfig& cfg = A.cfg;
-  const int km = pool.k_moving, ks = pool.k_static, K = km + ks;
-  const int S = K + pool.n_world;  // obstacle slots: moving, static circles, shared world polygons
-  const double range = cfg.sensor_range;
-  const float rangef = (float)range;
+  const AuvBatch& batch = A.batch;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int n = batch.n_envs;
+  const int e = blockIdx.x * AUV_LIDAR_WARPS + wib;
+  if (e >= n) return;
+  const int R = cfg.n_sensors;
+  const int rpad = cfg.use_lidar ? ((R + 31) & ~31) : 32;
+  const size_t per_warp = sizeof(WarpSmem) + sizeof(float) * rpad;
+  WarpSmem& sm = *reinterpret_cast<WarpSmem*>(smem_raw + per_warp * wib);
+  float* sdist = reinterpret_cast<float*>(smem_raw + per_warp * wib + sizeof(WarpSmem));
+  const float rangef = (float)cfg.sensor_range;
   const float widthf = (float)cfg.vessel_width;
-  int mode = A.mode;
+  float* obs = A.out.obs + (long long)e * A.obs_dim;
+  const bool pooling = A.out.sector_min_dist != nullptr || A.out.sector_feasible_dist != nullptr;
+  const uint4* grec4 = reinterpret_cast<const uint4*>(reinterpret_cast<const ObstRec*>(batch.rec) +
+                                                      (long long)e * batch.rec_cap);
 
-  for (int pass = 0; pass < 2; ++pass) {
-    // Every per-env scalar is fetched up front by a different lane (three independent
-    // 1-sector loads in flight together) and broadcast by shuffle when needed:
-    //   navv: lanes 0..11 = navigation record written by k_vessel_nav (or by lane 0 below
-    //         after an auto-reset);  stv: lanes 0..5 = x, y, psi, u, v, r;
-    //   auxv: lane 0 cum_reward, 1 cte_sum, 2 max_progress, 3 t_step, 4 step_counter, 5 scn_id
-    double navv = 0.0, stv = 0.0, auxv = 0.0;
-    if (lane < AUV_NAV_W) navv = batch.nav[(long long)e * AUV_NAV_W + lane];
-    if (lane < 6) stv = batch.state[(long long)lane * n + e];
-    if (lane == 0) auxv = batch.cum_reward[e];
-    if (lane == 1) auxv = batch.cte_sum[e];
-    if (lane == 2) auxv = batch.max_progress[e];
-    if (lane == 3) auxv = (double)batch.t_step[e];
-    if (lane == 4) auxv = (double)batch.step_counter[e];
-    if (lane == 5) auxv = (double)batch.scn_id[e];
-    unsigned maskv = 0u;  // lane w holds word w of the nearby list (<= 32 words = 1024 slots)
-    if (cfg.use_lidar && lane < batch.mask_words) maskv = batch.nearby_mask[(long long)e * batch.mask_words + lane];
-    const int scn = (int)__shfl_sync(AUV_FULL, auxv, 5);
-    const double px = __shfl_sync(AUV_FULL, stv, 0), py = __shfl_sync(AUV_FULL, stv, 1);
-    const double psi = __shfl_sync(AUV_FULL, stv, 2);
-    const int step_counter = (int)__shfl_sync(AUV_FULL, auxv, 4);
+  // ---- one round trip: every per-env scalar is fetched by a different lane, and the first
+  //      RROUND records are fetched speculatively (30 lanes x 16 B) before their count is known
+  double sc = 0.0;
+  if (lane < AUV_NAV_W) sc = batch.nav[(long long)e * AUV_NAV_W + lane];
+  else if (lane < SC_STATE + 6) sc = batch.state[(long long)(lane - SC_STATE) * n + e];
+  else if (lane == SC_CUM) sc = batch.cum_reward[e];
+  else if (lane == SC_CTE) sc = batch.cte_sum[e];
+  else if (lane == SC_MAXPROG) sc = batch.max_progress[e];
+  else if (lane == SC_TSTEP) sc = (double)batch.t_step[e];
+  else if (lane == SC_SCN) sc = (double)batch.scn_id[e];
+  else if (lane == SC_CNT) sc = cfg.use_lidar ? (double)batch.rec_cnt[e] : 0.0;
+  uint4 spec = make_uint4(0, 0, 0, 0);
+  if (cfg.use_lidar && lane < RROUND * 5 && lane / 5 < batch.rec_cap) spec = grec4[lane];
+#define SCAL(k) __shfl_sync(AUV_FULL, sc, (k))
 
-    float* obs = A.out.obs + (long long)e * A.obs_dim;
-    bool collision = false;
-    float pen_sum = 0.f;       // sum_i w_i * range * exp(-0.1 d_i)
-    unsigned long long ntests = 0;
-
-    if (cfg.use_lidar) {
-      // ---------------- perceive ----------------
-      const bool refresh = (step_counter % cfg.sensor_interval_load_obstacles) == 0;
+  bool collision = false;
+  float pen = 0.f;
+  unsigned long long ntests = 0;
+  if (cfg.use_lidar) {
+    const int cnt = (int)SCAL(SC_CNT);
+    if (cnt > 0) {
+      const double px = SCAL(SC_STATE), py = SCAL(SC_STATE + 1), psi = SCAL(SC_STATE + 2);
+      const double cpsi = SCAL(NAV_COSPSI), spsi = SCAL(NAV_SINPSI);
       const double dth_d = 2.0 * AUV_PI / (double)R;
-      const double cpsi = __shfl_sync(AUV_FULL, navv, NAV_COSPSI), spsi = __shfl_sync(AUV_FULL, navv, NAV_SINPSI);
-      bool any_active = false;
-      for (int base = 0; base < S; base += 32) {
-        const int j = base + lane;
-        unsigned word = 0u;
-        if (!refresh) {
-          word = __shfl_sync(AUV_FULL, maskv, base >> 5);
-          if (word == 0u) {
-            if (A.out.windows != nullptr && j < S)
-              reinterpret_cast<int2*>(A.out.windows)[(long long)e * S + j] = make_int2(0, 0);
-            continue;  // nothing of this chunk is on the nearby list: no loads at all
-          }
-        }
-        // only obstacles that are (or may become) nearby are loaded
-        const bool want = j < S && (refresh || ((word >> lane) & 1u));
-        bool valid = false;
-        bool pent = false, world = false;
-        double cx = 0, cy = 0, rho = 0, geo = 0, hx = 1.0, hy = 0.0;
-        int nv_cnt = 0;  // vertices incl. closing one
-        int vbase = 0;   // world polygon: first vertex
-        if (want) {
-          if (j >= K) {
-            const int wi = j - K;
-            const double* c3 = pool.world_circle + 3ll * wi;
-            vbase = pool.world_voff[wi];
-            nv_cnt = pool.world_voff[wi + 1] - vbase;
-            valid = nv_cnt >= 4;
-            world = true;
-            cx = c3[0] - px;
-            cy = c3[1] - py;
-            rho = c3[2];
-          } else if (j < km) {
-            const long long ps = (long long)scn * km + j, pe = (long long)e * km + j;
-            const double w = pool.mov_width[ps];
-            const double2 pos = reinterpret_cast<const double2*>(batch.mov_pos)[pe];
-            const double2 dsp = reinterpret_cast<const double2*>(batch.mov_disp)[pe];
-            if (w > 0.0) {
-              valid = true;
-              pent = true;
-              geo = w;
-              const double dl2 = dsp.x * dsp.x + dsp.y * dsp.y;
-              if (dl2 > 0.0) {
-                const double inv = rsqrt(dl2);
-                hx = dsp.x * inv;
-                hy = dsp.y * inv;
-              }
-              // enclosing circle of the min-rotated rectangle (obstacles.py:230-262; App. A.3)
-              cx = (pos.x - px) + 5.0 * w / 18.0 + (2.0 * w / 9.0) * hx;
-              cy = (pos.y - py) + (2.0 * w / 9.0) * hy;
-              rho = w * 1.1180339887498949;  // sqrt(5)/2
-              nv_cnt = 6;
+      const double2* __restrict__ unit = reinterpret_cast<const double2*>(A.rays.unit64);
+      uint4* srec4 = reinterpret_cast<uint4*>(sm.rec);
+      for (int r0 = 0; r0 < cnt;) {
+        // ---- round: up to RROUND records, bounded by the vertex budget
+        __syncwarp();
+        if (lane < RROUND * 5) srec4[lane] = r0 == 0 ? spec : ((r0 + lane / 5 < cnt) ? grec4[r0 * 5 + lane] : spec);
+        __syncwarp();
+        int nvv = 0;
+        if (lane < RROUND && r0 + lane < cnt) nvv = sm.rec[lane].nv;
+        const int incl = warp_incl_scan(nvv, lane);
+        const unsigned fm = __ballot_sync(AUV_FULL, nvv > 0 && incl <= VMAX);
+        const int take = max(1, fm == AUV_FULL ? 32 : __ffs(~fm) - 1);  // a prefix: incl is monotone
+        if (lane < take) sm.voff[lane] = incl - nvv;
+        __syncwarp();
+        const int nr = take;
+        // ---- stage vertices: vessel-relative, formed in FP64, stored FP32
+        for (int rr = 0; rr < nr; ++rr) {
+          const ObstRec& q = sm.rec[rr];
+          const int off = sm.voff[rr], nq = q.nv;
+          if (q.flags & OFLAG_WORLD) {
+            const double2* wv = reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase;
+            for (int k = lane; k < nq; k += 32) {
+              const double2 w = wv[k];
+              sm.verts[off + k] = make_float2((float)(w.x - px), (float)(w.y - py));
+            }
+          } else if (q.flags & OFLAG_PENTAGON) {
+            if (lane < 6) {
+              double vx, vy;
+              pent_vertex(lane == 5 ? 0 : lane, q.cx, q.cy, q.geo, q.hx, q.hy, vx, vy);
+              sm.verts[off + lane] = make_float2((float)vx, (float)vy);
             }
           } else {
-            const long long ps = (long long)scn * ks + (j - km);
-            const double r = pool.st_radius[ps];
-            const double2 c = reinterpret_cast<const double2*>(pool.st_pos)[ps];
-            if (r > 0.0) {
-              valid = true;
-              geo = r;
-              cx = c.x - px;
-              cy = c.y - py;
-              rho = r;
-              nv_cnt = ngon_sides(r) + 1;
+            const int ne = nq - 1, stride = 64 / ne;
+            for (int k = lane; k < nq; k += 32) {
+              const double2 un = __ldg(&unit[(k == ne ? 0 : k) * stride]);
+              sm.verts[off + k] = make_float2((float)(q.cx + q.geo * un.x), (float)(q.cy + q.geo * un.y));
             }
           }
         }
-        // rotation centre of the pentagon, vessel-relative: V_k = b + w R(heading) P'_k
-        const double bx0 = cx - (2.0 * geo / 9.0) * hx, by0 = cy - (2.0 * geo / 9.0) * hy;
-
-        // ---- nearby list: refreshed every sensor_interval_load_obstacles vessel steps
-        if (refresh) {
-          bool near = false;
-          if (valid) {
-            // cheap conservative pre-tests on the enclosing circle (exact test only in between)
-            const double dc = sqrt(cx * cx + cy * cy);
-            if (dc - rho - cfg.vessel_width >= range + 1e-6) {
-              near = false;  // boundary lies inside the circle: distance >= dc - rho
-            } else if (dc + rho - cfg.vessel_width < range - 1e-6) {
-              near = true;  // the boundary lies inside the circle: distance <= dc + rho
-            } else {
-              bool in_dummy;
-              const double dist =
-                  world ? world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + vbase, nv_cnt,
-                                                 px, py, in_dummy)
-                        : boundary_distance(pent, cx, cy, bx0, by0, geo, hx, hy, nv_cnt, s_unit);
-              near = (dist - cfg.vessel_width) < range;  // vessel.py:269-270
+        __syncwarp();
+        // ---- cast: lanes over rays
+        for (int i = lane; i < R; i += 32) {
+          const double2 cs = reinterpret_cast<const double2*>(A.rays.cos_sin)[i];
+          const float c = (float)(cs.x * cpsi - cs.y * spsi);
+          const float s = (float)(cs.y * cpsi + cs.x * spsi);
+          const float theta = (float)((-AUV_PI + (double)(i + 1) * dth_d) + psi);  // world angle of ray i
+          float best = r0 == 0 ? rangef : sdist[i];
+          for (int rr = 0; rr < nr; ++rr) {
+            const ObstRec& q = sm.rec[rr];
+            const int oa = q.a, ob = q.b, fl = q.flags;
+            // candidate(i) <=> a<=i<b or a<=i-R<b (Python negative-index wrap, sensor.py:93-95);
+            // an obstacle whose window is wider than R is listed -- and tested -- twice upstream
+            const int hits = ((oa <= i && i < ob) ? 1 : 0) + ((oa <= i - R && i - R < ob) ? 1 : 0);
+            if (!((fl & OFLAG_ALLRAYS) || hits > 0)) continue;
+            const int nq = q.nv;
+            ntests += (unsigned)((nq - 1) * max(hits, 1));
+            if (fl & OFLAG_INSIDE) {
+              best = 0.f;
+              continue;
             }
-          }
-          word = __ballot_sync(AUV_FULL, near);
-          if (lane == 0) batch.nearby_mask[(long long)e * batch.mask_words + (base >> 5)] = word;
-        }
-        const bool active = valid && ((word >> lane) & 1u);
-
-        int wa = 0, wb = 0;
-        bool allrays = false, inside = false;
-        if (active) {
-          int lo, hi;
-          cull_bounds(cx, cy, rho, psi, R, lo, hi);
-          window_from_bounds(lo, hi, R, cfg.cull_mode, wa, wb, allrays);
-          if (pent && cx * cx + cy * cy <= rho * rho) {
-            inside = vessel_inside_pentagon(bx0, by0, geo, hx, hy);  // range 0, SURVEY A.5
-          } else if (world && cx * cx + cy * cy <= rho * rho) {
-            world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + vbase, nv_cnt, px, py, inside);
-          }
-        }
-        if (A.out.windows != nullptr && j < S) {
-          int2 wv = active ? make_int2(wa, wb) : make_int2(0, 0);
-          reinterpret_cast<int2*>(A.out.windows)[(long long)e * S + j] = wv;
-        }
-
-        // ---- stage active obstacles in batches bounded by the vertex budget
-        unsigned rem = __ballot_sync(AUV_FULL, active);
-        while (rem) {
-          if (!any_active) {
-            for (int i = lane; i < rpad; i += 32) sdist[i] = rangef;
-            any_active = true;
-          }
-          const bool mine = (rem >> lane) & 1u;
-          const int cnt = mine ? nv_cnt : 0;
-          const int incl = warp_incl_scan(cnt, lane);
-          const bool take = mine && incl <= VMAX;
-          const unsigned tk = __ballot_sync(AUV_FULL, take);
-          const int nact = __popc(tk);
-          if (take) {
-            const int ci = __popc(tk & ((1u << lane) - 1u));
-            W.ocx[ci] = (float)cx;
-            W.ocy[ci] = (float)cy;
-            W.orho[ci] = (float)rho;
-            W.oa[ci] = wa;
-            W.ob[ci] = wb;
-            W.ovoff[ci] = incl - cnt;
-            W.onv[ci] = nv_cnt;
-            W.oflag[ci] = (pent ? (OFLAG_FILLED | OFLAG_PENTAGON) : 0) | (world ? (OFLAG_FILLED | OFLAG_WORLD) : 0) |
-                          (inside ? OFLAG_INSIDE : 0) | (allrays ? OFLAG_ALLRAYS : 0);
-          }
-          rem &= ~tk;
-          __syncwarp();
-          // vertices: vessel-relative, formed in FP64, stored FP32.  The owning lane's
-          // FP64 parameters are broadcast by shuffle (no FP64 staging in shared memory).
-          {
-            const double bcx = pent ? bx0 : cx, bcy = pent ? by0 : cy;  // rotation centre | circle centre
-            unsigned todo = tk;
-            int i = 0;
-            while (todo) {
-              const int src = __ffs(todo) - 1;
-              todo &= todo - 1;
-              const double ox = __shfl_sync(AUV_FULL, bcx, src), oy = __shfl_sync(AUV_FULL, bcy, src);
-              const double g = __shfl_sync(AUV_FULL, geo, src);
-              const int nvv = W.onv[i], off = W.ovoff[i];
-              if (W.oflag[i] & OFLAG_WORLD) {
-                const int vb = __shfl_sync(AUV_FULL, vbase, src);
-                const double2* wv = reinterpret_cast<const double2*>(pool.world_verts) + vb;
-                for (int k = lane; k < nvv; k += 32) {
-                  const double2 q = wv[k];
-                  W.verts[off + k] = make_float2((float)(q.x - px), (float)(q.y - py));
-                }
-              } else if (W.oflag[i] & OFLAG_PENTAGON) {
-                const double h_x = __shfl_sync(AUV_FULL, hx, src), h_y = __shfl_sync(AUV_FULL, hy, src);
-                if (lane < 6) {
-                  double vx, vy;
-                  pent_vertex(lane == 5 ? 0 : lane, ox, oy, g, h_x, h_y, vx, vy);
-                  W.verts[off + lane] = make_float2((float)vx, (float)vy);
-                }
-              } else {
-                const int ne = nvv - 1;
-                const int stride = 64 / ne;
-                for (int k = lane; k < nvv; k += 32) {
-                  const double2 un = __ldg(&s_unit[(k == ne ? 0 : k) * stride]);
-                  W.verts[off + k] = make_float2((float)(ox + g * un.x), (float)(oy + g * un.y));
-                }
-              }
-              ++i;
-            }
-          }
-          __syncwarp();
-          // ---- rays: lanes over rays, loop over staged obstacles
-          for (int i0 = 0; i0 < R; i0 += 32) {
-            const int i = i0 + lane;
-            if (i < R) {
-              const double2 cs = reinterpret_cast<const double2*>(A.rays.cos_sin)[i];
-              const float c = (float)(cs.x * cpsi - cs.y * spsi);
-              const float s = (float)(cs.y * cpsi + cs.x * spsi);
-              const float theta = (float)((-AUV_PI + (double)(i + 1) * dth_d) + psi);  // world angle of ray i
-              float best = sdist[i];
-              for (int o = 0; o < nact; ++o) {
-                const int oa = W.oa[o], ob = W.ob[o], fl = W.oflag[o];
-                // candidate(i) <=> a<=i<b or a<=i-R<b (Python negative-index wrap); an obstacle
-                // whose window is wider than R is listed -- and tested -- twice by the reference
-                const int hits = ((oa <= i && i < ob) ? 1 : 0) + ((oa <= i - R && i - R < ob) ? 1 : 0);
-                const bool inwin = (fl & OFLAG_ALLRAYS) || hits > 0;
-                if (!inwin) continue;
-                const int nvv = W.onv[o];
-                ntests += (unsigned)((nvv - 1) * max(hits, 1));
-                if (fl & OFLAG_INSIDE) {
-                  best = 0.f;
-                  continue;
-                }
-                const float ocx = W.ocx[o], ocy = W.ocy[o], rho = W.orho[o];
-                const float tc = ocx * c + ocy * s;
-                const float hc = ocy * c - ocx * s;
-                const float slack = rho * 1e-5f + 1e-4f;
-                if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > best) continue;
-                const float2* vp = W.verts + W.ovoff[o];
-                if (!(fl & (OFLAG_PENTAGON | OFLAG_WORLD)) && nvv > 16) {
-                  // Regular n-gon inscribed in the enclosing circle (n = 16/32/64): the ray's
-                  // line meets the circle at polar angles theta+g and theta+pi-g (g =
-                  // asin(-hc/r)); between circle and polygon lies the circular segment of
-                  // exactly one edge, so the polygon crossing is on the edge whose angular span
-                  // contains that angle.  The neighbour on the nearer side is tested too, which
-                  // absorbs the FP32 error of asinf near grazing incidence.
-                  const int nn = nvv - 1;
-                  const float g = asinf(fminf(fmaxf(-hc / rho, -1.f), 1.f));
-                  const float invd = (float)nn * 0.15915494309189535f;
+            const float rho = q.rho;
+            const float tc = q.ecx * c + q.ecy * s;
+            const float hc = q.ecy * c - q.ecx * s;
+            const float slack = rho * 1e-5f + 1e-4f;
+            if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > best) continue;
+            const float2* vp = sm.verts + sm.voff[rr];
+            if (!(fl & (OFLAG_PENTAGON | OFLAG_WORLD)) && nq > 16) {
+              // Regular n-gon inscribed in the enclosing circle (n = 16/32/64): the ray's line
+              // meets the circle at polar angles theta+g and theta+pi-g (g = asin(-hc/r));
+              // between circle and polygon lies the circular segment of exactly one edge, so the
+              // polygon crossing is on the edge whose angular span contains that angle.  The
+              // neighbour on the nearer side is tested too (FP32 error of asinf near grazing).
+              const int nn = nq - 1;
+              const float g = asinf(fminf(fmaxf(-hc / rho, -1.f), 1.f));
+              const float invd = (float)nn * 0.15915494309189535f;
 #pragma unroll
-                  for (int sol = 0; sol < 2; ++sol) {
-                    const float p = (sol == 0 ? theta + g : theta + 3.14159265358979f - g) * invd;
-                    const float kf = floorf(p);
-                    const int k0 = (int)kf & (nn - 1);
-                    const int k1 = (p - kf < 0.5f ? k0 - 1 : k0 + 1) & (nn - 1);
+              for (int sol = 0; sol < 2; ++sol) {
+                const float p = (sol == 0 ? theta + g : theta + 3.14159265358979f - g) * invd;
+                const float kf = floorf(p);
+                const int k0 = (int)kf & (nn - 1);
+                const int k1 = (p - kf < 0.5f ? k0 - 1 : k0 + 1) & (nn - 1);
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                      const int k = q == 0 ? k0 : k1;
-                      const float2 va = vp[k], vb = vp[k + 1];
-                      const float ya = va.y * c - va.x * s, yb = vb.y * c - vb.x * s;
-                      if ((ya <= 0.f && yb >= 0.f) || (ya >= 0.f && yb <= 0.f)) {
-                        const float xa = va.x * c + va.y * s, xb = vb.x * c + vb.y * s;
-                        const float t = xa + (xb - xa) * (ya / (ya - yb));
-                        if (t >= 0.f && t <= rangef) best = fminf(best, t);
-                      }
-                    }
-                  }
-                  continue;
-                }
-                float2 v = vp[0];
-                float xp = v.x * c + v.y * s;
-                float yp = v.y * c - v.x * s;
-                for (int k = 1; k < nvv; ++k) {
-                  v = vp[k];
-                  const float xc = v.x * c + v.y * s;
-                  const float yc = v.y * c - v.x * s;
-                  if ((yp <= 0.f && yc >= 0.f) || (yp >= 0.f && yc <= 0.f)) {
-                    const float t = xp + (xc - xp) * (yp / (yp - yc));
+                for (int w = 0; w < 2; ++w) {
+                  const int k = w == 0 ? k0 : k1;
+                  const float2 va = vp[k], vb = vp[k + 1];
+                  const float ya = va.y * c - va.x * s, yb = vb.y * c - vb.x * s;
+                  if ((ya <= 0.f && yb >= 0.f) || (ya >= 0.f && yb <= 0.f)) {
+                    const float xa = va.x * c + va.y * s, xb = vb.x * c + vb.y * s;
+                    const float t = xa + (xb - xa) * (ya / (ya - yb));
                     if (t >= 0.f && t <= rangef) best = fminf(best, t);
                   }
-                  xp = xc;
-                  yp = yc;
                 }
               }
-              sdist[i] = best;
+              continue;
             }
-          }
-          __syncwarp();
-        }
-      }
-      // ---- closeness / collision / penalty  (vessel.py:88-95,356-359; rewarder.py:199-214)
-      if (!any_active) {
-        // vessel.py:275-305: no nearby obstacles => every range = sensor_range, closeness 0
-        for (int i = lane; i < R; i += 32) {
-          obs[6 + i] = 0.f;
-          if (A.out.lidar_dist != nullptr) A.out.lidar_dist[(long long)e * R + i] = rangef;
-        }
-        pen_sum = A.pen_clear;
-      } else {
-        const float inv_log = 1.f / log1pf(rangef);
-        for (int i0 = 0; i0 < R; i0 += 32) {
-          const int i = i0 + lane;
-          if (i < R) {
-            const float d = sdist[i];
-            const float w = A.rays.weight[i];
-            float cl;
-            if (d >= rangef) {
-              cl = 0.f;  // 1 - log(1+range)/log(1+range) is exactly 0 in the reference
-              pen_sum += w * A.pen_clear_ray;  // range * exp(-0.1 range), no transcendental
-            } else {
-              if (cfg.sensor_log_transform) {
-                cl = 1.f - fminf(fmaxf(log1pf(d) * inv_log, 0.f), 1.f);
-              } else {
-                cl = 1.f - fminf(fmaxf(d / rangef, 0.f), 1.f);
+            float2 v = vp[0];
+            float xp = v.x * c + v.y * s;
+            float yp = v.y * c - v.x * s;
+            for (int k = 1; k < nq; ++k) {
+              v = vp[k];
+              const float xc = v.x * c + v.y * s;
+              const float yc = v.y * c - v.x * s;
+              if ((yp <= 0.f && yc >= 0.f) || (yp >= 0.f && yc <= 0.f)) {
+                const float t = xp + (xc - xp) * (yp / (yp - yc));
+                if (t >= 0.f && t <= rangef) best = fminf(best, t);
               }
-              pen_sum += w * rangef * __expf(-0.1f * d);
+              xp = xc;
+              yp = yc;
             }
-            obs[6 + i] = fminf(fmaxf(cl, -1.f), 1.f);
-            if (A.out.lidar_dist != nullptr) A.out.lidar_dist[(long long)e * R + i] = d;
-            collision = collision || (d < widthf);
           }
+          sdist[i] = best;
         }
-        collision = __any_sync(AUV_FULL, collision);
-        pen_sum = warp_sum(pen_sum);
+        r0 += nr;
       }
-      // ---- optional sector pooling (utils/sector_partitioning.py; sensor.py:215-296)
-      if (A.out.sector_min_dist != nullptr || A.out.sector_feasible_dist != nullptr) {
-        const int ns = cfg.n_sectors;
-        __syncwarp();
-        if (!any_active)
-          for (int i = lane; i < rpad; i += 32) sdist[i] = rangef;
-        float* ssec = reinterpret_cast<float*>(W.verts);  // vertex staging is free again: reuse
-        if (lane < 32) ssec[lane] = rangef;
-        __syncwarp();
-        // min-pooling: segmented warp-shuffle reduction keyed by the ray's sector id
-        for (int i0 = 0; i0 < R; i0 += 32) {
-          const int i = i0 + lane;
-          float d = i < R ? sdist[i] : INFINITY;
-          const int sid = i < R ? (int)A.rays.sector[i] : -1 - lane;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const float od = __shfl_down_sync(AUV_FULL, d, o);
-            const int os = __shfl_down_sync(AUV_FULL, sid, o);
-            if (lane + o < 32 && os == sid) d = fminf(d, od);
-          }
-          const int ps = __shfl_up_sync(AUV_FULL, sid, 1);
-          const bool head = i < R && (lane == 0 || ps != sid);
-          if (head && sid < 32) ssec[sid] = fminf(ssec[sid], d);  // one head per sector per iteration
-          __syncwarp();
+      __syncwarp();
+      // ---- closeness / collision / penalty  (vessel.py:88-95,356-359; rewarder.py:199-214)
+      const float inv_log = 1.f / log1pf(rangef);
+      for (int i = lane; i < R; i += 32) {
+        const float d = sdist[i];
+        const float w = A.rays.weight[i];
+        float cl;
+        if (d >= rangef) {
+          cl = 0.f;  // 1 - log(1+range)/log(1+range) is exactly 0 upstream
+          pen += w * A.pen_clear_ray;
+        } else {
+          if (cfg.sensor_log_transform)
+            cl = 1.f - fminf(fmaxf(log1pf(d) * inv_log, 0.f), 1.f);
+          else
+            cl = 1.f - fminf(fmaxf(d / rangef, 0.f), 1.f);
+          pen += w * rangef * __expf(-0.1f * d);
         }
-        if (A.out.sector_min_dist != nullptr && lane < ns)
-          A.out.sector_min_dist[(long long)e * ns + lane] = ssec[lane];
-        if (A.out.sector_feasible_dist != nullptr) {
-          // lane s pools sector s (sectors are contiguous ray ranges)
-          float res = rangef;
-          if (lane < ns) {
-            int lo = 0, hi = R;
-            for (int i = 0; i < R; ++i) {  // sector table is monotone
-              const int sd = A.rays.sector[i];
-              if (sd < lane) lo = i + 1;
-              if (sd <= lane) hi = i + 1;
-            }
-            res = hi > lo ? feasibility_pooling(sdist + lo, hi - lo, A.feas_width, dth_d) : rangef;
-          }
-          if (lane < ns) A.out.sector_feasible_dist[(long long)e * ns + lane] = res;
-        }
-        __syncwarp();
+        obs[6 + i] = fminf(fmaxf(cl, -1.f), 1.f);
+        if (A.out.lidar_dist != nullptr) A.out.lidar_dist[(long long)e * R + i] = d;
+        collision = collision || (d < widthf);
       }
-      if (cfg.sensor_use_velocity_observations)  // sensor.py:159: speed channel is (0,0) at HEAD
-        for (int i = lane; i < 2 * R; i += 32) obs[6 + R + i] = 0.f;
-    }
-
-    // ---------------- navigation part of the observation (vessel.py:518-539) ----------
-    {
-      // obs[0..5] = u, v, r, look-ahead heading error, heading error, cross-track/100
-      double val = __shfl_sync(AUV_FULL, stv, (lane + 3) & 31);  // lanes 0..2 <- u, v, r
-      const double la = __shfl_sync(AUV_FULL, navv, NAV_LA_ERR), he = __shfl_sync(AUV_FULL, navv, NAV_HEAD_ERR);
-      const double ye = __shfl_sync(AUV_FULL, navv, NAV_YE);
-      if (lane == 3) val = la;
-      if (lane == 4) val = he;
-      if (lane == 5) val = ye / 100.0;
-      if (lane < 6) obs[lane] = (float)fmin(fmax(val, -1.0), 1.0);
-    }
-    if (A.out.seg_tests != nullptr) {
-      unsigned long long t = ntests;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(AUV_FULL, t, o);
-      if (lane == 0 && t) atomicAdd(A.out.seg_tests, t);
-    }
-    const double progress = __shfl_sync(AUV_FULL, navv, NAV_PROGRESS);
-    const double goal_dist = __shfl_sync(AUV_FULL, navv, NAV_GOAL);
-    const bool reached = __shfl_sync(AUV_FULL, navv, NAV_REACHED) != 0.0;
-    if (mode == AUV_OBSERVE_RESET) {
-      if (lane == 0 && pass == 0) {  // explicit reset observe: info mirrors a fresh env
-        if (A.out.collision) A.out.collision[e] = collision;
-        if (A.out.reached_goal) A.out.reached_goal[e] = reached;
-        if (A.out.goal_distance) A.out.goal_distance[e] = (float)goal_dist;
-        if (A.out.progress) A.out.progress[e] = (float)progress;
-      }
-      return;
-    }
-
-    // ---------------- reward (rewarder.py) + done (environment.py:375-384) ------------
-    const double vu = __shfl_sync(AUV_FULL, stv, 3), vv = __shfl_sync(AUV_FULL, stv, 4);
-    const double vr = __shfl_sync(AUV_FULL, stv, 5);
-    const double y_e = __shfl_sync(AUV_FULL, navv, NAV_YE);
-    const double cos_he = __shfl_sync(AUV_FULL, navv, NAV_COS_HEAD_ERR);
-    const double maxprog = __shfl_sync(AUV_FULL, auxv, 2);  // already includes this step (k_vessel_nav)
-    const double speed = sqrt(vu * vu + vv * vv);
-    double reward;
-    if (collision) {
-      reward = -10000.0 * (1.0 - 0.5);
+      collision = __any_sync(AUV_FULL, collision);
+      pen = warp_sum(pen);
     } else {
-      const double cte = y_e / 100.0;
-      double path_reward = (1.0 + cos_he * speed / 2.0) * (1.0 + (double)__expf((float)(-5.0 * fabs(cte)))) - 1.0;
-      const double living = 0.5 * (2.0 * 0.05 + 1.0);
-      if (cfg.rewarder == AUV_REWARDER_COLAV) {
-        // without LiDAR every ray keeps its reset value sensor_range (vessel.py:206-208)
-        const double closeness_reward =
-            cfg.use_lidar ? -(double)pen_sum / A.rays.weight_sum : A.clear_closeness;
-        if (progress < maxprog) path_reward = fmin(path_reward, 0.0);
-        const double slow = speed < 0.04 ? -2.0 : 0.0;
-        reward = 0.5 * path_reward + 0.5 * closeness_reward - living - 10.0 * fabs(vr) + slow;
-        if (reward < 0.0) reward *= 2.0;
-      } else {
-        const double slow = speed < 0.1 ? -2.0 : 0.0;
-        reward = path_reward - living - 10.0 * fabs(vr) + slow;
+      // vessel.py:275-305: no nearby obstacles => every range = sensor_range, closeness 0
+      for (int i = lane; i < R; i += 32) {
+        obs[6 + i] = 0.f;
+        if (A.out.lidar_dist != nullptr) A.out.lidar_dist[(long long)e * R + i] = rangef;
+        if (pooling) sdist[i] = rangef;
       }
+      pen = (float)A.rays.weight_sum * A.pen_clear_ray;
     }
-    const double cum = __shfl_sync(AUV_FULL, auxv, 0) + reward;
-    const int t_step = (int)__shfl_sync(AUV_FULL, auxv, 3);
-    const bool done = collision || reached ||
-                      (!cfg.test_mode && t_step >= cfg.max_timesteps - 1) ||
-                      (!cfg.test_mode && cum < cfg.min_cumulative_reward);
-    const double cte_sum = __shfl_sync(AUV_FULL, auxv, 1) + fabs(y_e);
+    if (cfg.sensor_use_velocity_observations)  // sensor.py:159: the speed channel is (0,0) at HEAD
+      for (int k = lane; k < 2 * R; k += 32) obs[6 + R + k] = 0.f;
+
+    // ---- optional sector pooling (utils/sector_partitioning.py:4-9; sensor.py:215-296)
+    if (pooling) {
+      const int ns = cfg.n_sectors;
+      __syncwarp();
+      float* ssec = reinterpret_cast<float*>(sm.verts);  // vertex staging is free again
+      ssec[lane] = rangef;
+      __syncwarp();
+      // min-pooling: segmented warp-shuffle reduction keyed by the ray's sector id
+      for (int i0 = 0; i0 < R; i0 += 32) {
+        const int i = i0 + lane;
+        float d = i < R ? sdist[i] : INFINITY;
+        const int sid = i < R ? (int)A.rays.sector[i] : -1 - lane;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float od = __shfl_down_sync(AUV_FULL, d, o);
+          const int os = __shfl_down_sync(AUV_FULL, sid, o);
+          if (lane + o < 32 && os == sid) d = fminf(d, od);
+        }
+        const int ps = __shfl_up_sync(AUV_FULL, sid, 1);
+        const bool head = i < R && (lane == 0 || ps != sid);
+        if (head && sid < 32) ssec[sid] = fminf(ssec[sid], d);  // one head per sector per iteration
+        __syncwarp();
+      }
+      if (A.out.sector_min_dist != nullptr && lane < ns) A.out.sector_min_dist[(long long)e * ns + lane] = ssec[lane];
+      if (A.out.sector_feasible_dist != nullptr && lane < ns) {
+        int lo = 0, hi = R;
+        for (int k = 0; k < R; ++k) {  // the sector table is monotone
+          const int sd = A.rays.sector[k];
+          if (sd < lane) lo = k + 1;
+          if (sd <= lane) hi = k + 1;
+        }
+        A.out.sector_feasible_dist[(long long)e * ns + lane] =
+            hi > lo ? feasibility_pooling(sdist + lo, hi - lo, A.feas_width, 2.0 * AUV_PI / (double)R) : rangef;
+      }
+      __syncwarp();
+    }
+  }
+  if (A.out.seg_tests != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ntests += __shfl_xor_sync(AUV_FULL, ntests, o);
+    if (lane == 0 && ntests) atomicAdd(A.out.seg_tests, ntests);
+  }
+
+  // ---- navigation part of the observation (vessel.py:518-539): u, v, r, look-ahead heading
+  //      error, heading error, cross-track / 100
+  {
+    const double uvr = SCAL((SC_STATE + 3 + lane) & 31);
+    const double la = SCAL(NAV_LA_ERR), he = SCAL(NAV_HEAD_ERR), ye = SCAL(NAV_YE);
+    double val = uvr;
+    if (lane == 3) val = la;
+    if (lane == 4) val = he;
+    if (lane == 5) val = ye / 100.0;
+    if (lane < 6) obs[lane] = (float)fmin(fmax(val, -1.0), 1.0);
+  }
+  const double progress = SCAL(NAV_PROGRESS), goal_dist = SCAL(NAV_GOAL);
+  const bool reached = SCAL(NAV_REACHED) != 0.0;
+  if (A.mode == AUV_OBSERVE_RESET) {  // explicit reset observe: info mirrors a fresh env
     if (lane == 0) {
-      batch.cum_reward[e] = cum;
-      batch.t_step[e] = t_step + 1;
-      batch.cte_sum[e] = cte_sum;
-      A.out.reward[e] = (float)reward;
-      A.out.done[e] = done;
       if (A.out.collision) A.out.collision[e] = collision;
       if (A.out.reached_goal) A.out.reached_goal[e] = reached;
       if (A.out.goal_distance) A.out.goal_distance[e] = (float)goal_dist;
       if (A.out.progress) A.out.progress[e] = (float)progress;
     }
-    if (!(done && cfg.auto_reset)) return;
-
-    // ---------------- auto-reset (VecEnv semantics) ------------------------------------
-    __syncwarp();
-    if (A.out.terminal_obs != nullptr) {
-      float* to = A.out.terminal_obs + (long long)e * A.obs_dim;
-      for (int i = lane; i < A.obs_dim; i += 32) to[i] = obs[i];
-    }
-    if (lane == 0 && A.out.stats != nullptr) {  // env.history entry, environment.py:476-489
-      double* st = A.out.stats;
-      atomicAdd(st + AUV_STAT_EPISODES, 1.0);
-      atomicAdd(st + AUV_STAT_REWARD, cum);
-      atomicAdd(st + AUV_STAT_REWARD_SQ, cum * cum);
-      atomicAdd(st + AUV_STAT_PROGRESS, progress);
-      atomicAdd(st + AUV_STAT_COLLISIONS, collision ? 1.0 : 0.0);
-      atomicAdd(st + AUV_STAT_REACHED_GOAL, reached ? 1.0 : 0.0);
-      atomicAdd(st + AUV_STAT_TIMESTEPS, (double)(t_step + 1));
-      atomicAdd(st + AUV_STAT_CROSS_TRACK, cte_sum / (double)(t_step + 1));
-      atomicAdd(st + AUV_STAT_PATHLENGTH, A.paths.length[pool.path_id[scn]]);
-    }
-    __syncwarp();
-    const int next = (int)(((long long)scn + n) % pool.n_scenarios);
-    reset_env_warp(pool, batch, e, next, lane);
-    if (lane == 0) {  // navigation of the fresh episode (rare: one lane, FP64)
-      const double* vi = pool.vessel_init + 3ll * next;
-      navigate_thread(cfg, A.paths, batch, pool.path_id[next], e, vi[0], vi[1], vi[2]);
-    }
-    __syncwarp();
-    mode = AUV_OBSERVE_RESET;
+    return;
   }
+
+  // ---- reward (rewarder.py) + done (environment.py:375-384) + counters (uniform across lanes)
+  const double vu = SCAL(SC_STATE + 3), vv = SCAL(SC_STATE + 4), vr = SCAL(SC_STATE + 5);
+  const double y_e = SCAL(NAV_YE);
+  const double maxprog = SCAL(SC_MAXPROG);  // already includes this step (navigate_thread)
+  const double speed = sqrt(vu * vu + vv * vv);
+  double reward;
+  if (collision) {
+    reward = -10000.0 * (1.0 - 0.5);
+  } else {
+    const double cte = y_e / 100.0;
+    double path_reward =
+        (1.0 + SCAL(NAV_COS_HEAD_ERR) * speed / 2.0) * (1.0 + (double)__expf((float)(-5.0 * fabs(cte)))) - 1.0;
+    const double living = 0.5 * (2.0 * 0.05 + 1.0);
+    if (cfg.rewarder == AUV_REWARDER_COLAV) {
+      // without LiDAR every ray keeps its reset value sensor_range (vessel.py:206-208)
+      const double closeness_reward = cfg.use_lidar ? -(double)pen / A.rays.weight_sum : A.clear_closeness;
+      if (progress < maxprog) path_reward = fmin(path_reward, 0.0);
+      const double slow = speed < 0.04 ? -2.0 : 0.0;
+      reward = 0.5 * path_reward + 0.5 * closeness_reward - living - 10.0 * fabs(vr) + slow;
+      if (reward < 0.0) reward *= 2.0;
+    } else {
+      const double slow = speed < 0.1 ? -2.0 : 0.0;
+      reward = path_reward - living - 10.0 * fabs(vr) + slow;
+    }
+  }
+  const double cum = SCAL(SC_CUM) + reward;
+  const int t_step = (int)SCAL(SC_TSTEP);
+  const bool done = collision || reached || (!cfg.test_mode && t_step >= cfg.max_timesteps - 1) ||
+                    (!cfg.test_mode && cum < cfg.min_cumulative_reward);
+  const double cte_sum = SCAL(SC_CTE) + fabs(y_e);
+  const bool do_reset = done && cfg.auto_reset;
+  const int scn = (int)SCAL(SC_SCN);
+  const int next = (int)(((long long)scn + n) % A.pool.n_scenarios);
+  if (lane == 0) {
+    A.out.reward[e] = (float)reward;
+    A.out.done[e] = done;
+    if (A.out.collision) A.out.collision[e] = collision;
+    if (A.out.reached_goal) A.out.reached_goal[e] = reached;
+    if (A.out.goal_distance) A.out.goal_distance[e] = (float)goal_dist;
+    if (A.out.progress) A.out.progress[e] = (float)progress;
+    if (!do_reset) {
+      batch.cum_reward[e] = cum;
+      batch.t_step[e] = t_step + 1;
+      batch.cte_sum[e] = cte_sum;
+    } else {
+      // ---- VecEnv auto-reset, scalar part.  The first observation of an episode depends on the
+      // scenario only, so it was computed once per pool scenario (pool.reset_*) and the reset
+      // is a copy: no navigation / culling / casting on the step path.
+      if (A.out.stats != nullptr) {  // env.history entry, environment.py:476-489
+        double* st = A.out.stats;
+        atomicAdd(st + AUV_STAT_EPISODES, 1.0);
+        atomicAdd(st + AUV_STAT_REWARD, cum);
+        atomicAdd(st + AUV_STAT_REWARD_SQ, cum * cum);
+        atomicAdd(st + AUV_STAT_PROGRESS, progress);
+        atomicAdd(st + AUV_STAT_COLLISIONS, collision ? 1.0 : 0.0);
+        atomicAdd(st + AUV_STAT_REACHED_GOAL, reached ? 1.0 : 0.0);
+        atomicAdd(st + AUV_STAT_TIMESTEPS, (double)(t_step + 1));
+        atomicAdd(st + AUV_STAT_CROSS_TRACK, cte_sum / (double)(t_step + 1));
+        atomicAdd(st + AUV_STAT_PATHLENGTH, A.paths.length[A.pool.path_id[scn]]);
+      }
+      batch.scn_id[e] = next;
+      batch.episode[e] += 1;
+      const double* vi = A.pool.vessel_init + 3ll * next;
+      batch.state[e] = vi[0];
+      batch.state[n + e] = vi[1];
+      batch.state[2ll * n + e] = vi[2];
+      batch.state[3ll * n + e] = 0.0;
+      batch.state[4ll * n + e] = 0.0;
+      batch.state[5ll * n + e] = 0.0;
+      batch.step_counter[e] = 0;
+      batch.t_step[e] = 0;
+      batch.cum_reward[e] = 0.0;
+      batch.cte_sum[e] = 0.0;
+      batch.max_progress[e] = A.pool.reset_max_progress[next];
+    }
+  }
+  if (!do_reset) return;
+  // ---- auto-reset, bulk part (whole warp): terminal obs out, cached first obs in, obstacle
+  //      state and nearby list of the next scenario
+  __syncwarp();
+  {
+    const int km = A.pool.k_moving;
+    const float* robs = A.pool.reset_obs + (long long)next * A.obs_dim;
+    float* tobs = A.out.terminal_obs ? A.out.terminal_obs + (long long)e * A.obs_dim : nullptr;
+    for (int k = lane; k < A.obs_dim; k += 32) {
+      if (tobs) tobs[k] = obs[k];
+      obs[k] = robs[k];
+    }
+    for (int j = lane; j < km; j += 32) {
+      const long long ps = (long long)next * km + j, pe = (long long)e * km + j;
+      reinterpret_cast<double2*>(batch.mov_pos)[pe] = reinterpret_cast<const double2*>(A.pool.mov_pos0)[ps];
+      reinterpret_cast<double2*>(batch.mov_disp)[pe] = reinterpret_cast<const double2*>(A.pool.mov_disp0)[ps];
+      batch.mov_counter[pe] = A.pool.mov_counter0[ps];
+    }
+    if (cfg.use_lidar)
+      for (int w = lane; w < batch.mask_words; w += 32)
+        batch.nearby_mask[(long long)e * batch.mask_words + w] = A.pool.reset_mask[(long long)next * batch.mask_words + w];
+  }
+#undef SCAL
 }
 
 // ------------------------------------------------------------------------------------
@@ -1280,47 +817,59 @@ int auv_reset(const AuvConfig* cfg, const AuvScenarioPool* pool, AuvBatch* batch
   if (int rc = check_cfg(cfg)) return rc;
   if (!pool || !batch) return set_err(AUV_EINVAL, "pool/batch is NULL");
   if (batch->n_envs <= 0) return set_err(AUV_EINVAL, "n_envs must be > 0");
-  const int threads = 256;
-  const long long blocks = ((long long)batch->n_envs * 32 + threads - 1) / threads;
-  auv::k_reset<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*pool, *batch, reset_mask);
+  const int threads = 128;
+  const int blocks = (batch->n_envs + threads - 1) / threads;
+  auv::k_reset<<<blocks, threads, 0, (cudaStream_t)stream>>>(*pool, *batch, reset_mask);
   return cuda_check(cudaGetLastError(), "k_reset");
+}
+
+static int check_batch(const AuvConfig* cfg, const AuvScenarioPool* pool, const AuvBatch* batch) {
+  if (batch->n_envs <= 0) return set_err(AUV_EINVAL, "n_envs must be > 0");
+  if (!batch->nav) return set_err(AUV_EINVAL, "batch.nav is NULL");
+  if (pool->n_world < 0) return set_err(AUV_EINVAL, "n_world < 0");
+  const int slots = pool->k_moving + pool->k_static + pool->n_world;
+  if (slots > AUV_MAX_OBSTACLES) return set_err(AUV_EINVAL, "too many obstacle slots");
+  if (batch->mask_words * 32 < slots) return set_err(AUV_EINVAL, "mask_words too small");
+  if (pool->n_world > 0 && (!pool->world_circle || !pool->world_voff || !pool->world_verts))
+    return set_err(AUV_EINVAL, "world arrays are NULL");
+  if (cfg->use_lidar && (!batch->rec_cnt || (slots > 0 && (!batch->rec || batch->rec_cap <= 0))))
+    return set_err(AUV_EINVAL, "batch.rec / rec_cnt / rec_cap missing");
+  return 0;
 }
 
 static int check_observe_args(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                               const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode) {
   if (int rc = check_cfg(cfg)) return rc;
   if (!paths || !pool || !batch || !out) return set_err(AUV_EINVAL, "NULL argument");
-  if (cfg->use_lidar && !rays) return set_err(AUV_EINVAL, "rays is NULL with use_lidar");
+  if (cfg->use_lidar && (!rays || !rays->unit64 || !rays->cos_sin || !rays->weight || !rays->sector))
+    return set_err(AUV_EINVAL, "ray table is NULL with use_lidar");
   if (!out->obs) return set_err(AUV_EINVAL, "out.obs is NULL");
-  if (!batch->nav) return set_err(AUV_EINVAL, "batch.nav is NULL");
   if (mode == AUV_OBSERVE_STEP && (!out->reward || !out->done))
     return set_err(AUV_EINVAL, "out.reward/out.done is NULL");
-  if (batch->n_envs <= 0) return set_err(AUV_EINVAL, "n_envs must be > 0");
-  if (pool->n_world < 0) return set_err(AUV_EINVAL, "n_world < 0");
-  if (pool->k_moving + pool->k_static + pool->n_world > AUV_MAX_OBSTACLES)
-    return set_err(AUV_EINVAL, "too many obstacle slots");
-  if (batch->mask_words * 32 < pool->k_moving + pool->k_static + pool->n_world || batch->mask_words > 32)
-    return set_err(AUV_EINVAL, "mask_words must cover all slots and be <= 32");
-  if (pool->n_world > 0 && (!pool->world_circle || !pool->world_voff || !pool->world_verts))
-    return set_err(AUV_EINVAL, "world arrays are NULL");
-  return 0;
+  if (mode == AUV_OBSERVE_STEP && cfg->auto_reset &&
+      (!pool->reset_obs || !pool->reset_max_progress || (cfg->use_lidar && !pool->reset_mask)))
+    return set_err(AUV_EINVAL, "auto_reset needs the pool's cached first observations (pool.reset_*)");
+  return check_batch(cfg, pool, batch);
 }
 
-static int launch_vessel_nav(const AuvConfig* cfg, const AuvPathBank* paths, const AuvScenarioPool* pool,
-                             AuvBatch* batch, const float* actions, void* stream) {
+static int launch_vessel_nav(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                             const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out,
+                             const float* actions, void* stream) {
   const int threads = 64;  // small CTAs: 65536 envs are only ~7 CTAs per SM, balance matters
   const int blocks = (batch->n_envs + threads - 1) / threads;
+  const double2* unit = rays ? reinterpret_cast<const double2*>(rays->unit64) : nullptr;
+  int* win = out ? out->windows : nullptr;
   if (actions)
-    auv::k_vessel_nav<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, actions);
+    auv::k_vessel_nav<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, unit, win, actions);
   else
-    auv::k_vessel_nav<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, nullptr);
+    auv::k_vessel_nav<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, unit, win, nullptr);
   return cuda_check(cudaGetLastError(), "k_vessel_nav");
 }
 
-static int launch_observe(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
-                          const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode,
-                          void* stream) {
-  auv::ObserveArgs args;
+static int launch_lidar(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                        const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode,
+                        void* stream) {
+  auv::LidarArgs args;
   args.cfg = *cfg;
   if (rays) args.rays = *rays; else memset(&args.rays, 0, sizeof(args.rays));
   args.paths = *paths;
@@ -1329,40 +878,38 @@ static int launch_observe(const AuvConfig* cfg, const AuvRayTable* rays, const A
   args.out = *out;
   args.mode = mode;
   args.obs_dim = auv_obs_dim(cfg);
-  args.pen_clear = (float)((rays ? rays->weight_sum : 1.0) * cfg->sensor_range * exp(-0.1 * cfg->sensor_range));
   args.clear_closeness = -cfg->sensor_range * exp(-0.1 * cfg->sensor_range);
   args.pen_clear_ray = (float)(-args.clear_closeness);
   args.feas_width = cfg->vessel_width * cfg->feasibility_width_multiplier;
   const int rpad = cfg->use_lidar ? ((cfg->n_sensors + 31) & ~31) : 32;
-  const size_t smem = (sizeof(auv::WarpScratch) + sizeof(float) * rpad) * auv::WARPS_PER_BLOCK;
+  const size_t smem = (sizeof(auv::WarpSmem) + sizeof(float) * rpad) * AUV_LIDAR_WARPS;
   static size_t configured = 0;
   if (smem > configured) {
-    if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem),
-                            "cudaFuncSetAttribute(k_observe)"))
+    if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_lidar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(k_lidar)"))
       return rc;
     configured = smem;
   }
-  const int blocks = (batch->n_envs + auv::WARPS_PER_BLOCK - 1) / auv::WARPS_PER_BLOCK;
-  auv::k_observe<<<blocks, auv::WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(args);
-  return cuda_check(cudaGetLastError(), "k_observe");
+  const int blocks = (batch->n_envs + AUV_LIDAR_WARPS - 1) / AUV_LIDAR_WARPS;
+  auv::k_lidar<<<blocks, AUV_LIDAR_WARPS * 32, smem, (cudaStream_t)stream>>>(args);
+  return cuda_check(cudaGetLastError(), "k_lidar");
 }
 
-int auv_navigate(const AuvConfig* cfg, const AuvPathBank* paths, const AuvScenarioPool* pool,
-                 AuvBatch* batch, void* stream) {
+int auv_navigate(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                 const AuvScenarioPool* pool, AuvBatch* batch, void* stream) {
   if (int rc = check_cfg(cfg)) return rc;
   if (!paths || !pool || !batch) return set_err(AUV_EINVAL, "NULL argument");
-  if (!batch->nav) return set_err(AUV_EINVAL, "batch.nav is NULL");
-  if (batch->n_envs <= 0) return set_err(AUV_EINVAL, "n_envs must be > 0");
-  return launch_vessel_nav(cfg, paths, pool, batch, nullptr, stream);
+  if (cfg->use_lidar && (!rays || !rays->unit64)) return set_err(AUV_EINVAL, "ray table is NULL with use_lidar");
+  if (int rc = check_batch(cfg, pool, batch)) return rc;
+  return launch_vessel_nav(cfg, rays, paths, pool, batch, nullptr, nullptr, stream);
 }
 
 int auv_observe(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                 const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode,
                 void* stream) {
   if (int rc = check_observe_args(cfg, rays, paths, pool, batch, out, mode)) return rc;
-  if (int rc = launch_vessel_nav(cfg, paths, pool, batch, nullptr, stream)) return rc;
-  return launch_observe(cfg, rays, paths, pool, batch, out, mode, stream);
+  if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, nullptr, stream)) return rc;
+  return launch_lidar(cfg, rays, paths, pool, batch, out, mode, stream);
 }
 
 int auv_step(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
@@ -1371,21 +918,22 @@ int auv_step(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* p
   if (!actions) return set_err(AUV_EINVAL, "actions is NULL");
   if (int rc = check_observe_args(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP)) return rc;
   if (int rc = auv_obstacle_update(cfg, pool, batch, stream)) return rc;
-  if (int rc = launch_vessel_nav(cfg, paths, pool, batch, actions, stream)) return rc;  // Vessel.step + navigate
-  return launch_observe(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, stream);
+  if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, actions, stream)) return rc;
+  return launch_lidar(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, stream);
 }
 
+#define AUV_TIMER_EVENTS 4
 struct AuvTimer {
   int capacity;
-  cudaEvent_t* ev;  // [capacity][4]
+  cudaEvent_t* ev;  // [capacity][AUV_TIMER_EVENTS]
 };
 
 AuvTimer* auv_timer_create(int capacity) {
   if (capacity <= 0) return nullptr;
   AuvTimer* t = new AuvTimer;
   t->capacity = capacity;
-  t->ev = new cudaEvent_t[(size_t)capacity * 4];
-  for (int i = 0; i < capacity * 4; ++i)
+  t->ev = new cudaEvent_t[(size_t)capacity * AUV_TIMER_EVENTS];
+  for (int i = 0; i < capacity * AUV_TIMER_EVENTS; ++i)
     if (cudaEventCreate(&t->ev[i]) != cudaSuccess) {
       for (int k = 0; k < i; ++k) cudaEventDestroy(t->ev[k]);
       delete[] t->ev;
@@ -1396,7 +944,7 @@ AuvTimer* auv_timer_create(int capacity) {
 }
 void auv_timer_destroy(AuvTimer* t) {
   if (!t) return;
-  for (int i = 0; i < t->capacity * 4; ++i) cudaEventDestroy(t->ev[i]);
+  for (int i = 0; i < t->capacity * AUV_TIMER_EVENTS; ++i) cudaEventDestroy(t->ev[i]);
   delete[] t->ev;
   delete t;
 }
@@ -1407,19 +955,19 @@ int auv_step_timed(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathB
   if (!actions) return set_err(AUV_EINVAL, "actions is NULL");
   if (int rc = check_observe_args(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  cudaEvent_t* e = t->ev + 4 * slot;
+  cudaEvent_t* e = t->ev + AUV_TIMER_EVENTS * slot;
   cudaEventRecord(e[0], s);
   if (int rc = auv_obstacle_update(cfg, pool, batch, stream)) return rc;
   cudaEventRecord(e[1], s);
-  if (int rc = launch_vessel_nav(cfg, paths, pool, batch, actions, stream)) return rc;
+  if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, actions, stream)) return rc;
   cudaEventRecord(e[2], s);
-  if (int rc = launch_observe(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, stream)) return rc;
+  if (int rc = launch_lidar(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, stream)) return rc;
   return cuda_check(cudaEventRecord(e[3], s), "cudaEventRecord");
 }
 int auv_timer_read(AuvTimer* t, int slot, float* ms) {
   if (!t || !ms || slot < 0 || slot >= t->capacity) return set_err(AUV_EINVAL, "bad timer/slot");
-  cudaEvent_t* e = t->ev + 4 * slot;
-  for (int k = 0; k < 3; ++k)
+  cudaEvent_t* e = t->ev + AUV_TIMER_EVENTS * slot;
+  for (int k = 0; k < AUV_TIMER_EVENTS - 1; ++k)
     if (int rc = cuda_check(cudaEventElapsedTime(&ms[k], e[k], e[k + 1]), "cudaEventElapsedTime")) return rc;
   return 0;
 }

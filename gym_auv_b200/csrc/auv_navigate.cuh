@@ -1,0 +1,219 @@
+// auv_navigate.cuh -- path projection (exact hierarchical LineString.project), PCHIP
+// evaluation and Vessel.navigate, one thread per env (FP64).
+#pragma once
+#include "auv_device.cuh"
+#include "../../include/auv_b200.h"
+
+namespace auv {
+
+// ------------------------------------------------------------------------------------
+// Path projection + navigation features, ONE THREAD per env (FP64)
+//   path.py:61-93 (PCHIP eval, LineString.project), vessel.py:461-541 (navigate)
+// The result is the env's navigation record nav[e][AUV_NAV_W] in HBM; the warp-per-env
+// LiDAR kernel reads it back (one 96 B coalesced load).
+// ------------------------------------------------------------------------------------
+#define NAV_S 0
+#define NAV_CHI 1
+#define NAV_YE 2
+#define NAV_SLA 3
+#define NAV_LA_ERR 4
+#define NAV_HEAD_ERR 5
+#define NAV_GOAL 6
+#define NAV_PROGRESS 7
+#define NAV_COSPSI 8
+#define NAV_SINPSI 9
+#define NAV_REACHED 10
+#define NAV_COS_HEAD_ERR 11
+
+// scipy PPoly evaluation (extrapolate=True): interval j with x[j] <= s < x[j+1], clamped.
+__device__ __forceinline__ void pchip_eval(const AuvPathBank& pb, int pid, double s, double& px,
+                                           double& py, double& dx, double& dy) {
+  const int nk = pb.n_knots;
+  const double* kn = pb.knots + (long long)pid * nk;
+  const double L = kn[nk - 1];
+  int j = (int)((s / L) * (nk - 1));
+  j = max(0, min(nk - 2, j));
+  while (j > 0 && s < kn[j]) --j;
+  while (j < nk - 2 && s >= kn[j + 1]) ++j;
+  const double t = s - kn[j];
+  const double* c = pb.coef + ((long long)pid * (nk - 1) + j) * 8;
+  px = ((c[0] * t + c[1]) * t + c[2]) * t + c[3];
+  py = ((c[4] * t + c[5]) * t + c[6]) * t + c[7];
+  dx = (3.0 * c[0] * t + 2.0 * c[1]) * t + c[2];
+  dy = (3.0 * c[4] * t + 2.0 * c[5]) * t + c[6];
+}
+
+// exact squared distance from P to segment AB (GEOS Distance::pointToSegment, squared;
+// the r<=0 / r>=1 tests are done on the numerator, no division)
+__device__ __forceinline__ double seg_d2(double px, double py, double2 A, double2 B) {
+  const double ex = B.x - A.x, ey = B.y - A.y;
+  const double wx = px - A.x, wy = py - A.y;
+  const double len2 = ex * ex + ey * ey;
+  const double num = wx * ex + wy * ey;
+  if (len2 == 0.0 || num <= 0.0) return wx * wx + wy * wy;
+  if (num >= len2) {
+    const double zx = px - B.x, zy = py - B.y;
+    return zx * zx + zy * zy;
+  }
+  const double cr = wx * ey - wy * ex;
+  return cr * cr / len2;
+}
+
+// GEOS LengthIndexOfPoint::indexOf (LineString.project) restated as an exact three-level
+// search.  Level 2 = superblocks of 32 blocks, level 1 = blocks of 32 segments; each node is
+// a capsule (chord, max deviation) that contains its part of the polyline, so
+//   dist(P, node) in [dc - dev, dc + dev],  dc = dist(P, chord)   (FP32, padded).
+// Pass A finds an upper bound over superblocks, pass B tightens it over the blocks of the
+// surviving superblocks, pass C refines in FP64 every block whose lower bound does not
+// exceed it.  The arg-min is lexicographic in (distance, segment index), which is GEOS's
+// "first minimum wins" independent of visiting order.
+__device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid, double px, double py) {
+  const int v0 = pb.poly_off[pid];
+  const int nseg = pb.poly_off[pid + 1] - v0 - 1;
+  const int b0 = pb.blk_off[pid];
+  const int nblk = pb.blk_off[pid + 1] - b0;
+  const int s0 = pb.sb_off[pid];
+  const int nsb = pb.sb_off[pid + 1] - s0;
+  const double ox = pb.origin[2 * pid], oy = pb.origin[2 * pid + 1];
+  const float qx = (float)(px - ox), qy = (float)(py - oy);
+  const float pad = 1e-6f * (fabsf(qx) + fabsf(qy)) + 1e-6f;
+  const float4* chord = reinterpret_cast<const float4*>(pb.blk_chord) + b0;
+  const float* dev = pb.blk_dev + b0;
+  const float4* sbc = reinterpret_cast<const float4*>(pb.sb_chord) + s0;
+  const float* sbd = pb.sb_dev + s0;
+  const float up = 1.f + 4e-6f, dn = 1.f - 4e-6f;
+  // All node loops below issue their loads in groups of U before any arithmetic, so a
+  // thread has U independent L2 requests in flight instead of one (the kernel is bound by
+  // load latency, not by FP64 issue: profiles/r1b).
+  constexpr int U = 8;
+  float ub = INFINITY;
+  for (int g0 = 0; g0 < nsb; g0 += U) {
+    float4 ch[U];
+    float dv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = min(g0 + u, nsb - 1);
+      ch[u] = sbc[i];
+      dv[u] = sbd[i];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      ub = fminf(ub, pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * up + dv[u] + pad);
+  }
+  // pass B: tighten over blocks of surviving superblocks; remember which survive
+  unsigned long long live = 0ull;  // up to 64 superblocks tracked exactly, the rest are always visited
+  for (int sb = 0; sb < nsb; ++sb) {
+    const float4 c0 = sbc[sb];
+    const float lb = pt_seg_dist_f(qx, qy, c0.x, c0.y, c0.z, c0.w) * dn - sbd[sb] - pad;
+    if (lb > ub) continue;
+    if (sb < 64) live |= 1ull << sb;
+    const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
+    for (int g0 = sb * AUV_PATH_SUPER; g0 < be; g0 += U) {
+      float4 ch[U];
+      float dv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = min(g0 + u, be - 1);
+        ch[u] = chord[i];
+        dv[u] = dev[i];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        ub = fminf(ub, pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * up + dv[u] + pad);
+    }
+  }
+  // pass C: exact refine
+  const double2* poly = reinterpret_cast<const double2*>(pb.poly_xy) + v0;
+  double best_d2 = INFINITY;
+  int best_seg = 0;
+  for (int sb = 0; sb < nsb; ++sb) {
+    if (sb < 64 && !((live >> sb) & 1ull)) continue;
+    const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
+    for (int g0 = sb * AUV_PATH_SUPER; g0 < be; g0 += U) {
+      float4 ch[U];
+      float dv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = min(g0 + u, be - 1);
+        ch[u] = chord[i];
+        dv[u] = dev[i];
+      }
+      unsigned cand = 0u;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (g0 + u < be && pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * dn - dv[u] - pad <= ub)
+          cand |= 1u << u;
+      while (cand) {  // blocks in increasing order
+        const int b = g0 + __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int se = min(nseg, (b + 1) * AUV_PATH_BLOCK);
+        for (int k0 = b * AUV_PATH_BLOCK; k0 < se; k0 += U) {
+          double2 v[U + 1];
+#pragma unroll
+          for (int u = 0; u <= U; ++u) v[u] = poly[min(k0 + u, se)];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (k0 + u < se) {
+              const double d2 = seg_d2(px, py, v[u], v[u + 1]);
+              if (d2 < best_d2) {  // segments are visited in increasing k: strict '<' keeps the first
+                best_d2 = d2;
+                best_seg = k0 + u;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // segmentNearestMeasure of the winning segment
+  const double2 A = poly[best_seg], B = poly[best_seg + 1];
+  const double start = pb.poly_cum[v0 + best_seg];
+  const double ex = B.x - A.x, ey = B.y - A.y;
+  const double len2 = ex * ex + ey * ey;
+  if (len2 == 0.0) return start;
+  const double r = ((px - A.x) * ex + (py - A.y) * ey) / len2;
+  if (r <= 0.0) return start;
+  const double seglen = sqrt(len2);
+  if (r <= 1.0) return start + r * seglen;
+  return start + seglen;
+}
+
+// Vessel.navigate (vessel.py:461-541) for env e; writes nav[e][:] and max_progress[e].
+__device__ __forceinline__ void navigate_thread(const AuvConfig& cfg, const AuvPathBank& pb,
+                                                const AuvBatch& batch, int pid, int e, double px,
+                                                double py, double psi) {
+  const double s = project_thread(pb, pid, px, py);
+  const double L = pb.length[pid];
+  const double s_la = fmin(L, s + cfg.look_ahead_distance);
+  double p_x, p_y, d_x, d_y, l_x, l_y, ldx, ldy;
+  pchip_eval(pb, pid, s, p_x, p_y, d_x, d_y);
+  pchip_eval(pb, pid, s_la, l_x, l_y, ldx, ldy);
+  const double chi = atan2(d_y, d_x);
+  double sc, cc;
+  sincos(chi, &sc, &cc);
+  const double y_e = -sc * (p_x - px) + cc * (p_y - py);
+  const double la_err = princip(atan2(ldy, ldx) - psi);
+  const double head_err = princip(atan2(l_y - py, l_x - px) - psi);
+  const double progress = s / L;
+  const double gx = pb.end_xy[2 * pid] - px, gy = pb.end_xy[2 * pid + 1] - py;
+  const double goal = sqrt(gx * gx + gy * gy);
+  const bool reached = (goal <= cfg.min_goal_distance) || (progress >= cfg.min_path_progress);
+  double sp, cp;
+  sincos(psi, &sp, &cp);
+  double* o = batch.nav + (long long)e * AUV_NAV_W;
+  o[NAV_S] = s;
+  o[NAV_CHI] = chi;
+  o[NAV_YE] = y_e;
+  o[NAV_SLA] = s_la;
+  o[NAV_LA_ERR] = la_err;
+  o[NAV_HEAD_ERR] = head_err;
+  o[NAV_GOAL] = goal;
+  o[NAV_PROGRESS] = progress;
+  o[NAV_COSPSI] = cp;
+  o[NAV_SINPSI] = sp;
+  o[NAV_REACHED] = reached ? 1.0 : 0.0;
+  o[NAV_COS_HEAD_ERR] = cos(head_err);
+  batch.max_progress[e] = fmax(progress, batch.max_progress[e]);  // vessel.py:507
+}
+
+}  // namespace auv

@@ -109,6 +109,8 @@ class AUVVecEnv:
         debug: bool = False,
         env_offset: int = 0,
         sector_outputs: bool = False,
+        max_nearby: Optional[int] = None,
+        _shared: Optional[dict] = None,
     ):
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -132,8 +134,11 @@ class AUVVecEnv:
         k64 = np.arange(64) * (2 * np.pi / 64)
         unit64 = np.stack([np.cos(k64), np.sin(k64)], axis=1)
         unit64[np.abs(unit64) < 1e-15] = 0.0
-        self._ray = dict(cos_sin=t(cos_sin, torch.float64), weight=t(weight, torch.float32),
-                         sector=t(sector, torch.uint8), unit64=t(unit64, torch.float64))
+        if _shared is not None:
+            self._ray = _shared["ray"]
+        else:
+            self._ray = dict(cos_sin=t(cos_sin, torch.float64), weight=t(weight, torch.float32),
+                             sector=t(sector, torch.uint8), unit64=t(unit64, torch.float64))
         self.sector_index = sector
         self.rays = _lib.AuvRayTable(
             self._ray["cos_sin"].data_ptr(), self._ray["weight"].data_ptr(), self._ray["sector"].data_ptr(), self._ray["unit64"].data_ptr(), wsum
@@ -141,7 +146,7 @@ class AUVVecEnv:
 
         # ---- path bank
         bank = scenarios.bank
-        self._bank = bank.device_arrays(dev)
+        self._bank = _shared["bank"] if _shared is not None else bank.device_arrays(dev)
         b = self._bank
         self.paths = _lib.AuvPathBank(
             bank.n_paths, bank.knots.shape[1], b["poly_off"].data_ptr(), b["poly_xy"].data_ptr(),
@@ -153,9 +158,12 @@ class AUVVecEnv:
         # ---- scenario pool
         M, Km, Ks = scenarios.n_scenarios, scenarios.k_moving, scenarios.k_static
         self.k_moving, self.k_static = Km, Ks
+        mw = max(1, (Km + Ks + scenarios.world.n + 31) // 32)
+        if mw > 32:
+            raise ValueError("at most 1024 obstacle slots (moving + static + world polygons) per env")
         pos0, disp0, counter0 = scenarios.initial_obstacle_state(float(self.config.simulation.t_step_size))
         vel = scenarios.vel_table if len(scenarios.vel_table) else np.zeros((1, 2))
-        self._pool = dict(
+        self._pool = _shared["pool"] if _shared is not None else dict(
             path_id=t(scenarios.path_id, torch.int32),
             vessel_init=t(scenarios.vessel_init, torch.float64),
             mov_start=t(scenarios.mov_start, torch.float64),
@@ -170,10 +178,17 @@ class AUVVecEnv:
         )
         world = scenarios.world
         self.n_world = Pw = world.n
-        if Pw:
+        if Pw and _shared is None:
             self._pool.update(
                 world_circle=t(world.circle, torch.float64), world_voff=t(world.voff, torch.int32),
                 world_verts=t(world.verts, torch.float64),
+            )
+        if _shared is None:
+            # cached first observation of every scenario (filled by _build_reset_cache)
+            self._pool.update(
+                reset_obs=torch.zeros((M, self.obs_dim), dtype=torch.float32, device=dev),
+                reset_max_progress=torch.zeros(M, dtype=torch.float64, device=dev),
+                reset_mask=torch.zeros((M, mw), dtype=torch.int32, device=dev),
             )
         p = self._pool
         wptr = lambda k: p[k].data_ptr() if k in p else None
@@ -182,12 +197,10 @@ class AUVVecEnv:
             p["mov_width"].data_ptr(), p["mov_track"].data_ptr(), p["mov_pos0"].data_ptr(), p["mov_disp0"].data_ptr(),
             p["mov_counter0"].data_ptr(), p["vel_table"].data_ptr(), p["st_pos"].data_ptr(), p["st_radius"].data_ptr(),
             wptr("world_circle"), wptr("world_voff"), wptr("world_verts"),
+            p["reset_obs"].data_ptr(), p["reset_max_progress"].data_ptr(), p["reset_mask"].data_ptr(),
         )
 
         # ---- mutable batch state
-        mw = max(1, (Km + Ks + Pw + 31) // 32)
-        if mw > 32:
-            raise ValueError("at most 1024 obstacle slots (moving + static + world polygons) per env")
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
         self._st = dict(
             scn_id=((torch.arange(N, device=dev, dtype=torch.int64) + self.env_offset) % M).to(torch.int32),
@@ -204,12 +217,23 @@ class AUVVecEnv:
             mov_counter=z((N, max(Km, 1)), torch.float64),
             nav=z((N, _lib.NAV_W), torch.float64),
         )
+        # scratch between the culling and the casting stage: one record slot per obstacle slot
+        # can never overflow; worlds with many polygons cap it (overflow raises, never silent)
+        slots = Km + Ks + Pw
+        self.rec_cap = int(max_nearby) if max_nearby is not None else (slots if slots <= 64 else 64)
+        self.rec_cap = max(1, min(self.rec_cap, max(slots, 1)))
+        self._scratch = dict(
+            rec=torch.zeros((N, self.rec_cap, _lib.REC_BYTES), dtype=torch.uint8, device=dev),
+            rec_cnt=z(N, torch.int32), status=z(1, torch.int32),
+        )
         s = self._st
         self.batch = _lib.AuvBatch(
             N, mw, self.env_offset, 0, s["scn_id"].data_ptr(), s["episode"].data_ptr(), s["state"].data_ptr(),
             s["step_counter"].data_ptr(), s["t_step"].data_ptr(), s["cum_reward"].data_ptr(),
             s["max_progress"].data_ptr(), s["cte_sum"].data_ptr(), s["nearby_mask"].data_ptr(),
             s["mov_pos"].data_ptr(), s["mov_disp"].data_ptr(), s["mov_counter"].data_ptr(), s["nav"].data_ptr(),
+            self._scratch["rec"].data_ptr(), self._scratch["rec_cnt"].data_ptr(),
+            self._scratch["status"].data_ptr(), self.rec_cap, 0,
         )
 
         # ---- outputs
@@ -247,6 +271,29 @@ class AUVVecEnv:
 
         self.action_space = Box(low=np.array([-1, -0.15]), high=np.array([1, 0.15]), dtype=np.float32)
         self.observation_space = Box(low=-np.ones(self.obs_dim), high=np.ones(self.obs_dim), dtype=np.float32)
+        self._max_nearby = max_nearby
+        self._cull_mode = cull_mode
+        if auto_reset and _shared is None:
+            self._build_reset_cache()
+
+    def _build_reset_cache(self, chunk: int = 65536):
+        """reset() of scenario m always returns the same observation (it depends on the
+        scenario only), so it is computed once per pool scenario -- by the same kernels, over a
+        temporary batch that shares this env's device tables -- and the in-step auto-reset of a
+        finished env becomes a copy (pool.reset_obs / reset_max_progress / reset_mask)."""
+        M = self.scenarios.n_scenarios
+        shared = dict(ray=self._ray, bank=self._bank, pool=self._pool)
+        for start in range(0, M, chunk):
+            n = min(chunk, M - start)
+            tmp = AUVVecEnv(self.scenarios, n, self.config, device=self.device, test_mode=self.test_mode,
+                            auto_reset=False, cull_mode=self._cull_mode, env_offset=start,
+                            max_nearby=self._max_nearby, _shared=shared)
+            obs = tmp.reset()
+            self._pool["reset_obs"][start:start + n].copy_(obs)
+            self._pool["reset_max_progress"][start:start + n].copy_(tmp._st["max_progress"])
+            self._pool["reset_mask"][start:start + n].copy_(tmp._st["nearby_mask"])
+            del tmp
+        torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -254,6 +301,16 @@ class AUVVecEnv:
 
     def _refs(self):
         return C.byref(self.cfg), C.byref(self.rays), C.byref(self.paths), C.byref(self.pool), C.byref(self.batch)
+
+    def check_status(self):
+        """Raise if a kernel flagged a problem (synchronises).  Called by reset() and
+        episode_stats(); call it yourself after long unattended runs."""
+        st = int(self._scratch["status"].item())
+        if st & _lib.STATUS_REC_OVERFLOW:
+            raise RuntimeError(
+                f"more than max_nearby={self.rec_cap} obstacles were within sensor range of one env: "
+                "construct AUVVecEnv with a larger max_nearby"
+            )
 
     # ------------------------------------------------------------------ gym/VecEnv API
     def reset(self) -> torch.Tensor:
@@ -265,6 +322,7 @@ class AUVVecEnv:
                 self.lib.auv_observe(cfg, rays, paths, pool, batch, C.byref(self.out), _lib.OBSERVE_RESET, self._stream()),
                 "auv_observe",
             )
+        self.check_status()
         return self._out["obs"]
 
     def reset_envs(self, mask: torch.Tensor, scenario_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -357,9 +415,9 @@ class AUVVecEnv:
     def navigate(self):
         """Vessel.navigate for every env -> nav record [N, 12] (s, chi, y_e, s_la, look-ahead
         heading error, heading error, goal distance, progress, cos psi, sin psi, reached, ...)."""
-        cfg, _, paths, pool, batch = self._refs()
+        cfg, rays, paths, pool, batch = self._refs()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.auv_navigate(cfg, paths, pool, batch, self._stream()), "auv_navigate")
+            _lib.check(self.lib.auv_navigate(cfg, rays, paths, pool, batch, self._stream()), "auv_navigate")
         return self._st["nav"]
 
     def observe(self, mode=_lib.OBSERVE_STEP):
@@ -397,6 +455,7 @@ class AUVVecEnv:
         over ranks first -- the only collective on this path."""
         from .sharding import reduce_stats, summarize_stats
 
+        self.check_status()
         st = self._out["stats"].clone()
         st[9] = float(self.total_steps) * self.num_envs
         if reduce:

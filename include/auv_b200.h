@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 7
+#define AUV_ABI_VERSION 9
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -59,6 +59,9 @@ extern "C" {
 #define AUV_PATH_BLOCK 32     /* polyline segments per projection block */
 #define AUV_PATH_SUPER 32     /* blocks per projection superblock */
 #define AUV_NAV_W 12          /* doubles per env in AuvBatch.nav */
+#define AUV_REC_BYTES 80      /* bytes per obstacle record in AuvBatch.rec */
+#define AUV_MAX_POLY_VERTS 192 /* vertices of one world polygon incl. the closing one */
+#define AUV_STATUS_REC_OVERFLOW 1 /* AuvBatch.status bit: more nearby obstacles than rec_cap */
 
 /* gym_auv/config.py field names (EpisodeConfig/SimulationConfig/VesselConfig).  POD. */
 typedef struct AuvConfig {
@@ -149,6 +152,12 @@ typedef struct AuvScenarioPool {
   const double* world_circle;  /* [n_world][3] cx, cy, rho                              */
   const int32_t* world_voff;   /* [n_world+1] first vertex of each closed ring          */
   const double* world_verts;   /* [total][2]  rings, last vertex repeats the first      */
+  /* what reset() returns depends on the scenario only: with auto_reset these caches (filled
+   * once by running auv_reset + auv_observe(RESET) over the pool) turn the in-step reset of
+   * a finished env into a copy */
+  const float* reset_obs;            /* [M][obs_dim] first observation of each scenario        */
+  const double* reset_max_progress;  /* [M]          Vessel._max_progress after that observe    */
+  const uint32_t* reset_mask;        /* [M][mask_words] nearby list loaded by that observe      */
 } AuvScenarioPool;
 
 /* Mutable per-env state (SoA).  N = n_envs. */
@@ -172,6 +181,12 @@ typedef struct AuvBatch {
   double* nav;            /* [N][AUV_NAV_W] Vessel._last_navi_state_dict: s, chi, y_e, s_la,
                              look_ahead_heading_error, heading_error, goal_distance, progress,
                              cos psi, sin psi, reached_goal, cos(heading_error)            */
+  /* scratch between the culling stage and the ray-casting stage (opaque to the caller) */
+  void* rec;              /* [N][rec_cap][AUV_REC_BYTES] obstacle records, 16-byte aligned       */
+  int32_t* rec_cnt;       /* [N] records of each env                                            */
+  int32_t* status;        /* [1] or NULL: AUV_STATUS_* bits raised by kernels                   */
+  int32_t rec_cap;        /* records per env; >= k_moving+k_static+n_world can never overflow  */
+  int32_t reserved1;
 } AuvBatch;
 
 /* Outputs of one step / observe (all optional except obs/reward/done). */
@@ -222,9 +237,11 @@ int auv_obstacle_update(const AuvConfig* cfg, const AuvScenarioPool* pool, AuvBa
                         void* stream);
 int auv_vessel_step(const AuvConfig* cfg, AuvBatch* batch, const float* actions /*[N][2]*/,
                     void* stream);
-/* Vessel.navigate for every env (fills AuvBatch.nav / max_progress); auv_observe calls it. */
-int auv_navigate(const AuvConfig* cfg, const AuvPathBank* paths, const AuvScenarioPool* pool,
-                 AuvBatch* batch, void* stream);
+/* Vessel.navigate for every env (fills AuvBatch.nav / max_progress) and, with use_lidar, the
+ * culling stage of Vessel.perceive (nearby list, ray windows -> AuvBatch.rec); auv_observe
+ * calls it. */
+int auv_navigate(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                 const AuvScenarioPool* pool, AuvBatch* batch, void* stream);
 int auv_observe(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                 const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode,
                 void* stream);
@@ -247,11 +264,11 @@ int auv_step_host(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBa
 typedef struct AuvTimer AuvTimer;
 AuvTimer* auv_timer_create(int capacity);
 void auv_timer_destroy(AuvTimer* t);
-/* auv_step with events recorded around k_obstacle_update, k_vessel_nav and k_observe. */
+/* auv_step with events recorded around k_obstacle_update, k_vessel_nav and k_lidar. */
 int auv_step_timed(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                    const AuvScenarioPool* pool, AuvBatch* batch, const float* actions,
                    AuvStepOut* out, void* stream, AuvTimer* t, int slot);
-/* after the stream is synchronised: ms[0..2] = obstacle_update, vessel_nav, observe */
+/* after the stream is synchronised: ms[0..2] = obstacle_update, vessel_nav, lidar */
 int auv_timer_read(AuvTimer* t, int slot, float* ms);
 /* Measured FP32 FMA peak helper (roofline denominator): runs `iters` dependent FMAs per
  * thread on a full grid; the caller times it with CUDA events. Returns flop count. */
