@@ -60,6 +60,15 @@ __device__ __forceinline__ float pt_seg_dist_f(float qx, float qy, float ax, flo
   return sqrtf(dx * dx + dy * dy);
 }
 
+// squared distance from the origin-relative point (qx,qy) to the segment a + t e, t in [0,1],
+// with the precomputed inv = 1/|e|^2 (0 for a degenerate segment): no division, no sqrt
+__device__ __forceinline__ float pt_chord_d2_f(float qx, float qy, float4 ch, float inv) {
+  const float wx = qx - ch.x, wy = qy - ch.y;
+  const float t = fminf(fmaxf((wx * ch.z + wy * ch.w) * inv, 0.f), 1.f);
+  const float dx = wx - t * ch.z, dy = wy - t * ch.w;
+  return dx * dx + dy * dy;
+}
+
 // circle -> regular n-gon side count of buffer(r).boundary.simplify(0.3)
 // (obstacles.py:101-106; closed form SURVEY.md App. A.5, pinned against a literal
 // Douglas-Peucker in oracle/geos_lite.py): n = 64/m, m the largest power of two <= 32

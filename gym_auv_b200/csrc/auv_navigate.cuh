@@ -78,48 +78,56 @@ __device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid,
   const float qx = (float)(px - ox), qy = (float)(py - oy);
   const float pad = 1e-6f * (fabsf(qx) + fabsf(qy)) + 1e-6f;
   const float4* chord = reinterpret_cast<const float4*>(pb.blk_chord) + b0;
-  const float* dev = pb.blk_dev + b0;
+  const float2* aux = reinterpret_cast<const float2*>(pb.blk_dev) + b0;  // (1/|e|^2, deviation)
   const float4* sbc = reinterpret_cast<const float4*>(pb.sb_chord) + s0;
-  const float* sbd = pb.sb_dev + s0;
-  const float up = 1.f + 4e-6f, dn = 1.f - 4e-6f;
+  const float2* sba = reinterpret_cast<const float2*>(pb.sb_dev) + s0;
+  const float up = 1.f + 4e-6f, dn2 = (1.f - 4e-6f) * (1.f - 4e-6f);
   // All node loops below issue their loads in groups of U before any arithmetic, so a
   // thread has U independent L2 requests in flight instead of one (the kernel is bound by
-  // load latency, not by FP64 issue: profiles/r1b).
+  // load latency, not by FP64 issue: profiles/r1b).  Bounds are compared in the squared
+  // domain: an upper bound dc + dev + pad is only evaluated (one sqrt) when it can improve
+  // ub, and a node is discarded when dc^2 (1-eps)^2 > (ub + dev + pad)^2.
   constexpr int U = 8;
   float ub = INFINITY;
+#define AUV_TIGHTEN(d2, dv)                                         \
+  if ((d2) < ub * ub) ub = fminf(ub, sqrtf(d2) * up + (dv) + pad);
+#define AUV_PRUNED(d2, dv) ((d2) * dn2 > (ub + (dv) + pad) * (ub + (dv) + pad))
   for (int g0 = 0; g0 < nsb; g0 += U) {
     float4 ch[U];
-    float dv[U];
+    float2 ax[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int i = min(g0 + u, nsb - 1);
       ch[u] = sbc[i];
-      dv[u] = sbd[i];
+      ax[u] = sba[i];
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      ub = fminf(ub, pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * up + dv[u] + pad);
+    for (int u = 0; u < U; ++u) {
+      const float d2 = pt_chord_d2_f(qx, qy, ch[u], ax[u].x);
+      AUV_TIGHTEN(d2, ax[u].y)
+    }
   }
   // pass B: tighten over blocks of surviving superblocks; remember which survive
   unsigned long long live = 0ull;  // up to 64 superblocks tracked exactly, the rest are always visited
   for (int sb = 0; sb < nsb; ++sb) {
-    const float4 c0 = sbc[sb];
-    const float lb = pt_seg_dist_f(qx, qy, c0.x, c0.y, c0.z, c0.w) * dn - sbd[sb] - pad;
-    if (lb > ub) continue;
+    const float2 a0 = sba[sb];
+    if (AUV_PRUNED(pt_chord_d2_f(qx, qy, sbc[sb], a0.x), a0.y)) continue;
     if (sb < 64) live |= 1ull << sb;
     const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
     for (int g0 = sb * AUV_PATH_SUPER; g0 < be; g0 += U) {
       float4 ch[U];
-      float dv[U];
+      float2 ax[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = min(g0 + u, be - 1);
         ch[u] = chord[i];
-        dv[u] = dev[i];
+        ax[u] = aux[i];
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        ub = fminf(ub, pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * up + dv[u] + pad);
+      for (int u = 0; u < U; ++u) {
+        const float d2 = pt_chord_d2_f(qx, qy, ch[u], ax[u].x);
+        AUV_TIGHTEN(d2, ax[u].y)
+      }
     }
   }
   // pass C: exact refine
@@ -131,18 +139,17 @@ __device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid,
     const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
     for (int g0 = sb * AUV_PATH_SUPER; g0 < be; g0 += U) {
       float4 ch[U];
-      float dv[U];
+      float2 ax[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = min(g0 + u, be - 1);
         ch[u] = chord[i];
-        dv[u] = dev[i];
+        ax[u] = aux[i];
       }
       unsigned cand = 0u;
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (g0 + u < be && pt_seg_dist_f(qx, qy, ch[u].x, ch[u].y, ch[u].z, ch[u].w) * dn - dv[u] - pad <= ub)
-          cand |= 1u << u;
+        if (g0 + u < be && !AUV_PRUNED(pt_chord_d2_f(qx, qy, ch[u], ax[u].x), ax[u].y)) cand |= 1u << u;
       while (cand) {  // blocks in increasing order
         const int b = g0 + __ffs(cand) - 1;
         cand &= cand - 1;
@@ -165,6 +172,8 @@ __device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid,
       }
     }
   }
+#undef AUV_TIGHTEN
+#undef AUV_PRUNED
   // segmentNearestMeasure of the winning segment
   const double2 A = poly[best_seg], B = poly[best_seg + 1];
   const double start = pb.poly_cum[v0 + best_seg];
@@ -188,12 +197,15 @@ __device__ __forceinline__ void navigate_thread(const AuvConfig& cfg, const AuvP
   double p_x, p_y, d_x, d_y, l_x, l_y, ldx, ldy;
   pchip_eval(pb, pid, s, p_x, p_y, d_x, d_y);
   pchip_eval(pb, pid, s_la, l_x, l_y, ldx, ldy);
-  const double chi = atan2(d_y, d_x);
-  double sc, cc;
-  sincos(chi, &sc, &cc);
+  const double chi = (double)atan2f((float)d_y, (float)d_x);  // diagnostic only (nav[NAV_CHI])
+  // cross-track error = second row of Rz(-chi) applied to (path(s) - p); cos/sin(chi) are the
+  // normalised derivative (no trig needed)
+  const double dn = sqrt(d_x * d_x + d_y * d_y);
+  const double cc = dn > 0.0 ? d_x / dn : 1.0, sc = dn > 0.0 ? d_y / dn : 0.0;
   const double y_e = -sc * (p_x - px) + cc * (p_y - py);
-  const double la_err = princip(atan2(ldy, ldx) - psi);
-  const double head_err = princip(atan2(l_y - py, l_x - px) - psi);
+  // heading errors feed float32 observations and cos() in the reward: FP32 atan2 (~2e-7 rad)
+  const double la_err = princip((double)atan2f((float)ldy, (float)ldx) - psi);
+  const double head_err = princip((double)atan2f((float)(l_y - py), (float)(l_x - px)) - psi);
   const double progress = s / L;
   const double gx = pb.end_xy[2 * pid] - px, gy = pb.end_xy[2 * pid + 1] - py;
   const double goal = sqrt(gx * gx + gy * gy);
@@ -212,7 +224,7 @@ __device__ __forceinline__ void navigate_thread(const AuvConfig& cfg, const AuvP
   o[NAV_COSPSI] = cp;
   o[NAV_SINPSI] = sp;
   o[NAV_REACHED] = reached ? 1.0 : 0.0;
-  o[NAV_COS_HEAD_ERR] = cos(head_err);
+  o[NAV_COS_HEAD_ERR] = (double)cosf((float)head_err);
   batch.max_progress[e] = fmax(progress, batch.max_progress[e]);  // vessel.py:507
 }
 

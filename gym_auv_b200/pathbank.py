@@ -34,10 +34,10 @@ class PathTable:
     coef: np.ndarray  # [999, 2, 4]
     poly: np.ndarray  # [n, 2]
     cum: np.ndarray  # [n]
-    blk_chord: np.ndarray  # [nblk, 4] float32, relative to origin
-    blk_dev: np.ndarray  # [nblk] float32
+    blk_chord: np.ndarray  # [nblk, 4] float32 (ax, ay, ex, ey), relative to origin
+    blk_dev: np.ndarray  # [nblk, 2] float32 (1/|e|^2, deviation)
     sb_chord: np.ndarray  # [nsb, 4] float32
-    sb_dev: np.ndarray  # [nsb] float32
+    sb_dev: np.ndarray  # [nsb, 2] float32
     origin: np.ndarray  # [2]
     length: float
     end: np.ndarray  # [2]
@@ -57,28 +57,31 @@ def _chord_lengths(pts: np.ndarray) -> np.ndarray:
 
 
 def _capsules(rel: np.ndarray, nseg: int, span: int):
-    """One (chord, deviation) capsule per `span` consecutive segments: chord = first/last
-    vertex (rounded to float32), deviation = max distance of the covered vertices from the
-    ROUNDED chord (FP64) plus a float32 rounding allowance, rounded up."""
+    """One capsule per `span` consecutive segments.  Returns
+      chord [n, 4] float32 = (ax, ay, ex, ey): first vertex and chord vector (last - first),
+      aux   [n, 2] float32 = (1/|e|^2 or 0, deviation): the deviation is the max distance of
+    the covered vertices from the ROUNDED chord (evaluated in FP64) plus a float32 rounding
+    allowance, rounded up -- so dist(P, polyline part) is within [dc - dev, dc + dev] of the
+    distance dc from P to the rounded chord."""
     n = (nseg + span - 1) // span
     first = np.arange(n) * span
     last = np.minimum(first + span, nseg)
-    chord = np.concatenate([rel[first], rel[last]], axis=1).astype(np.float32)
+    chord = np.concatenate([rel[first], rel[last] - rel[first]], axis=1).astype(np.float32)
     a = chord[:, 0:2].astype(np.float64)
-    b = chord[:, 2:4].astype(np.float64)
-    e = b - a
+    e = chord[:, 2:4].astype(np.float64)
     len2 = np.sum(e * e, axis=1)
+    with np.errstate(divide="ignore"):
+        inv = np.where(len2 > 0, 1.0 / len2, 0.0).astype(np.float32)
     dev = np.zeros(n)
     for k in range(span + 1):  # loop over the offset inside the node keeps memory O(n)
         v = rel[np.minimum(first + k, last)]
         w = v - a
-        with np.errstate(divide="ignore", invalid="ignore"):
-            t = np.where(len2 > 0, np.sum(w * e, axis=1) / len2, 0.0)
-        t = np.clip(t, 0.0, 1.0)
+        t = np.clip(np.sum(w * e, axis=1) * inv.astype(np.float64), 0.0, 1.0)
         dev = np.maximum(dev, np.sqrt(np.sum((w - t[:, None] * e) ** 2, axis=1)))
     extent = float(np.abs(rel).max()) + 1.0
     dev = dev + 8.0 * np.finfo(np.float32).eps * extent
-    return chord, np.nextafter(dev.astype(np.float32), np.float32(np.inf))
+    dev = np.nextafter(dev.astype(np.float32), np.float32(np.inf))
+    return chord, np.stack([inv, dev], axis=1).astype(np.float32)
 
 
 def build_path(waypoints) -> PathTable:

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 9
+#define AUV_ABI_VERSION 10
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -113,11 +113,13 @@ typedef struct AuvPathBank {
   const double* poly_xy;   /* [total_vertices][2]                                       */
   const double* poly_cum;  /* [total_vertices] chord-length prefix sum at each vertex   */
   const int32_t* blk_off;  /* [n_paths+1] first block of each path                      */
-  const float* blk_chord;  /* [total_blocks][4] ax,ay,bx,by relative to origin[path]    */
-  const float* blk_dev;    /* [total_blocks] max vertex deviation from chord + fp pad   */
+  const float* blk_chord;  /* [total_blocks][4] ax, ay, ex, ey: first vertex and chord vector,
+                              relative to origin[path]                                  */
+  const float* blk_dev;    /* [total_blocks][2] 1/|e|^2 (0 if degenerate), max vertex
+                              deviation from the chord + fp pad                         */
   const int32_t* sb_off;   /* [n_paths+1] first superblock (32 blocks) of each path     */
-  const float* sb_chord;   /* [total_superblocks][4]                                    */
-  const float* sb_dev;     /* [total_superblocks]                                       */
+  const float* sb_chord;   /* [total_superblocks][4] same layout as blk_chord            */
+  const float* sb_dev;     /* [total_superblocks][2] same layout as blk_dev              */
   const double* origin;    /* [n_paths][2]                                              */
   const double* knots;     /* [n_paths][n_knots]                                        */
   const double* coef;      /* [n_paths][n_knots-1][2][4]  (x: c0..c3, y: c0..c3)        */

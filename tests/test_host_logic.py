@@ -67,10 +67,13 @@ def test_path_blocks_bound_their_segments():
     assert len(tab.blk_dev) == (nseg + PATH_BLOCK - 1) // PATH_BLOCK
     for b in (0, 7, len(tab.blk_dev) - 1):
         lo, hi = b * PATH_BLOCK, min((b + 1) * PATH_BLOCK, nseg)
-        a, c = tab.blk_chord[b, :2].astype(float), tab.blk_chord[b, 2:].astype(float)
+        a = tab.blk_chord[b, :2].astype(float)
+        c = a + tab.blk_chord[b, 2:].astype(float)  # (first vertex, chord vector)
         for k in range(lo, hi + 1):
             d = G.point_segment_distance(rel[k, 0], rel[k, 1], a[0], a[1], c[0], c[1])
-            assert d <= tab.blk_dev[b]
+            assert d <= tab.blk_dev[b, 1]
+        e2 = float(np.sum(tab.blk_chord[b, 2:].astype(float) ** 2))
+        assert tab.blk_dev[b, 0] == pytest.approx(1.0 / e2, rel=1e-6)
 
 
 def test_random_curve_shape():
