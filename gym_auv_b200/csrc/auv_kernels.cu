@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(64) k_vessel_nav(const __grid_constant__ AuvCo
 constexpr int VMAX = 192;  // staged vertices per warp per round (float2)
 constexpr int RROUND = 6;  // records per round: 6 x 80 B = 30 lanes x 16 B, one coalesced load
 #ifndef AUV_LIDAR_WARPS
-#define AUV_LIDAR_WARPS 8  // envs per CTA (the warps of a CTA never synchronise with each other)
+#define AUV_LIDAR_WARPS 2  // envs per CTA; sweep 1/2/4/8/16: 0.175/0.157/0.161/0.178/0.205 ms (profiles/r1e) (the warps of a CTA never synchronise with each other)
 #endif
 
 struct LidarArgs {
@@ -641,7 +641,8 @@ __global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32) k_lidar(const __grid_con
   const double cte_sum = SCAL(SC_CTE) + fabs(y_e);
   const bool do_reset = done && cfg.auto_reset;
   const int scn = (int)SCAL(SC_SCN);
-  const int next = (int)(((long long)scn + n) % A.pool.n_scenarios);
+  int next = 0;
+  if (do_reset) next = (int)(((long long)scn + n) % A.pool.n_scenarios);  // uniform across the warp
   if (lane == 0) {
     A.out.reward[e] = (float)reward;
     A.out.done[e] = done;

@@ -419,3 +419,60 @@ def test_dict_observation_facade():
     assert set(obs) == {"proprioceptive", "lidar"}
     assert obs["proprioceptive"].shape == (6,) and obs["lidar"].shape == (3, 180)
     assert env.observation_space.contains({k: v.astype(np.float32) for k, v in obs.items()})
+
+
+def test_auto_reset_uses_cached_first_observation_and_matches_fresh_reset():
+    """The in-step reset copies the scenario's cached first observation; it must equal what an
+    explicit reset() of that scenario returns, and the following steps must be identical to
+    those of a freshly reset env (nearby list, obstacle state and counters included)."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    cfg.episode.max_timesteps = 4
+    scn = S.moving_obstacles(6, 5, 5, seed=14)
+    a = torch.as_tensor(random_actions(9, 6, 2), dtype=torch.float32, device="cuda")
+    env = AUVVecEnv(scn, 6, cfg, test_mode=False, auto_reset=True, debug=True)
+    fresh = AUVVecEnv(scn, 6, cfg, test_mode=False, auto_reset=False, debug=True)
+    obs0 = fresh.reset().clone()
+    env.reset()
+    for t in range(4):
+        obs, _, done, _ = env.step(a[t])
+    assert bool(done.all())  # time limit
+    assert torch.equal(obs, obs0)  # cached reset obs == explicit reset obs, bit for bit
+    for t in range(4, 7):  # second episode of env == first episode of a fresh env, same actions
+        o1, r1, d1, _ = env.step(a[t])
+        o2, r2, d2, _ = fresh.step(a[t])
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+        assert torch.equal(env.get_attr("mov_pos"), fresh.get_attr("mov_pos"))
+
+
+def test_record_capacity_overflow_is_reported_not_silent():
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    scn = S.test_scenario3()  # 21 circles, many within sensor range
+    env = AUVVecEnv(scn, 1, lidar_config(), test_mode=True, auto_reset=False, max_nearby=2)
+    with pytest.raises(RuntimeError, match="max_nearby"):
+        env.reset()
+    ok = AUVVecEnv(scn, 1, lidar_config(), test_mode=True, auto_reset=False)  # default capacity = all slots
+    ok.reset()
+
+
+def test_staged_entry_points_compose_to_a_step():
+    """obstacle_update + vessel_step + observe (the staged ABI mirroring _update /
+    Vessel.step / observe) == one auv_step."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    scn = S.moving_obstacles(5, 4, 4, seed=3)
+    e1 = AUVVecEnv(scn, 5, cfg, test_mode=True, auto_reset=False)
+    e2 = AUVVecEnv(scn, 5, cfg, test_mode=True, auto_reset=False)
+    e1.reset(), e2.reset()
+    a = torch.as_tensor(random_actions(5, 5, 1), dtype=torch.float32, device="cuda")
+    for t in range(5):
+        o1, r1, d1, _ = e1.step(a[t])
+        e2.obstacle_update()
+        e2.vessel_step(a[t])
+        o2 = e2.observe()
+        assert torch.equal(o1, o2) and torch.equal(r1, e2._out["reward"]) and torch.equal(e1.state, e2.state)
+    nav = e2.navigate()
+    assert nav.shape == (5, 12) and torch.equal(nav, e1.get_attr("nav"))
