@@ -8,11 +8,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
-ABI_VERSION = 10
+ABI_VERSION = 12
 REC_BYTES = 80
 MAX_POLY_VERTS = 192
 STATUS_REC_OVERFLOW = 1
-NAV_W = 12
+NAV_W = 16
 N_STATS = 16
 STAT_NAMES = [
     "episodes",
@@ -176,6 +176,10 @@ EXPORTS = [
     "auv_timer_destroy",
     "auv_step_timed",
     "auv_timer_read",
+    "auv_pipeline_create",
+    "auv_pipeline_destroy",
+    "auv_step_chunked",
+    "auv_step_host_chunked",
 ]
 
 _lib = None
@@ -216,6 +220,18 @@ def load():
     lib.auv_step_host.argtypes = [
         P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, _vp, P(AuvStepOut),
         _vp, _vp, _vp, _vp,
+    ]
+    lib.auv_pipeline_create.argtypes = [C.c_int]
+    lib.auv_pipeline_create.restype = _vp
+    lib.auv_pipeline_destroy.argtypes = [_vp]
+    lib.auv_pipeline_destroy.restype = None
+    lib.auv_step_chunked.argtypes = [
+        P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, P(AuvStepOut), _vp,
+        _vp, C.c_int,
+    ]
+    lib.auv_step_host_chunked.argtypes = [
+        P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, _vp, P(AuvStepOut),
+        _vp, _vp, _vp, _vp, _vp, C.c_int,
     ]
     lib.auv_timer_create.argtypes = [C.c_int]
     lib.auv_timer_create.restype = _vp

@@ -8,7 +8,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "auv_kernels.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "auv_device.cuh"), os.path.join(HERE, "..", "include", "auv_b200.h")]
+DEPS = [SRC, os.path.join(HERE, "..", "include", "auv_b200.h")] + [
+    os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc"))) if f.endswith(".cuh")
+]
 OUT = os.path.join(HERE, "libauv_b200.so")
 
 NVCC_FLAGS = [

@@ -35,10 +35,11 @@ namespace auv {
 // k_obstacle_update     obstacles.py:195-215
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_obstacle_update(AuvConfig cfg, AuvScenarioPool pool,
-                                                          AuvBatch batch) {
+                                                          AuvBatch batch, int e0, int cnt) {
   const int km = pool.k_moving;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)batch.n_envs * km) return;
+  const long long lid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lid >= (long long)cnt * km) return;
+  const long long gid = lid + (long long)e0 * km;  // envs [e0, e0 + cnt)
   const int e = (int)(gid / km);
   const int j = (int)(gid - (long long)e * km);
   const long long ps = (long long)batch.scn_id[e] * km + j;
@@ -296,10 +297,11 @@ __global__ void __launch_bounds__(64) k_vessel_nav(const __grid_constant__ AuvCo
                                                     const __grid_constant__ AuvBatch batch,
                                                     const double2* __restrict__ unit64,
                                                     int* __restrict__ windows_out,
-                                                    const float* __restrict__ actions) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+                                                    const float* __restrict__ actions, float* __restrict__ obs_out,
+                                                    int obs_dim, int e0, int e1) {
+  const int e = e0 + blockIdx.x * blockDim.x + threadIdx.x;  // envs [e0, e1)
   const int n = batch.n_envs;
-  if (e >= n) return;
+  if (e >= e1) return;
   S6 y = load_state(batch.state, n, e);
   int step_counter = batch.step_counter[e];
   if (DYN) {
@@ -308,17 +310,22 @@ __global__ void __launch_bounds__(64) k_vessel_nav(const __grid_constant__ AuvCo
     batch.step_counter[e] = ++step_counter;
   }
   const int scn = batch.scn_id[e];
-  navigate_thread(cfg, paths, batch, pool.path_id[scn], e, y.x, y.y, y.psi);
+  navigate_thread(cfg, paths, batch, pool.path_id[scn], e, y.x, y.y, y.psi, y.u, y.v, y.r,
+                  obs_out ? obs_out + (long long)e * obs_dim : nullptr);
   if (cfg.use_lidar) cull_env_thread(cfg, pool, batch, unit64, windows_out, e, scn, y.x, y.y, y.psi, step_counter);
 }
 
 // ------------------------------------------------------------------------------------
-// k_lidar: CTA per env, thread per ray
+// k_lidar: warp per env (AUV_LIDAR_EPW consecutive envs per warp, the next env's scalars and
+// first records prefetched while the current one is cast)
 // ------------------------------------------------------------------------------------
 constexpr int VMAX = 192;  // staged vertices per warp per round (float2)
 constexpr int RROUND = 6;  // records per round: 6 x 80 B = 30 lanes x 16 B, one coalesced load
 #ifndef AUV_LIDAR_WARPS
-#define AUV_LIDAR_WARPS 2  // envs per CTA; sweep 1/2/4/8/16: 0.175/0.157/0.161/0.178/0.205 ms (profiles/r1e) (the warps of a CTA never synchronise with each other)
+#define AUV_LIDAR_WARPS 2  // warps per CTA (the warps of a CTA never synchronise with each other)
+#endif
+#ifndef AUV_LIDAR_EPW
+#define AUV_LIDAR_EPW 2    // envs per warp, processed one after the other (sweep 1/2/4/8: 0.146/0.142/0.145/0.146 ms)
 #endif
 
 struct LidarArgs {
@@ -330,72 +337,142 @@ struct LidarArgs {
   AuvStepOut out;
   int mode;       // AUV_OBSERVE_STEP | AUV_OBSERVE_RESET
   int obs_dim;
+  int e0, e1;     // envs [e0, e1) of the batch are processed by this launch
   float pen_clear_ray;     // range * exp(-0.1 range): penalty term of a ray that reads sensor_range
+  float inv_log_range;     // 1 / log(1 + range)
   double clear_closeness;  // -range * exp(-0.1 range): closeness reward when every ray is clear
+  double inv_weight_sum;   // 1 / sum of the ray weights
   double feas_width;       // vessel_width * feasibility_width_multiplier (sensor.py:166-168)
 };
 
 struct __align__(16) WarpSmem {
   float2 verts[VMAX];
   ObstRec rec[RROUND];
+  int4 cand[RROUND];  // per record of the round: first slot in the flat candidate list, I1.lo, |I1|, I2.lo
   int voff[RROUND + 1];
   int pad;
 };
-// lanes of the per-env scalar pack (one register per lane, read back by shuffle)
-#define SC_STATE 12
-#define SC_CUM 18
-#define SC_CTE 19
-#define SC_MAXPROG 20
+// lanes of the per-env scalar pack (one register per lane, read back by shuffle): lanes
+// 0..AUV_NAV_W-1 hold the navigation record
+#define SC_STATE 16  // x, y, psi
+#define SC_CUM 19
+#define SC_CTE 20
 #define SC_TSTEP 21
 #define SC_SCN 22
 #define SC_CNT 23
 
-__global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32) k_lidar(const __grid_constant__ LidarArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// one round trip per env: every per-env scalar is fetched by a different lane, and the first
+// RROUND records are fetched speculatively (30 lanes x 16 B) before their count is known
+__device__ __forceinline__ void lidar_fetch(const AuvConfig& cfg, const AuvBatch& batch, int e, int lane,
+                                            double& sc, uint4& spec) {
+  const int n = batch.n_envs;
+  sc = 0.0;
+  if (lane < AUV_NAV_W) sc = batch.nav[(long long)e * AUV_NAV_W + lane];
+  else if (lane < SC_STATE + 3) sc = batch.state[(long long)(lane - SC_STATE) * n + e];
+  else if (lane == SC_CUM) sc = batch.cum_reward[e];
+  else if (lane == SC_CTE) sc = batch.cte_sum[e];
+  else if (lane == SC_TSTEP) sc = (double)batch.t_step[e];
+  else if (lane == SC_SCN) sc = (double)batch.scn_id[e];
+  else if (lane == SC_CNT) sc = cfg.use_lidar ? (double)batch.rec_cnt[e] : 0.0;
+  spec = make_uint4(0, 0, 0, 0);
+  if (cfg.use_lidar && lane < RROUND * 5 && lane / 5 < batch.rec_cap)
+    spec = reinterpret_cast<const uint4*>(reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap)[lane];
+}
+
+// range of ray (c, s, world angle theta) against one staged obstacle record; `best` is the
+// ray's current reading (only used to skip obstacles that cannot improve it)
+__device__ __forceinline__ float cast_ray_record(const ObstRec& q, const float2* __restrict__ vp, float c, float s,
+                                                 float theta, float best, float rangef) {
+  const int fl = q.flags, nq = q.nv;
+  if (fl & OFLAG_INSIDE) return 0.f;
+  const float rho = q.rho;
+  const float tc = q.ecx * c + q.ecy * s;
+  const float hc = q.ecy * c - q.ecx * s;
+  const float slack = rho * 1e-5f + 1e-4f;
+  if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > best) return best;
+  if (!(fl & (OFLAG_PENTAGON | OFLAG_WORLD)) && nq > 16) {
+    // Regular n-gon inscribed in the enclosing circle (n = 16/32/64): the ray's line
+    // meets the circle at polar angles theta+g and theta+pi-g (g = asin(-hc/r));
+    // between circle and polygon lies the circular segment of exactly one edge, so the
+    // polygon crossing is on the edge whose angular span contains that angle.  The
+    // neighbour on the nearer side is tested too (FP32 error of asinf near grazing).
+    const int nn = nq - 1;
+    const float g = asinf(fminf(fmaxf(-hc / rho, -1.f), 1.f));
+    const float invd = (float)nn * 0.15915494309189535f;
+#pragma unroll
+    for (int sol = 0; sol < 2; ++sol) {
+      const float p = (sol == 0 ? theta + g : theta + 3.14159265358979f - g) * invd;
+      const float kf = floorf(p);
+      const int k0 = (int)kf & (nn - 1);
+      const int k1 = (p - kf < 0.5f ? k0 - 1 : k0 + 1) & (nn - 1);
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int k = w == 0 ? k0 : k1;
+        const float2 va = vp[k], vb = vp[k + 1];
+        const float ya = va.y * c - va.x * s, yb = vb.y * c - vb.x * s;
+        if ((ya <= 0.f && yb >= 0.f) || (ya >= 0.f && yb <= 0.f)) {
+          const float xa = va.x * c + va.y * s, xb = vb.x * c + vb.y * s;
+          const float t = xa + (xb - xa) * (ya / (ya - yb));
+          if (t >= 0.f && t <= rangef) best = fminf(best, t);
+        }
+      }
+    }
+    return best;
+  }
+  float2 v = vp[0];
+  float xp = v.x * c + v.y * s;
+  float yp = v.y * c - v.x * s;
+  for (int k = 1; k < nq; ++k) {
+    v = vp[k];
+    const float xc = v.x * c + v.y * s;
+    const float yc = v.y * c - v.x * s;
+    if ((yp <= 0.f && yc >= 0.f) || (yp >= 0.f && yc <= 0.f)) {
+      const float t = xp + (xc - xp) * (yp / (yp - yc));
+      if (t >= 0.f && t <= rangef) best = fminf(best, t);
+    }
+    xp = xc;
+    yp = yc;
+  }
+  return best;
+}
+
+// everything after the culling stage for ONE env, by one warp.  sdist[rpad]: range per ray,
+// scl[rpad]: closeness per ray, hitmask[rpad/32]: rays some obstacle shortened.
+template <bool COUNT>
+__device__ __forceinline__ void lidar_env(const LidarArgs& A, WarpSmem& sm, float* __restrict__ sdist,
+                                          float* __restrict__ scl, unsigned* __restrict__ hitmask, const int rpad,
+                                          const int e, const int lane, const double sc, const uint4 spec) {
   const AuvConfig& cfg = A.cfg;
   const AuvBatch& batch = A.batch;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int n = batch.n_envs;
-  const int e = blockIdx.x * AUV_LIDAR_WARPS + wib;
-  if (e >= n) return;
   const int R = cfg.n_sensors;
-  const int rpad = cfg.use_lidar ? ((R + 31) & ~31) : 32;
-  const size_t per_warp = sizeof(WarpSmem) + sizeof(float) * rpad;
-  WarpSmem& sm = *reinterpret_cast<WarpSmem*>(smem_raw + per_warp * wib);
-  float* sdist = reinterpret_cast<float*>(smem_raw + per_warp * wib + sizeof(WarpSmem));
   const float rangef = (float)cfg.sensor_range;
   const float widthf = (float)cfg.vessel_width;
   float* obs = A.out.obs + (long long)e * A.obs_dim;
   const bool pooling = A.out.sector_min_dist != nullptr || A.out.sector_feasible_dist != nullptr;
   const uint4* grec4 = reinterpret_cast<const uint4*>(reinterpret_cast<const ObstRec*>(batch.rec) +
                                                       (long long)e * batch.rec_cap);
-
-  // ---- one round trip: every per-env scalar is fetched by a different lane, and the first
-  //      RROUND records are fetched speculatively (30 lanes x 16 B) before their count is known
-  double sc = 0.0;
-  if (lane < AUV_NAV_W) sc = batch.nav[(long long)e * AUV_NAV_W + lane];
-  else if (lane < SC_STATE + 6) sc = batch.state[(long long)(lane - SC_STATE) * n + e];
-  else if (lane == SC_CUM) sc = batch.cum_reward[e];
-  else if (lane == SC_CTE) sc = batch.cte_sum[e];
-  else if (lane == SC_MAXPROG) sc = batch.max_progress[e];
-  else if (lane == SC_TSTEP) sc = (double)batch.t_step[e];
-  else if (lane == SC_SCN) sc = (double)batch.scn_id[e];
-  else if (lane == SC_CNT) sc = cfg.use_lidar ? (double)batch.rec_cnt[e] : 0.0;
-  uint4 spec = make_uint4(0, 0, 0, 0);
-  if (cfg.use_lidar && lane < RROUND * 5 && lane / 5 < batch.rec_cap) spec = grec4[lane];
 #define SCAL(k) __shfl_sync(AUV_FULL, sc, (k))
 
   bool collision = false;
-  float pen = 0.f;
+  float pen = (float)A.rays.weight_sum * A.pen_clear_ray;  // every ray clear; hit rays add their excess below
   unsigned long long ntests = 0;
   if (cfg.use_lidar) {
     const int cnt = (int)SCAL(SC_CNT);
+    bool any_hit = false;
     if (cnt > 0) {
       const double px = SCAL(SC_STATE), py = SCAL(SC_STATE + 1), psi = SCAL(SC_STATE + 2);
       const double cpsi = SCAL(NAV_COSPSI), spsi = SCAL(NAV_SINPSI);
       const double dth_d = 2.0 * AUV_PI / (double)R;
       const double2* __restrict__ unit = reinterpret_cast<const double2*>(A.rays.unit64);
       uint4* srec4 = reinterpret_cast<uint4*>(sm.rec);
+      // ---- every ray starts at sensor_range with closeness 0 (vector stores)
+      __syncwarp();
+      for (int k = lane; k < rpad / 4; k += 32) {
+        reinterpret_cast<float4*>(sdist)[k] = make_float4(rangef, rangef, rangef, rangef);
+        reinterpret_cast<float4*>(scl)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (lane < rpad / 32) hitmask[lane] = 0u;
       for (int r0 = 0; r0 < cnt;) {
         // ---- round: up to RROUND records, bounded by the vertex budget
         __syncwarp();
@@ -407,8 +484,30 @@ __global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32) k_lidar(const __grid_con
         const unsigned fm = __ballot_sync(AUV_FULL, nvv > 0 && incl <= VMAX);
         const int take = max(1, fm == AUV_FULL ? 32 : __ffs(~fm) - 1);  // a prefix: incl is monotone
         if (lane < take) sm.voff[lane] = incl - nvv;
-        __syncwarp();
         const int nr = take;
+        // ---- candidate rays of each record (sensor.py:93-95): i in I1 = [a,b) or i-R in [a,b),
+        //      i.e. I2 = [a+R, b+R), both clipped to [0,R).  An obstacle whose window is wider
+        //      than R is listed -- and tested -- twice upstream: the min does not care, so the
+        //      part of I2 that repeats I1 is dropped here (and counted in COUNT mode below).
+        int n1 = 0, n2 = 0, lo1 = 0, lo2 = 0;
+        if (lane < nr) {
+          const ObstRec& q = sm.rec[lane];
+          if (q.flags & OFLAG_ALLRAYS) {
+            n1 = R;
+          } else {
+            lo1 = max(q.a, 0);
+            const int hi1 = min(q.b, R);
+            n1 = max(0, hi1 - lo1);
+            lo2 = max(q.a + R, 0);
+            if (n1 > 0) lo2 = max(lo2, hi1);
+            n2 = max(0, min(q.b + R, R) - lo2);
+          }
+        }
+        const int tot = n1 + n2;
+        const int cincl = warp_incl_scan(tot, lane);
+        if (lane < nr) sm.cand[lane] = make_int4(cincl - tot, lo1, n1, lo2);
+        const int T = __shfl_sync(AUV_FULL, cincl, nr - 1);
+        __syncwarp();
         // ---- stage vertices: vessel-relative, formed in FP64, stored FP32
         for (int rr = 0; rr < nr; ++rr) {
           const ObstRec& q = sm.rec[rr];
@@ -426,120 +525,86 @@ __global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32) k_lidar(const __grid_con
               sm.verts[off + lane] = make_float2((float)vx, (float)vy);
             }
           } else {
-            const int ne = nq - 1, stride = 64 / ne;
+            const int ne = nq - 1, sh = 6 - (31 - __clz(ne));  // stride 64 / ne, ne a power of two
             for (int k = lane; k < nq; k += 32) {
-              const double2 un = __ldg(&unit[(k == ne ? 0 : k) * stride]);
+              const double2 un = __ldg(&unit[(k == ne ? 0 : k) << sh]);
               sm.verts[off + k] = make_float2((float)(q.cx + q.geo * un.x), (float)(q.cy + q.geo * un.y));
             }
           }
         }
+        if (COUNT) {  // reference-semantics ray/segment tests of this round (bench / parity only)
+          for (int i = lane; i < R; i += 32)
+            for (int rr = 0; rr < nr; ++rr) {
+              const ObstRec& q = sm.rec[rr];
+              const int hits = ((q.a <= i && i < q.b) ? 1 : 0) + ((q.a <= i - R && i - R < q.b) ? 1 : 0);
+              if ((q.flags & OFLAG_ALLRAYS) || hits > 0) ntests += (unsigned)((q.nv - 1) * max(hits, 1));
+            }
+        }
         __syncwarp();
-        // ---- cast: lanes over rays
-        for (int i = lane; i < R; i += 32) {
+        // ---- cast: lanes over the flat list of (record, candidate ray) pairs of this round
+        for (int t = lane; t < T; t += 32) {
+          int rr = 0;
+#pragma unroll
+          for (int k = 1; k < RROUND; ++k)
+            if (k < nr && t >= sm.cand[k].x) rr = k;
+          const int4 cd = sm.cand[rr];
+          const int u = t - cd.x;
+          const int i = u < cd.z ? cd.y + u : cd.w + (u - cd.z);
+          // ray direction in the world frame, formed in FP64 (vessel.py:317)
           const double2 cs = reinterpret_cast<const double2*>(A.rays.cos_sin)[i];
-          const float c = (float)(cs.x * cpsi - cs.y * spsi);
-          const float s = (float)(cs.y * cpsi + cs.x * spsi);
+          const float c = (float)(cs.x * cpsi - cs.y * spsi), sn = (float)(cs.y * cpsi + cs.x * spsi);
           const float theta = (float)((-AUV_PI + (double)(i + 1) * dth_d) + psi);  // world angle of ray i
-          float best = r0 == 0 ? rangef : sdist[i];
-          for (int rr = 0; rr < nr; ++rr) {
-            const ObstRec& q = sm.rec[rr];
-            const int oa = q.a, ob = q.b, fl = q.flags;
-            // candidate(i) <=> a<=i<b or a<=i-R<b (Python negative-index wrap, sensor.py:93-95);
-            // an obstacle whose window is wider than R is listed -- and tested -- twice upstream
-            const int hits = ((oa <= i && i < ob) ? 1 : 0) + ((oa <= i - R && i - R < ob) ? 1 : 0);
-            if (!((fl & OFLAG_ALLRAYS) || hits > 0)) continue;
-            const int nq = q.nv;
-            ntests += (unsigned)((nq - 1) * max(hits, 1));
-            if (fl & OFLAG_INSIDE) {
-              best = 0.f;
-              continue;
-            }
-            const float rho = q.rho;
-            const float tc = q.ecx * c + q.ecy * s;
-            const float hc = q.ecy * c - q.ecx * s;
-            const float slack = rho * 1e-5f + 1e-4f;
-            if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > best) continue;
-            const float2* vp = sm.verts + sm.voff[rr];
-            if (!(fl & (OFLAG_PENTAGON | OFLAG_WORLD)) && nq > 16) {
-              // Regular n-gon inscribed in the enclosing circle (n = 16/32/64): the ray's line
-              // meets the circle at polar angles theta+g and theta+pi-g (g = asin(-hc/r));
-              // between circle and polygon lies the circular segment of exactly one edge, so the
-              // polygon crossing is on the edge whose angular span contains that angle.  The
-              // neighbour on the nearer side is tested too (FP32 error of asinf near grazing).
-              const int nn = nq - 1;
-              const float g = asinf(fminf(fmaxf(-hc / rho, -1.f), 1.f));
-              const float invd = (float)nn * 0.15915494309189535f;
-#pragma unroll
-              for (int sol = 0; sol < 2; ++sol) {
-                const float p = (sol == 0 ? theta + g : theta + 3.14159265358979f - g) * invd;
-                const float kf = floorf(p);
-                const int k0 = (int)kf & (nn - 1);
-                const int k1 = (p - kf < 0.5f ? k0 - 1 : k0 + 1) & (nn - 1);
-#pragma unroll
-                for (int w = 0; w < 2; ++w) {
-                  const int k = w == 0 ? k0 : k1;
-                  const float2 va = vp[k], vb = vp[k + 1];
-                  const float ya = va.y * c - va.x * s, yb = vb.y * c - vb.x * s;
-                  if ((ya <= 0.f && yb >= 0.f) || (ya >= 0.f && yb <= 0.f)) {
-                    const float xa = va.x * c + va.y * s, xb = vb.x * c + vb.y * s;
-                    const float t = xa + (xb - xa) * (ya / (ya - yb));
-                    if (t >= 0.f && t <= rangef) best = fminf(best, t);
-                  }
-                }
-              }
-              continue;
-            }
-            float2 v = vp[0];
-            float xp = v.x * c + v.y * s;
-            float yp = v.y * c - v.x * s;
-            for (int k = 1; k < nq; ++k) {
-              v = vp[k];
-              const float xc = v.x * c + v.y * s;
-              const float yc = v.y * c - v.x * s;
-              if ((yp <= 0.f && yc >= 0.f) || (yp >= 0.f && yc <= 0.f)) {
-                const float t = xp + (xc - xp) * (yp / (yp - yc));
-                if (t >= 0.f && t <= rangef) best = fminf(best, t);
-              }
-              xp = xc;
-              yp = yc;
-            }
+          const float cur = sdist[i];
+          const float got = cast_ray_record(sm.rec[rr], sm.verts + sm.voff[rr], c, sn, theta, cur, rangef);
+          if (got < cur) {  // readings are >= 0: their bit patterns order like the values
+            atomicMin(reinterpret_cast<int*>(sdist) + i, __float_as_int(got));
+            atomicOr(hitmask + (i >> 5), 1u << (i & 31));
           }
-          sdist[i] = best;
         }
         r0 += nr;
       }
       __syncwarp();
-      // ---- closeness / collision / penalty  (vessel.py:88-95,356-359; rewarder.py:199-214)
-      const float inv_log = 1.f / log1pf(rangef);
-      for (int i = lane; i < R; i += 32) {
-        const float d = sdist[i];
-        const float w = A.rays.weight[i];
-        float cl;
-        if (d >= rangef) {
-          cl = 0.f;  // 1 - log(1+range)/log(1+range) is exactly 0 upstream
-          pen += w * A.pen_clear_ray;
-        } else {
+      // ---- closeness / collision / penalty of the rays that were shortened
+      //      (vessel.py:88-95,356-359; rewarder.py:199-214)
+      float extra = 0.f;
+      for (int w = 0; w < rpad / 32; ++w) {
+        const unsigned m = hitmask[w];  // warp-uniform
+        if (m == 0u) continue;
+        any_hit = true;
+        if ((m >> lane) & 1u) {
+          const int i = w * 32 + lane;
+          const float d = sdist[i];
+          float cl;
           if (cfg.sensor_log_transform)
-            cl = 1.f - fminf(fmaxf(log1pf(d) * inv_log, 0.f), 1.f);
+            cl = 1.f - fminf(fmaxf(log1pf(d) * A.inv_log_range, 0.f), 1.f);
           else
             cl = 1.f - fminf(fmaxf(d / rangef, 0.f), 1.f);
-          pen += w * rangef * __expf(-0.1f * d);
+          scl[i] = fminf(fmaxf(cl, -1.f), 1.f);
+          extra += A.rays.weight[i] * (rangef * __expf(-0.1f * d) - A.pen_clear_ray);
+          collision = collision || (d < widthf);
         }
-        obs[6 + i] = fminf(fmaxf(cl, -1.f), 1.f);
-        if (A.out.lidar_dist != nullptr) A.out.lidar_dist[(long long)e * R + i] = d;
-        collision = collision || (d < widthf);
       }
-      collision = __any_sync(AUV_FULL, collision);
-      pen = warp_sum(pen);
-    } else {
-      // vessel.py:275-305: no nearby obstacles => every range = sensor_range, closeness 0
-      for (int i = lane; i < R; i += 32) {
-        obs[6 + i] = 0.f;
-        if (A.out.lidar_dist != nullptr) A.out.lidar_dist[(long long)e * R + i] = rangef;
-        if (pooling) sdist[i] = rangef;
+      if (any_hit) {
+        collision = __any_sync(AUV_FULL, collision);
+        pen += warp_sum(extra);
+        __syncwarp();
       }
-      pen = (float)A.rays.weight_sum * A.pen_clear_ray;
     }
+    // ---- closeness part of the observation: zeros (vessel.py:275-305) unless some ray was hit
+    if ((A.obs_dim & 1) == 0) {  // rows and obs + 6 are 8-byte aligned
+      float2* o2 = reinterpret_cast<float2*>(obs + 6);
+      if (any_hit) {
+        for (int k = lane; k < R / 2; k += 32) o2[k] = reinterpret_cast<const float2*>(scl)[k];
+        if ((R & 1) && lane == 0) obs[6 + R - 1] = scl[R - 1];
+      } else {
+        for (int k = lane; k < R / 2; k += 32) o2[k] = make_float2(0.f, 0.f);
+        if ((R & 1) && lane == 0) obs[6 + R - 1] = 0.f;
+      }
+    } else {
+      for (int i = lane; i < R; i += 32) obs[6 + i] = any_hit ? scl[i] : 0.f;
+    }
+    if (A.out.lidar_dist != nullptr)
+      for (int i = lane; i < R; i += 32) A.out.lidar_dist[(long long)e * R + i] = cnt > 0 ? sdist[i] : rangef;
     if (cfg.sensor_use_velocity_observations)  // sensor.py:159: the speed channel is (0,0) at HEAD
       for (int k = lane; k < 2 * R; k += 32) obs[6 + R + k] = 0.f;
 
@@ -547,6 +612,8 @@ __global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32) k_lidar(const __grid_con
     if (pooling) {
       const int ns = cfg.n_sectors;
       __syncwarp();
+      if (cnt == 0)
+        for (int i = lane; i < R; i += 32) sdist[i] = rangef;
       float* ssec = reinterpret_cast<float*>(sm.verts);  // vertex staging is free again
       ssec[lane] = rangef;
       __syncwarp();
@@ -580,23 +647,13 @@ __global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32) k_lidar(const __grid_con
       __syncwarp();
     }
   }
-  if (A.out.seg_tests != nullptr) {
+  if (COUNT) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ntests += __shfl_xor_sync(AUV_FULL, ntests, o);
     if (lane == 0 && ntests) atomicAdd(A.out.seg_tests, ntests);
   }
 
-  // ---- navigation part of the observation (vessel.py:518-539): u, v, r, look-ahead heading
-  //      error, heading error, cross-track / 100
-  {
-    const double uvr = SCAL((SC_STATE + 3 + lane) & 31);
-    const double la = SCAL(NAV_LA_ERR), he = SCAL(NAV_HEAD_ERR), ye = SCAL(NAV_YE);
-    double val = uvr;
-    if (lane == 3) val = la;
-    if (lane == 4) val = he;
-    if (lane == 5) val = ye / 100.0;
-    if (lane < 6) obs[lane] = (float)fmin(fmax(val, -1.0), 1.0);
-  }
+  // the navigation part of the observation (obs[0..5]) was written by k_vessel_nav
   const double progress = SCAL(NAV_PROGRESS), goal_dist = SCAL(NAV_GOAL);
   const bool reached = SCAL(NAV_REACHED) != 0.0;
   if (A.mode == AUV_OBSERVE_RESET) {  // explicit reset observe: info mirrors a fresh env
@@ -609,31 +666,18 @@ __global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32) k_lidar(const __grid_con
     return;
   }
 
-  // ---- reward (rewarder.py) + done (environment.py:375-384) + counters (uniform across lanes)
-  const double vu = SCAL(SC_STATE + 3), vv = SCAL(SC_STATE + 4), vr = SCAL(SC_STATE + 5);
-  const double y_e = SCAL(NAV_YE);
-  const double maxprog = SCAL(SC_MAXPROG);  // already includes this step (navigate_thread)
-  const double speed = sqrt(vu * vu + vv * vv);
-  double reward;
+  // ---- reward (rewarder.py) + done (environment.py:375-384) + counters (uniform across lanes):
+  //      k_vessel_nav computed everything that does not depend on the LiDAR
+  double reward = SCAL(NAV_REWARD_BASE);
   if (collision) {
     reward = -10000.0 * (1.0 - 0.5);
-  } else {
-    const double cte = y_e / 100.0;
-    double path_reward =
-        (1.0 + SCAL(NAV_COS_HEAD_ERR) * speed / 2.0) * (1.0 + (double)__expf((float)(-5.0 * fabs(cte)))) - 1.0;
-    const double living = 0.5 * (2.0 * 0.05 + 1.0);
-    if (cfg.rewarder == AUV_REWARDER_COLAV) {
-      // without LiDAR every ray keeps its reset value sensor_range (vessel.py:206-208)
-      const double closeness_reward = cfg.use_lidar ? -(double)pen / A.rays.weight_sum : A.clear_closeness;
-      if (progress < maxprog) path_reward = fmin(path_reward, 0.0);
-      const double slow = speed < 0.04 ? -2.0 : 0.0;
-      reward = 0.5 * path_reward + 0.5 * closeness_reward - living - 10.0 * fabs(vr) + slow;
-      if (reward < 0.0) reward *= 2.0;
-    } else {
-      const double slow = speed < 0.1 ? -2.0 : 0.0;
-      reward = path_reward - living - 10.0 * fabs(vr) + slow;
-    }
+  } else if (cfg.rewarder == AUV_REWARDER_COLAV) {
+    // without LiDAR every ray keeps its reset value sensor_range (vessel.py:206-208)
+    const double closeness_reward = cfg.use_lidar ? -(double)pen * A.inv_weight_sum : A.clear_closeness;
+    reward += 0.5 * closeness_reward;
+    if (reward < 0.0) reward *= 2.0;
   }
+  const double y_e = SCAL(NAV_YE);
   const double cum = SCAL(SC_CUM) + reward;
   const int t_step = (int)SCAL(SC_TSTEP);
   const bool done = collision || reached || (!cfg.test_mode && t_step >= cfg.max_timesteps - 1) ||
@@ -709,6 +753,40 @@ __global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32) k_lidar(const __grid_con
         batch.nearby_mask[(long long)e * batch.mask_words + w] = A.pool.reset_mask[(long long)next * batch.mask_words + w];
   }
 #undef SCAL
+}
+
+// shared memory of one warp: staging + range[rpad] + closeness[rpad] + hit bits (rpad/8 bytes,
+// padded to rpad so every warp's block stays 16-byte aligned)
+__host__ __device__ constexpr size_t lidar_smem_per_warp(int rpad) {
+  return sizeof(WarpSmem) + 2 * sizeof(float) * rpad + rpad;
+}
+
+#ifndef AUV_LIDAR_MINB
+#define AUV_LIDAR_MINB 16  // min resident CTAs per SM asked of the compiler: 64 registers (108 uncapped: 0.177 ms, 80: 0.152, 64: 0.142)
+#endif
+template <bool COUNT>
+__global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32, AUV_LIDAR_MINB) k_lidar(const __grid_constant__ LidarArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int R = A.cfg.n_sensors;
+  const int rpad = A.cfg.use_lidar ? ((R + 31) & ~31) : 32;
+  const size_t per_warp = lidar_smem_per_warp(rpad);
+  WarpSmem& sm = *reinterpret_cast<WarpSmem*>(smem_raw + per_warp * wib);
+  float* sdist = reinterpret_cast<float*>(smem_raw + per_warp * wib + sizeof(WarpSmem));
+  float* scl = sdist + rpad;
+  unsigned* hitmask = reinterpret_cast<unsigned*>(scl + rpad);
+  int e = A.e0 + (blockIdx.x * AUV_LIDAR_WARPS + wib) * AUV_LIDAR_EPW;
+  if (e >= A.e1) return;
+  const int eend = min(e + AUV_LIDAR_EPW, A.e1);
+  double sc, scn;
+  uint4 spec, specn;
+  lidar_fetch(A.cfg, A.batch, e, lane, sc, spec);
+  for (; e < eend; ++e) {
+    if (e + 1 < eend) lidar_fetch(A.cfg, A.batch, e + 1, lane, scn, specn);  // in flight while env e is cast
+    lidar_env<COUNT>(A, sm, sdist, scl, hitmask, rpad, e, lane, sc, spec);
+    sc = scn;
+    spec = specn;
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -790,17 +868,22 @@ static int check_cfg(const AuvConfig* cfg) {
   return 0;
 }
 
+static int launch_obstacle_update(const AuvConfig* cfg, const AuvScenarioPool* pool, const AuvBatch* batch,
+                                  int e0, int cnt, void* stream) {
+  const long long total = (long long)cnt * pool->k_moving;
+  if (total == 0) return 0;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  auv::k_obstacle_update<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *pool, *batch, e0, cnt);
+  return cuda_check(cudaGetLastError(), "k_obstacle_update");
+}
+
 int auv_obstacle_update(const AuvConfig* cfg, const AuvScenarioPool* pool, AuvBatch* batch,
                         void* stream) {
   if (int rc = check_cfg(cfg)) return rc;
   if (!pool || !batch) return set_err(AUV_EINVAL, "pool/batch is NULL");
   if (batch->n_envs <= 0) return set_err(AUV_EINVAL, "n_envs must be > 0");
-  const long long total = (long long)batch->n_envs * pool->k_moving;
-  if (total == 0) return 0;
-  const int threads = 256;
-  const long long blocks = (total + threads - 1) / threads;
-  auv::k_obstacle_update<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *pool, *batch);
-  return cuda_check(cudaGetLastError(), "k_obstacle_update");
+  return launch_obstacle_update(cfg, pool, batch, 0, batch->n_envs, stream);
 }
 
 int auv_vessel_step(const AuvConfig* cfg, AuvBatch* batch, const float* actions, void* stream) {
@@ -855,21 +938,25 @@ static int check_observe_args(const AuvConfig* cfg, const AuvRayTable* rays, con
 
 static int launch_vessel_nav(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                              const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out,
-                             const float* actions, void* stream) {
+                             const float* actions, void* stream, int e0 = 0, int cnt = -1) {
+  if (cnt < 0) cnt = batch->n_envs - e0;
   const int threads = 64;  // small CTAs: 65536 envs are only ~7 CTAs per SM, balance matters
-  const int blocks = (batch->n_envs + threads - 1) / threads;
+  const int blocks = (cnt + threads - 1) / threads;
   const double2* unit = rays ? reinterpret_cast<const double2*>(rays->unit64) : nullptr;
   int* win = out ? out->windows : nullptr;
+  float* obs = out ? out->obs : nullptr;
+  const int od = auv_obs_dim(cfg);
   if (actions)
-    auv::k_vessel_nav<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, unit, win, actions);
+    auv::k_vessel_nav<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, unit, win, actions, obs, od, e0, e0 + cnt);
   else
-    auv::k_vessel_nav<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, unit, win, nullptr);
+    auv::k_vessel_nav<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, unit, win, nullptr, obs, od, e0, e0 + cnt);
   return cuda_check(cudaGetLastError(), "k_vessel_nav");
 }
 
 static int launch_lidar(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                         const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode,
-                        void* stream) {
+                        void* stream, int e0 = 0, int cnt = -1) {
+  if (cnt < 0) cnt = batch->n_envs - e0;
   auv::LidarArgs args;
   args.cfg = *cfg;
   if (rays) args.rays = *rays; else memset(&args.rays, 0, sizeof(args.rays));
@@ -879,20 +966,31 @@ static int launch_lidar(const AuvConfig* cfg, const AuvRayTable* rays, const Auv
   args.out = *out;
   args.mode = mode;
   args.obs_dim = auv_obs_dim(cfg);
+  args.e0 = e0;
+  args.e1 = e0 + cnt;
   args.clear_closeness = -cfg->sensor_range * exp(-0.1 * cfg->sensor_range);
   args.pen_clear_ray = (float)(-args.clear_closeness);
+  args.inv_log_range = (float)(1.0 / log1p(cfg->sensor_range));
+  args.inv_weight_sum = (rays && rays->weight_sum > 0.0) ? 1.0 / rays->weight_sum : 0.0;
   args.feas_width = cfg->vessel_width * cfg->feasibility_width_multiplier;
   const int rpad = cfg->use_lidar ? ((cfg->n_sensors + 31) & ~31) : 32;
-  const size_t smem = (sizeof(auv::WarpSmem) + sizeof(float) * rpad) * AUV_LIDAR_WARPS;
+  const size_t smem = auv::lidar_smem_per_warp(rpad) * AUV_LIDAR_WARPS;
   static size_t configured = 0;
   if (smem > configured) {
-    if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_lidar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_lidar<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(k_lidar)"))
+      return rc;
+    if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_lidar<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(k_lidar)"))
       return rc;
     configured = smem;
   }
-  const int blocks = (batch->n_envs + AUV_LIDAR_WARPS - 1) / AUV_LIDAR_WARPS;
-  auv::k_lidar<<<blocks, AUV_LIDAR_WARPS * 32, smem, (cudaStream_t)stream>>>(args);
+  const int per_cta = AUV_LIDAR_WARPS * AUV_LIDAR_EPW;
+  const int blocks = (cnt + per_cta - 1) / per_cta;
+  if (out->seg_tests != nullptr)
+    auv::k_lidar<true><<<blocks, AUV_LIDAR_WARPS * 32, smem, (cudaStream_t)stream>>>(args);
+  else
+    auv::k_lidar<false><<<blocks, AUV_LIDAR_WARPS * 32, smem, (cudaStream_t)stream>>>(args);
   return cuda_check(cudaGetLastError(), "k_lidar");
 }
 
@@ -918,9 +1016,128 @@ int auv_step(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* p
              void* stream) {
   if (!actions) return set_err(AUV_EINVAL, "actions is NULL");
   if (int rc = check_observe_args(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP)) return rc;
-  if (int rc = auv_obstacle_update(cfg, pool, batch, stream)) return rc;
+  if (int rc = launch_obstacle_update(cfg, pool, batch, 0, batch->n_envs, stream)) return rc;
   if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, actions, stream)) return rc;
   return launch_lidar(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, stream);
+}
+
+// ---- chunked step: the batch is cut into env ranges, each range runs its three kernels (and,
+// for the host-buffer variant, its copies) on its own stream.  The thread-per-env culling kernel
+// is latency-bound at low occupancy and the warp-per-env casting kernel is issue-bound, so ranges
+// in different stages fill each other's idle issue slots; with host buffers the D2H of range c
+// overlaps the kernels of range c+1.  Envs are independent: no ordering is needed between ranges.
+#define AUV_PIPE_MAX_STREAMS 16
+struct AuvPipeline {
+  int n_streams;
+  cudaStream_t st[AUV_PIPE_MAX_STREAMS];
+  cudaEvent_t fork, join[AUV_PIPE_MAX_STREAMS];
+};
+
+AuvPipeline* auv_pipeline_create(int n_streams) {
+  if (n_streams <= 0 || n_streams > AUV_PIPE_MAX_STREAMS) {
+    set_err(AUV_EINVAL, "n_streams out of range");
+    return nullptr;
+  }
+  AuvPipeline* p = new AuvPipeline;
+  p->n_streams = n_streams;
+  bool ok = cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) == cudaSuccess;
+  int made = 0;
+  for (; ok && made < n_streams; ++made) {
+    ok = cudaStreamCreateWithFlags(&p->st[made], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&p->join[made], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
+    cuda_check(cudaGetLastError(), "auv_pipeline_create");
+    delete p;  // leaks the few objects created before the failure; the context is unusable anyway
+    return nullptr;
+  }
+  return p;
+}
+void auv_pipeline_destroy(AuvPipeline* p) {
+  if (!p) return;
+  for (int i = 0; i < p->n_streams; ++i) {
+    cudaStreamDestroy(p->st[i]);
+    cudaEventDestroy(p->join[i]);
+  }
+  cudaEventDestroy(p->fork);
+  delete p;
+}
+
+static int chunk_size(int n, int n_chunks) {
+  int c = (n + n_chunks - 1) / n_chunks;
+  return (c + 63) / 64 * 64;  // whole CTAs of every kernel
+}
+
+// host == true: actions_in / obs_host / reward_host / done_host are HOST pointers (pinned)
+static int step_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                        const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_in,
+                        float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
+                        uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks, bool host) {
+  if (!p) return set_err(AUV_EINVAL, "pipeline is NULL");
+  if (n_chunks <= 0) return set_err(AUV_EINVAL, "n_chunks must be > 0");
+  if (int rc = check_observe_args(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = batch->n_envs;
+  const int cs = chunk_size(n, n_chunks);
+  const size_t od = (size_t)auv_obs_dim(cfg);
+  if (int rc = cuda_check(cudaEventRecord(p->fork, s), "fork")) return rc;
+  int used = 0;
+  for (int c = 0, e0 = 0; e0 < n; ++c, e0 += cs) {
+    const int cnt = n - e0 < cs ? n - e0 : cs;
+    const int si = c % p->n_streams;
+    cudaStream_t cst = p->st[si];
+    void* vs = (void*)cst;
+    if (c < p->n_streams) {
+      if (int rc = cuda_check(cudaStreamWaitEvent(cst, p->fork, 0), "wait fork")) return rc;
+      used = c + 1;
+    }
+    const float* act = actions_in;
+    if (host) {
+      if (int rc = cuda_check(cudaMemcpyAsync(actions_dev + 2ll * e0, actions_in + 2ll * e0, (size_t)cnt * 2 * sizeof(float),
+                                              cudaMemcpyHostToDevice, cst), "H2D actions"))
+        return rc;
+      act = actions_dev;
+    }
+    if (int rc = launch_obstacle_update(cfg, pool, batch, e0, cnt, vs)) return rc;
+    if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, act, vs, e0, cnt)) return rc;
+    if (int rc = launch_lidar(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, vs, e0, cnt)) return rc;
+    if (host) {
+      if (int rc = cuda_check(cudaMemcpyAsync(obs_host + od * e0, out->obs + od * e0, (size_t)cnt * od * sizeof(float),
+                                              cudaMemcpyDeviceToHost, cst), "D2H obs"))
+        return rc;
+      if (int rc = cuda_check(cudaMemcpyAsync(reward_host + e0, out->reward + e0, (size_t)cnt * sizeof(float),
+                                              cudaMemcpyDeviceToHost, cst), "D2H reward"))
+        return rc;
+      if (int rc = cuda_check(cudaMemcpyAsync(done_host + e0, out->done + e0, (size_t)cnt, cudaMemcpyDeviceToHost, cst),
+                              "D2H done"))
+        return rc;
+    }
+  }
+  for (int i = 0; i < used; ++i) {
+    if (int rc = cuda_check(cudaEventRecord(p->join[i], p->st[i]), "join record")) return rc;
+    if (int rc = cuda_check(cudaStreamWaitEvent(s, p->join[i], 0), "join wait")) return rc;
+  }
+  return 0;
+}
+
+int auv_step_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                     const AuvScenarioPool* pool, AuvBatch* batch, const float* actions, AuvStepOut* out,
+                     void* stream, AuvPipeline* p, int n_chunks) {
+  if (!actions) return set_err(AUV_EINVAL, "actions is NULL");
+  return step_chunked(cfg, rays, paths, pool, batch, actions, nullptr, out, nullptr, nullptr, nullptr, stream, p,
+                      n_chunks, false);
+}
+
+int auv_step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                          const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
+                          float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
+                          uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks) {
+  if (!cfg || !batch || !out || !actions_host || !actions_dev || !obs_host || !reward_host || !done_host)
+    return set_err(AUV_EINVAL, "NULL argument");
+  if (int rc = step_chunked(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, obs_host, reward_host,
+                            done_host, stream, p, n_chunks, true))
+    return rc;
+  return cuda_check(cudaStreamSynchronize((cudaStream_t)stream), "sync");
 }
 
 #define AUV_TIMER_EVENTS 4
@@ -958,7 +1175,7 @@ int auv_step_timed(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathB
   cudaStream_t s = (cudaStream_t)stream;
   cudaEvent_t* e = t->ev + AUV_TIMER_EVENTS * slot;
   cudaEventRecord(e[0], s);
-  if (int rc = auv_obstacle_update(cfg, pool, batch, stream)) return rc;
+  if (int rc = launch_obstacle_update(cfg, pool, batch, 0, batch->n_envs, stream)) return rc;
   cudaEventRecord(e[1], s);
   if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, actions, stream)) return rc;
   cudaEventRecord(e[2], s);

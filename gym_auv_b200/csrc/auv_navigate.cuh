@@ -24,6 +24,7 @@ namespace auv {
 #define NAV_SINPSI 9
 #define NAV_REACHED 10
 #define NAV_COS_HEAD_ERR 11
+#define NAV_REWARD_BASE 12
 
 // scipy PPoly evaluation (extrapolate=True): interval j with x[j] <= s < x[j+1], clamped.
 __device__ __forceinline__ void pchip_eval(const AuvPathBank& pb, int pid, double s, double& px,
@@ -187,10 +188,13 @@ __device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid,
   return start + seglen;
 }
 
-// Vessel.navigate (vessel.py:461-541) for env e; writes nav[e][:] and max_progress[e].
+// Vessel.navigate (vessel.py:461-541) for env e; writes nav[e][:] and max_progress[e], the
+// navigation part of the observation (vessel.py:518-539, clipped: environment.py:276-280) and
+// the LiDAR-independent part of the reward (rewarder.py:78-140,167-241).
 __device__ __forceinline__ void navigate_thread(const AuvConfig& cfg, const AuvPathBank& pb,
                                                 const AuvBatch& batch, int pid, int e, double px,
-                                                double py, double psi) {
+                                                double py, double psi, double vu, double vv, double vr,
+                                                float* __restrict__ obs_row) {
   const double s = project_thread(pb, pid, px, py);
   const double L = pb.length[pid];
   const double s_la = fmin(L, s + cfg.look_ahead_distance);
@@ -224,8 +228,34 @@ __device__ __forceinline__ void navigate_thread(const AuvConfig& cfg, const AuvP
   o[NAV_COSPSI] = cp;
   o[NAV_SINPSI] = sp;
   o[NAV_REACHED] = reached ? 1.0 : 0.0;
-  o[NAV_COS_HEAD_ERR] = (double)cosf((float)head_err);
-  batch.max_progress[e] = fmax(progress, batch.max_progress[e]);  // vessel.py:507
+  const double cos_he = (double)cosf((float)head_err);
+  o[NAV_COS_HEAD_ERR] = cos_he;
+  const double maxprog = fmax(progress, batch.max_progress[e]);  // vessel.py:507
+  batch.max_progress[e] = maxprog;
+  // ---- reward without the closeness term.  Colav (rewarder.py:216-239):
+  //   r = 0.5 path + 0.5 closeness - living - 10|r| + slow, x2 if negative (k_lidar adds closeness);
+  // PathFollow (rewarder.py:118-140): r = path - living - 10|r| + slow.
+  const double cte = y_e * 0.01;  // y_e / 100 to within 1 ulp; feeds a float32 observation and exp()
+  const double speed2 = vu * vu + vv * vv;
+  const double speed = sqrt(speed2);
+  double path_reward = (1.0 + cos_he * speed * 0.5) * (1.0 + (double)__expf((float)(-5.0 * fabs(cte)))) - 1.0;
+  const double living = 0.5 * (2.0 * 0.05 + 1.0);
+  double base;
+  if (cfg.rewarder == AUV_REWARDER_COLAV) {
+    if (progress < maxprog) path_reward = fmin(path_reward, 0.0);
+    base = 0.5 * path_reward - living - 10.0 * fabs(vr) + (speed2 < 0.04 * 0.04 ? -2.0 : 0.0);
+  } else {
+    base = path_reward - living - 10.0 * fabs(vr) + (speed2 < 0.1 * 0.1 ? -2.0 : 0.0);
+  }
+  o[NAV_REWARD_BASE] = base;
+  if (obs_row != nullptr) {  // [u, v, r, look-ahead heading error, heading error, cross-track / 100]
+    obs_row[0] = (float)fmin(fmax(vu, -1.0), 1.0);
+    obs_row[1] = (float)fmin(fmax(vv, -1.0), 1.0);
+    obs_row[2] = (float)fmin(fmax(vr, -1.0), 1.0);
+    obs_row[3] = (float)fmin(fmax(la_err, -1.0), 1.0);
+    obs_row[4] = (float)fmin(fmax(head_err, -1.0), 1.0);
+    obs_row[5] = (float)fmin(fmax(cte, -1.0), 1.0);
+  }
 }
 
 }  // namespace auv

@@ -95,6 +95,9 @@ class AUVVecEnv:
     debug     : also record per-ray distances, culling windows and FP64 navigation values
     sector_outputs : also produce per-sector min-pooled and feasibility-pooled ranges
                      (get_attr("sector_min_dist") / get_attr("sector_feasible_dist"))
+    chunks    : > 1 cuts the batch into that many env ranges which run their kernels (and
+                for step_host their H2D/D2H copies) on ``chunk_streams`` internal streams
+                (auv_step_chunked / auv_step_host_chunked); results are identical
     """
 
     def __init__(
@@ -110,6 +113,8 @@ class AUVVecEnv:
         env_offset: int = 0,
         sector_outputs: bool = False,
         max_nearby: Optional[int] = None,
+        chunks: int = 1,
+        chunk_streams: Optional[int] = None,
         _shared: Optional[dict] = None,
     ):
         self.device = torch.device(device)
@@ -267,6 +272,15 @@ class AUVVecEnv:
         )
         self.actions_dev = z((N, 2), torch.float32)
         self._pinned = None
+        self.chunks = max(1, int(chunks))
+        self._pipe = None
+        if self.chunks > 1:
+            ns = int(chunk_streams) if chunk_streams else min(self.chunks, 4)
+            with torch.cuda.device(self.device):
+                self._pipe = self.lib.auv_pipeline_create(ns)
+            if not self._pipe:
+                raise _lib.AuvLibraryError("auv_pipeline_create failed: " + self.lib.auv_last_error().decode())
+            self.chunk_streams = ns
         self.total_steps = 0
 
         self.action_space = Box(low=np.array([-1, -0.15]), high=np.array([1, 0.15]), dtype=np.float32)
@@ -349,10 +363,17 @@ class AUVVecEnv:
         a = actions.to(device=self.device, dtype=torch.float32).contiguous()
         cfg, rays, paths, pool, batch = self._refs()
         with torch.cuda.device(self.device):
-            _lib.check(
-                self.lib.auv_step(cfg, rays, paths, pool, batch, C.c_void_p(a.data_ptr()), C.byref(self.out), self._stream()),
-                "auv_step",
-            )
+            if self._pipe:
+                _lib.check(
+                    self.lib.auv_step_chunked(cfg, rays, paths, pool, batch, C.c_void_p(a.data_ptr()), C.byref(self.out),
+                                              self._stream(), self._pipe, self.chunks),
+                    "auv_step_chunked",
+                )
+            else:
+                _lib.check(
+                    self.lib.auv_step(cfg, rays, paths, pool, batch, C.c_void_p(a.data_ptr()), C.byref(self.out), self._stream()),
+                    "auv_step",
+                )
         self.total_steps += 1
         return self._out["obs"], self._out["reward"], self._out["done"], self.info()
 
@@ -371,14 +392,13 @@ class AUVVecEnv:
         pin["act"].numpy()[...] = actions
         cfg, rays, paths, pool, batch = self._refs()
         with torch.cuda.device(self.device):
-            _lib.check(
-                self.lib.auv_step_host(
-                    cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
-                    C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.c_void_p(pin["obs"].data_ptr()),
-                    C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()), self._stream(),
-                ),
-                "auv_step_host",
-            )
+            hargs = (cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
+                     C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.c_void_p(pin["obs"].data_ptr()),
+                     C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()), self._stream())
+            if self._pipe:
+                _lib.check(self.lib.auv_step_host_chunked(*hargs, self._pipe, self.chunks), "auv_step_host_chunked")
+            else:
+                _lib.check(self.lib.auv_step_host(*hargs), "auv_step_host")
         self.total_steps += 1
         return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy()
 
@@ -463,4 +483,13 @@ class AUVVecEnv:
         return summarize_stats(st.cpu().numpy(), float(self.config.simulation.t_step_size))
 
     def close(self):
-        pass
+        if self._pipe:
+            torch.cuda.synchronize(self.device)
+            self.lib.auv_pipeline_destroy(self._pipe)
+            self._pipe = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

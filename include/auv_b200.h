@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 10
+#define AUV_ABI_VERSION 12
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -58,7 +58,7 @@ extern "C" {
 #define AUV_MAX_OBSTACLES 1024 /* moving + static slots per env */
 #define AUV_PATH_BLOCK 32     /* polyline segments per projection block */
 #define AUV_PATH_SUPER 32     /* blocks per projection superblock */
-#define AUV_NAV_W 12          /* doubles per env in AuvBatch.nav */
+#define AUV_NAV_W 16          /* doubles per env in AuvBatch.nav (one 128 B line) */
 #define AUV_REC_BYTES 80      /* bytes per obstacle record in AuvBatch.rec */
 #define AUV_MAX_POLY_VERTS 192 /* vertices of one world polygon incl. the closing one */
 #define AUV_STATUS_REC_OVERFLOW 1 /* AuvBatch.status bit: more nearby obstacles than rec_cap */
@@ -182,7 +182,9 @@ typedef struct AuvBatch {
   double* mov_counter;    /* [N][k_moving]                                              */
   double* nav;            /* [N][AUV_NAV_W] Vessel._last_navi_state_dict: s, chi, y_e, s_la,
                              look_ahead_heading_error, heading_error, goal_distance, progress,
-                             cos psi, sin psi, reached_goal, cos(heading_error)            */
+                             cos psi, sin psi, reached_goal, cos(heading_error), [12] the part of
+                             the reward that does not depend on the LiDAR (rewarder.py:216-239
+                             without the closeness term / rewarder.py:118-140), [13..15] unused */
   /* scratch between the culling stage and the ray-casting stage (opaque to the caller) */
   void* rec;              /* [N][rec_cap][AUV_REC_BYTES] obstacle records, 16-byte aligned       */
   int32_t* rec_cnt;       /* [N] records of each env                                            */
@@ -261,6 +263,23 @@ int auv_step_host(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBa
                   const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
                   float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
                   uint8_t* done_host, void* stream);
+/* Chunked step.  Envs are independent (environment.py:292-366 touches one env only), so the
+ * batch can be cut into n_chunks env ranges that run their three kernels -- and, for the
+ * host-buffer variant, their H2D/D2H copies -- on the pipeline's own streams: ranges in
+ * different stages fill each other's idle issue slots and the D2H of one range overlaps the
+ * kernels of the next.  The call forks from `stream` and joins back into it (work submitted to
+ * `stream` afterwards sees the whole step); results are identical to auv_step / auv_step_host.
+ * A pipeline holds n_streams (1..16) non-blocking streams + events, no device memory. */
+typedef struct AuvPipeline AuvPipeline;
+AuvPipeline* auv_pipeline_create(int n_streams);
+void auv_pipeline_destroy(AuvPipeline* p);
+int auv_step_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                     const AuvScenarioPool* pool, AuvBatch* batch, const float* actions,
+                     AuvStepOut* out, void* stream, AuvPipeline* p, int n_chunks);
+int auv_step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                          const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
+                          float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
+                          uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks);
 /* Per-kernel CUDA-event timing of a step on the launching stream (used by bench.py for the
  * roofline of the dominant kernel).  A timer holds `capacity` slots of 4 events. */
 typedef struct AuvTimer AuvTimer;

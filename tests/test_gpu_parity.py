@@ -381,6 +381,62 @@ def test_step_host_equals_step():
     assert e2.h2d_bytes_per_step == 33 * 8 and e2.d2h_bytes_per_step == 33 * (186 * 4 + 5)
 
 
+@pytest.mark.parametrize("chunks,streams", [(2, 2), (3, 2), (5, 4), (8, 1)])
+def test_chunked_step_is_bit_identical(chunks, streams):
+    """auv_step_chunked / auv_step_host_chunked: env ranges on the pipeline's own streams give
+    exactly the results of the single-stream step (envs are independent), including the
+    auto-reset bookkeeping and the episode statistics."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    cfg.episode.max_timesteps = 9  # force auto-resets inside the rollout
+    n = 333  # several ragged 64-env ranges
+    scn = S.moving_obstacles(n, 5, 5, seed=21)
+    e1 = AUVVecEnv(scn, n, cfg, auto_reset=True)
+    e2 = AUVVecEnv(scn, n, cfg, auto_reset=True, chunks=chunks, chunk_streams=streams)
+    e3 = AUVVecEnv(scn, n, cfg, auto_reset=True, chunks=chunks, chunk_streams=streams)
+    e1.reset(), e2.reset(), e3.reset()
+    acts = random_actions(24, n, 4).astype(np.float32)
+    for t in range(24):
+        a = torch.as_tensor(acts[t], device="cuda")
+        o1, r1, d1, i1 = e1.step(a)
+        o2, r2, d2, i2 = e2.step(a)
+        o3, r3, d3 = e3.step_host(acts[t])
+        torch.cuda.synchronize()
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+        for k in i1:
+            assert torch.equal(i1[k], i2[k]), k
+        assert np.array_equal(o1.cpu().numpy(), o3) and np.array_equal(r1.cpu().numpy(), r3)
+        assert np.array_equal(d1.cpu().numpy(), d3)
+    for k in ("state", "mov_pos", "scn_id", "t_step", "cum_reward", "nearby_mask"):
+        assert torch.equal(e1._st[k], e2._st[k]) and torch.equal(e1._st[k], e3._st[k]), k
+    s1, s2 = e1.episode_stats(reduce=False), e2.episode_stats(reduce=False)
+    assert s1["episodes"] == s2["episodes"] > 0
+    assert abs(s1["reward"] - s2["reward"]) <= 1e-9 * abs(s1["reward"])  # atomic order differs
+    e2.close(), e3.close()
+
+
+def test_counting_variant_equals_product_variant():
+    """debug=True launches k_lidar<COUNT=true> (+ lidar_dist / windows outputs); the product
+    launch must produce the same observations, rewards and state."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    n = 97
+    scn = S.moving_obstacles(n, 17, 11, seed=31)
+    e1 = AUVVecEnv(scn, n, cfg, auto_reset=True, debug=True)
+    e2 = AUVVecEnv(scn, n, cfg, auto_reset=True, debug=False)
+    assert torch.equal(e1.reset(), e2.reset())
+    acts = random_actions(40, n, 6).astype(np.float32)
+    for t in range(40):
+        a = torch.as_tensor(acts[t], device="cuda")
+        o1, r1, d1, _ = e1.step(a)
+        o2, r2, d2, _ = e2.step(a)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+    assert torch.equal(e1.state, e2.state)
+    assert int(e1._out["seg_tests"].item()) > 0
+
+
 def test_bad_shapes_raise():
     from gym_auv_b200.vec_env import AUVVecEnv
 
@@ -475,4 +531,4 @@ def test_staged_entry_points_compose_to_a_step():
         o2 = e2.observe()
         assert torch.equal(o1, o2) and torch.equal(r1, e2._out["reward"]) and torch.equal(e1.state, e2.state)
     nav = e2.navigate()
-    assert nav.shape == (5, 12) and torch.equal(nav, e1.get_attr("nav"))
+    assert nav.shape == (5, 16) and torch.equal(nav, e1.get_attr("nav"))
