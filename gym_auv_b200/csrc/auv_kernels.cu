@@ -1,12 +1,15 @@
 // auv_kernels.cu -- hand-written sm_100a kernels for the gym-auv step path + the C ABI.
 //
 // Kernel inventory (reference file:line each one replaces is in include/auv_b200.h):
-//   k_obstacle_update  thread per (env, moving-obstacle slot)                        HBM
-//   k_vessel_nav<DYN>  thread per env, FP64: RKF45 vessel step (DYN) -> path projection
-//                      (exact hierarchical LineString.project) -> navigation record ->
-//                      obstacle culling: nearby list (every 25 steps), enclosing circles,
-//                      reference-exact ray windows, inside tests -> compact per-env
-//                      obstacle records in HBM                                latency / FP64
+//   k_obstacle_update  thread per (env, moving-obstacle slot): staged entry point only, the
+//                      step runs the update inside k_vessel_nav                       HBM
+//   k_vessel_nav<DYN,OBST,G>  a group of G lanes per env, FP64: moving-obstacle update (OBST)
+//                      -> RKF45 vessel step (DYN) -> path projection (exact hierarchical
+//                      LineString.project, nodes/segments split over the group) -> navigation
+//                      record, obs[0..5], LiDAR-independent part of the reward -> obstacle
+//                      culling (slots split over the group): nearby list (every 25 steps),
+//                      enclosing circles, reference-exact ray windows, inside tests ->
+//                      compact per-env obstacle records in HBM                 latency / FP64
 //   k_lidar            WARP per env, lanes over rays: per-env scalars and obstacle records
 //                      arrive in one round trip, vertices are staged in shared memory (formed
 //                      in FP64 relative to the vessel), ray/segment casting (analytic edge pick
@@ -31,6 +34,30 @@
 
 namespace auv {
 
+// moving-obstacle update of one (env, slot)   obstacles.py:195-215
+__device__ __forceinline__ void obstacle_update_slot(const AuvConfig& cfg, const AuvScenarioPool& pool,
+                                                     const AuvBatch& batch, long long pe, long long ps) {
+  const double w = pool.mov_width[ps];
+  if (!(w > 0.0)) return;
+  const double dt = cfg.t_step_size;
+  double counter = batch.mov_counter[pe] + dt;
+  int index = (int)floor(counter);
+  const int4 tr = reinterpret_cast<const int4*>(pool.mov_track)[ps];  // off, len, stride
+  double2 pos = reinterpret_cast<double2*>(batch.mov_pos)[pe];
+  if (index >= tr.y - 1) {
+    counter = 0.0;
+    index = 0;
+    pos = reinterpret_cast<const double2*>(pool.mov_start)[ps];
+  }
+  const double2 v = reinterpret_cast<const double2*>(pool.vel_table)[tr.x + (long long)index * tr.z];
+  const double dx = dt * v.x, dy = dt * v.y;
+  pos.x += dx;
+  pos.y += dy;
+  reinterpret_cast<double2*>(batch.mov_pos)[pe] = pos;
+  reinterpret_cast<double2*>(batch.mov_disp)[pe] = make_double2(dx, dy);
+  batch.mov_counter[pe] = counter;
+}
+
 // ------------------------------------------------------------------------------------
 // k_obstacle_update     obstacles.py:195-215
 // ------------------------------------------------------------------------------------
@@ -42,26 +69,7 @@ __global__ void __launch_bounds__(256) k_obstacle_update(AuvConfig cfg, AuvScena
   const long long gid = lid + (long long)e0 * km;  // envs [e0, e0 + cnt)
   const int e = (int)(gid / km);
   const int j = (int)(gid - (long long)e * km);
-  const long long ps = (long long)batch.scn_id[e] * km + j;
-  const double w = pool.mov_width[ps];
-  if (!(w > 0.0)) return;
-  const double dt = cfg.t_step_size;
-  double counter = batch.mov_counter[gid] + dt;
-  int index = (int)floor(counter);
-  const int4 tr = reinterpret_cast<const int4*>(pool.mov_track)[ps];  // off, len, stride
-  double2 pos = reinterpret_cast<double2*>(batch.mov_pos)[gid];
-  if (index >= tr.y - 1) {
-    counter = 0.0;
-    index = 0;
-    pos = reinterpret_cast<const double2*>(pool.mov_start)[ps];
-  }
-  const double2 v = reinterpret_cast<const double2*>(pool.vel_table)[tr.x + (long long)index * tr.z];
-  const double dx = dt * v.x, dy = dt * v.y;
-  pos.x += dx;
-  pos.y += dy;
-  reinterpret_cast<double2*>(batch.mov_pos)[gid] = pos;
-  reinterpret_cast<double2*>(batch.mov_disp)[gid] = make_double2(dx, dy);
-  batch.mov_counter[gid] = counter;
+  obstacle_update_slot(cfg, pool, batch, gid, (long long)batch.scn_id[e] * km + j);
 }
 
 // Vessel.step only (staged entry point auv_vessel_step)
@@ -194,10 +202,16 @@ __device__ __forceinline__ SlotGeom load_slot(const AuvScenarioPool& pool, const
   return g;
 }
 
-__device__ __forceinline__ void cull_env_thread(const AuvConfig& cfg, const AuvScenarioPool& pool,
-                                                const AuvBatch& batch, const double2* __restrict__ unit64,
-                                                int* __restrict__ windows_out, int e, int scn, double px,
-                                                double py, double psi, int step_counter) {
+// Culling stage for one env by its group of G lanes: the lanes take different obstacle slots
+// (slot j of a 32-slot word belongs to lane j % G), records are emitted in slot order by a
+// ballot prefix.  `store` is false for the padding groups past the end of the env range.
+template <int G>
+__device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvScenarioPool& pool,
+                                               const AuvBatch& batch, const double2* __restrict__ unit64,
+                                               int* __restrict__ windows_out, int e, int scn, double px,
+                                               double py, double psi, int step_counter, const int lane,
+                                               const unsigned gm, const bool store) {
+  const int sub = lane & (G - 1);
   const int R = cfg.n_sensors;
   const int S = pool.k_moving + pool.k_static + pool.n_world;
   const bool refresh = (step_counter % cfg.sensor_interval_load_obstacles) == 0;
@@ -210,109 +224,149 @@ __device__ __forceinline__ void cull_env_thread(const AuvConfig& cfg, const AuvS
     if (refresh) {
       // ---- nearby list: {o : dist(p0, o.boundary) - width < range}   vessel.py:266-273
       word = 0u;
-      const int jend = min(S, base + 32);
-      for (int j = base; j < jend; ++j) {
-        const SlotGeom g = load_slot(pool, batch, e, scn, j, px, py);
-        if (!g.valid) continue;
-        bool near;
-        const double dc = sqrt(g.cx * g.cx + g.cy * g.cy);
-        if (dc - g.rho - width >= range + 1e-6) {
-          near = false;  // the boundary lies inside the enclosing circle: distance >= dc - rho
-        } else if (dc + g.rho - width < range - 1e-6) {
-          near = true;  // ... and distance <= dc + rho
-        } else {
-          const double bx0 = g.cx - (2.0 * g.geo / 9.0) * g.hx, by0 = g.cy - (2.0 * g.geo / 9.0) * g.hy;
-          bool in_dummy;
-          const double dist =
-              g.world ? world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + g.vbase, g.nv,
-                                               px, py, in_dummy)
-                      : boundary_distance(g.pent, g.cx, g.cy, bx0, by0, g.geo, g.hx, g.hy, g.nv, unit64);
-          near = (dist - width) < range;
+#pragma unroll 1
+      for (int k = 0; k < 32 / G; ++k) {
+        const int j = base + k * G + sub;
+        bool near = false;
+        if (j < S) {
+          const SlotGeom g = load_slot(pool, batch, e, scn, j, px, py);
+          if (g.valid) {
+            const double dc = sqrt(g.cx * g.cx + g.cy * g.cy);
+            if (dc - g.rho - width >= range + 1e-6) {
+              near = false;  // the boundary lies inside the enclosing circle: distance >= dc - rho
+            } else if (dc + g.rho - width < range - 1e-6) {
+              near = true;  // ... and distance <= dc + rho
+            } else {
+              const double bx0 = g.cx - (2.0 * g.geo / 9.0) * g.hx, by0 = g.cy - (2.0 * g.geo / 9.0) * g.hy;
+              bool in_dummy;
+              const double dist =
+                  g.world ? world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + g.vbase, g.nv,
+                                                   px, py, in_dummy)
+                          : boundary_distance(g.pent, g.cx, g.cy, bx0, by0, g.geo, g.hx, g.hy, g.nv, unit64);
+              near = (dist - width) < range;
+            }
+          }
         }
-        if (near) word |= 1u << (j - base);
+        word |= group_ballot<G>(gm, lane, near) << (k * G);
       }
-      *mw = word;
+      if (store && sub == 0) *mw = word;
     } else {
       word = *mw;
     }
-    if (windows_out != nullptr) {
-      const int jend = min(S, base + 32);
-      for (int j = base; j < jend; ++j)
-        if (!((word >> (j - base)) & 1u))
-          reinterpret_cast<int2*>(windows_out)[(long long)e * S + j] = make_int2(0, 0);
+    // ---- one record per nearby obstacle: lane `sub` takes the (sub + t G)-th set bit of the word
+    //      ("by rank"), so the groups of a warp run the expensive window arithmetic together
+    if (windows_out != nullptr && store) {
+      for (int j = base + sub; j < min(S, base + 32); j += G)
+        reinterpret_cast<int2*>(windows_out)[(long long)e * S + j] = make_int2(0, 0);
+      __syncwarp(gm);
     }
-    // ---- one record per nearby obstacle
-    while (word) {
-      const int j = base + __ffs(word) - 1;
-      word &= word - 1;
+    const int nw = __popc(word);
+    for (int r = sub; r < nw; r += G) {
+      unsigned wv = word;
+      for (int t = 0; t < r; ++t) wv &= wv - 1;
+      const int j = base + __ffs(wv) - 1;
       const SlotGeom g = load_slot(pool, batch, e, scn, j, px, py);
       int wa = 0, wb = 0;
       bool allrays = false, inside = false;
+      double bx0 = 0.0, by0 = 0.0;
       if (g.valid) {
         int lo, hi;
         cull_bounds(g.cx, g.cy, g.rho, psi, R, lo, hi);
         window_from_bounds(lo, hi, R, cfg.cull_mode, wa, wb, allrays);
+        bx0 = g.cx - (2.0 * g.geo / 9.0) * g.hx;
+        by0 = g.cy - (2.0 * g.geo / 9.0) * g.hy;
+        if (g.cx * g.cx + g.cy * g.cy <= g.rho * g.rho) {  // filled boundaries: own-ship inside => range 0
+          if (g.pent)
+            inside = vessel_inside_pentagon(bx0, by0, g.geo, g.hx, g.hy);
+          else if (g.world)
+            world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + g.vbase, g.nv, px, py, inside);
+        }
       }
-      if (windows_out != nullptr)
-        reinterpret_cast<int2*>(windows_out)[(long long)e * S + j] = g.valid ? make_int2(wa, wb) : make_int2(0, 0);
-      if (!g.valid) continue;
-      const double bx0 = g.cx - (2.0 * g.geo / 9.0) * g.hx, by0 = g.cy - (2.0 * g.geo / 9.0) * g.hy;
-      if (g.cx * g.cx + g.cy * g.cy <= g.rho * g.rho) {  // filled boundaries: own-ship inside => range 0
-        if (g.pent)
-          inside = vessel_inside_pentagon(bx0, by0, g.geo, g.hx, g.hy);
-        else if (g.world)
-          world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + g.vbase, g.nv, px, py, inside);
-      }
-      if (cnt >= batch.rec_cap) {  // cannot happen when rec_cap >= number of slots
+      if (!store) continue;
+      if (windows_out != nullptr) reinterpret_cast<int2*>(windows_out)[(long long)e * S + j] = make_int2(wa, wb);
+      const int idx = cnt + r;
+      if (idx >= batch.rec_cap) {  // cannot happen when rec_cap >= number of slots
         if (batch.status != nullptr) atomicOr(batch.status, AUV_STATUS_REC_OVERFLOW);
         continue;
       }
-      ObstRec r;
-      r.cx = g.pent ? bx0 : g.cx;
-      r.cy = g.pent ? by0 : g.cy;
-      r.geo = g.geo;
-      r.hx = g.hx;
-      r.hy = g.hy;
-      r.ecx = (float)g.cx;
-      r.ecy = (float)g.cy;
-      r.rho = (float)g.rho;
-      r.a = wa;
-      r.b = wb;
-      r.flags = (g.pent ? (OFLAG_FILLED | OFLAG_PENTAGON) : 0) | (g.world ? (OFLAG_FILLED | OFLAG_WORLD) : 0) |
+      ObstRec q;
+      q.cx = g.pent ? bx0 : g.cx;
+      q.cy = g.pent ? by0 : g.cy;
+      q.geo = g.geo;
+      q.hx = g.hx;
+      q.hy = g.hy;
+      q.ecx = (float)g.cx;
+      q.ecy = (float)g.cy;
+      q.rho = (float)g.rho;
+      q.a = wa;  // a nearby bit is only ever set for a valid slot; an invalid one would leave an
+      q.b = wb;  // empty window (0, 0) that no ray tests
+      q.flags = (g.pent ? (OFLAG_FILLED | OFLAG_PENTAGON) : 0) | (g.world ? (OFLAG_FILLED | OFLAG_WORLD) : 0) |
                 (inside ? OFLAG_INSIDE : 0) | (allrays ? OFLAG_ALLRAYS : 0);
-      r.nv = g.nv;
-      r.vbase = g.vbase;
-      rec[cnt++] = r;
+      q.nv = g.valid ? g.nv : 1;
+      q.vbase = g.vbase;
+      rec[idx] = q;
     }
+    cnt = min(cnt + nw, batch.rec_cap);
   }
-  batch.rec_cnt[e] = cnt;
+  if (store && sub == 0) batch.rec_cnt[e] = cnt;
 }
 
-// Vessel.step fused with Vessel.navigate and the culling stage (DYN), or navigate + culling
-// only (reset / staged observe): the state never leaves registers in between.
-template <bool DYN>
-__global__ void __launch_bounds__(64) k_vessel_nav(const __grid_constant__ AuvConfig cfg,
-                                                    const __grid_constant__ AuvPathBank paths,
-                                                    const __grid_constant__ AuvScenarioPool pool,
-                                                    const __grid_constant__ AuvBatch batch,
-                                                    const double2* __restrict__ unit64,
-                                                    int* __restrict__ windows_out,
-                                                    const float* __restrict__ actions, float* __restrict__ obs_out,
-                                                    int obs_dim, int e0, int e1) {
-  const int e = e0 + blockIdx.x * blockDim.x + threadIdx.x;  // envs [e0, e1)
+// BaseEnvironment._update (OBST) + Vessel.step (DYN) + Vessel.navigate + the culling stage, a
+// group of G lanes per env.  The scalar FP64 chains (RK step, PCHIP, navigation features) are
+// computed redundantly by the lanes of a group; the table searches (path projection, obstacle
+// slots) are split over them, which shortens the per-warp critical path ~G-fold and gives the
+// SM G times more warps to hide the remaining load latency with (thread-per-env had N/32 warps:
+// 3 per scheduler at 65536 envs, one long dependent chain each -- profiles/r1e, r1h).
+#ifndef AUV_NAV_G
+#define AUV_NAV_G 4
+#endif
+#ifndef AUV_NAV_THREADS
+#define AUV_NAV_THREADS 128
+#endif
+#ifndef AUV_NAV_MINB
+#define AUV_NAV_MINB 8  // 64 registers: occupancy beats spills here (G x MINB sweep: profiles/r1j_variants.txt)
+#endif
+template <bool DYN, bool OBST, int G>
+__global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(const __grid_constant__ AuvConfig cfg,
+                                                                const __grid_constant__ AuvPathBank paths,
+                                                                const __grid_constant__ AuvScenarioPool pool,
+                                                                const __grid_constant__ AuvBatch batch,
+                                                                const double2* __restrict__ unit64,
+                                                                int* __restrict__ windows_out,
+                                                                const float* __restrict__ actions,
+                                                                float* __restrict__ obs_out, int obs_dim, int e0, int e1) {
+  const int lane = threadIdx.x & 31, sub = lane & (G - 1);
+  const unsigned gm = group_mask<G>(lane);
+  const int eraw = e0 + (blockIdx.x * AUV_NAV_THREADS + threadIdx.x) / G;  // envs [e0, e1)
+  if (eraw - (lane / G) >= e1) return;  // the whole warp is past the end
+  const bool store = eraw < e1;
+  const int e = store ? eraw : e1 - 1;  // padding groups shadow the last env and store nothing
   const int n = batch.n_envs;
-  if (e >= e1) return;
+  const int scn = batch.scn_id[e];
+  if (OBST) {  // the group's lanes take the env's moving-obstacle slots
+    const int km = pool.k_moving;
+    if (store)
+      for (int j = sub; j < km; j += G) obstacle_update_slot(cfg, pool, batch, (long long)e * km + j, (long long)scn * km + j);
+  }
   S6 y = load_state(batch.state, n, e);
   int step_counter = batch.step_counter[e];
+  float2 act = make_float2(0.f, 0.f);
+  if (DYN) act = reinterpret_cast<const float2*>(actions)[e];
+  __syncwarp();  // every lane has read the old state / the updated obstacles are visible to the group
   if (DYN) {
-    y = vessel_rk_step(cfg, y, reinterpret_cast<const float2*>(actions)[e]);
-    store_state(batch.state, n, e, y);
-    batch.step_counter[e] = ++step_counter;
+    y = vessel_rk_step(cfg, y, act);
+    ++step_counter;
+    if (store && sub == 0) {
+      store_state(batch.state, n, e, y);
+      batch.step_counter[e] = step_counter;
+    }
   }
-  const int scn = batch.scn_id[e];
-  navigate_thread(cfg, paths, batch, pool.path_id[scn], e, y.x, y.y, y.psi, y.u, y.v, y.r,
-                  obs_out ? obs_out + (long long)e * obs_dim : nullptr);
-  if (cfg.use_lidar) cull_env_thread(cfg, pool, batch, unit64, windows_out, e, scn, y.x, y.y, y.psi, step_counter);
+  const int pid = pool.path_id[scn];
+  const double s = project_group<G>(paths, pid, y.x, y.y, lane, gm);
+  navigate_env(cfg, paths, batch, pid, e, s, y.x, y.y, y.psi, y.u, y.v, y.r,
+               obs_out ? obs_out + (long long)e * obs_dim : nullptr, store && sub == 0);
+  if (cfg.use_lidar)
+    cull_env_group<G>(cfg, pool, batch, unit64, windows_out, e, scn, y.x, y.y, y.psi, step_counter, lane, gm, store);
 }
 
 // ------------------------------------------------------------------------------------
@@ -938,18 +992,21 @@ static int check_observe_args(const AuvConfig* cfg, const AuvRayTable* rays, con
 
 static int launch_vessel_nav(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                              const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out,
-                             const float* actions, void* stream, int e0 = 0, int cnt = -1) {
+                             const float* actions, void* stream, int e0 = 0, int cnt = -1, bool with_obstacles = false) {
   if (cnt < 0) cnt = batch->n_envs - e0;
-  const int threads = 64;  // small CTAs: 65536 envs are only ~7 CTAs per SM, balance matters
-  const int blocks = (cnt + threads - 1) / threads;
+  const int per_cta = AUV_NAV_THREADS / AUV_NAV_G;  // envs per CTA
+  const int blocks = (cnt + per_cta - 1) / per_cta;
   const double2* unit = rays ? reinterpret_cast<const double2*>(rays->unit64) : nullptr;
   int* win = out ? out->windows : nullptr;
   float* obs = out ? out->obs : nullptr;
   const int od = auv_obs_dim(cfg);
-  if (actions)
-    auv::k_vessel_nav<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, unit, win, actions, obs, od, e0, e0 + cnt);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (actions && with_obstacles && pool->k_moving > 0)
+    auv::k_vessel_nav<true, true, AUV_NAV_G><<<blocks, AUV_NAV_THREADS, 0, s>>>(*cfg, *paths, *pool, *batch, unit, win, actions, obs, od, e0, e0 + cnt);
+  else if (actions)
+    auv::k_vessel_nav<true, false, AUV_NAV_G><<<blocks, AUV_NAV_THREADS, 0, s>>>(*cfg, *paths, *pool, *batch, unit, win, actions, obs, od, e0, e0 + cnt);
   else
-    auv::k_vessel_nav<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, *paths, *pool, *batch, unit, win, nullptr, obs, od, e0, e0 + cnt);
+    auv::k_vessel_nav<false, false, AUV_NAV_G><<<blocks, AUV_NAV_THREADS, 0, s>>>(*cfg, *paths, *pool, *batch, unit, win, nullptr, obs, od, e0, e0 + cnt);
   return cuda_check(cudaGetLastError(), "k_vessel_nav");
 }
 
@@ -1016,8 +1073,8 @@ int auv_step(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* p
              void* stream) {
   if (!actions) return set_err(AUV_EINVAL, "actions is NULL");
   if (int rc = check_observe_args(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP)) return rc;
-  if (int rc = launch_obstacle_update(cfg, pool, batch, 0, batch->n_envs, stream)) return rc;
-  if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, actions, stream)) return rc;
+  // the moving-obstacle update (environment.py:386-392) runs inside the vessel/navigation kernel
+  if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, actions, stream, 0, -1, true)) return rc;
   return launch_lidar(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, stream);
 }
 
@@ -1098,8 +1155,7 @@ static int step_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const Auv
         return rc;
       act = actions_dev;
     }
-    if (int rc = launch_obstacle_update(cfg, pool, batch, e0, cnt, vs)) return rc;
-    if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, act, vs, e0, cnt)) return rc;
+    if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, act, vs, e0, cnt, true)) return rc;
     if (int rc = launch_lidar(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, vs, e0, cnt)) return rc;
     if (host) {
       if (int rc = cuda_check(cudaMemcpyAsync(obs_host + od * e0, out->obs + od * e0, (size_t)cnt * od * sizeof(float),
@@ -1175,9 +1231,8 @@ int auv_step_timed(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathB
   cudaStream_t s = (cudaStream_t)stream;
   cudaEvent_t* e = t->ev + AUV_TIMER_EVENTS * slot;
   cudaEventRecord(e[0], s);
-  if (int rc = launch_obstacle_update(cfg, pool, batch, 0, batch->n_envs, stream)) return rc;
-  cudaEventRecord(e[1], s);
-  if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, actions, stream)) return rc;
+  cudaEventRecord(e[1], s);  // the obstacle update is fused into k_vessel_nav: slot 0 reads ~0
+  if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, actions, stream, 0, -1, true)) return rc;
   cudaEventRecord(e[2], s);
   if (int rc = launch_lidar(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, stream)) return rc;
   return cuda_check(cudaEventRecord(e[3], s), "cudaEventRecord");

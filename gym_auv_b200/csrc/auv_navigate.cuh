@@ -7,7 +7,7 @@
 namespace auv {
 
 // ------------------------------------------------------------------------------------
-// Path projection + navigation features, ONE THREAD per env (FP64)
+// Path projection + navigation features, a group of G lanes per env (FP64)
 //   path.py:61-93 (PCHIP eval, LineString.project), vessel.py:461-541 (navigate)
 // The result is the env's navigation record nav[e][AUV_NAV_W] in HBM; the warp-per-env
 // LiDAR kernel reads it back (one 96 B coalesced load).
@@ -60,15 +60,44 @@ __device__ __forceinline__ double seg_d2(double px, double py, double2 A, double
   return cr * cr / len2;
 }
 
+// ---- sub-warp groups: G consecutive lanes (G = 4, 8, 16 or 32) work on one env
+template <int G>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+  return G == 32 ? AUV_FULL : (((1u << G) - 1u) << (lane & ~(G - 1)));
+}
+template <int G>
+__device__ __forceinline__ float group_min(unsigned gm, float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(gm, v, o));
+  return v;
+}
+// bits of the group's lanes (bit k = lane k of the group) for which pred holds
+template <int G>
+__device__ __forceinline__ unsigned group_ballot(unsigned gm, int lane, bool pred) {
+  const unsigned b = __ballot_sync(gm, pred);
+  return G == 32 ? b : ((b >> (lane & ~(G - 1))) & ((1u << G) - 1u));
+}
+
 // GEOS LengthIndexOfPoint::indexOf (LineString.project) restated as an exact three-level
-// search.  Level 2 = superblocks of 32 blocks, level 1 = blocks of 32 segments; each node is
-// a capsule (chord, max deviation) that contains its part of the polyline, so
+// search, executed by a GROUP of G lanes per env.  Level 2 = superblocks of 32 blocks, level 1
+// = blocks of 32 segments; each node is a capsule (chord, max deviation) that contains its part
+// of the polyline, so
 //   dist(P, node) in [dc - dev, dc + dev],  dc = dist(P, chord)   (FP32, padded).
 // Pass A finds an upper bound over superblocks, pass B tightens it over the blocks of the
 // surviving superblocks, pass C refines in FP64 every block whose lower bound does not
-// exceed it.  The arg-min is lexicographic in (distance, segment index), which is GEOS's
-// "first minimum wins" independent of visiting order.
-__device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid, double px, double py) {
+// exceed it.  In every pass the lanes of the group take different nodes / segments, so one
+// round of loads covers G of them, and the bound is shared by a shuffle-min; all bounds are
+// compared in the squared domain (one sqrt only when a bound improves).  The arg-min is
+// lexicographic in (distance, segment index), which is GEOS's "first minimum wins"
+// independent of visiting order.  Every lane returns the same arclength.
+template <int G>
+__device__ __forceinline__ double project_group(const AuvPathBank& pb, int pid, double px, double py,
+                                                const int lane, const unsigned gm) {
+  constexpr int KB = AUV_PATH_SUPER / G;  // blocks of a superblock per lane
+  constexpr int KS = AUV_PATH_BLOCK / G;  // segments of a block per lane
+  constexpr int KBB = KB < 8 ? KB : 8;    // ... loaded in batches of at most 8
+  constexpr int KSB = KS < 8 ? KS : 8;
+  const int sub = lane & (G - 1);
   const int v0 = pb.poly_off[pid];
   const int nseg = pb.poly_off[pid + 1] - v0 - 1;
   const int b0 = pb.blk_off[pid];
@@ -83,87 +112,92 @@ __device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid,
   const float4* sbc = reinterpret_cast<const float4*>(pb.sb_chord) + s0;
   const float2* sba = reinterpret_cast<const float2*>(pb.sb_dev) + s0;
   const float up = 1.f + 4e-6f, dn2 = (1.f - 4e-6f) * (1.f - 4e-6f);
-  // All node loops below issue their loads in groups of U before any arithmetic, so a
-  // thread has U independent L2 requests in flight instead of one (the kernel is bound by
-  // load latency, not by FP64 issue: profiles/r1b).  Bounds are compared in the squared
-  // domain: an upper bound dc + dev + pad is only evaluated (one sqrt) when it can improve
-  // ub, and a node is discarded when dc^2 (1-eps)^2 > (ub + dev + pad)^2.
-  constexpr int U = 8;
   float ub = INFINITY;
 #define AUV_TIGHTEN(d2, dv)                                         \
   if ((d2) < ub * ub) ub = fminf(ub, sqrtf(d2) * up + (dv) + pad);
 #define AUV_PRUNED(d2, dv) ((d2) * dn2 > (ub + (dv) + pad) * (ub + (dv) + pad))
-  for (int g0 = 0; g0 < nsb; g0 += U) {
-    float4 ch[U];
-    float2 ax[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = min(g0 + u, nsb - 1);
-      ch[u] = sbc[i];
-      ax[u] = sba[i];
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float d2 = pt_chord_d2_f(qx, qy, ch[u], ax[u].x);
-      AUV_TIGHTEN(d2, ax[u].y)
-    }
+  // pass A: upper bound over the superblocks
+  for (int g0 = 0; g0 < nsb; g0 += G) {
+    const int i = min(g0 + sub, nsb - 1);
+    const float4 ch = sbc[i];
+    const float2 ax = sba[i];
+    const float d2 = pt_chord_d2_f(qx, qy, ch, ax.x);
+    AUV_TIGHTEN(d2, ax.y)
   }
-  // pass B: tighten over blocks of surviving superblocks; remember which survive
-  unsigned long long live = 0ull;  // up to 64 superblocks tracked exactly, the rest are always visited
-  for (int sb = 0; sb < nsb; ++sb) {
-    const float2 a0 = sba[sb];
-    if (AUV_PRUNED(pt_chord_d2_f(qx, qy, sbc[sb], a0.x), a0.y)) continue;
-    if (sb < 64) live |= 1ull << sb;
-    const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
-    for (int g0 = sb * AUV_PATH_SUPER; g0 < be; g0 += U) {
-      float4 ch[U];
-      float2 ax[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = min(g0 + u, be - 1);
-        ch[u] = chord[i];
-        ax[u] = aux[i];
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float d2 = pt_chord_d2_f(qx, qy, ch[u], ax[u].x);
-        AUV_TIGHTEN(d2, ax[u].y)
-      }
-    }
-  }
-  // pass C: exact refine
+  ub = group_min<G>(gm, ub);
   const double2* poly = reinterpret_cast<const double2*>(pb.poly_xy) + v0;
   double best_d2 = INFINITY;
-  int best_seg = 0;
-  for (int sb = 0; sb < nsb; ++sb) {
-    if (sb < 64 && !((live >> sb) & 1ull)) continue;
-    const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
-    for (int g0 = sb * AUV_PATH_SUPER; g0 < be; g0 += U) {
-      float4 ch[U];
-      float2 ax[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = min(g0 + u, be - 1);
-        ch[u] = chord[i];
-        ax[u] = aux[i];
+  int best_seg = 0x7fffffff;
+  // Superblocks are handled in windows of 64 (one bit each).  All loops below pop the next set
+  // bit of a mask that is uniform in the group ("by rank"): the groups of a warp then run their
+  // r-th live node together instead of serialising over node indices.
+  for (int w0 = 0; w0 < nsb; w0 += 64) {
+    const int wn = min(64, nsb - w0);
+    unsigned long long live = 0ull;
+    for (int t = 0; t < wn; ++t) {
+      const float2 a0 = sba[w0 + t];
+      if (!AUV_PRUNED(pt_chord_d2_f(qx, qy, sbc[w0 + t], a0.x), a0.y)) live |= 1ull << t;
+    }
+    // pass B: tighten over the blocks of the surviving superblocks
+    for (unsigned long long rest = live; rest;) {
+      const int t = __ffsll((long long)rest) - 1;
+      rest &= rest - 1;
+      const int sb = w0 + t;
+      const float2 a0 = sba[sb];
+      if (AUV_PRUNED(pt_chord_d2_f(qx, qy, sbc[sb], a0.x), a0.y)) {  // ub has tightened since
+        live &= ~(1ull << t);
+        continue;
       }
-      unsigned cand = 0u;
+      const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (g0 + u < be && !AUV_PRUNED(pt_chord_d2_f(qx, qy, ch[u], ax[u].x), ax[u].y)) cand |= 1u << u;
-      while (cand) {  // blocks in increasing order
-        const int b = g0 + __ffs(cand) - 1;
+      for (int k0 = 0; k0 < KB; k0 += KBB) {
+        float4 ch[KBB];
+        float2 ax[KBB];
+#pragma unroll
+        for (int k = 0; k < KBB; ++k) {
+          const int i = min(sb * AUV_PATH_SUPER + (k0 + k) * G + sub, be - 1);
+          ch[k] = chord[i];
+          ax[k] = aux[i];
+        }
+#pragma unroll
+        for (int k = 0; k < KBB; ++k) {
+          const float d2 = pt_chord_d2_f(qx, qy, ch[k], ax[k].x);
+          AUV_TIGHTEN(d2, ax[k].y)
+        }
+      }
+      ub = group_min<G>(gm, ub);
+    }
+    // pass C: exact refine of the blocks that can still hold the minimum
+    for (unsigned long long rest = live; rest;) {
+      const int t = __ffsll((long long)rest) - 1;
+      rest &= rest - 1;
+      const int sb = w0 + t;
+      const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
+      unsigned cand = 0u;  // bit = block offset inside the superblock, uniform in the group
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        const int b = sb * AUV_PATH_SUPER + k * G + sub;
+        const int i = min(b, be - 1);
+        const float4 ch = chord[i];
+        const float2 ax = aux[i];
+        cand |= group_ballot<G>(gm, lane, b < be && !AUV_PRUNED(pt_chord_d2_f(qx, qy, ch, ax.x), ax.y)) << (k * G);
+      }
+      while (cand) {
+        const int b = sb * AUV_PATH_SUPER + __ffs(cand) - 1;
         cand &= cand - 1;
         const int se = min(nseg, (b + 1) * AUV_PATH_BLOCK);
-        for (int k0 = b * AUV_PATH_BLOCK; k0 < se; k0 += U) {
-          double2 v[U + 1];
 #pragma unroll
-          for (int u = 0; u <= U; ++u) v[u] = poly[min(k0 + u, se)];
+        for (int u0 = 0; u0 < KS; u0 += KSB) {
+          const int k0 = b * AUV_PATH_BLOCK + sub * KS + u0;  // this lane's consecutive segments
+          double2 v[KSB + 1];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
+          for (int u = 0; u <= KSB; ++u) v[u] = poly[min(k0 + u, se)];
+#pragma unroll
+          for (int u = 0; u < KSB; ++u) {
             if (k0 + u < se) {
               const double d2 = seg_d2(px, py, v[u], v[u + 1]);
-              if (d2 < best_d2) {  // segments are visited in increasing k: strict '<' keeps the first
+              // a lane's segments come in increasing order over the whole search
+              if (d2 < best_d2) {
                 best_d2 = d2;
                 best_seg = k0 + u;
               }
@@ -175,6 +209,15 @@ __device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid,
   }
 #undef AUV_TIGHTEN
 #undef AUV_PRUNED
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {  // lexicographic (distance, segment) arg-min over the group
+    const double od = __shfl_xor_sync(gm, best_d2, o);
+    const int oi = __shfl_xor_sync(gm, best_seg, o);
+    if (od < best_d2 || (od == best_d2 && oi < best_seg)) {
+      best_d2 = od;
+      best_seg = oi;
+    }
+  }
   // segmentNearestMeasure of the winning segment
   const double2 A = poly[best_seg], B = poly[best_seg + 1];
   const double start = pb.poly_cum[v0 + best_seg];
@@ -191,11 +234,12 @@ __device__ __forceinline__ double project_thread(const AuvPathBank& pb, int pid,
 // Vessel.navigate (vessel.py:461-541) for env e; writes nav[e][:] and max_progress[e], the
 // navigation part of the observation (vessel.py:518-539, clipped: environment.py:276-280) and
 // the LiDAR-independent part of the reward (rewarder.py:78-140,167-241).
-__device__ __forceinline__ void navigate_thread(const AuvConfig& cfg, const AuvPathBank& pb,
-                                                const AuvBatch& batch, int pid, int e, double px,
-                                                double py, double psi, double vu, double vv, double vr,
-                                                float* __restrict__ obs_row) {
-  const double s = project_thread(pb, pid, px, py);
+// `s` is the projected arclength (project_group); every lane of the env's group computes the
+// same scalars, `store` is true for the one lane that writes them.
+__device__ __forceinline__ void navigate_env(const AuvConfig& cfg, const AuvPathBank& pb,
+                                             const AuvBatch& batch, int pid, int e, const double s, double px,
+                                             double py, double psi, double vu, double vv, double vr,
+                                             float* __restrict__ obs_row, const bool store) {
   const double L = pb.length[pid];
   const double s_la = fmin(L, s + cfg.look_ahead_distance);
   double p_x, p_y, d_x, d_y, l_x, l_y, ldx, ldy;
@@ -216,22 +260,8 @@ __device__ __forceinline__ void navigate_thread(const AuvConfig& cfg, const AuvP
   const bool reached = (goal <= cfg.min_goal_distance) || (progress >= cfg.min_path_progress);
   double sp, cp;
   sincos(psi, &sp, &cp);
-  double* o = batch.nav + (long long)e * AUV_NAV_W;
-  o[NAV_S] = s;
-  o[NAV_CHI] = chi;
-  o[NAV_YE] = y_e;
-  o[NAV_SLA] = s_la;
-  o[NAV_LA_ERR] = la_err;
-  o[NAV_HEAD_ERR] = head_err;
-  o[NAV_GOAL] = goal;
-  o[NAV_PROGRESS] = progress;
-  o[NAV_COSPSI] = cp;
-  o[NAV_SINPSI] = sp;
-  o[NAV_REACHED] = reached ? 1.0 : 0.0;
   const double cos_he = (double)cosf((float)head_err);
-  o[NAV_COS_HEAD_ERR] = cos_he;
   const double maxprog = fmax(progress, batch.max_progress[e]);  // vessel.py:507
-  batch.max_progress[e] = maxprog;
   // ---- reward without the closeness term.  Colav (rewarder.py:216-239):
   //   r = 0.5 path + 0.5 closeness - living - 10|r| + slow, x2 if negative (k_lidar adds closeness);
   // PathFollow (rewarder.py:118-140): r = path - living - 10|r| + slow.
@@ -247,6 +277,21 @@ __device__ __forceinline__ void navigate_thread(const AuvConfig& cfg, const AuvP
   } else {
     base = path_reward - living - 10.0 * fabs(vr) + (speed2 < 0.1 * 0.1 ? -2.0 : 0.0);
   }
+  if (!store) return;
+  batch.max_progress[e] = maxprog;
+  double* o = batch.nav + (long long)e * AUV_NAV_W;
+  o[NAV_S] = s;
+  o[NAV_CHI] = chi;
+  o[NAV_YE] = y_e;
+  o[NAV_SLA] = s_la;
+  o[NAV_LA_ERR] = la_err;
+  o[NAV_HEAD_ERR] = head_err;
+  o[NAV_GOAL] = goal;
+  o[NAV_PROGRESS] = progress;
+  o[NAV_COSPSI] = cp;
+  o[NAV_SINPSI] = sp;
+  o[NAV_REACHED] = reached ? 1.0 : 0.0;
+  o[NAV_COS_HEAD_ERR] = cos_he;
   o[NAV_REWARD_BASE] = base;
   if (obs_row != nullptr) {  // [u, v, r, look-ahead heading error, heading error, cross-track / 100]
     obs_row[0] = (float)fmin(fmax(vu, -1.0), 1.0);
