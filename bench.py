@@ -73,6 +73,8 @@ def parse():
     ap.add_argument("--chunks", type=int, default=4,
                     help="env ranges per step on the pipeline's own streams (auv_step_chunked); 1 = single stream")
     ap.add_argument("--chunk-streams", type=int, default=None)
+    ap.add_argument("--host-chunks", type=int, default=4,
+                    help="env ranges of the host-buffer step (auv_step_host_chunked): D2H of a range overlaps the next")
     ap.add_argument("--scenario-cache", default=None,
                     help="pickle the generated scenario set here / reuse it (tuning sweeps; same seeds => same set)")
     return ap.parse_args()
@@ -266,7 +268,7 @@ def run_ours(args):
     N, K, Wm = args.envs, args.steps, max(args.warmup, 3)
     R = cfg.vessel.n_sensors
     env = AUVVecEnv(scn, N, cfg, device=device, test_mode=False, auto_reset=True, env_offset=0,
-                    chunks=args.chunks, chunk_streams=args.chunk_streams)
+                    chunks=args.chunks, chunk_streams=args.chunk_streams, host_chunks=args.host_chunks)
     gen = torch.Generator(device=device)
     gen.manual_seed(1234 + rank)
     lo = torch.tensor([-1.0, -0.15], device=device)
@@ -297,7 +299,7 @@ def run_ours(args):
     sp = C.c_void_p(stream.cuda_stream)
 
     def product_step(a):
-        if env._pipe:
+        if env._pipe and env.chunks > 1:
             _lib.check(env.lib.auv_step_chunked(cfgp, rays, paths, pool, batch, C.c_void_p(a.data_ptr()),
                                                 C.byref(env.out), sp, env._pipe, env.chunks), "auv_step_chunked")
         else:
@@ -391,9 +393,27 @@ def run_ours(args):
         t_e = torch.tensor([dt], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        # what the link alone allows: the same D2H copies (obs, reward, done) with no kernels
+        pin = env._pinned
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        c0.record(stream)
+        for _ in range(10):
+            pin["obs"].copy_(env._out["obs"], non_blocking=True)
+            pin["reward"].copy_(env._out["reward"], non_blocking=True)
+            pin["done"].copy_(env._out["done"], non_blocking=True)
+        c1.record(stream)
+        torch.cuda.synchronize()
+        d2h_ms = c0.elapsed_time(c1) / 10
+        e2e_ms = 1e3 * float(t_e.item()) / ke
         e2e = {"value": world * N * ke / float(t_e.item()), "unit": UNIT,
                "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
-               "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": ke}
+               "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": ke, "ms_per_step": e2e_ms,
+               "host_chunks": env.host_chunks,
+               "pcie": {"d2h_only_ms_per_step": d2h_ms, "d2h_gbs": env.d2h_bytes_per_step / (d2h_ms * 1e-3) / 1e9,
+                        "frac_of_link_bound": d2h_ms / e2e_ms,
+                        "note": "rank-0 link; the e2e step is bound by the D2H of the observations "
+                                "(pinned host memory); frac = D2H-only time / e2e step time"}}
 
     stats = env.episode_stats(reduce=True)  # the only collective on the path (NCCL all-reduce)
 

@@ -178,6 +178,7 @@ EXPORTS = [
     "auv_timer_read",
     "auv_pipeline_create",
     "auv_pipeline_destroy",
+    "auv_pipeline_graph_state",
     "auv_step_chunked",
     "auv_step_host_chunked",
 ]
@@ -225,6 +226,7 @@ def load():
     lib.auv_pipeline_create.restype = _vp
     lib.auv_pipeline_destroy.argtypes = [_vp]
     lib.auv_pipeline_destroy.restype = None
+    lib.auv_pipeline_graph_state.argtypes = [_vp]
     lib.auv_step_chunked.argtypes = [
         P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, P(AuvStepOut), _vp,
         _vp, C.c_int,

@@ -95,9 +95,10 @@ class AUVVecEnv:
     debug     : also record per-ray distances, culling windows and FP64 navigation values
     sector_outputs : also produce per-sector min-pooled and feasibility-pooled ranges
                      (get_attr("sector_min_dist") / get_attr("sector_feasible_dist"))
-    chunks    : > 1 cuts the batch into that many env ranges which run their kernels (and
-                for step_host their H2D/D2H copies) on ``chunk_streams`` internal streams
-                (auv_step_chunked / auv_step_host_chunked); results are identical
+    chunks    : > 1 cuts the batch into that many env ranges which run their kernels on
+                ``chunk_streams`` internal streams (auv_step_chunked); results are identical
+    host_chunks : ranges of step_host (auv_step_host_chunked): each range's observations start
+                their D2H copy while the next range is computed (default: ``chunks``)
     """
 
     def __init__(
@@ -115,6 +116,7 @@ class AUVVecEnv:
         max_nearby: Optional[int] = None,
         chunks: int = 1,
         chunk_streams: Optional[int] = None,
+        host_chunks: Optional[int] = None,
         _shared: Optional[dict] = None,
     ):
         self.device = torch.device(device)
@@ -273,9 +275,10 @@ class AUVVecEnv:
         self.actions_dev = z((N, 2), torch.float32)
         self._pinned = None
         self.chunks = max(1, int(chunks))
+        self.host_chunks = max(1, min(64, int(host_chunks))) if host_chunks else self.chunks
         self._pipe = None
-        if self.chunks > 1:
-            ns = int(chunk_streams) if chunk_streams else min(self.chunks, 4)
+        if self.chunks > 1 or self.host_chunks > 1:
+            ns = int(chunk_streams) if chunk_streams else max(2, min(self.chunks, 4))
             with torch.cuda.device(self.device):
                 self._pipe = self.lib.auv_pipeline_create(ns)
             if not self._pipe:
@@ -363,7 +366,7 @@ class AUVVecEnv:
         a = actions.to(device=self.device, dtype=torch.float32).contiguous()
         cfg, rays, paths, pool, batch = self._refs()
         with torch.cuda.device(self.device):
-            if self._pipe:
+            if self._pipe and self.chunks > 1:
                 _lib.check(
                     self.lib.auv_step_chunked(cfg, rays, paths, pool, batch, C.c_void_p(a.data_ptr()), C.byref(self.out),
                                               self._stream(), self._pipe, self.chunks),
@@ -395,8 +398,8 @@ class AUVVecEnv:
             hargs = (cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
                      C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.c_void_p(pin["obs"].data_ptr()),
                      C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()), self._stream())
-            if self._pipe:
-                _lib.check(self.lib.auv_step_host_chunked(*hargs, self._pipe, self.chunks), "auv_step_host_chunked")
+            if self._pipe and self.host_chunks > 1:
+                _lib.check(self.lib.auv_step_host_chunked(*hargs, self._pipe, self.host_chunks), "auv_step_host_chunked")
             else:
                 _lib.check(self.lib.auv_step_host(*hargs), "auv_step_host")
         self.total_steps += 1

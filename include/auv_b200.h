@@ -264,15 +264,21 @@ int auv_step_host(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBa
                   float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
                   uint8_t* done_host, void* stream);
 /* Chunked step.  Envs are independent (environment.py:292-366 touches one env only), so the
- * batch can be cut into n_chunks env ranges that run their three kernels -- and, for the
- * host-buffer variant, their H2D/D2H copies -- on the pipeline's own streams: ranges in
- * different stages fill each other's idle issue slots and the D2H of one range overlaps the
- * kernels of the next.  The call forks from `stream` and joins back into it (work submitted to
- * `stream` afterwards sees the whole step); results are identical to auv_step / auv_step_host.
- * A pipeline holds n_streams (1..16) non-blocking streams + events, no device memory. */
+ * batch can be cut into n_chunks env ranges.  auv_step_chunked runs the ranges on the
+ * pipeline's own streams (round robin), forking from `stream` and joining back into it.
+ * auv_step_host_chunked computes the ranges in order on `stream` and sends each range's
+ * observations to the host on the pipeline's copy stream as soon as the range is done, so the
+ * D2H of the observations (what bounds the host-buffer step) overlaps the remaining kernels;
+ * n_chunks <= 64.  Results are identical to auv_step / auv_step_host; work submitted to
+ * `stream` afterwards sees the whole step.  A pipeline holds n_streams (1..16) non-blocking
+ * streams + events, no device memory. */
 typedef struct AuvPipeline AuvPipeline;
 AuvPipeline* auv_pipeline_create(int n_streams);
 void auv_pipeline_destroy(AuvPipeline* p);
+/* 1: auv_step_host_chunked replays an instantiated CUDA graph (one launch per step; re-captured
+ * when an argument changes), 0: nothing captured yet, -1: direct submission (capture was not
+ * possible, or AUV_B200_NO_GRAPH is set in the environment). */
+int auv_pipeline_graph_state(const AuvPipeline* p);
 int auv_step_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                      const AuvScenarioPool* pool, AuvBatch* batch, const float* actions,
                      AuvStepOut* out, void* stream, AuvPipeline* p, int n_chunks);

@@ -125,6 +125,64 @@ def test_moving_obstacles_close_quarters():
     assert rep["windows_checked"] > 100
 
 
+@pytest.mark.parametrize("n_sectors,per_sector", [(8, 8), (8, 16), (9, 40), (9, 7), (3, 11), (1, 33)])
+def test_ray_counts_rollout(n_sectors, per_sector):
+    """BASELINE config 5 ray counts (64 / 128 / 360) plus odd counts that are not a multiple of
+    the warp size and give an odd observation width (scalar store path of k_lidar)."""
+    cfg = lidar_config()
+    cfg.vessel.n_sectors = n_sectors
+    cfg.vessel.n_sensors_per_sector = per_sector
+    assert cfg.vessel.n_sensors == n_sectors * per_sector
+    scn = S.moving_obstacles(6, 17, 11, seed=40 + per_sector)
+    actions = random_actions(30, 6, 200 + per_sector)
+    ref = rollout_oracle(scn, cfg, actions)
+    gpu, env = rollout_gpu(scn, cfg, actions)
+    compare(ref, gpu, cfg, f"rays={n_sectors}x{per_sector}")
+    assert env.obs_dim == 6 + n_sectors * per_sector
+    if ref["alive"].all():
+        assert gpu["seg_tests"] == int(ref["n_tests"].sum())
+
+
+def test_dense_harbour_many_records_per_env():
+    """Dozens of obstacles inside sensor range of every vessel: more records than one staging
+    round of k_lidar holds (6 records / 192 vertices), 64-gons (r > 62.3 m) that exhaust the
+    vertex budget on their own, vessels inside rings, overlapping windows."""
+    cfg = lidar_config()
+    M, Km, Ks = 6, 8, 40
+    scn = S.moving_obstacles(M, Km, Ks, seed=77)
+    rng = np.random.RandomState(9)
+    for m in range(M):
+        p0 = scn.vessel_init[m, :2]
+        for j in range(Ks):
+            ang = rng.uniform(-np.pi, np.pi)
+            r = [2.0, 6.0, 20.0, 45.0, 70.0, 90.0][j % 6] * rng.uniform(0.9, 1.1)
+            dist = r + rng.uniform(3.0, 120.0)
+            if j == 0 and m % 2 == 0:
+                dist = 0.5 * r  # own-ship starts inside a ring: rays measure the exit distance
+                r = max(r, 30.0)
+            scn.st_radius[m, j] = r
+            scn.st_pos[m, j] = p0 + dist * np.array([np.cos(ang), np.sin(ang)])
+    actions = random_actions(30, M, 78)
+    ref = rollout_oracle(scn, cfg, actions)
+    gpu, env = rollout_gpu(scn, cfg, actions)
+    rep = compare(ref, gpu, cfg, "dense harbour")
+    assert int(env._scratch["rec_cnt"].max().item()) > 12, "fixture should need several staging rounds"
+    assert rep["windows_checked"] > 1000
+    if ref["alive"].all():
+        assert gpu["seg_tests"] == int(ref["n_tests"].sum())
+
+
+def test_linear_closeness_transform():
+    """sensor_log_transform=False (vessel.py:88-95: closeness = 1 - clip(d / range))."""
+    cfg = lidar_config()
+    cfg.vessel.sensor_log_transform = False
+    scn = S.moving_obstacles(6, 17, 11, seed=5)
+    actions = random_actions(25, 6, 6)
+    ref = rollout_oracle(scn, cfg, actions)
+    gpu, _ = rollout_gpu(scn, cfg, actions)
+    compare(ref, gpu, cfg, "linear closeness")
+
+
 DETERMINISTIC = ["TestScenario1-v0", "TestScenario2-v0", "TestScenario3-v0", "TestScenario4-v0", "TestHeadOn-v0",
                  "TestCrossing-v0", "TestCrossing1-v0", "EmptyScenario-v0", "DebugScenario-v0"]
 
@@ -394,7 +452,7 @@ def test_chunked_step_is_bit_identical(chunks, streams):
     scn = S.moving_obstacles(n, 5, 5, seed=21)
     e1 = AUVVecEnv(scn, n, cfg, auto_reset=True)
     e2 = AUVVecEnv(scn, n, cfg, auto_reset=True, chunks=chunks, chunk_streams=streams)
-    e3 = AUVVecEnv(scn, n, cfg, auto_reset=True, chunks=chunks, chunk_streams=streams)
+    e3 = AUVVecEnv(scn, n, cfg, auto_reset=True, chunks=1, host_chunks=chunks + 1)
     e1.reset(), e2.reset(), e3.reset()
     acts = random_actions(24, n, 4).astype(np.float32)
     for t in range(24):
@@ -410,6 +468,7 @@ def test_chunked_step_is_bit_identical(chunks, streams):
         assert np.array_equal(d1.cpu().numpy(), d3)
     for k in ("state", "mov_pos", "scn_id", "t_step", "cum_reward", "nearby_mask"):
         assert torch.equal(e1._st[k], e2._st[k]) and torch.equal(e1._st[k], e3._st[k]), k
+    assert e3.lib.auv_pipeline_graph_state(e3._pipe) == 1, "host-buffer step should replay a CUDA graph"
     s1, s2 = e1.episode_stats(reduce=False), e2.episode_stats(reduce=False)
     assert s1["episodes"] == s2["episodes"] > 0
     assert abs(s1["reward"] - s2["reward"]) <= 1e-9 * abs(s1["reward"])  # atomic order differs
