@@ -8,11 +8,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
-ABI_VERSION = 12
+ABI_VERSION = 13
 REC_BYTES = 80
 MAX_POLY_VERTS = 192
 STATUS_REC_OVERFLOW = 1
-NAV_W = 16
+NAV_W = 24
 N_STATS = 16
 STAT_NAMES = [
     "episodes",

@@ -308,7 +308,10 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
     }
     cnt = min(cnt + nw, batch.rec_cap);
   }
-  if (store && sub == 0) batch.rec_cnt[e] = cnt;
+  if (store && sub == 0) {
+    batch.rec_cnt[e] = cnt;
+    batch.nav[(long long)e * AUV_NAV_W + NAV_CNT] = (double)cnt;
+  }
 }
 
 // BaseEnvironment._update (OBST) + Vessel.step (DYN) + Vessel.navigate + the culling stage, a
@@ -406,28 +409,21 @@ struct __align__(16) WarpSmem {
   int voff[RROUND + 1];
   int pad;
 };
-// lanes of the per-env scalar pack (one register per lane, read back by shuffle): lanes
-// 0..AUV_NAV_W-1 hold the navigation record
-#define SC_STATE 16  // x, y, psi
-#define SC_CUM 19
-#define SC_CTE 20
-#define SC_TSTEP 21
-#define SC_SCN 22
-#define SC_CNT 23
+// per-env scalar pack: lane k < AUV_NAV_W holds nav[e][k] (one register per lane, read back by
+// shuffle); the navigation kernel put everything the casting stage needs into that record
+#define SC_STATE NAV_X  // x, y, psi
+#define SC_CUM NAV_CUM
+#define SC_CTE NAV_CTE
+#define SC_TSTEP NAV_TSTEP
+#define SC_SCN NAV_SCN
+#define SC_CNT NAV_CNT
 
-// one round trip per env: every per-env scalar is fetched by a different lane, and the first
-// RROUND records are fetched speculatively (30 lanes x 16 B) before their count is known
+// one round trip per env: the env's navigation record (one coalesced 192 B load) and,
+// speculatively, its first RROUND obstacle records (30 lanes x 16 B) before their count is known
 __device__ __forceinline__ void lidar_fetch(const AuvConfig& cfg, const AuvBatch& batch, int e, int lane,
                                             double& sc, uint4& spec) {
-  const int n = batch.n_envs;
   sc = 0.0;
   if (lane < AUV_NAV_W) sc = batch.nav[(long long)e * AUV_NAV_W + lane];
-  else if (lane < SC_STATE + 3) sc = batch.state[(long long)(lane - SC_STATE) * n + e];
-  else if (lane == SC_CUM) sc = batch.cum_reward[e];
-  else if (lane == SC_CTE) sc = batch.cte_sum[e];
-  else if (lane == SC_TSTEP) sc = (double)batch.t_step[e];
-  else if (lane == SC_SCN) sc = (double)batch.scn_id[e];
-  else if (lane == SC_CNT) sc = cfg.use_lidar ? (double)batch.rec_cnt[e] : 0.0;
   spec = make_uint4(0, 0, 0, 0);
   if (cfg.use_lidar && lane < RROUND * 5 && lane / 5 < batch.rec_cap)
     spec = reinterpret_cast<const uint4*>(reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap)[lane];
@@ -512,7 +508,7 @@ __device__ __forceinline__ void lidar_env(const LidarArgs& A, WarpSmem& sm, floa
   float pen = (float)A.rays.weight_sum * A.pen_clear_ray;  // every ray clear; hit rays add their excess below
   unsigned long long ntests = 0;
   if (cfg.use_lidar) {
-    const int cnt = (int)SCAL(SC_CNT);
+    const int cnt = cfg.use_lidar ? (int)SCAL(SC_CNT) : 0;
     bool any_hit = false;
     if (cnt > 0) {
       const double px = SCAL(SC_STATE), py = SCAL(SC_STATE + 1), psi = SCAL(SC_STATE + 2);

@@ -25,6 +25,15 @@ namespace auv {
 #define NAV_REACHED 10
 #define NAV_COS_HEAD_ERR 11
 #define NAV_REWARD_BASE 12
+// hand-over to the casting stage (k_lidar reads lanes 0..AUV_NAV_W-1 of this record in one load)
+#define NAV_X 16
+#define NAV_Y 17
+#define NAV_PSI 18
+#define NAV_CUM 19
+#define NAV_CTE 20
+#define NAV_TSTEP 21
+#define NAV_SCN 22
+#define NAV_CNT 23
 
 // scipy PPoly evaluation (extrapolate=True): interval j with x[j] <= s < x[j+1], clamped.
 __device__ __forceinline__ void pchip_eval(const AuvPathBank& pb, int pid, double s, double& px,
@@ -293,6 +302,14 @@ __device__ __forceinline__ void navigate_env(const AuvConfig& cfg, const AuvPath
   o[NAV_REACHED] = reached ? 1.0 : 0.0;
   o[NAV_COS_HEAD_ERR] = cos_he;
   o[NAV_REWARD_BASE] = base;
+  o[NAV_X] = px;
+  o[NAV_Y] = py;
+  o[NAV_PSI] = psi;
+  o[NAV_CUM] = batch.cum_reward[e];
+  o[NAV_CTE] = batch.cte_sum[e];
+  o[NAV_TSTEP] = (double)batch.t_step[e];
+  o[NAV_SCN] = (double)batch.scn_id[e];
+  o[NAV_CNT] = 0.0;  // the culling stage overwrites it
   if (obs_row != nullptr) {  // [u, v, r, look-ahead heading error, heading error, cross-track / 100]
     obs_row[0] = (float)fmin(fmax(vu, -1.0), 1.0);
     obs_row[1] = (float)fmin(fmax(vv, -1.0), 1.0);

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 12
+#define AUV_ABI_VERSION 13
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -58,7 +58,7 @@ extern "C" {
 #define AUV_MAX_OBSTACLES 1024 /* moving + static slots per env */
 #define AUV_PATH_BLOCK 32     /* polyline segments per projection block */
 #define AUV_PATH_SUPER 32     /* blocks per projection superblock */
-#define AUV_NAV_W 16          /* doubles per env in AuvBatch.nav (one 128 B line) */
+#define AUV_NAV_W 24          /* doubles per env in AuvBatch.nav */
 #define AUV_REC_BYTES 80      /* bytes per obstacle record in AuvBatch.rec */
 #define AUV_MAX_POLY_VERTS 192 /* vertices of one world polygon incl. the closing one */
 #define AUV_STATUS_REC_OVERFLOW 1 /* AuvBatch.status bit: more nearby obstacles than rec_cap */
@@ -184,7 +184,10 @@ typedef struct AuvBatch {
                              look_ahead_heading_error, heading_error, goal_distance, progress,
                              cos psi, sin psi, reached_goal, cos(heading_error), [12] the part of
                              the reward that does not depend on the LiDAR (rewarder.py:216-239
-                             without the closeness term / rewarder.py:118-140), [13..15] unused */
+                             without the closeness term / rewarder.py:118-140), [13..15] unused,
+                             [16..23] hand-over to the casting stage: x, y, psi, cumulative
+                             reward, cte sum, t_step, scenario id, record count (one coalesced
+                             load per env instead of eight scattered ones)                     */
   /* scratch between the culling stage and the ray-casting stage (opaque to the caller) */
   void* rec;              /* [N][rec_cap][AUV_REC_BYTES] obstacle records, 16-byte aligned       */
   int32_t* rec_cnt;       /* [N] records of each env                                            */
