@@ -34,28 +34,46 @@
 
 namespace auv {
 
-// moving-obstacle update of one (env, slot)   obstacles.py:195-215
-__device__ __forceinline__ void obstacle_update_slot(const AuvConfig& cfg, const AuvScenarioPool& pool,
-                                                     const AuvBatch& batch, long long pe, long long ps) {
-  const double w = pool.mov_width[ps];
-  if (!(w > 0.0)) return;
+// moving-obstacle update of one (env, slot)   obstacles.py:195-215.  Split into the loads that
+// do not depend on each other (one round trip), the velocity lookup (second round trip) and the
+// stores, so that callers can keep several slots in flight.
+struct ObstLoad {
+  double w, counter;
+  int4 tr;  // vel_off, vel_len, vel_stride, 0
+  double2 pos;
+};
+__device__ __forceinline__ ObstLoad obstacle_load(const AuvScenarioPool& pool, const AuvBatch& batch, long long pe,
+                                                  long long ps) {
+  ObstLoad o;
+  o.w = pool.mov_width[ps];
+  o.counter = batch.mov_counter[pe];
+  o.tr = reinterpret_cast<const int4*>(pool.mov_track)[ps];
+  o.pos = reinterpret_cast<const double2*>(batch.mov_pos)[pe];
+  return o;
+}
+__device__ __forceinline__ void obstacle_finish(const AuvConfig& cfg, const AuvScenarioPool& pool, const AuvBatch& batch,
+                                                long long pe, long long ps, ObstLoad o) {
+  if (!(o.w > 0.0)) return;
   const double dt = cfg.t_step_size;
-  double counter = batch.mov_counter[pe] + dt;
+  double counter = o.counter + dt;
   int index = (int)floor(counter);
-  const int4 tr = reinterpret_cast<const int4*>(pool.mov_track)[ps];  // off, len, stride
-  double2 pos = reinterpret_cast<double2*>(batch.mov_pos)[pe];
-  if (index >= tr.y - 1) {
+  double2 pos = o.pos;
+  if (index >= o.tr.y - 1) {
     counter = 0.0;
     index = 0;
     pos = reinterpret_cast<const double2*>(pool.mov_start)[ps];
   }
-  const double2 v = reinterpret_cast<const double2*>(pool.vel_table)[tr.x + (long long)index * tr.z];
+  const double2 v = reinterpret_cast<const double2*>(pool.vel_table)[o.tr.x + (long long)index * o.tr.z];
   const double dx = dt * v.x, dy = dt * v.y;
   pos.x += dx;
   pos.y += dy;
   reinterpret_cast<double2*>(batch.mov_pos)[pe] = pos;
   reinterpret_cast<double2*>(batch.mov_disp)[pe] = make_double2(dx, dy);
   batch.mov_counter[pe] = counter;
+}
+__device__ __forceinline__ void obstacle_update_slot(const AuvConfig& cfg, const AuvScenarioPool& pool,
+                                                     const AuvBatch& batch, long long pe, long long ps) {
+  obstacle_finish(cfg, pool, batch, pe, ps, obstacle_load(pool, batch, pe, ps));
 }
 
 // ------------------------------------------------------------------------------------
@@ -348,8 +366,16 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
   const int scn = batch.scn_id[e];
   if (OBST) {  // the group's lanes take the env's moving-obstacle slots
     const int km = pool.k_moving;
-    if (store)
-      for (int j = sub; j < km; j += G) obstacle_update_slot(cfg, pool, batch, (long long)e * km + j, (long long)scn * km + j);
+    if (store) {
+      const long long pe0 = (long long)e * km, ps0 = (long long)scn * km;
+      for (int j = sub; j < km; j += 2 * G) {  // two slots in flight per lane
+        const bool two = j + G < km;
+        const ObstLoad a = obstacle_load(pool, batch, pe0 + j, ps0 + j);
+        const ObstLoad b = obstacle_load(pool, batch, pe0 + (two ? j + G : j), ps0 + (two ? j + G : j));
+        obstacle_finish(cfg, pool, batch, pe0 + j, ps0 + j, a);
+        if (two) obstacle_finish(cfg, pool, batch, pe0 + j + G, ps0 + j + G, b);
+      }
+    }
   }
   S6 y = load_state(batch.state, n, e);
   int step_counter = batch.step_counter[e];

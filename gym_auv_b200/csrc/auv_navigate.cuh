@@ -35,22 +35,56 @@ namespace auv {
 #define NAV_SCN 22
 #define NAV_CNT 23
 
-// scipy PPoly evaluation (extrapolate=True): interval j with x[j] <= s < x[j+1], clamped.
-__device__ __forceinline__ void pchip_eval(const AuvPathBank& pb, int pid, double s, double& px,
-                                           double& py, double& dx, double& dy) {
+// scipy PPoly evaluation (extrapolate=True) at TWO arclengths at once: interval j with
+// x[j] <= s < x[j+1], clamped.  The knots are nearly uniform, so the interval is found among
+// the four knots around the uniform guess (one round of loads for both evaluations); the
+// sequential search only runs when it is not.  L = knots[n_knots - 1] (Path.length).
+struct PchipOut {
+  double px, py, dx, dy;
+};
+__device__ __forceinline__ int pchip_interval(const double* __restrict__ kn, int nk, double s, int j, double k0,
+                                              double k1, double k2, double k3) {
+  // k0..k3 = kn[j-1], kn[j], kn[j+1], kn[j+2] (clamped indices)
+  if (s < k1) {
+    if (j > 0) {
+      --j;
+      if (j > 0 && s < k0) {
+        --j;
+        while (j > 0 && s < kn[j]) --j;
+      }
+    }
+  } else if (j < nk - 2 && s >= k2) {
+    ++j;
+    if (j < nk - 2 && s >= k3) {
+      ++j;
+      while (j < nk - 2 && s >= kn[j + 1]) ++j;
+    }
+  }
+  return j;
+}
+__device__ __forceinline__ void pchip_eval2(const AuvPathBank& pb, int pid, double L, double s1, double s2,
+                                            PchipOut& o1, PchipOut& o2) {
   const int nk = pb.n_knots;
-  const double* kn = pb.knots + (long long)pid * nk;
-  const double L = kn[nk - 1];
-  int j = (int)((s / L) * (nk - 1));
-  j = max(0, min(nk - 2, j));
-  while (j > 0 && s < kn[j]) --j;
-  while (j < nk - 2 && s >= kn[j + 1]) ++j;
-  const double t = s - kn[j];
-  const double* c = pb.coef + ((long long)pid * (nk - 1) + j) * 8;
-  px = ((c[0] * t + c[1]) * t + c[2]) * t + c[3];
-  py = ((c[4] * t + c[5]) * t + c[6]) * t + c[7];
-  dx = (3.0 * c[0] * t + 2.0 * c[1]) * t + c[2];
-  dy = (3.0 * c[4] * t + 2.0 * c[5]) * t + c[6];
+  const double* __restrict__ kn = pb.knots + (long long)pid * nk;
+  int j1 = max(0, min(nk - 2, (int)((s1 / L) * (nk - 1))));
+  int j2 = max(0, min(nk - 2, (int)((s2 / L) * (nk - 1))));
+  const double a0 = kn[max(j1 - 1, 0)], a1 = kn[j1], a2 = kn[j1 + 1], a3 = kn[min(j1 + 2, nk - 1)];
+  const double b0 = kn[max(j2 - 1, 0)], b1 = kn[j2], b2 = kn[j2 + 1], b3 = kn[min(j2 + 2, nk - 1)];
+  j1 = pchip_interval(kn, nk, s1, j1, a0, a1, a2, a3);
+  j2 = pchip_interval(kn, nk, s2, j2, b0, b1, b2, b3);
+  const double2* __restrict__ c1 = reinterpret_cast<const double2*>(pb.coef + ((long long)pid * (nk - 1) + j1) * 8);
+  const double2* __restrict__ c2 = reinterpret_cast<const double2*>(pb.coef + ((long long)pid * (nk - 1) + j2) * 8);
+  const double t1 = s1 - kn[j1], t2 = s2 - kn[j2];
+  const double2 p0 = c1[0], p1 = c1[1], p2 = c1[2], p3 = c1[3];
+  const double2 q0 = c2[0], q1 = c2[1], q2 = c2[2], q3 = c2[3];
+  o1.px = ((p0.x * t1 + p0.y) * t1 + p1.x) * t1 + p1.y;
+  o1.py = ((p2.x * t1 + p2.y) * t1 + p3.x) * t1 + p3.y;
+  o1.dx = (3.0 * p0.x * t1 + 2.0 * p0.y) * t1 + p1.x;
+  o1.dy = (3.0 * p2.x * t1 + 2.0 * p2.y) * t1 + p3.x;
+  o2.px = ((q0.x * t2 + q0.y) * t2 + q1.x) * t2 + q1.y;
+  o2.py = ((q2.x * t2 + q2.y) * t2 + q3.x) * t2 + q3.y;
+  o2.dx = (3.0 * q0.x * t2 + 2.0 * q0.y) * t2 + q1.x;
+  o2.dy = (3.0 * q2.x * t2 + 2.0 * q2.y) * t2 + q3.x;
 }
 
 // exact squared distance from P to segment AB (GEOS Distance::pointToSegment, squared;
@@ -126,12 +160,20 @@ __device__ __forceinline__ double project_group(const AuvPathBank& pb, int pid, 
   if ((d2) < ub * ub) ub = fminf(ub, sqrtf(d2) * up + (dv) + pad);
 #define AUV_PRUNED(d2, dv) ((d2) * dn2 > (ub + (dv) + pad) * (ub + (dv) + pad))
   // pass A: upper bound over the superblocks
-  for (int g0 = 0; g0 < nsb; g0 += G) {
-    const int i = min(g0 + sub, nsb - 1);
-    const float4 ch = sbc[i];
-    const float2 ax = sba[i];
-    const float d2 = pt_chord_d2_f(qx, qy, ch, ax.x);
-    AUV_TIGHTEN(d2, ax.y)
+  for (int g0 = 0; g0 < nsb; g0 += 4 * G) {  // four rounds of loads in flight
+    float4 ch[4];
+    float2 ax[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = min(g0 + k * G + sub, nsb - 1);
+      ch[k] = sbc[i];
+      ax[k] = sba[i];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d2 = pt_chord_d2_f(qx, qy, ch[k], ax[k].x);
+      AUV_TIGHTEN(d2, ax[k].y)
+    }
   }
   ub = group_min<G>(gm, ub);
   const double2* poly = reinterpret_cast<const double2*>(pb.poly_xy) + v0;
@@ -251,9 +293,10 @@ __device__ __forceinline__ void navigate_env(const AuvConfig& cfg, const AuvPath
                                              float* __restrict__ obs_row, const bool store) {
   const double L = pb.length[pid];
   const double s_la = fmin(L, s + cfg.look_ahead_distance);
-  double p_x, p_y, d_x, d_y, l_x, l_y, ldx, ldy;
-  pchip_eval(pb, pid, s, p_x, p_y, d_x, d_y);
-  pchip_eval(pb, pid, s_la, l_x, l_y, ldx, ldy);
+  PchipOut at_s, at_la;
+  pchip_eval2(pb, pid, L, s, s_la, at_s, at_la);
+  const double p_x = at_s.px, p_y = at_s.py, d_x = at_s.dx, d_y = at_s.dy;
+  const double l_x = at_la.px, l_y = at_la.py, ldx = at_la.dx, ldy = at_la.dy;
   const double chi = (double)atan2f((float)d_y, (float)d_x);  // diagnostic only (nav[NAV_CHI])
   // cross-track error = second row of Rz(-chi) applied to (path(s) - p); cos/sin(chi) are the
   // normalised derivative (no trig needed)
