@@ -415,6 +415,51 @@ def run_ours(args):
                         "note": "rank-0 link; the e2e step is bound by the D2H of the observations "
                                 "(pinned host memory); frac = D2H-only time / e2e step time"}}
 
+    # ---- e2e, asynchronous interface: two env groups of N/2 stepped alternately with
+    #      step_async / step_wait (stable-baselines' VecEnv interface) so that one group's
+    #      observations travel while the other group is computed.  Same env count, same host
+    #      buffers, every step's actions come from host memory and every observation lands there.
+    if e2e is not None and N >= 128:
+        half = N // 2
+        shared = dict(ray=env._ray, bank=env._bank, pool=env._pool)
+        groups = [AUVVecEnv(scn, half, cfg, device=device, test_mode=False, auto_reset=True, env_offset=o,
+                            host_chunks=max(1, args.host_chunks // 2), _shared=shared) for o in (0, half)]
+        for g in groups:
+            g.reset()
+        ah = [[a[:half].copy() for a in acts_np], [a[half:2 * half].copy() for a in acts_np]]
+        for g, a in zip(groups, ah):
+            g.step_async(a[0])
+        for i in range(3):  # warm-up (graph capture happens here)
+            for g, a in zip(groups, ah):
+                g.step_wait()
+                g.step_async(a[i % 4])
+        for g in groups:
+            g.step_wait()
+        barrier()
+        t0 = time.perf_counter()
+        for g, a in zip(groups, ah):
+            g.step_async(a[0])
+        for i in range(ke):
+            for g, a in zip(groups, ah):
+                g.step_wait()
+                g.step_async(a[(i + 1) % 4])
+        for g in groups:
+            g.step_wait()
+        dt = time.perf_counter() - t0
+        t_a = torch.tensor([dt], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_a, op=dist.ReduceOp.MAX)
+        a_ms = 1e3 * float(t_a.item()) / (ke + 1)
+        sync_part = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "host_chunks": e2e["host_chunks"],
+                     "call": "AUVVecEnv.step_host (one synchronous call per step)"}
+        e2e.update({"value": world * 2 * half * (ke + 1) / float(t_a.item()), "ms_per_step": a_ms, "steps": ke + 1,
+                    "mode": "AUVVecEnv.step_async / step_wait, two groups of N/2 envs stepped alternately",
+                    "host_chunks": groups[0].host_chunks, "sync": sync_part})
+        e2e["pcie"]["frac_of_link_bound"] = e2e["pcie"]["d2h_only_ms_per_step"] / a_ms
+        for g in groups:
+            g.close()
+        del groups
+
     stats = env.episode_stats(reduce=True)  # the only collective on the path (NCCL all-reduce)
 
     if rank != 0:

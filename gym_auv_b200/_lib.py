@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
-ABI_VERSION = 13
+ABI_VERSION = 14
 REC_BYTES = 80
 MAX_POLY_VERTS = 192
 STATUS_REC_OVERFLOW = 1
@@ -181,6 +181,7 @@ EXPORTS = [
     "auv_pipeline_graph_state",
     "auv_step_chunked",
     "auv_step_host_chunked",
+    "auv_step_host_submit",
 ]
 
 _lib = None
@@ -235,6 +236,7 @@ def load():
         P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, _vp, P(AuvStepOut),
         _vp, _vp, _vp, _vp, _vp, C.c_int,
     ]
+    lib.auv_step_host_submit.argtypes = lib.auv_step_host_chunked.argtypes
     lib.auv_timer_create.argtypes = [C.c_int]
     lib.auv_timer_create.restype = _vp
     lib.auv_timer_destroy.argtypes = [_vp]

@@ -1296,14 +1296,22 @@ int auv_step_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPat
   return step_chunked(cfg, rays, paths, pool, batch, actions, out, stream, p, n_chunks);
 }
 
+int auv_step_host_submit(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                         const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
+                         float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
+                         uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks) {
+  if (!cfg || !batch || !out || !actions_host || !actions_dev || !obs_host || !reward_host || !done_host)
+    return set_err(AUV_EINVAL, "NULL argument");
+  return step_host_chunked(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, obs_host, reward_host,
+                           done_host, stream, p, n_chunks);
+}
+
 int auv_step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                           const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
                           float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
                           uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks) {
-  if (!cfg || !batch || !out || !actions_host || !actions_dev || !obs_host || !reward_host || !done_host)
-    return set_err(AUV_EINVAL, "NULL argument");
-  if (int rc = step_host_chunked(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, obs_host, reward_host,
-                                 done_host, stream, p, n_chunks))
+  if (int rc = auv_step_host_submit(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, obs_host, reward_host,
+                                    done_host, stream, p, n_chunks))
     return rc;
   return cuda_check(cudaStreamSynchronize((cudaStream_t)stream), "sync");
 }

@@ -383,15 +383,7 @@ class AUVVecEnv:
     def step_host(self, actions: np.ndarray):
         """NumPy in / NumPy out: the call a CPU-side VecEnv consumer makes (the e2e
         path).  Copies actions H2D and obs/reward/done D2H through pinned buffers."""
-        N = self.num_envs
-        if self._pinned is None:
-            self._pinned = dict(
-                act=torch.zeros((N, 2), dtype=torch.float32).pin_memory(),
-                obs=torch.zeros((N, self.obs_dim), dtype=torch.float32).pin_memory(),
-                reward=torch.zeros(N, dtype=torch.float32).pin_memory(),
-                done=torch.zeros(N, dtype=torch.uint8).pin_memory(),
-            )
-        pin = self._pinned
+        pin = self.step_host_buffers()
         pin["act"].numpy()[...] = actions
         cfg, rays, paths, pool, batch = self._refs()
         with torch.cuda.device(self.device):
@@ -404,6 +396,58 @@ class AUVVecEnv:
                 _lib.check(self.lib.auv_step_host(*hargs), "auv_step_host")
         self.total_steps += 1
         return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy()
+
+    # stable-baselines' asynchronous VecEnv interface (vec_env/base_vec_env.py: step_async /
+    # step_wait): the step is submitted on a stream owned by this env; step_wait blocks on it.
+    # Two env groups stepped alternately (wait A, submit A, wait B, submit B, ...) keep the
+    # D2H link busy: one group's observations travel while the other group is computed.
+    def step_async(self, actions: np.ndarray):
+        if getattr(self, "_async_pending", False):
+            raise RuntimeError("step_async() called twice without step_wait()")
+        if self._pinned is None:
+            self.step_host_buffers()
+        if self._pipe is None:
+            with torch.cuda.device(self.device):
+                self._pipe = self.lib.auv_pipeline_create(2)
+            self.chunk_streams = 2
+        if getattr(self, "_async_stream", None) is None:
+            self._async_stream = torch.cuda.Stream(device=self.device)
+            self._async_done = torch.cuda.Event()
+        pin = self._pinned
+        pin["act"].numpy()[...] = actions
+        cfg, rays, paths, pool, batch = self._refs()
+        cur = torch.cuda.current_stream(self.device)
+        self._async_stream.wait_stream(cur)  # earlier work of this env (reset, step) is ordered before
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.auv_step_host_submit(
+                cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
+                C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.c_void_p(pin["obs"].data_ptr()),
+                C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()),
+                C.c_void_p(self._async_stream.cuda_stream), self._pipe, max(1, self.host_chunks)), "auv_step_host_submit")
+        self._async_done.record(self._async_stream)
+        self._async_pending = True
+        self.total_steps += 1
+
+    def step_wait(self):
+        if not getattr(self, "_async_pending", False):
+            raise RuntimeError("step_wait() without a pending step_async()")
+        self._async_done.synchronize()
+        torch.cuda.current_stream(self.device).wait_event(self._async_done)
+        self._async_pending = False
+        pin = self._pinned
+        return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy()
+
+    def step_host_buffers(self):
+        """Pinned host buffers of step_host / step_async (actions in; obs, reward, done out)."""
+        N = self.num_envs
+        if self._pinned is None:
+            self._pinned = dict(
+                act=torch.zeros((N, 2), dtype=torch.float32).pin_memory(),
+                obs=torch.zeros((N, self.obs_dim), dtype=torch.float32).pin_memory(),
+                reward=torch.zeros(N, dtype=torch.float32).pin_memory(),
+                done=torch.zeros(N, dtype=torch.uint8).pin_memory(),
+            )
+        return self._pinned
 
     @property
     def h2d_bytes_per_step(self) -> int:

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 13
+#define AUV_ABI_VERSION 14
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -289,6 +289,14 @@ int auv_step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const A
                           const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
                           float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
                           uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks);
+/* auv_step_host_chunked without the final synchronise: the step is only submitted to `stream`;
+ * the host buffers are valid once `stream` has drained (VecEnv.step_async / step_wait,
+ * stable-baselines' asynchronous interface).  Two env groups on two streams keep the link busy:
+ * group A's observations travel while group B is computed. */
+int auv_step_host_submit(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                         const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
+                         float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
+                         uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks);
 /* Per-kernel CUDA-event timing of a step on the launching stream (used by bench.py for the
  * roofline of the dominant kernel).  A timer holds `capacity` slots of 4 events. */
 typedef struct AuvTimer AuvTimer;

@@ -496,6 +496,44 @@ def test_counting_variant_equals_product_variant():
     assert int(e1._out["seg_tests"].item()) > 0
 
 
+def test_step_async_two_groups_equals_sync():
+    """step_async / step_wait (stable-baselines' asynchronous VecEnv interface): two env groups
+    stepped alternately on their own streams give exactly the synchronous results."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    cfg.episode.max_timesteps = 11
+    n = 130
+    scn = S.moving_obstacles(2 * n, 5, 5, seed=33)
+    ref = AUVVecEnv(scn, 2 * n, cfg, auto_reset=True)
+    ga = AUVVecEnv(scn, n, cfg, auto_reset=True, env_offset=0, host_chunks=2)
+    gb = AUVVecEnv(scn, n, cfg, auto_reset=True, env_offset=n, host_chunks=3)
+    ref.reset(), ga.reset(), gb.reset()
+    acts = random_actions(20, 2 * n, 8).astype(np.float32)
+    ga.step_async(acts[0, :n])
+    gb.step_async(acts[0, n:])
+    with pytest.raises(RuntimeError):
+        ga.step_async(acts[0, :n])
+    for t in range(20):
+        o, r, d, _ = ref.step(torch.as_tensor(acts[t], device="cuda"))
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+        oa, ra, da = (x.copy() for x in ga.step_wait())
+        if t + 1 < 20:
+            ga.step_async(acts[t + 1, :n])  # group A's next step is in flight while B is read
+        ob, rb, db = (x.copy() for x in gb.step_wait())
+        if t + 1 < 20:
+            gb.step_async(acts[t + 1, n:])
+        # a pool of 2n scenarios shared by two groups of n: env i of group B is env n + i of ref
+        # only until its first reset (ref moves on by 2n scenarios, the groups by n)
+        fresh_a = ga.get_attr("episode").cpu().numpy() == 0
+        fresh_b = gb.get_attr("episode").cpu().numpy() == 0
+        assert np.array_equal(oa[fresh_a], o[:n][fresh_a]) and np.array_equal(ra[fresh_a], r[:n][fresh_a])
+        assert np.array_equal(ob[fresh_b], o[n:][fresh_b]) and np.array_equal(db[fresh_b], d[n:][fresh_b])
+    with pytest.raises(RuntimeError):
+        ga.step_wait()
+    assert (~fresh_a).any(), "fixture should contain resets"
+
+
 def test_bad_shapes_raise():
     from gym_auv_b200.vec_env import AUVVecEnv
 
