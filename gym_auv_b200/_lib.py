@@ -8,10 +8,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
-ABI_VERSION = 14
+ABI_VERSION = 15
 REC_BYTES = 80
 MAX_POLY_VERTS = 192
 STATUS_REC_OVERFLOW = 1
+STATUS_GEN_GAVE_UP = 2
 NAV_W = 24
 N_STATS = 16
 STAT_NAMES = [
@@ -159,6 +160,23 @@ class AuvStepOut(C.Structure):
     ]
 
 
+class AuvGenParams(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64),
+        ("epoch", C.c_uint32),
+        ("post_generate_update", C.c_int32),
+        ("t_step_size", C.c_double),
+        ("vessel_width", C.c_double),
+        ("init_pos_jitter", C.c_double),
+        ("mov_disp_std", C.c_double),
+        ("mov_width_mean", C.c_double),
+        ("mov_speed_lo", C.c_double),
+        ("mov_speed_hi", C.c_double),
+        ("st_disp_std", C.c_double),
+        ("st_radius_mean", C.c_double),
+    ]
+
+
 EXPORTS = [
     "auv_abi_version",
     "auv_sizeof",
@@ -182,6 +200,7 @@ EXPORTS = [
     "auv_step_chunked",
     "auv_step_host_chunked",
     "auv_step_host_submit",
+    "auv_generate_moving_obstacles",
 ]
 
 _lib = None
@@ -237,6 +256,7 @@ def load():
         _vp, _vp, _vp, _vp, _vp, C.c_int,
     ]
     lib.auv_step_host_submit.argtypes = lib.auv_step_host_chunked.argtypes
+    lib.auv_generate_moving_obstacles.argtypes = [P(AuvGenParams), P(AuvPathBank), P(AuvScenarioPool), _vp, C.c_int, _vp, _vp]
     lib.auv_timer_create.argtypes = [C.c_int]
     lib.auv_timer_create.restype = _vp
     lib.auv_timer_destroy.argtypes = [_vp]
@@ -251,7 +271,7 @@ def load():
     if ver != ABI_VERSION:
         raise AuvLibraryError(f"ABI mismatch: library {ver}, binding {ABI_VERSION}; rebuild")
     lib.auv_sizeof.argtypes = [C.c_int]
-    for i, st in enumerate([AuvConfig, AuvRayTable, AuvPathBank, AuvScenarioPool, AuvBatch, AuvStepOut]):
+    for i, st in enumerate([AuvConfig, AuvRayTable, AuvPathBank, AuvScenarioPool, AuvBatch, AuvStepOut, AuvGenParams]):
         if lib.auv_sizeof(i) != C.sizeof(st):
             raise AuvLibraryError(f"struct layout mismatch for {st.__name__}: C {lib.auv_sizeof(i)} vs ctypes {C.sizeof(st)}")
     _lib = lib

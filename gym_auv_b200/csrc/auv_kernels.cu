@@ -28,6 +28,7 @@
 #include "auv_dynamics.cuh"
 #include "auv_geometry.cuh"
 #include "auv_navigate.cuh"
+#include "auv_generate.cuh"
 #include "../../include/auv_b200.h"
 
 #include <math.h>
@@ -918,6 +919,7 @@ int auv_sizeof(int which) {
     case 3: return (int)sizeof(AuvScenarioPool);
     case 4: return (int)sizeof(AuvBatch);
     case 5: return (int)sizeof(AuvStepOut);
+    case 6: return (int)sizeof(AuvGenParams);
     default: return AUV_EINVAL;
   }
 }
@@ -1387,6 +1389,25 @@ int auv_step_host(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBa
   if (int rc = cuda_check(cudaMemcpyAsync(done_host, out->done, n, cudaMemcpyDeviceToHost, s), "D2H done"))
     return rc;
   return cuda_check(cudaStreamSynchronize(s), "sync");
+}
+
+int auv_generate_moving_obstacles(const AuvGenParams* gp, const AuvPathBank* paths, const AuvScenarioPool* pool,
+                                  const int32_t* ids, int n_ids, int32_t* status, void* stream) {
+  if (!gp || !paths || !pool) return set_err(AUV_EINVAL, "NULL argument");
+  if (n_ids <= 0 || (!ids && n_ids > pool->n_scenarios)) return set_err(AUV_EINVAL, "n_ids out of range");
+  if (paths->n_paths <= 0) return set_err(AUV_EINVAL, "empty path bank");
+  if (pool->k_moving < 0 || pool->k_static < 0) return set_err(AUV_EINVAL, "negative slot count");
+  if (!pool->path_id || !pool->vessel_init) return set_err(AUV_EINVAL, "pool.path_id / vessel_init is NULL");
+  if (pool->k_moving > 0 && (!pool->mov_start || !pool->mov_width || !pool->mov_track || !pool->vel_table ||
+                             !pool->mov_pos0 || !pool->mov_disp0 || !pool->mov_counter0))
+    return set_err(AUV_EINVAL, "moving-obstacle arrays are NULL");
+  if (pool->k_static > 0 && (!pool->st_pos || !pool->st_radius)) return set_err(AUV_EINVAL, "static-obstacle arrays are NULL");
+  const long long total = (long long)n_ids * (pool->k_moving + pool->k_static + 1);
+  const int threads = 128;
+  const long long blocks = (total + threads - 1) / threads;
+  auv::k_generate_moving_obstacles<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*gp, *paths, *pool, ids, n_ids,
+                                                                                          status);
+  return cuda_check(cudaGetLastError(), "k_generate_moving_obstacles");
 }
 
 int auv_fma_probe(float* sink, int blocks, int threads, int iters, void* stream, double* flops_out) {

@@ -133,8 +133,18 @@ __device__ __forceinline__ unsigned group_ballot(unsigned gm, int lane, bool pre
 // compared in the squared domain (one sqrt only when a bound improves).  The arg-min is
 // lexicographic in (distance, segment index), which is GEOS's "first minimum wins"
 // independent of visiting order.  Every lane returns the same arclength.
+#ifdef AUV_NOINLINE_PROJECT
+#define AUV_PROJECT_INLINE __noinline__
+#else
+#define AUV_PROJECT_INLINE __forceinline__
+#endif
+#ifdef AUV_NOINLINE_NAVIGATE
+#define AUV_NAVIGATE_INLINE __noinline__
+#else
+#define AUV_NAVIGATE_INLINE __forceinline__
+#endif
 template <int G>
-__device__ __forceinline__ double project_group(const AuvPathBank& pb, int pid, double px, double py,
+__device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, int pid, double px, double py,
                                                 const int lane, const unsigned gm) {
   constexpr int KB = AUV_PATH_SUPER / G;  // blocks of a superblock per lane
   constexpr int KS = AUV_PATH_BLOCK / G;  // segments of a block per lane
@@ -287,7 +297,7 @@ __device__ __forceinline__ double project_group(const AuvPathBank& pb, int pid, 
 // the LiDAR-independent part of the reward (rewarder.py:78-140,167-241).
 // `s` is the projected arclength (project_group); every lane of the env's group computes the
 // same scalars, `store` is true for the one lane that writes them.
-__device__ __forceinline__ void navigate_env(const AuvConfig& cfg, const AuvPathBank& pb,
+__device__ AUV_NAVIGATE_INLINE void navigate_env(const AuvConfig& cfg, const AuvPathBank& pb,
                                              const AuvBatch& batch, int pid, int e, const double s, double px,
                                              double py, double psi, double vu, double vv, double vr,
                                              float* __restrict__ obs_row, const bool store) {

@@ -125,7 +125,8 @@ class AUVVecEnv:
         self.lib = _lib.load()
         self.config = config.copy() if config is not None else Config()
         self.scenarios = scenarios
-        scenarios.validate()
+        if _shared is None:
+            scenarios.validate()
         self.num_envs = N = int(num_envs)
         self.test_mode = test_mode
         self.debug = debug
@@ -168,8 +169,9 @@ class AUVVecEnv:
         mw = max(1, (Km + Ks + scenarios.world.n + 31) // 32)
         if mw > 32:
             raise ValueError("at most 1024 obstacle slots (moving + static + world polygons) per env")
-        pos0, disp0, counter0 = scenarios.initial_obstacle_state(float(self.config.simulation.t_step_size))
-        vel = scenarios.vel_table if len(scenarios.vel_table) else np.zeros((1, 2))
+        if _shared is None:
+            pos0, disp0, counter0 = scenarios.initial_obstacle_state(float(self.config.simulation.t_step_size))
+            vel = scenarios.vel_table if len(scenarios.vel_table) else np.zeros((1, 2))
         self._pool = _shared["pool"] if _shared is not None else dict(
             path_id=t(scenarios.path_id, torch.int32),
             vessel_init=t(scenarios.vessel_init, torch.float64),
@@ -293,24 +295,101 @@ class AUVVecEnv:
         if auto_reset and _shared is None:
             self._build_reset_cache()
 
-    def _build_reset_cache(self, chunk: int = 65536):
+    def _build_reset_cache(self, ids: Optional[torch.Tensor] = None, chunk: int = 65536):
         """reset() of scenario m always returns the same observation (it depends on the
         scenario only), so it is computed once per pool scenario -- by the same kernels, over a
         temporary batch that shares this env's device tables -- and the in-step auto-reset of a
-        finished env becomes a copy (pool.reset_obs / reset_max_progress / reset_mask)."""
+        finished env becomes a copy (pool.reset_obs / reset_max_progress / reset_mask).
+        ``ids``: int tensor of pool scenarios to (re)compute, default all."""
         M = self.scenarios.n_scenarios
         shared = dict(ray=self._ray, bank=self._bank, pool=self._pool)
-        for start in range(0, M, chunk):
-            n = min(chunk, M - start)
+        total = M if ids is None else int(ids.numel())
+        for start in range(0, total, chunk):
+            n = min(chunk, total - start)
             tmp = AUVVecEnv(self.scenarios, n, self.config, device=self.device, test_mode=self.test_mode,
                             auto_reset=False, cull_mode=self._cull_mode, env_offset=start,
                             max_nearby=self._max_nearby, _shared=shared)
+            if ids is None:
+                sel = slice(start, start + n)
+            else:
+                sel = ids[start:start + n].to(self.device, torch.int64)
+                tmp._st["scn_id"].copy_(sel.to(torch.int32))
             obs = tmp.reset()
-            self._pool["reset_obs"][start:start + n].copy_(obs)
-            self._pool["reset_max_progress"][start:start + n].copy_(tmp._st["max_progress"])
-            self._pool["reset_mask"][start:start + n].copy_(tmp._st["nearby_mask"])
+            self._pool["reset_obs"][sel] = obs
+            self._pool["reset_max_progress"][sel] = tmp._st["max_progress"]
+            self._pool["reset_mask"][sel] = tmp._st["nearby_mask"]
             del tmp
         torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------ GPU-side scenario generation
+    def gen_params(self, seed: int, epoch: int) -> "_lib.AuvGenParams":
+        v = self.config.vessel
+        return _lib.AuvGenParams(
+            seed=int(seed) & 0xFFFFFFFFFFFFFFFF, epoch=int(epoch) & 0xFFFFFFFF,
+            post_generate_update=int(bool(self.scenarios.post_generate_update)),
+            t_step_size=float(self.config.simulation.t_step_size), vessel_width=float(v.vessel_width),
+            init_pos_jitter=50.0, mov_disp_std=500.0, mov_width_mean=10.0, mov_speed_lo=1.0, mov_speed_hi=3.0,
+            st_disp_std=250.0, st_radius_mean=30.0,
+        )
+
+    def regenerate_scenarios(self, ids: Optional[torch.Tensor] = None, seed: int = 0, epoch: int = 1):
+        """Draw fresh MovingObstacles scenarios ON THE GPU (auv_generate_moving_obstacles:
+        movingobstacles.py:28-95 + helpers.py:5-35 with Philox streams keyed by (seed; scenario,
+        slot, epoch)) into the listed pool slots (default: all) and refill their cached first
+        observation.  Slots that a live env is running must not be listed -- see
+        ``refresh_finished``.  The host copy ``self.scenarios`` goes stale: ``pull_scenarios()``."""
+        M, Km = self.scenarios.n_scenarios, self.k_moving
+        if self.n_world:
+            raise NotImplementedError("scenario generation with a shared land-polygon world")
+        if Km and self._pool["vel_table"].shape[0] < M * Km:
+            raise ValueError("pool.vel_table must hold n_scenarios * k_moving entries (constant-velocity tracks)")
+        gp = self.gen_params(seed, epoch)
+        idp, n = None, M
+        if ids is not None:
+            ids = ids.to(self.device, torch.int32).contiguous()
+            idp, n = C.c_void_p(ids.data_ptr()), int(ids.numel())
+            if n == 0:
+                return 0
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.auv_generate_moving_obstacles(
+                C.byref(gp), C.byref(self.paths), C.byref(self.pool), idp, n,
+                C.c_void_p(self._scratch["status"].data_ptr()), self._stream()), "auv_generate_moving_obstacles")
+        self._build_reset_cache(ids)
+        self.check_status()
+        return n
+
+    def refresh_finished(self, seed: int = 0) -> int:
+        """Ping-pong scenario refresh for sustained training: with a pool of M = 2 N scenarios env
+        e alternates between slots e and e + N at every reset, so the slot it is NOT running is
+        free.  Every env that finished an episode since the last call gets a freshly generated
+        scenario in its free slot (the one its next reset moves to).  Returns how many."""
+        N, M = self.num_envs, self.scenarios.n_scenarios
+        if M != 2 * N or self.env_offset != 0:
+            raise ValueError("refresh_finished needs a pool of exactly 2 * num_envs scenarios and env_offset 0")
+        ep = self._st["episode"]
+        if getattr(self, "_seen_episode", None) is None:
+            self._seen_episode = torch.zeros_like(ep)
+            self._gen_epoch = 1
+        changed = torch.nonzero(ep != self._seen_episode).flatten()
+        self._seen_episode.copy_(ep)
+        if changed.numel() == 0:
+            return 0
+        free = (self._st["scn_id"][changed].to(torch.int64) + N) % M
+        self._gen_epoch += 1
+        return self.regenerate_scenarios(free, seed=seed, epoch=self._gen_epoch)
+
+    def pull_scenarios(self) -> ScenarioSet:
+        """Host copy of the device pool (after regenerate_scenarios), e.g. to replay generated
+        scenarios through the CPU oracle."""
+        import dataclasses
+
+        p = self._pool
+        h = lambda k: p[k].cpu().numpy().copy()
+        return dataclasses.replace(
+            self.scenarios, path_id=h("path_id"), vessel_init=h("vessel_init"), mov_start=h("mov_start"),
+            mov_width=h("mov_width"), mov_track=h("mov_track"), vel_table=h("vel_table"), st_pos=h("st_pos"),
+            st_radius=h("st_radius"), _bank=self.scenarios.bank, _world=self.scenarios._world,
+        )
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -323,6 +402,8 @@ class AUVVecEnv:
         """Raise if a kernel flagged a problem (synchronises).  Called by reset() and
         episode_stats(); call it yourself after long unattended runs."""
         st = int(self._scratch["status"].item())
+        if st & _lib.STATUS_GEN_GAVE_UP:
+            raise RuntimeError("scenario generator: an obstacle slot was still rejected after 100000 draws")
         if st & _lib.STATUS_REC_OVERFLOW:
             raise RuntimeError(
                 f"more than max_nearby={self.rec_cap} obstacles were within sensor range of one env: "

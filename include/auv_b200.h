@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 14
+#define AUV_ABI_VERSION 15
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -62,6 +62,7 @@ extern "C" {
 #define AUV_REC_BYTES 80      /* bytes per obstacle record in AuvBatch.rec */
 #define AUV_MAX_POLY_VERTS 192 /* vertices of one world polygon incl. the closing one */
 #define AUV_STATUS_REC_OVERFLOW 1 /* AuvBatch.status bit: more nearby obstacles than rec_cap */
+#define AUV_STATUS_GEN_GAVE_UP 2  /* scenario generator: an obstacle was placed after 100000 rejections */
 
 /* gym_auv/config.py field names (EpisodeConfig/SimulationConfig/VesselConfig).  POD. */
 typedef struct AuvConfig {
@@ -235,7 +236,7 @@ typedef struct AuvStepOut {
 
 int auv_abi_version(void);
 /* sizeof of the ABI structs, in declaration order (0 AuvConfig, 1 AuvRayTable, 2 AuvPathBank,
- * 3 AuvScenarioPool, 4 AuvBatch, 5 AuvStepOut) so a binding can verify its layout. */
+ * 3 AuvScenarioPool, 4 AuvBatch, 5 AuvStepOut, 6 AuvGenParams) so a binding can verify its layout. */
 int auv_sizeof(int which);
 const char* auv_last_error(void);
 int auv_obs_dim(const AuvConfig* cfg);
@@ -308,6 +309,37 @@ int auv_step_timed(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathB
                    AuvStepOut* out, void* stream, AuvTimer* t, int slot);
 /* after the stream is synchronised: ms[0..2] = obstacle_update, vessel_nav, lidar */
 int auv_timer_read(AuvTimer* t, int slot, float* ms);
+/* GPU-side scenario generation for the MovingObstacles family:
+ * what MovingObstacles._generate (envs/movingobstacles.py:28-95) and helpers.generate_obstacle
+ * (utils/helpers.py:5-35) sample per episode -- path choice from the bank, vessel start
+ * (path(0) + jitter, heading dir(0) + U(-pi, pi)), per obstacle slot the rejection-sampled
+ * position (normal displacement from a uniform arclength in [0.1 L, 0.9 L], clear of the vessel
+ * and of the goal), radius / width max(1, Poisson(mean)), and for moving obstacles direction
+ * U(0, 2 pi) and speed U(lo, hi) -- for the listed scenarios of the pool, with counter-based
+ * Philox4x32-10 streams keyed by (seed; scenario, slot, epoch): same arguments, same scenarios.
+ * Every slot of a listed scenario is (re)generated as "used". */
+typedef struct AuvGenParams {
+  uint64_t seed;
+  uint32_t epoch;               /* bump to draw a fresh scenario for the same pool slot      */
+  int32_t post_generate_update; /* _generate() ends with self._update()  movingobstacles.py:95 */
+  double t_step_size;           /* dt of that update                                         */
+  double vessel_width;          /* config.py:41                                              */
+  double init_pos_jitter;       /* 50    movingobstacles.py:35                               */
+  double mov_disp_std;          /* 500   movingobstacles.py:58                               */
+  double mov_width_mean;        /* 10    movingobstacles.py:59                               */
+  double mov_speed_lo;          /* 1     movingobstacles.py:65                               */
+  double mov_speed_hi;          /* 3                                                         */
+  double st_disp_std;           /* 250   movingobstacles.py:84                               */
+  double st_radius_mean;        /* 30    helpers.py:11                                       */
+} AuvGenParams;
+/* Writes path_id, vessel_init, mov_start, mov_width, mov_track, vel_table (entry m*Km+j), the
+ * post-reset obstacle state mov_pos0/disp0/counter0, st_pos and st_radius of the scenarios
+ * ids[0..n_ids) (device array; NULL = scenarios 0..n_ids-1).  The pool's arrays must be writable
+ * device memory with vel_table holding n_scenarios * k_moving entries.  The reset cache of those
+ * scenarios is stale afterwards: refill it with auv_reset + auv_observe(AUV_OBSERVE_RESET).
+ * status (device int or NULL) receives AUV_STATUS_GEN_GAVE_UP. */
+int auv_generate_moving_obstacles(const AuvGenParams* gp, const AuvPathBank* paths, const AuvScenarioPool* pool,
+                                  const int32_t* ids, int n_ids, int32_t* status, void* stream);
 /* Measured FP32 FMA peak helper (roofline denominator): runs `iters` dependent FMAs per
  * thread on a full grid; the caller times it with CUDA events. Returns flop count. */
 int auv_fma_probe(float* sink, int blocks, int threads, int iters, void* stream,

@@ -534,6 +534,110 @@ def test_step_async_two_groups_equals_sync():
     assert (~fresh_a).any(), "fixture should contain resets"
 
 
+# ---------------------------------------------------------------------------------------
+# GPU-side scenario generation
+# ---------------------------------------------------------------------------------------
+def _generated_env(M=512, n_paths=8, seed=3, **kw):
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    scn = S.moving_obstacles(M, 17, 11, seed=seed, n_paths=n_paths)
+    env = AUVVecEnv(scn, kw.pop("num_envs", M), cfg, auto_reset=True, **kw)
+    return cfg, scn, env
+
+
+def test_gpu_generated_scenarios_obey_the_reference_rules_and_distributions():
+    cfg, host, env = _generated_env(M=2048)
+    env.regenerate_scenarios(seed=11, epoch=1)
+    g = env.pull_scenarios()
+    bank = host.bank
+    L = np.array([bank.tables[p].length for p in g.path_id])
+    # vessel start: within +-25 m of path(0) per axis, heading anywhere (movingobstacles.py:34-38)
+    p0 = np.array([bank.tables[p](0.0) for p in g.path_id])
+    assert np.abs(g.vessel_init[:, :2] - p0).max() <= 25.0 + 1e-9
+    assert g.vessel_init[:, 2].min() >= -np.pi and g.vessel_init[:, 2].max() < np.pi
+    assert len(np.unique(g.path_id)) == len(bank.tables)  # uniform choice over the bank
+    goal = np.array([bank.tables[p](bank.tables[p].length) for p in g.path_id])
+    w = cfg.vessel.vessel_width
+    for pos, rad in ((g.mov_start, g.mov_width), (g.st_pos, g.st_radius)):
+        # acceptance rule of helpers.generate_obstacle (utils/helpers.py:28-33)
+        dv = np.linalg.norm(pos - g.vessel_init[:, None, :2], axis=2) - w - rad
+        dg = np.linalg.norm(pos - goal[:, None, :], axis=2) - rad
+        assert np.minimum(dv, dg).min() > 0
+        assert rad.min() >= 1.0 and np.all(rad == np.round(rad))  # max(1, Poisson)
+    speed = np.linalg.norm(g.vel_table, axis=1)
+    assert speed.min() >= 1.0 and speed.max() <= 3.0 and abs(speed.mean() - 2.0) < 0.02
+    # distributions against the host generator (NumPy streams, same path bank): means within 2 %
+    for a, b in ((g.mov_width, host.mov_width), (g.st_radius, host.st_radius)):
+        assert abs(a.mean() - b.mean()) < 0.02 * b.mean() and abs(a.std() - b.std()) < 0.05 * b.std()
+    def spread(pos, sc):
+        return np.linalg.norm(pos - sc.vessel_init[:, None, :2], axis=2)
+    for a, b in ((spread(g.mov_start, g), spread(host.mov_start, host)), (spread(g.st_pos, g), spread(host.st_pos, host))):
+        assert abs(np.median(a) - np.median(b)) < 0.05 * np.median(b)
+    heading = np.arctan2(g.vel_table[:, 1], g.vel_table[:, 0])
+    assert abs(np.mean(np.cos(heading))) < 0.02 and abs(np.mean(np.sin(heading))) < 0.02
+
+
+def test_gpu_generation_is_deterministic_and_epoch_dependent():
+    _, _, e1 = _generated_env(M=256)
+    _, _, e2 = _generated_env(M=256)
+    e1.regenerate_scenarios(seed=5, epoch=1)
+    e2.regenerate_scenarios(seed=5, epoch=1)
+    a, b = e1.pull_scenarios(), e2.pull_scenarios()
+    for k in ("path_id", "vessel_init", "mov_start", "mov_width", "vel_table", "st_pos", "st_radius"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert torch.equal(e1._pool["reset_obs"], e2._pool["reset_obs"])
+    ids = torch.arange(0, 256, 2)
+    e2.regenerate_scenarios(ids, seed=5, epoch=2)  # only the even slots change
+    c = e2.pull_scenarios()
+    assert np.array_equal(c.st_pos[1::2], a.st_pos[1::2]) and not np.array_equal(c.st_pos[0::2], a.st_pos[0::2])
+
+
+def test_gpu_generated_scenarios_replay_through_the_oracle():
+    """Scenarios drawn on the GPU are pulled back and injected into the CPU oracle: the full
+    step parity holds on them like on host-generated ones (incl. the cached first observation)."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg, _, env = _generated_env(M=8, n_paths=3, seed=9)
+    env.regenerate_scenarios(seed=21, epoch=4)
+    scn = env.pull_scenarios()
+    actions = random_actions(40, 8, 91)
+    ref = rollout_oracle(scn, cfg, actions)
+    gpu, _ = rollout_gpu(scn, cfg, actions)
+    compare(ref, gpu, cfg, "gpu-generated")
+    assert np.allclose(env._pool["reset_obs"].cpu().numpy(), np.array(ref["obs0"]), atol=2e-5)
+    # post-reset obstacle state written by the generator == the host rule (obstacles.py:192-193)
+    pos0, disp0, counter0 = scn.initial_obstacle_state(float(cfg.simulation.t_step_size))
+    assert np.abs(env._pool["mov_pos0"].cpu().numpy() - pos0).max() < 1e-9
+    assert np.abs(env._pool["mov_disp0"].cpu().numpy() - disp0).max() < 1e-12
+    assert np.abs(env._pool["mov_counter0"].cpu().numpy() - counter0).max() < 1e-12
+
+
+def test_refresh_finished_gives_every_new_episode_a_fresh_scenario():
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    cfg.episode.max_timesteps = 6
+    N = 96
+    scn = S.moving_obstacles(2 * N, 6, 6, seed=2, n_paths=4)
+    env = AUVVecEnv(scn, N, cfg, auto_reset=True)
+    env.reset()
+    seen = []
+    a = torch.zeros((N, 2), device="cuda")
+    for t in range(20):
+        env.step(a)
+        if t % 3 == 2:
+            before = env._pool["st_pos"].clone()
+            n = env.refresh_finished(seed=77)
+            changed = (env._pool["st_pos"] != before).flatten(1).any(1).nonzero().flatten().cpu().numpy()
+            active = env._st["scn_id"].cpu().numpy()
+            assert len(changed) == n and not set(changed) & set(active), "a running scenario was overwritten"
+            seen.append(n)
+    assert sum(seen) >= N  # every env timed out at least once
+    with pytest.raises(ValueError):
+        AUVVecEnv(S.moving_obstacles(N, 2, 2, seed=1), N, cfg, auto_reset=True).refresh_finished()
+
+
 def test_bad_shapes_raise():
     from gym_auv_b200.vec_env import AUVVecEnv
 
