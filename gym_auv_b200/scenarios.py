@@ -237,6 +237,43 @@ def moving_obstacles(
     return scn
 
 
+def moving_obstacles_template(
+    n_scenarios: int,
+    n_moving: int = 17,
+    n_static: int = 11,
+    seed: int = 0,
+    n_paths: int = 1024,
+    rewarder: str = "colav",
+    path_length: float = 800.0,
+    name: str = "MovingObstaclesNoRules-v0",
+) -> ScenarioSet:
+    """Path bank + EMPTY obstacle slots for M scenarios: the input of
+    ``AUVVecEnv.regenerate_scenarios`` (GPU-side sampling of vessel starts and obstacles).  Only
+    the random curves (path.py:96-120, three SciPy PCHIP fits each) are built on the host."""
+    M, P = int(n_scenarios), int(min(n_paths, n_scenarios))
+    rng = np.random.RandomState(seed)
+    wps = []
+    for _ in range(P):
+        nwp = int(np.floor(4 * rng.rand() + 2))
+        wps.append(random_curve_waypoints(rng, nwp, length=path_length))
+    tables = [build_path(w) for w in wps]
+    path_id = (np.arange(M) % P).astype(np.int32)
+    vessel_init = np.zeros((M, 3))
+    for p in range(P):
+        vessel_init[path_id == p, 0:2] = tables[p](0.0)
+    mov_track = np.zeros((M, n_moving, 4), dtype=np.int32)
+    mov_track[..., 0] = np.arange(M * n_moving).reshape(M, n_moving)
+    mov_track[..., 1] = VESSEL_TRACK_LEN
+    scn = ScenarioSet(
+        waypoints=wps, path_id=path_id, vessel_init=vessel_init, mov_start=np.zeros((M, n_moving, 2)),
+        mov_width=np.zeros((M, n_moving)), mov_track=mov_track, vel_table=np.zeros((M * n_moving, 2)),
+        st_pos=np.zeros((M, n_static, 2)), st_radius=np.zeros((M, n_static)), rewarder=rewarder,
+        post_generate_update=True, name=name,
+    )
+    scn._bank = PathBank(tables)
+    return scn
+
+
 def path_follow_no_obstacles(n_scenarios: int, seed: int = 0, n_paths: Optional[int] = None) -> ScenarioSet:
     """``PathFollowNoObstacles`` (movingobstacles.py:114-120)."""
     return moving_obstacles(

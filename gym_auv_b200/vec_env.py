@@ -304,6 +304,24 @@ class AUVVecEnv:
         M = self.scenarios.n_scenarios
         shared = dict(ray=self._ray, bank=self._bank, pool=self._pool)
         total = M if ids is None else int(ids.numel())
+        if ids is not None and total <= 8192:
+            # small refreshes (refresh_finished): one cached worker batch, padded with repeats
+            cap = 1024 if total <= 1024 else 8192
+            w = self._workers.get(cap) if hasattr(self, "_workers") else None
+            if w is None:
+                if not hasattr(self, "_workers"):
+                    self._workers = {}
+                w = self._workers[cap] = AUVVecEnv(
+                    self.scenarios, cap, self.config, device=self.device, test_mode=self.test_mode, auto_reset=False,
+                    cull_mode=self._cull_mode, max_nearby=self._max_nearby, _shared=shared)
+            sel = ids.to(self.device, torch.int64)
+            padded = torch.cat([sel, sel[:1].expand(cap - total)]) if total < cap else sel
+            w._st["scn_id"].copy_(padded.to(torch.int32))
+            obs = w.reset(check=False)
+            self._pool["reset_obs"][sel] = obs[:total]
+            self._pool["reset_max_progress"][sel] = w._st["max_progress"][:total]
+            self._pool["reset_mask"][sel] = w._st["nearby_mask"][:total]
+            return
         for start in range(0, total, chunk):
             n = min(chunk, total - start)
             tmp = AUVVecEnv(self.scenarios, n, self.config, device=self.device, test_mode=self.test_mode,
@@ -314,7 +332,7 @@ class AUVVecEnv:
             else:
                 sel = ids[start:start + n].to(self.device, torch.int64)
                 tmp._st["scn_id"].copy_(sel.to(torch.int32))
-            obs = tmp.reset()
+            obs = tmp.reset(check=False)
             self._pool["reset_obs"][sel] = obs
             self._pool["reset_max_progress"][sel] = tmp._st["max_progress"]
             self._pool["reset_mask"][sel] = tmp._st["nearby_mask"]
@@ -355,7 +373,6 @@ class AUVVecEnv:
                 C.byref(gp), C.byref(self.paths), C.byref(self.pool), idp, n,
                 C.c_void_p(self._scratch["status"].data_ptr()), self._stream()), "auv_generate_moving_obstacles")
         self._build_reset_cache(ids)
-        self.check_status()
         return n
 
     def refresh_finished(self, seed: int = 0) -> int:
@@ -411,7 +428,7 @@ class AUVVecEnv:
             )
 
     # ------------------------------------------------------------------ gym/VecEnv API
-    def reset(self) -> torch.Tensor:
+    def reset(self, check: bool = True) -> torch.Tensor:
         """Reset every env (BaseEnvironment.reset, environment.py:176-245)."""
         cfg, rays, paths, pool, batch = self._refs()
         with torch.cuda.device(self.device):
@@ -420,7 +437,8 @@ class AUVVecEnv:
                 self.lib.auv_observe(cfg, rays, paths, pool, batch, C.byref(self.out), _lib.OBSERVE_RESET, self._stream()),
                 "auv_observe",
             )
-        self.check_status()
+        if check:
+            self.check_status()
         return self._out["obs"]
 
     def reset_envs(self, mask: torch.Tensor, scenario_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
