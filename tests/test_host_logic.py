@@ -174,6 +174,32 @@ def test_binding_layout_and_version(built_lib):
     assert lib.auv_obs_dim(ctypes.byref(cfg)) == 6
 
 
+def test_scenario_template_is_the_input_of_gpu_generation():
+    scn = S.moving_obstacles_template(64, 5, 3, seed=1, n_paths=4)
+    assert scn.n_scenarios == 64 and scn.k_moving == 5 and scn.k_static == 3 and len(scn.waypoints) == 4
+    assert scn.vel_table.shape == (64 * 5, 2)  # one constant-velocity entry per (scenario, slot)
+    assert np.array_equal(scn.mov_track[..., 0], np.arange(64 * 5).reshape(64, 5))
+    assert not (scn.mov_width > 0).any() and not (scn.st_radius > 0).any()  # every slot empty until generated
+    scn.validate()
+    pos, disp, counter = scn.initial_obstacle_state(1.0)
+    assert not disp.any() and not counter.any()
+
+
+def test_generator_and_pipeline_entry_points_reject_bad_arguments(built_lib):
+    from gym_auv_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.auv_generate_moving_obstacles(None, None, None, None, 1, None, None) == -1
+    gp, paths, pool = _lib.AuvGenParams(seed=1), _lib.AuvPathBank(n_paths=0), _lib.AuvScenarioPool(n_scenarios=4)
+    assert lib.auv_generate_moving_obstacles(ctypes.byref(gp), ctypes.byref(paths), ctypes.byref(pool), None, 8, None, None) == -1
+    assert b"n_ids" in lib.auv_last_error()
+    assert lib.auv_generate_moving_obstacles(ctypes.byref(gp), ctypes.byref(paths), ctypes.byref(pool), None, 4, None, None) == -1
+    assert b"path bank" in lib.auv_last_error()
+    assert lib.auv_pipeline_graph_state(None) == -1
+    assert not lib.auv_pipeline_create(0) and not lib.auv_pipeline_create(99)
+    assert ctypes.sizeof(_lib.AuvGenParams) == lib.auv_sizeof(6)
+
+
 def test_bad_arguments_return_error_codes_not_crashes(built_lib):
     from gym_auv_b200 import _lib
 
