@@ -435,9 +435,7 @@ def run_ours(args):
     #      buffers, every step's actions come from host memory and every observation lands there.
     if e2e is not None and N >= 128:
         half = N // 2
-        shared = dict(ray=env._ray, bank=env._bank, pool=env._pool)
-        groups = [AUVVecEnv(scn, half, cfg, device=device, test_mode=False, auto_reset=True, env_offset=o,
-                            host_chunks=max(1, args.host_chunks // 2), _shared=shared) for o in (0, half)]
+        groups = env.groups(2)  # two envs of N/2 sharing this env's device tables
         for g in groups:
             g.reset()
         ah = [[a[:half].copy() for a in acts_np], [a[half:2 * half].copy() for a in acts_np]]

@@ -176,26 +176,34 @@ __device__ __forceinline__ double world_polygon_distance(const double2* __restri
 __device__ __forceinline__ double boundary_distance(bool pent, double cx, double cy, double bx0, double by0,
                                                  double geo, double hx, double hy, int nv_cnt,
                                                  const double2* __restrict__ unit) {
-  float dmin = INFINITY;
   const int ne = nv_cnt - 1;
-  double vx, vy;
-  if (pent) {
-    pent_vertex(0, bx0, by0, geo, hx, hy, vx, vy);
-  } else {
-    vx = cx + geo;
-    vy = cy;
+  if (!pent) {
+    // ring of a regular n-gon (n a power of two): the edge nearest to a point is the one whose
+    // angular sector (seen from the centre) contains the point; its two neighbours are tested as
+    // well so that rounding of the angle cannot matter -- 3 edges instead of n
+    const float th = atan2f((float)-cy, (float)-cx);  // direction centre -> own-ship
+    const int k0 = (int)floorf(th * ((float)ne * 0.15915494309189535f)) & (ne - 1);
+    const int sh = 6 - (31 - __clz(ne));  // unit table stride 64 / ne
+    float dmin = INFINITY;
+    double2 un = __ldg(&unit[((k0 - 1) & (ne - 1)) << sh]);
+    float pxv = (float)(cx + geo * un.x), pyv = (float)(cy + geo * un.y);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      un = __ldg(&unit[((k0 + t) & (ne - 1)) << sh]);
+      const float qx = (float)(cx + geo * un.x), qy = (float)(cy + geo * un.y);
+      dmin = fminf(dmin, pt_seg_dist_f(0.f, 0.f, pxv, pyv, qx, qy));
+      pxv = qx;
+      pyv = qy;
+    }
+    return (double)dmin;
   }
+  float dmin = INFINITY;
+  double vx, vy;
+  pent_vertex(0, bx0, by0, geo, hx, hy, vx, vy);
   float pxv = (float)vx, pyv = (float)vy;
   bool allpos = true, allneg = true;
   for (int k = 1; k <= ne; ++k) {
-    const int kk = (k == ne) ? 0 : k;
-    if (pent) {
-      pent_vertex(kk, bx0, by0, geo, hx, hy, vx, vy);
-    } else {
-      const double2 un = __ldg(&unit[kk * (64 / ne)]);
-      vx = cx + geo * un.x;
-      vy = cy + geo * un.y;
-    }
+    pent_vertex(k == ne ? 0 : k, bx0, by0, geo, hx, hy, vx, vy);
     const float qx = (float)vx, qy = (float)vy;
     dmin = fminf(dmin, pt_seg_dist_f(0.f, 0.f, pxv, pyv, qx, qy));
     const float cr = pxv * qy - pyv * qx;  // cross(prev, cur) about the vessel
@@ -204,8 +212,7 @@ __device__ __forceinline__ double boundary_distance(bool pent, double cx, double
     pxv = qx;
     pyv = qy;
   }
-  const bool inside = pent && (allpos || allneg);
-  return inside ? 0.0 : (double)dmin;
+  return (allpos || allneg) ? 0.0 : (double)dmin;  // filled: own-ship inside => distance 0
 }
 
 // is the own-ship (origin) inside the convex vessel pentagon?  FP64.

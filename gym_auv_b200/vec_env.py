@@ -536,6 +536,21 @@ class AUVVecEnv:
         pin = self._pinned
         return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy()
 
+    def groups(self, n_groups: int = 2, **kw):
+        """``n_groups`` envs of num_envs / n_groups each that SHARE this env's device tables
+        (ray table, path bank, scenario pool incl. the cached first observations): the
+        asynchronous pattern ``wait(A); submit(A); wait(B); submit(B); ...`` with
+        step_async / step_wait keeps the host link busy.  Group g starts on the scenarios
+        g * n .. (g + 1) * n - 1; every group advances through the whole pool on resets."""
+        n = self.num_envs // int(n_groups)
+        if n <= 0:
+            raise ValueError("more groups than envs")
+        shared = dict(ray=self._ray, bank=self._bank, pool=self._pool)
+        kw.setdefault("host_chunks", max(1, self.host_chunks // int(n_groups)))
+        return [AUVVecEnv(self.scenarios, n, self.config, device=self.device, test_mode=self.test_mode,
+                          auto_reset=bool(self.cfg.auto_reset), cull_mode=self._cull_mode, env_offset=g * n,
+                          max_nearby=self._max_nearby, _shared=shared, **kw) for g in range(int(n_groups))]
+
     def step_host_buffers(self):
         """Pinned host buffers of step_host / step_async (actions in; obs, reward, done out)."""
         N = self.num_envs

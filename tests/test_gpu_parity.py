@@ -506,8 +506,8 @@ def test_step_async_two_groups_equals_sync():
     n = 130
     scn = S.moving_obstacles(2 * n, 5, 5, seed=33)
     ref = AUVVecEnv(scn, 2 * n, cfg, auto_reset=True)
-    ga = AUVVecEnv(scn, n, cfg, auto_reset=True, env_offset=0, host_chunks=2)
-    gb = AUVVecEnv(scn, n, cfg, auto_reset=True, env_offset=n, host_chunks=3)
+    ga, gb = ref.groups(2, host_chunks=3)  # share ref's device tables (pool, path bank, reset cache)
+    assert ga.num_envs == gb.num_envs == n and gb.env_offset == n
     ref.reset(), ga.reset(), gb.reset()
     acts = random_actions(20, 2 * n, 8).astype(np.float32)
     ga.step_async(acts[0, :n])
