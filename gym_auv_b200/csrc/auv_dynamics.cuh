@@ -84,8 +84,14 @@ __device__ __forceinline__ S6 vessel_rk_step(const AuvConfig& cfg, const S6& y, 
   const double h = cfg.t_step_size;
   double c0, s0, c, s, dpsi;
   sincos(princip(y.psi), &s0, &c0);
+  // The derivatives do not depend on x, y, so no stage needs the x/y parts of earlier k's: they
+  // are folded into the result as soon as they exist (b-weights in the tableau's order), which
+  // takes 2 x 5 doubles out of the live set of this register-bound kernel.
   S6 t, k1, k2, k3, k4, k5, k6, q;
+  const double b1 = h * (16.0 / 135.0), b3 = h * (6656.0 / 12825.0), b4 = h * (28561.0 / 56430.0),
+               b5 = h * (9.0 / 50.0), b6 = h * (2.0 / 55.0);
   k1 = state_dot_cs(y, c0, s0, tau_u, tau_r);
+  double ax = b1 * k1.x, ay = b1 * k1.y;
   const double a21 = h * (1.0 / 4.0);
 #define E2(f) a21 * k1.f
   S6_STAGE(t, y, E2, dpsi)
@@ -96,26 +102,37 @@ __device__ __forceinline__ S6 vessel_rk_step(const AuvConfig& cfg, const S6& y, 
   S6_STAGE(t, y, E3, dpsi)
   rot_cs(c0, s0, y.psi, dpsi, c, s);
   k3 = state_dot_cs(t, c, s, tau_u, tau_r);
+  ax += b3 * k3.x;
+  ay += b3 * k3.y;
   const double a41 = h * (1932.0 / 2197.0), a42 = h * (7200.0 / 2197.0), a43 = h * (7296.0 / 2197.0);
 #define E4(f) a41 * k1.f - a42 * k2.f + a43 * k3.f
   S6_STAGE(t, y, E4, dpsi)
   rot_cs(c0, s0, y.psi, dpsi, c, s);
   k4 = state_dot_cs(t, c, s, tau_u, tau_r);
+  ax += b4 * k4.x;
+  ay += b4 * k4.y;
   const double a51 = h * (439.0 / 216.0), a52 = h * 8.0, a53 = h * (3680.0 / 513.0), a54 = h * (845.0 / 4104.0);
 #define E5(f) a51 * k1.f - a52 * k2.f + a53 * k3.f - a54 * k4.f
   S6_STAGE(t, y, E5, dpsi)
   rot_cs(c0, s0, y.psi, dpsi, c, s);
   k5 = state_dot_cs(t, c, s, tau_u, tau_r);
+  ax -= b5 * k5.x;
+  ay -= b5 * k5.y;
   const double a61 = h * (8.0 / 27.0), a62 = h * 2.0, a63 = h * (3544.0 / 2565.0), a64 = h * (1859.0 / 4104.0),
                a65 = h * (11.0 / 40.0);
 #define E6(f) -a61 * k1.f + a62 * k2.f - a63 * k3.f + a64 * k4.f - a65 * k5.f
   S6_STAGE(t, y, E6, dpsi)
   rot_cs(c0, s0, y.psi, dpsi, c, s);
   k6 = state_dot_cs(t, c, s, tau_u, tau_r);
-  const double b1 = h * (16.0 / 135.0), b3 = h * (6656.0 / 12825.0), b4 = h * (28561.0 / 56430.0),
-               b5 = h * (9.0 / 50.0), b6 = h * (2.0 / 55.0);
+  ax += b6 * k6.x;
+  ay += b6 * k6.y;
 #define EQ(f) b1 * k1.f + b3 * k3.f + b4 * k4.f - b5 * k5.f + b6 * k6.f
-  S6_STAGE(q, y, EQ, dpsi)
+  q.x = y.x + ax;
+  q.y = y.y + ay;
+  q.psi = y.psi + (EQ(psi));
+  q.u = y.u + (EQ(u));
+  q.v = y.v + (EQ(v));
+  q.r = y.r + (EQ(r));
   q.psi = princip(q.psi);
   return q;
 }
