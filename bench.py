@@ -557,7 +557,7 @@ def run_ours(args):
         },
         "episode_stats": stats,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         small = argparse.Namespace(**vars(args))
         small.envs = args.cpu_sample_envs
         small.n_paths = min(args.n_paths, small.envs)
