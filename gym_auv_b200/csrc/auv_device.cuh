@@ -11,9 +11,14 @@ namespace auv {
 // geomutils.py:4-5  princip(angle) = ((angle + pi) % (2 pi)) - pi  with Python's floored
 // modulo (result of % has the sign of the divisor) => value in [-pi, pi).
 __device__ __forceinline__ double princip(double a) {
+  // x - q * 2pi with q = floor(x / 2pi) by ONE fused multiply-add: the exact remainder is a
+  // double, so the FMA returns it exactly -- the same value as fmod's, without its software loop
+  // (angles here are a few radians; the guards only act when x / 2pi rounds across an integer)
   const double two_pi = 2.0 * AUV_PI;
-  double m = fmod(a + AUV_PI, two_pi);
+  const double x = a + AUV_PI;
+  double m = fma(-two_pi, floor(x * (1.0 / two_pi)), x);
   if (m < 0.0) m += two_pi;
+  if (m >= two_pi) m -= two_pi;
   return m - AUV_PI;
 }
 

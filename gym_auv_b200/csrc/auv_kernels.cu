@@ -472,7 +472,8 @@ __device__ __forceinline__ float cast_ray_record(const ObstRec& q, const float2*
     // meets the circle at polar angles theta+g and theta+pi-g (g = asin(-hc/r));
     // between circle and polygon lies the circular segment of exactly one edge, so the
     // polygon crossing is on the edge whose angular span contains that angle.  The
-    // neighbour on the nearer side is tested too (FP32 error of asinf near grazing).
+    // neighbour on the nearer side is tested too (FP32 error of asinf near grazing); testing it
+    // only near the span boundary was measured slower (divergent, not unrolled: 0.106 -> 0.108 ms).
     const int nn = nq - 1;
     const float g = asinf(fminf(fmaxf(-hc / rho, -1.f), 1.f));
     const float invd = (float)nn * 0.15915494309189535f;
