@@ -67,6 +67,8 @@ def parse():
                          "--n-polygons static land polygons); pathfollow = config 2 (no LiDAR, PathFollowRewarder)")
     ap.add_argument("--n-polygons", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not pin the process to the CPU cores local to its GPU (NVML affinity)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-envs", type=int, default=8)
     ap.add_argument("--cpu-sample-steps", type=int, default=400)
@@ -266,6 +268,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    from gym_auv_b200.sharding import bind_to_gpu_numa
+
+    numa_cores = bind_to_gpu_numa(local_rank) if not args.no_numa_bind else ()
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
@@ -527,7 +532,8 @@ def run_ours(args):
                    % (N * ALGO_BYTES_PER_ENV_STEP / 2e6, scn.bank.poly_xy.nbytes * 1.5 / 1e6 + scn.bank.coef.nbytes / 1e6),
                    "auto_reset": True, "dones_per_step": dones_per_step,
                    "chunks": env.chunks, "chunk_streams": getattr(env, "chunk_streams", 1),
-                   "scenario_generation": scenario_gen or {"where": "host"}},
+                   "scenario_generation": scenario_gen or {"where": "host"},
+                   "host_cores_bound": len(numa_cores)},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": 2 * K * n_ranges(N, env.chunks),  # k_vessel_nav + k_lidar per env range
