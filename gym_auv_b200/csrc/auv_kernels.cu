@@ -346,7 +346,7 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
 #define AUV_NAV_THREADS 128
 #endif
 #ifndef AUV_NAV_MINB
-#define AUV_NAV_MINB 8  // 64 registers: occupancy beats spills here (G x MINB sweep: profiles/r1j_variants.txt)
+#define AUV_NAV_MINB 7  // 72 registers (profiles/r1j_variants.txt: 64 regs 0.114 ms, 72 regs 0.104, 80 regs 0.121)
 #endif
 template <bool DYN, bool OBST, int G>
 __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(const __grid_constant__ AuvConfig cfg,
