@@ -15,7 +15,12 @@ Parity status
   ``objects/vessel/odesolver.py``, ``utils/sector_partitioning.py``) and commits
   their outputs as fixtures; ``tests/test_oracle_pinned.py`` checks this
   restatement against them bit-for-bit (dynamics to 1e-15).
-* everything that goes through Shapely 1.7.0 / GEOS in the reference (ray/boundary
+* the reference's own classes run behind import stubs
+  (``tests/golden/make_reference_goldens_stubbed.py`` -> ``reference_stubbed.npz``) PIN the
+  culling-window integers incl. Python's negative-index wrap (``sensor.py:41-97``), feasibility
+  pooling, ``Path`` / ``RandomCurveThroughOrigin``, ``Vessel.step`` + ``Vessel.navigate`` rollouts,
+  ``VesselObstacle`` tracks and both rewarders (``tests/test_reference_goldens_stubbed.py``).
+* what the reference computes INSIDE Shapely 1.7.0 / GEOS (ray/boundary
   intersection, ``Point.distance``, ``LineString.project``, ``buffer().simplify()``,
   ``minimum_rotated_rectangle``, ``affinity.rotate``) is restated from GEOS' published
   algorithms in ``oracle/geos_lite.py`` -- Shapely/GEOS is not installable here

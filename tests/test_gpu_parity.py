@@ -1,6 +1,7 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on
 identical injected scenarios and actions, and against golden vectors produced by the
 reference's own dynamics files.  Run on the B200 box:  pytest tests -m gpu"""
+import math
 import os
 
 import numpy as np
@@ -733,3 +734,101 @@ def test_staged_entry_points_compose_to_a_step():
         assert torch.equal(o1, o2) and torch.equal(r1, e2._out["reward"]) and torch.equal(e1.state, e2.state)
     nav = e2.navigate()
     assert nav.shape == (5, 24) and torch.equal(nav[:, :16], e1.get_attr("nav")[:, :16])
+
+
+# ---------------------------------------------------------------------------------------
+# CUDA path against goldens produced by the REFERENCE'S OWN classes behind import stubs
+# (tests/golden/make_reference_goldens_stubbed.py) -- no oracle in between
+# ---------------------------------------------------------------------------------------
+STUBBED = np.load(os.path.join(GOLD, "reference_stubbed.npz"))
+
+
+def test_culling_windows_match_reference_sensor_module_on_gpu():
+    """k_vessel_nav's window integers == sensor._find_limit_angle_rays / the list indices of
+    find_rays_to_simulate_for_obstacles (sensor.py:41-97), run on the reference's own code."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cases, lim, err = STUBBED["win_cases"], STUBBED["win_limits"], STUBBED["win_index_error"]
+    M, Rn = len(cases), 180
+    base = S.empty_scenario()
+    scn = S.ScenarioSet(
+        waypoints=base.waypoints, path_id=np.zeros(M, dtype=np.int32), vessel_init=cases[:, [0, 1, 2]].copy(),
+        mov_start=np.zeros((M, 0, 2)), mov_width=np.zeros((M, 0)), mov_track=np.zeros((M, 0, 4), dtype=np.int32),
+        vel_table=np.zeros((0, 2)), st_pos=cases[:, None, 3:5].copy(), st_radius=cases[:, None, 5].copy(),
+        rewarder="colav", post_generate_update=False, name="windows")
+    scn._bank = base.bank
+    env = AUVVecEnv(scn, M, lidar_config(), auto_reset=False, debug=True)
+    env.reset()
+    win = env.get_attr("windows").cpu().numpy()[:, 0]
+    dist = np.hypot(cases[:, 3] - cases[:, 0], cases[:, 4] - cases[:, 1])
+    surely_near = np.abs(dist - cases[:, 5]) < 140.0  # ring within sensor range whatever the polygonisation
+    checked = 0
+    for k in range(M):
+        if not surely_near[k] or err[k]:
+            continue
+        assert (int(win[k, 0]), int(win[k, 1])) == (int(lim[k, 0]) - 1, int(lim[k, 1]) % Rn), k
+        checked += 1
+    assert checked > 250
+
+
+@pytest.mark.parametrize("r", range(8))
+def test_vessel_and_navigation_rollouts_match_reference_vessel_class_on_gpu(r):
+    """State after Vessel.step and the Vessel.navigate features, step by step, against the
+    reference's Vessel / Path classes (vessel.py:226-247,461-541; path.py)."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    pidx = int(STUBBED["roll_path"][r])
+    wp = STUBBED["path_waypoints"][pidx]
+    wp = wp[:, ~np.isnan(wp[0])]
+    cfg = Config()  # no LiDAR: dynamics + navigation only
+    cfg.simulation.t_step_size = float(STUBBED["roll_dt"][r])
+    scn = S._single(wp, vessel_init=STUBBED["roll_init"][r], rewarder="pathfollow")
+    env = AUVVecEnv(scn, 1, cfg, test_mode=True, auto_reset=False)
+    env.reset()
+    acts = torch.as_tensor(STUBBED["roll_actions"][r], dtype=torch.float32, device="cuda")
+    for t in range(acts.shape[0]):
+        obs, _, _, info = env.step(acts[t][None])
+        nav = env.get_attr("nav")[0].cpu().numpy()
+        st = env.state[:, 0].cpu().numpy()
+        assert np.abs(st - STUBBED["roll_state"][r, t]).max() <= 1e-9, t
+        assert abs(nav[0] - STUBBED["roll_s"][r, t]) <= 1e-7, t  # arclength (golden: brute-force stand-in for GEOS)
+        assert abs(nav[3] - STUBBED["roll_s_la"][r, t]) <= 1e-7
+        assert abs(nav[2] / 100 - STUBBED["roll_cte"][r, t]) <= 1e-9
+        assert abs(nav[4] - STUBBED["roll_la_err"][r, t]) <= 2e-6  # FP32 atan2 of FP64 differences
+        assert abs(nav[5] - STUBBED["roll_head_err"][r, t]) <= 2e-6
+        assert abs(nav[6] - STUBBED["roll_goal"][r, t]) <= 1e-9
+        assert abs(nav[7] - STUBBED["roll_progress"][r, t]) <= 1e-10
+        assert bool(nav[10]) == bool(STUBBED["roll_reached"][r, t]) == bool(info["reached_goal"][0].item())
+        assert abs(float(env.get_attr("max_progress")[0]) - STUBBED["roll_max_progress"][r, t]) <= 1e-10
+        want_obs = np.clip([*STUBBED["roll_state"][r, t, 3:6], STUBBED["roll_la_err"][r, t], STUBBED["roll_head_err"][r, t],
+                            STUBBED["roll_cte"][r, t]], -1, 1)
+        assert np.abs(obs[0].cpu().numpy() - want_obs).max() <= 2e-6
+
+
+@pytest.mark.parametrize("k", range(3))
+def test_moving_obstacle_tracks_match_reference_vessel_obstacle_on_gpu(k):
+    """k_obstacle_update (and the update fused into the step) against VesselObstacle.update
+    (obstacles.py:195-215) on the reference's own class: constant and table-driven tracks, wrap."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    tr = STUBBED["trk_traj"][k]
+    tr = tr[~np.isnan(tr[:, 0])]
+    traj = [(int(t), (x, y)) for t, x, y in tr]
+    dt = float(STUBBED["trk_dt"][k, 0])
+    cfg = lidar_config()
+    cfg.simulation.t_step_size = dt
+    scn = S._single(np.array([[0.0, 1000.0], [500.0, 500.0]]), moving_traj=[(5.0, traj)])
+    staged = AUVVecEnv(scn, 1, cfg, test_mode=True, auto_reset=False)
+    fused = AUVVecEnv(scn, 1, cfg, test_mode=True, auto_reset=False)
+    staged.reset(), fused.reset()
+    assert np.abs(staged.get_attr("mov_pos")[0, 0].cpu().numpy() - STUBBED["trk_pos"][k, 0]).max() <= 1e-12
+    a = torch.zeros((1, 2), device="cuda")
+    for t in range(60):
+        staged.obstacle_update()
+        fused.step(a)
+        for env in (staged, fused):
+            pos = env.get_attr("mov_pos")[0, 0].cpu().numpy()
+            disp = env._st["mov_disp"][0, 0].cpu().numpy()
+            assert np.abs(pos - STUBBED["trk_pos"][k, t + 1]).max() <= 1e-9, t
+            assert abs(math.atan2(disp[1], disp[0]) - STUBBED["trk_head"][k, t + 1]) <= 1e-12
+            assert abs(float(env.get_attr("mov_counter")[0, 0]) - STUBBED["trk_counter"][k, t + 1]) <= 1e-12

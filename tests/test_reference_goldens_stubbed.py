@@ -1,0 +1,158 @@
+"""The oracle (and the host-side product code) against golden vectors produced by the
+REFERENCE'S OWN classes run behind import stubs (tests/golden/make_reference_goldens_stubbed.py):
+culling windows incl. Python's negative-index wrap, feasibility pooling, Path /
+RandomCurveThroughOrigin, Vessel.step + Vessel.navigate rollouts, VesselObstacle tracks, both
+rewarders.  These pin everything on the path that does not need a real GEOS."""
+import math
+import os
+import types
+
+import numpy as np
+import pytest
+
+from gym_auv_b200 import Config, lidar_config, scenarios as S
+from gym_auv_b200.pathbank import build_path
+from oracle import sim as O
+from tests._parity import oracle_cfg
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_stubbed.npz"))
+R = 180
+DTH = 2 * np.pi / R
+
+
+def test_culling_windows_are_the_reference_integers():
+    lim = GOLD["win_limits"]
+    n_seam = 0
+    for k, (x, y, h, cx, cy, rho) in enumerate(GOLD["win_cases"]):
+        lo, hi = O.limit_angle_rays((cx, cy), rho, (x, y), h, DTH)
+        assert (lo, hi) == (int(lim[k, 0]), int(lim[k, 1])), k
+        n_seam += int(lim[k, 1] >= R)
+    assert n_seam > 20  # the fixture exercises the seam arithmetic
+
+
+def test_candidate_rays_reproduce_pythons_negative_index_wrap():
+    """How often each ray lists the obstacle in find_rays_to_simulate_for_obstacles: the closed
+    form used by the kernels, candidate(i) <=> a <= i < b or a <= i - R < b with a = lo - 1,
+    b = hi mod R, counted with multiplicity; IndexError upstream <=> a < -R."""
+    lim, counts, err = GOLD["win_limits"], GOLD["win_counts"], GOLD["win_index_error"]
+    i = np.arange(R)
+    for k in range(len(lim)):
+        a, b = int(lim[k, 0]) - 1, int(lim[k, 1]) % R
+        assert bool(err[k]) == (a < -R), k
+        if err[k]:
+            continue
+        mine = ((a <= i) & (i < b)).astype(int) + ((a <= i - R) & (i - R < b)).astype(int)
+        assert np.array_equal(mine, counts[k]), k
+
+    class Ob:
+        def __init__(self, c, r):
+            self.c, self.r = c, r
+
+        def enclosing_circle(self):
+            return self.c, self.r
+
+    for k in range(0, len(lim), 7):  # the oracle's own list-based restatement
+        x, y, h, cx, cy, rho = GOLD["win_cases"][k]
+        per_ray, _ = O.rays_for_obstacles([Ob((cx, cy), rho)], (x, y), h, DTH, R)
+        got = np.array([len(l) for l in per_ray])
+        assert np.array_equal(got, counts[k]) or err[k]
+
+
+def test_feasibility_pooling_matches_reference_static_method():
+    for row, want in zip(GOLD["pool_in"], GOLD["pool_out"]):
+        m = row[~np.isnan(row)]
+        assert O.feasibility_pooling(m, 1.255 * 5.0, DTH) == want
+
+
+@pytest.mark.parametrize("pidx", range(4))
+def test_paths_match_reference_path_class(pidx):
+    wp = GOLD["path_waypoints"][pidx]
+    wp = wp[:, ~np.isnan(wp[0])]
+    L = float(GOLD["path_length"][pidx])
+    Sg = GOLD["path_S"]
+    for path, direction in ((O.OraclePath(wp), lambda p, s: p.direction(s)), (build_path(wp), lambda p, s: p.direction(s))):
+        assert abs(path.length - L) <= 1e-9 * L
+        pos = np.array([path(s * L) for s in Sg]).reshape(len(Sg), 2)
+        assert np.abs(pos - GOLD["path_pos"][pidx]).max() <= 1e-8
+        d = np.array([float(direction(path, s * L)) for s in Sg])
+        assert np.abs(np.angle(np.exp(1j * (d - GOLD["path_dir"][pidx])))).max() <= 1e-9
+    tab = build_path(wp)
+    assert len(tab.poly) == int(GOLD["path_poly_n"][pidx])  # int(10 * length) vertices, path.py:38
+    step = max(1, len(tab.poly) // 64)
+    assert np.abs(tab.poly[::step][:64] - GOLD["path_poly_sample"][pidx]).max() <= 1e-8
+    assert np.abs(tab.knots - GOLD["path_knots"][pidx]).max() <= 1e-9 * L
+
+
+def test_random_curve_generator_matches_reference_class():
+    from gym_auv_b200.pathbank import random_curve_waypoints
+
+    for pidx in range(3):
+        rng = np.random.RandomState(100 + pidx)
+        nwp = int(np.floor(4 * rng.rand() + 2))
+        wp = random_curve_waypoints(rng, nwp, length=800)
+        want = GOLD["path_waypoints"][pidx]
+        want = want[:, ~np.isnan(want[0])]
+        assert wp.shape == want.shape and np.abs(wp - want).max() <= 1e-12
+
+
+@pytest.mark.parametrize("r", range(8))
+def test_vessel_step_and_navigate_rollouts_match_reference_vessel(r):
+    pidx = int(GOLD["roll_path"][r])
+    wp = GOLD["path_waypoints"][pidx]
+    wp = wp[:, ~np.isnan(wp[0])]
+    cfg = lidar_config()
+    cfg.simulation.t_step_size = float(GOLD["roll_dt"][r])
+    path = O.OraclePath(wp)
+    v = O.OracleVessel(oracle_cfg(cfg), GOLD["roll_init"][r])
+    v.navigate(path)  # the observe() of reset()
+    for t, a in enumerate(GOLD["roll_actions"][r]):
+        v.step(a)
+        v.navigate(path)
+        assert np.abs(v.state - GOLD["roll_state"][r, t]).max() <= 1e-10, t
+        # the golden arclength comes from the generator's brute-force stand-in for GEOS project
+        assert abs(v.nav["vessel_arclength"] - GOLD["roll_s"][r, t]) <= 1e-7, t
+        assert abs(v.nav["target_arclength"] - GOLD["roll_s_la"][r, t]) <= 1e-7
+        assert abs(v.nav["look_ahead_heading_error"] - GOLD["roll_la_err"][r, t]) <= 1e-8
+        assert abs(v.nav["heading_error"] - GOLD["roll_head_err"][r, t]) <= 1e-8
+        assert abs(v.nav["cross_track_error"] - GOLD["roll_cte"][r, t]) <= 1e-9
+        assert abs(v.nav["goal_distance"] - GOLD["roll_goal"][r, t]) <= 1e-9
+        assert abs(v.progress - GOLD["roll_progress"][r, t]) <= 1e-10
+        assert abs(v.max_progress - GOLD["roll_max_progress"][r, t]) <= 1e-10
+        assert v.reached_goal == bool(GOLD["roll_reached"][r, t])
+
+
+@pytest.mark.parametrize("k", range(4))
+def test_vessel_obstacle_tracks_match_reference_class(k):
+    tr = GOLD["trk_traj"][k]
+    tr = tr[~np.isnan(tr[:, 0])]
+    traj = [(int(t), (x, y)) for t, x, y in tr]
+    dt, init_update = float(GOLD["trk_dt"][k, 0]), bool(GOLD["trk_dt"][k, 1])
+    o = O.OracleVesselObstacle.from_trajectory(5.0, traj, init_update=init_update)
+    assert np.abs(o.position - GOLD["trk_pos"][k, 0]).max() <= 1e-12
+    for t in range(60):
+        o.update(dt)
+        assert np.abs(o.position - GOLD["trk_pos"][k, t + 1]).max() <= 1e-9, t
+        assert abs(o.heading - GOLD["trk_head"][k, t + 1]) <= 1e-12
+        assert abs(o.counter - GOLD["trk_counter"][k, t + 1]) <= 1e-12
+    # the host-side product code (scenario arrays + vectorised update) on the same trajectory
+    scn = S._single(np.array([[0.0, 100.0], [0.0, 0.0]]), moving_traj=[(5.0, traj)])
+    pos = scn.mov_start.astype(np.float64).copy()
+    counter = np.zeros(scn.mov_width.shape)
+    if init_update:
+        pos, _, counter = S.advance_obstacles(scn, pos, counter, 0.1)
+    for t in range(60):
+        pos, disp, counter = S.advance_obstacles(scn, pos, counter, dt)
+        assert np.abs(pos[0, 0] - GOLD["trk_pos"][k, t + 1]).max() <= 1e-9, t
+        assert abs(math.atan2(disp[0, 0, 1], disp[0, 0, 0]) - GOLD["trk_head"][k, t + 1]) <= 1e-12
+
+
+def test_rewarders_match_reference_classes():
+    angles = np.array([-np.pi + (i + 1) * DTH for i in range(R)])
+    for row, want_c, want_p in zip(GOLD["rew_in"], GOLD["rew_colav"], GOLD["rew_pathfollow"]):
+        speed, yaw, cte, he, prog, maxprog, collision = row[:7]
+        v = types.SimpleNamespace(
+            collision=bool(collision), nav=dict(cross_track_error=cte, heading_error=he), speed=speed,
+            n_sensors=R, sensor_angles=angles, dists=row[7:], cfg=dict(sensor_range=150.0), progress=prog,
+            max_progress=maxprog, state=np.array([0, 0, 0, 0, 0, yaw]))
+        assert abs(O.colav_reward(v) - want_c) <= 1e-9 * max(1.0, abs(want_c))
+        assert abs(O.pathfollow_reward(v) - want_p) <= 1e-9 * max(1.0, abs(want_p))
