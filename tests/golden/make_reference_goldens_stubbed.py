@@ -25,6 +25,11 @@ Recorded (unmodified reference code in every case):
   vessel     Vessel.step + Vessel.navigate rollouts (vessel.py:226-247,461-541) on those paths
   obstacles  VesselObstacle velocity table / update / wrap (obstacles.py:144-215)
   rewards    ColavRewarder.calculate / PathFollowRewarder.calculate (rewarder.py:78-241)
+  env        BaseEnvironment.reset / step / observe / _isdone / save_latest_episode
+             (environment.py:176-392,460-489) with ``gym`` and the 2-D renderer stubbed too, on
+             obstacle-free scenarios (Vessel.perceive then never reaches Shapely, vessel.py:275-305):
+             observation vectors, rewards, done flags, info, cumulative reward and the history entry
+             of whole episodes ending by time limit, reward limit and reached goal
 
 Usage:  python tests/golden/make_reference_goldens_stubbed.py   (writes reference_stubbed.npz)
 """
@@ -126,6 +131,38 @@ def install_stubs():
         m.__path__ = [os.path.join(REF, rel)]
         sys.modules[pkg] = m
     sys.modules["gym_auv"].Config = type("Config", (), {})
+    # gym 0.21 surface used by environment.py / clip_to_space.py, and the pygame-backed renderer
+    gym = types.ModuleType("gym")
+    spaces = types.ModuleType("gym.spaces")
+
+    class Space:
+        pass
+
+    class Box(Space):
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.low = np.full(shape, low, dtype=np.float64) if shape is not None else np.asarray(low, dtype=np.float64)
+            self.high = np.full(shape, high, dtype=np.float64) if shape is not None else np.asarray(high, dtype=np.float64)
+            self.shape, self.dtype = self.low.shape, dtype
+
+    class Dict(Space, dict):
+        def __init__(self, d):
+            dict.__init__(self, d)
+
+    spaces.Space, spaces.Box, spaces.Dict = Space, Box, Dict
+    gutils = types.ModuleType("gym.utils")
+    seeding = types.ModuleType("gym.utils.seeding")
+    seeding.np_random = lambda seed=None: (np.random.RandomState(seed), seed)
+    gutils.seeding = seeding
+    gym.Env, gym.spaces, gym.utils = type("Env", (), {}), spaces, gutils
+    sys.modules.update({"gym": gym, "gym.spaces": spaces, "gym.utils": gutils, "gym.utils.seeding": seeding})
+    r2d = types.ModuleType("gym_auv.render2d")
+    r2d.__path__ = []
+    st = types.ModuleType("gym_auv.render2d.state")
+    st.RenderableState = type("RenderableState", (), {})
+    rd = types.ModuleType("gym_auv.render2d.renderer")
+    rd.Renderer2d, rd.FPS = type("Renderer2d", (), {}), 30
+    r2d.state, r2d.renderer = st, rd
+    sys.modules.update({"gym_auv.render2d": r2d, "gym_auv.render2d.state": st, "gym_auv.render2d.renderer": rd})
 
 
 def ns(**kw):
@@ -315,6 +352,102 @@ def main():
         rout_colav.append(float(rc.calculate()))
         rout_pf.append(float(rp.calculate()))
     out.update(rew_in=np.array(rin), rew_colav=np.array(rout_colav), rew_pathfollow=np.array(rout_pf))
+
+    # ---------------------------------------------------------------- BaseEnvironment episodes
+    import contextlib
+    import io
+
+    envm = importlib.import_module("gym_auv.environment")
+    Config = sys.modules["gym_auv"].Config
+
+    def env_config(dt, use_lidar, max_timesteps, min_cum):
+        c = Config()
+        base = make_config(dt=dt)
+        c.vessel = base.vessel
+        c.vessel.use_lidar = use_lidar
+        c.vessel.dense_observation_size = 6
+        c.vessel.n_lidar_observations = R
+        c.vessel.use_dict_observation = False
+        c.vessel.sensor_use_velocity_observations = False
+        c.vessel.sensor_interval_load_obstacles = 25
+        c.simulation = base.simulation
+        c.episode = base.episode
+        c.episode.max_timesteps = max_timesteps
+        c.episode.min_cumulative_reward = min_cum
+        return c
+
+    ep = {k: [] for k in ("obs0", "obs", "reward", "done", "reached", "collision", "goal", "progress", "cum", "T",
+                          "actions", "init", "wp", "cfg", "history")}
+    Tmax = 120
+    specs = [  # (rewarder, use_lidar, dt, max_timesteps, min_cumulative_reward, test_mode, start_s_frac, thrust)
+        ("colav", True, 1.0, 40, -2000.0, False, 0.0, 0.3),      # ends by the time limit (t_step >= max - 1)
+        ("colav", True, 1.0, 10000, -60.0, False, 0.0, -1.0),    # ends by the cumulative-reward limit (no thrust: slow penalty)
+        ("colav", True, 1.0, 10000, -2000.0, False, 0.97, 1.0),  # reaches the goal (progress >= 0.99)
+        ("pathfollow", False, 0.5, 10000, -2000.0, False, 0.90, 1.0),
+        ("colav", True, 1.0, 30, -10.0, True, 0.0, 0.5),         # test_mode: neither limit ends the episode
+    ]
+    for k, (rname, use_lidar, dt, max_t, min_cum, test_mode, s_frac, thrust) in enumerate(specs):
+        erng = np.random.RandomState(400 + k)
+        wp = np.array([[0.0, 60.0, 150.0, 260.0], [0.0, 35.0, 20.0, -40.0]]) if k % 2 == 0 else np.array([[25.0, 25.0], [10.0, 200.0]])
+        path0 = pathm.Path(wp)
+        s0 = s_frac * path0.length
+        init = np.hstack([path0(s0) + (erng.rand(2) - 0.5) * 4.0, path0.get_direction(s0) + (erng.rand() - 0.5) * 0.4])
+
+        class Scn(envm.BaseEnvironment):
+            def __init__(self, *a, **kw):
+                self._rewarder_class = rew.ColavRewarder if rname == "colav" else rew.PathFollowRewarder
+                self._n_moving_obst = self._n_moving_stat = 0
+                super().__init__(*a, **kw)
+
+            def _generate(self):
+                self.path = pathm.Path(wp)
+                self.vessel = vesselm.Vessel(self.config, init)
+                self.obstacles = []
+                self.rewarder = None
+
+        cfg = env_config(dt, use_lidar, max_t, min_cum)
+        with contextlib.redirect_stdout(io.StringIO()):  # the reference prints its config and episode info
+            env = Scn(cfg, test_mode=test_mode, renderer=None)
+            obs0 = np.array(env.observe())  # what reset() returned
+            D = len(obs0)
+            rec = {kk: [] for kk in ("obs", "reward", "done", "reached", "collision", "goal", "progress", "cum")}
+            acts = np.stack([np.full(Tmax, thrust) + erng.uniform(-0.1, 0.1, Tmax), erng.uniform(-0.5, 0.5, Tmax)], axis=1)
+            acts = acts.astype(np.float32).astype(np.float64)
+            T = 0
+            for a in acts:
+                o, r_, d_, info = env.step(np.array(a))
+                T += 1
+                rec["obs"].append(np.array(o))
+                rec["reward"].append(float(r_))
+                rec["done"].append(bool(d_))
+                rec["reached"].append(bool(info["reached_goal"]))
+                rec["collision"].append(bool(info["collision"]))
+                rec["goal"].append(float(info["goal_distance"]))
+                rec["progress"].append(float(info["progress"]))
+                rec["cum"].append(float(env.cumulative_reward))
+                if d_ or T >= (60 if test_mode else Tmax):
+                    break
+            env.reset()  # files the finished episode under env.history (environment.py:476-489)
+        h = env.history[-1]
+        pad = lambda a, shape: np.concatenate([np.asarray(a, dtype=np.float64).reshape((len(a),) + shape[1:]),
+                                               np.full((shape[0] - len(a),) + shape[1:], np.nan)])
+        o186 = lambda o: np.concatenate([o, np.full(186 - len(o), np.nan)])
+        ep["obs0"].append(o186(obs0))
+        ep["obs"].append(pad([o186(o) for o in rec["obs"]], (Tmax, 186)))
+        for kk in ("reward", "goal", "progress", "cum"):
+            ep[kk].append(pad(rec[kk], (Tmax,)))
+        for kk in ("done", "reached", "collision"):
+            ep[kk].append(pad(np.array(rec[kk], dtype=np.float64), (Tmax,)))
+        ep["T"].append(T)
+        ep["actions"].append(acts)
+        ep["init"].append(init)
+        w = np.full((2, 4), np.nan)
+        w[:, : wp.shape[1]] = wp
+        ep["wp"].append(w)
+        ep["cfg"].append([float(rname == "colav"), float(use_lidar), dt, max_t, min_cum, float(test_mode)])
+        ep["history"].append([h["cross_track_error"], h["reached_goal"], h["collision"], h["reward"], h["timesteps"],
+                              h["duration"], h["progress"], h["pathlength"]])
+    out.update({"env_" + k: np.array(v) for k, v in ep.items()})
 
     np.savez_compressed(os.path.join(OUT, "reference_stubbed.npz"), **out)
     print("wrote", os.path.join(OUT, "reference_stubbed.npz"), {k: np.asarray(v).shape for k, v in out.items()})

@@ -832,3 +832,44 @@ def test_moving_obstacle_tracks_match_reference_vessel_obstacle_on_gpu(k):
             assert np.abs(pos - STUBBED["trk_pos"][k, t + 1]).max() <= 1e-9, t
             assert abs(math.atan2(disp[1], disp[0]) - STUBBED["trk_head"][k, t + 1]) <= 1e-12
             assert abs(float(env.get_attr("mov_counter")[0, 0]) - STUBBED["trk_counter"][k, t + 1]) <= 1e-12
+
+
+@pytest.mark.parametrize("k", range(5))
+def test_whole_episodes_match_reference_base_environment_on_gpu(k):
+    """One env through auv_step against the reference's BaseEnvironment episodes (gym / renderer
+    stubbed, obstacle-free): obs, reward, done by time limit / reward limit / goal, info, and -- via
+    the auto-reset that follows the done -- the env.history entry of the episode."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+    from tests.test_reference_goldens_stubbed import _env_case
+
+    cfg, scn, test_mode, T, D = _env_case(k)
+    env = AUVVecEnv(scn, 1, cfg, test_mode=test_mode, auto_reset=True)
+    obs0 = env.reset().cpu().numpy()[0].copy()
+    assert obs0.shape == (D,) and np.abs(obs0 - STUBBED["env_obs0"][k][:D]).max() <= 2e-6
+    acts = torch.as_tensor(STUBBED["env_actions"][k], dtype=torch.float32, device="cuda")
+    for t in range(T):
+        obs, rew, done, info = env.step(acts[t][None])
+        d = bool(done[0].item())
+        assert d == bool(STUBBED["env_done"][k, t]), t
+        o = (info["terminal_observation"] if d else obs)[0].cpu().numpy()
+        assert np.abs(o - STUBBED["env_obs"][k, t, :D]).max() <= 2e-6, t
+        r = float(rew[0].item())
+        assert abs(r - STUBBED["env_reward"][k, t]) <= 1e-5 * max(1.0, abs(r)), t  # reward[] is float32
+        assert bool(info["reached_goal"][0].item()) == bool(STUBBED["env_reached"][k, t])
+        assert not bool(info["collision"][0].item())
+        assert abs(float(info["goal_distance"][0]) - STUBBED["env_goal"][k, t]) <= 1e-4
+        assert abs(float(info["progress"][0]) - STUBBED["env_progress"][k, t]) <= 1e-6
+        if not d:
+            cum = float(env.get_attr("cumulative_reward")[0])
+            assert abs(cum - STUBBED["env_cum"][k, t]) <= 1e-5 * max(1.0, abs(cum))
+    h = STUBBED["env_history"][k]
+    st = env.episode_stats(reduce=False)
+    if bool(STUBBED["env_done"][k, T - 1]):  # the finished episode was filed by the in-step auto-reset
+        assert st["episodes"] == 1.0
+        assert abs(st["cross_track_error"] - h[0]) <= 1e-6 * max(1.0, h[0])
+        assert st["reached_goal"] == h[1] and st["collision"] == h[2]
+        assert abs(st["reward"] - h[3]) <= 1e-5 * max(1.0, abs(h[3]))
+        assert st["timesteps"] == h[4] and abs(st["duration"] - h[5]) <= 1e-12
+        assert abs(st["progress"] - h[6]) <= 1e-9 and abs(st["pathlength"] - h[7]) <= 1e-9
+    else:
+        assert st["episodes"] == 0.0

@@ -156,3 +156,39 @@ def test_rewarders_match_reference_classes():
             max_progress=maxprog, state=np.array([0, 0, 0, 0, 0, yaw]))
         assert abs(O.colav_reward(v) - want_c) <= 1e-9 * max(1.0, abs(want_c))
         assert abs(O.pathfollow_reward(v) - want_p) <= 1e-9 * max(1.0, abs(want_p))
+
+
+def _env_case(k):
+    """Scenario / config of BaseEnvironment episode k of the golden file."""
+    colav, use_lidar, dt, max_t, min_cum, test_mode = GOLD["env_cfg"][k]
+    wp = GOLD["env_wp"][k]
+    wp = wp[:, ~np.isnan(wp[0])]
+    cfg = lidar_config() if use_lidar else Config()
+    cfg.simulation.t_step_size = float(dt)
+    cfg.episode.max_timesteps = int(max_t)
+    cfg.episode.min_cumulative_reward = float(min_cum)
+    scn = S._single(wp, vessel_init=GOLD["env_init"][k], rewarder="colav" if colav else "pathfollow")
+    return cfg, scn, bool(test_mode), int(GOLD["env_T"][k]), (186 if use_lidar else 6)
+
+
+@pytest.mark.parametrize("k", range(5))
+def test_whole_episodes_match_reference_base_environment(k):
+    """reset / step / observe / _isdone of the reference's BaseEnvironment (gym and the renderer
+    stubbed, obstacle-free scenarios): observation vectors, rewards, done by time limit / reward
+    limit / reached goal, info, cumulative reward, and the env.history entry."""
+    cfg, scn, test_mode, T, D = _env_case(k)
+    env = O.OracleEnv(scn.describe(0), oracle_cfg(cfg), test_mode=test_mode)
+    obs0 = env.observe()
+    assert np.abs(obs0 - GOLD["env_obs0"][k][:D]).max() <= 1e-9
+    for t in range(T):
+        obs, rew, done, info = env.step(GOLD["env_actions"][k][t])
+        assert np.abs(obs - GOLD["env_obs"][k, t, :D]).max() <= 1e-9, t
+        assert abs(rew - GOLD["env_reward"][k, t]) <= 1e-9 * max(1.0, abs(rew)), t
+        assert done == bool(GOLD["env_done"][k, t]), t
+        assert info["reached_goal"] == bool(GOLD["env_reached"][k, t]) and not info["collision"]
+        assert abs(info["goal_distance"] - GOLD["env_goal"][k, t]) <= 1e-9
+        assert abs(info["progress"] - GOLD["env_progress"][k, t]) <= 1e-10
+        assert abs(env.cumulative_reward - GOLD["env_cum"][k, t]) <= 1e-9 * max(1.0, abs(env.cumulative_reward))
+    h = GOLD["env_history"][k]  # cross_track_error, reached_goal, collision, reward, timesteps, duration, progress, pathlength
+    assert abs(np.mean(env.cross_track_errors) - h[0]) <= 1e-9
+    assert env.t_step == int(h[4]) and abs(env.path.length - h[7]) <= 1e-9
