@@ -20,6 +20,9 @@ Parity status
   culling-window integers incl. Python's negative-index wrap (``sensor.py:41-97``), feasibility
   pooling, ``Path`` / ``RandomCurveThroughOrigin``, ``Vessel.step`` + ``Vessel.navigate`` rollouts,
   ``VesselObstacle`` tracks and both rewarders (``tests/test_reference_goldens_stubbed.py``).
+* ``tests/golden/make_reference_goldens_hybrid.py`` runs the reference's LiDAR pipeline classes
+  unmodified on ``geos_lite`` primitives and pins the glue (nearby list, per-ray obstacle lists,
+  min over intersection pieces, closeness, collision, obs, reward) -- not the primitives.
 * what the reference computes INSIDE Shapely 1.7.0 / GEOS (ray/boundary
   intersection, ``Point.distance``, ``LineString.project``, ``buffer().simplify()``,
   ``minimum_rotated_rectangle``, ``affinity.rotate``) is restated from GEOS' published

@@ -873,3 +873,32 @@ def test_whole_episodes_match_reference_base_environment_on_gpu(k):
         assert abs(st["progress"] - h[6]) <= 1e-9 and abs(st["pathlength"] - h[7]) <= 1e-9
     else:
         assert st["episodes"] == 0.0
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_lidar_pipeline_matches_reference_classes_on_geos_lite_on_gpu(k):
+    """The CUDA step against the reference's own LiDAR pipeline classes run on geos_lite
+    primitives (tests/golden/make_reference_goldens_hybrid.py): ranges within the FP32 casting
+    tolerance, closeness / obs, rewards, collision and done flags -- no oracle code in the loop
+    except those primitives."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+    from tests._parity import COLLISION_BAND, RANGE_ATOL, RANGE_RTOL, REWARD_ATOL, REWARD_RTOL
+    from tests.test_reference_goldens_stubbed import HYB, hybrid_case
+
+    cfg, scn, T = hybrid_case(k)
+    env = AUVVecEnv(scn, 1, cfg, test_mode=True, auto_reset=False, debug=True)
+    obs0 = env.reset().cpu().numpy()[0]
+    assert np.abs(obs0 - HYB["obs0"][k]).max() <= 2e-5
+    acts = torch.as_tensor(HYB["actions"][k], dtype=torch.float32, device="cuda")
+    for t in range(T):
+        obs, rew, done, info = env.step(acts[t][None])
+        d_ref = HYB["dists"][k, t]
+        d_gpu = env.get_attr("lidar_dist")[0].cpu().numpy()
+        assert np.all(np.abs(d_gpu - d_ref) <= RANGE_ATOL + RANGE_RTOL * d_ref), (t, np.abs(d_gpu - d_ref).max())
+        assert np.abs(obs[0].cpu().numpy() - HYB["obs"][k, t]).max() <= 1e-4, t
+        if abs(d_ref.min() - cfg.vessel.vessel_width) > COLLISION_BAND:
+            assert bool(info["collision"][0].item()) == bool(HYB["collision"][k, t]), t
+            assert bool(done[0].item()) == bool(HYB["done"][k, t]), t
+            r = float(rew[0].item())
+            assert abs(r - HYB["reward"][k, t]) <= REWARD_ATOL + REWARD_RTOL * abs(r), t
+        assert int(env._scratch["rec_cnt"][0].item()) == int(HYB["n_nearby"][k, t]), t

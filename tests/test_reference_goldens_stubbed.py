@@ -192,3 +192,45 @@ def test_whole_episodes_match_reference_base_environment(k):
     h = GOLD["env_history"][k]  # cross_track_error, reached_goal, collision, reward, timesteps, duration, progress, pathlength
     assert abs(np.mean(env.cross_track_errors) - h[0]) <= 1e-9
     assert env.t_step == int(h[4]) and abs(env.path.length - h[7]) <= 1e-9
+
+
+# ---------------------------------------------------------------------------------------
+# HYBRID goldens: the reference's LiDAR pipeline classes run on oracle/geos_lite primitives
+# (tests/golden/make_reference_goldens_hybrid.py) -- pins the glue, not the primitives
+# ---------------------------------------------------------------------------------------
+HYB = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_hybrid.npz"))
+
+
+def hybrid_case(k):
+    wp = HYB["scn_waypoints"][k]
+    wp = wp[:, ~np.isnan(wp[0])]
+    Km, Ks = HYB["scn_mov_width"][k].shape[0], HYB["scn_st_radius"][k].shape[0]
+    mov_track = np.zeros((1, Km, 4), dtype=np.int32)
+    mov_track[0, :, 0] = np.arange(Km)
+    mov_track[0, :, 1] = S.VESSEL_TRACK_LEN
+    scn = S.ScenarioSet(
+        waypoints=[wp], path_id=np.zeros(1, dtype=np.int32), vessel_init=HYB["scn_vessel_init"][k][None],
+        mov_start=HYB["scn_mov_start"][k][None], mov_width=HYB["scn_mov_width"][k][None], mov_track=mov_track,
+        vel_table=HYB["scn_vel"][k].copy(), st_pos=HYB["scn_st_pos"][k][None], st_radius=HYB["scn_st_radius"][k][None],
+        rewarder="colav", post_generate_update=True, name="hybrid")
+    cfg = lidar_config()
+    cfg.simulation.t_step_size = float(HYB["dt"][k])
+    return cfg, scn, int(HYB["T"][k])
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_lidar_pipeline_matches_reference_classes_on_geos_lite(k):
+    """Vessel.perceive / simulate_sensor / _standardize_intersect / obstacle classes of the
+    reference, run unmodified on geos_lite primitives, against the oracle's restatement of the same
+    pipeline: nearby-list size and refresh, every ray's range, closeness, collision, obs, reward."""
+    cfg, scn, T = hybrid_case(k)
+    env = O.OracleEnv(scn.describe(0), oracle_cfg(cfg), test_mode=True)
+    assert np.abs(env.observe() - HYB["obs0"][k]).max() <= 1e-9
+    for t in range(T):
+        obs, rew, done, info = env.step(HYB["actions"][k][t])
+        assert len(env.vessel.nearby) == int(HYB["n_nearby"][k, t]), t
+        assert np.abs(env.vessel.dists - HYB["dists"][k, t]).max() <= 1e-9, t
+        assert np.abs(obs - HYB["obs"][k, t]).max() <= 1e-9, t
+        assert abs(rew - HYB["reward"][k, t]) <= 1e-9 * max(1.0, abs(rew)), t
+        assert info["collision"] == bool(HYB["collision"][k, t]) and done == bool(HYB["done"][k, t])
+        assert info["reached_goal"] == bool(HYB["reached"][k, t])
