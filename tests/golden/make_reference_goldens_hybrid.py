@@ -296,6 +296,78 @@ def main():
         print("case", seed, "steps", n, "collision", any(rec["collision"]), "min range %.3f" % np.min(rec["dists"]),
               "nearby", sorted(set(rec["n_nearby"])))
     out.update({"scn_" + k: v for k, v in scenario_arrays.items()})
+    # ------------------------------------------------------------------ the reference's own scenario class
+    # MovingObstaclesNoRules (envs/movingobstacles.py:17-104: 17 vessels + 11 circles, ColavRewarder)
+    # generates its scenarios with its own RNG calls; the generated scenario is read back from the
+    # env (path waypoints, vessel start, obstacle tracks / circles) so that the same episode can be
+    # replayed through the oracle and the CUDA path ("the reference's own step() on identical inputs").
+    envs_pkg = types.ModuleType("gym_auv.envs")
+    envs_pkg.__path__ = [os.path.join(stubbed.REF, "envs")]
+    sys.modules["gym_auv.envs"] = envs_pkg
+    mo = importlib.import_module("gym_auv.envs.movingobstacles")
+    Tm = 50
+    mo_out = {k: [] for k in ("waypoints", "vessel_init", "mov_start", "mov_width", "vel", "st_pos", "st_radius", "obs0",
+                              "obs", "reward", "done", "collision", "dists", "n_nearby", "actions", "T")}
+    gen_stats = {k: [] for k in ("mov_width", "st_radius", "speed", "mov_dist", "st_dist", "init_offset")}
+    for seed in range(12):
+        with contextlib.redirect_stdout(io.StringIO()):
+            np.random.seed(seed)
+            env = mo.MovingObstaclesNoRules(env_config(1.0), test_mode=True, renderer=None)
+            # the constructor already ran reset() -> _generate(); that scenario is the one recorded
+            mov = [o for o in env.obstacles if not o.static]
+            sta = [o for o in env.obstacles if o.static]
+            v0 = np.array(env.vessel._state[:3])
+            start = np.array([o.trajectory[0][1] for o in mov])
+            vel = np.array([o.trajectory_velocities[0] for o in mov])
+            width = np.array([o.width for o in mov], dtype=np.float64)
+            spos = np.array([o.position for o in sta])
+            srad = np.array([o.radius for o in sta], dtype=np.float64)
+            gen_stats["mov_width"] += list(width)
+            gen_stats["st_radius"] += list(srad)
+            gen_stats["speed"] += list(np.linalg.norm(vel, axis=1))
+            gen_stats["mov_dist"] += list(np.linalg.norm(start - v0[:2], axis=1))
+            gen_stats["st_dist"] += list(np.linalg.norm(spos - v0[:2], axis=1))
+            gen_stats["init_offset"] += list(v0[:2] - env.path(0))
+            if seed >= 3:
+                continue  # seeds 3.. only feed the generator statistics
+            obs0 = np.array(env.observe())
+            arng = np.random.RandomState(700 + seed)
+            acts = arng.uniform([0.0, -0.15], [1.0, 0.15], size=(Tm, 2)).astype(np.float32).astype(np.float64)
+            rec = {k: [] for k in ("obs", "reward", "done", "collision", "dists", "n_nearby")}
+            n = 0
+            for a in acts:
+                o, r_, d_, info = env.step(np.array(a))
+                n += 1
+                rec["obs"].append(np.array(o))
+                rec["reward"].append(float(r_))
+                rec["done"].append(bool(d_))
+                rec["collision"].append(bool(info["collision"]))
+                rec["dists"].append(np.array(env.vessel._last_sensor_dist_measurements, dtype=np.float64))
+                rec["n_nearby"].append(len(env.vessel._nearby_obstacles))
+                if d_:
+                    break
+        w = np.full((2, 16), np.nan)
+        w[:, : env.path.init_waypoints.shape[1]] = env.path.init_waypoints
+        mo_out["waypoints"].append(w)
+        mo_out["vessel_init"].append(v0)
+        mo_out["mov_start"].append(start)
+        mo_out["mov_width"].append(width)
+        mo_out["vel"].append(vel)
+        mo_out["st_pos"].append(spos)
+        mo_out["st_radius"].append(srad)
+        mo_out["obs0"].append(obs0)
+        mo_out["obs"].append(pad(rec["obs"], (Tm, 186)))
+        mo_out["dists"].append(pad(rec["dists"], (Tm, 180)))
+        mo_out["reward"].append(pad(rec["reward"], (Tm,)))
+        for k in ("done", "collision", "n_nearby"):
+            mo_out[k].append(pad(np.array(rec[k], dtype=np.float64), (Tm,)))
+        mo_out["actions"].append(acts)
+        mo_out["T"].append(n)
+        print("MovingObstaclesNoRules seed", seed, "steps", n, "min range %.2f" % np.min(rec["dists"]), "nearby",
+              sorted(set(rec["n_nearby"])))
+    out.update({"mo_" + k: v for k, v in mo_out.items()})
+    out.update({"gen_" + k: np.array(v) for k, v in gen_stats.items()})
+
     np.savez_compressed(os.path.join(HERE, "reference_hybrid.npz"), **{k: np.array(v) for k, v in out.items()})
     print("wrote reference_hybrid.npz")
 

@@ -902,3 +902,48 @@ def test_lidar_pipeline_matches_reference_classes_on_geos_lite_on_gpu(k):
             r = float(rew[0].item())
             assert abs(r - HYB["reward"][k, t]) <= REWARD_ATOL + REWARD_RTOL * abs(r), t
         assert int(env._scratch["rec_cnt"][0].item()) == int(HYB["n_nearby"][k, t]), t
+
+
+@pytest.mark.parametrize("k", range(3))
+def test_reference_movingobstacles_class_episodes_on_gpu(k):
+    """The CUDA step on scenarios generated by the reference's own MovingObstaclesNoRules._generate,
+    against that class's own step() (geometry primitives from geos_lite): BASELINE config 1."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+    from tests._parity import COLLISION_BAND, RANGE_ATOL, RANGE_RTOL, REWARD_ATOL, REWARD_RTOL
+    from tests.test_reference_goldens_stubbed import HYB, movingobstacles_case
+
+    cfg, scn, T = movingobstacles_case(k)
+    env = AUVVecEnv(scn, 1, cfg, test_mode=True, auto_reset=False, debug=True)
+    assert np.abs(env.reset().cpu().numpy()[0] - HYB["mo_obs0"][k]).max() <= 2e-5
+    acts = torch.as_tensor(HYB["mo_actions"][k], dtype=torch.float32, device="cuda")
+    for t in range(T):
+        obs, rew, done, info = env.step(acts[t][None])
+        d_ref = HYB["mo_dists"][k, t]
+        d_gpu = env.get_attr("lidar_dist")[0].cpu().numpy()
+        assert np.all(np.abs(d_gpu - d_ref) <= RANGE_ATOL + RANGE_RTOL * d_ref), (t, np.abs(d_gpu - d_ref).max())
+        assert np.abs(obs[0].cpu().numpy() - HYB["mo_obs"][k, t]).max() <= 1e-4, t
+        assert int(env._scratch["rec_cnt"][0].item()) == int(HYB["mo_n_nearby"][k, t]), t
+        if abs(d_ref.min() - cfg.vessel.vessel_width) > COLLISION_BAND:
+            assert bool(info["collision"][0].item()) == bool(HYB["mo_collision"][k, t])
+            assert bool(done[0].item()) == bool(HYB["mo_done"][k, t])
+            r = float(rew[0].item())
+            assert abs(r - HYB["mo_reward"][k, t]) <= REWARD_ATOL + REWARD_RTOL * abs(r), t
+
+
+def test_gpu_scenario_generator_matches_reference_generate_statistics():
+    """auv_generate_moving_obstacles against 12 scenarios drawn by the reference's own
+    MovingObstacles._generate + helpers.generate_obstacle (204 vessels, 132 circles)."""
+    from tests.test_reference_goldens_stubbed import HYB
+
+    _, _, env = _generated_env(M=2048, n_paths=64, seed=4)
+    env.regenerate_scenarios(seed=99, epoch=1)
+    g = env.pull_scenarios()
+    v0 = g.vessel_init[:, None, :2]
+    stats = {
+        "mov_width": g.mov_width.ravel(), "st_radius": g.st_radius.ravel(), "speed": np.linalg.norm(g.vel_table, axis=1),
+        "mov_dist": np.linalg.norm(g.mov_start - v0, axis=2).ravel(), "st_dist": np.linalg.norm(g.st_pos - v0, axis=2).ravel(),
+    }
+    for key, mine in stats.items():
+        ref = HYB["gen_" + key]
+        se = ref.std() / math.sqrt(len(ref)) + mine.std() / math.sqrt(len(mine))
+        assert abs(ref.mean() - mine.mean()) <= 4.0 * se, (key, ref.mean(), mine.mean(), se)

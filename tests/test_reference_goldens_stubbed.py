@@ -234,3 +234,57 @@ def test_lidar_pipeline_matches_reference_classes_on_geos_lite(k):
         assert abs(rew - HYB["reward"][k, t]) <= 1e-9 * max(1.0, abs(rew)), t
         assert info["collision"] == bool(HYB["collision"][k, t]) and done == bool(HYB["done"][k, t])
         assert info["reached_goal"] == bool(HYB["reached"][k, t])
+
+
+def movingobstacles_case(k):
+    """Scenario k generated by the reference's MovingObstaclesNoRules._generate (read back from the env)."""
+    HYB2 = HYB
+    wp = HYB2["mo_waypoints"][k]
+    wp = wp[:, ~np.isnan(wp[0])]
+    Km, Ks = HYB2["mo_mov_width"][k].shape[0], HYB2["mo_st_radius"][k].shape[0]
+    mov_track = np.zeros((1, Km, 4), dtype=np.int32)
+    mov_track[0, :, 0] = np.arange(Km)
+    mov_track[0, :, 1] = S.VESSEL_TRACK_LEN
+    scn = S.ScenarioSet(
+        waypoints=[wp], path_id=np.zeros(1, dtype=np.int32), vessel_init=HYB2["mo_vessel_init"][k][None],
+        mov_start=HYB2["mo_mov_start"][k][None], mov_width=HYB2["mo_mov_width"][k][None], mov_track=mov_track,
+        vel_table=HYB2["mo_vel"][k].copy(), st_pos=HYB2["mo_st_pos"][k][None], st_radius=HYB2["mo_st_radius"][k][None],
+        rewarder="colav", post_generate_update=True, name="MovingObstaclesNoRules-v0")
+    return lidar_config(), scn, int(HYB2["mo_T"][k])
+
+
+@pytest.mark.parametrize("k", range(3))
+def test_reference_movingobstacles_class_episodes(k):
+    """Episodes of the reference's own MovingObstaclesNoRules (17 vessels + 11 circles, its own
+    _generate and step(), geometry primitives from geos_lite) replayed through the oracle."""
+    cfg, scn, T = movingobstacles_case(k)
+    assert scn.k_moving == 17 and scn.k_static == 11
+    env = O.OracleEnv(scn.describe(0), oracle_cfg(cfg), test_mode=True)
+    assert np.abs(env.observe() - HYB["mo_obs0"][k]).max() <= 1e-9
+    for t in range(T):
+        obs, rew, done, info = env.step(HYB["mo_actions"][k][t])
+        assert len(env.vessel.nearby) == int(HYB["mo_n_nearby"][k, t]), t
+        assert np.abs(env.vessel.dists - HYB["mo_dists"][k, t]).max() <= 1e-9, t
+        assert np.abs(obs - HYB["mo_obs"][k, t]).max() <= 1e-9, t
+        assert abs(rew - HYB["mo_reward"][k, t]) <= 1e-9 * max(1.0, abs(rew)), t
+        assert info["collision"] == bool(HYB["mo_collision"][k, t]) and done == bool(HYB["mo_done"][k, t])
+
+
+def test_host_scenario_generator_matches_reference_generate_statistics():
+    """12 scenarios drawn by the reference's own MovingObstacles._generate + helpers.generate_obstacle
+    (204 vessels, 132 circles) against the host generator's distribution (same parameters, own RNG
+    streams -- the reference mixes a seeded stream with the global np.random)."""
+    mine = S.moving_obstacles(400, 17, 11, seed=123)
+    v0 = mine.vessel_init[:, None, :2]
+    stats = {
+        "mov_width": mine.mov_width.ravel(), "st_radius": mine.st_radius.ravel(),
+        "speed": np.linalg.norm(mine.vel_table, axis=1),
+        "mov_dist": np.linalg.norm(mine.mov_start - v0, axis=2).ravel(),
+        "st_dist": np.linalg.norm(mine.st_pos - v0, axis=2).ravel(),
+    }
+    for key, mine_v in stats.items():
+        ref = HYB["gen_" + key]
+        se = ref.std() / math.sqrt(len(ref)) + mine_v.std() / math.sqrt(len(mine_v))
+        assert abs(ref.mean() - mine_v.mean()) <= 4.0 * se, (key, ref.mean(), mine_v.mean(), se)
+    off = HYB["gen_init_offset"]
+    assert np.abs(off).max() <= 25.0 and HYB["gen_mov_width"].min() >= 1 and HYB["gen_speed"].min() >= 1.0
