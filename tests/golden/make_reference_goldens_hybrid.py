@@ -311,9 +311,12 @@ def main():
     gen_stats = {k: [] for k in ("mov_width", "st_radius", "speed", "mov_dist", "st_dist", "init_offset")}
     for seed in range(12):
         with contextlib.redirect_stdout(io.StringIO()):
-            np.random.seed(seed)
             env = mo.MovingObstaclesNoRules(env_config(1.0), test_mode=True, renderer=None)
-            # the constructor already ran reset() -> _generate(); that scenario is the one recorded
+            # the constructor seeds itself from the OS (environment.py:96,439-442); reseed the way
+            # SURVEY 8d prescribes and generate the scenario that is recorded
+            np.random.seed(seed)
+            env.seed(seed)
+            env.reset()
             mov = [o for o in env.obstacles if not o.static]
             sta = [o for o in env.obstacles if o.static]
             v0 = np.array(env.vessel._state[:3])
@@ -365,10 +368,60 @@ def main():
         mo_out["T"].append(n)
         print("MovingObstaclesNoRules seed", seed, "steps", n, "min range %.2f" % np.min(rec["dists"]), "nearby",
               sorted(set(rec["n_nearby"])))
+    # ------------------------------------------------------------------ the deterministic test scenarios
+    # envs/testscenario.py classes instantiated as they are; the scenario each one builds is read
+    # back (path, vessel start, obstacle circles / tracks with their velocity tables) and a short
+    # episode of its step() is recorded.  DebugScenario draws from env.rng -> seeded.
+    ts = importlib.import_module("gym_auv.envs.testscenario")
+    names = ["TestScenario1", "TestScenario2", "TestScenario3", "TestScenario4", "TestHeadOn", "TestCrossing",
+             "TestCrossing1", "EmptyScenario", "DebugScenario"]
+    Tt = 25
+    for name in names:
+        with contextlib.redirect_stdout(io.StringIO()):
+            # The FIRST episode (the constructor's reset()) is what is recorded: a second reset() would
+            # list every circle of TestScenario1-4 twice (they never clear self.obstacles) and would
+            # leave the rewarder bound to the first episode's vessel (these classes never reassign
+            # self.rewarder; environment.py:222-228 only creates one when it is None).  DebugScenario
+            # draws from env.rng, which the constructor seeds from the OS: seed 0 is injected instead.
+            seeding = sys.modules["gym.utils.seeding"]
+            keep = seeding.np_random
+            seeding.np_random = lambda seed=None: (np.random.RandomState(0 if seed is None else seed), seed)
+            try:
+                env = getattr(ts, name)(env_config(1.0), test_mode=True, renderer=None)
+            finally:
+                seeding.np_random = keep
+            mov = [o for o in env.obstacles if not o.static]
+            sta = [o for o in env.obstacles if o.static]
+            arng = np.random.RandomState(800)
+            acts = arng.uniform([0.2, -0.1], [1.0, 0.1], size=(Tt, 2)).astype(np.float32).astype(np.float64)
+            v0 = np.array(env.vessel._state[:3])
+            obs0 = np.array(env.observe())
+            obs, rews, dists, dones = [], [], [], []
+            for a in acts:
+                o, r_, d_, info = env.step(np.array(a))
+                obs.append(np.array(o))
+                rews.append(float(r_))
+                dists.append(np.array(env.vessel._last_sensor_dist_measurements, dtype=np.float64))
+                dones.append(bool(d_))
+                if d_:
+                    break
+        key = "ts_" + name + "_"
+        out[key + "waypoints"] = np.array(env.path.init_waypoints, dtype=np.float64)
+        out[key + "vessel_init"] = v0
+        out[key + "st_pos"] = np.array([o.position for o in sta], dtype=np.float64).reshape(len(sta), 2)
+        out[key + "st_radius"] = np.array([o.radius for o in sta], dtype=np.float64)
+        out[key + "mov_width"] = np.array([o.width for o in mov], dtype=np.float64)
+        out[key + "mov_start"] = np.array([o.trajectory[0][1] for o in mov], dtype=np.float64).reshape(len(mov), 2)
+        out[key + "mov_nvel"] = np.array([len(o.trajectory_velocities) for o in mov], dtype=np.int64)
+        out[key + "mov_vel_head"] = (np.array([np.array(o.trajectory_velocities[:8], dtype=np.float64) for o in mov])
+                                     if mov else np.zeros((0, 8, 2)))
+        out[key + "obs0"], out[key + "obs"], out[key + "reward"] = obs0, np.array(obs), np.array(rews)
+        out[key + "dists"], out[key + "done"], out[key + "actions"] = np.array(dists), np.array(dones), acts
+        print(name, "static", len(sta), "moving", len(mov), "steps", len(obs), "min range %.2f" % np.min(dists))
     out.update({"mo_" + k: v for k, v in mo_out.items()})
     out.update({"gen_" + k: np.array(v) for k, v in gen_stats.items()})
 
-    np.savez_compressed(os.path.join(HERE, "reference_hybrid.npz"), **{k: np.array(v) for k, v in out.items()})
+    np.savez_compressed(os.path.join(HERE, "reference_hybrid.npz"), **{k: np.asarray(v) for k, v in out.items()})
     print("wrote reference_hybrid.npz")
 
 

@@ -947,3 +947,27 @@ def test_gpu_scenario_generator_matches_reference_generate_statistics():
         ref = HYB["gen_" + key]
         se = ref.std() / math.sqrt(len(ref)) + mine.std() / math.sqrt(len(mine))
         assert abs(ref.mean() - mine.mean()) <= 4.0 * se, (key, ref.mean(), mine.mean(), se)
+
+
+@pytest.mark.parametrize("name", ["TestScenario1", "TestScenario3", "TestScenario4", "TestHeadOn", "TestCrossing",
+                                  "TestCrossing1", "EmptyScenario", "DebugScenario"])
+def test_registered_scenario_episodes_match_reference_classes_on_gpu(name):
+    """25 steps of each reference test-scenario class (its own step(), geos_lite primitives) against
+    the CUDA step on the PRODUCT's definition of that scenario id."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+    from tests._parity import RANGE_ATOL, RANGE_RTOL, REWARD_ATOL, REWARD_RTOL
+    from tests.test_reference_goldens_stubbed import HYB, _product_scenario
+
+    g = lambda k: HYB["ts_" + name + "_" + k]
+    cfg = lidar_config()
+    env = AUVVecEnv(_product_scenario(name), 1, cfg, test_mode=True, auto_reset=False, debug=True)
+    assert np.abs(env.reset().cpu().numpy()[0] - g("obs0")).max() <= 2e-5
+    acts = torch.as_tensor(g("actions"), dtype=torch.float32, device="cuda")
+    for t in range(len(g("obs"))):
+        obs, rew, done, _ = env.step(acts[t][None])
+        d_ref, d_gpu = g("dists")[t], env.get_attr("lidar_dist")[0].cpu().numpy()
+        assert np.all(np.abs(d_gpu - d_ref) <= RANGE_ATOL + RANGE_RTOL * d_ref), (t, np.abs(d_gpu - d_ref).max())
+        assert np.abs(obs[0].cpu().numpy() - g("obs")[t]).max() <= 1e-4, t
+        r = float(rew[0].item())
+        assert abs(r - g("reward")[t]) <= REWARD_ATOL + REWARD_RTOL * abs(r), t
+        assert bool(done[0].item()) == bool(g("done")[t])

@@ -288,3 +288,57 @@ def test_host_scenario_generator_matches_reference_generate_statistics():
         assert abs(ref.mean() - mine_v.mean()) <= 4.0 * se, (key, ref.mean(), mine_v.mean(), se)
     off = HYB["gen_init_offset"]
     assert np.abs(off).max() <= 25.0 and HYB["gen_mov_width"].min() >= 1 and HYB["gen_speed"].min() >= 1.0
+
+
+TS_NAMES = ["TestScenario1", "TestScenario2", "TestScenario3", "TestScenario4", "TestHeadOn", "TestCrossing",
+            "TestCrossing1", "EmptyScenario", "DebugScenario"]
+
+
+def _product_scenario(name):
+    """The product's scenario of that id; TestHeadOn's start angle is drawn from the global `random`
+    upstream (testscenario.py:145) and an explicit argument here: take it from the recorded start."""
+    if name == "TestHeadOn":
+        sx, sy = HYB["ts_TestHeadOn_mov_start"][0] - HYB["ts_TestHeadOn_vessel_init"][:2]
+        return S.test_head_on(start_angle=math.atan2(sx, sy))
+    return S.SCENARIOS[name + "-v0"]()
+
+
+@pytest.mark.parametrize("name", TS_NAMES)
+def test_registered_scenarios_equal_the_reference_scenario_classes(name):
+    """gym_auv_b200.scenarios.SCENARIOS[<id>] against what the reference's envs/testscenario.py class
+    of the same id builds (instantiated behind the stubs, scenario read back from the env): path,
+    vessel start, every circle, every vessel track (start, width, velocity table)."""
+    g = lambda k: HYB["ts_" + name + "_" + k]
+    scn = _product_scenario(name)
+    assert np.abs(scn.waypoints[0] - g("waypoints")).max() <= 1e-12
+    vi = scn.vessel_init[0]
+    assert np.abs(vi[:2] - g("vessel_init")[:2]).max() <= 1e-9
+    assert abs(math.remainder(vi[2] - g("vessel_init")[2], 2 * math.pi)) <= 1e-12
+    used = scn.st_radius[0] > 0
+    assert used.sum() == len(g("st_radius"))
+    if used.any():
+        assert np.abs(scn.st_pos[0][used] - g("st_pos")).max() <= 1e-9
+        assert np.abs(scn.st_radius[0][used] - g("st_radius")).max() <= 1e-12
+    mused = scn.mov_width[0] > 0
+    assert mused.sum() == len(g("mov_width"))
+    for j, slot in enumerate(np.nonzero(mused)[0]):
+        off, ln, stride, _ = scn.mov_track[0, slot]
+        assert scn.mov_width[0, slot] == g("mov_width")[j] and ln == int(g("mov_nvel")[j])
+        assert np.abs(scn.mov_start[0, slot] - g("mov_start")[j]).max() <= 1e-9
+        head = scn.vel_table[off + np.arange(8) * stride]
+        assert np.abs(head - g("mov_vel_head")[j]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name", [n for n in TS_NAMES if n != "TestScenario2"])
+def test_registered_scenario_episodes_match_reference_classes(name):
+    """A 25-step episode of each reference test-scenario class (its own step(), geos_lite
+    primitives) replayed through the oracle on the PRODUCT's scenario definition."""
+    g = lambda k: HYB["ts_" + name + "_" + k]
+    scn = _product_scenario(name)
+    env = O.OracleEnv(scn.describe(0), oracle_cfg(lidar_config()), test_mode=True)
+    assert np.abs(env.observe() - g("obs0")).max() <= 1e-9
+    for t in range(len(g("obs"))):
+        obs, rew, done, _ = env.step(g("actions")[t])
+        assert np.abs(env.vessel.dists - g("dists")[t]).max() <= 1e-9, t
+        assert np.abs(obs - g("obs")[t]).max() <= 1e-9 and abs(rew - g("reward")[t]) <= 1e-9 * max(1.0, abs(rew))
+        assert done == bool(g("done")[t])
