@@ -301,16 +301,61 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
-    for i in range(Wm):
-        env.step(actions[i % n_act])
-    barrier()
-    # snapshot so the counting pass can replay the exact same K steps
-    snap = {k: v.clone() for k, v in env._st.items()}
-
+    # ---- warm-up: W steps after reset(); the timed region starts from THIS state (the same
+    #      episode phase the reference arm measures).
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(Wm):
+        env.step(actions[i % n_act])
+    barrier()
+    # snapshot so that the pre-roll below can be undone and the counting pass can replay the K steps
+    snap = {k: v.clone() for k, v in env._st.items()}
+    # ---- pre-roll: ~0.4 s of the same steps.  (1) the clock sampler (nvidia-smi every 100 ms)
+    #      gets several samples under exactly this load -- K steps of 0.2 ms are over before a second
+    #      sample would arrive; (2) its last block measures the steady state thousands of steps into
+    #      the run, when vessels have left their start areas and more obstacles are in range.
+    t_pre = time.perf_counter()
+    i, blk = Wm, 50
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    while True:
+        last = time.perf_counter() - t_pre >= 0.4
+        s0.record()
+        for _ in range(blk):
+            env.step(actions[i % n_act])
+            i += 1
+        s1.record()
+        torch.cuda.synchronize()
+        if last:
+            break
+    steady_ms = s0.elapsed_time(s1) / blk
+    steady_records = float(env._scratch["rec_cnt"].sum().item()) / N
+    import ctypes as C
+
+    cfgp, rays, paths, pool, batch = env._refs()
+    tm = env.lib.auv_timer_create(20)
+    sps = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    for j in range(20):  # per-kernel split of the steady state (single stream)
+        a = actions[(i + j) % n_act]
+        _lib.check(env.lib.auv_step_timed(cfgp, rays, paths, pool, batch, C.c_void_p(a.data_ptr()), C.byref(env.out),
+                                          sps, tm, j), "auv_step_timed")
+    torch.cuda.synchronize()
+    sk = np.zeros((20, 3), dtype=np.float32)
+    for j in range(20):
+        _lib.check(env.lib.auv_timer_read(tm, j, sk[j].ctypes.data_as(C.POINTER(C.c_float))), "auv_timer_read")
+    env.lib.auv_timer_destroy(tm)
+    cross_track = float(env._st["nav"][:, 2].abs().mean().item())
+    t_s = torch.tensor([steady_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+    steady = {"value": world * N / (float(t_s.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t_s.item()),
+              "steps_since_reset": i, "records_per_env_step": steady_records,
+              "kernel_ms": {"k_vessel_nav": float(sk[:, 1].mean()), "k_lidar": float(sk[:, 2].mean())},
+              "mean_abs_cross_track_m": cross_track,
+              "note": "same kernels, measured over the last %d of %d untimed steps (auto-reset running)" % (blk, i)}
+    for k, v in snap.items():
+        env._st[k].copy_(v)
+    barrier()
     stream = torch.cuda.current_stream(device)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cfgp, rays, paths, pool, batch = env._refs()
@@ -535,6 +580,7 @@ def run_ours(args):
                    "scenario_generation": scenario_gen or {"where": "host"},
                    "host_cores_bound": len(numa_cores)},
         "clocks": clocks,
+        "steady_state": steady,
         "e2e": e2e,
         "gpu_launches": 2 * K * n_ranges(N, env.chunks),  # k_vessel_nav + k_lidar per env range
         "roofline": {
