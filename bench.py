@@ -80,6 +80,9 @@ def parse():
     ap.add_argument("--gpu-scenarios", action="store_true",
                     help="sample vessel starts and obstacles on the GPU (auv_generate_moving_obstacles) instead of "
                          "the host generator; same distributions, seconds instead of ~16 s of set-up")
+    ap.add_argument("--preroll-steps", type=int, default=0,
+                    help="untimed steps of the side pre-roll (0 = run for ~0.4 s); a fixed count makes profiler "
+                         "captures of the steady state addressable by launch index")
     ap.add_argument("--scenario-cache", default=None,
                     help="pickle the generated scenario set here / reuse it (tuning sweeps; same seeds => same set)")
     return ap.parse_args()
@@ -319,7 +322,7 @@ def run_ours(args):
     i, blk = Wm, 50
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     while True:
-        last = time.perf_counter() - t_pre >= 0.4
+        last = (i - Wm + blk >= args.preroll_steps) if args.preroll_steps > 0 else (time.perf_counter() - t_pre >= 0.4)
         s0.record()
         for _ in range(blk):
             env.step(actions[i % n_act])

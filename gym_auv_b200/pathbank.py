@@ -18,11 +18,13 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Sequence
 
+import os
+
 import numpy as np
 from scipy import interpolate
 
 PATH_BLOCK = 32  # must equal AUV_PATH_BLOCK in include/auv_b200.h
-PATH_SUPER = 32  # blocks per superblock, AUV_PATH_SUPER
+PATH_SUPER = int(os.environ.get("AUV_PATH_SUPER", 16))  # blocks per superblock, AUV_PATH_SUPER (env override: tuning builds only)
 N_KNOTS = 1000
 
 

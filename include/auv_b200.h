@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 15
+#define AUV_ABI_VERSION 16
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -57,7 +57,9 @@ extern "C" {
 #define AUV_MAX_RAYS 1024
 #define AUV_MAX_OBSTACLES 1024 /* moving + static slots per env */
 #define AUV_PATH_BLOCK 32     /* polyline segments per projection block */
-#define AUV_PATH_SUPER 32     /* blocks per projection superblock */
+#ifndef AUV_PATH_SUPER
+#define AUV_PATH_SUPER 16     /* blocks per projection superblock (8 / 16 / 32 swept: profiles/r1j_variants.txt) */
+#endif
 #define AUV_NAV_W 24          /* doubles per env in AuvBatch.nav */
 #define AUV_REC_BYTES 80      /* bytes per obstacle record in AuvBatch.rec */
 #define AUV_MAX_POLY_VERTS 192 /* vertices of one world polygon incl. the closing one */
