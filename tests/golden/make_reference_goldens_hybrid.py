@@ -369,7 +369,9 @@ def main():
         print("MovingObstaclesNoRules seed", seed, "steps", n, "min range %.2f" % np.min(rec["dists"]), "nearby",
               sorted(set(rec["n_nearby"])))
     # ------------------------------------------------------------------ the deterministic test scenarios
-    # envs/testscenario.py classes instantiated as they are; the scenario each one builds is read
+    # envs/testscenario.py classes instantiated as they are (TestHeadOn draws its start angle from the
+    # global, unseeded `random` module -- testscenario.py:145 -- so its entries differ from run to run;
+    # the tests read the angle back from the fixture); the scenario each one builds is read
     # back (path, vessel start, obstacle circles / tracks with their velocity tables) and a short
     # episode of its step() is recorded.  DebugScenario draws from env.rng -> seeded.
     ts = importlib.import_module("gym_auv.envs.testscenario")
@@ -418,6 +420,43 @@ def main():
         out[key + "obs0"], out[key + "obs"], out[key + "reward"] = obs0, np.array(obs), np.array(rews)
         out[key + "dists"], out[key + "done"], out[key + "actions"] = np.array(dists), np.array(dones), acts
         print(name, "static", len(sta), "moving", len(mov), "steps", len(obs), "min range %.2f" % np.min(dists))
+    # ------------------------------------------------------------------ PathFollowNoObstacles (BASELINE config 2)
+    # the reference's own class (movingobstacles.py:114-120: no obstacles, PathFollowRewarder) with
+    # use_lidar=False: random curve, 6-dimensional observation
+    pf = {k: [] for k in ("waypoints", "vessel_init", "obs0", "obs", "reward", "done", "actions", "T")}
+    for seed in range(3):
+        with contextlib.redirect_stdout(io.StringIO()):
+            cfg_pf = env_config(1.0)
+            cfg_pf.vessel.use_lidar = False
+            env = mo.PathFollowNoObstacles(cfg_pf, test_mode=True, renderer=None)
+            np.random.seed(seed)
+            env.seed(seed)
+            env.reset()
+            assert env.obstacles == [] and isinstance(env.rewarder, rew.PathFollowRewarder)
+            v0 = np.array(env.vessel._state[:3])
+            obs0 = np.array(env.observe())
+            arng = np.random.RandomState(900 + seed)
+            acts = arng.uniform([0.0, -0.15], [1.0, 0.15], size=(Tm, 2)).astype(np.float32).astype(np.float64)
+            obs, rews, dones = [], [], []
+            for a in acts:
+                o, r_, d_, info = env.step(np.array(a))
+                obs.append(np.array(o))
+                rews.append(float(r_))
+                dones.append(bool(d_))
+                if d_:
+                    break
+        w = np.full((2, 16), np.nan)
+        w[:, : env.path.init_waypoints.shape[1]] = env.path.init_waypoints
+        pf["waypoints"].append(w)
+        pf["vessel_init"].append(v0)
+        pf["obs0"].append(obs0)
+        pf["obs"].append(pad(obs, (Tm, 6)))
+        pf["reward"].append(pad(rews, (Tm,)))
+        pf["done"].append(pad(np.array(dones, dtype=np.float64), (Tm,)))
+        pf["actions"].append(acts)
+        pf["T"].append(len(obs))
+        print("PathFollowNoObstacles seed", seed, "steps", len(obs))
+    out.update({"pf_" + k: v for k, v in pf.items()})
     out.update({"mo_" + k: v for k, v in mo_out.items()})
     out.update({"gen_" + k: np.array(v) for k, v in gen_stats.items()})
 

@@ -342,3 +342,20 @@ def test_registered_scenario_episodes_match_reference_classes(name):
         assert np.abs(env.vessel.dists - g("dists")[t]).max() <= 1e-9, t
         assert np.abs(obs - g("obs")[t]).max() <= 1e-9 and abs(rew - g("reward")[t]) <= 1e-9 * max(1.0, abs(rew))
         assert done == bool(g("done")[t])
+
+
+@pytest.mark.parametrize("k", range(3))
+def test_reference_pathfollow_class_episodes(k):
+    """BASELINE config 2: the reference's own PathFollowNoObstacles class (no obstacles,
+    PathFollowRewarder, use_lidar=False, 6-dimensional observation) replayed through the oracle."""
+    wp = HYB["pf_waypoints"][k]
+    wp = wp[:, ~np.isnan(wp[0])]
+    scn = S._single(wp, vessel_init=HYB["pf_vessel_init"][k], rewarder="pathfollow")
+    env = O.OracleEnv(scn.describe(0), oracle_cfg(Config()), test_mode=True)
+    obs0 = env.observe()
+    assert obs0.shape == (6,) and np.abs(obs0 - HYB["pf_obs0"][k]).max() <= 1e-9
+    for t in range(int(HYB["pf_T"][k])):
+        obs, rew, done, _ = env.step(HYB["pf_actions"][k][t])
+        assert np.abs(obs - HYB["pf_obs"][k, t]).max() <= 1e-9, t
+        assert abs(rew - HYB["pf_reward"][k, t]) <= 1e-9 * max(1.0, abs(rew)), t
+        assert done == bool(HYB["pf_done"][k, t])
