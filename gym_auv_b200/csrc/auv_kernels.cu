@@ -1066,7 +1066,12 @@ static int launch_lidar(const AuvConfig* cfg, const AuvRayTable* rays, const Auv
   args.feas_width = cfg->vessel_width * cfg->feasibility_width_multiplier;
   const int rpad = cfg->use_lidar ? ((cfg->n_sensors + 31) & ~31) : 32;
   const size_t smem = auv::lidar_smem_per_warp(rpad) * AUV_LIDAR_WARPS;
-  static size_t configured = 0;
+  // the opt-in is per device and per function; one slot per device ordinal (processes normally
+  // drive one GPU each, but nothing here assumes it)
+  static size_t configured_by_device[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  size_t& configured = configured_by_device[dev];
   if (smem > configured) {
     if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_lidar<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(k_lidar)"))
