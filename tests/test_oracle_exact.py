@@ -129,3 +129,45 @@ def test_linestring_project_picks_the_exact_first_minimum(seed):
         assert got == got_seq
         if ties == 1 and (len(d2) == 1 or sorted(d2)[1] - d2[k] > F(1, 10**9)):  # a unique, well separated minimum is unambiguous in FP64
             assert abs(got - want) <= 1e-9 * max(1.0, want)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_minimum_rotated_rectangle_is_the_geometric_minimum(seed):
+    """Shapely's minimum_rotated_rectangle enumerates the hull edges; by the rotating-calipers theorem
+    the minimum-area enclosing rectangle has a side on a hull edge, so the restatement must (a) contain
+    every point and (b) not be beaten by any rectangle of a fine sweep over orientations."""
+    rng = np.random.RandomState(400 + seed)
+    for _ in range(40):
+        pts = rng.uniform(-30, 30, size=(rng.randint(3, 12), 2))
+        ring = np.vstack([pts, pts[:1]])
+        box = G.minimum_rotated_rectangle(ring)
+        e0, e1 = box[1] - box[0], box[3] - box[0]
+        area = abs(e0[0] * e1[1] - e0[1] * e1[0])
+        assert abs(e0 @ e1) <= 1e-9 * max(1.0, area)  # a rectangle
+        u, v = e0 / np.linalg.norm(e0), e1 / np.linalg.norm(e1)
+        rel = pts - box[0]
+        assert (rel @ u).min() >= -1e-9 and (rel @ u).max() <= np.linalg.norm(e0) + 1e-9
+        assert (rel @ v).min() >= -1e-9 and (rel @ v).max() <= np.linalg.norm(e1) + 1e-9
+        th = np.linspace(0.0, np.pi / 2, 2001)
+        c, s = np.cos(th)[:, None], np.sin(th)[:, None]
+        x = pts[:, 0][None] * c + pts[:, 1][None] * s
+        y = -pts[:, 0][None] * s + pts[:, 1][None] * c
+        sweep = ((x.max(1) - x.min(1)) * (y.max(1) - y.min(1))).min()
+        assert area <= sweep * (1 + 1e-9)
+        # the enclosing circle the reference derives from it (obstacles.py:235-262) contains every point
+        centre, radius = G.enclosing_circle_of_ring(ring)
+        assert np.linalg.norm(pts - np.asarray(centre), axis=1).max() <= radius + 1e-9
+
+
+def test_vessel_pentagon_centroid_and_enclosing_circle_closed_forms():
+    """The closed forms the kernels use: area centroid (5w/18, 0) of the pentagon,
+    enclosing circle = centre of its 2w x w rectangle, radius w sqrt(5)/2, for any heading."""
+    for w in (1.0, 6.0, 30.0):
+        body = np.array([(-w / 2, -w / 2), (-w / 2, w / 2), (w / 2, w / 2), (1.5 * w, 0.0), (w / 2, -w / 2), (-w / 2, -w / 2)])
+        c = G.polygon_centroid(body)
+        assert np.abs(c - np.array([5 * w / 18, 0.0])).max() <= 1e-12 * w
+        for th in (0.0, 0.3, 2.0, -2.5):
+            ring = G.rotate_about(body, th, c) + np.array([10.0, -4.0])
+            centre, radius = G.enclosing_circle_of_ring(ring)
+            want = c + np.array([np.cos(th), np.sin(th)]) * (w / 2 - 5 * w / 18) + np.array([10.0, -4.0])
+            assert np.abs(np.asarray(centre) - want).max() <= 1e-9 * w and abs(radius - w * math.sqrt(5) / 2) <= 1e-9 * w
