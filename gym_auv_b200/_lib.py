@@ -8,11 +8,14 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
-ABI_VERSION = 16
+ABI_VERSION = 17
 REC_BYTES = 80
 MAX_POLY_VERTS = 192
 STATUS_REC_OVERFLOW = 1
 STATUS_GEN_GAVE_UP = 2
+STATUS_POLY_TOO_LARGE = 4
+PP_W = 12
+PATH_STAGE_BLOCKS = 512
 NAV_W = 24
 N_STATS = 16
 STAT_NAMES = [
@@ -32,6 +35,7 @@ OBSERVE_STEP = 0
 OBSERVE_RESET = 1
 REWARDER_IDS = {"colav": 0, "pathfollow": 1}
 CULL_IDS = {"reference": 0, "exact": 1}
+VELOCITY_IDS = {"zero": 0, "nearest": 1}
 
 _vp = C.c_void_p
 
@@ -59,7 +63,7 @@ class AuvConfig(C.Structure):
         ("test_mode", C.c_int32),
         ("cull_mode", C.c_int32),
         ("auto_reset", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("velocity_mode", C.c_int32),
     ]
 
 
@@ -67,24 +71,33 @@ class AuvRayTable(C.Structure):
     _fields_ = [("cos_sin", _vp), ("weight", _vp), ("sector", _vp), ("unit64", _vp), ("weight_sum", C.c_double)]
 
 
+class AuvPathHdr(C.Structure):
+    _fields_ = [
+        ("v0", C.c_int32),
+        ("nseg", C.c_int32),
+        ("b0", C.c_int32),
+        ("s0", C.c_int32),
+        ("ox", C.c_double),
+        ("oy", C.c_double),
+        ("length", C.c_double),
+        ("end_x", C.c_double),
+        ("end_y", C.c_double),
+        ("reserved", C.c_double),
+    ]
+
+
 class AuvPathBank(C.Structure):
     _fields_ = [
         ("n_paths", C.c_int32),
         ("n_knots", C.c_int32),
-        ("poly_off", _vp),
+        ("hdr", _vp),
         ("poly_xy", _vp),
         ("poly_cum", _vp),
-        ("blk_off", _vp),
         ("blk_chord", _vp),
         ("blk_dev", _vp),
-        ("sb_off", _vp),
         ("sb_chord", _vp),
         ("sb_dev", _vp),
-        ("origin", _vp),
-        ("knots", _vp),
-        ("coef", _vp),
-        ("length", _vp),
-        ("end_xy", _vp),
+        ("pp", _vp),
     ]
 
 
@@ -105,6 +118,12 @@ class AuvScenarioPool(C.Structure):
         ("vel_table", _vp),
         ("st_pos", _vp),
         ("st_radius", _vp),
+        ("st_rec", _vp),
+        ("mov_lin", _vp),
+        ("linear_tracks", C.c_int32),
+        ("lin_first_wrap", C.c_int32),
+        ("lin_wrap_period", C.c_int32),
+        ("reserved0", C.c_int32),
         ("world_circle", _vp),
         ("world_voff", _vp),
         ("world_verts", _vp),
@@ -138,6 +157,9 @@ class AuvBatch(C.Structure):
         ("status", _vp),
         ("rec_cap", C.c_int32),
         ("reserved1", C.c_int32),
+        ("obst_steps", _vp),
+        ("prev_seg", _vp),
+        ("env_pid", _vp),
     ]
 
 
@@ -174,6 +196,8 @@ class AuvGenParams(C.Structure):
         ("mov_speed_hi", C.c_double),
         ("st_disp_std", C.c_double),
         ("st_radius_mean", C.c_double),
+        ("path_group", C.c_int32),
+        ("path_period", C.c_int32),
     ]
 
 
@@ -201,6 +225,9 @@ EXPORTS = [
     "auv_step_host_chunked",
     "auv_step_host_submit",
     "auv_generate_moving_obstacles",
+    "auv_linear_wrap",
+    "auv_pool_pack",
+    "auv_obstacle_state",
 ]
 
 _lib = None
@@ -257,6 +284,9 @@ def load():
     ]
     lib.auv_step_host_submit.argtypes = lib.auv_step_host_chunked.argtypes
     lib.auv_generate_moving_obstacles.argtypes = [P(AuvGenParams), P(AuvPathBank), P(AuvScenarioPool), _vp, C.c_int, _vp, _vp]
+    lib.auv_linear_wrap.argtypes = [C.c_double, C.c_double, C.c_int, P(C.c_int32), P(C.c_int32)]
+    lib.auv_pool_pack.argtypes = [P(AuvConfig), P(AuvScenarioPool), _vp, C.c_int, _vp]
+    lib.auv_obstacle_state.argtypes = [P(AuvConfig), P(AuvScenarioPool), P(AuvBatch), _vp, _vp, _vp, _vp]
     lib.auv_timer_create.argtypes = [C.c_int]
     lib.auv_timer_create.restype = _vp
     lib.auv_timer_destroy.argtypes = [_vp]

@@ -86,8 +86,12 @@ __global__ void __launch_bounds__(128) k_generate_moving_obstacles(const __grid_
   const int m = ids ? ids[li] : li;
   // ---- per-scenario draws, recomputed by every thread of the scenario (same stream => same values)
   GenRng rp(gp.seed, (unsigned)m, AUV_GEN_SLOT_PATH, gp.epoch);
-  const int pid = min(pb.n_paths - 1, (int)(rp.u01() * pb.n_paths));
-  const double L = pb.length[pid];
+  // path choice: uniform over the bank (movingobstacles.py:28-31 draws a fresh curve), or -- path-major
+  // pools -- the path the slot is laid out for: consecutive groups of path_group scenarios share a path
+  const double upath = rp.u01();
+  const int pid = gp.path_group > 0 ? (int)(((long long)m % gp.path_period) / gp.path_group) % pb.n_paths
+                                    : min(pb.n_paths - 1, (int)(upath * pb.n_paths));
+  const double L = pb.hdr[pid].length;
   GenRng rv(gp.seed, (unsigned)m, AUV_GEN_SLOT_VESSEL, gp.epoch);
   double x0, y0, dir0;
   gen_path_point(pb, pid, L, 0.0, x0, y0, dir0);
@@ -154,11 +158,27 @@ __global__ void __launch_bounds__(128) k_generate_moving_obstacles(const __grid_
     const_cast<double*>(pool.mov_disp0)[2 * ps] = last * ux;
     const_cast<double*>(pool.mov_disp0)[2 * ps + 1] = last * uy;
     const_cast<double*>(pool.mov_counter0)[ps] = 0.1 + h2;
+    if (pool.mov_lin != nullptr) {  // packed record of the closed-form update (auv_pool_pack layout)
+      double* q = const_cast<double*>(pool.mov_lin) + ps * 8;
+      q[0] = (ox + 0.1 * ux) + h2 * ux;
+      q[1] = (oy + 0.1 * uy) + h2 * uy;
+      q[2] = gp.t_step_size * ux;
+      q[3] = gp.t_step_size * uy;
+      q[4] = rad;
+      q[5] = ox;
+      q[6] = oy;
+      q[7] = 0.0;
+    }
   } else {
     const long long ps = (long long)m * ks + (slot - km);
     const_cast<double*>(pool.st_pos)[2 * ps] = ox;
     const_cast<double*>(pool.st_pos)[2 * ps + 1] = oy;
     const_cast<double*>(pool.st_radius)[ps] = rad;
+    double* q = const_cast<double*>(pool.st_rec) + ps * 4;
+    q[0] = ox;
+    q[1] = oy;
+    q[2] = rad;
+    q[3] = 0.0;
   }
 }
 

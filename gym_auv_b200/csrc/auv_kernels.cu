@@ -1,29 +1,32 @@
 // auv_kernels.cu -- hand-written sm_100a kernels for the gym-auv step path + the C ABI.
 //
 // Kernel inventory (reference file:line each one replaces is in include/auv_b200.h):
-//   k_obstacle_update  thread per (env, moving-obstacle slot): staged entry point only, the
-//                      step runs the update inside k_vessel_nav                       HBM
-//   k_vessel_nav<DYN,OBST,G>  a group of G lanes per env, FP64: moving-obstacle update (OBST)
-//                      -> RKF45 vessel step (DYN) -> path projection (exact hierarchical
-//                      LineString.project, nodes/segments split over the group) -> navigation
-//                      record, obs[0..5], LiDAR-independent part of the reward -> obstacle
-//                      culling (slots split over the group): nearby list (every 25 steps),
-//                      enclosing circles, reference-exact ray windows, inside tests ->
-//                      compact per-env obstacle records in HBM                 latency / FP64
-//   k_lidar            WARP per env, lanes over rays: per-env scalars and obstacle records
-//                      arrive in one round trip, vertices are staged in shared memory (formed
-//                      in FP64 relative to the vessel), ray/segment casting (analytic edge pick
-//                      for polygonised circles), closeness, collision, obs, warp-reduced
-//                      reward, done, counters, sector pooling, and the VecEnv auto-reset of
-//                      finished envs as a COPY of the scenario's cached first observation
-//                      (no navigation / culling / casting on reset)              FP32 issue
-//   k_vessel_step / k_reset   staged entry points (Vessel.step only / explicit reset)
+//   k_vessel_nav<DYN,OBST,G>  a group of G lanes per env, FP64: moving-obstacle update (OBST;
+//                      closed form for constant-velocity tracks, else per-env state) -> RKF45
+//                      vessel step (DYN) -> path projection (exact hierarchical
+//                      LineString.project; the path's capsule tables are staged in shared memory
+//                      by one bulk async copy per CTA while the RK step runs; warm upper bound
+//                      from the previous step's segment) -> navigation record, obs[0..5],
+//                      LiDAR-independent part of the reward -> obstacle culling (slots split over
+//                      the group): nearby list (every 25 steps), enclosing circles,
+//                      reference-exact ray windows, inside tests -> compact per-env obstacle
+//                      records in HBM                                          latency / FP64
+//   k_lidar<COUNT,G>   a group of G lanes per env (32/G envs per warp side by side), lanes over
+//                      rays: the env's hand-over line and first records arrive in one round
+//                      trip, ranges live in shared memory (one writer per ray and record: no
+//                      atomics), ray/segment casting (analytic edge pick for polygonised
+//                      circles, vertices formed on the fly), closeness, collision, obs,
+//                      group-reduced reward, done, counters, sector pooling, optional obstacle
+//                      velocity channel, and the VecEnv auto-reset of finished envs as a COPY
+//                      of the scenario's cached first observation                 FP32 issue
+//   k_obstacle_update / k_vessel_step / k_reset   staged entry points
+//   k_pool_pack, k_obstacle_state                  pool packing / obstacle state read-back
 //   k_fma_probe        FP32 FMA peak micro-benchmark (roofline denominator)
 //
 // Precision plan: everything cheap and threshold-sensitive is FP64 (vessel state, RK step,
 // obstacle positions, vessel-relative obstacle centres, culling-window integers via an FP32
 // fast path with FP64 fallback, projection refine, navigation and reward scalars); the
-// O(rays x segments) casting is FP32 on vessel-relative vertices formed in FP64.
+// O(rays x segments) casting is FP32 on vessel-relative geometry formed in FP64.
 #include "auv_device.cuh"
 #include "auv_dynamics.cuh"
 #include "auv_geometry.cuh"
@@ -37,7 +40,8 @@ namespace auv {
 
 // moving-obstacle update of one (env, slot)   obstacles.py:195-215.  Split into the loads that
 // do not depend on each other (one round trip), the velocity lookup (second round trip) and the
-// stores, so that callers can keep several slots in flight.
+// stores, so that callers can keep several slots in flight.  (General, table-driven tracks; pools
+// of constant-velocity tracks use the closed form in lin_position.)
 struct ObstLoad {
   double w, counter;
   int4 tr;  // vel_off, vel_len, vel_stride, 0
@@ -77,8 +81,18 @@ __device__ __forceinline__ void obstacle_update_slot(const AuvConfig& cfg, const
   obstacle_finish(cfg, pool, batch, pe, ps, obstacle_load(pool, batch, pe, ps));
 }
 
+// constant-velocity track after n updates since reset (closed form of obstacles.py:195-215, see
+// AuvScenarioPool.linear_tracks): r = the slot's 64 B record in pool.mov_lin
+__device__ __forceinline__ double2 lin_position(const AuvScenarioPool& pool, const double2* __restrict__ r, double2 p0,
+                                                double2 d, int n) {
+  if (n < pool.lin_first_wrap) return make_double2(fma((double)n, d.x, p0.x), fma((double)n, d.y, p0.y));
+  const double m = (double)((n - pool.lin_first_wrap) % pool.lin_wrap_period + 1);
+  const double sx = r[2].y, sy = r[3].x;
+  return make_double2(fma(m, d.x, sx), fma(m, d.y, sy));
+}
+
 // ------------------------------------------------------------------------------------
-// k_obstacle_update     obstacles.py:195-215
+// k_obstacle_update     obstacles.py:195-215 (staged entry point: thread per (env, slot))
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_obstacle_update(AuvConfig cfg, AuvScenarioPool pool,
                                                           AuvBatch batch, int e0, int cnt) {
@@ -88,7 +102,8 @@ __global__ void __launch_bounds__(256) k_obstacle_update(AuvConfig cfg, AuvScena
   const long long gid = lid + (long long)e0 * km;  // envs [e0, e0 + cnt)
   const int e = (int)(gid / km);
   const int j = (int)(gid - (long long)e * km);
-  obstacle_update_slot(cfg, pool, batch, gid, (long long)batch.scn_id[e] * km + j);
+  if (j == 0) batch.obst_steps[e] += 1;
+  if (!pool.linear_tracks) obstacle_update_slot(cfg, pool, batch, gid, (long long)batch.scn_id[e] * km + j);
 }
 
 // Vessel.step only (staged entry point auv_vessel_step)
@@ -100,6 +115,77 @@ __global__ void __launch_bounds__(128) k_vessel_step(AuvConfig cfg, AuvBatch bat
   const S6 q = vessel_rk_step(cfg, load_state(batch.state, n, e), reinterpret_cast<const float2*>(actions)[e]);
   store_state(batch.state, n, e, q);
   batch.step_counter[e] += 1;
+}
+
+// pack pool.st_rec / pool.mov_lin from the unpacked arrays: thread per (listed scenario, slot)
+__global__ void __launch_bounds__(128) k_pool_pack(AuvConfig cfg, AuvScenarioPool pool, const int* __restrict__ ids,
+                                                   int n_ids) {
+  const int km = pool.k_moving, ks = pool.k_static, per = km + ks;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n_ids * per) return;
+  const int li = (int)(gid / per), slot = (int)(gid - (long long)li * per);
+  const int m = ids ? ids[li] : li;
+  if (slot < km) {
+    if (!pool.linear_tracks) return;
+    const long long ps = (long long)m * km + slot;
+    double* r = const_cast<double*>(pool.mov_lin) + ps * 8;
+    const double w = pool.mov_width[ps];
+    const int voff = pool.mov_track[4 * ps];
+    const double2 v = w > 0.0 ? reinterpret_cast<const double2*>(pool.vel_table)[voff] : make_double2(0.0, 0.0);
+    r[0] = pool.mov_pos0[2 * ps];
+    r[1] = pool.mov_pos0[2 * ps + 1];
+    r[2] = cfg.t_step_size * v.x;  // dx = dt * vel[idx][0]   obstacles.py:206-207
+    r[3] = cfg.t_step_size * v.y;
+    r[4] = w;
+    r[5] = pool.mov_start[2 * ps];
+    r[6] = pool.mov_start[2 * ps + 1];
+    r[7] = 0.0;
+  } else {
+    const long long ps = (long long)m * ks + (slot - km);
+    double* r = const_cast<double*>(pool.st_rec) + ps * 4;
+    r[0] = pool.st_pos[2 * ps];
+    r[1] = pool.st_pos[2 * ps + 1];
+    r[2] = pool.st_radius[ps];
+    r[3] = 0.0;
+  }
+}
+
+// VesselObstacle.position / (dx, dy) / waypoint_counter of every (env, slot)
+__global__ void __launch_bounds__(128) k_obstacle_state(AuvConfig cfg, AuvScenarioPool pool, AuvBatch batch,
+                                                        double* __restrict__ pos, double* __restrict__ disp,
+                                                        double* __restrict__ counter) {
+  const int km = pool.k_moving;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)batch.n_envs * km) return;
+  const int e = (int)(gid / km), j = (int)(gid - (long long)e * km);
+  double2 p, d;
+  double c;
+  if (pool.linear_tracks) {
+    const long long ps = (long long)batch.scn_id[e] * km + j;
+    const double2* r = reinterpret_cast<const double2*>(pool.mov_lin + ps * 8);
+    const int n = batch.obst_steps[e];
+    const double w = r[2].x;
+    d = r[1];
+    p = r[0];
+    c = pool.mov_counter0[ps];
+    if (w > 0.0) {
+      p = lin_position(pool, r, r[0], d, n);
+      if (n == 0) d = reinterpret_cast<const double2*>(pool.mov_disp0)[ps];
+      // the counter is accumulated literally (counter += dt per update), as the reference does
+      const int since = n < pool.lin_first_wrap ? n : (n - pool.lin_first_wrap) % pool.lin_wrap_period;
+      if (n >= pool.lin_first_wrap) c = 0.0;
+      for (int k = 0; k < since; ++k) c += cfg.t_step_size;
+    } else {
+      d = make_double2(0.0, 0.0);
+    }
+  } else {
+    p = reinterpret_cast<const double2*>(batch.mov_pos)[gid];
+    d = reinterpret_cast<const double2*>(batch.mov_disp)[gid];
+    c = batch.mov_counter[gid];
+  }
+  if (pos) reinterpret_cast<double2*>(pos)[gid] = p;
+  if (disp) reinterpret_cast<double2*>(disp)[gid] = d;
+  if (counter) counter[gid] = c;
 }
 
 // ------------------------------------------------------------------------------------
@@ -115,6 +201,8 @@ struct __align__(16) ObstRec {
   int flags;             // OFLAG_*
   int nv;                // boundary vertices incl. the closing one
   int vbase;             // world polygon: first vertex in pool.world_verts
+  float step_len;        // |(dx, dy)| of a vessel obstacle's last update (velocity channel)
+  int pad;
 };
 static_assert(sizeof(ObstRec) == AUV_REC_BYTES, "ObstRec layout");
 
@@ -124,6 +212,9 @@ __device__ __forceinline__ void reset_env_thread(const AuvScenarioPool& pool, co
   const int n = batch.n_envs;
   const int km = pool.k_moving;
   batch.scn_id[e] = scn;
+  batch.env_pid[e] = pool.path_id[scn];
+  batch.prev_seg[e] = -1;
+  batch.obst_steps[e] = 0;
   batch.episode[e] += 1;
   const double* vi = pool.vessel_init + 3ll * scn;
   batch.state[e] = vi[0];
@@ -137,12 +228,13 @@ __device__ __forceinline__ void reset_env_thread(const AuvScenarioPool& pool, co
   batch.cum_reward[e] = 0.0;
   batch.max_progress[e] = 0.0;
   batch.cte_sum[e] = 0.0;
-  for (int j = 0; j < km; ++j) {
-    const long long ps = (long long)scn * km + j, pe = (long long)e * km + j;
-    reinterpret_cast<double2*>(batch.mov_pos)[pe] = reinterpret_cast<const double2*>(pool.mov_pos0)[ps];
-    reinterpret_cast<double2*>(batch.mov_disp)[pe] = reinterpret_cast<const double2*>(pool.mov_disp0)[ps];
-    batch.mov_counter[pe] = pool.mov_counter0[ps];
-  }
+  if (!pool.linear_tracks)
+    for (int j = 0; j < km; ++j) {
+      const long long ps = (long long)scn * km + j, pe = (long long)e * km + j;
+      reinterpret_cast<double2*>(batch.mov_pos)[pe] = reinterpret_cast<const double2*>(pool.mov_pos0)[ps];
+      reinterpret_cast<double2*>(batch.mov_disp)[pe] = reinterpret_cast<const double2*>(pool.mov_disp0)[ps];
+      batch.mov_counter[pe] = pool.mov_counter0[ps];
+    }
   for (int w = 0; w < batch.mask_words; ++w) batch.nearby_mask[(long long)e * batch.mask_words + w] = 0u;
 }
 
@@ -156,23 +248,26 @@ __global__ void __launch_bounds__(128) k_reset(AuvScenarioPool pool, AuvBatch ba
 }
 
 // ------------------------------------------------------------------------------------
-// Culling stage ("hierarchical collision detector"), one thread per env.
+// Culling stage ("hierarchical collision detector"), a group of G lanes per env.
 //   vessel.py:266-273 nearby list, sensor.py:22-97 windows, obstacles.py:108-113,230-262
 //   enclosing circles.  Emits rec[e][0..cnt) and rec_cnt[e].
 // ------------------------------------------------------------------------------------
 struct SlotGeom {
   bool valid, pent, world;
   double cx, cy, rho, geo, hx, hy;
+  float step_len;
   int nv, vbase;
 };
 
+// n_upd = obstacle updates since reset (closed-form tracks only)
 __device__ __forceinline__ SlotGeom load_slot(const AuvScenarioPool& pool, const AuvBatch& batch, int e, int scn,
-                                              int j, double px, double py) {
+                                              int j, double px, double py, int n_upd) {
   SlotGeom g;
   g.valid = g.pent = g.world = false;
   g.cx = g.cy = g.rho = g.geo = 0.0;
   g.hx = 1.0;
   g.hy = 0.0;
+  g.step_len = 0.f;
   g.nv = g.vbase = 0;
   const int km = pool.k_moving, ks = pool.k_static, K = km + ks;
   if (j >= K) {  // shared world polygon (PolygonObstacle): cached enclosing circle
@@ -186,11 +281,26 @@ __device__ __forceinline__ SlotGeom load_slot(const AuvScenarioPool& pool, const
     g.cy = c3[1] - py;
     g.rho = c3[2];
   } else if (j < km) {  // VesselObstacle: pentagon, enclosing circle of its min-rotated rectangle
-    const long long ps = (long long)scn * km + j, pe = (long long)e * km + j;
-    const double w = pool.mov_width[ps];
+    const long long ps = (long long)scn * km + j;
+    double w;
+    double2 pos, dsp;
+    if (pool.linear_tracks) {
+      const double2* __restrict__ r = reinterpret_cast<const double2*>(pool.mov_lin + ps * 8);
+      const double2 p0 = r[0];
+      dsp = r[1];
+      w = r[2].x;
+      pos = p0;
+      if (w > 0.0) {
+        pos = lin_position(pool, r, p0, dsp, n_upd);
+        if (n_upd == 0) dsp = reinterpret_cast<const double2*>(pool.mov_disp0)[ps];  // update(0.1) of __init__
+      }
+    } else {
+      const long long pe = (long long)e * km + j;
+      w = pool.mov_width[ps];
+      pos = reinterpret_cast<const double2*>(batch.mov_pos)[pe];
+      dsp = reinterpret_cast<const double2*>(batch.mov_disp)[pe];
+    }
     if (w > 0.0) {
-      const double2 pos = reinterpret_cast<const double2*>(batch.mov_pos)[pe];
-      const double2 dsp = reinterpret_cast<const double2*>(batch.mov_disp)[pe];
       g.valid = g.pent = true;
       g.geo = w;
       const double dl2 = dsp.x * dsp.x + dsp.y * dsp.y;
@@ -198,6 +308,7 @@ __device__ __forceinline__ SlotGeom load_slot(const AuvScenarioPool& pool, const
         const double inv = rsqrt(dl2);
         g.hx = dsp.x * inv;
         g.hy = dsp.y * inv;
+        g.step_len = (float)(dl2 * inv);
       }
       // obstacles.py:230-262, SURVEY App. A.3: centre = c + R(th)((w/2,0) - c) + pos, c = (5w/18, 0)
       g.cx = (pos.x - px) + 5.0 * w / 18.0 + (2.0 * w / 9.0) * g.hx;
@@ -206,16 +317,16 @@ __device__ __forceinline__ SlotGeom load_slot(const AuvScenarioPool& pool, const
       g.nv = 6;
     }
   } else {  // CircularObstacle: ring = regular n-gon, enclosing circle = (position, radius)
-    const long long ps = (long long)scn * ks + (j - km);
-    const double r = pool.st_radius[ps];
-    if (r > 0.0) {
-      const double2 c = reinterpret_cast<const double2*>(pool.st_pos)[ps];
+    const double2* __restrict__ r = reinterpret_cast<const double2*>(pool.st_rec + ((long long)scn * ks + (j - km)) * 4);
+    const double2 c = r[0];
+    const double rad = r[1].x;
+    if (rad > 0.0) {
       g.valid = true;
-      g.geo = r;
+      g.geo = rad;
       g.cx = c.x - px;
       g.cy = c.y - py;
-      g.rho = r;
-      g.nv = ngon_sides(r) + 1;
+      g.rho = rad;
+      g.nv = ngon_sides(rad) + 1;
     }
   }
   return g;
@@ -228,7 +339,7 @@ template <int G>
 __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvScenarioPool& pool,
                                                const AuvBatch& batch, const double2* __restrict__ unit64,
                                                int* __restrict__ windows_out, int e, int scn, double px,
-                                               double py, double psi, int step_counter, const int lane,
+                                               double py, double psi, int step_counter, int n_upd, const int lane,
                                                const unsigned gm, const bool store) {
   const int sub = lane & (G - 1);
   const int R = cfg.n_sensors;
@@ -248,7 +359,7 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
         const int j = base + k * G + sub;
         bool near = false;
         if (j < S) {
-          const SlotGeom g = load_slot(pool, batch, e, scn, j, px, py);
+          const SlotGeom g = load_slot(pool, batch, e, scn, j, px, py, n_upd);
           if (g.valid) {
             const double dc = sqrt(g.cx * g.cx + g.cy * g.cy);
             if (dc - g.rho - width >= range + 1e-6) {
@@ -284,7 +395,7 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
       unsigned wv = word;
       for (int t = 0; t < r; ++t) wv &= wv - 1;
       const int j = base + __ffs(wv) - 1;
-      const SlotGeom g = load_slot(pool, batch, e, scn, j, px, py);
+      const SlotGeom g = load_slot(pool, batch, e, scn, j, px, py, n_upd);
       int wa = 0, wb = 0;
       bool allrays = false, inside = false;
       double bx0 = 0.0, by0 = 0.0;
@@ -323,6 +434,8 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
                 (inside ? OFLAG_INSIDE : 0) | (allrays ? OFLAG_ALLRAYS : 0);
       q.nv = g.valid ? g.nv : 1;
       q.vbase = g.vbase;
+      q.step_len = g.step_len;
+      q.pad = 0;
       rec[idx] = q;
     }
     cnt = min(cnt + nw, batch.rec_cap);
@@ -333,12 +446,46 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
   }
 }
 
+// ---- bulk async copy (TMA, 1-D) + mbarrier: a CTA's copy of its path's capsule tables
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "AUV_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra AUV_DONE;\n"
+      "bra AUV_WAIT;\n"
+      "AUV_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // BaseEnvironment._update (OBST) + Vessel.step (DYN) + Vessel.navigate + the culling stage, a
 // group of G lanes per env.  The scalar FP64 chains (RK step, PCHIP, navigation features) are
 // computed redundantly by the lanes of a group; the table searches (path projection, obstacle
 // slots) are split over them, which shortens the per-warp critical path ~G-fold and gives the
 // SM G times more warps to hide the remaining load latency with (thread-per-env had N/32 warps:
-// 3 per scheduler at 65536 envs, one long dependent chain each -- profiles/r1e, r1h).
+// 3 per scheduler at 65536 envs, one long dependent chain each -- profiles/earlier).
+// When every env of the CTA follows the same path (scenario pools are laid out path-major, so this
+// is the normal case) the path's capsule tables -- <= 13 KB -- are copied to shared memory by
+// ONE bulk async copy (cp.async.bulk + mbarrier) issued before the RK step and awaited after it:
+// the ~50 capsule tests per env then read shared memory instead of four dependent rounds of
+// global loads.  CTAs with mixed paths (or a path with more than AUV_PATH_STAGE_BLOCKS blocks)
+// search the global tables; the arithmetic is the same.
 #ifndef AUV_NAV_G
 #define AUV_NAV_G 4
 #endif
@@ -348,6 +495,7 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
 #ifndef AUV_NAV_MINB
 #define AUV_NAV_MINB 7  // 72 registers (profiles/r1j_variants.txt: 64 regs 0.114 ms, 72 regs 0.104, 80 regs 0.121)
 #endif
+constexpr int NAV_STAGE_SB = (AUV_PATH_STAGE_BLOCKS + AUV_PATH_SUPER - 1) / AUV_PATH_SUPER;
 template <bool DYN, bool OBST, int G>
 __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(const __grid_constant__ AuvConfig cfg,
                                                                 const __grid_constant__ AuvPathBank paths,
@@ -357,32 +505,67 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
                                                                 int* __restrict__ windows_out,
                                                                 const float* __restrict__ actions,
                                                                 float* __restrict__ obs_out, int obs_dim, int e0, int e1) {
+  __shared__ __align__(16) float4 s_chord[AUV_PATH_STAGE_BLOCKS];
+  __shared__ __align__(16) float2 s_aux[AUV_PATH_STAGE_BLOCKS];
+  __shared__ __align__(16) float4 s_sbc[NAV_STAGE_SB];
+  __shared__ __align__(16) float2 s_sba[NAV_STAGE_SB];
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_pid[AUV_NAV_THREADS / 32];
   const int lane = threadIdx.x & 31, sub = lane & (G - 1);
   const unsigned gm = group_mask<G>(lane);
   const int eraw = e0 + (blockIdx.x * AUV_NAV_THREADS + threadIdx.x) / G;  // envs [e0, e1)
-  if (eraw - (lane / G) >= e1) return;  // the whole warp is past the end
   const bool store = eraw < e1;
   const int e = store ? eraw : e1 - 1;  // padding groups shadow the last env and store nothing
   const int n = batch.n_envs;
+  // ---- first round of loads: everything that is indexed by the env alone
   const int scn = batch.scn_id[e];
-  if (OBST) {  // the group's lanes take the env's moving-obstacle slots
-    const int km = pool.k_moving;
-    if (store) {
-      const long long pe0 = (long long)e * km, ps0 = (long long)scn * km;
-      for (int j = sub; j < km; j += 2 * G) {  // two slots in flight per lane
-        const bool two = j + G < km;
-        const ObstLoad a = obstacle_load(pool, batch, pe0 + j, ps0 + j);
-        const ObstLoad b = obstacle_load(pool, batch, pe0 + (two ? j + G : j), ps0 + (two ? j + G : j));
-        obstacle_finish(cfg, pool, batch, pe0 + j, ps0 + j, a);
-        if (two) obstacle_finish(cfg, pool, batch, pe0 + j + G, ps0 + j + G, b);
-      }
-    }
-  }
-  S6 y = load_state(batch.state, n, e);
+  const int pid = batch.env_pid[e];
+  const int prev_seg = batch.prev_seg[e];
   int step_counter = batch.step_counter[e];
+  int n_upd = batch.obst_steps[e];
+  S6 y = load_state(batch.state, n, e);
   float2 act = make_float2(0.f, 0.f);
   if (DYN) act = reinterpret_cast<const float2*>(actions)[e];
-  __syncwarp();  // every lane has read the old state / the updated obstacles are visible to the group
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  {  // does the whole CTA follow one path?
+    int same;
+    __match_all_sync(AUV_FULL, pid, &same);
+    if (lane == 0) s_pid[threadIdx.x >> 5] = same ? pid : -1;
+  }
+  __syncthreads();
+  // ---- second round: the path's header line
+  const AuvPathHdr h = paths.hdr[pid];
+  const int nblk = (h.nseg + AUV_PATH_BLOCK - 1) / AUV_PATH_BLOCK;
+  const int nsb = (nblk + AUV_PATH_SUPER - 1) / AUV_PATH_SUPER;
+  bool staged = s_pid[0] >= 0 && nblk <= AUV_PATH_STAGE_BLOCKS;
+#pragma unroll
+  for (int w = 1; w < AUV_NAV_THREADS / 32; ++w) staged = staged && s_pid[w] == s_pid[0];
+  if (staged && threadIdx.x == 0) {
+    const unsigned nb2 = (unsigned)(nblk + 1) & ~1u, ns2 = (unsigned)(nsb + 1) & ~1u;  // tables are padded to even counts
+    mbar_expect_tx(&s_bar, nb2 * 24u + ns2 * 24u);
+    bulk_g2s(s_chord, reinterpret_cast<const float4*>(paths.blk_chord) + h.b0, nb2 * 16u, &s_bar);
+    bulk_g2s(s_aux, reinterpret_cast<const float2*>(paths.blk_dev) + h.b0, nb2 * 8u, &s_bar);
+    bulk_g2s(s_sbc, reinterpret_cast<const float4*>(paths.sb_chord) + h.s0, ns2 * 16u, &s_bar);
+    bulk_g2s(s_sba, reinterpret_cast<const float2*>(paths.sb_dev) + h.s0, ns2 * 8u, &s_bar);
+  }
+  if (OBST) {
+    ++n_upd;
+    if (store && sub == 0) batch.obst_steps[e] = n_upd;
+    if (!pool.linear_tracks) {  // table-driven tracks: the group's lanes take the env's moving-obstacle slots
+      const int km = pool.k_moving;
+      if (store) {
+        const long long pe0 = (long long)e * km, ps0 = (long long)scn * km;
+        for (int j = sub; j < km; j += 2 * G) {  // two slots in flight per lane
+          const bool two = j + G < km;
+          const ObstLoad a = obstacle_load(pool, batch, pe0 + j, ps0 + j);
+          const ObstLoad b = obstacle_load(pool, batch, pe0 + (two ? j + G : j), ps0 + (two ? j + G : j));
+          obstacle_finish(cfg, pool, batch, pe0 + j, ps0 + j, a);
+          if (two) obstacle_finish(cfg, pool, batch, pe0 + j + G, ps0 + j + G, b);
+        }
+      }
+      __syncwarp();  // the updated obstacles are visible to the group
+    }
+  }
   if (DYN) {
     y = vessel_rk_step(cfg, y, act);
     ++step_counter;
@@ -391,25 +574,42 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
       batch.step_counter[e] = step_counter;
     }
   }
-  const int pid = pool.path_id[scn];
-  const double s = project_group<G>(paths, pid, y.x, y.y, lane, gm);
-  navigate_env(cfg, paths, batch, pid, e, s, y.x, y.y, y.psi, y.u, y.v, y.r,
+  PathTabs T;
+  if (staged) {
+    mbar_wait(&s_bar, 0);
+    T.sbc = s_sbc;
+    T.sba = s_sba;
+    T.chord = s_chord;
+    T.aux = s_aux;
+  } else {
+    T.sbc = reinterpret_cast<const float4*>(paths.sb_chord) + h.s0;
+    T.sba = reinterpret_cast<const float2*>(paths.sb_dev) + h.s0;
+    T.chord = reinterpret_cast<const float4*>(paths.blk_chord) + h.b0;
+    T.aux = reinterpret_cast<const float2*>(paths.blk_dev) + h.b0;
+  }
+  int seg;
+  const double s = project_group<G>(paths, h, T, y.x, y.y, prev_seg, lane, gm, seg);
+  if (store && sub == 0) batch.prev_seg[e] = seg;
+  navigate_env(cfg, paths, h, batch, pid, e, scn, s, y.x, y.y, y.psi, y.u, y.v, y.r,
                obs_out ? obs_out + (long long)e * obs_dim : nullptr, store && sub == 0);
   if (cfg.use_lidar)
-    cull_env_group<G>(cfg, pool, batch, unit64, windows_out, e, scn, y.x, y.y, y.psi, step_counter, lane, gm, store);
+    cull_env_group<G>(cfg, pool, batch, unit64, windows_out, e, scn, y.x, y.y, y.psi, step_counter, n_upd, lane, gm, store);
 }
 
 // ------------------------------------------------------------------------------------
-// k_lidar: warp per env (AUV_LIDAR_EPW consecutive envs per warp, the next env's scalars and
-// first records prefetched while the current one is cast)
+// k_lidar: a group of G lanes per env (32/G envs side by side in a warp, AUV_LIDAR_EPG
+// consecutive envs per group one after the other, the next env's hand-over line and first
+// records prefetched while the current one is cast)
 // ------------------------------------------------------------------------------------
-constexpr int VMAX = 192;  // staged vertices per warp per round (float2)
-constexpr int RROUND = 6;  // records per round: 6 x 80 B = 30 lanes x 16 B, one coalesced load
+constexpr int RROUND = 4;  // records per shared-memory round
 #ifndef AUV_LIDAR_WARPS
-#define AUV_LIDAR_WARPS 2  // warps per CTA (the warps of a CTA never synchronise with each other)
+#define AUV_LIDAR_WARPS 2  // warps per CTA (the warps of a CTA only meet once, after the unit table is staged)
 #endif
-#ifndef AUV_LIDAR_EPW
-#define AUV_LIDAR_EPW 2    // envs per warp, processed one after the other (sweep 1/2/4/8: 0.146/0.142/0.145/0.146 ms)
+#ifndef AUV_LIDAR_EPG
+#define AUV_LIDAR_EPG 2    // envs per group, processed one after the other
+#endif
+#ifndef AUV_LIDAR_G
+#define AUV_LIDAR_G 16     // lanes per env
 #endif
 
 struct LidarArgs {
@@ -422,6 +622,8 @@ struct LidarArgs {
   int mode;       // AUV_OBSERVE_STEP | AUV_OBSERVE_RESET
   int obs_dim;
   int e0, e1;     // envs [e0, e1) of the batch are processed by this launch
+  int vmax;       // staged vertices per env (float2): AUV_MAX_POLY_VERTS with world polygons, else 16
+  int velocity;   // 1: track the nearest obstacle per ray (sensor.py:100-137 semantics)
   float pen_clear_ray;     // range * exp(-0.1 range): penalty term of a ray that reads sensor_range
   float inv_log_range;     // 1 / log(1 + range)
   double clear_closeness;  // -range * exp(-0.1 range): closeness reward when every ray is clear
@@ -429,74 +631,86 @@ struct LidarArgs {
   double feas_width;       // vessel_width * feasibility_width_multiplier (sensor.py:166-168)
 };
 
-struct __align__(16) WarpSmem {
-  float2 verts[VMAX];
-  ObstRec rec[RROUND];
-  int4 cand[RROUND];  // per record of the round: first slot in the flat candidate list, I1.lo, |I1|, I2.lo
-  int voff[RROUND + 1];
-  int pad;
+// shared memory of one env in flight: records of the round, vertex stage, range per ray and
+// (velocity mode) the record that produced it.  Every part is 16-byte aligned.
+__host__ __device__ constexpr size_t lidar_smem_per_env(int rpad, int vmax, int velocity) {
+  return RROUND * sizeof(ObstRec) + (size_t)vmax * sizeof(float2) + sizeof(float) * rpad + (velocity ? rpad : 0);
+}
+struct EnvSmem {
+  ObstRec* rec;     // [RROUND]
+  float2* verts;    // [vmax]
+  float* sdist;     // [rpad]
+  uint8_t* sslot;   // [rpad] or nullptr
 };
-// per-env scalar pack: lane k < AUV_NAV_W holds nav[e][k] (one register per lane, read back by
-// shuffle); the navigation kernel put everything the casting stage needs into that record
-#define SC_STATE NAV_X  // x, y, psi
-#define SC_CUM NAV_CUM
-#define SC_CTE NAV_CTE
-#define SC_TSTEP NAV_TSTEP
-#define SC_SCN NAV_SCN
-#define SC_CNT NAV_CNT
 
-// one round trip per env: the env's navigation record (one coalesced 192 B load) and,
-// speculatively, its first RROUND obstacle records (30 lanes x 16 B) before their count is known
-__device__ __forceinline__ void lidar_fetch(const AuvConfig& cfg, const AuvBatch& batch, int e, int lane,
-                                            double& sc, uint4& spec) {
-  sc = 0.0;
-  if (lane < AUV_NAV_W) sc = batch.nav[(long long)e * AUV_NAV_W + lane];
-  spec = make_uint4(0, 0, 0, 0);
-  if (cfg.use_lidar && lane < RROUND * 5 && lane / 5 < batch.rec_cap)
-    spec = reinterpret_cast<const uint4*>(reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap)[lane];
+// one round trip per env: the env's hand-over line (16 doubles, one coalesced 128 B load) and,
+// speculatively, its first records before their count is known
+template <int G>
+struct LidarFetch {
+  static constexpr int NSC = (16 + G - 1) / G;             // hand-over doubles per lane
+  static constexpr int SPEC = (G / 5) < RROUND ? (G / 5) : RROUND;  // speculative records (5 x 16 B each)
+  double sc[NSC];
+  uint4 spec;
+};
+template <int G>
+__device__ __forceinline__ void lidar_fetch(const AuvConfig& cfg, const AuvBatch& batch, int e, int sub, LidarFetch<G>& f) {
+  const double* nv = batch.nav + (long long)e * AUV_NAV_W + NAV_HAND;
+#pragma unroll
+  for (int k = 0; k < LidarFetch<G>::NSC; ++k) f.sc[k] = (sub + k * G < 16) ? nv[sub + k * G] : 0.0;
+  f.spec = make_uint4(0, 0, 0, 0);
+  if (cfg.use_lidar && sub < LidarFetch<G>::SPEC * 5 && sub / 5 < batch.rec_cap)
+    f.spec = reinterpret_cast<const uint4*>(reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap)[sub];
 }
 
-// range of ray (c, s, world angle theta) against one staged obstacle record; `best` is the
-// ray's current reading (only used to skip obstacles that cannot improve it)
-__device__ __forceinline__ float cast_ray_record(const ObstRec& q, const float2* __restrict__ vp, float c, float s,
-                                                 float theta, float best, float rangef) {
-  const int fl = q.flags, nq = q.nv;
-  if (fl & OFLAG_INSIDE) return 0.f;
-  const float rho = q.rho;
-  const float tc = q.ecx * c + q.ecy * s;
-  const float hc = q.ecy * c - q.ecx * s;
-  const float slack = rho * 1e-5f + 1e-4f;
-  if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > best) return best;
-  if (!(fl & (OFLAG_PENTAGON | OFLAG_WORLD)) && nq > 16) {
-    // Regular n-gon inscribed in the enclosing circle (n = 16/32/64): the ray's line
-    // meets the circle at polar angles theta+g and theta+pi-g (g = asin(-hc/r));
-    // between circle and polygon lies the circular segment of exactly one edge, so the
-    // polygon crossing is on the edge whose angular span contains that angle.  The
-    // neighbour on the nearer side is tested too (FP32 error of asinf near grazing); testing it
-    // only near the span boundary was measured slower (divergent, not unrolled: 0.106 -> 0.108 ms).
-    const int nn = nq - 1;
-    const float g = asinf(fminf(fmaxf(-hc / rho, -1.f), 1.f));
-    const float invd = (float)nn * 0.15915494309189535f;
+// range of the ray (c, s) against one regular n-gon ring inscribed in the circle (ecx, ecy, rho),
+// n = nn >= 16 sides, vertex k at polar angle 2 pi k / nn (unit table u64 = cos/sin(2 pi k / 64)).
+// The ray's line meets the circle at polar angles theta + g (far side) and theta + pi - g (near
+// side), g = asin(-hc / rho); between circle and polygon lies the circular segment of exactly one
+// edge, so the polygon crossing is on the edge whose angular span contains that angle.  The
+// neighbour on the nearer side is tested too (FP32 error of asinf near span boundaries).  With the
+// own-ship outside the circle the near side alone decides: a line that does not cross the edge under
+// its entry point leaves the circle through the same circular segment.  Vertices are formed on the
+// fly from the FP32 centre (rounded once from the FP64 vessel-relative centre).
+__device__ __forceinline__ float cast_ngon(float ecx, float ecy, float rho, int nn, const float2* __restrict__ u64,
+                                           float c, float s, float theta, float tc, float hc, float best, float rangef) {
+  const float g = asinf(fminf(fmaxf(-hc / rho, -1.f), 1.f));
+  const float invd = (float)nn * 0.15915494309189535f;
+  const int sh = 6 - (31 - __clz(nn));  // unit table stride 64 / nn
+  const bool outside = tc * tc + hc * hc > rho * rho * 1.0001f + 1e-3f;
 #pragma unroll
-    for (int sol = 0; sol < 2; ++sol) {
-      const float p = (sol == 0 ? theta + g : theta + 3.14159265358979f - g) * invd;
-      const float kf = floorf(p);
-      const int k0 = (int)kf & (nn - 1);
-      const int k1 = (p - kf < 0.5f ? k0 - 1 : k0 + 1) & (nn - 1);
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        const int k = w == 0 ? k0 : k1;
-        const float2 va = vp[k], vb = vp[(k + 1) & (nn - 1)];  // no closing vertex is staged for these
-        const float ya = va.y * c - va.x * s, yb = vb.y * c - vb.x * s;
-        if ((ya <= 0.f && yb >= 0.f) || (ya >= 0.f && yb <= 0.f)) {
-          const float xa = va.x * c + va.y * s, xb = vb.x * c + vb.y * s;
-          const float t = xa + (xb - xa) * (ya / (ya - yb));
-          if (t >= 0.f && t <= rangef) best = fminf(best, t);
-        }
-      }
+  for (int sol = 0; sol < 2; ++sol) {
+    if (sol == 1 && outside) break;
+    const float p = (sol == 0 ? theta + 3.14159265358979f - g : theta + g) * invd;
+    const float kf = floorf(p);
+    const int k0 = (int)kf;
+    const int first = (p - kf < 0.5f) ? k0 - 1 : k0;  // edges (first, first+1), (first+1, first+2)
+    float xp, yp;
+    {
+      const float2 un = u64[(first & (nn - 1)) << sh];
+      const float vx = fmaf(rho, un.x, ecx), vy = fmaf(rho, un.y, ecy);
+      xp = vx * c + vy * s;
+      yp = vy * c - vx * s;
     }
-    return best;
+#pragma unroll
+    for (int w = 1; w <= 2; ++w) {
+      const float2 un = u64[((first + w) & (nn - 1)) << sh];
+      const float vx = fmaf(rho, un.x, ecx), vy = fmaf(rho, un.y, ecy);
+      const float xc = vx * c + vy * s;
+      const float yc = vy * c - vx * s;
+      if ((yp <= 0.f && yc >= 0.f) || (yp >= 0.f && yc <= 0.f)) {
+        const float t = xp + (xc - xp) * (yp / (yp - yc));
+        if (t >= 0.f && t <= rangef) best = fminf(best, t);
+      }
+      xp = xc;
+      yp = yc;
+    }
   }
+  return best;
+}
+
+// range of the ray (c, s) against a staged closed vertex chain vp[0..nq)
+__device__ __forceinline__ float cast_chain(const float2* __restrict__ vp, int nq, float c, float s, float best,
+                                            float rangef) {
   float2 v = vp[0];
   float xp = v.x * c + v.y * s;
   float yp = v.y * c - v.x * s;
@@ -514,63 +728,67 @@ __device__ __forceinline__ float cast_ray_record(const ObstRec& q, const float2*
   return best;
 }
 
-// everything after the culling stage for ONE env, by one warp.  sdist[rpad]: range per ray,
-// scl[rpad]: closeness per ray, hitmask[rpad/32]: rays some obstacle shortened.
-template <bool COUNT>
-__device__ __forceinline__ void lidar_env(const LidarArgs& A, WarpSmem& sm, float* __restrict__ sdist,
-                                          float* __restrict__ scl, unsigned* __restrict__ hitmask, const int rpad,
-                                          const int e, const int lane, const double sc, const uint4 spec) {
+template <int G>
+__device__ __forceinline__ float group_sum(unsigned gm, float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o);
+  return v;
+}
+
+// everything after the culling stage for ONE env, by one group of G lanes.
+template <bool COUNT, int G>
+__device__ __forceinline__ void lidar_env(const LidarArgs& A, const EnvSmem& sm, const float2* __restrict__ s_unit,
+                                          const int rpad, const int e, const int lane, const unsigned gm,
+                                          const LidarFetch<G>& F) {
   const AuvConfig& cfg = A.cfg;
   const AuvBatch& batch = A.batch;
   const int n = batch.n_envs;
   const int R = cfg.n_sensors;
+  const int sub = lane & (G - 1), gbase = lane & ~(G - 1);
   const float rangef = (float)cfg.sensor_range;
   const float widthf = (float)cfg.vessel_width;
   float* obs = A.out.obs + (long long)e * A.obs_dim;
   const bool pooling = A.out.sector_min_dist != nullptr || A.out.sector_feasible_dist != nullptr;
-  const uint4* grec4 = reinterpret_cast<const uint4*>(reinterpret_cast<const ObstRec*>(batch.rec) +
-                                                      (long long)e * batch.rec_cap);
-#define SCAL(k) __shfl_sync(AUV_FULL, sc, (k))
+  const ObstRec* grec = reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
+  float* sdist = sm.sdist;
+// hand-over value k (NAV_HAND <= k < NAV_HAND + 16): register (k - 8) / G of lane (k - 8) % G of the group
+#define SCAL(k) __shfl_sync(gm, F.sc[((k) - NAV_HAND) / G], gbase + (((k) - NAV_HAND) % G))
 
   bool collision = false;
   float pen = (float)A.rays.weight_sum * A.pen_clear_ray;  // every ray clear; hit rays add their excess below
   unsigned long long ntests = 0;
   if (cfg.use_lidar) {
-    const int cnt = cfg.use_lidar ? (int)SCAL(SC_CNT) : 0;
-    bool any_hit = false;
+    const int cnt = (int)SCAL(NAV_CNT);
     if (cnt > 0) {
-      const double px = SCAL(SC_STATE), py = SCAL(SC_STATE + 1), psi = SCAL(SC_STATE + 2);
+      const double px = SCAL(NAV_X), py = SCAL(NAV_Y), psi = SCAL(NAV_PSI);
       const double cpsi = SCAL(NAV_COSPSI), spsi = SCAL(NAV_SINPSI);
       const float dth_f = (float)(2.0 * AUV_PI / (double)R), psi_m_pi = (float)(psi - AUV_PI);
       const double2* __restrict__ unit = reinterpret_cast<const double2*>(A.rays.unit64);
+      const double2* __restrict__ cos_sin = reinterpret_cast<const double2*>(A.rays.cos_sin);
       uint4* srec4 = reinterpret_cast<uint4*>(sm.rec);
-      // ---- every ray starts at sensor_range with closeness 0 (vector stores)
-      __syncwarp();
-      for (int k = lane; k < rpad / 4; k += 32) {
-        reinterpret_cast<float4*>(sdist)[k] = make_float4(rangef, rangef, rangef, rangef);
-        reinterpret_cast<float4*>(scl)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (lane < rpad / 32) hitmask[lane] = 0u;
-      for (int r0 = 0; r0 < cnt;) {
-        // ---- round: up to RROUND records, bounded by the vertex budget
-        __syncwarp();
-        if (lane < RROUND * 5) srec4[lane] = r0 == 0 ? spec : ((r0 + lane / 5 < cnt) ? grec4[r0 * 5 + lane] : spec);
-        __syncwarp();
-        int nvv = 0;
-        if (lane < RROUND && r0 + lane < cnt) nvv = sm.rec[lane].nv;
-        const int incl = warp_incl_scan(nvv, lane);
-        const unsigned fm = __ballot_sync(AUV_FULL, nvv > 0 && incl <= VMAX);
-        const int take = max(1, fm == AUV_FULL ? 32 : __ffs(~fm) - 1);  // a prefix: incl is monotone
-        if (lane < take) sm.voff[lane] = incl - nvv;
-        const int nr = take;
-        // ---- candidate rays of each record (sensor.py:93-95): i in I1 = [a,b) or i-R in [a,b),
-        //      i.e. I2 = [a+R, b+R), both clipped to [0,R).  An obstacle whose window is wider
-        //      than R is listed -- and tested -- twice upstream: the min does not care, so the
-        //      part of I2 that repeats I1 is dropped here (and counted in COUNT mode below).
-        int n1 = 0, n2 = 0, lo1 = 0, lo2 = 0;
-        if (lane < nr) {
-          const ObstRec& q = sm.rec[lane];
-          if (q.flags & OFLAG_ALLRAYS) {
+      // ---- every ray starts at sensor_range (vector stores)
+      __syncwarp(gm);
+      for (int k = sub; k < rpad / 4; k += G) reinterpret_cast<float4*>(sdist)[k] = make_float4(rangef, rangef, rangef, rangef);
+      for (int r0 = 0; r0 < cnt; r0 += RROUND) {
+        // ---- round: up to RROUND records into shared memory (the first ones were prefetched)
+        const int nr = min(RROUND, cnt - r0);
+        __syncwarp(gm);
+        if (r0 == 0) {
+          if (sub < LidarFetch<G>::SPEC * 5) srec4[sub] = F.spec;
+          for (int k = LidarFetch<G>::SPEC * 5 + sub; k < nr * 5; k += G) srec4[k] = reinterpret_cast<const uint4*>(grec)[k];
+        } else {
+          for (int k = sub; k < nr * 5; k += G) srec4[k] = reinterpret_cast<const uint4*>(grec + r0)[k];
+        }
+        __syncwarp(gm);
+        for (int rr = 0; rr < nr; ++rr) {
+          const ObstRec& q = sm.rec[rr];
+          const int fl = q.flags, nq = q.nv;
+          // ---- candidate rays of the record (sensor.py:93-95): i in I1 = [a,b) or i-R in [a,b),
+          //      i.e. I2 = [a+R, b+R), both clipped to [0,R).  An obstacle whose window is wider
+          //      than R is listed -- and tested -- twice upstream: the min does not care, so the
+          //      part of I2 that repeats I1 is dropped here (and counted in COUNT mode below).
+          int n1, n2 = 0, lo1 = 0, lo2 = 0;
+          if (fl & OFLAG_ALLRAYS) {
             n1 = R;
           } else {
             lo1 = max(q.a, 0);
@@ -580,170 +798,195 @@ __device__ __forceinline__ void lidar_env(const LidarArgs& A, WarpSmem& sm, floa
             if (n1 > 0) lo2 = max(lo2, hi1);
             n2 = max(0, min(q.b + R, R) - lo2);
           }
-        }
-        const int tot = n1 + n2;
-        const int cincl = warp_incl_scan(tot, lane);
-        if (lane < nr) sm.cand[lane] = make_int4(cincl - tot, lo1, n1, lo2);
-        const int T = __shfl_sync(AUV_FULL, cincl, nr - 1);
-        __syncwarp();
-        // ---- stage vertices: vessel-relative, formed in FP64, stored FP32
-        for (int rr = 0; rr < nr; ++rr) {
-          const ObstRec& q = sm.rec[rr];
-          const int off = sm.voff[rr], nq = q.nv;
-          if (q.flags & OFLAG_WORLD) {
-            const double2* wv = reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase;
-            for (int k = lane; k < nq; k += 32) {
-              const double2 w = wv[k];
-              sm.verts[off + k] = make_float2((float)(w.x - px), (float)(w.y - py));
-            }
-          } else if (q.flags & OFLAG_PENTAGON) {
-            if (lane < 6) {
-              double vx, vy;
-              pent_vertex(lane == 5 ? 0 : lane, q.cx, q.cy, q.geo, q.hx, q.hy, vx, vy);
-              sm.verts[off + lane] = make_float2((float)vx, (float)vy);
-            }
-          } else {
-            const int ne = nq - 1, sh = 6 - (31 - __clz(ne));  // stride 64 / ne, ne a power of two
-            // polygons cast by the analytic edge pick (ne >= 16) index their vertices modulo ne:
-            // the closing vertex is only staged for the small ones that take the edge loop
-            const int ns = ne >= 16 ? ne : nq;
-            for (int k = lane; k < ns; k += 32) {
-              const double2 un = __ldg(&unit[(k == ne ? 0 : k) << sh]);
-              sm.verts[off + k] = make_float2((float)(q.cx + q.geo * un.x), (float)(q.cy + q.geo * un.y));
-            }
-          }
-        }
-        if (COUNT) {  // reference-semantics ray/segment tests of this round (bench / parity only)
-          for (int i = lane; i < R; i += 32)
-            for (int rr = 0; rr < nr; ++rr) {
-              const ObstRec& q = sm.rec[rr];
+          const int tot = n1 + n2;
+          if (COUNT) {  // reference-semantics ray/segment tests of this record (bench / parity only)
+            for (int i = sub; i < R; i += G) {
               const int hits = ((q.a <= i && i < q.b) ? 1 : 0) + ((q.a <= i - R && i - R < q.b) ? 1 : 0);
-              if ((q.flags & OFLAG_ALLRAYS) || hits > 0) ntests += (unsigned)((q.nv - 1) * max(hits, 1));
+              if ((fl & OFLAG_ALLRAYS) || hits > 0) ntests += (unsigned)((nq - 1) * max(hits, 1));
             }
-        }
-        __syncwarp();
-        // ---- cast: lanes over the flat list of (record, candidate ray) pairs of this round
-        for (int t = lane; t < T; t += 32) {
-          int rr = 0;
-#pragma unroll
-          for (int k = 1; k < RROUND; ++k)
-            if (k < nr && t >= sm.cand[k].x) rr = k;
-          const int4 cd = sm.cand[rr];
-          const int u = t - cd.x;
-          const int i = u < cd.z ? cd.y + u : cd.w + (u - cd.z);
-          // ray direction in the world frame, formed in FP64 (vessel.py:317)
-          const double2 cs = reinterpret_cast<const double2*>(A.rays.cos_sin)[i];
-          const float c = (float)(cs.x * cpsi - cs.y * spsi), sn = (float)(cs.y * cpsi + cs.x * spsi);
-          // world angle of ray i; only selects which polygon edge the analytic pick looks at
-          // (both neighbours are tested), FP32 is plenty
-          const float theta = fmaf((float)(i + 1), dth_f, psi_m_pi);
-          const float cur = sdist[i];
-          const float got = cast_ray_record(sm.rec[rr], sm.verts + sm.voff[rr], c, sn, theta, cur, rangef);
-          if (got < cur) {  // readings are >= 0: their bit patterns order like the values
-            atomicMin(reinterpret_cast<int*>(sdist) + i, __float_as_int(got));
-            atomicOr(hitmask + (i >> 5), 1u << (i & 31));
           }
+          if (tot == 0) continue;  // uniform in the group
+          const bool ngon = !(fl & (OFLAG_PENTAGON | OFLAG_WORLD | OFLAG_INSIDE)) && nq > 16;
+          const bool chain = !ngon && !(fl & OFLAG_INSIDE);
+          if (chain) {
+            if (nq > A.vmax) {  // a polygon the vertex stage cannot hold: flagged, never silently miscast
+              if (sub == 0 && batch.status != nullptr) atomicOr(batch.status, AUV_STATUS_POLY_TOO_LARGE);
+              continue;
+            }
+            // ---- stage the vertices: vessel-relative, formed in FP64, stored FP32
+            if (fl & OFLAG_WORLD) {
+              const double2* wv = reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase;
+              for (int k = sub; k < nq; k += G) {
+                const double2 w = wv[k];
+                sm.verts[k] = make_float2((float)(w.x - px), (float)(w.y - py));
+              }
+            } else if (fl & OFLAG_PENTAGON) {
+              if (sub < 6) {
+                double vx, vy;
+                pent_vertex(sub == 5 ? 0 : sub, q.cx, q.cy, q.geo, q.hx, q.hy, vx, vy);
+                sm.verts[sub] = make_float2((float)vx, (float)vy);
+              }
+            } else {  // small polygonised circle (4 / 8 / 16 sides) incl. the closing vertex
+              const int ne = nq - 1, sh = 6 - (31 - __clz(ne));
+              for (int k = sub; k < nq; k += G) {
+                const double2 un = __ldg(&unit[(k == ne ? 0 : k) << sh]);
+                sm.verts[k] = make_float2((float)(q.cx + q.geo * un.x), (float)(q.cy + q.geo * un.y));
+              }
+            }
+            __syncwarp(gm);
+          }
+          const float ecx = q.ecx, ecy = q.ecy, rho = q.rho;
+          const float slack = rho * 1e-5f + 1e-4f;
+          // ---- cast: the group's lanes over the record's candidate rays (one writer per ray)
+          for (int u = sub; u < tot; u += G) {
+            const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
+            const float cur = sdist[i];
+            float got = cur;
+            if (fl & OFLAG_INSIDE) {
+              got = 0.f;
+            } else {
+              // ray direction in the world frame, formed in FP64 (vessel.py:317)
+              const double2 cs = cos_sin[i];
+              const float c = (float)(cs.x * cpsi - cs.y * spsi), sn = (float)(cs.y * cpsi + cs.x * spsi);
+              const float tc = ecx * c + ecy * sn;
+              const float hc = ecy * c - ecx * sn;
+              if (!(fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > cur)) {
+                if (ngon) {
+                  // world angle of ray i; only selects which polygon edge the analytic pick looks at
+                  const float theta = fmaf((float)(i + 1), dth_f, psi_m_pi);
+                  got = cast_ngon(ecx, ecy, rho, nq - 1, s_unit, c, sn, theta, tc, hc, cur, rangef);
+                } else {
+                  got = cast_chain(sm.verts, nq, c, sn, cur, rangef);
+                }
+              }
+            }
+            if (got < cur) {
+              sdist[i] = got;
+              if (sm.sslot != nullptr) sm.sslot[i] = (uint8_t)min(r0 + rr, 255);
+            }
+          }
+          __syncwarp(gm);  // next record: other lanes touch these rays, the vertex stage is reused
         }
-        r0 += nr;
-      }
-      __syncwarp();
-      // ---- closeness / collision / penalty of the rays that were shortened
-      //      (vessel.py:88-95,356-359; rewarder.py:199-214)
-      float extra = 0.f;
-      // words of the hit mask that are not empty (rpad <= 1024: at most 32 words, one per lane)
-      unsigned words = __ballot_sync(AUV_FULL, lane < rpad / 32 && hitmask[lane] != 0u);
-      any_hit = words != 0u;
-      while (words) {
-        const int w = __ffs(words) - 1;
-        words &= words - 1;
-        const unsigned m = hitmask[w];  // warp-uniform
-        if ((m >> lane) & 1u) {
-          const int i = w * 32 + lane;
-          const float d = sdist[i];
-          float cl;
-          if (cfg.sensor_log_transform)  // log(1 + d) by the hardware log2: |error| < 1e-6 of a value in [0, 5]
-            cl = 1.f - fminf(fmaxf(__logf(1.f + d) * A.inv_log_range, 0.f), 1.f);
-          else
-            cl = 1.f - fminf(fmaxf(d / rangef, 0.f), 1.f);
-          scl[i] = fminf(fmaxf(cl, -1.f), 1.f);
-          extra += A.rays.weight[i] * (rangef * __expf(-0.1f * d) - A.pen_clear_ray);
-          collision = collision || (d < widthf);
-        }
-      }
-      if (any_hit) {
-        collision = __any_sync(AUV_FULL, collision);
-        pen += warp_sum(extra);
-        __syncwarp();
       }
     }
-    // ---- closeness part of the observation: zeros (vessel.py:275-305) unless some ray was hit
-    if ((A.obs_dim & 1) == 0) {  // rows and obs + 6 are 8-byte aligned
-      float2* o2 = reinterpret_cast<float2*>(obs + 6);
-      if (any_hit) {
-        for (int k = lane; k < R / 2; k += 32) o2[k] = reinterpret_cast<const float2*>(scl)[k];
-        if ((R & 1) && lane == 0) obs[6 + R - 1] = scl[R - 1];
-      } else {
-        for (int k = lane; k < R / 2; k += 32) o2[k] = make_float2(0.f, 0.f);
-        if ((R & 1) && lane == 0) obs[6 + R - 1] = 0.f;
+    // ---- closeness / collision / penalty / observation in one pass over the rays
+    //      (vessel.py:88-95,356-359; rewarder.py:199-214; zeros without nearby obstacles: vessel.py:275-305)
+    float extra = 0.f;
+    const bool vel_obs = cfg.sensor_use_velocity_observations != 0;
+    if (cnt > 0) {
+      const double cpsi = SCAL(NAV_COSPSI), spsi = SCAL(NAV_SINPSI);
+      const double2* __restrict__ cos_sin = reinterpret_cast<const double2*>(A.rays.cos_sin);
+      const bool vec2 = (A.obs_dim & 1) == 0;  // rows and obs + 6 are 8-byte aligned
+      for (int k = sub; k < (R + 1) / 2; k += G) {
+        float cl2[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = 2 * k + h;
+          if (i >= R) continue;
+          const float d = sdist[i];
+          float vxr = 0.f, vyr = 0.f;
+          if (d < rangef) {
+            if (cfg.sensor_log_transform)  // log(1 + d) by the hardware log2: |error| < 1e-6 of a value in [0, 5]
+              cl2[h] = 1.f - fminf(fmaxf(__logf(1.f + d) * A.inv_log_range, 0.f), 1.f);
+            else
+              cl2[h] = 1.f - fminf(fmaxf(d / rangef, 0.f), 1.f);
+            cl2[h] = fminf(fmaxf(cl2[h], -1.f), 1.f);
+            if (sm.sslot != nullptr) {
+              // sensor.py:118-128: Rz(-theta - pi/2) (dx, dy) of the nearest obstacle hit by the ray
+              const ObstRec& q = grec[sm.sslot[i]];
+              if (q.flags & OFLAG_PENTAGON) {
+                const double2 cs = cos_sin[i];
+                const double c = cs.x * cpsi - cs.y * spsi, sn = cs.y * cpsi + cs.x * spsi;
+                const double dx = (double)q.step_len * q.hx, dy = (double)q.step_len * q.hy;
+                vxr = (float)(-sn * dx + c * dy);
+                vyr = (float)(-c * dx - sn * dy);
+              }
+            }
+            extra += A.rays.weight[i] * (rangef * __expf(-0.1f * d + fmaxf(0.f, vyr)) - A.pen_clear_ray);
+            collision = collision || (d < widthf);
+          }
+          if (vel_obs) {
+            obs[6 + R + i] = fminf(fmaxf(vxr, -1.f), 1.f);
+            obs[6 + 2 * R + i] = fminf(fmaxf(vyr, -1.f), 1.f);
+          }
+          if (!vec2) obs[6 + i] = cl2[h];
+        }
+        if (vec2) {
+          if (2 * k + 1 < R)
+            reinterpret_cast<float2*>(obs + 6)[k] = make_float2(cl2[0], cl2[1]);
+          else
+            obs[6 + 2 * k] = cl2[0];
+        }
       }
+      collision = __any_sync(gm, collision);
+      pen += group_sum<G>(gm, extra);
     } else {
-      for (int i = lane; i < R; i += 32) obs[6 + i] = any_hit ? scl[i] : 0.f;
+      if ((A.obs_dim & 1) == 0) {
+        float2* o2 = reinterpret_cast<float2*>(obs + 6);
+        for (int k = sub; k < R / 2; k += G) o2[k] = make_float2(0.f, 0.f);
+        if ((R & 1) && sub == 0) obs[6 + R - 1] = 0.f;
+      } else {
+        for (int i = sub; i < R; i += G) obs[6 + i] = 0.f;
+      }
+      if (vel_obs)
+        for (int k = sub; k < 2 * R; k += G) obs[6 + R + k] = 0.f;
     }
     if (A.out.lidar_dist != nullptr)
-      for (int i = lane; i < R; i += 32) A.out.lidar_dist[(long long)e * R + i] = cnt > 0 ? sdist[i] : rangef;
-    if (cfg.sensor_use_velocity_observations)  // sensor.py:159: the speed channel is (0,0) at HEAD
-      for (int k = lane; k < 2 * R; k += 32) obs[6 + R + k] = 0.f;
+      for (int i = sub; i < R; i += G) A.out.lidar_dist[(long long)e * R + i] = cnt > 0 ? sdist[i] : rangef;
 
     // ---- optional sector pooling (utils/sector_partitioning.py:4-9; sensor.py:215-296)
     if (pooling) {
       const int ns = cfg.n_sectors;
-      __syncwarp();
+      __syncwarp(gm);
       if (cnt == 0)
-        for (int i = lane; i < R; i += 32) sdist[i] = rangef;
-      float* ssec = reinterpret_cast<float*>(sm.verts);  // vertex staging is free again
-      ssec[lane] = rangef;
-      __syncwarp();
-      // min-pooling: segmented warp-shuffle reduction keyed by the ray's sector id
-      for (int i0 = 0; i0 < R; i0 += 32) {
-        const int i = i0 + lane;
+        for (int i = sub; i < R; i += G) sdist[i] = rangef;
+      float* ssec = reinterpret_cast<float*>(sm.verts);  // vertex staging is free again (vmax >= 16: 32 floats)
+      for (int k = sub; k < 32; k += G) ssec[k] = rangef;
+      __syncwarp(gm);
+      // min-pooling: segmented shuffle reduction keyed by the ray's sector id
+      for (int i0 = 0; i0 < R; i0 += G) {
+        const int i = i0 + sub;
         float d = i < R ? sdist[i] : INFINITY;
-        const int sid = i < R ? (int)A.rays.sector[i] : -1 - lane;
+        const int sid = i < R ? (int)A.rays.sector[i] : -1 - sub;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const float od = __shfl_down_sync(AUV_FULL, d, o);
-          const int os = __shfl_down_sync(AUV_FULL, sid, o);
-          if (lane + o < 32 && os == sid) d = fminf(d, od);
+        for (int o = 1; o < G; o <<= 1) {
+          const float od = __shfl_down_sync(gm, d, o, G);
+          const int os = __shfl_down_sync(gm, sid, o, G);
+          if (sub + o < G && os == sid) d = fminf(d, od);
         }
-        const int ps = __shfl_up_sync(AUV_FULL, sid, 1);
-        const bool head = i < R && (lane == 0 || ps != sid);
+        const int ps = __shfl_up_sync(gm, sid, 1, G);
+        const bool head = i < R && (sub == 0 || ps != sid);
         if (head && sid < 32) ssec[sid] = fminf(ssec[sid], d);  // one head per sector per iteration
-        __syncwarp();
+        __syncwarp(gm);
       }
-      if (A.out.sector_min_dist != nullptr && lane < ns) A.out.sector_min_dist[(long long)e * ns + lane] = ssec[lane];
-      if (A.out.sector_feasible_dist != nullptr && lane < ns) {
-        int lo = 0, hi = R;
-        for (int k = 0; k < R; ++k) {  // the sector table is monotone
-          const int sd = A.rays.sector[k];
-          if (sd < lane) lo = k + 1;
-          if (sd <= lane) hi = k + 1;
+      if (A.out.sector_min_dist != nullptr)
+        for (int sct = sub; sct < ns; sct += G) A.out.sector_min_dist[(long long)e * ns + sct] = ssec[sct];
+      if (A.out.sector_feasible_dist != nullptr) {
+        for (int sct = sub; sct < ns; sct += G) {
+          int lo = 0, hi = R;
+          for (int k = 0; k < R; ++k) {  // the sector table is monotone
+            const int sd = A.rays.sector[k];
+            if (sd < sct) lo = k + 1;
+            if (sd <= sct) hi = k + 1;
+          }
+          A.out.sector_feasible_dist[(long long)e * ns + sct] =
+              hi > lo ? feasibility_pooling(sdist + lo, hi - lo, A.feas_width, 2.0 * AUV_PI / (double)R) : rangef;
         }
-        A.out.sector_feasible_dist[(long long)e * ns + lane] =
-            hi > lo ? feasibility_pooling(sdist + lo, hi - lo, A.feas_width, 2.0 * AUV_PI / (double)R) : rangef;
       }
-      __syncwarp();
+      __syncwarp(gm);
     }
   }
   if (COUNT) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ntests += __shfl_xor_sync(AUV_FULL, ntests, o);
-    if (lane == 0 && ntests) atomicAdd(A.out.seg_tests, ntests);
+    for (int o = G / 2; o > 0; o >>= 1) ntests += __shfl_xor_sync(gm, ntests, o);
+    if (sub == 0 && ntests) atomicAdd(A.out.seg_tests, ntests);
   }
 
   // the navigation part of the observation (obs[0..5]) was written by k_vessel_nav
-  const double progress = SCAL(NAV_PROGRESS), goal_dist = SCAL(NAV_GOAL);
+  const double progress = SCAL(NAV_H_PROGRESS), goal_dist = SCAL(NAV_H_GOAL);
   const bool reached = SCAL(NAV_REACHED) != 0.0;
   if (A.mode == AUV_OBSERVE_RESET) {  // explicit reset observe: info mirrors a fresh env
-    if (lane == 0) {
+    if (sub == 0) {
       if (A.out.collision) A.out.collision[e] = collision;
       if (A.out.reached_goal) A.out.reached_goal[e] = reached;
       if (A.out.goal_distance) A.out.goal_distance[e] = (float)goal_dist;
@@ -752,7 +995,7 @@ __device__ __forceinline__ void lidar_env(const LidarArgs& A, WarpSmem& sm, floa
     return;
   }
 
-  // ---- reward (rewarder.py) + done (environment.py:375-384) + counters (uniform across lanes):
+  // ---- reward (rewarder.py) + done (environment.py:375-384) + counters (uniform across the group):
   //      k_vessel_nav computed everything that does not depend on the LiDAR
   double reward = SCAL(NAV_REWARD_BASE);
   if (collision) {
@@ -763,17 +1006,17 @@ __device__ __forceinline__ void lidar_env(const LidarArgs& A, WarpSmem& sm, floa
     reward += 0.5 * closeness_reward;
     if (reward < 0.0) reward *= 2.0;
   }
-  const double y_e = SCAL(NAV_YE);
-  const double cum = SCAL(SC_CUM) + reward;
-  const int t_step = (int)SCAL(SC_TSTEP);
+  const double y_e = SCAL(NAV_H_YE);
+  const double cum = SCAL(NAV_CUM) + reward;
+  const int t_step = (int)SCAL(NAV_TSTEP);
   const bool done = collision || reached || (!cfg.test_mode && t_step >= cfg.max_timesteps - 1) ||
                     (!cfg.test_mode && cum < cfg.min_cumulative_reward);
-  const double cte_sum = SCAL(SC_CTE) + fabs(y_e);
+  const double cte_sum = SCAL(NAV_CTE) + fabs(y_e);
   const bool do_reset = done && cfg.auto_reset;
-  const int scn = (int)SCAL(SC_SCN);
+  const int scn = (int)SCAL(NAV_SCN);
   int next = 0;
-  if (do_reset) next = (int)(((long long)scn + n) % A.pool.n_scenarios);  // uniform across the warp
-  if (lane == 0) {
+  if (do_reset) next = (int)(((long long)scn + n) % A.pool.n_scenarios);  // uniform across the group
+  if (sub == 0) {
     A.out.reward[e] = (float)reward;
     A.out.done[e] = done;
     if (A.out.collision) A.out.collision[e] = collision;
@@ -788,6 +1031,7 @@ __device__ __forceinline__ void lidar_env(const LidarArgs& A, WarpSmem& sm, floa
       // ---- VecEnv auto-reset, scalar part.  The first observation of an episode depends on the
       // scenario only, so it was computed once per pool scenario (pool.reset_*) and the reset
       // is a copy: no navigation / culling / casting on the step path.
+      const int npid = A.pool.path_id[next];
       if (A.out.stats != nullptr) {  // env.history entry, environment.py:476-489
         double* st = A.out.stats;
         atomicAdd(st + AUV_STAT_EPISODES, 1.0);
@@ -798,9 +1042,12 @@ __device__ __forceinline__ void lidar_env(const LidarArgs& A, WarpSmem& sm, floa
         atomicAdd(st + AUV_STAT_REACHED_GOAL, reached ? 1.0 : 0.0);
         atomicAdd(st + AUV_STAT_TIMESTEPS, (double)(t_step + 1));
         atomicAdd(st + AUV_STAT_CROSS_TRACK, cte_sum / (double)(t_step + 1));
-        atomicAdd(st + AUV_STAT_PATHLENGTH, A.paths.length[A.pool.path_id[scn]]);
+        atomicAdd(st + AUV_STAT_PATHLENGTH, A.paths.hdr[batch.env_pid[e]].length);
       }
       batch.scn_id[e] = next;
+      batch.env_pid[e] = npid;
+      batch.prev_seg[e] = -1;
+      batch.obst_steps[e] = 0;
       batch.episode[e] += 1;
       const double* vi = A.pool.vessel_init + 3ll * next;
       batch.state[e] = vi[0];
@@ -817,61 +1064,67 @@ __device__ __forceinline__ void lidar_env(const LidarArgs& A, WarpSmem& sm, floa
     }
   }
   if (!do_reset) return;
-  // ---- auto-reset, bulk part (whole warp): terminal obs out, cached first obs in, obstacle
-  //      state and nearby list of the next scenario
-  __syncwarp();
+  // ---- auto-reset, bulk part (whole group): terminal obs out, cached first obs in, obstacle
+  //      state (table-driven tracks only) and nearby list of the next scenario
+  __syncwarp(gm);
   {
     const int km = A.pool.k_moving;
     const float* robs = A.pool.reset_obs + (long long)next * A.obs_dim;
     float* tobs = A.out.terminal_obs ? A.out.terminal_obs + (long long)e * A.obs_dim : nullptr;
-    for (int k = lane; k < A.obs_dim; k += 32) {
+    for (int k = sub; k < A.obs_dim; k += G) {
       if (tobs) tobs[k] = obs[k];
       obs[k] = robs[k];
     }
-    for (int j = lane; j < km; j += 32) {
-      const long long ps = (long long)next * km + j, pe = (long long)e * km + j;
-      reinterpret_cast<double2*>(batch.mov_pos)[pe] = reinterpret_cast<const double2*>(A.pool.mov_pos0)[ps];
-      reinterpret_cast<double2*>(batch.mov_disp)[pe] = reinterpret_cast<const double2*>(A.pool.mov_disp0)[ps];
-      batch.mov_counter[pe] = A.pool.mov_counter0[ps];
-    }
+    if (!A.pool.linear_tracks)
+      for (int j = sub; j < km; j += G) {
+        const long long ps = (long long)next * km + j, pe = (long long)e * km + j;
+        reinterpret_cast<double2*>(batch.mov_pos)[pe] = reinterpret_cast<const double2*>(A.pool.mov_pos0)[ps];
+        reinterpret_cast<double2*>(batch.mov_disp)[pe] = reinterpret_cast<const double2*>(A.pool.mov_disp0)[ps];
+        batch.mov_counter[pe] = A.pool.mov_counter0[ps];
+      }
     if (cfg.use_lidar)
-      for (int w = lane; w < batch.mask_words; w += 32)
+      for (int w = sub; w < batch.mask_words; w += G)
         batch.nearby_mask[(long long)e * batch.mask_words + w] = A.pool.reset_mask[(long long)next * batch.mask_words + w];
   }
 #undef SCAL
 }
 
-// shared memory of one warp: staging + range[rpad] + closeness[rpad] + hit bits (rpad/8 bytes,
-// padded to rpad so every warp's block stays 16-byte aligned)
-__host__ __device__ constexpr size_t lidar_smem_per_warp(int rpad) {
-  return sizeof(WarpSmem) + 2 * sizeof(float) * rpad + rpad;
-}
-
 #ifndef AUV_LIDAR_MINB
-#define AUV_LIDAR_MINB 16  // min resident CTAs per SM asked of the compiler: 64 registers (108 uncapped: 0.177 ms, 80: 0.152, 64: 0.142)
+#define AUV_LIDAR_MINB 16  // min resident CTAs per SM asked of the compiler: 64 registers
 #endif
-template <bool COUNT>
+template <bool COUNT, int G>
 __global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32, AUV_LIDAR_MINB) k_lidar(const __grid_constant__ LidarArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int GPW = 32 / G;  // env groups per warp
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int sub = lane & (G - 1), grp = lane / G;
+  const unsigned gm = group_mask<G>(lane);
   const int R = A.cfg.n_sensors;
   const int rpad = A.cfg.use_lidar ? ((R + 31) & ~31) : 32;
-  const size_t per_warp = lidar_smem_per_warp(rpad);
-  WarpSmem& sm = *reinterpret_cast<WarpSmem*>(smem_raw + per_warp * wib);
-  float* sdist = reinterpret_cast<float*>(smem_raw + per_warp * wib + sizeof(WarpSmem));
-  float* scl = sdist + rpad;
-  unsigned* hitmask = reinterpret_cast<unsigned*>(scl + rpad);
-  int e = A.e0 + (blockIdx.x * AUV_LIDAR_WARPS + wib) * AUV_LIDAR_EPW;
-  if (e >= A.e1) return;
-  const int eend = min(e + AUV_LIDAR_EPW, A.e1);
-  double sc, scn;
-  uint4 spec, specn;
-  lidar_fetch(A.cfg, A.batch, e, lane, sc, spec);
+  // cos/sin(2 pi k / 64) in FP32 for the on-the-fly polygon vertices, once per CTA
+  float2* s_unit = reinterpret_cast<float2*>(smem_raw);
+  if (A.cfg.use_lidar)
+    for (int k = threadIdx.x; k < 64; k += AUV_LIDAR_WARPS * 32) {
+      const double2 un = reinterpret_cast<const double2*>(A.rays.unit64)[k];
+      s_unit[k] = make_float2((float)un.x, (float)un.y);
+    }
+  __syncthreads();
+  const size_t per = lidar_smem_per_env(rpad, A.vmax, A.velocity);
+  unsigned char* my = smem_raw + 64 * sizeof(float2) + per * (size_t)(wib * GPW + grp);
+  EnvSmem sm;
+  sm.rec = reinterpret_cast<ObstRec*>(my);
+  sm.verts = reinterpret_cast<float2*>(my + RROUND * sizeof(ObstRec));
+  sm.sdist = reinterpret_cast<float*>(my + RROUND * sizeof(ObstRec) + (size_t)A.vmax * sizeof(float2));
+  sm.sslot = A.velocity ? reinterpret_cast<uint8_t*>(sm.sdist + rpad) : nullptr;
+  int e = A.e0 + ((blockIdx.x * AUV_LIDAR_WARPS + wib) * GPW + grp) * AUV_LIDAR_EPG;
+  if (e >= A.e1) return;  // the whole group leaves together: every sync below is group-wide only
+  const int eend = min(e + AUV_LIDAR_EPG, A.e1);
+  LidarFetch<G> cur, nxt;
+  lidar_fetch<G>(A.cfg, A.batch, e, sub, cur);
   for (; e < eend; ++e) {
-    if (e + 1 < eend) lidar_fetch(A.cfg, A.batch, e + 1, lane, scn, specn);  // in flight while env e is cast
-    lidar_env<COUNT>(A, sm, sdist, scl, hitmask, rpad, e, lane, sc, spec);
-    sc = scn;
-    spec = specn;
+    if (e + 1 < eend) lidar_fetch<G>(A.cfg, A.batch, e + 1, sub, nxt);  // in flight while env e is cast
+    lidar_env<COUNT, G>(A, sm, s_unit, rpad, e, lane, gm, cur);
+    cur = nxt;
   }
 }
 
@@ -904,6 +1157,7 @@ __global__ void __launch_bounds__(256) k_fma_probe(float* sink, int iters) {
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 
 static thread_local char g_err[512] = "";
 
@@ -918,6 +1172,8 @@ static int cuda_check(cudaError_t e, const char* where) {
 }
 
 extern "C" {
+
+static int check_pool_tracks(const AuvScenarioPool* pool, const AuvBatch* batch);
 
 int auv_abi_version(void) { return AUV_ABI_VERSION; }
 int auv_sizeof(int which) {
@@ -971,6 +1227,8 @@ int auv_obstacle_update(const AuvConfig* cfg, const AuvScenarioPool* pool, AuvBa
   if (int rc = check_cfg(cfg)) return rc;
   if (!pool || !batch) return set_err(AUV_EINVAL, "pool/batch is NULL");
   if (batch->n_envs <= 0) return set_err(AUV_EINVAL, "n_envs must be > 0");
+  if (!batch->obst_steps) return set_err(AUV_EINVAL, "batch.obst_steps is NULL");
+  if (int rc = check_pool_tracks(pool, batch)) return rc;
   return launch_obstacle_update(cfg, pool, batch, 0, batch->n_envs, stream);
 }
 
@@ -989,10 +1247,27 @@ int auv_reset(const AuvConfig* cfg, const AuvScenarioPool* pool, AuvBatch* batch
   if (int rc = check_cfg(cfg)) return rc;
   if (!pool || !batch) return set_err(AUV_EINVAL, "pool/batch is NULL");
   if (batch->n_envs <= 0) return set_err(AUV_EINVAL, "n_envs must be > 0");
+  if (!batch->obst_steps || !batch->prev_seg || !batch->env_pid)
+    return set_err(AUV_EINVAL, "batch.obst_steps / prev_seg / env_pid is NULL");
+  if (int rc = check_pool_tracks(pool, batch)) return rc;
   const int threads = 128;
   const int blocks = (batch->n_envs + threads - 1) / threads;
   auv::k_reset<<<blocks, threads, 0, (cudaStream_t)stream>>>(*pool, *batch, reset_mask);
   return cuda_check(cudaGetLastError(), "k_reset");
+}
+
+static int check_pool_tracks(const AuvScenarioPool* pool, const AuvBatch* batch) {
+  if (pool->k_static > 0 && !pool->st_rec) return set_err(AUV_EINVAL, "pool.st_rec is NULL (auv_pool_pack)");
+  if (pool->k_moving > 0) {
+    if (pool->linear_tracks) {
+      if (!pool->mov_lin) return set_err(AUV_EINVAL, "pool.mov_lin is NULL with linear_tracks (auv_pool_pack)");
+      if (pool->lin_first_wrap <= 0 || pool->lin_wrap_period <= 0)
+        return set_err(AUV_EINVAL, "pool.lin_first_wrap / lin_wrap_period not set (auv_linear_wrap)");
+    } else if (!batch->mov_pos || !batch->mov_disp || !batch->mov_counter) {
+      return set_err(AUV_EINVAL, "batch.mov_pos / mov_disp / mov_counter is NULL with table-driven tracks");
+    }
+  }
+  return 0;
 }
 
 static int check_batch(const AuvConfig* cfg, const AuvScenarioPool* pool, const AuvBatch* batch) {
@@ -1006,6 +1281,9 @@ static int check_batch(const AuvConfig* cfg, const AuvScenarioPool* pool, const 
     return set_err(AUV_EINVAL, "world arrays are NULL");
   if (cfg->use_lidar && (!batch->rec_cnt || (slots > 0 && (!batch->rec || batch->rec_cap <= 0))))
     return set_err(AUV_EINVAL, "batch.rec / rec_cnt / rec_cap missing");
+  if (!batch->obst_steps || !batch->prev_seg || !batch->env_pid)
+    return set_err(AUV_EINVAL, "batch.obst_steps / prev_seg / env_pid is NULL");
+  if (int rc = check_pool_tracks(pool, batch)) return rc;
   return 0;
 }
 
@@ -1044,6 +1322,32 @@ static int launch_vessel_nav(const AuvConfig* cfg, const AuvRayTable* rays, cons
   return cuda_check(cudaGetLastError(), "k_vessel_nav");
 }
 
+// the dynamic shared-memory opt-in of k_lidar is per device and per function; it is made once,
+// outside any stream capture (auv_step_host_submit calls lidar_configure before capturing)
+static std::atomic<size_t> g_lidar_smem_configured[64];
+static int lidar_configure(size_t smem) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (smem <= g_lidar_smem_configured[dev].load(std::memory_order_acquire)) return 0;
+  if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_lidar<false, AUV_LIDAR_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(k_lidar)"))
+    return rc;
+  if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_lidar<true, AUV_LIDAR_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(k_lidar)"))
+    return rc;
+  size_t seen = g_lidar_smem_configured[dev].load(std::memory_order_relaxed);
+  while (seen < smem && !g_lidar_smem_configured[dev].compare_exchange_weak(seen, smem, std::memory_order_release)) {
+  }
+  return 0;
+}
+static int lidar_vmax(const AuvScenarioPool* pool) { return pool->n_world > 0 ? AUV_MAX_POLY_VERTS : 16; }
+static int lidar_velocity(const AuvConfig* cfg) { return cfg->use_lidar && cfg->velocity_mode == AUV_VELOCITY_NEAREST; }
+static size_t lidar_smem_bytes(const AuvConfig* cfg, const AuvScenarioPool* pool) {
+  const int rpad = cfg->use_lidar ? ((cfg->n_sensors + 31) & ~31) : 32;
+  return 64 * sizeof(float2) +
+         auv::lidar_smem_per_env(rpad, lidar_vmax(pool), lidar_velocity(cfg)) * AUV_LIDAR_WARPS * (32 / AUV_LIDAR_G);
+}
+
 static int launch_lidar(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                         const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out, int mode,
                         void* stream, int e0 = 0, int cnt = -1) {
@@ -1059,34 +1363,21 @@ static int launch_lidar(const AuvConfig* cfg, const AuvRayTable* rays, const Auv
   args.obs_dim = auv_obs_dim(cfg);
   args.e0 = e0;
   args.e1 = e0 + cnt;
+  args.vmax = lidar_vmax(pool);
+  args.velocity = lidar_velocity(cfg);
   args.clear_closeness = -cfg->sensor_range * exp(-0.1 * cfg->sensor_range);
   args.pen_clear_ray = (float)(-args.clear_closeness);
   args.inv_log_range = (float)(1.0 / log1p(cfg->sensor_range));
   args.inv_weight_sum = (rays && rays->weight_sum > 0.0) ? 1.0 / rays->weight_sum : 0.0;
   args.feas_width = cfg->vessel_width * cfg->feasibility_width_multiplier;
-  const int rpad = cfg->use_lidar ? ((cfg->n_sensors + 31) & ~31) : 32;
-  const size_t smem = auv::lidar_smem_per_warp(rpad) * AUV_LIDAR_WARPS;
-  // the opt-in is per device and per function; one slot per device ordinal (processes normally
-  // drive one GPU each, but nothing here assumes it)
-  static size_t configured_by_device[64] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-  size_t& configured = configured_by_device[dev];
-  if (smem > configured) {
-    if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_lidar<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                            "cudaFuncSetAttribute(k_lidar)"))
-      return rc;
-    if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_lidar<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                            "cudaFuncSetAttribute(k_lidar)"))
-      return rc;
-    configured = smem;
-  }
-  const int per_cta = AUV_LIDAR_WARPS * AUV_LIDAR_EPW;
+  const size_t smem = lidar_smem_bytes(cfg, pool);
+  if (int rc = lidar_configure(smem)) return rc;
+  const int per_cta = AUV_LIDAR_WARPS * (32 / AUV_LIDAR_G) * AUV_LIDAR_EPG;
   const int blocks = (cnt + per_cta - 1) / per_cta;
   if (out->seg_tests != nullptr)
-    auv::k_lidar<true><<<blocks, AUV_LIDAR_WARPS * 32, smem, (cudaStream_t)stream>>>(args);
+    auv::k_lidar<true, AUV_LIDAR_G><<<blocks, AUV_LIDAR_WARPS * 32, smem, (cudaStream_t)stream>>>(args);
   else
-    auv::k_lidar<false><<<blocks, AUV_LIDAR_WARPS * 32, smem, (cudaStream_t)stream>>>(args);
+    auv::k_lidar<false, AUV_LIDAR_G><<<blocks, AUV_LIDAR_WARPS * 32, smem, (cudaStream_t)stream>>>(args);
   return cuda_check(cudaGetLastError(), "k_lidar");
 }
 
@@ -1177,7 +1468,7 @@ int auv_pipeline_graph_state(const AuvPipeline* p) { return p ? p->graph_state :
 
 static int chunk_size(int n, int n_chunks) {
   int c = (n + n_chunks - 1) / n_chunks;
-  return (c + 63) / 64 * 64;  // whole CTAs of every kernel
+  return (c + 127) / 128 * 128;  // whole CTAs of every kernel
 }
 
 // device-resident variant: every range on its own stream (round robin)
@@ -1278,7 +1569,8 @@ static int step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, cons
         p->gexec = nullptr;
       }
       p->graph_state = 0;
-      // make sure one-time function attributes are set outside the capture
+      // one-time function attributes are set outside the capture
+      if (int rc0 = lidar_configure(lidar_smem_bytes(cfg, pool))) return rc0;
       cudaStream_t cs = p->st[1];
       cudaGraph_t graph = nullptr;
       int rc = 0;
@@ -1422,6 +1714,62 @@ int auv_generate_moving_obstacles(const AuvGenParams* gp, const AuvPathBank* pat
   auv::k_generate_moving_obstacles<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*gp, *paths, *pool, ids, n_ids,
                                                                                           status);
   return cuda_check(cudaGetLastError(), "k_generate_moving_obstacles");
+}
+
+int auv_linear_wrap(double dt, double counter0, int vel_len, int32_t* first_wrap, int32_t* wrap_period) {
+  if (!(dt > 0.0) || vel_len < 2 || !first_wrap || !wrap_period) return set_err(AUV_EINVAL, "bad auv_linear_wrap arguments");
+  const int limit = 1 << 30;
+  // obstacles.py:195-215, literally: counter += dt; index = floor(counter); index >= len - 1 wraps
+  double c = counter0;
+  int n = 0;
+  for (;;) {
+    ++n;
+    c += dt;
+    if ((int)floor(c) >= vel_len - 1) break;
+    if (n >= limit) return set_err(AUV_EINVAL, "track never wraps");
+  }
+  *first_wrap = n;
+  c = 0.0;
+  n = 0;
+  for (;;) {
+    ++n;
+    c += dt;
+    if ((int)floor(c) >= vel_len - 1) break;
+    if (n >= limit) return set_err(AUV_EINVAL, "track never wraps");
+  }
+  *wrap_period = n;
+  return 0;
+}
+
+int auv_pool_pack(const AuvConfig* cfg, const AuvScenarioPool* pool, const int32_t* ids, int n_ids, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  if (!pool) return set_err(AUV_EINVAL, "pool is NULL");
+  if (n_ids <= 0 || (!ids && n_ids > pool->n_scenarios)) return set_err(AUV_EINVAL, "n_ids out of range");
+  if (pool->k_static > 0 && (!pool->st_rec || !pool->st_pos || !pool->st_radius))
+    return set_err(AUV_EINVAL, "static-obstacle arrays are NULL");
+  if (pool->k_moving > 0 && pool->linear_tracks &&
+      (!pool->mov_lin || !pool->mov_pos0 || !pool->mov_start || !pool->mov_width || !pool->mov_track || !pool->vel_table))
+    return set_err(AUV_EINVAL, "moving-obstacle arrays are NULL");
+  const long long total = (long long)n_ids * (pool->k_moving + pool->k_static);
+  if (total == 0) return 0;
+  const int threads = 128;
+  auv::k_pool_pack<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(*cfg, *pool, ids, n_ids);
+  return cuda_check(cudaGetLastError(), "k_pool_pack");
+}
+
+int auv_obstacle_state(const AuvConfig* cfg, const AuvScenarioPool* pool, const AuvBatch* batch, double* pos,
+                       double* disp, double* counter, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  if (!pool || !batch) return set_err(AUV_EINVAL, "pool/batch is NULL");
+  if (batch->n_envs <= 0) return set_err(AUV_EINVAL, "n_envs must be > 0");
+  if (!batch->obst_steps) return set_err(AUV_EINVAL, "batch.obst_steps is NULL");
+  if (int rc = check_pool_tracks(pool, batch)) return rc;
+  const long long total = (long long)batch->n_envs * pool->k_moving;
+  if (total == 0) return 0;
+  const int threads = 128;
+  auv::k_obstacle_state<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(*cfg, *pool, *batch, pos,
+                                                                                                         disp, counter);
+  return cuda_check(cudaGetLastError(), "k_obstacle_state");
 }
 
 int auv_fma_probe(float* sink, int blocks, int threads, int iters, void* stream, double* flops_out) {

@@ -20,12 +20,15 @@ namespace auv {
 #define NAV_HEAD_ERR 5
 #define NAV_GOAL 6
 #define NAV_PROGRESS 7
+// [8..23]: the 128 B hand-over line of the casting stage (k_lidar reads exactly these 16 doubles)
+#define NAV_HAND 8
 #define NAV_COSPSI 8
 #define NAV_SINPSI 9
 #define NAV_REACHED 10
-#define NAV_COS_HEAD_ERR 11
+#define NAV_H_YE 11
 #define NAV_REWARD_BASE 12
-// hand-over to the casting stage (k_lidar reads lanes 0..AUV_NAV_W-1 of this record in one load)
+#define NAV_H_GOAL 13
+#define NAV_H_PROGRESS 14
 #define NAV_X 16
 #define NAV_Y 17
 #define NAV_PSI 18
@@ -35,56 +38,49 @@ namespace auv {
 #define NAV_SCN 22
 #define NAV_CNT 23
 
-// scipy PPoly evaluation (extrapolate=True) at TWO arclengths at once: interval j with
-// x[j] <= s < x[j+1], clamped.  The knots are nearly uniform, so the interval is found among
-// the four knots around the uniform guess (one round of loads for both evaluations); the
-// sequential search only runs when it is not.  L = knots[n_knots - 1] (Path.length).
+// scipy PPoly evaluation (extrapolate=True): interval j with x[j] <= s < x[j+1], clamped.
+// One PCHIP piece is one 96 B record (its two knots + 8 coefficients), so an evaluation is a
+// single round of loads: the knots are nearly uniform, the record of the uniform guess almost
+// always is the right one; its own knots tell, and the neighbour is fetched when it is not.
 struct PchipOut {
   double px, py, dx, dy;
 };
-__device__ __forceinline__ int pchip_interval(const double* __restrict__ kn, int nk, double s, int j, double k0,
-                                              double k1, double k2, double k3) {
-  // k0..k3 = kn[j-1], kn[j], kn[j+1], kn[j+2] (clamped indices)
-  if (s < k1) {
-    if (j > 0) {
-      --j;
-      if (j > 0 && s < k0) {
-        --j;
-        while (j > 0 && s < kn[j]) --j;
-      }
-    }
-  } else if (j < nk - 2 && s >= k2) {
-    ++j;
-    if (j < nk - 2 && s >= k3) {
-      ++j;
-      while (j < nk - 2 && s >= kn[j + 1]) ++j;
-    }
-  }
-  return j;
+struct PPiece {
+  double2 k, a, b, c, d;  // (knot j, knot j+1), x: (c0, c1), (c2, c3), y: (c0, c1), (c2, c3)
+};
+__device__ __forceinline__ PPiece pp_load(const double* __restrict__ base, int j) {
+  const double2* __restrict__ r = reinterpret_cast<const double2*>(base + (long long)j * AUV_PP_W);
+  PPiece p;
+  p.k = r[0];
+  p.a = r[1];
+  p.b = r[2];
+  p.c = r[3];
+  p.d = r[4];
+  return p;
 }
+__device__ __forceinline__ void pp_settle(const double* __restrict__ base, int nk, double s, int& j, PPiece& p) {
+  while (j > 0 && s < p.k.x) p = pp_load(base, --j);
+  while (j < nk - 2 && s >= p.k.y) p = pp_load(base, ++j);
+}
+__device__ __forceinline__ void pp_eval(const PPiece& p, double s, PchipOut& o) {
+  const double t = s - p.k.x;
+  o.px = ((p.a.x * t + p.a.y) * t + p.b.x) * t + p.b.y;
+  o.py = ((p.c.x * t + p.c.y) * t + p.d.x) * t + p.d.y;
+  o.dx = (3.0 * p.a.x * t + 2.0 * p.a.y) * t + p.b.x;
+  o.dy = (3.0 * p.c.x * t + 2.0 * p.c.y) * t + p.d.x;
+}
+// two evaluations, both records in flight together.  L = Path.length (last knot).
 __device__ __forceinline__ void pchip_eval2(const AuvPathBank& pb, int pid, double L, double s1, double s2,
                                             PchipOut& o1, PchipOut& o2) {
   const int nk = pb.n_knots;
-  const double* __restrict__ kn = pb.knots + (long long)pid * nk;
+  const double* __restrict__ base = pb.pp + (long long)pid * (nk - 1) * AUV_PP_W;
   int j1 = max(0, min(nk - 2, (int)((s1 / L) * (nk - 1))));
   int j2 = max(0, min(nk - 2, (int)((s2 / L) * (nk - 1))));
-  const double a0 = kn[max(j1 - 1, 0)], a1 = kn[j1], a2 = kn[j1 + 1], a3 = kn[min(j1 + 2, nk - 1)];
-  const double b0 = kn[max(j2 - 1, 0)], b1 = kn[j2], b2 = kn[j2 + 1], b3 = kn[min(j2 + 2, nk - 1)];
-  j1 = pchip_interval(kn, nk, s1, j1, a0, a1, a2, a3);
-  j2 = pchip_interval(kn, nk, s2, j2, b0, b1, b2, b3);
-  const double2* __restrict__ c1 = reinterpret_cast<const double2*>(pb.coef + ((long long)pid * (nk - 1) + j1) * 8);
-  const double2* __restrict__ c2 = reinterpret_cast<const double2*>(pb.coef + ((long long)pid * (nk - 1) + j2) * 8);
-  const double t1 = s1 - kn[j1], t2 = s2 - kn[j2];
-  const double2 p0 = c1[0], p1 = c1[1], p2 = c1[2], p3 = c1[3];
-  const double2 q0 = c2[0], q1 = c2[1], q2 = c2[2], q3 = c2[3];
-  o1.px = ((p0.x * t1 + p0.y) * t1 + p1.x) * t1 + p1.y;
-  o1.py = ((p2.x * t1 + p2.y) * t1 + p3.x) * t1 + p3.y;
-  o1.dx = (3.0 * p0.x * t1 + 2.0 * p0.y) * t1 + p1.x;
-  o1.dy = (3.0 * p2.x * t1 + 2.0 * p2.y) * t1 + p3.x;
-  o2.px = ((q0.x * t2 + q0.y) * t2 + q1.x) * t2 + q1.y;
-  o2.py = ((q2.x * t2 + q2.y) * t2 + q3.x) * t2 + q3.y;
-  o2.dx = (3.0 * q0.x * t2 + 2.0 * q0.y) * t2 + q1.x;
-  o2.dy = (3.0 * q2.x * t2 + 2.0 * q2.y) * t2 + q3.x;
+  PPiece p1 = pp_load(base, j1), p2 = pp_load(base, j2);
+  pp_settle(base, nk, s1, j1, p1);
+  pp_settle(base, nk, s2, j2, p2);
+  pp_eval(p1, s1, o1);
+  pp_eval(p2, s2, o2);
 }
 
 // exact squared distance from P to segment AB (GEOS Distance::pointToSegment, squared;
@@ -121,18 +117,31 @@ __device__ __forceinline__ unsigned group_ballot(unsigned gm, int lane, bool pre
   return G == 32 ? b : ((b >> (lane & ~(G - 1))) & ((1u << G) - 1u));
 }
 
+// capsule tables of one path: the global arrays, or the CTA's shared-memory copy of them
+struct PathTabs {
+  const float4* sbc;    // superblock chords
+  const float2* sba;    // superblock (1/|e|^2, deviation)
+  const float4* chord;  // block chords
+  const float2* aux;    // block (1/|e|^2, deviation)
+};
+
 // GEOS LengthIndexOfPoint::indexOf (LineString.project) restated as an exact three-level
-// search, executed by a GROUP of G lanes per env.  Level 2 = superblocks of 32 blocks, level 1
-// = blocks of 32 segments; each node is a capsule (chord, max deviation) that contains its part
-// of the polyline, so
+// search, executed by a GROUP of G lanes per env.  Level 2 = superblocks of AUV_PATH_SUPER
+// blocks, level 1 = blocks of 32 segments; each node is a capsule (chord, max deviation) that
+// contains its part of the polyline, so
 //   dist(P, node) in [dc - dev, dc + dev],  dc = dist(P, chord)   (FP32, padded).
-// Pass A finds an upper bound over superblocks, pass B tightens it over the blocks of the
-// surviving superblocks, pass C refines in FP64 every block whose lower bound does not
-// exceed it.  In every pass the lanes of the group take different nodes / segments, so one
-// round of loads covers G of them, and the bound is shared by a shuffle-min; all bounds are
-// compared in the squared domain (one sqrt only when a bound improves).  The arg-min is
-// lexicographic in (distance, segment index), which is GEOS's "first minimum wins"
-// independent of visiting order.  Every lane returns the same arclength.
+// An upper bound `ub` of the minimum distance comes either from the segment the previous step's
+// projection ended on (WARM: the own-ship moves < 1 m per step, so the exact FP64 distance to a few
+// segments around it is within millimetres of the answer -- it is only used as a bound, the search
+// below stays exhaustive) or, without one (first step of an episode), from pass A over the
+// superblock capsules and pass B over the block capsules of the surviving superblocks.  Pass C
+// refines in FP64 every block whose lower bound does not exceed `ub`.  In every pass the lanes of
+// the group take different nodes / segments, so one round of loads covers G of them, and bounds are
+// shared by shuffle-min; all bounds are compared in the squared domain.  Every loop pops the next set
+// bit of a mask that is uniform in the group ("by rank"): the groups of a warp then run their r-th
+// live node together instead of serialising over node indices.  The arg-min is lexicographic in
+// (distance, segment index), which is GEOS's "first minimum wins" independent of visiting order.
+// Every lane returns the same arclength; seg_out = the winning segment.
 #ifdef AUV_NOINLINE_PROJECT
 #define AUV_PROJECT_INLINE __noinline__
 #else
@@ -144,93 +153,103 @@ __device__ __forceinline__ unsigned group_ballot(unsigned gm, int lane, bool pre
 #define AUV_NAVIGATE_INLINE __forceinline__
 #endif
 template <int G>
-__device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, int pid, double px, double py,
-                                                const int lane, const unsigned gm) {
+__device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const AuvPathHdr& h, const PathTabs& T,
+                                                   const double px, const double py, const int prev_seg,
+                                                   const int lane, const unsigned gm, int& seg_out) {
   constexpr int KB = AUV_PATH_SUPER / G;  // blocks of a superblock per lane
   constexpr int KS = AUV_PATH_BLOCK / G;  // segments of a block per lane
   constexpr int KBB = KB < 8 ? KB : 8;    // ... loaded in batches of at most 8
   constexpr int KSB = KS < 8 ? KS : 8;
   const int sub = lane & (G - 1);
-  const int v0 = pb.poly_off[pid];
-  const int nseg = pb.poly_off[pid + 1] - v0 - 1;
-  const int b0 = pb.blk_off[pid];
-  const int nblk = pb.blk_off[pid + 1] - b0;
-  const int s0 = pb.sb_off[pid];
-  const int nsb = pb.sb_off[pid + 1] - s0;
-  const double ox = pb.origin[2 * pid], oy = pb.origin[2 * pid + 1];
-  const float qx = (float)(px - ox), qy = (float)(py - oy);
+  const int nseg = h.nseg;
+  const int nblk = (nseg + AUV_PATH_BLOCK - 1) / AUV_PATH_BLOCK;
+  const int nsb = (nblk + AUV_PATH_SUPER - 1) / AUV_PATH_SUPER;
+  const float qx = (float)(px - h.ox), qy = (float)(py - h.oy);
   const float pad = 1e-6f * (fabsf(qx) + fabsf(qy)) + 1e-6f;
-  const float4* chord = reinterpret_cast<const float4*>(pb.blk_chord) + b0;
-  const float2* aux = reinterpret_cast<const float2*>(pb.blk_dev) + b0;  // (1/|e|^2, deviation)
-  const float4* sbc = reinterpret_cast<const float4*>(pb.sb_chord) + s0;
-  const float2* sba = reinterpret_cast<const float2*>(pb.sb_dev) + s0;
+  const float4* chord = T.chord;
+  const float2* aux = T.aux;
+  const float4* sbc = T.sbc;
+  const float2* sba = T.sba;
+  const double2* __restrict__ poly = reinterpret_cast<const double2*>(pb.poly_xy) + h.v0;
   const float up = 1.f + 4e-6f, dn2 = (1.f - 4e-6f) * (1.f - 4e-6f);
   float ub = INFINITY;
 #define AUV_TIGHTEN(d2, dv)                                         \
   if ((d2) < ub * ub) ub = fminf(ub, sqrtf(d2) * up + (dv) + pad);
 #define AUV_PRUNED(d2, dv) ((d2) * dn2 > (ub + (dv) + pad) * (ub + (dv) + pad))
-  // pass A: upper bound over the superblocks
-  for (int g0 = 0; g0 < nsb; g0 += 4 * G) {  // four rounds of loads in flight
-    float4 ch[4];
-    float2 ax[4];
+  const bool warm = prev_seg >= 0 && prev_seg < nseg;  // uniform in the group
+  if (warm) {
+    // lanes look at segments prev-3, prev, prev+3, prev+6 (...): an actual segment's distance
+    const int k = min(max(prev_seg + (sub - 1) * 3, 0), nseg - 1);
+    double d2 = seg_d2(px, py, poly[k], poly[k + 1]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = min(g0 + k * G + sub, nsb - 1);
-      ch[k] = sbc[i];
-      ax[k] = sba[i];
-    }
+    for (int o = G / 2; o > 0; o >>= 1) d2 = fmin(d2, __shfl_xor_sync(gm, d2, o));
+    ub = sqrtf((float)d2) * up + pad;
+  } else {
+    // pass A: upper bound over the superblocks
+    for (int g0 = 0; g0 < nsb; g0 += 4 * G) {  // four rounds of loads in flight
+      float4 ch[4];
+      float2 ax[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float d2 = pt_chord_d2_f(qx, qy, ch[k], ax[k].x);
-      AUV_TIGHTEN(d2, ax[k].y)
+      for (int k = 0; k < 4; ++k) {
+        const int i = min(g0 + k * G + sub, nsb - 1);
+        ch[k] = sbc[i];
+        ax[k] = sba[i];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float d2 = pt_chord_d2_f(qx, qy, ch[k], ax[k].x);
+        AUV_TIGHTEN(d2, ax[k].y)
+      }
     }
+    ub = group_min<G>(gm, ub);
   }
-  ub = group_min<G>(gm, ub);
-  const double2* poly = reinterpret_cast<const double2*>(pb.poly_xy) + v0;
   double best_d2 = INFINITY;
   int best_seg = 0x7fffffff;
-  // Superblocks are handled in windows of 64 (one bit each).  All loops below pop the next set
-  // bit of a mask that is uniform in the group ("by rank"): the groups of a warp then run their
-  // r-th live node together instead of serialising over node indices.
-  for (int w0 = 0; w0 < nsb; w0 += 64) {
-    const int wn = min(64, nsb - w0);
-    unsigned long long live = 0ull;
-    for (int t = 0; t < wn; ++t) {
-      const float2 a0 = sba[w0 + t];
-      if (!AUV_PRUNED(pt_chord_d2_f(qx, qy, sbc[w0 + t], a0.x), a0.y)) live |= 1ull << t;
+  // superblocks in windows of 32 (one bit each); the lanes test different superblocks
+  for (int w0 = 0; w0 < nsb; w0 += 32) {
+    const int wn = min(32, nsb - w0);
+    unsigned live = 0u;
+#pragma unroll
+    for (int k = 0; k < 32 / G; ++k) {
+      const int t = k * G + sub;
+      const int i = min(w0 + t, nsb - 1);
+      const float2 a0 = sba[i];
+      live |= group_ballot<G>(gm, lane, t < wn && !AUV_PRUNED(pt_chord_d2_f(qx, qy, sbc[i], a0.x), a0.y)) << (k * G);
     }
-    // pass B: tighten over the blocks of the surviving superblocks
-    for (unsigned long long rest = live; rest;) {
-      const int t = __ffsll((long long)rest) - 1;
-      rest &= rest - 1;
-      const int sb = w0 + t;
-      const float2 a0 = sba[sb];
-      if (AUV_PRUNED(pt_chord_d2_f(qx, qy, sbc[sb], a0.x), a0.y)) {  // ub has tightened since
-        live &= ~(1ull << t);
-        continue;
-      }
-      const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
-#pragma unroll
-      for (int k0 = 0; k0 < KB; k0 += KBB) {
-        float4 ch[KBB];
-        float2 ax[KBB];
-#pragma unroll
-        for (int k = 0; k < KBB; ++k) {
-          const int i = min(sb * AUV_PATH_SUPER + (k0 + k) * G + sub, be - 1);
-          ch[k] = chord[i];
-          ax[k] = aux[i];
+    if (!warm) {
+      // pass B: tighten over the blocks of the surviving superblocks
+      for (unsigned rest = live; rest;) {
+        const int t = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int sb = w0 + t;
+        const float2 a0 = sba[sb];
+        if (AUV_PRUNED(pt_chord_d2_f(qx, qy, sbc[sb], a0.x), a0.y)) {  // ub has tightened since
+          live &= ~(1u << t);
+          continue;
         }
+        const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
 #pragma unroll
-        for (int k = 0; k < KBB; ++k) {
-          const float d2 = pt_chord_d2_f(qx, qy, ch[k], ax[k].x);
-          AUV_TIGHTEN(d2, ax[k].y)
+        for (int k0 = 0; k0 < KB; k0 += KBB) {
+          float4 ch[KBB];
+          float2 ax[KBB];
+#pragma unroll
+          for (int k = 0; k < KBB; ++k) {
+            const int i = min(sb * AUV_PATH_SUPER + (k0 + k) * G + sub, be - 1);
+            ch[k] = chord[i];
+            ax[k] = aux[i];
+          }
+#pragma unroll
+          for (int k = 0; k < KBB; ++k) {
+            const float d2 = pt_chord_d2_f(qx, qy, ch[k], ax[k].x);
+            AUV_TIGHTEN(d2, ax[k].y)
+          }
         }
+        ub = group_min<G>(gm, ub);
       }
-      ub = group_min<G>(gm, ub);
     }
     // pass C: exact refine of the blocks that can still hold the minimum
-    for (unsigned long long rest = live; rest;) {
-      const int t = __ffsll((long long)rest) - 1;
+    for (unsigned rest = live; rest;) {
+      const int t = __ffs(rest) - 1;
       rest &= rest - 1;
       const int sb = w0 + t;
       const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
@@ -279,9 +298,10 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, int pi
       best_seg = oi;
     }
   }
+  seg_out = best_seg;
   // segmentNearestMeasure of the winning segment
   const double2 A = poly[best_seg], B = poly[best_seg + 1];
-  const double start = pb.poly_cum[v0 + best_seg];
+  const double start = pb.poly_cum[h.v0 + best_seg];
   const double ex = B.x - A.x, ey = B.y - A.y;
   const double len2 = ex * ex + ey * ey;
   if (len2 == 0.0) return start;
@@ -297,11 +317,11 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, int pi
 // the LiDAR-independent part of the reward (rewarder.py:78-140,167-241).
 // `s` is the projected arclength (project_group); every lane of the env's group computes the
 // same scalars, `store` is true for the one lane that writes them.
-__device__ AUV_NAVIGATE_INLINE void navigate_env(const AuvConfig& cfg, const AuvPathBank& pb,
-                                             const AuvBatch& batch, int pid, int e, const double s, double px,
+__device__ AUV_NAVIGATE_INLINE void navigate_env(const AuvConfig& cfg, const AuvPathBank& pb, const AuvPathHdr& h,
+                                             const AuvBatch& batch, int pid, int e, int scn, const double s, double px,
                                              double py, double psi, double vu, double vv, double vr,
                                              float* __restrict__ obs_row, const bool store) {
-  const double L = pb.length[pid];
+  const double L = h.length;
   const double s_la = fmin(L, s + cfg.look_ahead_distance);
   PchipOut at_s, at_la;
   pchip_eval2(pb, pid, L, s, s_la, at_s, at_la);
@@ -317,7 +337,7 @@ __device__ AUV_NAVIGATE_INLINE void navigate_env(const AuvConfig& cfg, const Auv
   const double la_err = princip((double)atan2f((float)ldy, (float)ldx) - psi);
   const double head_err = princip((double)atan2f((float)(l_y - py), (float)(l_x - px)) - psi);
   const double progress = s / L;
-  const double gx = pb.end_xy[2 * pid] - px, gy = pb.end_xy[2 * pid + 1] - py;
+  const double gx = h.end_x - px, gy = h.end_y - py;
   const double goal = sqrt(gx * gx + gy * gy);
   const bool reached = (goal <= cfg.min_goal_distance) || (progress >= cfg.min_path_progress);
   double sp, cp;
@@ -341,28 +361,20 @@ __device__ AUV_NAVIGATE_INLINE void navigate_env(const AuvConfig& cfg, const Auv
   }
   if (!store) return;
   batch.max_progress[e] = maxprog;
-  double* o = batch.nav + (long long)e * AUV_NAV_W;
-  o[NAV_S] = s;
-  o[NAV_CHI] = chi;
-  o[NAV_YE] = y_e;
-  o[NAV_SLA] = s_la;
-  o[NAV_LA_ERR] = la_err;
-  o[NAV_HEAD_ERR] = head_err;
-  o[NAV_GOAL] = goal;
-  o[NAV_PROGRESS] = progress;
-  o[NAV_COSPSI] = cp;
-  o[NAV_SINPSI] = sp;
-  o[NAV_REACHED] = reached ? 1.0 : 0.0;
-  o[NAV_COS_HEAD_ERR] = cos_he;
-  o[NAV_REWARD_BASE] = base;
-  o[NAV_X] = px;
-  o[NAV_Y] = py;
-  o[NAV_PSI] = psi;
-  o[NAV_CUM] = batch.cum_reward[e];
-  o[NAV_CTE] = batch.cte_sum[e];
-  o[NAV_TSTEP] = (double)batch.t_step[e];
-  o[NAV_SCN] = (double)batch.scn_id[e];
-  o[NAV_CNT] = 0.0;  // the culling stage overwrites it
+  // the 192 B record leaves as 12 x 16 B stores (indices: NAV_* above)
+  double2* o = reinterpret_cast<double2*>(batch.nav + (long long)e * AUV_NAV_W);
+  o[0] = make_double2(s, chi);                                // NAV_S, NAV_CHI
+  o[1] = make_double2(y_e, s_la);                             // NAV_YE, NAV_SLA
+  o[2] = make_double2(la_err, head_err);                      // NAV_LA_ERR, NAV_HEAD_ERR
+  o[3] = make_double2(goal, progress);                        // NAV_GOAL, NAV_PROGRESS
+  o[4] = make_double2(cp, sp);                                // NAV_COSPSI, NAV_SINPSI
+  o[5] = make_double2(reached ? 1.0 : 0.0, y_e);              // NAV_REACHED, NAV_H_YE
+  o[6] = make_double2(base, goal);                            // NAV_REWARD_BASE, NAV_H_GOAL
+  o[7] = make_double2(progress, 0.0);                         // NAV_H_PROGRESS, unused
+  o[8] = make_double2(px, py);                                // NAV_X, NAV_Y
+  o[9] = make_double2(psi, batch.cum_reward[e]);              // NAV_PSI, NAV_CUM
+  o[10] = make_double2(batch.cte_sum[e], (double)batch.t_step[e]);  // NAV_CTE, NAV_TSTEP
+  o[11] = make_double2((double)scn, 0.0);                     // NAV_SCN, NAV_CNT (the culling stage overwrites it)
   if (obs_row != nullptr) {  // [u, v, r, look-ahead heading error, heading error, cross-track / 100]
     obs_row[0] = (float)fmin(fmax(vu, -1.0), 1.0);
     obs_row[1] = (float)fmin(fmax(vv, -1.0), 1.0);

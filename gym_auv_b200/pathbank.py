@@ -26,6 +26,9 @@ from scipy import interpolate
 PATH_BLOCK = 32  # must equal AUV_PATH_BLOCK in include/auv_b200.h
 PATH_SUPER = int(os.environ.get("AUV_PATH_SUPER", 16))  # blocks per superblock, AUV_PATH_SUPER (env override: tuning builds only)
 N_KNOTS = 1000
+PP_W = 12  # AUV_PP_W
+HDR_DTYPE = np.dtype([("v0", "<i4"), ("nseg", "<i4"), ("b0", "<i4"), ("s0", "<i4"), ("ox", "<f8"), ("oy", "<f8"),
+                      ("length", "<f8"), ("end_x", "<f8"), ("end_y", "<f8"), ("reserved", "<f8")])  # AuvPathHdr
 
 
 @dataclass
@@ -129,7 +132,9 @@ def build_path(waypoints) -> PathTable:
 
 
 class PathBank:
-    """A list of PathTable concatenated into the flat arrays of ``AuvPathBank``."""
+    """A list of PathTable concatenated into the flat arrays of ``AuvPathBank``: one 64 B header
+    per path, capsule tables whose per-path offsets are even (so a CTA can bulk-copy a path's
+    tables into shared memory in 16 B units), one 96 B record per PCHIP piece."""
 
     def __init__(self, tables: Sequence[PathTable]):
         if len(tables) == 0:
@@ -139,16 +144,26 @@ class PathBank:
         self.poly_off = np.zeros(self.n_paths + 1, dtype=np.int32)
         self.blk_off = np.zeros(self.n_paths + 1, dtype=np.int32)
         self.sb_off = np.zeros(self.n_paths + 1, dtype=np.int32)
+        even = lambda k: (int(k) + 1) & ~1
         for i, t in enumerate(tables):
             self.poly_off[i + 1] = self.poly_off[i] + len(t.poly)
-            self.blk_off[i + 1] = self.blk_off[i] + len(t.blk_dev)
-            self.sb_off[i + 1] = self.sb_off[i] + len(t.sb_dev)
-        self.sb_chord = np.concatenate([t.sb_chord for t in tables], axis=0)
-        self.sb_dev = np.concatenate([t.sb_dev for t in tables])
+            self.blk_off[i + 1] = self.blk_off[i] + even(len(t.blk_dev))
+            self.sb_off[i + 1] = self.sb_off[i] + even(len(t.sb_dev))
+
+        def padded(parts, width):
+            out = np.zeros((int(sum(even(len(p)) for p in parts)), width), dtype=np.float32)
+            o = 0
+            for p in parts:
+                out[o:o + len(p)] = p
+                o += even(len(p))
+            return out
+
+        self.sb_chord = padded([t.sb_chord for t in tables], 4)
+        self.sb_dev = padded([t.sb_dev for t in tables], 2)
+        self.blk_chord = padded([t.blk_chord for t in tables], 4)
+        self.blk_dev = padded([t.blk_dev for t in tables], 2)
         self.poly_xy = np.concatenate([t.poly for t in tables], axis=0)
         self.poly_cum = np.concatenate([t.cum for t in tables])
-        self.blk_chord = np.concatenate([t.blk_chord for t in tables], axis=0)
-        self.blk_dev = np.concatenate([t.blk_dev for t in tables])
         self.origin = np.stack([t.origin for t in tables])
         self.knots = np.stack([t.knots for t in tables])
         self.coef = np.stack([t.coef for t in tables])
@@ -159,6 +174,28 @@ class PathBank:
     def from_waypoints(cls, waypoint_list) -> "PathBank":
         return cls([build_path(w) for w in waypoint_list])
 
+    def header_array(self) -> np.ndarray:
+        """[n_paths] records with the layout of ``AuvPathHdr`` (64 B)."""
+        hdr = np.zeros(self.n_paths, dtype=HDR_DTYPE)
+        hdr["v0"] = self.poly_off[:-1]
+        hdr["nseg"] = np.diff(self.poly_off) - 1
+        hdr["b0"] = self.blk_off[:-1]
+        hdr["s0"] = self.sb_off[:-1]
+        hdr["ox"], hdr["oy"] = self.origin[:, 0], self.origin[:, 1]
+        hdr["length"] = self.length
+        hdr["end_x"], hdr["end_y"] = self.end_xy[:, 0], self.end_xy[:, 1]
+        return hdr
+
+    def piece_array(self) -> np.ndarray:
+        """[n_paths, n_knots - 1, 12]: knot j, knot j + 1, x c0..c3, y c0..c3, 2 unused (``AuvPathBank.pp``)."""
+        nk = self.knots.shape[1]
+        pp = np.zeros((self.n_paths, nk - 1, PP_W), dtype=np.float64)
+        pp[:, :, 0] = self.knots[:, :-1]
+        pp[:, :, 1] = self.knots[:, 1:]
+        pp[:, :, 2:6] = self.coef[:, :, 0, :]
+        pp[:, :, 6:10] = self.coef[:, :, 1, :]
+        return pp
+
     def device_arrays(self, device):
         import torch
 
@@ -166,20 +203,14 @@ class PathBank:
             return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device)
 
         return dict(
-            poly_off=dev(self.poly_off, torch.int32),
+            hdr=torch.from_numpy(self.header_array().view(np.uint8).copy()).to(device),
             poly_xy=dev(self.poly_xy, torch.float64),
             poly_cum=dev(self.poly_cum, torch.float64),
-            blk_off=dev(self.blk_off, torch.int32),
             blk_chord=dev(self.blk_chord, torch.float32),
             blk_dev=dev(self.blk_dev, torch.float32),
-            sb_off=dev(self.sb_off, torch.int32),
             sb_chord=dev(self.sb_chord, torch.float32),
             sb_dev=dev(self.sb_dev, torch.float32),
-            origin=dev(self.origin, torch.float64),
-            knots=dev(self.knots, torch.float64),
-            coef=dev(self.coef, torch.float64),
-            length=dev(self.length, torch.float64),
-            end_xy=dev(self.end_xy, torch.float64),
+            pp=dev(self.piece_array(), torch.float64),
         )
 
 

@@ -42,6 +42,10 @@ class ScenarioSet:
     post_generate_update: bool = False  # scenario's _generate() ends with self._update()
     name: str = ""
     world_polygons: List[np.ndarray] = field(default_factory=list)  # static land shared by all scenarios
+    # path-major layout: scenario m follows path ((m mod path_period) // path_group) mod n_paths, so that
+    # consecutive envs share a path (0 = no such structure; the GPU generator then draws paths at random)
+    path_group: int = 0
+    path_period: int = 0
     _bank: Optional[PathBank] = field(default=None, repr=False)
     _world: Optional[object] = field(default=None, repr=False)
 
@@ -88,6 +92,18 @@ class ScenarioSet:
         for h in steps:
             pos, disp, counter = advance_obstacles(self, pos, counter, h)
         return pos, disp, counter
+
+    def linear_track_info(self, dt: float):
+        """``dict(vel_len, counter0)`` when every used moving slot follows a constant-velocity track
+        (stride 0) of one common length -- the MovingObstacles family, movingobstacles.py:51-75 --
+        else None.  Such pools are stepped with the closed form of ``VesselObstacle._update``."""
+        if self.k_moving == 0:
+            return None
+        used = self.mov_width > 0
+        tr = self.mov_track[used] if used.any() else self.mov_track.reshape(-1, 4)
+        if len(tr) == 0 or np.any(tr[:, 2] != 0) or np.any(tr[:, 1] != tr[0, 1]) or tr[0, 1] < 2:
+            return None
+        return dict(vel_len=int(tr[0, 1]), counter0=0.1 + (float(dt) if self.post_generate_update else 0.0))
 
     def describe(self, i: int) -> dict:
         """Neutral single-scenario description (input of oracle.sim.OracleEnv)."""
@@ -183,11 +199,16 @@ def moving_obstacles(
     vessel_width: float = 1.255,
     path_length: float = 800.0,
     name: str = "MovingObstaclesNoRules-v0",
+    path_period: Optional[int] = None,
 ) -> ScenarioSet:
     """M scenarios distributed like ``MovingObstacles._generate``.  ``n_paths`` distinct
-    random curves are shared round-robin (None = one path per scenario)."""
+    random curves are shared by index, path-major (None = one path per scenario): scenario m
+    follows path ``((m mod path_period) // group) mod P`` with ``group = path_period // P`` and
+    ``path_period`` = M by default -- consecutive scenarios (hence consecutive envs, hence whole
+    CTAs of the step kernels) share a path."""
     M = int(n_scenarios)
     P = M if n_paths is None else int(min(n_paths, M))
+    period, group = _path_layout(M, P, path_period)
     rng = np.random.RandomState(seed)
     grng = np.random.RandomState(seed + 0x5EED)
     wps = []
@@ -195,7 +216,7 @@ def moving_obstacles(
         nwp = int(np.floor(4 * rng.rand() + 2))
         wps.append(random_curve_waypoints(rng, nwp, length=path_length))
     tables = [build_path(w) for w in wps]
-    path_id = (np.arange(M) % P).astype(np.int32)
+    path_id = _path_major_ids(M, P, period, group)
     vessel_init = np.zeros((M, 3))
     mov_start = np.zeros((M, n_moving, 2))
     mov_width = np.zeros((M, n_moving))
@@ -231,10 +252,20 @@ def moving_obstacles(
     scn = ScenarioSet(
         waypoints=wps, path_id=path_id, vessel_init=vessel_init, mov_start=mov_start, mov_width=mov_width,
         mov_track=mov_track, vel_table=vel_table, st_pos=st_pos, st_radius=st_radius, rewarder=rewarder,
-        post_generate_update=True, name=name,
+        post_generate_update=True, name=name, path_group=group, path_period=period,
     )
     scn._bank = PathBank(tables)
     return scn
+
+
+def _path_layout(M: int, P: int, path_period: Optional[int]):
+    period = int(path_period) if path_period else M
+    group = max(1, period // P)
+    return period, group
+
+
+def _path_major_ids(M: int, P: int, period: int, group: int) -> np.ndarray:
+    return (((np.arange(M) % period) // group) % P).astype(np.int32)
 
 
 def moving_obstacles_template(
@@ -246,6 +277,7 @@ def moving_obstacles_template(
     rewarder: str = "colav",
     path_length: float = 800.0,
     name: str = "MovingObstaclesNoRules-v0",
+    path_period: Optional[int] = None,
 ) -> ScenarioSet:
     """Path bank + EMPTY obstacle slots for M scenarios: the input of
     ``AUVVecEnv.regenerate_scenarios`` (GPU-side sampling of vessel starts and obstacles).  Only
@@ -257,7 +289,8 @@ def moving_obstacles_template(
         nwp = int(np.floor(4 * rng.rand() + 2))
         wps.append(random_curve_waypoints(rng, nwp, length=path_length))
     tables = [build_path(w) for w in wps]
-    path_id = (np.arange(M) % P).astype(np.int32)
+    period, group = _path_layout(M, P, path_period)
+    path_id = _path_major_ids(M, P, period, group)
     vessel_init = np.zeros((M, 3))
     for p in range(P):
         vessel_init[path_id == p, 0:2] = tables[p](0.0)
@@ -268,7 +301,7 @@ def moving_obstacles_template(
         waypoints=wps, path_id=path_id, vessel_init=vessel_init, mov_start=np.zeros((M, n_moving, 2)),
         mov_width=np.zeros((M, n_moving)), mov_track=mov_track, vel_table=np.zeros((M * n_moving, 2)),
         st_pos=np.zeros((M, n_static, 2)), st_radius=np.zeros((M, n_static)), rewarder=rewarder,
-        post_generate_update=True, name=name,
+        post_generate_update=True, name=name, path_group=group, path_period=period,
     )
     scn._bank = PathBank(tables)
     return scn

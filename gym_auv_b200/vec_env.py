@@ -48,7 +48,8 @@ def ray_table(n_sensors: int, n_sectors: int):
     return ang, cos_sin, weight.astype(np.float32), wsum, sector
 
 
-def make_auv_config(cfg: Config, rewarder: str, test_mode: bool, auto_reset: bool, cull_mode: str) -> _lib.AuvConfig:
+def make_auv_config(cfg: Config, rewarder: str, test_mode: bool, auto_reset: bool, cull_mode: str,
+                    velocity_mode: str = "zero") -> _lib.AuvConfig:
     v, e, s = cfg.vessel, cfg.episode, cfg.simulation
     if cfg.vessel.sensor_use_feasibility_pooling:
         raise NotImplementedError(
@@ -76,7 +77,7 @@ def make_auv_config(cfg: Config, rewarder: str, test_mode: bool, auto_reset: boo
         test_mode=int(bool(test_mode)),
         cull_mode=_lib.CULL_IDS[cull_mode],
         auto_reset=int(bool(auto_reset)),
-        reserved0=0,
+        velocity_mode=_lib.VELOCITY_IDS[velocity_mode],
     )
 
 
@@ -99,6 +100,14 @@ class AUVVecEnv:
                 ``chunk_streams`` internal streams (auv_step_chunked); results are identical
     host_chunks : ranges of step_host (auv_step_host_chunked): each range's observations start
                 their D2H copy while the next range is computed (default: ``chunks``)
+    velocity_mode : "zero" (default) = the LiDAR speed measurements are (0, 0) as in the reference's live
+                ``simulate_sensor`` (sensor.py:140-159); "nearest" = ``simulate_sensor_brute_force``
+                (sensor.py:100-137): per ray the displacement of the nearest hit obstacle rotated into the
+                ray frame -- it feeds ``max(0, v_y)`` of the Colav penalty (rewarder.py:199-206) and, with
+                ``sensor_use_velocity_observations``, the 2 R velocity channels of the observation
+    linear_tracks : "auto" (default) = pools whose moving obstacles all follow constant-velocity tracks
+                (the MovingObstacles family) are stepped with the closed form of the update and keep no
+                per-env obstacle state; False forces the general table-driven update
     """
 
     def __init__(
@@ -117,6 +126,8 @@ class AUVVecEnv:
         chunks: int = 1,
         chunk_streams: Optional[int] = None,
         host_chunks: Optional[int] = None,
+        velocity_mode: str = "zero",
+        linear_tracks="auto",
         _shared: Optional[dict] = None,
     ):
         self.device = torch.device(device)
@@ -131,7 +142,8 @@ class AUVVecEnv:
         self.test_mode = test_mode
         self.debug = debug
         self.env_offset = int(env_offset)
-        self.cfg = make_auv_config(self.config, scenarios.rewarder, test_mode, auto_reset, cull_mode)
+        self.cfg = make_auv_config(self.config, scenarios.rewarder, test_mode, auto_reset, cull_mode, velocity_mode)
+        self._velocity_mode = velocity_mode
         self.obs_dim = self.lib.auv_obs_dim(C.byref(self.cfg))
         self.n_sensors = R = int(self.config.vessel.n_sensors)
         dev = self.device
@@ -157,10 +169,9 @@ class AUVVecEnv:
         self._bank = _shared["bank"] if _shared is not None else bank.device_arrays(dev)
         b = self._bank
         self.paths = _lib.AuvPathBank(
-            bank.n_paths, bank.knots.shape[1], b["poly_off"].data_ptr(), b["poly_xy"].data_ptr(),
-            b["poly_cum"].data_ptr(), b["blk_off"].data_ptr(), b["blk_chord"].data_ptr(), b["blk_dev"].data_ptr(),
-            b["sb_off"].data_ptr(), b["sb_chord"].data_ptr(), b["sb_dev"].data_ptr(), b["origin"].data_ptr(), b["knots"].data_ptr(), b["coef"].data_ptr(), b["length"].data_ptr(),
-            b["end_xy"].data_ptr(),
+            bank.n_paths, bank.knots.shape[1], b["hdr"].data_ptr(), b["poly_xy"].data_ptr(), b["poly_cum"].data_ptr(),
+            b["blk_chord"].data_ptr(), b["blk_dev"].data_ptr(), b["sb_chord"].data_ptr(), b["sb_dev"].data_ptr(),
+            b["pp"].data_ptr(),
         )
 
         # ---- scenario pool
@@ -184,7 +195,20 @@ class AUVVecEnv:
             vel_table=t(vel, torch.float64),
             st_pos=t(scenarios.st_pos, torch.float64),
             st_radius=t(scenarios.st_radius, torch.float64),
+            st_rec=torch.zeros((M, max(Ks, 1), 4), dtype=torch.float64, device=dev),
         )
+        # closed-form obstacle update for pools of constant-velocity tracks (AuvScenarioPool.linear_tracks)
+        if _shared is not None:
+            self.linear = _shared["linear"]
+        else:
+            lin = scenarios.linear_track_info(float(self.config.simulation.t_step_size)) if linear_tracks else None
+            self.linear = None
+            if lin is not None and Km > 0:
+                first, period = C.c_int32(0), C.c_int32(0)
+                _lib.check(self.lib.auv_linear_wrap(float(self.config.simulation.t_step_size), lin["counter0"],
+                                                    lin["vel_len"], C.byref(first), C.byref(period)), "auv_linear_wrap")
+                self.linear = dict(first_wrap=int(first.value), wrap_period=int(period.value), **lin)
+                self._pool["mov_lin"] = torch.zeros((M, Km, 8), dtype=torch.float64, device=dev)
         world = scenarios.world
         self.n_world = Pw = world.n
         if Pw and _shared is None:
@@ -201,13 +225,20 @@ class AUVVecEnv:
             )
         p = self._pool
         wptr = lambda k: p[k].data_ptr() if k in p else None
+        lin = self.linear
         self.pool = _lib.AuvScenarioPool(
             M, Km, Ks, Pw, p["path_id"].data_ptr(), p["vessel_init"].data_ptr(), p["mov_start"].data_ptr(),
             p["mov_width"].data_ptr(), p["mov_track"].data_ptr(), p["mov_pos0"].data_ptr(), p["mov_disp0"].data_ptr(),
             p["mov_counter0"].data_ptr(), p["vel_table"].data_ptr(), p["st_pos"].data_ptr(), p["st_radius"].data_ptr(),
+            p["st_rec"].data_ptr(), wptr("mov_lin"), int(lin is not None), lin["first_wrap"] if lin else 0,
+            lin["wrap_period"] if lin else 0, 0,
             wptr("world_circle"), wptr("world_voff"), wptr("world_verts"),
             p["reset_obs"].data_ptr(), p["reset_max_progress"].data_ptr(), p["reset_mask"].data_ptr(),
         )
+        if _shared is None:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.auv_pool_pack(C.byref(self.cfg), C.byref(self.pool), None, M, self._stream()),
+                           "auv_pool_pack")
 
         # ---- mutable batch state
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
@@ -221,11 +252,17 @@ class AUVVecEnv:
             max_progress=z(N, torch.float64),
             cte_sum=z(N, torch.float64),
             nearby_mask=z((N, mw), torch.int32),
-            mov_pos=z((N, max(Km, 1), 2), torch.float64),
-            mov_disp=z((N, max(Km, 1), 2), torch.float64),
-            mov_counter=z((N, max(Km, 1)), torch.float64),
             nav=z((N, _lib.NAV_W), torch.float64),
+            obst_steps=z(N, torch.int32),
+            prev_seg=torch.full((N,), -1, dtype=torch.int32, device=dev),
+            env_pid=z(N, torch.int32),
         )
+        if self.linear is None:  # table-driven tracks keep per-env obstacle state
+            self._st.update(
+                mov_pos=z((N, max(Km, 1), 2), torch.float64),
+                mov_disp=z((N, max(Km, 1), 2), torch.float64),
+                mov_counter=z((N, max(Km, 1)), torch.float64),
+            )
         # scratch between the culling and the casting stage: one record slot per obstacle slot
         # can never overflow; worlds with many polygons cap it (overflow raises, never silent)
         slots = Km + Ks + Pw
@@ -236,13 +273,15 @@ class AUVVecEnv:
             rec_cnt=z(N, torch.int32), status=z(1, torch.int32),
         )
         s = self._st
+        sptr = lambda k: s[k].data_ptr() if k in s else None
         self.batch = _lib.AuvBatch(
             N, mw, self.env_offset, 0, s["scn_id"].data_ptr(), s["episode"].data_ptr(), s["state"].data_ptr(),
             s["step_counter"].data_ptr(), s["t_step"].data_ptr(), s["cum_reward"].data_ptr(),
             s["max_progress"].data_ptr(), s["cte_sum"].data_ptr(), s["nearby_mask"].data_ptr(),
-            s["mov_pos"].data_ptr(), s["mov_disp"].data_ptr(), s["mov_counter"].data_ptr(), s["nav"].data_ptr(),
+            sptr("mov_pos"), sptr("mov_disp"), sptr("mov_counter"), s["nav"].data_ptr(),
             self._scratch["rec"].data_ptr(), self._scratch["rec_cnt"].data_ptr(),
             self._scratch["status"].data_ptr(), self.rec_cap, 0,
+            s["obst_steps"].data_ptr(), s["prev_seg"].data_ptr(), s["env_pid"].data_ptr(),
         )
 
         # ---- outputs
@@ -302,7 +341,7 @@ class AUVVecEnv:
         finished env becomes a copy (pool.reset_obs / reset_max_progress / reset_mask).
         ``ids``: int tensor of pool scenarios to (re)compute, default all."""
         M = self.scenarios.n_scenarios
-        shared = dict(ray=self._ray, bank=self._bank, pool=self._pool)
+        shared = self._shared_tables()
         total = M if ids is None else int(ids.numel())
         if ids is not None and total <= 8192:
             # small refreshes (refresh_finished): one cached worker batch, padded with repeats
@@ -313,7 +352,8 @@ class AUVVecEnv:
                     self._workers = {}
                 w = self._workers[cap] = AUVVecEnv(
                     self.scenarios, cap, self.config, device=self.device, test_mode=self.test_mode, auto_reset=False,
-                    cull_mode=self._cull_mode, max_nearby=self._max_nearby, _shared=shared)
+                    cull_mode=self._cull_mode, max_nearby=self._max_nearby, velocity_mode=self._velocity_mode,
+                    _shared=shared)
             sel = ids.to(self.device, torch.int64)
             padded = torch.cat([sel, sel[:1].expand(cap - total)]) if total < cap else sel
             w._st["scn_id"].copy_(padded.to(torch.int32))
@@ -326,7 +366,7 @@ class AUVVecEnv:
             n = min(chunk, total - start)
             tmp = AUVVecEnv(self.scenarios, n, self.config, device=self.device, test_mode=self.test_mode,
                             auto_reset=False, cull_mode=self._cull_mode, env_offset=start,
-                            max_nearby=self._max_nearby, _shared=shared)
+                            max_nearby=self._max_nearby, velocity_mode=self._velocity_mode, _shared=shared)
             if ids is None:
                 sel = slice(start, start + n)
             else:
@@ -348,6 +388,7 @@ class AUVVecEnv:
             t_step_size=float(self.config.simulation.t_step_size), vessel_width=float(v.vessel_width),
             init_pos_jitter=50.0, mov_disp_std=500.0, mov_width_mean=10.0, mov_speed_lo=1.0, mov_speed_hi=3.0,
             st_disp_std=250.0, st_radius_mean=30.0,
+            path_group=int(self.scenarios.path_group), path_period=int(self.scenarios.path_period or self.scenarios.n_scenarios),
         )
 
     def regenerate_scenarios(self, ids: Optional[torch.Tensor] = None, seed: int = 0, epoch: int = 1):
@@ -409,6 +450,26 @@ class AUVVecEnv:
         )
 
     # ------------------------------------------------------------------ helpers
+    def _shared_tables(self):
+        return dict(ray=self._ray, bank=self._bank, pool=self._pool, linear=self.linear)
+
+    def obstacle_state(self):
+        """(position [N, Km, 2], last displacement [N, Km, 2], waypoint counter [N, Km]) of the moving
+        obstacles -- VesselObstacle.position / (dx, dy) / waypoint_counter (obstacles.py:195-215).  Pools
+        of constant-velocity tracks keep no per-env obstacle state: the values are evaluated on demand."""
+        if self.linear is None:
+            return self._st["mov_pos"], self._st["mov_disp"], self._st["mov_counter"]
+        N, Km = self.num_envs, max(self.k_moving, 1)
+        pos = torch.zeros((N, Km, 2), dtype=torch.float64, device=self.device)
+        disp = torch.zeros_like(pos)
+        cnt = torch.zeros((N, Km), dtype=torch.float64, device=self.device)
+        if self.k_moving:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.auv_obstacle_state(
+                    C.byref(self.cfg), C.byref(self.pool), C.byref(self.batch), C.c_void_p(pos.data_ptr()),
+                    C.c_void_p(disp.data_ptr()), C.c_void_p(cnt.data_ptr()), self._stream()), "auv_obstacle_state")
+        return pos, disp, cnt
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -421,6 +482,8 @@ class AUVVecEnv:
         st = int(self._scratch["status"].item())
         if st & _lib.STATUS_GEN_GAVE_UP:
             raise RuntimeError("scenario generator: an obstacle slot was still rejected after 100000 draws")
+        if st & _lib.STATUS_POLY_TOO_LARGE:
+            raise RuntimeError(f"a world polygon has more than {_lib.MAX_POLY_VERTS} vertices: split it")
         if st & _lib.STATUS_REC_OVERFLOW:
             raise RuntimeError(
                 f"more than max_nearby={self.rec_cap} obstacles were within sensor range of one env: "
@@ -508,6 +571,8 @@ class AUVVecEnv:
         if self._pipe is None:
             with torch.cuda.device(self.device):
                 self._pipe = self.lib.auv_pipeline_create(2)
+            if not self._pipe:
+                raise _lib.AuvLibraryError("auv_pipeline_create failed: " + self.lib.auv_last_error().decode())
             self.chunk_streams = 2
         if getattr(self, "_async_stream", None) is None:
             self._async_stream = torch.cuda.Stream(device=self.device)
@@ -545,11 +610,12 @@ class AUVVecEnv:
         n = self.num_envs // int(n_groups)
         if n <= 0:
             raise ValueError("more groups than envs")
-        shared = dict(ray=self._ray, bank=self._bank, pool=self._pool)
+        shared = self._shared_tables()
         kw.setdefault("host_chunks", max(1, self.host_chunks // int(n_groups)))
         return [AUVVecEnv(self.scenarios, n, self.config, device=self.device, test_mode=self.test_mode,
                           auto_reset=bool(self.cfg.auto_reset), cull_mode=self._cull_mode, env_offset=g * n,
-                          max_nearby=self._max_nearby, _shared=shared, **kw) for g in range(int(n_groups))]
+                          max_nearby=self._max_nearby, velocity_mode=self._velocity_mode, _shared=shared, **kw)
+                for g in range(int(n_groups))]
 
     def step_host_buffers(self):
         """Pinned host buffers of step_host / step_async (actions in; obs, reward, done out)."""
@@ -621,11 +687,12 @@ class AUVVecEnv:
         table = dict(
             t_step=self._st["t_step"], cumulative_reward=self._st["cum_reward"], episode=self._st["episode"],
             step_counter=self._st["step_counter"], max_progress=self._st["max_progress"], scn_id=self._st["scn_id"],
-            nearby_mask=self._st["nearby_mask"], mov_pos=self._st["mov_pos"], mov_counter=self._st["mov_counter"],
-            nav=self._st["nav"],
+            nearby_mask=self._st["nearby_mask"], nav=self._st["nav"], obst_steps=self._st["obst_steps"],
         )
         if name in table:
             return table[name]
+        if name in ("mov_pos", "mov_disp", "mov_counter"):
+            return dict(zip(("mov_pos", "mov_disp", "mov_counter"), self.obstacle_state()))[name]
         if name in self._out:
             return self._out[name]
         raise AttributeError(name)

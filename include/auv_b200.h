@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 16
+#define AUV_ABI_VERSION 17
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -53,6 +53,11 @@ extern "C" {
 
 #define AUV_CULL_REFERENCE 0 /* replicate sensor.py:93 seam arithmetic exactly (default) */
 #define AUV_CULL_EXACT 1     /* wrap both window ends: every obstacle in range is seen   */
+
+#define AUV_VELOCITY_ZERO 0    /* LiDAR speed measurements are (0, 0): simulate_sensor at HEAD, sensor.py:140-159 */
+#define AUV_VELOCITY_NEAREST 1 /* Rz(-angle - pi/2) (dx, dy) of the nearest obstacle a ray hits:
+                                  simulate_sensor_brute_force, sensor.py:100-137 (feeds max(0, v_y) in
+                                  rewarder.py:199-206 and the 2 R velocity channels of the observation) */
 
 #define AUV_MAX_RAYS 1024
 #define AUV_MAX_OBSTACLES 1024 /* moving + static slots per env */
@@ -65,6 +70,10 @@ extern "C" {
 #define AUV_MAX_POLY_VERTS 192 /* vertices of one world polygon incl. the closing one */
 #define AUV_STATUS_REC_OVERFLOW 1 /* AuvBatch.status bit: more nearby obstacles than rec_cap */
 #define AUV_STATUS_GEN_GAVE_UP 2  /* scenario generator: an obstacle was placed after 100000 rejections */
+#define AUV_STATUS_POLY_TOO_LARGE 4 /* a world polygon has more than AUV_MAX_POLY_VERTS vertices: it was skipped */
+#define AUV_PATH_STAGE_BLOCKS 512 /* paths with at most this many projection blocks (~1.6 km) are searched from a
+                                     shared-memory copy of their capsule tables (one bulk async copy per CTA) */
+#define AUV_PP_W 12           /* doubles per PCHIP piece record in AuvPathBank.pp */
 
 /* gym_auv/config.py field names (EpisodeConfig/SimulationConfig/VesselConfig).  POD. */
 typedef struct AuvConfig {
@@ -89,7 +98,7 @@ typedef struct AuvConfig {
   int32_t test_mode;            /* BaseEnvironment(test_mode=...)    environment.py:32  */
   int32_t cull_mode;            /* AUV_CULL_*                                           */
   int32_t auto_reset;           /* VecEnv semantics: reset done envs inside the step    */
-  int32_t reserved0;
+  int32_t velocity_mode;        /* AUV_VELOCITY_*                                       */
 } AuvConfig;
 
 /* Per-ray constants, built once on the host from the config (vessel.py:63-68,
@@ -105,29 +114,38 @@ typedef struct AuvRayTable {
 
 /* Path bank: every distinct path (objects/path.py:19-40) tabulated once; envs refer to a
  * path by id.  Polyline = the 0.1 m LineString of path.py:38-40 (FP64), its chord-length
- * prefix sums, and per 32-segment block (and per 32-block superblock) a chord + max
- * deviation used as an exact hierarchical search structure for LineString.project
- * (path.py:93).  PCHIP pieces are
- * scipy PPoly coefficients (path.py:26). */
+ * prefix sums, and per 32-segment block (and per AUV_PATH_SUPER-block superblock) a capsule
+ * (chord + max deviation) used as an exact hierarchical search structure for
+ * LineString.project (path.py:93).  PCHIP pieces are scipy PPoly coefficients (path.py:26).
+ * Tables are laid out so that every dependent look-up of the step is ONE line: a 64 B header
+ * per path, a 96 B record per PCHIP piece (its two knots and eight coefficients). */
+typedef struct AuvPathHdr {
+  int32_t v0;      /* first polyline vertex in poly_xy / poly_cum                          */
+  int32_t nseg;    /* polyline segments (vertices - 1); blocks = ceil(nseg / AUV_PATH_BLOCK),
+                      superblocks = ceil(blocks / AUV_PATH_SUPER)                           */
+  int32_t b0;      /* first block capsule (even, so the tables can be bulk-copied)          */
+  int32_t s0;      /* first superblock capsule (even)                                       */
+  double ox, oy;   /* origin the FP32 capsules are relative to                              */
+  double length;   /* Path.length                                                           */
+  double end_x, end_y; /* Path.end                                                          */
+  double reserved;
+} AuvPathHdr;
+
 typedef struct AuvPathBank {
   int32_t n_paths;
   int32_t n_knots;         /* 1000 */
-  const int32_t* poly_off; /* [n_paths+1] first polyline vertex of each path            */
+  const AuvPathHdr* hdr;   /* [n_paths]                                                   */
   const double* poly_xy;   /* [total_vertices][2]                                       */
   const double* poly_cum;  /* [total_vertices] chord-length prefix sum at each vertex   */
-  const int32_t* blk_off;  /* [n_paths+1] first block of each path                      */
   const float* blk_chord;  /* [total_blocks][4] ax, ay, ex, ey: first vertex and chord vector,
-                              relative to origin[path]                                  */
+                              relative to the path's origin                             */
   const float* blk_dev;    /* [total_blocks][2] 1/|e|^2 (0 if degenerate), max vertex
                               deviation from the chord + fp pad                         */
-  const int32_t* sb_off;   /* [n_paths+1] first superblock (32 blocks) of each path     */
   const float* sb_chord;   /* [total_superblocks][4] same layout as blk_chord            */
   const float* sb_dev;     /* [total_superblocks][2] same layout as blk_dev              */
-  const double* origin;    /* [n_paths][2]                                              */
-  const double* knots;     /* [n_paths][n_knots]                                        */
-  const double* coef;      /* [n_paths][n_knots-1][2][4]  (x: c0..c3, y: c0..c3)        */
-  const double* length;    /* [n_paths]   Path.length                                   */
-  const double* end_xy;    /* [n_paths][2] Path.end                                     */
+  const double* pp;        /* [n_paths][n_knots-1][AUV_PP_W]: knot j, knot j+1, x: c0..c3,
+                              y: c0..c3 (value = ((c0 t + c1) t + c2) t + c3, t = s - knot j),
+                              2 unused                                                   */
 } AuvPathBank;
 
 /* Scenario pool: the read-only part of what a scenario plug-in's _generate() produces
@@ -151,6 +169,21 @@ typedef struct AuvScenarioPool {
   const double* vel_table;     /* [n_vel][2] per-second velocities obstacles.py:160-172 */
   const double* st_pos;        /* [M][k_static][2]                                      */
   const double* st_radius;     /* [M][k_static]                                         */
+  /* Packed per-slot records the step kernels read (one line per look-up).  Filled from the
+   * arrays above by auv_pool_pack, or directly by auv_generate_moving_obstacles. */
+  const double* st_rec;        /* [M][k_static][4]  x, y, radius, 0                      */
+  const double* mov_lin;       /* [M][k_moving][8]  constant-velocity tracks: position right after
+                                  reset() (2), per-step displacement dt*v (2), width, track start (2), 0 */
+  /* linear_tracks = 1: every used moving slot follows a constant-velocity track of the same length
+   * and the same post-reset counter (the MovingObstacles family, movingobstacles.py:51-75).  The
+   * update of obstacles.py:195-215 then has a closed form in the number n of updates since reset:
+   *   n <  lin_first_wrap : pos = pos0 + n d
+   *   n >= lin_first_wrap : pos = start + ((n - lin_first_wrap) mod lin_wrap_period + 1) d
+   * and the step keeps no per-env obstacle state (AuvBatch.mov_* are unused, may be NULL). */
+  int32_t linear_tracks;
+  int32_t lin_first_wrap;      /* auv_linear_wrap()                                      */
+  int32_t lin_wrap_period;
+  int32_t reserved0;
   /* static land polygons shared by every scenario of the pool (obstacles.py:116-127):
    * filled, enclosing circle = cached enclosing_circle_of_shape (obstacles.py:235-262).
    * Slots K .. K+n_world-1 of the nearby list / windows output. */
@@ -183,20 +216,25 @@ typedef struct AuvBatch {
   double* mov_pos;        /* [N][k_moving][2]                                           */
   double* mov_disp;       /* [N][k_moving][2]                                           */
   double* mov_counter;    /* [N][k_moving]                                              */
-  double* nav;            /* [N][AUV_NAV_W] Vessel._last_navi_state_dict: s, chi, y_e, s_la,
-                             look_ahead_heading_error, heading_error, goal_distance, progress,
-                             cos psi, sin psi, reached_goal, cos(heading_error), [12] the part of
-                             the reward that does not depend on the LiDAR (rewarder.py:216-239
-                             without the closeness term / rewarder.py:118-140), [13..15] unused,
-                             [16..23] hand-over to the casting stage: x, y, psi, cumulative
-                             reward, cte sum, t_step, scenario id, record count (one coalesced
-                             load per env instead of eight scattered ones)                     */
+  double* nav;            /* [N][AUV_NAV_W] Vessel._last_navi_state_dict (vessel.py:518-539):
+                             [0] s, [1] chi, [2] y_e, [3] s_la, [4] look_ahead_heading_error,
+                             [5] heading_error, [6] goal_distance, [7] progress;
+                             [8..23] = the 128 B hand-over line the casting stage reads in one
+                             coalesced load: cos psi, sin psi, reached_goal, y_e, the part of the
+                             reward that does not depend on the LiDAR (rewarder.py:216-239 without
+                             the closeness term / rewarder.py:118-140), goal_distance, progress,
+                             (unused), x, y, psi, cumulative reward, cte sum, t_step, scenario id,
+                             record count                                                       */
   /* scratch between the culling stage and the ray-casting stage (opaque to the caller) */
   void* rec;              /* [N][rec_cap][AUV_REC_BYTES] obstacle records, 16-byte aligned       */
   int32_t* rec_cnt;       /* [N] records of each env                                            */
   int32_t* status;        /* [1] or NULL: AUV_STATUS_* bits raised by kernels                   */
   int32_t rec_cap;        /* records per env; >= k_moving+k_static+n_world can never overflow  */
   int32_t reserved1;
+  int32_t* obst_steps;    /* [N] obstacle updates since reset (environment.py:386-392 calls)    */
+  int32_t* prev_seg;      /* [N] polyline segment the last projection ended on, -1 = none:
+                             warm start of the next one (an upper bound only; the search stays exact) */
+  int32_t* env_pid;       /* [N] pool.path_id[scn_id[e]], cached by reset                       */
 } AuvBatch;
 
 /* Outputs of one step / observe (all optional except obs/reward/done). */
@@ -333,6 +371,12 @@ typedef struct AuvGenParams {
   double mov_speed_hi;          /* 3                                                         */
   double st_disp_std;           /* 250   movingobstacles.py:84                               */
   double st_radius_mean;        /* 30    helpers.py:11                                       */
+  /* path of scenario slot m: path_group = 0 -> uniform over the bank (a fresh random curve per
+   * episode, movingobstacles.py:28-31); > 0 -> ((m mod path_period) / path_group) mod n_paths, i.e.
+   * "paths shared by index" with consecutive slots on the same path (path-major pools: the step
+   * kernels then find whole CTAs on one path) */
+  int32_t path_group;
+  int32_t path_period;
 } AuvGenParams;
 /* Writes path_id, vessel_init, mov_start, mov_width, mov_track, vel_table (entry m*Km+j), the
  * post-reset obstacle state mov_pos0/disp0/counter0, st_pos and st_radius of the scenarios
@@ -342,6 +386,20 @@ typedef struct AuvGenParams {
  * status (device int or NULL) receives AUV_STATUS_GEN_GAVE_UP. */
 int auv_generate_moving_obstacles(const AuvGenParams* gp, const AuvPathBank* paths, const AuvScenarioPool* pool,
                                   const int32_t* ids, int n_ids, int32_t* status, void* stream);
+/* Host helper (no GPU work): first wrap and wrap period, in updates, of a constant-velocity
+ * VesselObstacle track (obstacles.py:195-215: counter += dt; floor(counter) >= vel_len - 1 wraps the
+ * counter to 0 and the position to the track start).  counter0 = waypoint counter right after
+ * reset().  The loop is run literally in FP64, so the integers are the reference's. */
+int auv_linear_wrap(double dt, double counter0, int vel_len, int32_t* first_wrap, int32_t* wrap_period);
+/* Fill pool.st_rec (and, with pool.linear_tracks, pool.mov_lin) from the unpacked pool arrays for
+ * the scenarios ids[0..n_ids) (device array; NULL = scenarios 0..n_ids-1). */
+int auv_pool_pack(const AuvConfig* cfg, const AuvScenarioPool* pool, const int32_t* ids, int n_ids, void* stream);
+/* Current moving-obstacle positions, last displacements and waypoint counters of every env
+ * ([N][k_moving][2], [N][k_moving][2], [N][k_moving]; any may be NULL) -- what
+ * VesselObstacle.position / .dx,.dy / .waypoint_counter hold (obstacles.py:195-215).  With
+ * pool.linear_tracks they are evaluated from the closed form, otherwise copied from AuvBatch. */
+int auv_obstacle_state(const AuvConfig* cfg, const AuvScenarioPool* pool, const AuvBatch* batch, double* pos,
+                       double* disp, double* counter, void* stream);
 /* Measured FP32 FMA peak helper (roofline denominator): runs `iters` dependent FMAs per
  * thread on a full grid; the caller times it with CUDA events. Returns flop count. */
 int auv_fma_probe(float* sink, int blocks, int threads, int iters, void* stream,

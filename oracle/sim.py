@@ -42,6 +42,9 @@ DEFAULT_CFG = dict(
     sensor_range=150.0,
     sensor_log_transform=True,
     sensor_use_velocity_observations=False,
+    # "zero": simulate_sensor at HEAD returns (0, 0) speeds (sensor.py:140-159);
+    # "nearest": simulate_sensor_brute_force (sensor.py:100-137)
+    velocity_mode="zero",
 )
 
 
@@ -219,10 +222,13 @@ def rays_for_obstacles(obstacles, p0, heading, angle_per_ray, n_rays):
     return per_ray, windows
 
 
-def cast_ray(angle, p0, sensor_range, obstacles):
-    """sensor.py:140-159: min distance to ray∩boundary over the candidate list."""
+def cast_ray(angle, p0, sensor_range, obstacles, with_obstacle=False):
+    """sensor.py:140-159: min distance to ray∩boundary over the candidate list.  With
+    ``with_obstacle`` also the obstacle of the nearest intersection, first one on ties
+    (``min((distance, i))`` of simulate_sensor_brute_force, sensor.py:113-117)."""
     p1 = (p0[0] + math.cos(angle) * sensor_range, p0[1] + math.sin(angle) * sensor_range)
     best = None
+    who = None
     for ob in obstacles:
         if ob.filled and G.point_in_ring(p0, ob.ring):
             d = 0.0
@@ -230,7 +236,17 @@ def cast_ray(angle, p0, sensor_range, obstacles):
             d = G.ray_ring_min_distance_np(p0, p1, ob.ring)
         if d is not None and (best is None or d < best):
             best = d
-    return sensor_range if best is None else best
+            who = ob
+    d = sensor_range if best is None else best
+    return (d, who) if with_obstacle else d
+
+
+def relative_speed(angle, ob):
+    """sensor.py:118-128: Rz(-sensor_angle - pi/2) applied to the obstacle's last displacement (dx, dy)."""
+    if ob is None or ob.static:
+        return 0.0, 0.0
+    a = -angle - math.pi / 2
+    return (math.cos(a) * ob.dx - math.sin(a) * ob.dy, math.sin(a) * ob.dx + math.cos(a) * ob.dy)
 
 
 # ---------------------------------------------------------------------------------
@@ -246,6 +262,7 @@ class OracleVessel:
         self.sensor_angles = np.array([-math.pi + (i + 1) * self.d_angle for i in range(self.n_sensors)])
         self.state = np.hstack([np.array(init_state, dtype=np.float64), np.zeros(3)])
         self.dists = np.ones(self.n_sensors) * cfg["sensor_range"]
+        self.speeds = np.zeros((2, self.n_sensors))
         self.collision = False
         self.progress = 0.0
         self.max_progress = 0.0
@@ -292,17 +309,23 @@ class OracleVessel:
             ]
         if not self.nearby:
             self.dists = np.ones(self.n_sensors) * rng
+            self.speeds = np.zeros((2, self.n_sensors))
             self.collision = False
             return np.zeros(self.n_sensors), np.zeros((2, self.n_sensors))
         angles = self.sensor_angles + self.heading
         per_ray, self.windows = rays_for_obstacles(self.nearby, p0, self.heading, self.d_angle, self.n_sensors)
         d = np.empty(self.n_sensors)
+        v = np.zeros((2, self.n_sensors))
+        nearest = self.cfg.get("velocity_mode", "zero") == "nearest"
         for i in range(self.n_sensors):
-            d[i] = cast_ray(angles[i], p0, rng, per_ray[i])
+            d[i], who = cast_ray(angles[i], p0, rng, per_ray[i], with_obstacle=True)
+            if nearest:
+                v[:, i] = relative_speed(angles[i], who)
             self.n_tests += sum(len(ob.ring) - 1 for ob in per_ray[i])
         self.dists = d
+        self.speeds = v
         self.collision = bool(np.any(d < width))
-        return self.closeness(d), np.zeros((2, self.n_sensors))
+        return self.closeness(d), v
 
     def navigate(self, path):
         cfg = self.cfg
@@ -348,7 +371,7 @@ def colav_reward(v: OracleVessel):
     rng = v.cfg["sensor_range"]
     for i in range(v.n_sensors):
         weight = 1 / (1 + abs(10.0 * v.sensor_angles[i]))
-        raw = rng * math.exp(-0.1 * v.dists[i] + 1.0 * max(0, 0.0))
+        raw = rng * math.exp(-0.1 * v.dists[i] + 1.0 * max(0, v.speeds[1, i]))
         num += weight * raw
         den += weight
     closeness_reward = -num / den if v.n_sensors > 0 else 0.0

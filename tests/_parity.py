@@ -32,14 +32,15 @@ def oracle_cfg(config, **extra):
     return d
 
 
-def rollout_oracle(scn, config, actions, test_mode=True):
+def rollout_oracle(scn, config, actions, test_mode=True, **cfg_extra):
     """actions: [T, M, 2].  Returns dict of arrays [T(+1), M, ...] (stops an env at done)."""
     from oracle.sim import OracleEnv
 
     T, M = actions.shape[0], scn.n_scenarios
     R = config.vessel.n_sensors if config.vessel.use_lidar else 0
+    D = 6 + R + (2 * R if (R and config.vessel.sensor_use_velocity_observations) else 0)
     out = dict(
-        obs0=[], obs=np.full((T, M, 6 + R), np.nan), reward=np.full((T, M), np.nan),
+        obs0=[], obs=np.full((T, M, D), np.nan), reward=np.full((T, M), np.nan),
         done=np.zeros((T, M), bool), collision=np.zeros((T, M), bool), reached=np.zeros((T, M), bool),
         state=np.full((T, M, 6), np.nan), dists=np.full((T, M, max(R, 1)), np.nan),
         progress=np.full((T, M), np.nan), goal_distance=np.full((T, M), np.nan),
@@ -52,7 +53,7 @@ def rollout_oracle(scn, config, actions, test_mode=True):
         for m in range(M)
     ]
     for m in range(M):
-        env = OracleEnv(scn.describe(m), oracle_cfg(config), test_mode=test_mode)
+        env = OracleEnv(scn.describe(m), oracle_cfg(config, **cfg_extra), test_mode=test_mode)
         out["obs0"].append(env.reset())
         for t in range(T):
             obs, rew, done, info = env.step(actions[t, m])
@@ -81,13 +82,13 @@ def rollout_oracle(scn, config, actions, test_mode=True):
     return out
 
 
-def rollout_gpu(scn, config, actions, test_mode=True, device="cuda:0", cull_mode="reference"):
+def rollout_gpu(scn, config, actions, test_mode=True, device="cuda:0", cull_mode="reference", **env_kw):
     import torch
     from gym_auv_b200.vec_env import AUVVecEnv
 
     T, M = actions.shape[0], scn.n_scenarios
     env = AUVVecEnv(scn, M, config, device=device, test_mode=test_mode, auto_reset=False, debug=True,
-                    cull_mode=cull_mode)
+                    cull_mode=cull_mode, **env_kw)
     obs0 = env.reset().cpu().numpy().copy()
     R = config.vessel.n_sensors if config.vessel.use_lidar else 0
     out = dict(obs0=obs0, obs=[], reward=[], done=[], collision=[], reached=[], state=[], dists=[], progress=[],
@@ -171,4 +172,112 @@ def compare(ref, gpu, config, label=""):
     oerr = np.abs(gpu["obs"] - ref["obs"])[alive]
     rep["obs_max_abs"] = float(oerr.max())
     assert oerr.max() <= max(OBS_ATOL, RANGE_RTOL), (label, "obs", oerr.max())
+    return rep
+
+
+# ---------------------------------------------------------------------------------------
+# Oracle replay of LIVE envs of a running batch (the regime bench.py measures)
+# ---------------------------------------------------------------------------------------
+def _oracle_from_live(scn_host, config, m, state, step_counter, max_progress, t_step, cum_reward, mask_words,
+                      mov_pos, mov_disp, mov_counter, **cfg_extra):
+    """OracleEnv of pool scenario m put into the given live state (vessel, counters, nearby list,
+    moving-obstacle positions / last displacement / waypoint counter)."""
+    import math
+
+    from oracle.sim import OracleEnv
+
+    o = OracleEnv(scn_host.describe(m), oracle_cfg(config, **cfg_extra), test_mode=False)
+    o.vessel.state = np.array(state, dtype=np.float64)
+    o.vessel.step_counter = int(step_counter)
+    o.vessel.max_progress = float(max_progress)
+    o.t_step = int(t_step)
+    o.cumulative_reward = float(cum_reward)
+    used_m = np.nonzero(scn_host.mov_width[m] > 0)[0]
+    used_s = np.nonzero(scn_host.st_radius[m] > 0)[0]
+    slots = list(used_m) + [scn_host.k_moving + j for j in used_s] + [
+        scn_host.k_moving + scn_host.k_static + k for k in range(len(scn_host.world_polygons))]
+    for ob, j in zip(o.obstacles, slots):
+        if not ob.static:
+            ob.position = np.array(mov_pos[j], dtype=np.float64)
+            ob.dx, ob.dy = float(mov_disp[j][0]), float(mov_disp[j][1])
+            ob.heading = math.atan2(ob.dy, ob.dx)
+            ob.counter = float(mov_counter[j])
+            ob._rebuild()
+    bits = np.asarray(mask_words).astype(np.uint32)
+    o.vessel.nearby = [ob for ob, j in zip(o.obstacles, slots) if (int(bits[j >> 5]) >> (j & 31)) & 1]
+    return o
+
+
+def live_sample_compare(env, config, acts, horizon, n_sample, start, prefer_records=False, **cfg_extra):
+    """env: a running AUVVecEnv(auto_reset=True, debug=True).  Steps it `horizon` more steps with
+    acts[(start + t) % len(acts)], then replays a sample of its envs through the oracle from their
+    full live state at the start of the window -- through auto-resets onto the next pool scenario --
+    and compares ranges, observations (terminal and first-of-next-episode), rewards and done flags."""
+    import torch
+
+    N, M = env.num_envs, env.scenarios.n_scenarios
+    width = config.vessel.vessel_width
+    R = config.vessel.n_sensors
+    scn_host = env.pull_scenarios()
+    snap = {k: v.clone().cpu().numpy() for k, v in env._st.items()}
+    pos, disp, cnt = [x.clone().cpu().numpy() for x in env.obstacle_state()]
+    rec_cnt = env._scratch["rec_cnt"].clone().cpu().numpy()
+    outs = []
+    for t in range(horizon):
+        obs, rew, done, info = env.step(acts[(start + t) % len(acts)])
+        outs.append(dict(obs=obs.clone(), reward=rew.clone(), done=done.clone(),
+                         dists=env.get_attr("lidar_dist").clone(), term=info["terminal_observation"].clone()))
+    env.check_status()
+    done_any = torch.stack([o["done"] for o in outs]).any(0).cpu().numpy().astype(bool)
+    rs = np.random.RandomState(0)
+    with_done = rs.permutation(np.nonzero(done_any)[0])[: max(2, n_sample // 5)]
+    with_rec = rs.permutation(np.nonzero((rec_cnt > 0) & ~done_any)[0])
+    with_rec = with_rec[: (n_sample - len(with_done)) if prefer_records else (n_sample - len(with_done)) // 2]
+    rest = rs.permutation(np.nonzero(~done_any)[0])[: max(0, n_sample - len(with_done) - len(with_rec))]
+    sample = np.unique(np.concatenate([with_done, with_rec, rest])).astype(int)
+    tid = torch.as_tensor(sample, device=env.device)
+    G = [dict(obs=o["obs"][tid].cpu().numpy(), reward=o["reward"][tid].cpu().numpy(),
+              done=o["done"][tid].cpu().numpy().astype(bool), dists=o["dists"][tid].cpu().numpy(),
+              term=o["term"][tid].cpu().numpy()) for o in outs]
+    A = [acts[(start + t) % len(acts)][tid].cpu().numpy().astype(np.float64) for t in range(horizon)]
+    rep = dict(envs=len(sample), resets=0, refreshes=0, with_records=0, env_steps=0, skipped_in_band=0,
+               range_max_abs=0.0, obs_max_abs=0.0, reward_max_abs=0.0)
+    interval = config.vessel.sensor_interval_load_obstacles
+    for k, e in enumerate(sample):
+        m = int(snap["scn_id"][e])
+        o = _oracle_from_live(scn_host, config, m, snap["state"][:, e], snap["step_counter"][e], snap["max_progress"][e],
+                              snap["t_step"][e], snap["cum_reward"][e], snap["nearby_mask"][e], pos[e], disp[e], cnt[e],
+                              **cfg_extra)
+        saw_records = False
+        for t in range(horizon):
+            ob, rew, done, info = o.step(A[t][k])
+            g = G[t]
+            margin = abs(float(o.vessel.dists.min()) - width) if config.vessel.use_lidar else np.inf
+            if margin <= COLLISION_BAND or abs(o.cumulative_reward - config.episode.min_cumulative_reward) < 0.05:
+                rep["skipped_in_band"] += 1  # FP32 casting may legitimately decide the other way: stop this env here
+                break
+            rep["env_steps"] += 1
+            rep["refreshes"] += int(o.vessel.step_counter % interval == 0)
+            saw_records = saw_records or bool(o.vessel.nearby)
+            assert bool(g["done"][k]) == bool(done), ("done", e, t)
+            g_obs = g["term"][k] if done else g["obs"][k]
+            derr = np.abs(g["dists"][k] - o.vessel.dists)
+            assert (derr <= RANGE_ATOL + RANGE_RTOL * o.vessel.dists).all(), ("ranges", e, t, derr.max())
+            oerr = np.abs(g_obs - ob).max()
+            assert oerr <= max(OBS_ATOL, RANGE_RTOL), ("obs", e, t, oerr)
+            rerr = abs(float(g["reward"][k]) - rew)
+            assert rerr <= REWARD_ATOL + REWARD_RTOL * abs(rew), ("reward", e, t, rerr)
+            rep["range_max_abs"] = max(rep["range_max_abs"], float(derr.max()))
+            rep["obs_max_abs"] = max(rep["obs_max_abs"], float(oerr))
+            rep["reward_max_abs"] = max(rep["reward_max_abs"], rerr)
+            if done:  # VecEnv auto-reset: the env moves on to pool scenario (m + N) mod M
+                from oracle.sim import OracleEnv
+
+                rep["resets"] += 1
+                m = (m + N) % M
+                o = OracleEnv(scn_host.describe(m), oracle_cfg(config, **cfg_extra), test_mode=False)
+                first = o.reset()  # (the constructor already reset once; the second reset is identical)
+                ferr = np.abs(g["obs"][k] - first).max()
+                assert ferr <= max(OBS_ATOL, RANGE_RTOL), ("first obs of the next episode", e, t, ferr)
+        rep["with_records"] += int(saw_records)
     return rep

@@ -467,8 +467,9 @@ def test_chunked_step_is_bit_identical(chunks, streams):
             assert torch.equal(i1[k], i2[k]), k
         assert np.array_equal(o1.cpu().numpy(), o3) and np.array_equal(r1.cpu().numpy(), r3)
         assert np.array_equal(d1.cpu().numpy(), d3)
-    for k in ("state", "mov_pos", "scn_id", "t_step", "cum_reward", "nearby_mask"):
+    for k in ("state", "scn_id", "t_step", "cum_reward", "nearby_mask", "obst_steps", "prev_seg", "env_pid"):
         assert torch.equal(e1._st[k], e2._st[k]) and torch.equal(e1._st[k], e3._st[k]), k
+    assert torch.equal(e1.get_attr("mov_pos"), e2.get_attr("mov_pos")) and torch.equal(e1.get_attr("mov_pos"), e3.get_attr("mov_pos"))
     assert e3.lib.auv_pipeline_graph_state(e3._pipe) == 1, "host-buffer step should replay a CUDA graph"
     s1, s2 = e1.episode_stats(reduce=False), e2.episode_stats(reduce=False)
     assert s1["episodes"] == s2["episodes"] > 0
@@ -828,7 +829,7 @@ def test_moving_obstacle_tracks_match_reference_vessel_obstacle_on_gpu(k):
         fused.step(a)
         for env in (staged, fused):
             pos = env.get_attr("mov_pos")[0, 0].cpu().numpy()
-            disp = env._st["mov_disp"][0, 0].cpu().numpy()
+            disp = env.get_attr("mov_disp")[0, 0].cpu().numpy()
             assert np.abs(pos - STUBBED["trk_pos"][k, t + 1]).max() <= 1e-9, t
             assert abs(math.atan2(disp[1], disp[0]) - STUBBED["trk_head"][k, t + 1]) <= 1e-12
             assert abs(float(env.get_attr("mov_counter")[0, 0]) - STUBBED["trk_counter"][k, t + 1]) <= 1e-12
