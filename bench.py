@@ -46,7 +46,7 @@ def n_ranges(n, chunks):
     """env ranges auv_step_chunked cuts n envs into (range size = ceil(n/chunks) rounded up to 64)."""
     if chunks <= 1:
         return 1
-    cs = -(-(-(-n // chunks)) // 64) * 64
+    cs = -(-(-(-n // chunks)) // 128) * 128
     return -(-n // cs)
 
 
@@ -77,12 +77,15 @@ def parse():
     ap.add_argument("--chunk-streams", type=int, default=None)
     ap.add_argument("--host-chunks", type=int, default=4,
                     help="env ranges of the host-buffer step (auv_step_host_chunked): D2H of a range overlaps the next")
-    ap.add_argument("--gpu-scenarios", action="store_true",
-                    help="sample vessel starts and obstacles on the GPU (auv_generate_moving_obstacles) instead of "
-                         "the host generator; same distributions, seconds instead of ~16 s of set-up")
-    ap.add_argument("--preroll-steps", type=int, default=0,
-                    help="untimed steps of the side pre-roll (0 = run for ~0.4 s); a fixed count makes profiler "
-                         "captures of the steady state addressable by launch index")
+    ap.add_argument("--gpu-scenarios", action="store_true", help="(default; kept for old command lines)")
+    ap.add_argument("--host-scenarios", action="store_true",
+                    help="sample vessel starts and obstacles with the host generator once (pool of N scenarios, replayed "
+                         "on reset) instead of the default: GPU generator, pool of 2N, a fresh scenario per episode")
+    ap.add_argument("--refresh-every", type=int, default=8,
+                    help="steps between auv_refresh_finished calls (fresh scenarios for the envs that finished)")
+    ap.add_argument("--preroll-steps", type=int, default=2000,
+                    help="untimed steps before the timed region (steady state: vessels spread along their paths, "
+                         "episodes desynchronised); also gives the clock sampler its samples under load")
     ap.add_argument("--scenario-cache", default=None,
                     help="pickle the generated scenario set here / reuse it (tuning sweeps; same seeds => same set)")
     return ap.parse_args()
@@ -148,7 +151,8 @@ def build_workload(args, rank):
 
     cache = getattr(args, "scenario_cache", None)
     if cache:
-        cache = f"{cache}.{args.workload}.{args.envs}.{args.rays}.{args.n_moving}.{args.n_static}.{args.n_paths}.{args.seed}.{rank}"
+        cache = (f"{cache}.{args.workload}.{args.envs}.{args.rays}.{args.n_moving}.{args.n_static}.{args.n_paths}."
+                 f"{args.seed}.{rank}.{int(bool(getattr(args, 'host_scenarios', False)))}")
         if os.path.exists(cache):
             with open(cache, "rb") as f:
                 return pickle.load(f)
@@ -175,9 +179,10 @@ def _build_workload(args, rank):
     if getattr(args, "workload", "moving") == "land":
         scn = S.land_scenarios(args.envs, n_polygons=args.n_polygons, n_moving=args.n_moving, n_static=args.n_static,
                                seed=args.seed + 1000 * rank, n_paths=args.n_paths)
-    elif getattr(args, "gpu_scenarios", False):
-        scn = S.moving_obstacles_template(args.envs, args.n_moving, args.n_static, seed=args.seed + 1000 * rank,
-                                          n_paths=args.n_paths)
+    elif not getattr(args, "host_scenarios", False):
+        # pool of 2N slots, path-major within N: env e alternates between slots e and e + N
+        scn = S.moving_obstacles_template(2 * args.envs, args.n_moving, args.n_static, seed=args.seed + 1000 * rank,
+                                          n_paths=args.n_paths, path_period=args.envs)
     else:
         scn = S.moving_obstacles(args.envs, args.n_moving, args.n_static, seed=args.seed + 1000 * rank,
                                  n_paths=args.n_paths)
@@ -238,6 +243,7 @@ def run_reference(args):
     small = argparse.Namespace(**vars(args))
     small.envs = max(cores * 2, 16)
     small.n_paths = min(args.n_paths, small.envs)
+    small.host_scenarios = True
     cfg, scn = build_workload(small, 0)
     per_step_envs = small.envs
     val, total, tmax = cpu_baseline(args, cfg, scn, per_step_envs, args.steps, args.warmup, cores)
@@ -259,6 +265,8 @@ def run_reference(args):
 # GPU arm
 # --------------------------------------------------------------------------------------
 def run_ours(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
     from gym_auv_b200 import _lib
@@ -278,19 +286,24 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
 
+    t_setup = time.perf_counter()
     cfg, scn = build_workload(args, rank)
     N, K, Wm = args.envs, args.steps, max(args.warmup, 3)
     R = cfg.vessel.n_sensors
+    fresh = args.workload == "moving" and not args.host_scenarios  # a fresh GPU-generated scenario per episode
     env = AUVVecEnv(scn, N, cfg, device=device, test_mode=False, auto_reset=True, env_offset=0,
                     chunks=args.chunks, chunk_streams=args.chunk_streams, host_chunks=args.host_chunks)
-    scenario_gen = None
-    if args.gpu_scenarios and args.workload == "moving":
+    seed = args.seed + 1000 * rank
+    scenario_gen = {"where": "host", "scenarios": scn.n_scenarios}
+    if fresh:
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        env.regenerate_scenarios(seed=args.seed + 1000 * rank, epoch=1)
+        env.regenerate_scenarios(seed=seed, epoch=1)
         g1.record()
         torch.cuda.synchronize()
-        scenario_gen = {"where": "gpu", "scenarios": scn.n_scenarios, "ms_incl_reset_cache": g0.elapsed_time(g1)}
+        scenario_gen = {"where": "gpu", "scenarios": scn.n_scenarios, "ms_incl_reset_cache": g0.elapsed_time(g1),
+                        "per_episode": "every finished env gets a freshly generated scenario "
+                                       "(auv_refresh_finished every %d steps, inside the timed region)" % args.refresh_every}
     gen = torch.Generator(device=device)
     gen.manual_seed(1234 + rank)
     lo = torch.tensor([-1.0, -0.15], device=device)
@@ -298,138 +311,100 @@ def run_ours(args):
     n_act = 16
     actions = [lo + (hi - lo) * torch.rand((N, 2), device=device, generator=gen) for _ in range(n_act)]
     env.reset()
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up: W steps after reset(); the timed region starts from THIS state (the same
-    #      episode phase the reference arm measures).
+    step_no = [0]
+
+    def run_steps(k):
+        """k steps through the public API (AUVVecEnv.step), scenario refresh included"""
+        for _ in range(k):
+            i = step_no[0]
+            env.step(actions[i % n_act])
+            if fresh and i % args.refresh_every == args.refresh_every - 1:
+                env.refresh_finished_device(seed=seed)
+            step_no[0] = i + 1
+
+    stream = torch.cuda.current_stream(device)
+
+    def timed(k):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record(stream)
+        run_steps(k)
+        b.record(stream)
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up, then the phase right after reset() as a side note (every vessel still at its path
+    #      start, nearby lists refreshed in lock-step: the favourable phase)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for i in range(Wm):
-        env.step(actions[i % n_act])
+    run_steps(Wm)
+    after_reset_ms = timed(K) / K
+    # ---- pre-roll into the steady state: vessels spread along their paths, episodes desynchronised,
+    #      auto-reset and scenario refresh running.  The clock sampler (nvidia-smi every 100 ms) gets its
+    #      samples under exactly this load.
+    run_steps(max(0, args.preroll_steps - step_no[0]))
     barrier()
-    # snapshot so that the pre-roll below can be undone and the counting pass can replay the K steps
-    snap = {k: v.clone() for k, v in env._st.items()}
-    # ---- pre-roll: ~0.4 s of the same steps.  (1) the clock sampler (nvidia-smi every 100 ms)
-    #      gets several samples under exactly this load -- K steps of 0.2 ms are over before a second
-    #      sample would arrive; (2) its last block measures the steady state thousands of steps into
-    #      the run, when vessels have left their start areas and more obstacles are in range.
-    t_pre = time.perf_counter()
-    i, blk = Wm, 50
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    while True:
-        last = (i - Wm + blk >= args.preroll_steps) if args.preroll_steps > 0 else (time.perf_counter() - t_pre >= 0.4)
-        s0.record()
-        for _ in range(blk):
-            env.step(actions[i % n_act])
-            i += 1
-        s1.record()
-        torch.cuda.synchronize()
-        if last:
-            break
-    steady_ms = s0.elapsed_time(s1) / blk
-    steady_records = float(env._scratch["rec_cnt"].sum().item()) / N
-    import ctypes as C
-
-    cfgp, rays, paths, pool, batch = env._refs()
-    tm = env.lib.auv_timer_create(20)
-    sps = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-    for j in range(20):  # per-kernel split of the steady state (single stream)
-        a = actions[(i + j) % n_act]
-        _lib.check(env.lib.auv_step_timed(cfgp, rays, paths, pool, batch, C.c_void_p(a.data_ptr()), C.byref(env.out),
-                                          sps, tm, j), "auv_step_timed")
-    torch.cuda.synchronize()
-    sk = np.zeros((20, 3), dtype=np.float32)
-    for j in range(20):
-        _lib.check(env.lib.auv_timer_read(tm, j, sk[j].ctypes.data_as(C.POINTER(C.c_float))), "auv_timer_read")
-    env.lib.auv_timer_destroy(tm)
-    cross_track = float(env._st["nav"][:, 2].abs().mean().item())
-    t_s = torch.tensor([steady_ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
-    steady = {"value": world * N / (float(t_s.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t_s.item()),
-              "steps_since_reset": i, "records_per_env_step": steady_records,
-              "kernel_ms": {"k_vessel_nav": float(sk[:, 1].mean()), "k_lidar": float(sk[:, 2].mean())},
-              "mean_abs_cross_track_m": cross_track,
-              "note": "same kernels, measured over the last %d of %d untimed steps (auto-reset running)" % (blk, i)}
-    for k, v in snap.items():
-        env._st[k].copy_(v)
-    barrier()
-    stream = torch.cuda.current_stream(device)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    cfgp, rays, paths, pool, batch = env._refs()
-    import ctypes as C
-    sp = C.c_void_p(stream.cuda_stream)
-
-    def product_step(a):
-        if env._pipe and env.chunks > 1:
-            _lib.check(env.lib.auv_step_chunked(cfgp, rays, paths, pool, batch, C.c_void_p(a.data_ptr()),
-                                                C.byref(env.out), sp, env._pipe, env.chunks), "auv_step_chunked")
-        else:
-            _lib.check(env.lib.auv_step(cfgp, rays, paths, pool, batch, C.c_void_p(a.data_ptr()), C.byref(env.out), sp),
-                       "auv_step")
-
-    # ---- timed region: K product steps (the chunked step forks from / joins into `stream`, so
-    #      the two events on `stream` bracket all of its work)
-    barrier()
-    ev0.record(stream)
-    for i in range(K):
-        product_step(actions[(Wm + i) % n_act])
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    t_local = torch.tensor([ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
-    ms_max = float(t_local.item())
+    env._out["stats"].zero_()
+    env.total_steps = 0
+    # ---- timed region: K steps of the steady state through AUVVecEnv.step
+    ms_max = timed(K)
     value = world * N * K / (ms_max * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+    stats_timed = env.episode_stats(reduce=True)  # the only collective on the path (NCCL all-reduce)
+    dones_per_step = stats_timed["episodes"] / max(K, 1) / world
+    steady_records = float(env._scratch["rec_cnt"].sum().item()) / N
+    cross_track = float(env._st["nav"][:, 2].abs().mean().item())
 
-    # ---- per-kernel attribution: replay the same K steps on ONE stream with CUDA events around
-    #      each kernel (auv_step_timed); these are the launch durations the roofline uses
-    for k, v in snap.items():
-        env._st[k].copy_(v)
+    # ---- per-kernel attribution: K more steps of the same steady state on ONE stream with CUDA events
+    #      around each kernel (auv_step_timed); these are the launch durations the roofline uses
+    cfgp, rays, paths, pool, batch = env._refs()
+    sp = C.c_void_p(stream.cuda_stream)
     timer = env.lib.auv_timer_create(K)
     assert timer, "auv_timer_create failed"
     torch.cuda.synchronize()
     es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     es0.record(stream)
     for i in range(K):
-        a = actions[(Wm + i) % n_act]
+        a = actions[(step_no[0] + i) % n_act]
         _lib.check(env.lib.auv_step_timed(cfgp, rays, paths, pool, batch, C.c_void_p(a.data_ptr()), C.byref(env.out),
                                           sp, timer, i), "auv_step_timed")
     es1.record(stream)
     torch.cuda.synchronize()
+    step_no[0] += K
     serial_ms_per_step = es0.elapsed_time(es1) / K
     kms = np.zeros((K, 3), dtype=np.float32)
     for i in range(K):
         _lib.check(env.lib.auv_timer_read(timer, i, kms[i].ctypes.data_as(C.POINTER(C.c_float))), "auv_timer_read")
     env.lib.auv_timer_destroy(timer)
-    kernel_ms = {"k_obstacle_update": float(kms[:, 0].mean()), "k_vessel_nav": float(kms[:, 1].mean()),
-                 "k_lidar": float(kms[:, 2].mean())}
-    obs_ms = kernel_ms["k_lidar"]
+    kernel_ms = {"k_vessel_nav": float(kms[:, 1].mean()), "k_lidar": float(kms[:, 2].mean())}
     kernel_ms["k_lidar_min_med_max"] = [float(kms[:, 2].min()), float(np.median(kms[:, 2])), float(kms[:, 2].max())]
     kernel_ms["k_vessel_nav_min_med_max"] = [float(kms[:, 1].min()), float(np.median(kms[:, 1])), float(kms[:, 1].max())]
     kernel_ms["single_stream_ms_per_step"] = serial_ms_per_step
 
-    # ---- counting pass (untimed): replay the same K steps with the seg-test counter on
-    for k, v in snap.items():
-        env._st[k].copy_(v)
+    # ---- counting pass (untimed): K more steps with the seg-test counter on
     seg = torch.zeros(1, dtype=torch.int64, device=device)
     env.out.seg_tests = seg.data_ptr()
     recs = torch.zeros(1, dtype=torch.int64, device=device)
     for i in range(K):
-        env.step(actions[(Wm + i) % n_act])
+        env.step(actions[(step_no[0] + i) % n_act])
         recs += env._scratch["rec_cnt"].sum()
     torch.cuda.synchronize()
+    step_no[0] += K
     env.out.seg_tests = None
     seg_tests_per_step = float(seg.item()) / K
     records_per_step = float(recs.item()) / K  # obstacle records k_vessel_nav hands to k_lidar
-    dones_per_step = float(env._out["stats"][0].item()) / max(env.total_steps, 1)
 
     # ---- FP32 FMA peak probe (roofline denominator for the LiDAR kernel), measured live
     sink = torch.zeros(1, device=device)
@@ -492,6 +467,13 @@ def run_ours(args):
         for g in groups:
             g.reset()
         ah = [[a[:half].copy() for a in acts_np], [a[half:2 * half].copy() for a in acts_np]]
+
+        def refresh_groups(i):
+            if fresh and i % args.refresh_every == args.refresh_every - 1:
+                for g in groups:  # ordered after the group's step on its own stream
+                    with torch.cuda.stream(g._async_stream):
+                        g.refresh_finished_device(seed=seed + 17)
+
         for g, a in zip(groups, ah):
             g.step_async(a[0])
         for i in range(3):  # warm-up (graph capture happens here)
@@ -508,6 +490,7 @@ def run_ours(args):
             for g, a in zip(groups, ah):
                 g.step_wait()
                 g.step_async(a[(i + 1) % 4])
+            refresh_groups(i)
         for g in groups:
             g.step_wait()
         dt = time.perf_counter() - t0
@@ -521,18 +504,18 @@ def run_ours(args):
                     "mode": "AUVVecEnv.step_async / step_wait, two groups of N/2 envs stepped alternately",
                     "host_chunks": groups[0].host_chunks, "sync": sync_part})
         e2e["pcie"]["frac_of_link_bound"] = e2e["pcie"]["d2h_only_ms_per_step"] / a_ms
+        torch.cuda.synchronize()
         for g in groups:
             g.close()
         del groups
-
-    stats = env.episode_stats(reduce=True)  # the only collective on the path (NCCL all-reduce)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    print(f"[bench] value={value:.4g} ms/step={ms_max / K:.4f} kernel_ms={kernel_ms} e2e={e2e}", file=sys.stderr)
+    print(f"[bench] value={value:.4g} ms/step={ms_max / K:.4f} after_reset_ms={after_reset_ms:.4f} kernel_ms={kernel_ms} "
+          f"setup_s={setup_s:.1f} e2e={e2e}", file=sys.stderr)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -540,18 +523,22 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     flops_per_launch = FLOP_PER_SEG_TEST * seg_tests_per_step + FLOP_PER_RAY * (R if cfg.vessel.use_lidar else 0) * N
-    achieved_tflops = flops_per_launch / (obs_ms * 1e-3) / 1e12
-    # Algorithmic bytes per launch of the two step kernels.
-    #   k_lidar per env: reads the navigation record 192 and its obstacle records (80 B each),
-    #     writes the closeness part of obs 4*(obs_dim-6), reward/done/info 15, counters 20.
-    #   k_vessel_nav per env (SURVEY 8d accounting, FP64 state): reads state 48 + action 8 +
-    #     counters 40 + path tables ~192 + moving Km x (40 state + 40 pool) + static Ks x 24, writes
-    #     state 48 + counters 8 + moving Km x 40 + navigation record 192 + obs[0..5] 24 + its
-    #     obstacle records (80 B each).
+    lidar_tflops = flops_per_launch / (kernel_ms["k_lidar"] * 1e-3) / 1e12
+    # Algorithmic bytes per launch of the two step kernels, steady state.
+    #   k_vessel_nav per env: reads state 48 + action 8 + counters / ids 44 + the path's header line 64 +
+    #     2 PCHIP piece records 2 x 96 + the winning polyline segment 48 + its obstacle records' sources
+    #     (64 B per nearby moving slot, 32 B per nearby static slot; all slots once per 25 steps), writes
+    #     state 48 + counters 16 + navigation record 192 + obs[0..5] 24 + its obstacle records (80 B each).
+    #   k_lidar per env: reads the hand-over line 128 and its obstacle records (80 B each), writes the
+    #     closeness part of obs 4*(obs_dim-6), reward/done/info 15, counters 20.
     Km, Ks = env.k_moving, env.k_static
+    rec_per_env = records_per_step / N
+    slot_bytes = (Km * 64 + Ks * 32) / max(cfg.vessel.sensor_interval_load_obstacles, 1) + rec_per_env * 48
+    if env.linear is None:
+        slot_bytes += Km * (80 + 40)  # table-driven tracks: per-env obstacle state read + written every step
     kbytes = {
-        "k_lidar": N * (192 + 4 * (env.obs_dim - 6) + 15 + 20) + 80.0 * records_per_step,
-        "k_vessel_nav": N * (48 + 8 + 40 + 192 + Km * 80 + Ks * 24 + 48 + 8 + Km * 40 + 192 + 24) + 80.0 * records_per_step,
+        "k_vessel_nav": N * (48 + 8 + 44 + 64 + 192 + 48 + slot_bytes + 48 + 16 + 192 + 24) + 80.0 * records_per_step,
+        "k_lidar": N * (128 + 4 * (env.obs_dim - 6) + 15 + 20) + 80.0 * records_per_step,
     }
     traffic = {}
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/)
@@ -563,11 +550,35 @@ def run_ours(args):
     kernels = {}
     for k, nbytes in kbytes.items():
         gbs = nbytes / (kernel_ms[k] * 1e-3) / 1e9
-        kernels[k] = {"ms_per_launch": kernel_ms[k], "algo_bytes_per_launch": nbytes, "achieved": gbs,
-                      "frac": gbs / hbm_peak, "traffic": traffic.get(k)}
-    dominant = max(kernels, key=lambda k: kernels[k]["ms_per_launch"])
-    achieved_gbs = kernels[dominant]["achieved"]
+        kernels[k] = {"ms_per_launch": kernel_ms[k], "algo_bytes_per_launch": nbytes, "hbm_gbs": gbs,
+                      "hbm_frac": gbs / hbm_peak, "traffic": traffic.get(k)}
+    kernels["k_lidar"].update({"fp32_tflops": lidar_tflops, "fp32_peak_tflops": fp32_peak_tflops,
+                               "fp32_frac": lidar_tflops / fp32_peak_tflops if fp32_peak_tflops else None,
+                               "seg_tests_per_env_step": seg_tests_per_step / N})
+    dominant = max(("k_vessel_nav", "k_lidar"), key=lambda k: kernels[k]["ms_per_launch"])
     step_gbs = ALGO_BYTES_PER_ENV_STEP * N / (ms_max / K * 1e-3) / 1e9
+    if dominant == "k_vessel_nav":
+        roof = {"kernel": dominant, "bound": "hbm", "achieved": kernels[dominant]["hbm_gbs"], "peak": hbm_peak,
+                "unit": "GB/s", "frac": kernels[dominant]["hbm_frac"], "traffic": kernels[dominant]["traffic"],
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
+    else:  # lidar_cast is bound by the FP32 pipe / instruction issue, not by tensor cores or HBM
+        roof = {"kernel": dominant, "bound": "fp32", "achieved": lidar_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                "frac": kernels[dominant]["fp32_frac"], "traffic": kernels[dominant]["traffic"],
+                "peak_source": "FP32 FMA probe measured in this run (no FP32 peak in MEASURED_PEAKS.json)"}
+    roof.update({
+        "ms_per_launch": kernels[dominant]["ms_per_launch"],
+        "algo_bytes_per_launch": kernels[dominant]["algo_bytes_per_launch"],
+        "records_per_env_step": rec_per_env,
+        "kernels": kernels,
+        "kernel_ms": kernel_ms,
+        "note": "dominant kernel of the STEADY STATE (CUDA-event launch durations of a single-stream run of K steps, "
+                "auv_step_timed).  k_vessel_nav: algorithmic bytes against the measured HBM peak; k_lidar: SURVEY 8(d) "
+                "FLOPs (16 x reference-semantics ray/segment tests + 60 x rays) against an FP32 FMA probe; ncu pipe / "
+                "issue numbers of both: profiles/.",
+        "step_hbm_view": {"achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
+                          "algo_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                          "note": "whole step (both kernels), SURVEY 8(d) bytes per env-step / timed-region time per step"},
+    })
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -576,46 +587,28 @@ def run_ours(args):
                    f"{args.workload}: {N} envs/GPU x {R if cfg.vessel.use_lidar else 0} rays x {args.n_moving}+{args.n_static} obstacles"
                    + (f" + {args.n_polygons} shared land polygons" if args.workload == "land" else ""),
                    "envs_per_gpu": N, "rays": R, "obstacles": args.n_moving + args.n_static,
-                   "paths": args.n_paths, "l2": "per-step working set (state+obstacles ~%.0f MB, path bank ~%.0f MB) exceeds the 126 MB L2; no explicit flush"
-                   % (N * ALGO_BYTES_PER_ENV_STEP / 2e6, scn.bank.poly_xy.nbytes * 1.5 / 1e6 + scn.bank.coef.nbytes / 1e6),
-                   "auto_reset": True, "dones_per_step": dones_per_step,
+                   "paths": args.n_paths, "l2": "per-step working set (state + records + observations ~%.0f MB, path bank ~%.0f MB) exceeds the 126 MB L2; no explicit flush"
+                   % (N * ALGO_BYTES_PER_ENV_STEP / 1e6, (scn.bank.poly_xy.nbytes * 1.5 + scn.bank.coef.nbytes * 1.5) / 1e6),
+                   "phase": "steady state: %d steps after reset(), auto-reset running, timed through AUVVecEnv.step" % (step_no[0] - 3 * K),
+                   "auto_reset": True, "dones_per_step": dones_per_step, "records_per_env_step": steady_records,
+                   "mean_abs_cross_track_m": cross_track,
                    "chunks": env.chunks, "chunk_streams": getattr(env, "chunk_streams", 1),
-                   "scenario_generation": scenario_gen or {"where": "host"},
+                   "scenario_generation": scenario_gen, "setup_s": setup_s,
                    "host_cores_bound": len(numa_cores)},
         "clocks": clocks,
-        "steady_state": steady,
+        "after_reset": {"value": world * N / (after_reset_ms * 1e-3), "ms_per_step": after_reset_ms,
+                        "note": "side note: the same K steps right after reset() (vessels at their path starts, nearby "
+                                "lists refreshed in lock-step) -- NOT the headline"},
         "e2e": e2e,
-        "gpu_launches": 2 * K * n_ranges(N, env.chunks),  # k_vessel_nav + k_lidar per env range
-        "roofline": {
-            "kernel": dominant, "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved_gbs / hbm_peak, "traffic": kernels[dominant]["traffic"],
-            "ms_per_launch": kernels[dominant]["ms_per_launch"],
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-            "algo_bytes_per_launch": kernels[dominant]["algo_bytes_per_launch"],
-            "records_per_env_step": records_per_step / N,
-            "kernels": kernels,
-            "note": "Neither step kernel is HBM-bound: k_vessel_nav is bound by the latency of dependent FP64 chains "
-                    "and table look-ups (ncu: 41 %% issue slots at 42 %% occupancy, dram 20 %% of peak), k_lidar by "
-                    "instruction issue (68 %% issue slots, dram 6 %% of peak), see fp32_view; the HBM fractions are "
-                    "low by construction.  Launch durations are CUDA-event times of a single-stream replay of the same "
-                    "K steps (auv_step_timed); the headline `value` runs the same kernels as %d env ranges on %d "
-                    "streams." % (env.chunks, getattr(env, "chunk_streams", 1)),
-            "kernel_ms": kernel_ms,
-            "fp32_view": {"kernel": "k_lidar", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                          "frac": achieved_tflops / fp32_peak_tflops if fp32_peak_tflops else None,
-                          "seg_tests_per_env_step": seg_tests_per_step / N,
-                          "note": "algorithmic FLOPs = 16 x reference-semantics ray/segment tests + 60 x rays "
-                                  "(SURVEY 8d); peak = FP32 FMA probe measured in this run"},
-            "step_hbm_view": {"achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
-                              "algo_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
-                              "note": "whole step (both kernels) algorithmic bytes / timed-region time per step"},
-        },
-        "episode_stats": stats,
+        "gpu_launches": 2 * K * n_ranges(N, env.chunks) + (7 * (K // args.refresh_every) if fresh else 0),
+        "roofline": roof,
+        "episode_stats": stats_timed,
     }
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         small = argparse.Namespace(**vars(args))
         small.envs = args.cpu_sample_envs
         small.n_paths = min(args.n_paths, small.envs)
+        small.host_scenarios = True
         ccfg, cscn = build_workload(small, 0)
         v, total, tmax = cpu_baseline(args, ccfg, cscn, small.envs, args.cpu_sample_steps, 4, 1)
         line["cpu_baseline"] = {

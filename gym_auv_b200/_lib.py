@@ -138,7 +138,7 @@ class AuvBatch(C.Structure):
         ("n_envs", C.c_int32),
         ("mask_words", C.c_int32),
         ("env_offset", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("reset_stride", C.c_int32),
         ("scn_id", _vp),
         ("episode", _vp),
         ("state", _vp),
@@ -201,6 +201,10 @@ class AuvGenParams(C.Structure):
     ]
 
 
+class AuvRefreshScratch(C.Structure):
+    _fields_ = [("seen_episode", _vp), ("ids", _vp), ("count", _vp), ("capacity", C.c_int32), ("reserved0", C.c_int32)]
+
+
 EXPORTS = [
     "auv_abi_version",
     "auv_sizeof",
@@ -228,6 +232,8 @@ EXPORTS = [
     "auv_linear_wrap",
     "auv_pool_pack",
     "auv_obstacle_state",
+    "auv_reset_cache_fill",
+    "auv_refresh_finished",
 ]
 
 _lib = None
@@ -287,6 +293,10 @@ def load():
     lib.auv_linear_wrap.argtypes = [C.c_double, C.c_double, C.c_int, P(C.c_int32), P(C.c_int32)]
     lib.auv_pool_pack.argtypes = [P(AuvConfig), P(AuvScenarioPool), _vp, C.c_int, _vp]
     lib.auv_obstacle_state.argtypes = [P(AuvConfig), P(AuvScenarioPool), P(AuvBatch), _vp, _vp, _vp, _vp]
+    lib.auv_reset_cache_fill.argtypes = [P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch),
+                                         P(AuvStepOut), _vp, C.c_int, C.c_int, _vp]
+    lib.auv_refresh_finished.argtypes = [P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch),
+                                         P(AuvBatch), P(AuvStepOut), P(AuvRefreshScratch), P(AuvGenParams), _vp]
     lib.auv_timer_create.argtypes = [C.c_int]
     lib.auv_timer_create.restype = _vp
     lib.auv_timer_destroy.argtypes = [_vp]
@@ -301,7 +311,8 @@ def load():
     if ver != ABI_VERSION:
         raise AuvLibraryError(f"ABI mismatch: library {ver}, binding {ABI_VERSION}; rebuild")
     lib.auv_sizeof.argtypes = [C.c_int]
-    for i, st in enumerate([AuvConfig, AuvRayTable, AuvPathBank, AuvScenarioPool, AuvBatch, AuvStepOut, AuvGenParams]):
+    for i, st in enumerate([AuvConfig, AuvRayTable, AuvPathBank, AuvScenarioPool, AuvBatch, AuvStepOut, AuvGenParams,
+                            AuvPathHdr, AuvRefreshScratch]):
         if lib.auv_sizeof(i) != C.sizeof(st):
             raise AuvLibraryError(f"struct layout mismatch for {st.__name__}: C {lib.auv_sizeof(i)} vs ctypes {C.sizeof(st)}")
     _lib = lib

@@ -78,9 +78,11 @@ __global__ void __launch_bounds__(128) k_generate_moving_obstacles(const __grid_
                                                                     const __grid_constant__ AuvPathBank pb,
                                                                     const __grid_constant__ AuvScenarioPool pool,
                                                                     const int* __restrict__ ids, int n_ids,
+                                                                    const int* __restrict__ n_ids_dev,
                                                                     int* __restrict__ status) {
   const int km = pool.k_moving, ks = pool.k_static, per = km + ks + 1;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_ids_dev != nullptr) n_ids = min(n_ids, *n_ids_dev);  // list length decided on the device (auv_refresh_finished)
   if (gid >= (long long)n_ids * per) return;
   const int li = (int)(gid / per), slot = (int)(gid - (long long)li * per);
   const int m = ids ? ids[li] : li;

@@ -150,7 +150,7 @@ __device__ __forceinline__ void pent_vertex(int k, double bx, double by, double 
 // distance from the own-ship to the filled polygon / crossing-number inside test, on
 // vessel-relative FP32 vertices formed in FP64.  Cold (nearby refresh / own-ship within
 // the enclosing circle only).
-__device__ __forceinline__ double world_polygon_distance(const double2* __restrict__ v, int nv, double px,
+__device__ __noinline__ double world_polygon_distance(const double2* __restrict__ v, int nv, double px,
                                                          double py, bool& inside) {
   float dmin = INFINITY;
   bool in = false;
@@ -173,7 +173,7 @@ __device__ __forceinline__ double world_polygon_distance(const double2* __restri
 // of the polygonised circle (ring) or 0 / min over edges for the filled vessel pentagon.
 // FP32 on vessel-relative vertices formed in FP64.  Cold (only on nearby-list refresh and
 // only for obstacles whose enclosing circle straddles the range limit).
-__device__ __forceinline__ double boundary_distance(bool pent, double cx, double cy, double bx0, double by0,
+__device__ __noinline__ double boundary_distance(bool pent, double cx, double cy, double bx0, double by0,
                                                  double geo, double hx, double hy, int nv_cnt,
                                                  const double2* __restrict__ unit) {
   const int ne = nv_cnt - 1;

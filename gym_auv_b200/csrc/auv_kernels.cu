@@ -11,14 +11,14 @@
 //                      the group): nearby list (every 25 steps), enclosing circles,
 //                      reference-exact ray windows, inside tests -> compact per-env obstacle
 //                      records in HBM                                          latency / FP64
-//   k_lidar<COUNT,G>   a group of G lanes per env (32/G envs per warp side by side), lanes over
-//                      rays: the env's hand-over line and first records arrive in one round
-//                      trip, ranges live in shared memory (one writer per ray and record: no
-//                      atomics), ray/segment casting (analytic edge pick for polygonised
-//                      circles, vertices formed on the fly), closeness, collision, obs,
-//                      group-reduced reward, done, counters, sector pooling, optional obstacle
-//                      velocity channel, and the VecEnv auto-reset of finished envs as a COPY
-//                      of the scenario's cached first observation                 FP32 issue
+//   k_lidar<COUNT,VEL> one CTA per 32 consecutive envs, every phase with the mapping that fills
+//                      its lanes: hand-over lines + obstacle records -> shared memory; WARP PER
+//                      RECORD over the CTA's flat record list (analytic edge pick for polygonised
+//                      circles, vertices formed on the fly, results merged into the env's range
+//                      row by shared-memory atomicMin); WARP PER ENV for closeness / collision /
+//                      penalty / observation row / sector pooling / velocity channel; THREAD PER
+//                      ENV for reward, done, counters; a warp per finished env for the VecEnv
+//                      auto-reset (a COPY of the scenario's cached first observation)  FP32 issue
 //   k_obstacle_update / k_vessel_step / k_reset   staged entry points
 //   k_pool_pack, k_obstacle_state                  pool packing / obstacle state read-back
 //   k_fma_probe        FP32 FMA peak micro-benchmark (roofline denominator)
@@ -446,6 +446,62 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
   }
 }
 
+// ---- reset cache (pool.reset_*) and sustained scenario refresh, all on the device
+// worker env w takes the k-th listed scenario (padded with repeats: recomputing is idempotent)
+__global__ void __launch_bounds__(128) k_worker_fill(AuvBatch wb, const int* __restrict__ ids, int first, int n,
+                                                     const int* __restrict__ n_dev) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= wb.n_envs) return;
+  if (n_dev != nullptr) n = min(n, *n_dev);
+  const int k = n > 0 ? min(w, n - 1) : 0;
+  wb.scn_id[w] = ids ? ids[k] : first + k;
+}
+// one warp per worker env: its first observation, max progress and nearby list become the
+// cached reset of its scenario (environment.py:176-245 computed once per scenario)
+__global__ void __launch_bounds__(128) k_cache_scatter(AuvScenarioPool pool, AuvBatch wb, const float* __restrict__ wobs,
+                                                       int obs_dim, int use_lidar, int n, const int* __restrict__ n_dev) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n_dev != nullptr) n = min(n, *n_dev);
+  if (w >= n || w >= wb.n_envs) return;
+  const int m = wb.scn_id[w];
+  float* dst = const_cast<float*>(pool.reset_obs) + (long long)m * obs_dim;
+  const float* src = wobs + (long long)w * obs_dim;
+  for (int k = lane; k < obs_dim; k += 32) dst[k] = src[k];
+  if (lane == 0) const_cast<double*>(pool.reset_max_progress)[m] = wb.max_progress[w];
+  if (use_lidar)
+    for (int k = lane; k < wb.mask_words; k += 32)
+      const_cast<uint32_t*>(pool.reset_mask)[(long long)m * wb.mask_words + k] = wb.nearby_mask[(long long)w * wb.mask_words + k];
+}
+// envs that finished an episode since the last call list the pool slot they vacated: with a
+// ping-pong pool of 2 N scenarios env e alternates between slots e and e + N
+__global__ void __launch_bounds__(128) k_refresh_collect(AuvBatch live, int n_scenarios, int* __restrict__ seen,
+                                                         int* __restrict__ ids, int* __restrict__ count, int capacity) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= live.n_envs) return;
+  const int ep = live.episode[e];
+  if (ep == seen[e]) return;
+  const int k = atomicAdd(count, 1);
+  if (k >= capacity) return;  // stays listed as unseen: picked up by the next call
+  seen[e] = ep;
+  ids[k] = (int)(((long long)live.scn_id[e] + (live.reset_stride > 0 ? live.reset_stride : live.n_envs)) % n_scenarios);
+}
+
+// table-driven moving-obstacle update of one env by its group of G lanes (two slots in flight per lane)
+template <int G>
+__device__ __noinline__ void obstacle_update_group(const AuvConfig& cfg, const AuvScenarioPool& pool, const AuvBatch& batch,
+                                                   int e, int scn, int sub, bool store) {
+  if (!store) return;
+  const int km = pool.k_moving;
+  const long long pe0 = (long long)e * km, ps0 = (long long)scn * km;
+  for (int j = sub; j < km; j += 2 * G) {
+    const bool two = j + G < km;
+    const ObstLoad a = obstacle_load(pool, batch, pe0 + j, ps0 + j);
+    const ObstLoad b = obstacle_load(pool, batch, pe0 + (two ? j + G : j), ps0 + (two ? j + G : j));
+    obstacle_finish(cfg, pool, batch, pe0 + j, ps0 + j, a);
+    if (two) obstacle_finish(cfg, pool, batch, pe0 + j + G, ps0 + j + G, b);
+  }
+}
+
 // ---- bulk async copy (TMA, 1-D) + mbarrier: a CTA's copy of its path's capsule tables
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -493,7 +549,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #define AUV_NAV_THREADS 128
 #endif
 #ifndef AUV_NAV_MINB
-#define AUV_NAV_MINB 7  // 72 registers (profiles/r1j_variants.txt: 64 regs 0.114 ms, 72 regs 0.104, 80 regs 0.121)
+#define AUV_NAV_MINB 8  // 64 registers (steady state, round 2: 6 / 7 / 8 CTAs per SM = 0.106 / 0.101 / 0.096 ms)
 #endif
 constexpr int NAV_STAGE_SB = (AUV_PATH_STAGE_BLOCKS + AUV_PATH_SUPER - 1) / AUV_PATH_SUPER;
 template <bool DYN, bool OBST, int G>
@@ -551,18 +607,8 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
   if (OBST) {
     ++n_upd;
     if (store && sub == 0) batch.obst_steps[e] = n_upd;
-    if (!pool.linear_tracks) {  // table-driven tracks: the group's lanes take the env's moving-obstacle slots
-      const int km = pool.k_moving;
-      if (store) {
-        const long long pe0 = (long long)e * km, ps0 = (long long)scn * km;
-        for (int j = sub; j < km; j += 2 * G) {  // two slots in flight per lane
-          const bool two = j + G < km;
-          const ObstLoad a = obstacle_load(pool, batch, pe0 + j, ps0 + j);
-          const ObstLoad b = obstacle_load(pool, batch, pe0 + (two ? j + G : j), ps0 + (two ? j + G : j));
-          obstacle_finish(cfg, pool, batch, pe0 + j, ps0 + j, a);
-          if (two) obstacle_finish(cfg, pool, batch, pe0 + j + G, ps0 + j + G, b);
-        }
-      }
+    if (!pool.linear_tracks) {  // table-driven tracks (out of line: pools of constant-velocity tracks never get here)
+      obstacle_update_group<G>(cfg, pool, batch, e, scn, sub, store);
       __syncwarp();  // the updated obstacles are visible to the group
     }
   }
@@ -597,20 +643,27 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
 }
 
 // ------------------------------------------------------------------------------------
-// k_lidar: a group of G lanes per env (32/G envs side by side in a warp, AUV_LIDAR_EPG
-// consecutive envs per group one after the other, the next env's hand-over line and first
-// records prefetched while the current one is cast)
+// k_lidar: one CTA per block of E (<= 32) consecutive envs, four phases that each use the
+// mapping that fills the lanes:
+//   1. the envs' hand-over lines (E x 128 B, coalesced) and obstacle records (contiguous per env)
+//      go to shared memory; every ray of every env starts at sensor_range
+//   2. WARP PER RECORD over the CTA's flat record list (warps never idle on an env with nothing
+//      in range, and a warp's record has one boundary type: no divergence): lanes over the
+//      record's candidate rays, analytic edge pick / staged vertex chain, results merged into
+//      the env's range row in shared memory by atomicMin on the bit pattern
+//   3. WARP PER ENV over the range rows: closeness, collision, penalty, observation row
+//      (8-byte vector stores), optional per-ray / per-sector outputs
+//   4. THREAD PER ENV: reward, done, counters, statistics -- one warp does the scalar tail of all
+//      E envs at once, its outputs leave coalesced; finished envs are then auto-reset by a warp
+//      each (copy of the cached first observation)
 // ------------------------------------------------------------------------------------
-constexpr int RROUND = 4;  // records per shared-memory round
-#ifndef AUV_LIDAR_WARPS
-#define AUV_LIDAR_WARPS 2  // warps per CTA (the warps of a CTA only meet once, after the unit table is staged)
+#ifndef AUV_LIDAR_THREADS
+#define AUV_LIDAR_THREADS 256
 #endif
-#ifndef AUV_LIDAR_EPG
-#define AUV_LIDAR_EPG 2    // envs per group, processed one after the other
+#ifndef AUV_LIDAR_RCAP
+#define AUV_LIDAR_RCAP 96  // records per shared-memory round
 #endif
-#ifndef AUV_LIDAR_G
-#define AUV_LIDAR_G 16     // lanes per env
-#endif
+#define AUV_LIDAR_MAX_ENVS 32
 
 struct LidarArgs {
   AuvConfig cfg;
@@ -622,8 +675,8 @@ struct LidarArgs {
   int mode;       // AUV_OBSERVE_STEP | AUV_OBSERVE_RESET
   int obs_dim;
   int e0, e1;     // envs [e0, e1) of the batch are processed by this launch
-  int vmax;       // staged vertices per env (float2): AUV_MAX_POLY_VERTS with world polygons, else 16
-  int velocity;   // 1: track the nearest obstacle per ray (sensor.py:100-137 semantics)
+  int envs_per_cta;  // E: 32 unless the ray count makes the range rows too large
+  int vmax;       // staged vertices per warp (float2): AUV_MAX_POLY_VERTS with world polygons, else 16
   float pen_clear_ray;     // range * exp(-0.1 range): penalty term of a ray that reads sensor_range
   float inv_log_range;     // 1 / log(1 + range)
   double clear_closeness;  // -range * exp(-0.1 range): closeness reward when every ray is clear
@@ -631,35 +684,45 @@ struct LidarArgs {
   double feas_width;       // vessel_width * feasibility_width_multiplier (sensor.py:166-168)
 };
 
-// shared memory of one env in flight: records of the round, vertex stage, range per ray and
-// (velocity mode) the record that produced it.  Every part is 16-byte aligned.
-__host__ __device__ constexpr size_t lidar_smem_per_env(int rpad, int vmax, int velocity) {
-  return RROUND * sizeof(ObstRec) + (size_t)vmax * sizeof(float2) + sizeof(float) * rpad + (velocity ? rpad : 0);
+// dynamic shared memory of a CTA; every part is 16-byte aligned
+struct LidarSmem {
+  double* hand;     // [E][16]   hand-over lines
+  void* sdist;      // [E][rpad] float ranges, or (VEL) u64 keys = range bits << 32 | record index
+  ObstRec* rec;     // [RCAP]    records of the round
+  int* rec_env;     // [RCAP]    local env | (record index in its env << 8)
+  float2* verts;    // [warps][vmax]
+  float2* unit;     // [64]      cos/sin(2 pi k / 64) in FP32
+  int* off;         // [E + 1]   exclusive scan of the envs' record counts
+  float* pen;       // [E]       sum of w_i (penalty_i - clear penalty) over hit rays
+  int* flag;        // [E]       bit 0 collision, bit 1 auto-reset pending
+  int* next;        // [E]       scenario the env resets onto
+};
+__host__ __device__ constexpr size_t lidar_smem_bytes_for(int E, int rpad, int vmax, int vel) {
+  return (size_t)E * 16 * 8 + (size_t)E * rpad * (vel ? 8 : 4) + AUV_LIDAR_RCAP * sizeof(ObstRec) + AUV_LIDAR_RCAP * 4 +
+         (size_t)(AUV_LIDAR_THREADS / 32) * vmax * 8 + 64 * 8 + 48 * 4 + 32 * 4 + 32 * 4 + 32 * 4;
 }
-struct EnvSmem {
-  ObstRec* rec;     // [RROUND]
-  float2* verts;    // [vmax]
-  float* sdist;     // [rpad]
-  uint8_t* sslot;   // [rpad] or nullptr
-};
-
-// one round trip per env: the env's hand-over line (16 doubles, one coalesced 128 B load) and,
-// speculatively, its first records before their count is known
-template <int G>
-struct LidarFetch {
-  static constexpr int NSC = (16 + G - 1) / G;             // hand-over doubles per lane
-  static constexpr int SPEC = (G / 5) < RROUND ? (G / 5) : RROUND;  // speculative records (5 x 16 B each)
-  double sc[NSC];
-  uint4 spec;
-};
-template <int G>
-__device__ __forceinline__ void lidar_fetch(const AuvConfig& cfg, const AuvBatch& batch, int e, int sub, LidarFetch<G>& f) {
-  const double* nv = batch.nav + (long long)e * AUV_NAV_W + NAV_HAND;
-#pragma unroll
-  for (int k = 0; k < LidarFetch<G>::NSC; ++k) f.sc[k] = (sub + k * G < 16) ? nv[sub + k * G] : 0.0;
-  f.spec = make_uint4(0, 0, 0, 0);
-  if (cfg.use_lidar && sub < LidarFetch<G>::SPEC * 5 && sub / 5 < batch.rec_cap)
-    f.spec = reinterpret_cast<const uint4*>(reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap)[sub];
+__device__ __forceinline__ LidarSmem lidar_carve(unsigned char* p, int E, int rpad, int vmax, int vel) {
+  LidarSmem s;
+  s.hand = reinterpret_cast<double*>(p);
+  p += (size_t)E * 16 * 8;
+  s.sdist = p;
+  p += (size_t)E * rpad * (vel ? 8 : 4);
+  s.rec = reinterpret_cast<ObstRec*>(p);
+  p += AUV_LIDAR_RCAP * sizeof(ObstRec);
+  s.rec_env = reinterpret_cast<int*>(p);
+  p += AUV_LIDAR_RCAP * 4;
+  s.verts = reinterpret_cast<float2*>(p);
+  p += (size_t)(AUV_LIDAR_THREADS / 32) * vmax * 8;
+  s.unit = reinterpret_cast<float2*>(p);
+  p += 64 * 8;
+  s.off = reinterpret_cast<int*>(p);
+  p += 48 * 4;
+  s.pen = reinterpret_cast<float*>(p);
+  p += 32 * 4;
+  s.flag = reinterpret_cast<int*>(p);
+  p += 32 * 4;
+  s.next = reinterpret_cast<int*>(p);
+  return s;
 }
 
 // range of the ray (c, s) against one regular n-gon ring inscribed in the circle (ecx, ecy, rho),
@@ -728,404 +791,437 @@ __device__ __forceinline__ float cast_chain(const float2* __restrict__ vp, int n
   return best;
 }
 
-template <int G>
-__device__ __forceinline__ float group_sum(unsigned gm, float v) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o);
-  return v;
+// range row access: plain floats, or (velocity mode) 64-bit keys that carry the record index of
+// the nearest hit -- ranges are >= 0, so both order like the values; ties go to the lower record
+// index = the earlier obstacle of the nearby list (min((distance, i)), sensor.py:113-117)
+template <bool VEL>
+__device__ __forceinline__ float range_get(const void* row, int i) {
+  if (VEL) return __uint_as_float((unsigned)(reinterpret_cast<const unsigned long long*>(row)[i] >> 32));
+  return reinterpret_cast<const float*>(row)[i];
+}
+template <bool VEL>
+__device__ __forceinline__ void range_min(void* row, int i, float d, int slot) {
+  if (VEL)
+    atomicMin(reinterpret_cast<unsigned long long*>(row) + i,
+              ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)min(slot, 255));
+  else
+    atomicMin(reinterpret_cast<int*>(row) + i, __float_as_int(d));
 }
 
-// everything after the culling stage for ONE env, by one group of G lanes.
-template <bool COUNT, int G>
-__device__ __forceinline__ void lidar_env(const LidarArgs& A, const EnvSmem& sm, const float2* __restrict__ s_unit,
-                                          const int rpad, const int e, const int lane, const unsigned gm,
-                                          const LidarFetch<G>& F) {
+#ifndef AUV_LIDAR_MINB
+#define AUV_LIDAR_MINB 4  // 64 registers
+#endif
+template <bool COUNT, bool VEL>
+__global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(const __grid_constant__ LidarArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NW = AUV_LIDAR_THREADS / 32;
   const AuvConfig& cfg = A.cfg;
   const AuvBatch& batch = A.batch;
-  const int n = batch.n_envs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = cfg.n_sensors;
-  const int sub = lane & (G - 1), gbase = lane & ~(G - 1);
+  const int rpad = cfg.use_lidar ? ((R + 31) & ~31) : 32;
+  const int E = A.envs_per_cta;
+  const int env0 = A.e0 + blockIdx.x * E;
+  const int ne = min(E, A.e1 - env0);
+  const LidarSmem sm = lidar_carve(smem_raw, E, rpad, A.vmax, VEL ? 1 : 0);
   const float rangef = (float)cfg.sensor_range;
   const float widthf = (float)cfg.vessel_width;
-  float* obs = A.out.obs + (long long)e * A.obs_dim;
-  const bool pooling = A.out.sector_min_dist != nullptr || A.out.sector_feasible_dist != nullptr;
-  const ObstRec* grec = reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
-  float* sdist = sm.sdist;
-// hand-over value k (NAV_HAND <= k < NAV_HAND + 16): register (k - 8) / G of lane (k - 8) % G of the group
-#define SCAL(k) __shfl_sync(gm, F.sc[((k) - NAV_HAND) / G], gbase + (((k) - NAV_HAND) % G))
+  const int n = batch.n_envs;
+#define HAND(el, k) sm.hand[(el) * 16 + ((k) - NAV_HAND)]
 
-  bool collision = false;
-  float pen = (float)A.rays.weight_sum * A.pen_clear_ray;  // every ray clear; hit rays add their excess below
+  // ---- phase 1: hand-over lines, unit table, range rows
+  for (int k = tid; k < ne * 16; k += AUV_LIDAR_THREADS)
+    sm.hand[k] = batch.nav[(long long)(env0 + (k >> 4)) * AUV_NAV_W + NAV_HAND + (k & 15)];
+  if (cfg.use_lidar) {
+    if (tid < 64) {
+      const double2 un = reinterpret_cast<const double2*>(A.rays.unit64)[tid];
+      sm.unit[tid] = make_float2((float)un.x, (float)un.y);
+    }
+    if (VEL) {
+      const unsigned long long key0 = ((unsigned long long)__float_as_uint(rangef) << 32) | 255ull;
+      for (int k = tid; k < ne * rpad; k += AUV_LIDAR_THREADS) reinterpret_cast<unsigned long long*>(sm.sdist)[k] = key0;
+    } else {
+      for (int k = tid; k < ne * rpad / 4; k += AUV_LIDAR_THREADS)
+        reinterpret_cast<float4*>(sm.sdist)[k] = make_float4(rangef, rangef, rangef, rangef);
+    }
+  }
+  __syncthreads();
   unsigned long long ntests = 0;
   if (cfg.use_lidar) {
-    const int cnt = (int)SCAL(NAV_CNT);
-    if (cnt > 0) {
-      const double px = SCAL(NAV_X), py = SCAL(NAV_Y), psi = SCAL(NAV_PSI);
-      const double cpsi = SCAL(NAV_COSPSI), spsi = SCAL(NAV_SINPSI);
-      const float dth_f = (float)(2.0 * AUV_PI / (double)R), psi_m_pi = (float)(psi - AUV_PI);
-      const double2* __restrict__ unit = reinterpret_cast<const double2*>(A.rays.unit64);
-      const double2* __restrict__ cos_sin = reinterpret_cast<const double2*>(A.rays.cos_sin);
-      uint4* srec4 = reinterpret_cast<uint4*>(sm.rec);
-      // ---- every ray starts at sensor_range (vector stores)
-      __syncwarp(gm);
-      for (int k = sub; k < rpad / 4; k += G) reinterpret_cast<float4*>(sdist)[k] = make_float4(rangef, rangef, rangef, rangef);
-      for (int r0 = 0; r0 < cnt; r0 += RROUND) {
-        // ---- round: up to RROUND records into shared memory (the first ones were prefetched)
-        const int nr = min(RROUND, cnt - r0);
-        __syncwarp(gm);
-        if (r0 == 0) {
-          if (sub < LidarFetch<G>::SPEC * 5) srec4[sub] = F.spec;
-          for (int k = LidarFetch<G>::SPEC * 5 + sub; k < nr * 5; k += G) srec4[k] = reinterpret_cast<const uint4*>(grec)[k];
+    if (warp == 0) {  // exclusive scan of the record counts (E <= 32)
+      const int c = lane < ne ? (int)HAND(lane, NAV_CNT) : 0;
+      const int incl = warp_incl_scan(c, lane);
+      sm.off[lane + 1] = incl;
+      if (lane == 0) sm.off[0] = 0;
+    }
+    __syncthreads();
+    const int total = sm.off[ne];
+    const double2* __restrict__ unit = reinterpret_cast<const double2*>(A.rays.unit64);
+    const double2* __restrict__ cos_sin = reinterpret_cast<const double2*>(A.rays.cos_sin);
+    const float dth_f = (float)(2.0 * AUV_PI / (double)R);
+    float2* wverts = sm.verts + (size_t)warp * A.vmax;
+    for (int r0 = 0; r0 < total; r0 += AUV_LIDAR_RCAP) {
+      const int nr = min(AUV_LIDAR_RCAP, total - r0);
+      // ---- records of the round: 16-byte pieces, the env of a record by bisection of the scan
+      for (int k = tid; k < nr * 5; k += AUV_LIDAR_THREADS) {
+        const int r = r0 + k / 5, piece = k - (k / 5) * 5;
+        int lo = 0, hi = ne - 1;  // last env with off[env] <= r
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (sm.off[mid] <= r) lo = mid; else hi = mid - 1;
+        }
+        const int idx = r - sm.off[lo];
+        const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const ObstRec*>(batch.rec) +
+                                                        (long long)(env0 + lo) * batch.rec_cap + idx);
+        reinterpret_cast<uint4*>(sm.rec)[k] = g[piece];
+        if (piece == 0) sm.rec_env[r - r0] = lo | (idx << 8);
+      }
+      __syncthreads();
+      // ---- phase 2: warp per record
+      for (int rr = warp; rr < nr; rr += NW) {
+        const ObstRec& q = sm.rec[rr];
+        const int el = sm.rec_env[rr] & 255, slot = sm.rec_env[rr] >> 8;
+        const int fl = q.flags, nq = q.nv;
+        // candidate rays of the record (sensor.py:93-95): i in I1 = [a,b) or i-R in [a,b), i.e.
+        // I2 = [a+R, b+R), both clipped to [0,R).  An obstacle whose window is wider than R is
+        // listed -- and tested -- twice upstream: the min does not care, so the part of I2 that
+        // repeats I1 is dropped here (and counted in COUNT mode below).
+        int n1, n2 = 0, lo1 = 0, lo2 = 0;
+        if (fl & OFLAG_ALLRAYS) {
+          n1 = R;
         } else {
-          for (int k = sub; k < nr * 5; k += G) srec4[k] = reinterpret_cast<const uint4*>(grec + r0)[k];
+          lo1 = max(q.a, 0);
+          const int hi1 = min(q.b, R);
+          n1 = max(0, hi1 - lo1);
+          lo2 = max(q.a + R, 0);
+          if (n1 > 0) lo2 = max(lo2, hi1);
+          n2 = max(0, min(q.b + R, R) - lo2);
         }
-        __syncwarp(gm);
-        for (int rr = 0; rr < nr; ++rr) {
-          const ObstRec& q = sm.rec[rr];
-          const int fl = q.flags, nq = q.nv;
-          // ---- candidate rays of the record (sensor.py:93-95): i in I1 = [a,b) or i-R in [a,b),
-          //      i.e. I2 = [a+R, b+R), both clipped to [0,R).  An obstacle whose window is wider
-          //      than R is listed -- and tested -- twice upstream: the min does not care, so the
-          //      part of I2 that repeats I1 is dropped here (and counted in COUNT mode below).
-          int n1, n2 = 0, lo1 = 0, lo2 = 0;
-          if (fl & OFLAG_ALLRAYS) {
-            n1 = R;
+        const int tot = n1 + n2;
+        if (COUNT) {  // reference-semantics ray/segment tests of this record (bench / parity only)
+          for (int i = lane; i < R; i += 32) {
+            const int hits = ((q.a <= i && i < q.b) ? 1 : 0) + ((q.a <= i - R && i - R < q.b) ? 1 : 0);
+            if ((fl & OFLAG_ALLRAYS) || hits > 0) ntests += (unsigned)((nq - 1) * max(hits, 1));
+          }
+        }
+        if (tot == 0) continue;
+        void* row = VEL ? (void*)(reinterpret_cast<unsigned long long*>(sm.sdist) + (size_t)el * rpad)
+                        : (void*)(reinterpret_cast<float*>(sm.sdist) + (size_t)el * rpad);
+        if (fl & OFLAG_INSIDE) {  // own-ship inside a filled boundary: every candidate ray reads 0
+          for (int u = lane; u < tot; u += 32) range_min<VEL>(row, u < n1 ? lo1 + u : lo2 + (u - n1), 0.f, slot);
+          continue;
+        }
+        const bool ngon = !(fl & (OFLAG_PENTAGON | OFLAG_WORLD)) && nq > 16;
+        if (!ngon) {
+          if (nq > A.vmax) {  // a polygon the vertex stage cannot hold: flagged, never silently miscast
+            if (lane == 0 && batch.status != nullptr) atomicOr(batch.status, AUV_STATUS_POLY_TOO_LARGE);
+            continue;
+          }
+          // stage the vertices: vessel-relative, formed in FP64, stored FP32
+          __syncwarp();
+          if (fl & OFLAG_WORLD) {
+            const double px = HAND(el, NAV_X), py = HAND(el, NAV_Y);
+            const double2* wv = reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase;
+            for (int k = lane; k < nq; k += 32) {
+              const double2 w = wv[k];
+              wverts[k] = make_float2((float)(w.x - px), (float)(w.y - py));
+            }
+          } else if (fl & OFLAG_PENTAGON) {
+            if (lane < 6) {
+              double vx, vy;
+              pent_vertex(lane == 5 ? 0 : lane, q.cx, q.cy, q.geo, q.hx, q.hy, vx, vy);
+              wverts[lane] = make_float2((float)vx, (float)vy);
+            }
+          } else {  // small polygonised circle (2 / 4 / 8 sides) incl. the closing vertex
+            const int ne_ = nq - 1, sh = 6 - (31 - __clz(ne_));
+            if (lane < nq) {
+              const double2 un = __ldg(&unit[(lane == ne_ ? 0 : lane) << sh]);
+              wverts[lane] = make_float2((float)(q.cx + q.geo * un.x), (float)(q.cy + q.geo * un.y));
+            }
+          }
+          __syncwarp();
+        }
+        const double cpsi = HAND(el, NAV_COSPSI), spsi = HAND(el, NAV_SINPSI);
+        const float psi_m_pi = (float)(HAND(el, NAV_PSI) - AUV_PI);
+        const float ecx = q.ecx, ecy = q.ecy, rho = q.rho;
+        const float slack = rho * 1e-5f + 1e-4f;
+        for (int u = lane; u < tot; u += 32) {
+          const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
+          const float cur = range_get<VEL>(row, i);
+          // ray direction in the world frame, formed in FP64 (vessel.py:317)
+          const double2 cs = cos_sin[i];
+          const float c = (float)(cs.x * cpsi - cs.y * spsi), sn = (float)(cs.y * cpsi + cs.x * spsi);
+          const float tc = ecx * c + ecy * sn;
+          const float hc = ecy * c - ecx * sn;
+          if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > cur) continue;
+          float got;
+          if (ngon) {
+            // world angle of ray i; only selects which polygon edge the analytic pick looks at
+            const float theta = fmaf((float)(i + 1), dth_f, psi_m_pi);
+            got = cast_ngon(ecx, ecy, rho, nq - 1, sm.unit, c, sn, theta, tc, hc, cur, rangef);
           } else {
-            lo1 = max(q.a, 0);
-            const int hi1 = min(q.b, R);
-            n1 = max(0, hi1 - lo1);
-            lo2 = max(q.a + R, 0);
-            if (n1 > 0) lo2 = max(lo2, hi1);
-            n2 = max(0, min(q.b + R, R) - lo2);
+            got = cast_chain(wverts, nq, c, sn, cur, rangef);
           }
-          const int tot = n1 + n2;
-          if (COUNT) {  // reference-semantics ray/segment tests of this record (bench / parity only)
-            for (int i = sub; i < R; i += G) {
-              const int hits = ((q.a <= i && i < q.b) ? 1 : 0) + ((q.a <= i - R && i - R < q.b) ? 1 : 0);
-              if ((fl & OFLAG_ALLRAYS) || hits > 0) ntests += (unsigned)((nq - 1) * max(hits, 1));
-            }
-          }
-          if (tot == 0) continue;  // uniform in the group
-          const bool ngon = !(fl & (OFLAG_PENTAGON | OFLAG_WORLD | OFLAG_INSIDE)) && nq > 16;
-          const bool chain = !ngon && !(fl & OFLAG_INSIDE);
-          if (chain) {
-            if (nq > A.vmax) {  // a polygon the vertex stage cannot hold: flagged, never silently miscast
-              if (sub == 0 && batch.status != nullptr) atomicOr(batch.status, AUV_STATUS_POLY_TOO_LARGE);
-              continue;
-            }
-            // ---- stage the vertices: vessel-relative, formed in FP64, stored FP32
-            if (fl & OFLAG_WORLD) {
-              const double2* wv = reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase;
-              for (int k = sub; k < nq; k += G) {
-                const double2 w = wv[k];
-                sm.verts[k] = make_float2((float)(w.x - px), (float)(w.y - py));
-              }
-            } else if (fl & OFLAG_PENTAGON) {
-              if (sub < 6) {
-                double vx, vy;
-                pent_vertex(sub == 5 ? 0 : sub, q.cx, q.cy, q.geo, q.hx, q.hy, vx, vy);
-                sm.verts[sub] = make_float2((float)vx, (float)vy);
-              }
-            } else {  // small polygonised circle (4 / 8 / 16 sides) incl. the closing vertex
-              const int ne = nq - 1, sh = 6 - (31 - __clz(ne));
-              for (int k = sub; k < nq; k += G) {
-                const double2 un = __ldg(&unit[(k == ne ? 0 : k) << sh]);
-                sm.verts[k] = make_float2((float)(q.cx + q.geo * un.x), (float)(q.cy + q.geo * un.y));
-              }
-            }
-            __syncwarp(gm);
-          }
-          const float ecx = q.ecx, ecy = q.ecy, rho = q.rho;
-          const float slack = rho * 1e-5f + 1e-4f;
-          // ---- cast: the group's lanes over the record's candidate rays (one writer per ray)
-          for (int u = sub; u < tot; u += G) {
-            const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
-            const float cur = sdist[i];
-            float got = cur;
-            if (fl & OFLAG_INSIDE) {
-              got = 0.f;
-            } else {
-              // ray direction in the world frame, formed in FP64 (vessel.py:317)
-              const double2 cs = cos_sin[i];
-              const float c = (float)(cs.x * cpsi - cs.y * spsi), sn = (float)(cs.y * cpsi + cs.x * spsi);
-              const float tc = ecx * c + ecy * sn;
-              const float hc = ecy * c - ecx * sn;
-              if (!(fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > cur)) {
-                if (ngon) {
-                  // world angle of ray i; only selects which polygon edge the analytic pick looks at
-                  const float theta = fmaf((float)(i + 1), dth_f, psi_m_pi);
-                  got = cast_ngon(ecx, ecy, rho, nq - 1, s_unit, c, sn, theta, tc, hc, cur, rangef);
-                } else {
-                  got = cast_chain(sm.verts, nq, c, sn, cur, rangef);
-                }
-              }
-            }
-            if (got < cur) {
-              sdist[i] = got;
-              if (sm.sslot != nullptr) sm.sslot[i] = (uint8_t)min(r0 + rr, 255);
-            }
-          }
-          __syncwarp(gm);  // next record: other lanes touch these rays, the vertex stage is reused
+          if (got < cur) range_min<VEL>(row, i, got, slot);
         }
       }
-    }
-    // ---- closeness / collision / penalty / observation in one pass over the rays
-    //      (vessel.py:88-95,356-359; rewarder.py:199-214; zeros without nearby obstacles: vessel.py:275-305)
-    float extra = 0.f;
-    const bool vel_obs = cfg.sensor_use_velocity_observations != 0;
-    if (cnt > 0) {
-      const double cpsi = SCAL(NAV_COSPSI), spsi = SCAL(NAV_SINPSI);
-      const double2* __restrict__ cos_sin = reinterpret_cast<const double2*>(A.rays.cos_sin);
-      const bool vec2 = (A.obs_dim & 1) == 0;  // rows and obs + 6 are 8-byte aligned
-      for (int k = sub; k < (R + 1) / 2; k += G) {
-        float cl2[2] = {0.f, 0.f};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int i = 2 * k + h;
-          if (i >= R) continue;
-          const float d = sdist[i];
-          float vxr = 0.f, vyr = 0.f;
-          if (d < rangef) {
-            if (cfg.sensor_log_transform)  // log(1 + d) by the hardware log2: |error| < 1e-6 of a value in [0, 5]
-              cl2[h] = 1.f - fminf(fmaxf(__logf(1.f + d) * A.inv_log_range, 0.f), 1.f);
-            else
-              cl2[h] = 1.f - fminf(fmaxf(d / rangef, 0.f), 1.f);
-            cl2[h] = fminf(fmaxf(cl2[h], -1.f), 1.f);
-            if (sm.sslot != nullptr) {
-              // sensor.py:118-128: Rz(-theta - pi/2) (dx, dy) of the nearest obstacle hit by the ray
-              const ObstRec& q = grec[sm.sslot[i]];
-              if (q.flags & OFLAG_PENTAGON) {
-                const double2 cs = cos_sin[i];
-                const double c = cs.x * cpsi - cs.y * spsi, sn = cs.y * cpsi + cs.x * spsi;
-                const double dx = (double)q.step_len * q.hx, dy = (double)q.step_len * q.hy;
-                vxr = (float)(-sn * dx + c * dy);
-                vyr = (float)(-c * dx - sn * dy);
-              }
-            }
-            extra += A.rays.weight[i] * (rangef * __expf(-0.1f * d + fmaxf(0.f, vyr)) - A.pen_clear_ray);
-            collision = collision || (d < widthf);
-          }
-          if (vel_obs) {
-            obs[6 + R + i] = fminf(fmaxf(vxr, -1.f), 1.f);
-            obs[6 + 2 * R + i] = fminf(fmaxf(vyr, -1.f), 1.f);
-          }
-          if (!vec2) obs[6 + i] = cl2[h];
-        }
-        if (vec2) {
-          if (2 * k + 1 < R)
-            reinterpret_cast<float2*>(obs + 6)[k] = make_float2(cl2[0], cl2[1]);
-          else
-            obs[6 + 2 * k] = cl2[0];
-        }
-      }
-      collision = __any_sync(gm, collision);
-      pen += group_sum<G>(gm, extra);
-    } else {
-      if ((A.obs_dim & 1) == 0) {
-        float2* o2 = reinterpret_cast<float2*>(obs + 6);
-        for (int k = sub; k < R / 2; k += G) o2[k] = make_float2(0.f, 0.f);
-        if ((R & 1) && sub == 0) obs[6 + R - 1] = 0.f;
-      } else {
-        for (int i = sub; i < R; i += G) obs[6 + i] = 0.f;
-      }
-      if (vel_obs)
-        for (int k = sub; k < 2 * R; k += G) obs[6 + R + k] = 0.f;
-    }
-    if (A.out.lidar_dist != nullptr)
-      for (int i = sub; i < R; i += G) A.out.lidar_dist[(long long)e * R + i] = cnt > 0 ? sdist[i] : rangef;
-
-    // ---- optional sector pooling (utils/sector_partitioning.py:4-9; sensor.py:215-296)
-    if (pooling) {
-      const int ns = cfg.n_sectors;
-      __syncwarp(gm);
-      if (cnt == 0)
-        for (int i = sub; i < R; i += G) sdist[i] = rangef;
-      float* ssec = reinterpret_cast<float*>(sm.verts);  // vertex staging is free again (vmax >= 16: 32 floats)
-      for (int k = sub; k < 32; k += G) ssec[k] = rangef;
-      __syncwarp(gm);
-      // min-pooling: segmented shuffle reduction keyed by the ray's sector id
-      for (int i0 = 0; i0 < R; i0 += G) {
-        const int i = i0 + sub;
-        float d = i < R ? sdist[i] : INFINITY;
-        const int sid = i < R ? (int)A.rays.sector[i] : -1 - sub;
-#pragma unroll
-        for (int o = 1; o < G; o <<= 1) {
-          const float od = __shfl_down_sync(gm, d, o, G);
-          const int os = __shfl_down_sync(gm, sid, o, G);
-          if (sub + o < G && os == sid) d = fminf(d, od);
-        }
-        const int ps = __shfl_up_sync(gm, sid, 1, G);
-        const bool head = i < R && (sub == 0 || ps != sid);
-        if (head && sid < 32) ssec[sid] = fminf(ssec[sid], d);  // one head per sector per iteration
-        __syncwarp(gm);
-      }
-      if (A.out.sector_min_dist != nullptr)
-        for (int sct = sub; sct < ns; sct += G) A.out.sector_min_dist[(long long)e * ns + sct] = ssec[sct];
-      if (A.out.sector_feasible_dist != nullptr) {
-        for (int sct = sub; sct < ns; sct += G) {
-          int lo = 0, hi = R;
-          for (int k = 0; k < R; ++k) {  // the sector table is monotone
-            const int sd = A.rays.sector[k];
-            if (sd < sct) lo = k + 1;
-            if (sd <= sct) hi = k + 1;
-          }
-          A.out.sector_feasible_dist[(long long)e * ns + sct] =
-              hi > lo ? feasibility_pooling(sdist + lo, hi - lo, A.feas_width, 2.0 * AUV_PI / (double)R) : rangef;
-        }
-      }
-      __syncwarp(gm);
+      __syncthreads();
     }
   }
   if (COUNT) {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) ntests += __shfl_xor_sync(gm, ntests, o);
-    if (sub == 0 && ntests) atomicAdd(A.out.seg_tests, ntests);
+    for (int o = 16; o > 0; o >>= 1) ntests += __shfl_xor_sync(AUV_FULL, ntests, o);
+    if (lane == 0 && ntests) atomicAdd(A.out.seg_tests, ntests);
   }
 
-  // the navigation part of the observation (obs[0..5]) was written by k_vessel_nav
-  const double progress = SCAL(NAV_H_PROGRESS), goal_dist = SCAL(NAV_H_GOAL);
-  const bool reached = SCAL(NAV_REACHED) != 0.0;
-  if (A.mode == AUV_OBSERVE_RESET) {  // explicit reset observe: info mirrors a fresh env
-    if (sub == 0) {
+  // ---- phase 3: warp per env -- closeness / collision / penalty / observation in one pass over the rays
+  //      (vessel.py:88-95,356-359; rewarder.py:199-214; zeros without nearby obstacles: vessel.py:275-305)
+  if (cfg.use_lidar) {
+    const bool pooling = A.out.sector_min_dist != nullptr || A.out.sector_feasible_dist != nullptr;
+    const bool vel_obs = cfg.sensor_use_velocity_observations != 0;
+    const bool vec2 = (A.obs_dim & 1) == 0;  // rows and obs + 6 are 8-byte aligned
+    const double2* __restrict__ cos_sin = reinterpret_cast<const double2*>(A.rays.cos_sin);
+    for (int el = warp; el < ne; el += NW) {
+      const int e = env0 + el;
+      float* obs = A.out.obs + (long long)e * A.obs_dim;
+      const int cnt = sm.off[el + 1] - sm.off[el];
+      const void* row = VEL ? (const void*)(reinterpret_cast<const unsigned long long*>(sm.sdist) + (size_t)el * rpad)
+                            : (const void*)(reinterpret_cast<const float*>(sm.sdist) + (size_t)el * rpad);
+      float extra = 0.f;
+      bool collision = false;
+      if (cnt > 0) {
+        const double cpsi = HAND(el, NAV_COSPSI), spsi = HAND(el, NAV_SINPSI);
+        const ObstRec* grec = reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
+        for (int k = lane; k < (R + 1) / 2; k += 32) {
+          float cl2[2] = {0.f, 0.f};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int i = 2 * k + h;
+            if (i >= R) continue;
+            const float d = range_get<VEL>(row, i);
+            float vxr = 0.f, vyr = 0.f;
+            if (d < rangef) {
+              if (cfg.sensor_log_transform)  // log(1 + d) by the hardware log2: |error| < 1e-6 of a value in [0, 5]
+                cl2[h] = 1.f - fminf(fmaxf(__logf(1.f + d) * A.inv_log_range, 0.f), 1.f);
+              else
+                cl2[h] = 1.f - fminf(fmaxf(d / rangef, 0.f), 1.f);
+              cl2[h] = fminf(fmaxf(cl2[h], -1.f), 1.f);
+              if (VEL) {
+                // sensor.py:118-128: Rz(-theta - pi/2) (dx, dy) of the nearest obstacle hit by the ray
+                const int slot = (int)(reinterpret_cast<const unsigned long long*>(row)[i] & 255ull);
+                const ObstRec& q = grec[slot];
+                if (q.flags & OFLAG_PENTAGON) {
+                  const double2 cs = cos_sin[i];
+                  const double c = cs.x * cpsi - cs.y * spsi, sn = cs.y * cpsi + cs.x * spsi;
+                  const double dx = (double)q.step_len * q.hx, dy = (double)q.step_len * q.hy;
+                  vxr = (float)(-sn * dx + c * dy);
+                  vyr = (float)(-c * dx - sn * dy);
+                }
+              }
+              extra += A.rays.weight[i] * (rangef * __expf(-0.1f * d + fmaxf(0.f, vyr)) - A.pen_clear_ray);
+              collision = collision || (d < widthf);
+            }
+            if (vel_obs) {
+              obs[6 + R + i] = fminf(fmaxf(vxr, -1.f), 1.f);
+              obs[6 + 2 * R + i] = fminf(fmaxf(vyr, -1.f), 1.f);
+            }
+            if (!vec2) obs[6 + i] = cl2[h];
+          }
+          if (vec2) {
+            if (2 * k + 1 < R)
+              reinterpret_cast<float2*>(obs + 6)[k] = make_float2(cl2[0], cl2[1]);
+            else
+              obs[6 + 2 * k] = cl2[0];
+          }
+        }
+        collision = __any_sync(AUV_FULL, collision);
+        extra = warp_sum(extra);
+      } else {
+        if (vec2) {
+          float2* o2 = reinterpret_cast<float2*>(obs + 6);
+          for (int k = lane; k < R / 2; k += 32) o2[k] = make_float2(0.f, 0.f);
+          if ((R & 1) && lane == 0) obs[6 + R - 1] = 0.f;
+        } else {
+          for (int i = lane; i < R; i += 32) obs[6 + i] = 0.f;
+        }
+        if (vel_obs)
+          for (int k = lane; k < 2 * R; k += 32) obs[6 + R + k] = 0.f;
+      }
+      if (lane == 0) {
+        sm.pen[el] = extra;
+        sm.flag[el] = collision ? 1 : 0;
+      }
+      if (A.out.lidar_dist != nullptr)
+        for (int i = lane; i < R; i += 32) A.out.lidar_dist[(long long)e * R + i] = range_get<VEL>(row, i);
+
+      // ---- optional sector pooling (utils/sector_partitioning.py:4-9; sensor.py:215-296)
+      if (pooling) {
+        const int ns = cfg.n_sectors;
+        float* prow = reinterpret_cast<float*>(sm.verts + (size_t)warp * A.vmax);  // vertex stage is free again
+        float* ssec = prow;                // [32] sector minima
+        __syncwarp();
+        ssec[lane] = rangef;
+        __syncwarp();
+        // min-pooling: segmented warp-shuffle reduction keyed by the ray's sector id
+        for (int i0 = 0; i0 < R; i0 += 32) {
+          const int i = i0 + lane;
+          float d = i < R ? range_get<VEL>(row, i) : INFINITY;
+          const int sid = i < R ? (int)A.rays.sector[i] : -1 - lane;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float od = __shfl_down_sync(AUV_FULL, d, o);
+            const int os = __shfl_down_sync(AUV_FULL, sid, o);
+            if (lane + o < 32 && os == sid) d = fminf(d, od);
+          }
+          const int ps = __shfl_up_sync(AUV_FULL, sid, 1);
+          const bool head = i < R && (lane == 0 || ps != sid);
+          if (head && sid < 32) ssec[sid] = fminf(ssec[sid], d);  // one head per sector per iteration
+          __syncwarp();
+        }
+        if (A.out.sector_min_dist != nullptr && lane < ns) A.out.sector_min_dist[(long long)e * ns + lane] = ssec[lane];
+        if (A.out.sector_feasible_dist != nullptr) {
+          // the pooling routine reads plain float ranges: velocity mode keeps keys, so it gets a copy
+          const float* frow;
+          if (VEL) {
+            float* tmp = reinterpret_cast<float*>(const_cast<void*>(row));  // compact the keys in place (row is done)
+            __syncwarp();
+            for (int i0 = 0; i0 < R; i0 += 32) {
+              const int i = i0 + lane;
+              const float d = i < R ? range_get<VEL>(row, i) : 0.f;
+              __syncwarp();
+              if (i < R) tmp[i] = d;
+              __syncwarp();
+            }
+            frow = tmp;
+          } else {
+            frow = reinterpret_cast<const float*>(row);
+          }
+          if (lane < ns) {
+            int lo = 0, hi = R;
+            for (int k = 0; k < R; ++k) {  // the sector table is monotone
+              const int sd = A.rays.sector[k];
+              if (sd < lane) lo = k + 1;
+              if (sd <= lane) hi = k + 1;
+            }
+            A.out.sector_feasible_dist[(long long)e * ns + lane] =
+                hi > lo ? feasibility_pooling(frow + lo, hi - lo, A.feas_width, 2.0 * AUV_PI / (double)R) : rangef;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 4: thread per env -- reward (rewarder.py) + done (environment.py:375-384) + counters;
+  //      k_vessel_nav computed everything that does not depend on the LiDAR.  obs[0..5] is its too.
+  if (warp == 0 && lane < ne) {
+    const int el = lane, e = env0 + el;
+    const bool collision = cfg.use_lidar && (sm.flag[el] & 1);
+    const double progress = HAND(el, NAV_H_PROGRESS), goal_dist = HAND(el, NAV_H_GOAL);
+    const bool reached = HAND(el, NAV_REACHED) != 0.0;
+    int fl = 0;
+    if (A.mode == AUV_OBSERVE_RESET) {  // explicit reset observe: info mirrors a fresh env
       if (A.out.collision) A.out.collision[e] = collision;
       if (A.out.reached_goal) A.out.reached_goal[e] = reached;
       if (A.out.goal_distance) A.out.goal_distance[e] = (float)goal_dist;
       if (A.out.progress) A.out.progress[e] = (float)progress;
-    }
-    return;
-  }
-
-  // ---- reward (rewarder.py) + done (environment.py:375-384) + counters (uniform across the group):
-  //      k_vessel_nav computed everything that does not depend on the LiDAR
-  double reward = SCAL(NAV_REWARD_BASE);
-  if (collision) {
-    reward = -10000.0 * (1.0 - 0.5);
-  } else if (cfg.rewarder == AUV_REWARDER_COLAV) {
-    // without LiDAR every ray keeps its reset value sensor_range (vessel.py:206-208)
-    const double closeness_reward = cfg.use_lidar ? -(double)pen * A.inv_weight_sum : A.clear_closeness;
-    reward += 0.5 * closeness_reward;
-    if (reward < 0.0) reward *= 2.0;
-  }
-  const double y_e = SCAL(NAV_H_YE);
-  const double cum = SCAL(NAV_CUM) + reward;
-  const int t_step = (int)SCAL(NAV_TSTEP);
-  const bool done = collision || reached || (!cfg.test_mode && t_step >= cfg.max_timesteps - 1) ||
-                    (!cfg.test_mode && cum < cfg.min_cumulative_reward);
-  const double cte_sum = SCAL(NAV_CTE) + fabs(y_e);
-  const bool do_reset = done && cfg.auto_reset;
-  const int scn = (int)SCAL(NAV_SCN);
-  int next = 0;
-  if (do_reset) next = (int)(((long long)scn + n) % A.pool.n_scenarios);  // uniform across the group
-  if (sub == 0) {
-    A.out.reward[e] = (float)reward;
-    A.out.done[e] = done;
-    if (A.out.collision) A.out.collision[e] = collision;
-    if (A.out.reached_goal) A.out.reached_goal[e] = reached;
-    if (A.out.goal_distance) A.out.goal_distance[e] = (float)goal_dist;
-    if (A.out.progress) A.out.progress[e] = (float)progress;
-    if (!do_reset) {
-      batch.cum_reward[e] = cum;
-      batch.t_step[e] = t_step + 1;
-      batch.cte_sum[e] = cte_sum;
     } else {
-      // ---- VecEnv auto-reset, scalar part.  The first observation of an episode depends on the
-      // scenario only, so it was computed once per pool scenario (pool.reset_*) and the reset
-      // is a copy: no navigation / culling / casting on the step path.
-      const int npid = A.pool.path_id[next];
-      if (A.out.stats != nullptr) {  // env.history entry, environment.py:476-489
-        double* st = A.out.stats;
-        atomicAdd(st + AUV_STAT_EPISODES, 1.0);
-        atomicAdd(st + AUV_STAT_REWARD, cum);
-        atomicAdd(st + AUV_STAT_REWARD_SQ, cum * cum);
-        atomicAdd(st + AUV_STAT_PROGRESS, progress);
-        atomicAdd(st + AUV_STAT_COLLISIONS, collision ? 1.0 : 0.0);
-        atomicAdd(st + AUV_STAT_REACHED_GOAL, reached ? 1.0 : 0.0);
-        atomicAdd(st + AUV_STAT_TIMESTEPS, (double)(t_step + 1));
-        atomicAdd(st + AUV_STAT_CROSS_TRACK, cte_sum / (double)(t_step + 1));
-        atomicAdd(st + AUV_STAT_PATHLENGTH, A.paths.hdr[batch.env_pid[e]].length);
+      double reward = HAND(el, NAV_REWARD_BASE);
+      if (collision) {
+        reward = -10000.0 * (1.0 - 0.5);
+      } else if (cfg.rewarder == AUV_REWARDER_COLAV) {
+        // without LiDAR every ray keeps its reset value sensor_range (vessel.py:206-208)
+        const float pen = (float)A.rays.weight_sum * A.pen_clear_ray + sm.pen[el];
+        const double closeness_reward = cfg.use_lidar ? -(double)pen * A.inv_weight_sum : A.clear_closeness;
+        reward += 0.5 * closeness_reward;
+        if (reward < 0.0) reward *= 2.0;
       }
-      batch.scn_id[e] = next;
-      batch.env_pid[e] = npid;
-      batch.prev_seg[e] = -1;
-      batch.obst_steps[e] = 0;
-      batch.episode[e] += 1;
-      const double* vi = A.pool.vessel_init + 3ll * next;
-      batch.state[e] = vi[0];
-      batch.state[n + e] = vi[1];
-      batch.state[2ll * n + e] = vi[2];
-      batch.state[3ll * n + e] = 0.0;
-      batch.state[4ll * n + e] = 0.0;
-      batch.state[5ll * n + e] = 0.0;
-      batch.step_counter[e] = 0;
-      batch.t_step[e] = 0;
-      batch.cum_reward[e] = 0.0;
-      batch.cte_sum[e] = 0.0;
-      batch.max_progress[e] = A.pool.reset_max_progress[next];
+      const double y_e = HAND(el, NAV_H_YE);
+      const double cum = HAND(el, NAV_CUM) + reward;
+      const int t_step = (int)HAND(el, NAV_TSTEP);
+      const bool done = collision || reached || (!cfg.test_mode && t_step >= cfg.max_timesteps - 1) ||
+                        (!cfg.test_mode && cum < cfg.min_cumulative_reward);
+      const double cte_sum = HAND(el, NAV_CTE) + fabs(y_e);
+      const bool do_reset = done && cfg.auto_reset;
+      const int scn = (int)HAND(el, NAV_SCN);
+      A.out.reward[e] = (float)reward;
+      A.out.done[e] = done;
+      if (A.out.collision) A.out.collision[e] = collision;
+      if (A.out.reached_goal) A.out.reached_goal[e] = reached;
+      if (A.out.goal_distance) A.out.goal_distance[e] = (float)goal_dist;
+      if (A.out.progress) A.out.progress[e] = (float)progress;
+      if (!do_reset) {
+        batch.cum_reward[e] = cum;
+        batch.t_step[e] = t_step + 1;
+        batch.cte_sum[e] = cte_sum;
+      } else {
+        // ---- VecEnv auto-reset, scalar part.  The first observation of an episode depends on the
+        // scenario only, so it was computed once per pool scenario (pool.reset_*) and the reset
+        // is a copy: no navigation / culling / casting on the step path.
+        const int next = (int)(((long long)scn + (batch.reset_stride > 0 ? batch.reset_stride : n)) % A.pool.n_scenarios);
+        const int npid = A.pool.path_id[next];
+        if (A.out.stats != nullptr) {  // env.history entry, environment.py:476-489
+          double* st = A.out.stats;
+          atomicAdd(st + AUV_STAT_EPISODES, 1.0);
+          atomicAdd(st + AUV_STAT_REWARD, cum);
+          atomicAdd(st + AUV_STAT_REWARD_SQ, cum * cum);
+          atomicAdd(st + AUV_STAT_PROGRESS, progress);
+          atomicAdd(st + AUV_STAT_COLLISIONS, collision ? 1.0 : 0.0);
+          atomicAdd(st + AUV_STAT_REACHED_GOAL, reached ? 1.0 : 0.0);
+          atomicAdd(st + AUV_STAT_TIMESTEPS, (double)(t_step + 1));
+          atomicAdd(st + AUV_STAT_CROSS_TRACK, cte_sum / (double)(t_step + 1));
+          atomicAdd(st + AUV_STAT_PATHLENGTH, A.paths.hdr[batch.env_pid[e]].length);
+        }
+        batch.scn_id[e] = next;
+        batch.env_pid[e] = npid;
+        batch.prev_seg[e] = -1;
+        batch.obst_steps[e] = 0;
+        batch.episode[e] += 1;
+        const double* vi = A.pool.vessel_init + 3ll * next;
+        batch.state[e] = vi[0];
+        batch.state[n + e] = vi[1];
+        batch.state[2ll * n + e] = vi[2];
+        batch.state[3ll * n + e] = 0.0;
+        batch.state[4ll * n + e] = 0.0;
+        batch.state[5ll * n + e] = 0.0;
+        batch.step_counter[e] = 0;
+        batch.t_step[e] = 0;
+        batch.cum_reward[e] = 0.0;
+        batch.cte_sum[e] = 0.0;
+        batch.max_progress[e] = A.pool.reset_max_progress[next];
+        sm.next[el] = next;
+        fl = 2;
+      }
     }
+    sm.flag[el] = fl;
   }
-  if (!do_reset) return;
-  // ---- auto-reset, bulk part (whole group): terminal obs out, cached first obs in, obstacle
-  //      state (table-driven tracks only) and nearby list of the next scenario
-  __syncwarp(gm);
-  {
+  __syncthreads();
+  // ---- auto-reset, bulk part (a warp per finished env): terminal obs out, cached first obs in,
+  //      obstacle state (table-driven tracks only) and nearby list of the next scenario
+  for (int el = warp; el < ne; el += NW) {
+    if (!(sm.flag[el] & 2)) continue;
+    const int e = env0 + el, next = sm.next[el];
     const int km = A.pool.k_moving;
+    float* obs = A.out.obs + (long long)e * A.obs_dim;
     const float* robs = A.pool.reset_obs + (long long)next * A.obs_dim;
     float* tobs = A.out.terminal_obs ? A.out.terminal_obs + (long long)e * A.obs_dim : nullptr;
-    for (int k = sub; k < A.obs_dim; k += G) {
+    for (int k = lane; k < A.obs_dim; k += 32) {
       if (tobs) tobs[k] = obs[k];
       obs[k] = robs[k];
     }
     if (!A.pool.linear_tracks)
-      for (int j = sub; j < km; j += G) {
+      for (int j = lane; j < km; j += 32) {
         const long long ps = (long long)next * km + j, pe = (long long)e * km + j;
         reinterpret_cast<double2*>(batch.mov_pos)[pe] = reinterpret_cast<const double2*>(A.pool.mov_pos0)[ps];
         reinterpret_cast<double2*>(batch.mov_disp)[pe] = reinterpret_cast<const double2*>(A.pool.mov_disp0)[ps];
         batch.mov_counter[pe] = A.pool.mov_counter0[ps];
       }
     if (cfg.use_lidar)
-      for (int w = sub; w < batch.mask_words; w += G)
+      for (int w = lane; w < batch.mask_words; w += 32)
         batch.nearby_mask[(long long)e * batch.mask_words + w] = A.pool.reset_mask[(long long)next * batch.mask_words + w];
   }
-#undef SCAL
-}
-
-#ifndef AUV_LIDAR_MINB
-#define AUV_LIDAR_MINB 16  // min resident CTAs per SM asked of the compiler: 64 registers
-#endif
-template <bool COUNT, int G>
-__global__ void __launch_bounds__(AUV_LIDAR_WARPS * 32, AUV_LIDAR_MINB) k_lidar(const __grid_constant__ LidarArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int GPW = 32 / G;  // env groups per warp
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int sub = lane & (G - 1), grp = lane / G;
-  const unsigned gm = group_mask<G>(lane);
-  const int R = A.cfg.n_sensors;
-  const int rpad = A.cfg.use_lidar ? ((R + 31) & ~31) : 32;
-  // cos/sin(2 pi k / 64) in FP32 for the on-the-fly polygon vertices, once per CTA
-  float2* s_unit = reinterpret_cast<float2*>(smem_raw);
-  if (A.cfg.use_lidar)
-    for (int k = threadIdx.x; k < 64; k += AUV_LIDAR_WARPS * 32) {
-      const double2 un = reinterpret_cast<const double2*>(A.rays.unit64)[k];
-      s_unit[k] = make_float2((float)un.x, (float)un.y);
-    }
-  __syncthreads();
-  const size_t per = lidar_smem_per_env(rpad, A.vmax, A.velocity);
-  unsigned char* my = smem_raw + 64 * sizeof(float2) + per * (size_t)(wib * GPW + grp);
-  EnvSmem sm;
-  sm.rec = reinterpret_cast<ObstRec*>(my);
-  sm.verts = reinterpret_cast<float2*>(my + RROUND * sizeof(ObstRec));
-  sm.sdist = reinterpret_cast<float*>(my + RROUND * sizeof(ObstRec) + (size_t)A.vmax * sizeof(float2));
-  sm.sslot = A.velocity ? reinterpret_cast<uint8_t*>(sm.sdist + rpad) : nullptr;
-  int e = A.e0 + ((blockIdx.x * AUV_LIDAR_WARPS + wib) * GPW + grp) * AUV_LIDAR_EPG;
-  if (e >= A.e1) return;  // the whole group leaves together: every sync below is group-wide only
-  const int eend = min(e + AUV_LIDAR_EPG, A.e1);
-  LidarFetch<G> cur, nxt;
-  lidar_fetch<G>(A.cfg, A.batch, e, sub, cur);
-  for (; e < eend; ++e) {
-    if (e + 1 < eend) lidar_fetch<G>(A.cfg, A.batch, e + 1, sub, nxt);  // in flight while env e is cast
-    lidar_env<COUNT, G>(A, sm, s_unit, rpad, e, lane, gm, cur);
-    cur = nxt;
-  }
+#undef HAND
 }
 
 // ------------------------------------------------------------------------------------
@@ -1185,6 +1281,8 @@ int auv_sizeof(int which) {
     case 4: return (int)sizeof(AuvBatch);
     case 5: return (int)sizeof(AuvStepOut);
     case 6: return (int)sizeof(AuvGenParams);
+    case 7: return (int)sizeof(AuvPathHdr);
+    case 8: return (int)sizeof(AuvRefreshScratch);
     default: return AUV_EINVAL;
   }
 }
@@ -1329,12 +1427,12 @@ static int lidar_configure(size_t smem) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
   if (smem <= g_lidar_smem_configured[dev].load(std::memory_order_acquire)) return 0;
-  if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_lidar<false, AUV_LIDAR_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                          "cudaFuncSetAttribute(k_lidar)"))
-    return rc;
-  if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_lidar<true, AUV_LIDAR_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                          "cudaFuncSetAttribute(k_lidar)"))
-    return rc;
+  const void* fns[4] = {(const void*)auv::k_lidar<false, false>, (const void*)auv::k_lidar<true, false>,
+                        (const void*)auv::k_lidar<false, true>, (const void*)auv::k_lidar<true, true>};
+  for (int i = 0; i < 4; ++i)
+    if (int rc = cuda_check(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(k_lidar)"))
+      return rc;
   size_t seen = g_lidar_smem_configured[dev].load(std::memory_order_relaxed);
   while (seen < smem && !g_lidar_smem_configured[dev].compare_exchange_weak(seen, smem, std::memory_order_release)) {
   }
@@ -1342,10 +1440,16 @@ static int lidar_configure(size_t smem) {
 }
 static int lidar_vmax(const AuvScenarioPool* pool) { return pool->n_world > 0 ? AUV_MAX_POLY_VERTS : 16; }
 static int lidar_velocity(const AuvConfig* cfg) { return cfg->use_lidar && cfg->velocity_mode == AUV_VELOCITY_NEAREST; }
+static int lidar_rpad(const AuvConfig* cfg) { return cfg->use_lidar ? ((cfg->n_sensors + 31) & ~31) : 32; }
+// envs per CTA: 32 unless the range rows would not leave room for several CTAs per SM
+static int lidar_envs_per_cta(const AuvConfig* cfg) {
+  int e = AUV_LIDAR_MAX_ENVS;
+  const size_t row = (size_t)lidar_rpad(cfg) * (lidar_velocity(cfg) ? 8 : 4);
+  while (e > 1 && row * e > 40 * 1024) e >>= 1;
+  return e;
+}
 static size_t lidar_smem_bytes(const AuvConfig* cfg, const AuvScenarioPool* pool) {
-  const int rpad = cfg->use_lidar ? ((cfg->n_sensors + 31) & ~31) : 32;
-  return 64 * sizeof(float2) +
-         auv::lidar_smem_per_env(rpad, lidar_vmax(pool), lidar_velocity(cfg)) * AUV_LIDAR_WARPS * (32 / AUV_LIDAR_G);
+  return auv::lidar_smem_bytes_for(lidar_envs_per_cta(cfg), lidar_rpad(cfg), lidar_vmax(pool), lidar_velocity(cfg));
 }
 
 static int launch_lidar(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
@@ -1363,8 +1467,8 @@ static int launch_lidar(const AuvConfig* cfg, const AuvRayTable* rays, const Auv
   args.obs_dim = auv_obs_dim(cfg);
   args.e0 = e0;
   args.e1 = e0 + cnt;
+  args.envs_per_cta = lidar_envs_per_cta(cfg);
   args.vmax = lidar_vmax(pool);
-  args.velocity = lidar_velocity(cfg);
   args.clear_closeness = -cfg->sensor_range * exp(-0.1 * cfg->sensor_range);
   args.pen_clear_ray = (float)(-args.clear_closeness);
   args.inv_log_range = (float)(1.0 / log1p(cfg->sensor_range));
@@ -1372,12 +1476,13 @@ static int launch_lidar(const AuvConfig* cfg, const AuvRayTable* rays, const Auv
   args.feas_width = cfg->vessel_width * cfg->feasibility_width_multiplier;
   const size_t smem = lidar_smem_bytes(cfg, pool);
   if (int rc = lidar_configure(smem)) return rc;
-  const int per_cta = AUV_LIDAR_WARPS * (32 / AUV_LIDAR_G) * AUV_LIDAR_EPG;
-  const int blocks = (cnt + per_cta - 1) / per_cta;
-  if (out->seg_tests != nullptr)
-    auv::k_lidar<true, AUV_LIDAR_G><<<blocks, AUV_LIDAR_WARPS * 32, smem, (cudaStream_t)stream>>>(args);
-  else
-    auv::k_lidar<false, AUV_LIDAR_G><<<blocks, AUV_LIDAR_WARPS * 32, smem, (cudaStream_t)stream>>>(args);
+  const int blocks = (cnt + args.envs_per_cta - 1) / args.envs_per_cta;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool count = out->seg_tests != nullptr, vel = lidar_velocity(cfg) != 0;
+  if (count && vel) auv::k_lidar<true, true><<<blocks, AUV_LIDAR_THREADS, smem, s>>>(args);
+  else if (count) auv::k_lidar<true, false><<<blocks, AUV_LIDAR_THREADS, smem, s>>>(args);
+  else if (vel) auv::k_lidar<false, true><<<blocks, AUV_LIDAR_THREADS, smem, s>>>(args);
+  else auv::k_lidar<false, false><<<blocks, AUV_LIDAR_THREADS, smem, s>>>(args);
   return cuda_check(cudaGetLastError(), "k_lidar");
 }
 
@@ -1712,7 +1817,7 @@ int auv_generate_moving_obstacles(const AuvGenParams* gp, const AuvPathBank* pat
   const int threads = 128;
   const long long blocks = (total + threads - 1) / threads;
   auv::k_generate_moving_obstacles<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*gp, *paths, *pool, ids, n_ids,
-                                                                                          status);
+                                                                                          nullptr, status);
   return cuda_check(cudaGetLastError(), "k_generate_moving_obstacles");
 }
 
@@ -1770,6 +1875,55 @@ int auv_obstacle_state(const AuvConfig* cfg, const AuvScenarioPool* pool, const 
   auv::k_obstacle_state<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(*cfg, *pool, *batch, pos,
                                                                                                          disp, counter);
   return cuda_check(cudaGetLastError(), "k_obstacle_state");
+}
+
+// first observation of the listed scenarios -> pool.reset_* (at most worker->n_envs per call)
+static int reset_cache_fill(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                            const AuvScenarioPool* pool, AuvBatch* worker, AuvStepOut* wout, const int32_t* ids, int first,
+                            int n, const int32_t* n_dev, void* stream) {
+  if (n <= 0 || n > worker->n_envs) return set_err(AUV_EINVAL, "n must be in 1..worker.n_envs");
+  if (!pool->reset_obs || !pool->reset_max_progress || (cfg->use_lidar && !pool->reset_mask))
+    return set_err(AUV_EINVAL, "pool.reset_* is NULL");
+  if (int rc = check_observe_args(cfg, rays, paths, pool, worker, wout, AUV_OBSERVE_RESET)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int wn = worker->n_envs, threads = 128;
+  auv::k_worker_fill<<<(wn + threads - 1) / threads, threads, 0, s>>>(*worker, ids, first, n, n_dev);
+  if (int rc = cuda_check(cudaGetLastError(), "k_worker_fill")) return rc;
+  if (int rc = auv_reset(cfg, pool, worker, nullptr, stream)) return rc;
+  if (int rc = auv_observe(cfg, rays, paths, pool, worker, wout, AUV_OBSERVE_RESET, stream)) return rc;
+  auv::k_cache_scatter<<<(n * 32 + threads - 1) / threads, threads, 0, s>>>(*pool, *worker, wout->obs, auv_obs_dim(cfg),
+                                                                          cfg->use_lidar, n, n_dev);
+  return cuda_check(cudaGetLastError(), "k_cache_scatter");
+}
+
+int auv_reset_cache_fill(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                         const AuvScenarioPool* pool, AuvBatch* worker, AuvStepOut* worker_out, const int32_t* ids,
+                         int first, int n, void* stream) {
+  if (!cfg || !paths || !pool || !worker || !worker_out) return set_err(AUV_EINVAL, "NULL argument");
+  if (!ids && (first < 0 || first + n > pool->n_scenarios)) return set_err(AUV_EINVAL, "scenario range out of bounds");
+  return reset_cache_fill(cfg, rays, paths, pool, worker, worker_out, ids, first, n, nullptr, stream);
+}
+
+int auv_refresh_finished(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                         const AuvScenarioPool* pool, const AuvBatch* live, AuvBatch* worker, AuvStepOut* worker_out,
+                         const AuvRefreshScratch* rs, const AuvGenParams* gp, void* stream) {
+  if (!cfg || !paths || !pool || !live || !worker || !worker_out || !rs || !gp) return set_err(AUV_EINVAL, "NULL argument");
+  if (!rs->seen_episode || !rs->ids || !rs->count || rs->capacity <= 0 || rs->capacity > worker->n_envs)
+    return set_err(AUV_EINVAL, "refresh scratch: NULL array or capacity not in 1..worker.n_envs");
+  if (pool->n_scenarios != 2 * (live->reset_stride > 0 ? live->reset_stride : live->n_envs))
+    return set_err(AUV_EINVAL, "refresh needs a pool of exactly 2 * reset_stride (default n_envs) scenarios");
+  if (pool->n_world > 0) return set_err(AUV_ENOTSUP, "scenario generation with a shared land-polygon world");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int threads = 128;
+  if (int rc = cuda_check(cudaMemsetAsync(rs->count, 0, sizeof(int32_t), s), "memset")) return rc;
+  auv::k_refresh_collect<<<(live->n_envs + threads - 1) / threads, threads, 0, s>>>(*live, pool->n_scenarios, rs->seen_episode,
+                                                                                    rs->ids, rs->count, rs->capacity);
+  if (int rc = cuda_check(cudaGetLastError(), "k_refresh_collect")) return rc;
+  const long long total = (long long)rs->capacity * (pool->k_moving + pool->k_static + 1);
+  auv::k_generate_moving_obstacles<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
+      *gp, *paths, *pool, rs->ids, rs->capacity, rs->count, live->status);
+  if (int rc = cuda_check(cudaGetLastError(), "k_generate_moving_obstacles")) return rc;
+  return reset_cache_fill(cfg, rays, paths, pool, worker, worker_out, rs->ids, 0, rs->capacity, rs->count, stream);
 }
 
 int auv_fma_probe(float* sink, int blocks, int threads, int iters, void* stream, double* flops_out) {

@@ -152,6 +152,45 @@ struct PathTabs {
 #else
 #define AUV_NAVIGATE_INLINE __forceinline__
 #endif
+// Upper bound of the distance without a previous segment (first step of an episode): pass A over
+// the superblock capsules, pass B over the block capsules of the superblocks that survive it.
+// Cold: kept out of line so that the hot path of the kernel stays small (the step kernel is
+// instruction-cache bound otherwise: 130 KB of SASS before this split).
+template <int G>
+__device__ __noinline__ float project_cold_bound(const PathTabs& T, const int nblk, const int nsb, const float qx,
+                                                 const float qy, const float pad, const int lane, const unsigned gm) {
+  constexpr int KB = AUV_PATH_SUPER / G;
+  const int sub = lane & (G - 1);
+  const float up = 1.f + 4e-6f, dn2 = (1.f - 4e-6f) * (1.f - 4e-6f);
+  float ub = INFINITY;
+#define AUV_TIGHTEN(d2, dv)                                         \
+  if ((d2) < ub * ub) ub = fminf(ub, sqrtf(d2) * up + (dv) + pad);
+#define AUV_PRUNED(d2, dv) ((d2) * dn2 > (ub + (dv) + pad) * (ub + (dv) + pad))
+  for (int g0 = 0; g0 < nsb; g0 += G) {
+    const int i = min(g0 + sub, nsb - 1);
+    const float2 ax = T.sba[i];
+    const float d2 = pt_chord_d2_f(qx, qy, T.sbc[i], ax.x);
+    AUV_TIGHTEN(d2, ax.y)
+  }
+  ub = group_min<G>(gm, ub);
+  for (int sb = 0; sb < nsb; ++sb) {
+    const float2 a0 = T.sba[sb];
+    if (AUV_PRUNED(pt_chord_d2_f(qx, qy, T.sbc[sb], a0.x), a0.y)) continue;  // uniform in the group
+    const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
+#pragma unroll 1
+    for (int k = 0; k < KB; ++k) {
+      const int i = min(sb * AUV_PATH_SUPER + k * G + sub, be - 1);
+      const float2 ax = T.aux[i];
+      const float d2 = pt_chord_d2_f(qx, qy, T.chord[i], ax.x);
+      AUV_TIGHTEN(d2, ax.y)
+    }
+    ub = group_min<G>(gm, ub);
+  }
+#undef AUV_TIGHTEN
+#undef AUV_PRUNED
+  return ub;
+}
+
 template <int G>
 __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const AuvPathHdr& h, const PathTabs& T,
                                                    const double px, const double py, const int prev_seg,
@@ -185,23 +224,7 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
     for (int o = G / 2; o > 0; o >>= 1) d2 = fmin(d2, __shfl_xor_sync(gm, d2, o));
     ub = sqrtf((float)d2) * up + pad;
   } else {
-    // pass A: upper bound over the superblocks
-    for (int g0 = 0; g0 < nsb; g0 += 4 * G) {  // four rounds of loads in flight
-      float4 ch[4];
-      float2 ax[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = min(g0 + k * G + sub, nsb - 1);
-        ch[k] = sbc[i];
-        ax[k] = sba[i];
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float d2 = pt_chord_d2_f(qx, qy, ch[k], ax[k].x);
-        AUV_TIGHTEN(d2, ax[k].y)
-      }
-    }
-    ub = group_min<G>(gm, ub);
+    ub = project_cold_bound<G>(T, nblk, nsb, qx, qy, pad, lane, gm);  // first step of an episode: out of line
   }
   double best_d2 = INFINITY;
   int best_seg = 0x7fffffff;
@@ -215,37 +238,6 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
       const int i = min(w0 + t, nsb - 1);
       const float2 a0 = sba[i];
       live |= group_ballot<G>(gm, lane, t < wn && !AUV_PRUNED(pt_chord_d2_f(qx, qy, sbc[i], a0.x), a0.y)) << (k * G);
-    }
-    if (!warm) {
-      // pass B: tighten over the blocks of the surviving superblocks
-      for (unsigned rest = live; rest;) {
-        const int t = __ffs(rest) - 1;
-        rest &= rest - 1;
-        const int sb = w0 + t;
-        const float2 a0 = sba[sb];
-        if (AUV_PRUNED(pt_chord_d2_f(qx, qy, sbc[sb], a0.x), a0.y)) {  // ub has tightened since
-          live &= ~(1u << t);
-          continue;
-        }
-        const int be = min(nblk, (sb + 1) * AUV_PATH_SUPER);
-#pragma unroll
-        for (int k0 = 0; k0 < KB; k0 += KBB) {
-          float4 ch[KBB];
-          float2 ax[KBB];
-#pragma unroll
-          for (int k = 0; k < KBB; ++k) {
-            const int i = min(sb * AUV_PATH_SUPER + (k0 + k) * G + sub, be - 1);
-            ch[k] = chord[i];
-            ax[k] = aux[i];
-          }
-#pragma unroll
-          for (int k = 0; k < KBB; ++k) {
-            const float d2 = pt_chord_d2_f(qx, qy, ch[k], ax[k].x);
-            AUV_TIGHTEN(d2, ax[k].y)
-          }
-        }
-        ub = group_min<G>(gm, ub);
-      }
     }
     // pass C: exact refine of the blocks that can still hold the minimum
     for (unsigned rest = live; rest;) {

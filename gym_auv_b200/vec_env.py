@@ -128,6 +128,7 @@ class AUVVecEnv:
         host_chunks: Optional[int] = None,
         velocity_mode: str = "zero",
         linear_tracks="auto",
+        reset_stride: int = 0,
         _shared: Optional[dict] = None,
     ):
         self.device = torch.device(device)
@@ -274,8 +275,9 @@ class AUVVecEnv:
         )
         s = self._st
         sptr = lambda k: s[k].data_ptr() if k in s else None
+        self.reset_stride = int(reset_stride)
         self.batch = _lib.AuvBatch(
-            N, mw, self.env_offset, 0, s["scn_id"].data_ptr(), s["episode"].data_ptr(), s["state"].data_ptr(),
+            N, mw, self.env_offset, self.reset_stride, s["scn_id"].data_ptr(), s["episode"].data_ptr(), s["state"].data_ptr(),
             s["step_counter"].data_ptr(), s["t_step"].data_ptr(), s["cum_reward"].data_ptr(),
             s["max_progress"].data_ptr(), s["cte_sum"].data_ptr(), s["nearby_mask"].data_ptr(),
             sptr("mov_pos"), sptr("mov_disp"), sptr("mov_counter"), s["nav"].data_ptr(),
@@ -334,50 +336,43 @@ class AUVVecEnv:
         if auto_reset and _shared is None:
             self._build_reset_cache()
 
+    def _worker(self, cap: int) -> "AUVVecEnv":
+        """A batch of `cap` envs that shares this env's device tables: the scratch the reset cache is
+        computed on (auv_reset_cache_fill / auv_refresh_finished)."""
+        if not hasattr(self, "_workers"):
+            self._workers = {}
+        w = self._workers.get(cap)
+        if w is None:
+            w = self._workers[cap] = AUVVecEnv(
+                self.scenarios, cap, self.config, device=self.device, test_mode=self.test_mode, auto_reset=False,
+                cull_mode=self._cull_mode, max_nearby=self._max_nearby, velocity_mode=self._velocity_mode,
+                _shared=self._shared_tables())
+        return w
+
     def _build_reset_cache(self, ids: Optional[torch.Tensor] = None, chunk: int = 65536):
         """reset() of scenario m always returns the same observation (it depends on the
         scenario only), so it is computed once per pool scenario -- by the same kernels, over a
-        temporary batch that shares this env's device tables -- and the in-step auto-reset of a
-        finished env becomes a copy (pool.reset_obs / reset_max_progress / reset_mask).
-        ``ids``: int tensor of pool scenarios to (re)compute, default all."""
+        worker batch that shares this env's device tables (auv_reset_cache_fill) -- and the in-step
+        auto-reset of a finished env becomes a copy (pool.reset_obs / reset_max_progress /
+        reset_mask).  ``ids``: int tensor of pool scenarios to (re)compute, default all."""
         M = self.scenarios.n_scenarios
-        shared = self._shared_tables()
         total = M if ids is None else int(ids.numel())
-        if ids is not None and total <= 8192:
-            # small refreshes (refresh_finished): one cached worker batch, padded with repeats
-            cap = 1024 if total <= 1024 else 8192
-            w = self._workers.get(cap) if hasattr(self, "_workers") else None
-            if w is None:
-                if not hasattr(self, "_workers"):
-                    self._workers = {}
-                w = self._workers[cap] = AUVVecEnv(
-                    self.scenarios, cap, self.config, device=self.device, test_mode=self.test_mode, auto_reset=False,
-                    cull_mode=self._cull_mode, max_nearby=self._max_nearby, velocity_mode=self._velocity_mode,
-                    _shared=shared)
-            sel = ids.to(self.device, torch.int64)
-            padded = torch.cat([sel, sel[:1].expand(cap - total)]) if total < cap else sel
-            w._st["scn_id"].copy_(padded.to(torch.int32))
-            obs = w.reset(check=False)
-            self._pool["reset_obs"][sel] = obs[:total]
-            self._pool["reset_max_progress"][sel] = w._st["max_progress"][:total]
-            self._pool["reset_mask"][sel] = w._st["nearby_mask"][:total]
+        if total == 0:
             return
-        for start in range(0, total, chunk):
-            n = min(chunk, total - start)
-            tmp = AUVVecEnv(self.scenarios, n, self.config, device=self.device, test_mode=self.test_mode,
-                            auto_reset=False, cull_mode=self._cull_mode, env_offset=start,
-                            max_nearby=self._max_nearby, velocity_mode=self._velocity_mode, _shared=shared)
-            if ids is None:
-                sel = slice(start, start + n)
-            else:
-                sel = ids[start:start + n].to(self.device, torch.int64)
-                tmp._st["scn_id"].copy_(sel.to(torch.int32))
-            obs = tmp.reset(check=False)
-            self._pool["reset_obs"][sel] = obs
-            self._pool["reset_max_progress"][sel] = tmp._st["max_progress"]
-            self._pool["reset_mask"][sel] = tmp._st["nearby_mask"]
-            del tmp
-        torch.cuda.synchronize(self.device)
+        cap = 1024 if total <= 1024 else (8192 if total <= 8192 else min(chunk, 65536))
+        w = self._worker(cap)
+        idp = ids.to(self.device, torch.int32).contiguous() if ids is not None else None
+        cfg, rays, paths, pool, _ = self._refs()
+        with torch.cuda.device(self.device):
+            for start in range(0, total, cap):
+                n = min(cap, total - start)
+                p = C.c_void_p(idp.data_ptr() + 4 * start) if idp is not None else None
+                _lib.check(self.lib.auv_reset_cache_fill(cfg, rays, paths, pool, C.byref(w.batch), C.byref(w.out), p,
+                                                         start if idp is None else 0, n, self._stream()),
+                           "auv_reset_cache_fill")
+        if cap > 8192:  # the big worker is only needed once
+            torch.cuda.synchronize(self.device)
+            self._workers.pop(cap, None)
 
     # ------------------------------------------------------------------ GPU-side scenario generation
     def gen_params(self, seed: int, epoch: int) -> "_lib.AuvGenParams":
@@ -421,9 +416,9 @@ class AUVVecEnv:
         e alternates between slots e and e + N at every reset, so the slot it is NOT running is
         free.  Every env that finished an episode since the last call gets a freshly generated
         scenario in its free slot (the one its next reset moves to).  Returns how many."""
-        N, M = self.num_envs, self.scenarios.n_scenarios
-        if M != 2 * N or self.env_offset != 0:
-            raise ValueError("refresh_finished needs a pool of exactly 2 * num_envs scenarios and env_offset 0")
+        N, M = self.reset_stride or self.num_envs, self.scenarios.n_scenarios
+        if M != 2 * N:
+            raise ValueError("refresh_finished needs a pool of exactly 2 * reset_stride (default num_envs) scenarios")
         ep = self._st["episode"]
         if getattr(self, "_seen_episode", None) is None:
             self._seen_episode = torch.zeros_like(ep)
@@ -435,6 +430,35 @@ class AUVVecEnv:
         free = (self._st["scn_id"][changed].to(torch.int64) + N) % M
         self._gen_epoch += 1
         return self.regenerate_scenarios(free, seed=seed, epoch=self._gen_epoch)
+
+    def refresh_finished_device(self, seed: int = 0, capacity: int = 4096):
+        """``refresh_finished`` without a host round trip (auv_refresh_finished): collecting the envs
+        that finished, generating fresh scenarios into the slots they vacated and recomputing those
+        slots' cached first observation are all enqueued on the current stream -- nothing is read back,
+        so it can sit inside a training loop (the reference draws a new scenario in every reset()).
+        At most ``capacity`` slots per call; the rest are picked up by the next call."""
+        N, M = self.num_envs, self.scenarios.n_scenarios
+        if M != 2 * (self.reset_stride or N):
+            raise ValueError("refresh_finished_device needs a pool of exactly 2 * reset_stride (default num_envs) scenarios")
+        capacity = int(min(capacity, 65536))
+        rs = getattr(self, "_refresh", None)
+        if rs is None or rs["cap"] != capacity:
+            dev = self.device
+            # episode counters seen so far: envs that finished before the first call are not listed again
+            rs = self._refresh = dict(
+                cap=capacity, seen=self._st["episode"].clone(), ids=torch.zeros(capacity, dtype=torch.int32, device=dev),
+                count=torch.zeros(1, dtype=torch.int32, device=dev), epoch=getattr(self, "_gen_epoch", 1))
+            rs["struct"] = _lib.AuvRefreshScratch(rs["seen"].data_ptr(), rs["ids"].data_ptr(), rs["count"].data_ptr(),
+                                                  capacity, 0)
+        w = self._worker(1024 if capacity <= 1024 else (8192 if capacity <= 8192 else 65536))
+        rs["epoch"] += 1
+        self._gen_epoch = rs["epoch"]
+        gp = self.gen_params(seed, rs["epoch"])
+        cfg, rays, paths, pool, batch = self._refs()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.auv_refresh_finished(cfg, rays, paths, pool, batch, C.byref(w.batch), C.byref(w.out),
+                                                     C.byref(rs["struct"]), C.byref(gp), self._stream()),
+                       "auv_refresh_finished")
 
     def pull_scenarios(self) -> ScenarioSet:
         """Host copy of the device pool (after regenerate_scenarios), e.g. to replay generated
@@ -614,7 +638,8 @@ class AUVVecEnv:
         kw.setdefault("host_chunks", max(1, self.host_chunks // int(n_groups)))
         return [AUVVecEnv(self.scenarios, n, self.config, device=self.device, test_mode=self.test_mode,
                           auto_reset=bool(self.cfg.auto_reset), cull_mode=self._cull_mode, env_offset=g * n,
-                          max_nearby=self._max_nearby, velocity_mode=self._velocity_mode, _shared=shared, **kw)
+                          max_nearby=self._max_nearby, velocity_mode=self._velocity_mode,
+                          reset_stride=self.reset_stride or self.num_envs, _shared=shared, **kw)
                 for g in range(int(n_groups))]
 
     def step_host_buffers(self):

@@ -203,7 +203,9 @@ typedef struct AuvBatch {
   int32_t n_envs;
   int32_t mask_words;     /* ceil((k_moving+k_static+n_world)/32), <= 32               */
   int32_t env_offset;     /* global index of env 0 (multi-GPU shards), used by reset    */
-  int32_t reserved0;
+  int32_t reset_stride;   /* a finished env moves from scenario s to (s + reset_stride) mod M;
+                             0 = n_envs.  Batches that split one env population (two groups
+                             stepped alternately) keep the stride of the whole population       */
   int32_t* scn_id;        /* [N]   scenario each env currently runs                     */
   int32_t* episode;       /* [N]   BaseEnvironment.episode                              */
   double* state;          /* [6][N] x, y, psi, u, v, r   (Vessel._state)                */
@@ -276,7 +278,8 @@ typedef struct AuvStepOut {
 
 int auv_abi_version(void);
 /* sizeof of the ABI structs, in declaration order (0 AuvConfig, 1 AuvRayTable, 2 AuvPathBank,
- * 3 AuvScenarioPool, 4 AuvBatch, 5 AuvStepOut, 6 AuvGenParams) so a binding can verify its layout. */
+ * 3 AuvScenarioPool, 4 AuvBatch, 5 AuvStepOut, 6 AuvGenParams, 7 AuvPathHdr, 8 AuvRefreshScratch) so a binding
+ * can verify its layout. */
 int auv_sizeof(int which);
 const char* auv_last_error(void);
 int auv_obs_dim(const AuvConfig* cfg);
@@ -386,6 +389,30 @@ typedef struct AuvGenParams {
  * status (device int or NULL) receives AUV_STATUS_GEN_GAVE_UP. */
 int auv_generate_moving_obstacles(const AuvGenParams* gp, const AuvPathBank* paths, const AuvScenarioPool* pool,
                                   const int32_t* ids, int n_ids, int32_t* status, void* stream);
+/* Fill the reset cache (pool.reset_obs / reset_max_progress / reset_mask) of n <= worker->n_envs
+ * scenarios -- ids[0..n) (device array) or first..first+n-1 when ids is NULL -- by running
+ * reset() + the first observe() (environment.py:176-245) for them on a caller-owned WORKER batch
+ * (any AuvBatch / AuvStepOut of at least n envs sharing the pool; its contents are overwritten). */
+int auv_reset_cache_fill(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                         const AuvScenarioPool* pool, AuvBatch* worker, AuvStepOut* worker_out, const int32_t* ids,
+                         int first, int n, void* stream);
+/* Sustained fresh scenarios without a host round trip (the reference draws a new scenario in every
+ * reset(), envs/movingobstacles.py:28-95).  Pool of exactly 2 N scenarios: env e alternates between
+ * slots e and e + N at every auto-reset, so the slot it is NOT running is free.  One call, all on
+ * `stream`: every env whose episode counter moved since the last call lists the slot it vacated
+ * (at most `capacity` per call, the rest next time), those slots get freshly generated scenarios
+ * (auv_generate_moving_obstacles semantics, Philox streams keyed by gp->seed / gp->epoch -- bump the
+ * epoch per call) and their cached first observation is recomputed on the worker batch. */
+typedef struct AuvRefreshScratch {
+  int32_t* seen_episode; /* [N] episode counter of each env at the last call (zero-initialised)   */
+  int32_t* ids;          /* [capacity] pool slots being regenerated (zero-initialised)            */
+  int32_t* count;        /* [1]                                                                   */
+  int32_t capacity;      /* <= worker->n_envs                                                     */
+  int32_t reserved0;
+} AuvRefreshScratch;
+int auv_refresh_finished(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                         const AuvScenarioPool* pool, const AuvBatch* live, AuvBatch* worker, AuvStepOut* worker_out,
+                         const AuvRefreshScratch* rs, const AuvGenParams* gp, void* stream);
 /* Host helper (no GPU work): first wrap and wrap period, in updates, of a constant-velocity
  * VesselObstacle track (obstacles.py:195-215: counter += dt; floor(counter) >= vel_len - 1 wraps the
  * counter to 0 and the position to the track start).  counter0 = waypoint counter right after

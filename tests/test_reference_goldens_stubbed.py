@@ -152,7 +152,7 @@ def test_rewarders_match_reference_classes():
         speed, yaw, cte, he, prog, maxprog, collision = row[:7]
         v = types.SimpleNamespace(
             collision=bool(collision), nav=dict(cross_track_error=cte, heading_error=he), speed=speed,
-            n_sensors=R, sensor_angles=angles, dists=row[7:], cfg=dict(sensor_range=150.0), progress=prog,
+            n_sensors=R, sensor_angles=angles, dists=row[7:], speeds=np.zeros((2, R)), cfg=dict(sensor_range=150.0), progress=prog,
             max_progress=maxprog, state=np.array([0, 0, 0, 0, 0, yaw]))
         assert abs(O.colav_reward(v) - want_c) <= 1e-9 * max(1.0, abs(want_c))
         assert abs(O.pathfollow_reward(v) - want_p) <= 1e-9 * max(1.0, abs(want_p))
