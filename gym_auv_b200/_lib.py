@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
-ABI_VERSION = 17
+ABI_VERSION = 18
 REC_BYTES = 80
 MAX_POLY_VERTS = 192
 STATUS_REC_OVERFLOW = 1
@@ -82,7 +82,7 @@ class AuvPathHdr(C.Structure):
         ("length", C.c_double),
         ("end_x", C.c_double),
         ("end_y", C.c_double),
-        ("reserved", C.c_double),
+        ("extent", C.c_double),
     ]
 
 
@@ -93,6 +93,7 @@ class AuvPathBank(C.Structure):
         ("hdr", _vp),
         ("poly_xy", _vp),
         ("poly_cum", _vp),
+        ("poly_f32", _vp),
         ("blk_chord", _vp),
         ("blk_dev", _vp),
         ("sb_chord", _vp),
@@ -160,6 +161,7 @@ class AuvBatch(C.Structure):
         ("obst_steps", _vp),
         ("prev_seg", _vp),
         ("env_pid", _vp),
+        ("obs_nz", _vp),
     ]
 
 
@@ -205,6 +207,10 @@ class AuvRefreshScratch(C.Structure):
     _fields_ = [("seen_episode", _vp), ("ids", _vp), ("count", _vp), ("capacity", C.c_int32), ("reserved0", C.c_int32)]
 
 
+class AuvCompact(C.Structure):
+    _fields_ = [("head", _vp), ("mask", _vp), ("vals", _vp), ("counter", _vp), ("words", C.c_int32), ("capacity", C.c_int32)]
+
+
 EXPORTS = [
     "auv_abi_version",
     "auv_sizeof",
@@ -234,6 +240,8 @@ EXPORTS = [
     "auv_obstacle_state",
     "auv_reset_cache_fill",
     "auv_refresh_finished",
+    "auv_step_host_compact_submit",
+    "auv_compact_expand",
 ]
 
 _lib = None
@@ -297,6 +305,11 @@ def load():
                                          P(AuvStepOut), _vp, C.c_int, C.c_int, _vp]
     lib.auv_refresh_finished.argtypes = [P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch),
                                          P(AuvBatch), P(AuvStepOut), P(AuvRefreshScratch), P(AuvGenParams), _vp]
+    lib.auv_step_host_compact_submit.argtypes = [
+        P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, _vp, P(AuvStepOut),
+        P(AuvCompact), _vp, _vp, _vp, _vp, C.c_int,
+    ]
+    lib.auv_compact_expand.argtypes = [P(AuvConfig), C.c_int, P(AuvCompact), _vp, _vp, C.c_int]
     lib.auv_timer_create.argtypes = [C.c_int]
     lib.auv_timer_create.restype = _vp
     lib.auv_timer_destroy.argtypes = [_vp]

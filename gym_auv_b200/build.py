@@ -16,7 +16,7 @@ OUT = os.path.join(HERE, "libauv_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC,-fopenmp", "-lgomp",
 ]
 
 

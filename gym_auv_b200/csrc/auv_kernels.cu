@@ -989,18 +989,45 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
                             : (const void*)(reinterpret_cast<const float*>(sm.sdist) + (size_t)el * rpad);
       float extra = 0.f;
       bool collision = false;
-      if (cnt > 0) {
+      // which 64-ray groups of the row hold a non-zero closeness (bit = lane of the float2 pair): groups that
+      // are and were all zero are neither computed nor stored
+      unsigned* nzrow = (batch.obs_nz != nullptr && vec2 && !vel_obs) ? batch.obs_nz + (long long)e * (2 * ((R + 63) / 64)) : nullptr;
+      if (cnt > 0 || nzrow != nullptr) {
         const double cpsi = HAND(el, NAV_COSPSI), spsi = HAND(el, NAV_SINPSI);
         const ObstRec* grec = reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
-        for (int k = lane; k < (R + 1) / 2; k += 32) {
+        for (int k0 = 0; k0 < (R + 1) / 2; k0 += 32) {
+          const int k = k0 + lane;
+          const int j = k0 >> 5;
           float cl2[2] = {0.f, 0.f};
+          bool hit[2] = {false, false};
+          float dd[2] = {rangef, rangef};
+          if (cnt > 0 && k < (R + 1) / 2) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = 2 * k + h;
+              if (i < R) {
+                dd[h] = range_get<VEL>(row, i);
+                hit[h] = dd[h] < rangef;
+              }
+            }
+          }
+          const unsigned m0 = __ballot_sync(AUV_FULL, hit[0]), m1 = __ballot_sync(AUV_FULL, hit[1]);
+          if (nzrow != nullptr) {
+            const unsigned p0 = nzrow[2 * j], p1 = nzrow[2 * j + 1];  // warp-uniform
+            if ((m0 | m1 | p0 | p1) == 0u) continue;               // nothing there, nothing was there
+            if (lane == 0 && (m0 != p0 || m1 != p1)) {
+              nzrow[2 * j] = m0;
+              nzrow[2 * j + 1] = m1;
+            }
+          }
+          if (k >= (R + 1) / 2) continue;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int i = 2 * k + h;
             if (i >= R) continue;
-            const float d = range_get<VEL>(row, i);
+            const float d = dd[h];
             float vxr = 0.f, vyr = 0.f;
-            if (d < rangef) {
+            if (hit[h]) {
               if (cfg.sensor_log_transform)  // log(1 + d) by the hardware log2: |error| < 1e-6 of a value in [0, 5]
                 cl2[h] = 1.f - fminf(fmaxf(__logf(1.f + d) * A.inv_log_range, 0.f), 1.f);
               else
@@ -1210,6 +1237,18 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
       if (tobs) tobs[k] = obs[k];
       obs[k] = robs[k];
     }
+    if (batch.obs_nz != nullptr && cfg.use_lidar) {  // non-zero pattern of the row that was just copied in
+      unsigned* nzrow = batch.obs_nz + (long long)e * (2 * ((R + 63) / 64));
+      for (int k0 = 0; k0 < (R + 1) / 2; k0 += 32) {
+        const int k = k0 + lane;
+        const bool z0 = 2 * k < R && robs[6 + 2 * k] != 0.f, z1 = 2 * k + 1 < R && robs[6 + 2 * k + 1] != 0.f;
+        const unsigned m0 = __ballot_sync(AUV_FULL, z0), m1 = __ballot_sync(AUV_FULL, z1);
+        if (lane == 0) {
+          nzrow[2 * (k0 >> 5)] = m0;
+          nzrow[2 * (k0 >> 5) + 1] = m1;
+        }
+      }
+    }
     if (!A.pool.linear_tracks)
       for (int j = lane; j < km; j += 32) {
         const long long ps = (long long)next * km + j, pe = (long long)e * km + j;
@@ -1222,6 +1261,84 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
         batch.nearby_mask[(long long)e * batch.mask_words + w] = A.pool.reset_mask[(long long)next * batch.mask_words + w];
   }
 #undef HAND
+}
+
+// ------------------------------------------------------------------------------------
+// k_obs_ship: lossless compact transfer of a step's results to the host.  ~85 % of the closeness
+// block of an observation is exactly 0 (clear rays), and the dense [N][6 + R] float rows are what
+// bounds the host-buffer step (49 MB per 65536 envs over PCIe).  One CTA per 32 envs turns its rows
+// into: a 32 B head per env (obs[0..5], count, offset), the hit mask (one bit per ray) and the
+// non-zero values packed back to back -- and writes all three, plus reward / done, STRAIGHT into
+// pinned host memory with coalesced stores (the packed block of a CTA is contiguous and 128 B
+// aligned): the kernel's own stores are the transfer, its exact size is decided on the device,
+// and the whole step stays one replayable CUDA graph.  auv_compact_expand scatters on the host.
+// ------------------------------------------------------------------------------------
+#define AUV_SHIP_THREADS 256
+#define AUV_SHIP_ENVS 32
+__global__ void __launch_bounds__(AUV_SHIP_THREADS) k_obs_ship(const float* __restrict__ obs, int obs_dim, int R, int words,
+                                                              int e0, int e1, const float* __restrict__ reward,
+                                                              const uint8_t* __restrict__ done, float* __restrict__ head_h,
+                                                              uint32_t* __restrict__ mask_h, float* __restrict__ vals_h,
+                                                              int* __restrict__ counter, int capacity,
+                                                              float* __restrict__ reward_h, uint8_t* __restrict__ done_h) {
+  extern __shared__ __align__(16) unsigned char ship_smem[];
+  const int rpad = words * 32;
+  float* s_vals = reinterpret_cast<float*>(ship_smem);                       // [E][rpad] packed per env
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_vals + AUV_SHIP_ENVS * rpad);  // [E][words]
+  int* s_off = reinterpret_cast<int*>(s_mask + AUV_SHIP_ENVS * words);       // [E + 1]
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int env0 = e0 + blockIdx.x * AUV_SHIP_ENVS;
+  const int ne = min(AUV_SHIP_ENVS, e1 - env0);
+  // ---- pack: warp per env
+  for (int el = warp; el < ne; el += AUV_SHIP_THREADS / 32) {
+    const float* row = obs + (long long)(env0 + el) * obs_dim + 6;
+    int run = 0;
+    for (int w = 0; w < words; ++w) {
+      const int i = w * 32 + lane;
+      const float v = i < R ? row[i] : 0.f;
+      const unsigned m = __ballot_sync(AUV_FULL, v != 0.f);
+      if (v != 0.f) s_vals[el * rpad + run + __popc(m & ((1u << lane) - 1u))] = v;
+      if (lane == 0) s_mask[el * words + w] = m;
+      run += __popc(m);
+    }
+    if (lane == 0) s_off[el + 1] = run;  // counts for now
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the counts; one reservation per CTA, padded to 32 floats (128 B)
+    const int c = lane < ne ? s_off[lane + 1] : 0;
+    const int incl = warp_incl_scan(c, lane);
+    __syncwarp();
+    s_off[lane + 1] = incl;
+    if (lane == 0) s_off[0] = 0;
+    const int total = __shfl_sync(AUV_FULL, incl, 31);
+    if (lane == 0) s_base = total > 0 ? atomicAdd(counter, (total + 31) & ~31) : 0;
+  }
+  __syncthreads();
+  const int base = s_base, total = s_off[ne];
+  // ---- ship: head, mask, reward, done (contiguous per CTA), packed values (flat, coalesced)
+  for (int k = tid; k < ne * 8; k += AUV_SHIP_THREADS) {
+    const int el = k >> 3, f = k & 7;
+    float v;
+    if (f < 6) v = obs[(long long)(env0 + el) * obs_dim + f];
+    else if (f == 6) v = __int_as_float(s_off[el + 1] - s_off[el]);
+    else v = __int_as_float(base + s_off[el]);
+    head_h[(long long)env0 * 8 + k] = v;
+  }
+  for (int k = tid; k < ne * words; k += AUV_SHIP_THREADS) mask_h[(long long)env0 * words + k] = s_mask[k];
+  if (tid < ne) {
+    reward_h[env0 + tid] = reward[env0 + tid];
+    done_h[env0 + tid] = done[env0 + tid];
+  }
+  if (base + total <= capacity)
+    for (int k = tid; k < total; k += AUV_SHIP_THREADS) {
+      int lo = 0, hi = ne - 1;  // env of packed value k: last env with off <= k
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_off[mid] <= k) lo = mid; else hi = mid - 1;
+      }
+      vals_h[base + k] = s_vals[lo * rpad + (k - s_off[lo])];
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -1610,16 +1727,40 @@ static int step_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const Auv
 // leave on the pipeline's copy stream as soon as each range is done, so the link is busy from
 // the end of the first range to the end of the step (the step is bound by the D2H of the
 // observations: ~49 MB per step at 65536 envs x 186 floats)
+static int launch_obs_ship(const AuvConfig* cfg, const AuvStepOut* out, const AuvCompact* cb, float* reward_host,
+                           uint8_t* done_host, int e0, int cnt, cudaStream_t s) {
+  const int R = cfg->use_lidar ? cfg->n_sensors : 0;
+  const int words = cb->words;
+  const size_t smem = (size_t)AUV_SHIP_ENVS * words * 32 * 4 + (size_t)AUV_SHIP_ENVS * words * 4 + (AUV_SHIP_ENVS + 1) * 4 + 16;
+  static std::atomic<size_t> configured[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (smem > 48 * 1024 && smem > configured[dev].load()) {
+    if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_obs_ship, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(k_obs_ship)"))
+      return rc;
+    configured[dev].store(smem);
+  }
+  const int blocks = (cnt + AUV_SHIP_ENVS - 1) / AUV_SHIP_ENVS;
+  auv::k_obs_ship<<<blocks, AUV_SHIP_THREADS, smem, s>>>(out->obs, auv_obs_dim(cfg), R, words, e0, e0 + cnt, out->reward, out->done,
+                                                        cb->head, cb->mask, cb->vals, cb->counter, cb->capacity, reward_host,
+                                                        done_host);
+  return cuda_check(cudaGetLastError(), "k_obs_ship");
+}
+
 static int enqueue_host_step(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                              const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
                              float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
-                             uint8_t* done_host, cudaStream_t s, cudaStream_t ds, AuvPipeline* p, int n_chunks) {
+                             uint8_t* done_host, cudaStream_t s, cudaStream_t ds, AuvPipeline* p, int n_chunks,
+                             const AuvCompact* cb = nullptr) {
   const int n = batch->n_envs;
   const int cs = chunk_size(n, n_chunks);
   const size_t od = (size_t)auv_obs_dim(cfg);
   if (int rc = cuda_check(cudaMemcpyAsync(actions_dev, actions_host, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, s),
                           "H2D actions"))
     return rc;
+  if (cb != nullptr)
+    if (int rc = cuda_check(cudaMemsetAsync(cb->counter, 0, sizeof(int32_t), s), "compact counter")) return rc;
   for (int c = 0, e0 = 0; e0 < n; ++c, e0 += cs) {
     const int cnt = n - e0 < cs ? n - e0 : cs;
     if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, actions_dev, (void*)s, e0, cnt, true)) return rc;
@@ -1628,15 +1769,19 @@ static int enqueue_host_step(const AuvConfig* cfg, const AuvRayTable* rays, cons
       if (int rc = cuda_check(cudaEventRecord(p->chunk[c], s), "range done")) return rc;
       if (int rc = cuda_check(cudaStreamWaitEvent(ds, p->chunk[c], 0), "copy stream wait")) return rc;
     }
-    if (int rc = cuda_check(cudaMemcpyAsync(obs_host + od * e0, out->obs + od * e0, (size_t)cnt * od * sizeof(float),
-                                            cudaMemcpyDeviceToHost, ds), "D2H obs"))
+    if (cb != nullptr) {  // compact transfer: the kernel's own stores into pinned host memory
+      if (int rc = launch_obs_ship(cfg, out, cb, reward_host, done_host, e0, cnt, ds)) return rc;
+    } else if (int rc = cuda_check(cudaMemcpyAsync(obs_host + od * e0, out->obs + od * e0, (size_t)cnt * od * sizeof(float),
+                                                   cudaMemcpyDeviceToHost, ds), "D2H obs"))
       return rc;
   }
-  if (int rc = cuda_check(cudaMemcpyAsync(reward_host, out->reward, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ds),
-                          "D2H reward"))
-    return rc;
-  if (int rc = cuda_check(cudaMemcpyAsync(done_host, out->done, (size_t)n, cudaMemcpyDeviceToHost, ds), "D2H done"))
-    return rc;
+  if (cb == nullptr) {
+    if (int rc = cuda_check(cudaMemcpyAsync(reward_host, out->reward, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ds),
+                            "D2H reward"))
+      return rc;
+    if (int rc = cuda_check(cudaMemcpyAsync(done_host, out->done, (size_t)n, cudaMemcpyDeviceToHost, ds), "D2H done"))
+      return rc;
+  }
   if (ds != s) {
     if (int rc = cuda_check(cudaEventRecord(p->join[0], ds), "join record")) return rc;
     return cuda_check(cudaStreamWaitEvent(s, p->join[0], 0), "join wait");
@@ -1653,7 +1798,8 @@ static unsigned long long fnv1a(unsigned long long h, const void* data, size_t n
 static int step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                              const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
                              float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
-                             uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks) {
+                             uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks,
+                             const AuvCompact* cb = nullptr) {
   if (!p) return set_err(AUV_EINVAL, "pipeline is NULL");
   if (n_chunks <= 0 || n_chunks > AUV_PIPE_MAX_CHUNKS) return set_err(AUV_EINVAL, "n_chunks out of range");
   if (int rc = check_observe_args(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP)) return rc;
@@ -1668,6 +1814,7 @@ static int step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, cons
     key = fnv1a(key, out, sizeof(*out));
     const void* ptrs[6] = {actions_host, actions_dev, obs_host, reward_host, done_host, (const void*)(size_t)n_chunks};
     key = fnv1a(key, ptrs, sizeof(ptrs));
+    if (cb) key = fnv1a(key, cb, sizeof(*cb));
     if (p->graph_state == 0 || key != p->gkey) {
       if (p->gexec) {
         cudaGraphExecDestroy(p->gexec);
@@ -1681,7 +1828,7 @@ static int step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, cons
       int rc = 0;
       if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
         rc = enqueue_host_step(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, obs_host, reward_host,
-                               done_host, cs, ds, p, n_chunks);
+                               done_host, cs, ds, p, n_chunks, cb);
         const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
         if (rc == 0 && ce == cudaSuccess && graph != nullptr &&
             cudaGraphInstantiate(&p->gexec, graph, 0) == cudaSuccess) {
@@ -1699,7 +1846,7 @@ static int step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, cons
     if (p->graph_state == 1) return cuda_check(cudaGraphLaunch(p->gexec, s), "cudaGraphLaunch");
   }
   return enqueue_host_step(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, obs_host, reward_host, done_host,
-                           s, ds, p, n_chunks);
+                           s, ds, p, n_chunks, cb);
 }
 
 int auv_step_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
@@ -1717,6 +1864,58 @@ int auv_step_host_submit(const AuvConfig* cfg, const AuvRayTable* rays, const Au
     return set_err(AUV_EINVAL, "NULL argument");
   return step_host_chunked(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, obs_host, reward_host,
                            done_host, stream, p, n_chunks);
+}
+
+int auv_step_host_compact_submit(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                                 const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
+                                 float* actions_dev, AuvStepOut* out, const AuvCompact* cb, float* reward_host,
+                                 uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks) {
+  if (!cfg || !batch || !out || !actions_host || !actions_dev || !cb || !reward_host || !done_host)
+    return set_err(AUV_EINVAL, "NULL argument");
+  if (!cb->head || !cb->mask || !cb->vals || !cb->counter) return set_err(AUV_EINVAL, "compact buffers are NULL");
+  if (cfg->sensor_use_velocity_observations) return set_err(AUV_ENOTSUP, "compact transfer with velocity observations");
+  const int R = cfg->use_lidar ? cfg->n_sensors : 0;
+  if (cb->words != (R + 31) / 32 || cb->words <= 0) return set_err(AUV_EINVAL, "compact.words must be ceil(n_sensors / 32) >= 1");
+  if ((long long)cb->capacity < (long long)batch->n_envs * cb->words * 32)
+    return set_err(AUV_EINVAL, "compact.capacity must be >= n_envs * words * 32");
+  return step_host_chunked(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, nullptr, reward_host, done_host,
+                           stream, p, n_chunks, cb);
+}
+
+int auv_compact_expand(const AuvConfig* cfg, int n_envs, const AuvCompact* cb, uint32_t* prev_mask, float* obs_host,
+                       int n_threads) {
+  if (!cfg || !cb || !prev_mask || !obs_host || n_envs <= 0) return set_err(AUV_EINVAL, "bad auv_compact_expand arguments");
+  const int od = auv_obs_dim(cfg), words = cb->words;
+  const float* head = cb->head;
+  const uint32_t* mask = cb->mask;
+  const float* vals = cb->vals;
+  if (n_threads < 1) n_threads = 1;
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+  for (int e = 0; e < n_envs; ++e) {
+    float* row = obs_host + (size_t)e * od;
+    const float* h = head + (size_t)e * 8;
+    for (int k = 0; k < 6; ++k) row[k] = h[k];
+    int off;
+    memcpy(&off, h + 7, sizeof(int));
+    const float* v = vals + off;
+    uint32_t* pm = prev_mask + (size_t)e * words;
+    const uint32_t* nm = mask + (size_t)e * words;
+    float* cl = row + 6;
+    for (int w = 0; w < words; ++w) {
+      uint32_t clear = pm[w] & ~nm[w];  // rays that read clear again
+      while (clear) {
+        cl[w * 32 + __builtin_ctz(clear)] = 0.f;
+        clear &= clear - 1;
+      }
+      uint32_t set = nm[w];
+      while (set) {
+        cl[w * 32 + __builtin_ctz(set)] = *v++;
+        set &= set - 1;
+      }
+      pm[w] = nm[w];
+    }
+  }
+  return 0;
 }
 
 int auv_step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,

@@ -99,6 +99,21 @@ __device__ __forceinline__ double seg_d2(double px, double py, double2 A, double
   return cr * cr / len2;
 }
 
+// FP32 squared distance from the origin-relative point (qx, qy) to segment AB (same case split)
+__device__ __forceinline__ float seg_d2_f(float qx, float qy, float2 A, float2 B) {
+  const float ex = B.x - A.x, ey = B.y - A.y;
+  const float wx = qx - A.x, wy = qy - A.y;
+  const float len2 = ex * ex + ey * ey;
+  const float num = wx * ex + wy * ey;
+  if (len2 == 0.f || num <= 0.f) return wx * wx + wy * wy;
+  if (num >= len2) {
+    const float zx = qx - B.x, zy = qy - B.y;
+    return zx * zx + zy * zy;
+  }
+  const float cr = wx * ey - wy * ex;
+  return cr * cr / len2;
+}
+
 // ---- sub-warp groups: G consecutive lanes (G = 4, 8, 16 or 32) work on one env
 template <int G>
 __device__ __forceinline__ unsigned group_mask(int lane) {
@@ -116,6 +131,9 @@ __device__ __forceinline__ unsigned group_ballot(unsigned gm, int lane, bool pre
   const unsigned b = __ballot_sync(gm, pred);
   return G == 32 ? b : ((b >> (lane & ~(G - 1))) & ((1u << G) - 1u));
 }
+
+// upper bound of |coordinate| of a path's origin-relative polyline (stored in the header's spare double)
+__device__ __forceinline__ float h_extent(const AuvPathHdr& h) { return (float)h.extent; }
 
 // capsule tables of one path: the global arrays, or the CTA's shared-memory copy of them
 struct PathTabs {
@@ -210,24 +228,29 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
   const float4* sbc = T.sbc;
   const float2* sba = T.sba;
   const double2* __restrict__ poly = reinterpret_cast<const double2*>(pb.poly_xy) + h.v0;
+  const float2* __restrict__ polyf = reinterpret_cast<const float2*>(pb.poly_f32) + h.v0;
   const float up = 1.f + 4e-6f, dn2 = (1.f - 4e-6f) * (1.f - 4e-6f);
+  // error bound of an FP32 point-segment distance on the origin-relative FP32 polyline: vertex and query
+  // rounding (half an ulp of the coordinate magnitude each) plus the arithmetic, generously
+  const float ftol = 4e-7f * (fabsf(qx) + fabsf(qy) + h_extent(h)) + 5e-5f;
   float ub = INFINITY;
 #define AUV_TIGHTEN(d2, dv)                                         \
   if ((d2) < ub * ub) ub = fminf(ub, sqrtf(d2) * up + (dv) + pad);
 #define AUV_PRUNED(d2, dv) ((d2) * dn2 > (ub + (dv) + pad) * (ub + (dv) + pad))
   const bool warm = prev_seg >= 0 && prev_seg < nseg;  // uniform in the group
   if (warm) {
-    // lanes look at segments prev-3, prev, prev+3, prev+6 (...): an actual segment's distance
+    // lanes look at segments prev-3, prev, prev+3, prev+6 (...): an actual segment's distance (FP32 copy
+    // of the polyline, padded by its error bound ftol)
     const int k = min(max(prev_seg + (sub - 1) * 3, 0), nseg - 1);
-    double d2 = seg_d2(px, py, poly[k], poly[k + 1]);
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) d2 = fmin(d2, __shfl_xor_sync(gm, d2, o));
-    ub = sqrtf((float)d2) * up + pad;
+    float d2 = seg_d2_f(qx, qy, polyf[k], polyf[k + 1]);
+    d2 = group_min<G>(gm, d2);
+    ub = sqrtf(d2) * up + ftol + pad;
   } else {
     ub = project_cold_bound<G>(T, nblk, nsb, qx, qy, pad, lane, gm);  // first step of an episode: out of line
   }
   double best_d2 = INFINITY;
   int best_seg = 0x7fffffff;
+  float fbest = INFINITY;
   // superblocks in windows of 32 (one bit each); the lanes test different superblocks
   for (int w0 = 0; w0 < nsb; w0 += 32) {
     const int wn = min(32, nsb - w0);
@@ -258,21 +281,32 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
         const int b = sb * AUV_PATH_SUPER + __ffs(cand) - 1;
         cand &= cand - 1;
         const int se = min(nseg, (b + 1) * AUV_PATH_BLOCK);
+        const int k0 = b * AUV_PATH_BLOCK + sub * KS;  // this lane's consecutive segments
+        // screen in FP32 (8 B per vertex): every segment whose FP32 distance is within the error bound of
+        // the smallest one seen can be the exact first minimum; only those are evaluated in FP64
+        float df[KS];
+        {
+          float2 v[KS + 1];
 #pragma unroll
-        for (int u0 = 0; u0 < KS; u0 += KSB) {
-          const int k0 = b * AUV_PATH_BLOCK + sub * KS + u0;  // this lane's consecutive segments
-          double2 v[KSB + 1];
+          for (int u = 0; u <= KS; ++u) v[u] = polyf[min(k0 + u, se)];
 #pragma unroll
-          for (int u = 0; u <= KSB; ++u) v[u] = poly[min(k0 + u, se)];
+          for (int u = 0; u < KS; ++u) df[u] = (k0 + u < se) ? seg_d2_f(qx, qy, v[u], v[u + 1]) : INFINITY;
+        }
+        float m = df[0];
 #pragma unroll
-          for (int u = 0; u < KSB; ++u) {
-            if (k0 + u < se) {
-              const double d2 = seg_d2(px, py, v[u], v[u + 1]);
-              // a lane's segments come in increasing order over the whole search
-              if (d2 < best_d2) {
-                best_d2 = d2;
-                best_seg = k0 + u;
-              }
+        for (int u = 1; u < KS; ++u) m = fminf(m, df[u]);
+        m = group_min<G>(gm, m);
+        fbest = fminf(fbest, sqrtf(m));  // smallest FP32 distance over all refined blocks so far (group-uniform)
+        const float lim = fbest + 2.f * ftol;
+        const float lim2 = lim * lim * up;
+#pragma unroll
+        for (int u = 0; u < KS; ++u) {
+          if (df[u] <= lim2) {
+            const double d2 = seg_d2(px, py, poly[k0 + u], poly[k0 + u + 1]);
+            // a lane's segments come in increasing order over the whole search
+            if (d2 < best_d2) {
+              best_d2 = d2;
+              best_seg = k0 + u;
             }
           }
         }

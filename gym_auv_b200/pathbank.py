@@ -28,7 +28,7 @@ PATH_SUPER = int(os.environ.get("AUV_PATH_SUPER", 16))  # blocks per superblock,
 N_KNOTS = 1000
 PP_W = 12  # AUV_PP_W
 HDR_DTYPE = np.dtype([("v0", "<i4"), ("nseg", "<i4"), ("b0", "<i4"), ("s0", "<i4"), ("ox", "<f8"), ("oy", "<f8"),
-                      ("length", "<f8"), ("end_x", "<f8"), ("end_y", "<f8"), ("reserved", "<f8")])  # AuvPathHdr
+                      ("length", "<f8"), ("end_x", "<f8"), ("end_y", "<f8"), ("extent", "<f8")])  # AuvPathHdr
 
 
 @dataclass
@@ -184,7 +184,12 @@ class PathBank:
         hdr["ox"], hdr["oy"] = self.origin[:, 0], self.origin[:, 1]
         hdr["length"] = self.length
         hdr["end_x"], hdr["end_y"] = self.end_xy[:, 0], self.end_xy[:, 1]
+        hdr["extent"] = [float(np.abs(t.poly - t.origin).sum(axis=1).max()) for t in self.tables]
         return hdr
+
+    def poly_f32_array(self) -> np.ndarray:
+        """[total_vertices, 2] float32: polyline vertices relative to their path's origin."""
+        return np.concatenate([(t.poly - t.origin).astype(np.float32) for t in self.tables], axis=0)
 
     def piece_array(self) -> np.ndarray:
         """[n_paths, n_knots - 1, 12]: knot j, knot j + 1, x c0..c3, y c0..c3, 2 unused (``AuvPathBank.pp``)."""
@@ -206,6 +211,7 @@ class PathBank:
             hdr=torch.from_numpy(self.header_array().view(np.uint8).copy()).to(device),
             poly_xy=dev(self.poly_xy, torch.float64),
             poly_cum=dev(self.poly_cum, torch.float64),
+            poly_f32=dev(self.poly_f32_array(), torch.float32),
             blk_chord=dev(self.blk_chord, torch.float32),
             blk_dev=dev(self.blk_dev, torch.float32),
             sb_chord=dev(self.sb_chord, torch.float32),

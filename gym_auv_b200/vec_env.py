@@ -105,6 +105,10 @@ class AUVVecEnv:
                 (sensor.py:100-137): per ray the displacement of the nearest hit obstacle rotated into the
                 ray frame -- it feeds ``max(0, v_y)`` of the Colav penalty (rewarder.py:199-206) and, with
                 ``sensor_use_velocity_observations``, the 2 R velocity channels of the observation
+    compact_host : step_host / step_async send the observations to the host in the lossless compact
+                form (head + hit mask + non-zero closeness values, auv_step_host_compact_submit) and expand
+                them into the dense [N, obs_dim] array with ``host_threads`` host threads; results are
+                bit-identical to the dense copy.  Falls back to dense rows with velocity observations.
     linear_tracks : "auto" (default) = pools whose moving obstacles all follow constant-velocity tracks
                 (the MovingObstacles family) are stepped with the closed form of the update and keep no
                 per-env obstacle state; False forces the general table-driven update
@@ -129,6 +133,8 @@ class AUVVecEnv:
         velocity_mode: str = "zero",
         linear_tracks="auto",
         reset_stride: int = 0,
+        compact_host: bool = True,
+        host_threads: Optional[int] = None,
         _shared: Optional[dict] = None,
     ):
         self.device = torch.device(device)
@@ -171,7 +177,7 @@ class AUVVecEnv:
         b = self._bank
         self.paths = _lib.AuvPathBank(
             bank.n_paths, bank.knots.shape[1], b["hdr"].data_ptr(), b["poly_xy"].data_ptr(), b["poly_cum"].data_ptr(),
-            b["blk_chord"].data_ptr(), b["blk_dev"].data_ptr(), b["sb_chord"].data_ptr(), b["sb_dev"].data_ptr(),
+            b["poly_f32"].data_ptr(), b["blk_chord"].data_ptr(), b["blk_dev"].data_ptr(), b["sb_chord"].data_ptr(), b["sb_dev"].data_ptr(),
             b["pp"].data_ptr(),
         )
 
@@ -272,6 +278,8 @@ class AUVVecEnv:
         self._scratch = dict(
             rec=torch.zeros((N, self.rec_cap, _lib.REC_BYTES), dtype=torch.uint8, device=dev),
             rec_cnt=z(N, torch.int32), status=z(1, torch.int32),
+            # which closeness entries of the observation buffer are non-zero (all ones = unknown: first step writes all)
+            obs_nz=torch.full((N, 2 * ((max(R, 1) + 63) // 64)), -1, dtype=torch.int32, device=dev),
         )
         s = self._st
         sptr = lambda k: s[k].data_ptr() if k in s else None
@@ -284,6 +292,7 @@ class AUVVecEnv:
             self._scratch["rec"].data_ptr(), self._scratch["rec_cnt"].data_ptr(),
             self._scratch["status"].data_ptr(), self.rec_cap, 0,
             s["obst_steps"].data_ptr(), s["prev_seg"].data_ptr(), s["env_pid"].data_ptr(),
+            self._scratch["obs_nz"].data_ptr(),
         )
 
         # ---- outputs
@@ -317,6 +326,11 @@ class AUVVecEnv:
         )
         self.actions_dev = z((N, 2), torch.float32)
         self._pinned = None
+        self.compact_host = bool(compact_host) and bool(self.config.vessel.use_lidar) and not bool(
+            self.config.vessel.sensor_use_velocity_observations)
+        import os as _os
+
+        self.host_threads = int(host_threads) if host_threads else max(1, min(16, len(_os.sched_getaffinity(0))))
         self.chunks = max(1, int(chunks))
         self.host_chunks = max(1, min(64, int(host_chunks))) if host_chunks else self.chunks
         self._pipe = None
@@ -569,6 +583,9 @@ class AUVVecEnv:
     def step_host(self, actions: np.ndarray):
         """NumPy in / NumPy out: the call a CPU-side VecEnv consumer makes (the e2e
         path).  Copies actions H2D and obs/reward/done D2H through pinned buffers."""
+        if self.compact_host:
+            self.step_async(actions)
+            return self.step_wait()
         pin = self.step_host_buffers()
         pin["act"].numpy()[...] = actions
         cfg, rays, paths, pool, batch = self._refs()
@@ -607,11 +624,19 @@ class AUVVecEnv:
         cur = torch.cuda.current_stream(self.device)
         self._async_stream.wait_stream(cur)  # earlier work of this env (reset, step) is ordered before
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.auv_step_host_submit(
-                cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
-                C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.c_void_p(pin["obs"].data_ptr()),
-                C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()),
-                C.c_void_p(self._async_stream.cuda_stream), self._pipe, max(1, self.host_chunks)), "auv_step_host_submit")
+            if self.compact_host:
+                _lib.check(self.lib.auv_step_host_compact_submit(
+                    cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
+                    C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.byref(pin["compact"]),
+                    C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()),
+                    C.c_void_p(self._async_stream.cuda_stream), self._pipe, max(1, self.host_chunks)),
+                    "auv_step_host_compact_submit")
+            else:
+                _lib.check(self.lib.auv_step_host_submit(
+                    cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
+                    C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.c_void_p(pin["obs"].data_ptr()),
+                    C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()),
+                    C.c_void_p(self._async_stream.cuda_stream), self._pipe, max(1, self.host_chunks)), "auv_step_host_submit")
         self._async_done.record(self._async_stream)
         self._async_pending = True
         self.total_steps += 1
@@ -623,6 +648,11 @@ class AUVVecEnv:
         torch.cuda.current_stream(self.device).wait_event(self._async_done)
         self._async_pending = False
         pin = self._pinned
+        if self.compact_host:  # scatter head / mask / packed values into the dense array (host threads)
+            _lib.check(self.lib.auv_compact_expand(
+                C.byref(self.cfg), self.num_envs, C.byref(pin["compact"]), C.c_void_p(pin["prev_mask"].ctypes.data),
+                C.c_void_p(pin["obs_dense"].ctypes.data), self.host_threads), "auv_compact_expand")
+            return pin["obs_dense"], pin["reward"].numpy(), pin["done"].numpy()
         return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy()
 
     def groups(self, n_groups: int = 2, **kw):
@@ -648,10 +678,22 @@ class AUVVecEnv:
         if self._pinned is None:
             self._pinned = dict(
                 act=torch.zeros((N, 2), dtype=torch.float32).pin_memory(),
-                obs=torch.zeros((N, self.obs_dim), dtype=torch.float32).pin_memory(),
                 reward=torch.zeros(N, dtype=torch.float32).pin_memory(),
                 done=torch.zeros(N, dtype=torch.uint8).pin_memory(),
             )
+            if self.compact_host:
+                W = (self.n_sensors + 31) // 32
+                p = self._pinned
+                p["head"] = torch.zeros((N, 8), dtype=torch.float32).pin_memory()
+                p["mask"] = torch.zeros((N, W), dtype=torch.int32).pin_memory()
+                p["vals"] = torch.zeros(N * W * 32, dtype=torch.float32).pin_memory()
+                p["counter"] = torch.zeros(1, dtype=torch.int32, device=self.device)
+                p["prev_mask"] = np.zeros((N, W), dtype=np.uint32)
+                p["obs_dense"] = np.zeros((N, self.obs_dim), dtype=np.float32)
+                p["compact"] = _lib.AuvCompact(p["head"].data_ptr(), p["mask"].data_ptr(), p["vals"].data_ptr(),
+                                               p["counter"].data_ptr(), W, N * W * 32)
+            else:
+                self._pinned["obs"] = torch.zeros((N, self.obs_dim), dtype=torch.float32).pin_memory()
         return self._pinned
 
     @property
@@ -660,6 +702,12 @@ class AUVVecEnv:
 
     @property
     def d2h_bytes_per_step(self) -> int:
+        """bytes that cross the link per step: dense rows, or -- compact transfer -- heads, masks, reward,
+        done plus the packed non-zero values of the LAST step (read from its head records)"""
+        if self.compact_host and self._pinned is not None:
+            p = self._pinned
+            nz = int(p["head"].numpy().view(np.int32)[:, 6].sum())
+            return self.num_envs * (32 + 4 * p["mask"].shape[1] + 4 + 1) + 4 * nz
         return self.num_envs * (self.obs_dim * 4 + 4 + 1)
 
     def info(self) -> Dict[str, torch.Tensor]:

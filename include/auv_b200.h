@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 17
+#define AUV_ABI_VERSION 18
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -128,7 +128,7 @@ typedef struct AuvPathHdr {
   double ox, oy;   /* origin the FP32 capsules are relative to                              */
   double length;   /* Path.length                                                           */
   double end_x, end_y; /* Path.end                                                          */
-  double reserved;
+  double extent;   /* max |x - ox| + |y - oy| over the polyline: error bound of the FP32 copy     */
 } AuvPathHdr;
 
 typedef struct AuvPathBank {
@@ -137,6 +137,9 @@ typedef struct AuvPathBank {
   const AuvPathHdr* hdr;   /* [n_paths]                                                   */
   const double* poly_xy;   /* [total_vertices][2]                                       */
   const double* poly_cum;  /* [total_vertices] chord-length prefix sum at each vertex   */
+  const float* poly_f32;   /* [total_vertices][2] the same vertices relative to the path's origin, FP32:
+                              the projection screens segments on these 8 B vertices and evaluates in
+                              FP64 only the few that can be the exact minimum                    */
   const float* blk_chord;  /* [total_blocks][4] ax, ay, ex, ey: first vertex and chord vector,
                               relative to the path's origin                             */
   const float* blk_dev;    /* [total_blocks][2] 1/|e|^2 (0 if degenerate), max vertex
@@ -237,6 +240,12 @@ typedef struct AuvBatch {
   int32_t* prev_seg;      /* [N] polyline segment the last projection ended on, -1 = none:
                              warm start of the next one (an upper bound only; the search stays exact) */
   int32_t* env_pid;       /* [N] pool.path_id[scn_id[e]], cached by reset                       */
+  uint32_t* obs_nz;       /* [N][2 ceil(n_sensors / 64)] or NULL: which closeness entries of AuvStepOut.obs
+                             are non-zero (internal encoding), initialised to all ones by the caller.
+                             ~85 % of the closeness block is 0 from one step to the next: with this
+                             scratch the casting stage only stores the 64-ray groups that hold, or
+                             held, a non-zero value.  Requires that nobody else writes AuvStepOut.obs
+                             between calls (it is the env's persistent output buffer)              */
 } AuvBatch;
 
 /* Outputs of one step / observe (all optional except obs/reward/done). */
@@ -341,6 +350,31 @@ int auv_step_host_submit(const AuvConfig* cfg, const AuvRayTable* rays, const Au
                          const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
                          float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
                          uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks);
+/* Lossless COMPACT host step.  The dense observation rows are what bounds the host-buffer step
+ * (4 (6 + R) B per env over PCIe) although ~85 % of a row is exactly 0 (rays that read clear).
+ * auv_step_host_compact_submit is auv_step_host_submit with the D2H copies replaced by a kernel
+ * (k_obs_ship) that writes, straight into PINNED host memory: per env a 32 B head (obs[0..5], the
+ * number of non-zero closeness values, their offset in `vals`), the hit mask (one bit per ray) and
+ * the non-zero values packed back to back; reward / done go to reward_host / done_host the same way
+ * (all host pointers must be pinned, i.e. device-accessible).  Once `stream` has drained,
+ * auv_compact_expand scatters them into the caller's dense [N][obs_dim] array with n_threads host
+ * threads; prev_mask ([N][words], zero-initialised, owned by the caller together with the dense
+ * array) remembers which entries are non-zero so that only changes are touched.  Results are
+ * bit-identical to auv_step_host.  Not available with sensor_use_velocity_observations. */
+typedef struct AuvCompact {
+  float* head;      /* [N][8]       pinned host                                          */
+  uint32_t* mask;   /* [N][words]   pinned host                                          */
+  float* vals;      /* [capacity]   pinned host                                          */
+  int32_t* counter; /* [1]          device                                               */
+  int32_t words;    /* ceil(n_sensors / 32)                                              */
+  int32_t capacity; /* floats in vals, >= N * words * 32                                 */
+} AuvCompact;
+int auv_step_host_compact_submit(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                                 const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
+                                 float* actions_dev, AuvStepOut* out, const AuvCompact* cb, float* reward_host,
+                                 uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks);
+int auv_compact_expand(const AuvConfig* cfg, int n_envs, const AuvCompact* cb, uint32_t* prev_mask, float* obs_host,
+                       int n_threads);
 /* Per-kernel CUDA-event timing of a step on the launching stream (used by bench.py for the
  * roofline of the dominant kernel).  A timer holds `capacity` slots of 4 events. */
 typedef struct AuvTimer AuvTimer;

@@ -201,3 +201,47 @@ def test_steady_state_sample_matches_oracle_land_polygons():
         env.step(acts[t % 8])
     rep = live_sample_compare(env, cfg, acts, horizon=30, n_sample=32, start=300, prefer_records=True)
     assert rep["with_records"] >= 20, rep
+
+
+def test_compact_host_step_is_bit_identical_to_the_dense_copy():
+    """step_host / step_async ship head + hit mask + packed non-zero closeness values straight into
+    pinned host memory (k_obs_ship) and expand them on the host (auv_compact_expand): the dense array
+    they return equals the device observation and the dense D2H copy bit for bit -- through
+    auto-resets (the cached first observation replaces the row) and with the zero-group skipping of
+    the casting stage (obs_nz)."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    cfg.episode.max_timesteps = 9  # time-limit resets inside the rollout
+    n = 300  # not a multiple of the 32-env CTAs
+    scn = S.moving_obstacles(n, 6, 6, seed=13, n_paths=5)
+    rs = np.random.RandomState(3)
+    for m in range(0, n, 2):  # crowd every other start area: many hit rays there, none elsewhere
+        for j in range(6):
+            ang, dist = rs.uniform(0, 2 * np.pi), rs.uniform(20, 100)
+            scn.st_pos[m, j] = scn.vessel_init[m, :2] + dist * np.array([np.cos(ang), np.sin(ang)])
+    dev = AUVVecEnv(scn, n, cfg, auto_reset=True)
+    cmp_ = AUVVecEnv(scn, n, cfg, auto_reset=True, host_chunks=3, host_threads=3)
+    dense = AUVVecEnv(scn, n, cfg, auto_reset=True, host_chunks=2, compact_host=False)
+    assert cmp_.compact_host and not dense.compact_host
+    for e in (dev, cmp_, dense):
+        e.reset()
+    acts = random_actions(30, n, 6).astype(np.float32)
+    resets = 0
+    for t in range(30):
+        o1, r1, d1, _ = dev.step(torch.as_tensor(acts[t], device="cuda"))
+        if t % 2:
+            cmp_.step_async(acts[t])
+            o2, r2, d2 = cmp_.step_wait()
+        else:
+            o2, r2, d2 = cmp_.step_host(acts[t])
+        o3, r3, d3 = dense.step_host(acts[t])
+        torch.cuda.synchronize()
+        a = o1.cpu().numpy()
+        assert np.array_equal(a, o2) and np.array_equal(a, o3), t
+        assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(r2, r3)
+        assert np.array_equal(d1.cpu().numpy(), d2) and np.array_equal(d2, d3)
+        resets += int(d2.sum())
+        assert cmp_.d2h_bytes_per_step < dense.d2h_bytes_per_step
+    assert resets > n, "every env should have been auto-reset at least once"
+    assert (o2[:, 6:] != 0).any() and (o2[:, 6:] == 0).mean() > 0.5
