@@ -46,7 +46,7 @@ def n_ranges(n, chunks):
     """env ranges auv_step_chunked cuts n envs into (range size = ceil(n/chunks) rounded up to 64)."""
     if chunks <= 1:
         return 1
-    cs = -(-(-(-n // chunks)) // 128) * 128
+    cs = -(-(-(-n // chunks)) // 256) * 256
     return -(-n // cs)
 
 

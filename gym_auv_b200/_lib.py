@@ -181,6 +181,7 @@ class AuvStepOut(C.Structure):
         ("sector_feasible_dist", _vp),
         ("stats", _vp),
         ("seg_tests", _vp),
+        ("episode_out", _vp),
     ]
 
 

@@ -546,12 +546,23 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #define AUV_NAV_G 4
 #endif
 #ifndef AUV_NAV_THREADS
-#define AUV_NAV_THREADS 128
+#define AUV_NAV_THREADS 128  // a multiple of 128: one 32-env sub-block (4 warps) per 128 threads
 #endif
 #ifndef AUV_NAV_MINB
-#define AUV_NAV_MINB 8  // 64 registers (steady state, round 2: 6 / 7 / 8 CTAs per SM = 0.106 / 0.101 / 0.096 ms)
+#define AUV_NAV_MINB (1024 / AUV_NAV_THREADS)  // 64 registers: 32 warps per SM (6 / 7 / 8 CTAs of 128: 0.106 / 0.101 / 0.096 ms)
+#endif
+#ifndef AUV_NAV_PHASE_SYNC
+#define AUV_NAV_PHASE_SYNC 0  // 1: __syncthreads between the phases, so that the warps of a CTA run the same code
 #endif
 constexpr int NAV_STAGE_SB = (AUV_PATH_STAGE_BLOCKS + AUV_PATH_SUPER - 1) / AUV_PATH_SUPER;
+constexpr int NAV_SUBBLOCKS = AUV_NAV_THREADS / 128;
+// shared memory of one sub-block: its path's capsule tables
+struct __align__(16) NavStage {
+  float4 chord[AUV_PATH_STAGE_BLOCKS];
+  float2 aux[AUV_PATH_STAGE_BLOCKS];
+  float4 sbc[NAV_STAGE_SB];
+  float2 sba[NAV_STAGE_SB];
+};
 template <bool DYN, bool OBST, int G>
 __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(const __grid_constant__ AuvConfig cfg,
                                                                 const __grid_constant__ AuvPathBank paths,
@@ -561,13 +572,13 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
                                                                 int* __restrict__ windows_out,
                                                                 const float* __restrict__ actions,
                                                                 float* __restrict__ obs_out, int obs_dim, int e0, int e1) {
-  __shared__ __align__(16) float4 s_chord[AUV_PATH_STAGE_BLOCKS];
-  __shared__ __align__(16) float2 s_aux[AUV_PATH_STAGE_BLOCKS];
-  __shared__ __align__(16) float4 s_sbc[NAV_STAGE_SB];
-  __shared__ __align__(16) float2 s_sba[NAV_STAGE_SB];
-  __shared__ __align__(8) unsigned long long s_bar;
+  extern __shared__ __align__(16) unsigned char nav_smem[];
+  NavStage* stages = reinterpret_cast<NavStage*>(nav_smem);
+  __shared__ __align__(8) unsigned long long s_bar[NAV_SUBBLOCKS];
   __shared__ int s_pid[AUV_NAV_THREADS / 32];
   const int lane = threadIdx.x & 31, sub = lane & (G - 1);
+  const int sbk = threadIdx.x >> 7, tsb = threadIdx.x & 127;  // sub-block of 32 envs, thread within it
+  NavStage& st = stages[sbk];
   const unsigned gm = group_mask<G>(lane);
   const int eraw = e0 + (blockIdx.x * AUV_NAV_THREADS + threadIdx.x) / G;  // envs [e0, e1)
   const bool store = eraw < e1;
@@ -582,8 +593,8 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
   S6 y = load_state(batch.state, n, e);
   float2 act = make_float2(0.f, 0.f);
   if (DYN) act = reinterpret_cast<const float2*>(actions)[e];
-  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-  {  // does the whole CTA follow one path?
+  if (tsb == 0) mbar_init(&s_bar[sbk], 1);
+  {  // does the whole sub-block follow one path?
     int same;
     __match_all_sync(AUV_FULL, pid, &same);
     if (lane == 0) s_pid[threadIdx.x >> 5] = same ? pid : -1;
@@ -593,16 +604,16 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
   const AuvPathHdr h = paths.hdr[pid];
   const int nblk = (h.nseg + AUV_PATH_BLOCK - 1) / AUV_PATH_BLOCK;
   const int nsb = (nblk + AUV_PATH_SUPER - 1) / AUV_PATH_SUPER;
-  bool staged = s_pid[0] >= 0 && nblk <= AUV_PATH_STAGE_BLOCKS;
+  bool staged = s_pid[4 * sbk] >= 0 && nblk <= AUV_PATH_STAGE_BLOCKS;
 #pragma unroll
-  for (int w = 1; w < AUV_NAV_THREADS / 32; ++w) staged = staged && s_pid[w] == s_pid[0];
-  if (staged && threadIdx.x == 0) {
+  for (int w = 1; w < 4; ++w) staged = staged && s_pid[4 * sbk + w] == s_pid[4 * sbk];
+  if (staged && tsb == 0) {
     const unsigned nb2 = (unsigned)(nblk + 1) & ~1u, ns2 = (unsigned)(nsb + 1) & ~1u;  // tables are padded to even counts
-    mbar_expect_tx(&s_bar, nb2 * 24u + ns2 * 24u);
-    bulk_g2s(s_chord, reinterpret_cast<const float4*>(paths.blk_chord) + h.b0, nb2 * 16u, &s_bar);
-    bulk_g2s(s_aux, reinterpret_cast<const float2*>(paths.blk_dev) + h.b0, nb2 * 8u, &s_bar);
-    bulk_g2s(s_sbc, reinterpret_cast<const float4*>(paths.sb_chord) + h.s0, ns2 * 16u, &s_bar);
-    bulk_g2s(s_sba, reinterpret_cast<const float2*>(paths.sb_dev) + h.s0, ns2 * 8u, &s_bar);
+    mbar_expect_tx(&s_bar[sbk], nb2 * 24u + ns2 * 24u);
+    bulk_g2s(st.chord, reinterpret_cast<const float4*>(paths.blk_chord) + h.b0, nb2 * 16u, &s_bar[sbk]);
+    bulk_g2s(st.aux, reinterpret_cast<const float2*>(paths.blk_dev) + h.b0, nb2 * 8u, &s_bar[sbk]);
+    bulk_g2s(st.sbc, reinterpret_cast<const float4*>(paths.sb_chord) + h.s0, ns2 * 16u, &s_bar[sbk]);
+    bulk_g2s(st.sba, reinterpret_cast<const float2*>(paths.sb_dev) + h.s0, ns2 * 8u, &s_bar[sbk]);
   }
   if (OBST) {
     ++n_upd;
@@ -620,13 +631,14 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
       batch.step_counter[e] = step_counter;
     }
   }
+  if (AUV_NAV_PHASE_SYNC) __syncthreads();
   PathTabs T;
   if (staged) {
-    mbar_wait(&s_bar, 0);
-    T.sbc = s_sbc;
-    T.sba = s_sba;
-    T.chord = s_chord;
-    T.aux = s_aux;
+    mbar_wait(&s_bar[sbk], 0);
+    T.sbc = st.sbc;
+    T.sba = st.sba;
+    T.chord = st.chord;
+    T.aux = st.aux;
   } else {
     T.sbc = reinterpret_cast<const float4*>(paths.sb_chord) + h.s0;
     T.sba = reinterpret_cast<const float2*>(paths.sb_dev) + h.s0;
@@ -636,8 +648,10 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
   int seg;
   const double s = project_group<G>(paths, h, T, y.x, y.y, prev_seg, lane, gm, seg);
   if (store && sub == 0) batch.prev_seg[e] = seg;
+  if (AUV_NAV_PHASE_SYNC) __syncthreads();
   navigate_env(cfg, paths, h, batch, pid, e, scn, s, y.x, y.y, y.psi, y.u, y.v, y.r,
                obs_out ? obs_out + (long long)e * obs_dim : nullptr, store && sub == 0);
+  if (AUV_NAV_PHASE_SYNC) __syncthreads();
   if (cfg.use_lidar)
     cull_env_group<G>(cfg, pool, batch, unit64, windows_out, e, scn, y.x, y.y, y.psi, step_counter, n_upd, lane, gm, store);
 }
@@ -663,7 +677,9 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
 #ifndef AUV_LIDAR_RCAP
 #define AUV_LIDAR_RCAP 96  // records per shared-memory round
 #endif
-#define AUV_LIDAR_MAX_ENVS 32
+#ifndef AUV_LIDAR_MAX_ENVS
+#define AUV_LIDAR_MAX_ENVS 32  // envs per CTA (<= 32: one warp scans their record counts)
+#endif
 
 struct LidarArgs {
   AuvConfig cfg;
@@ -696,10 +712,12 @@ struct LidarSmem {
   float* pen;       // [E]       sum of w_i (penalty_i - clear penalty) over hit rays
   int* flag;        // [E]       bit 0 collision, bit 1 auto-reset pending
   int* next;        // [E]       scenario the env resets onto
+  unsigned* nz;     // [E][nzw]  non-zero pattern of the envs' observation rows (AuvBatch.obs_nz)
 };
 __host__ __device__ constexpr size_t lidar_smem_bytes_for(int E, int rpad, int vmax, int vel) {
   return (size_t)E * 16 * 8 + (size_t)E * rpad * (vel ? 8 : 4) + AUV_LIDAR_RCAP * sizeof(ObstRec) + AUV_LIDAR_RCAP * 4 +
-         (size_t)(AUV_LIDAR_THREADS / 32) * vmax * 8 + 64 * 8 + 48 * 4 + 32 * 4 + 32 * 4 + 32 * 4;
+         (size_t)(AUV_LIDAR_THREADS / 32) * vmax * 8 + 64 * 8 + 48 * 4 + 32 * 4 + 32 * 4 + 32 * 4 +
+         (size_t)E * 2 * ((rpad + 63) / 64) * 4;
 }
 __device__ __forceinline__ LidarSmem lidar_carve(unsigned char* p, int E, int rpad, int vmax, int vel) {
   LidarSmem s;
@@ -722,6 +740,8 @@ __device__ __forceinline__ LidarSmem lidar_carve(unsigned char* p, int E, int rp
   s.flag = reinterpret_cast<int*>(p);
   p += 32 * 4;
   s.next = reinterpret_cast<int*>(p);
+  p += 32 * 4;
+  s.nz = reinterpret_cast<unsigned*>(p);
   return s;
 }
 
@@ -832,6 +852,10 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
   // ---- phase 1: hand-over lines, unit table, range rows
   for (int k = tid; k < ne * 16; k += AUV_LIDAR_THREADS)
     sm.hand[k] = batch.nav[(long long)(env0 + (k >> 4)) * AUV_NAV_W + NAV_HAND + (k & 15)];
+  const int nzw = 2 * ((R + 63) / 64);
+  const bool use_nz = cfg.use_lidar && batch.obs_nz != nullptr && (A.obs_dim & 1) == 0 && !cfg.sensor_use_velocity_observations;
+  if (use_nz)
+    for (int k = tid; k < ne * nzw; k += AUV_LIDAR_THREADS) sm.nz[k] = batch.obs_nz[(long long)env0 * nzw + k];
   if (cfg.use_lidar) {
     if (tid < 64) {
       const double2 un = reinterpret_cast<const double2*>(A.rays.unit64)[tid];
@@ -991,7 +1015,8 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
       bool collision = false;
       // which 64-ray groups of the row hold a non-zero closeness (bit = lane of the float2 pair): groups that
       // are and were all zero are neither computed nor stored
-      unsigned* nzrow = (batch.obs_nz != nullptr && vec2 && !vel_obs) ? batch.obs_nz + (long long)e * (2 * ((R + 63) / 64)) : nullptr;
+      unsigned* nzrow = use_nz ? sm.nz + el * nzw : nullptr;
+      bool nz_dirty = false;
       if (cnt > 0 || nzrow != nullptr) {
         const double cpsi = HAND(el, NAV_COSPSI), spsi = HAND(el, NAV_SINPSI);
         const ObstRec* grec = reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
@@ -1015,9 +1040,12 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
           if (nzrow != nullptr) {
             const unsigned p0 = nzrow[2 * j], p1 = nzrow[2 * j + 1];  // warp-uniform
             if ((m0 | m1 | p0 | p1) == 0u) continue;               // nothing there, nothing was there
-            if (lane == 0 && (m0 != p0 || m1 != p1)) {
-              nzrow[2 * j] = m0;
-              nzrow[2 * j + 1] = m1;
+            if (m0 != p0 || m1 != p1) {
+              nz_dirty = true;
+              if (lane == 0) {
+                nzrow[2 * j] = m0;
+                nzrow[2 * j + 1] = m1;
+              }
             }
           }
           if (k >= (R + 1) / 2) continue;
@@ -1063,6 +1091,10 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
         }
         collision = __any_sync(AUV_FULL, collision);
         extra = warp_sum(extra);
+        if (nz_dirty) {  // warp-uniform
+          __syncwarp();
+          if (lane < nzw) batch.obs_nz[(long long)e * nzw + lane] = nzrow[lane];
+        }
       } else {
         if (vec2) {
           float2* o2 = reinterpret_cast<float2*>(obs + 6);
@@ -1178,6 +1210,12 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
       if (A.out.reached_goal) A.out.reached_goal[e] = reached;
       if (A.out.goal_distance) A.out.goal_distance[e] = (float)goal_dist;
       if (A.out.progress) A.out.progress[e] = (float)progress;
+      if (done && A.out.episode_out != nullptr) {  // env.history entry of the finished episode
+        float4* eo = reinterpret_cast<float4*>(A.out.episode_out + 8ll * e);
+        eo[0] = make_float4((float)cum, (float)(t_step + 1), (float)progress, collision ? 1.f : 0.f);
+        eo[1] = make_float4(reached ? 1.f : 0.f, (float)(cte_sum / (double)(t_step + 1)),
+                            (float)A.paths.hdr[batch.env_pid[e]].length, (float)batch.episode[e]);
+      }
       if (!do_reset) {
         batch.cum_reward[e] = cum;
         batch.t_step[e] = t_step + 1;
@@ -1238,7 +1276,7 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
       obs[k] = robs[k];
     }
     if (batch.obs_nz != nullptr && cfg.use_lidar) {  // non-zero pattern of the row that was just copied in
-      unsigned* nzrow = batch.obs_nz + (long long)e * (2 * ((R + 63) / 64));
+      unsigned* nzrow = batch.obs_nz + (long long)e * nzw;
       for (int k0 = 0; k0 < (R + 1) / 2; k0 += 32) {
         const int k = k0 + lane;
         const bool z0 = 2 * k < R && robs[6 + 2 * k] != 0.f, z1 = 2 * k + 1 < R && robs[6 + 2 * k + 1] != 0.f;
@@ -1517,23 +1555,41 @@ static int check_observe_args(const AuvConfig* cfg, const AuvRayTable* rays, con
   return check_batch(cfg, pool, batch);
 }
 
+static int nav_configure(size_t smem) {
+  if (smem <= 48 * 1024) return 0;
+  static std::atomic<size_t> configured[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (smem <= configured[dev].load(std::memory_order_acquire)) return 0;
+  const void* fns[3] = {(const void*)auv::k_vessel_nav<true, true, AUV_NAV_G>, (const void*)auv::k_vessel_nav<true, false, AUV_NAV_G>,
+                        (const void*)auv::k_vessel_nav<false, false, AUV_NAV_G>};
+  for (int i = 0; i < 3; ++i)
+    if (int rc = cuda_check(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(k_vessel_nav)"))
+      return rc;
+  configured[dev].store(smem, std::memory_order_release);
+  return 0;
+}
+
 static int launch_vessel_nav(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                              const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out,
                              const float* actions, void* stream, int e0 = 0, int cnt = -1, bool with_obstacles = false) {
   if (cnt < 0) cnt = batch->n_envs - e0;
   const int per_cta = AUV_NAV_THREADS / AUV_NAV_G;  // envs per CTA
   const int blocks = (cnt + per_cta - 1) / per_cta;
+  const size_t nsm = sizeof(auv::NavStage) * auv::NAV_SUBBLOCKS;
+  if (int rc = nav_configure(nsm)) return rc;
   const double2* unit = rays ? reinterpret_cast<const double2*>(rays->unit64) : nullptr;
   int* win = out ? out->windows : nullptr;
   float* obs = out ? out->obs : nullptr;
   const int od = auv_obs_dim(cfg);
   cudaStream_t s = (cudaStream_t)stream;
   if (actions && with_obstacles && pool->k_moving > 0)
-    auv::k_vessel_nav<true, true, AUV_NAV_G><<<blocks, AUV_NAV_THREADS, 0, s>>>(*cfg, *paths, *pool, *batch, unit, win, actions, obs, od, e0, e0 + cnt);
+    auv::k_vessel_nav<true, true, AUV_NAV_G><<<blocks, AUV_NAV_THREADS, nsm, s>>>(*cfg, *paths, *pool, *batch, unit, win, actions, obs, od, e0, e0 + cnt);
   else if (actions)
-    auv::k_vessel_nav<true, false, AUV_NAV_G><<<blocks, AUV_NAV_THREADS, 0, s>>>(*cfg, *paths, *pool, *batch, unit, win, actions, obs, od, e0, e0 + cnt);
+    auv::k_vessel_nav<true, false, AUV_NAV_G><<<blocks, AUV_NAV_THREADS, nsm, s>>>(*cfg, *paths, *pool, *batch, unit, win, actions, obs, od, e0, e0 + cnt);
   else
-    auv::k_vessel_nav<false, false, AUV_NAV_G><<<blocks, AUV_NAV_THREADS, 0, s>>>(*cfg, *paths, *pool, *batch, unit, win, nullptr, obs, od, e0, e0 + cnt);
+    auv::k_vessel_nav<false, false, AUV_NAV_G><<<blocks, AUV_NAV_THREADS, nsm, s>>>(*cfg, *paths, *pool, *batch, unit, win, nullptr, obs, od, e0, e0 + cnt);
   return cuda_check(cudaGetLastError(), "k_vessel_nav");
 }
 
@@ -1690,7 +1746,7 @@ int auv_pipeline_graph_state(const AuvPipeline* p) { return p ? p->graph_state :
 
 static int chunk_size(int n, int n_chunks) {
   int c = (n + n_chunks - 1) / n_chunks;
-  return (c + 127) / 128 * 128;  // whole CTAs of every kernel
+  return (c + 255) / 256 * 256;  // whole CTAs of every kernel (k_vessel_nav: up to 1024 threads = 256 envs)
 }
 
 // device-resident variant: every range on its own stream (round robin)
@@ -1823,6 +1879,7 @@ static int step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, cons
       p->graph_state = 0;
       // one-time function attributes are set outside the capture
       if (int rc0 = lidar_configure(lidar_smem_bytes(cfg, pool))) return rc0;
+      if (int rc0 = nav_configure(sizeof(auv::NavStage) * auv::NAV_SUBBLOCKS)) return rc0;
       cudaStream_t cs = p->st[1];
       cudaGraph_t graph = nullptr;
       int rc = 0;

@@ -250,7 +250,6 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
   }
   double best_d2 = INFINITY;
   int best_seg = 0x7fffffff;
-  float fbest = INFINITY;
   // superblocks in windows of 32 (one bit each); the lanes test different superblocks
   for (int w0 = 0; w0 < nsb; w0 += 32) {
     const int wn = min(32, nsb - w0);
@@ -282,33 +281,21 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
         cand &= cand - 1;
         const int se = min(nseg, (b + 1) * AUV_PATH_BLOCK);
         const int k0 = b * AUV_PATH_BLOCK + sub * KS;  // this lane's consecutive segments
-        // screen in FP32 (8 B per vertex): every segment whose FP32 distance is within the error bound of
-        // the smallest one seen can be the exact first minimum; only those are evaluated in FP64
-        float df[KS];
-        {
-          float2 v[KS + 1];
-#pragma unroll
-          for (int u = 0; u <= KS; ++u) v[u] = polyf[min(k0 + u, se)];
-#pragma unroll
-          for (int u = 0; u < KS; ++u) df[u] = (k0 + u < se) ? seg_d2_f(qx, qy, v[u], v[u + 1]) : INFINITY;
-        }
-        float m = df[0];
-#pragma unroll
-        for (int u = 1; u < KS; ++u) m = fminf(m, df[u]);
-        m = group_min<G>(gm, m);
-        fbest = fminf(fbest, sqrtf(m));  // smallest FP32 distance over all refined blocks so far (group-uniform)
-        const float lim = fbest + 2.f * ftol;
-        const float lim2 = lim * lim * up;
-#pragma unroll
+        // (screening these in FP32 first was measured slower: far from the path many segments tie within the
+        // FP32 error bound, and the divergent FP64 re-evaluation costs more than evaluating all of them)
+        double2 va = poly[min(k0, se)];
+#pragma unroll 2
         for (int u = 0; u < KS; ++u) {
-          if (df[u] <= lim2) {
-            const double d2 = seg_d2(px, py, poly[k0 + u], poly[k0 + u + 1]);
+          const double2 vb = poly[min(k0 + u + 1, se)];
+          if (k0 + u < se) {
+            const double d2 = seg_d2(px, py, va, vb);
             // a lane's segments come in increasing order over the whole search
             if (d2 < best_d2) {
               best_d2 = d2;
               best_seg = k0 + u;
             }
           }
+          va = vb;
         }
       }
     }

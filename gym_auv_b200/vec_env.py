@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from .config import Config
 from .scenarios import ScenarioSet
-from .spaces import Box
+from .spaces import Box, Dict as DictSpace
 
 
 def sector_partition(isensor: int, n_sensors: int, n_sectors: int, c: float = 0.1) -> int:
@@ -308,6 +308,7 @@ class AUVVecEnv:
             terminal_obs=z((N, self.obs_dim), torch.float32),
             stats=z(_lib.N_STATS, torch.float64),
             seg_tests=z(1, torch.int64),
+            episode_out=z((N, 8), torch.float32),
         )
         if sector_outputs and self.config.vessel.use_lidar:
             ns = int(self.config.vessel.n_sectors)
@@ -322,7 +323,7 @@ class AUVVecEnv:
             ptr("obs"), ptr("reward"), ptr("done"), ptr("collision"), ptr("reached_goal"), ptr("goal_distance"),
             ptr("progress"), ptr("lidar_dist"), ptr("windows"), ptr("terminal_obs"), ptr("sector_min_dist"),
             ptr("sector_feasible_dist"), ptr("stats"),
-            ptr("seg_tests") if debug else None,
+            ptr("seg_tests") if debug else None, ptr("episode_out"),
         )
         self.actions_dev = z((N, 2), torch.float32)
         self._pinned = None
@@ -345,6 +346,12 @@ class AUVVecEnv:
 
         self.action_space = Box(low=np.array([-1, -0.15]), high=np.array([1, 0.15]), dtype=np.float32)
         self.observation_space = Box(low=-np.ones(self.obs_dim), high=np.ones(self.obs_dim), dtype=np.float32)
+        self.dict_observation = bool(self.config.vessel.use_dict_observation) and bool(self.config.vessel.use_lidar)
+        if self.dict_observation:  # environment.py:116-137
+            self.observation_space = DictSpace({
+                "proprioceptive": Box(-1.0, 1.0, shape=(6,), dtype=np.float32),
+                "lidar": Box(-1.0, 1.0, shape=((self.obs_dim - 6) // R, R), dtype=np.float32),
+            })
         self._max_nearby = max_nearby
         self._cull_mode = cull_mode
         if auto_reset and _shared is None:
@@ -528,6 +535,19 @@ class AUVVecEnv:
                 "construct AUVVecEnv with a larger max_nearby"
             )
 
+    def observation_dict(self, obs=None):
+        """The Dict observation of environment.py:116-137,281-288 for the whole batch, as zero-copy views of
+        the flat observation: ``proprioceptive`` [N, 6] and the LiDAR "image" ``lidar`` [N, C, R] -- channel 0
+        closeness, with ``sensor_use_velocity_observations`` channels 1-2 the obstacle velocity in the ray
+        frame (v_x, v_y).  (The reference always stacks the two velocity rows; without velocity observations
+        they are all zero upstream and are simply not materialised here: C = 1.)"""
+        o = self._out["obs"] if obs is None else obs
+        R = self.n_sensors
+        return {"proprioceptive": o[:, :6], "lidar": o[:, 6:].reshape(o.shape[0], -1, R)}
+
+    def _fmt(self, obs):
+        return self.observation_dict(obs) if self.dict_observation else obs
+
     # ------------------------------------------------------------------ gym/VecEnv API
     def reset(self, check: bool = True) -> torch.Tensor:
         """Reset every env (BaseEnvironment.reset, environment.py:176-245)."""
@@ -540,7 +560,7 @@ class AUVVecEnv:
             )
         if check:
             self.check_status()
-        return self._out["obs"]
+        return self._fmt(self._out["obs"])
 
     def reset_envs(self, mask: torch.Tensor, scenario_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Reset the envs where mask != 0 (optionally onto explicit scenario ids)."""
@@ -578,7 +598,7 @@ class AUVVecEnv:
                     "auv_step",
                 )
         self.total_steps += 1
-        return self._out["obs"], self._out["reward"], self._out["done"], self.info()
+        return self._fmt(self._out["obs"]), self._out["reward"], self._out["done"], self.info()
 
     def step_host(self, actions: np.ndarray):
         """NumPy in / NumPy out: the call a CPU-side VecEnv consumer makes (the e2e

@@ -266,6 +266,10 @@ typedef struct AuvStepOut {
                                   (sensor.py:251-296) per sector                                  */
   double* stats;         /* [AUV_N_STATS] or NULL: episode-statistic accumulators       */
   unsigned long long* seg_tests; /* [1] or NULL: reference-semantics ray/segment tests  */
+  float* episode_out;    /* [N][8] or NULL: the env.history entry (environment.py:476-489) of the
+                            episode an env finished in this step (rows of envs with done = 1):
+                            reward, timesteps, progress, collision, reached_goal, mean
+                            cross-track error, path length, episode number                      */
 } AuvStepOut;
 
 /* indices into AuvStepOut.stats (mirrors env.history keys, environment.py:476-489) */

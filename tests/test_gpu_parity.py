@@ -437,7 +437,9 @@ def test_step_host_equals_step():
         o2, r2, d2 = e2.step_host(acts[t])
         assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
         assert np.array_equal(d1.cpu().numpy(), d2)
-    assert e2.h2d_bytes_per_step == 33 * 8 and e2.d2h_bytes_per_step == 33 * (186 * 4 + 5)
+    assert e2.h2d_bytes_per_step == 33 * 8
+    nz = int((o2[:, 6:] != 0).sum())  # compact transfer: 32 B head + 6 mask words + reward + done per env, 4 B per non-zero value
+    assert e2.compact_host and e2.d2h_bytes_per_step == 33 * (32 + 24 + 5) + 4 * nz < 33 * (186 * 4 + 5)
 
 
 @pytest.mark.parametrize("chunks,streams", [(2, 2), (3, 2), (5, 4), (8, 1)])

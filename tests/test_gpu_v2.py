@@ -245,3 +245,80 @@ def test_compact_host_step_is_bit_identical_to_the_dense_copy():
         assert cmp_.d2h_bytes_per_step < dense.d2h_bytes_per_step
     assert resets > n, "every env should have been auto-reset at least once"
     assert (o2[:, 6:] != 0).any() and (o2[:, 6:] == 0).mean() > 0.5
+
+
+def test_vecenv_adapter_history_and_report(tmp_path):
+    """B200VecEnv: the SubprocVecEnv surface scripts/run.py:278-475 drives (NumPy in / out, per-env
+    info list with terminal_observation, get_attr('history')) with a fresh GPU-generated scenario per
+    episode; its history entries add up to the device-side episode statistics, and write_report
+    produces the report.txt of reporting.py:37-79."""
+    from gym_auv_b200.adapters import B200VecEnv, write_report
+
+    cfg = lidar_config()
+    cfg.episode.max_timesteps = 7
+    n = 96
+    scn = S.moving_obstacles_template(2 * n, 5, 4, seed=1, n_paths=3, path_period=n)
+    venv = B200VecEnv(scn, n, cfg, fresh_scenarios=True, refresh_every=3, seed=9)
+    obs = venv.reset()
+    assert obs.shape == (n, 186) and venv.observation_space.shape == (186,)
+    rs = np.random.RandomState(0)
+    first_pool = venv.impl.pull_scenarios()
+    n_done = 0
+    for t in range(25):
+        a = rs.uniform([-1, -0.15], [1, 0.15], size=(n, 2)).astype(np.float32)
+        obs, rew, done, infos = venv.step(a)
+        assert obs.shape == (n, 186) and rew.shape == (n,) and done.dtype == bool and len(infos) == n
+        i0 = infos[0]
+        assert set(i0) >= {"collision", "reached_goal", "goal_distance", "progress"}
+        for i in np.nonzero(done)[0][:3]:
+            term = infos[int(i)]["terminal_observation"]
+            assert term.shape == (186,) and not np.array_equal(term, obs[i])
+        n_done += int(done.sum())
+    assert n_done >= 3 * n
+    hist = venv.get_attr("history")[0]
+    assert len(hist) == n_done
+    st = venv.episode_stats(reduce=False)
+    assert st["episodes"] == n_done
+    assert abs(np.mean([h["reward"] for h in hist]) - st["reward"]) <= 1e-3 * abs(st["reward"])
+    assert abs(np.mean([h["timesteps"] for h in hist]) - st["timesteps"]) <= 1e-6
+    assert all(h["timesteps"] <= 7 for h in hist)
+    path = write_report(hist, str(tmp_path), lastn=50)
+    text = open(path).read().splitlines()
+    assert text[0] == "# PERFORMANCE METRICS (LAST 50 EPISODES AVG.)"
+    assert text[1].split() == ["Episodes", "50"]
+    assert [l.split()[0] for l in text[2:4]] == ["Avg.", "Std."] and len(text) == 12
+    # fresh scenarios: the pool slots of finished envs were regenerated
+    later_pool = venv.impl.pull_scenarios()
+    assert (later_pool.st_pos != first_pool.st_pos).any()
+    venv.close()
+
+
+def test_dict_observation_views_on_the_batched_env():
+    """use_dict_observation (environment.py:116-137,281-288): 'proprioceptive' [N, 6] and the LiDAR
+    image 'lidar' [N, C, R] are zero-copy views of the flat observation; with velocity observations C = 3
+    and channels 1-2 carry (v_x, v_y)."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    cfg.vessel.use_dict_observation = True
+    cfg.vessel.sensor_use_velocity_observations = True
+    scn = S.moving_obstacles(16, 10, 4, seed=4)
+    rs = np.random.RandomState(1)
+    for m in range(16):
+        for j in range(10):
+            ang, dist = rs.uniform(0, 2 * np.pi), rs.uniform(25, 110)
+            scn.mov_start[m, j] = scn.vessel_init[m, :2] + dist * np.array([np.cos(ang), np.sin(ang)])
+    env = AUVVecEnv(scn, 16, cfg, test_mode=True, auto_reset=False, velocity_mode="nearest")
+    flat = AUVVecEnv(scn, 16, lidar_config(sensor_use_velocity_observations=True), test_mode=True, auto_reset=False,
+                     velocity_mode="nearest")
+    o = env.reset()
+    f = flat.reset()
+    assert set(o) == {"proprioceptive", "lidar"} and o["lidar"].shape == (16, 3, 180)
+    assert env.observation_space["lidar"].shape == (3, 180) and env.observation_space["proprioceptive"].shape == (6,)
+    a = torch.as_tensor(random_actions(10, 16, 3), dtype=torch.float32, device="cuda")
+    for t in range(10):
+        o, r, d, _ = env.step(a[t])
+        f, rf, df, _ = flat.step(a[t])
+        assert torch.equal(o["proprioceptive"], f[:, :6]) and torch.equal(o["lidar"].reshape(16, -1), f[:, 6:])
+        assert o["lidar"].data_ptr() == env._out["obs"].data_ptr() + 24  # a view, not a copy
+    assert (o["lidar"][:, 1:] != 0).any()
