@@ -14,6 +14,8 @@ MAX_POLY_VERTS = 192
 STATUS_REC_OVERFLOW = 1
 STATUS_GEN_GAVE_UP = 2
 STATUS_POLY_TOO_LARGE = 4
+STATUS_PATH_TOO_LONG = 8
+STATUS_BOUNDS = 16
 PP_W = 12
 PATH_STAGE_BLOCKS = 512
 NAV_W = 24
@@ -208,6 +210,11 @@ class AuvRefreshScratch(C.Structure):
     _fields_ = [("seen_episode", _vp), ("ids", _vp), ("count", _vp), ("capacity", C.c_int32), ("reserved0", C.c_int32)]
 
 
+class AuvPathBuild(C.Structure):
+    _fields_ = [("hdr", _vp), ("poly_xy", _vp), ("poly_cum", _vp), ("poly_f32", _vp), ("blk_chord", _vp), ("blk_dev", _vp),
+                ("sb_chord", _vp), ("sb_dev", _vp), ("pp", _vp), ("n_knots", C.c_int32), ("vcap", C.c_int32)]
+
+
 class AuvCompact(C.Structure):
     _fields_ = [("head", _vp), ("mask", _vp), ("vals", _vp), ("counter", _vp), ("words", C.c_int32), ("capacity", C.c_int32)]
 
@@ -243,6 +250,8 @@ EXPORTS = [
     "auv_refresh_finished",
     "auv_step_host_compact_submit",
     "auv_compact_expand",
+    "auv_pathbank_build",
+    "auv_random_curve_waypoints",
 ]
 
 _lib = None
@@ -311,6 +320,8 @@ def load():
         P(AuvCompact), _vp, _vp, _vp, _vp, C.c_int,
     ]
     lib.auv_compact_expand.argtypes = [P(AuvConfig), C.c_int, P(AuvCompact), _vp, _vp, C.c_int]
+    lib.auv_pathbank_build.argtypes = [_vp, _vp, _vp, C.c_int, P(AuvPathBuild), _vp, _vp]
+    lib.auv_random_curve_waypoints.argtypes = [C.c_uint64, C.c_uint32, C.c_double, _vp, C.c_int, _vp, _vp, _vp]
     lib.auv_timer_create.argtypes = [C.c_int]
     lib.auv_timer_create.restype = _vp
     lib.auv_timer_destroy.argtypes = [_vp]
@@ -326,7 +337,7 @@ def load():
         raise AuvLibraryError(f"ABI mismatch: library {ver}, binding {ABI_VERSION}; rebuild")
     lib.auv_sizeof.argtypes = [C.c_int]
     for i, st in enumerate([AuvConfig, AuvRayTable, AuvPathBank, AuvScenarioPool, AuvBatch, AuvStepOut, AuvGenParams,
-                            AuvPathHdr, AuvRefreshScratch]):
+                            AuvPathHdr, AuvRefreshScratch, AuvCompact, AuvPathBuild]):
         if lib.auv_sizeof(i) != C.sizeof(st):
             raise AuvLibraryError(f"struct layout mismatch for {st.__name__}: C {lib.auv_sizeof(i)} vs ctypes {C.sizeof(st)}")
     _lib = lib

@@ -6,6 +6,20 @@
 #define AUV_PI 3.14159265358979323846
 #define AUV_FULL 0xffffffffu
 
+// -DAUV_DEBUG_BOUNDS: every shared-memory / scratch index of the step kernels is checked and a violation
+// raises AUV_STATUS_BOUNDS in AuvBatch.status (compute-sanitizer is not available on every pool; this build
+// is run once by the GPU tests).  Without the flag the checks compile to nothing.
+#ifdef AUV_DEBUG_BOUNDS
+#define AUV_CHECK(status, cond)                                        \
+  do {                                                                 \
+    if (!(cond) && (status) != nullptr) atomicOr((status), 16);       \
+  } while (0)
+#else
+#define AUV_CHECK(status, cond) \
+  do {                          \
+  } while (0)
+#endif
+
 namespace auv {
 
 // geomutils.py:4-5  princip(angle) = ((angle + pi) % (2 pi)) - pi  with Python's floored

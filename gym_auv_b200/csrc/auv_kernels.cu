@@ -32,6 +32,7 @@
 #include "auv_geometry.cuh"
 #include "auv_navigate.cuh"
 #include "auv_generate.cuh"
+#include "auv_pathbuild.cuh"
 #include "../../include/auv_b200.h"
 
 #include <math.h>
@@ -415,6 +416,7 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
       if (!store) continue;
       if (windows_out != nullptr) reinterpret_cast<int2*>(windows_out)[(long long)e * S + j] = make_int2(wa, wb);
       const int idx = cnt + r;
+      AUV_CHECK(batch.status, j >= 0 && j < S && idx >= 0);
       if (idx >= batch.rec_cap) {  // cannot happen when rec_cap >= number of slots
         if (batch.status != nullptr) atomicOr(batch.status, AUV_STATUS_REC_OVERFLOW);
         continue;
@@ -646,7 +648,8 @@ __global__ void __launch_bounds__(AUV_NAV_THREADS, AUV_NAV_MINB) k_vessel_nav(co
     T.aux = reinterpret_cast<const float2*>(paths.blk_dev) + h.b0;
   }
   int seg;
-  const double s = project_group<G>(paths, h, T, y.x, y.y, prev_seg, lane, gm, seg);
+  const double s = project_group<G>(paths, h, T, y.x, y.y, prev_seg, lane, gm, seg, batch.status);
+  AUV_CHECK(batch.status, seg >= 0 && seg < h.nseg && (!staged || (nblk <= AUV_PATH_STAGE_BLOCKS && nsb <= NAV_STAGE_SB)));
   if (store && sub == 0) batch.prev_seg[e] = seg;
   if (AUV_NAV_PHASE_SYNC) __syncthreads();
   navigate_env(cfg, paths, h, batch, pid, e, scn, s, y.x, y.y, y.psi, y.u, y.v, y.r,
@@ -895,6 +898,7 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
           if (sm.off[mid] <= r) lo = mid; else hi = mid - 1;
         }
         const int idx = r - sm.off[lo];
+        AUV_CHECK(batch.status, lo >= 0 && lo < ne && idx >= 0 && idx < batch.rec_cap && k < AUV_LIDAR_RCAP * 5);
         const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const ObstRec*>(batch.rec) +
                                                         (long long)(env0 + lo) * batch.rec_cap + idx);
         reinterpret_cast<uint4*>(sm.rec)[k] = g[piece];
@@ -906,6 +910,7 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
         const ObstRec& q = sm.rec[rr];
         const int el = sm.rec_env[rr] & 255, slot = sm.rec_env[rr] >> 8;
         const int fl = q.flags, nq = q.nv;
+        AUV_CHECK(batch.status, rr < AUV_LIDAR_RCAP && el >= 0 && el < ne && slot >= 0 && slot < batch.rec_cap);
         // candidate rays of the record (sensor.py:93-95): i in I1 = [a,b) or i-R in [a,b), i.e.
         // I2 = [a+R, b+R), both clipped to [0,R).  An obstacle whose window is wider than R is
         // listed -- and tested -- twice upstream: the min does not care, so the part of I2 that
@@ -969,8 +974,10 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
         const float psi_m_pi = (float)(HAND(el, NAV_PSI) - AUV_PI);
         const float ecx = q.ecx, ecy = q.ecy, rho = q.rho;
         const float slack = rho * 1e-5f + 1e-4f;
+        AUV_CHECK(batch.status, tot <= R && lo1 >= 0 && lo1 + n1 <= R && lo2 >= 0 && lo2 + n2 <= R && (ngon || nq <= A.vmax));
         for (int u = lane; u < tot; u += 32) {
           const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
+          AUV_CHECK(batch.status, i >= 0 && i < R && i < rpad);
           const float cur = range_get<VEL>(row, i);
           // ray direction in the world frame, formed in FP64 (vessel.py:317)
           const double2 cs = cos_sin[i];
@@ -1438,6 +1445,8 @@ int auv_sizeof(int which) {
     case 6: return (int)sizeof(AuvGenParams);
     case 7: return (int)sizeof(AuvPathHdr);
     case 8: return (int)sizeof(AuvRefreshScratch);
+    case 9: return (int)sizeof(AuvCompact);
+    case 10: return (int)sizeof(AuvPathBuild);
     default: return AUV_EINVAL;
   }
 }
@@ -2180,6 +2189,47 @@ int auv_refresh_finished(const AuvConfig* cfg, const AuvRayTable* rays, const Au
       *gp, *paths, *pool, rs->ids, rs->capacity, rs->count, live->status);
   if (int rc = cuda_check(cudaGetLastError(), "k_generate_moving_obstacles")) return rc;
   return reset_cache_fill(cfg, rays, paths, pool, worker, worker_out, rs->ids, 0, rs->capacity, rs->count, stream);
+}
+
+int auv_pathbank_build(const double* waypoints, const int32_t* n_wp, const int32_t* path_ids, int n,
+                       const AuvPathBuild* out, int32_t* status, void* stream) {
+  if (!waypoints || !n_wp || !out || n <= 0) return set_err(AUV_EINVAL, "bad auv_pathbank_build arguments");
+  if (!out->hdr || !out->poly_xy || !out->poly_cum || !out->poly_f32 || !out->blk_chord || !out->blk_dev || !out->sb_chord ||
+      !out->sb_dev || !out->pp)
+    return set_err(AUV_EINVAL, "AuvPathBuild holds a NULL array");
+  if (out->n_knots != auv::PB_NK) return set_err(AUV_EINVAL, "n_knots must be 1000");
+  if (out->vcap <= 0 || out->vcap % (AUV_PATH_BLOCK * AUV_PATH_SUPER) != 0)
+    return set_err(AUV_EINVAL, "vcap must be a positive multiple of AUV_PATH_BLOCK * AUV_PATH_SUPER");
+  const size_t smem = auv::pathbuild_smem_bytes();
+  static std::atomic<int> configured[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!configured[dev].load()) {
+    if (int rc = cuda_check(cudaFuncSetAttribute(auv::k_path_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(k_path_build)"))
+      return rc;
+    configured[dev].store(1);
+  }
+  auv::PathBuildOut o;
+  o.hdr = out->hdr;
+  o.poly_xy = out->poly_xy;
+  o.poly_cum = out->poly_cum;
+  o.poly_f32 = out->poly_f32;
+  o.blk_chord = out->blk_chord;
+  o.blk_dev = out->blk_dev;
+  o.sb_chord = out->sb_chord;
+  o.sb_dev = out->sb_dev;
+  o.pp = out->pp;
+  o.vcap = out->vcap;
+  auv::k_path_build<<<n, auv::PB_THREADS, smem, (cudaStream_t)stream>>>(waypoints, n_wp, path_ids, n, o, status);
+  return cuda_check(cudaGetLastError(), "k_path_build");
+}
+
+int auv_random_curve_waypoints(uint64_t seed, uint32_t epoch, double length, const int32_t* path_ids, int n,
+                               double* waypoints, int32_t* n_wp, void* stream) {
+  if (!waypoints || !n_wp || n <= 0 || !(length > 0.0)) return set_err(AUV_EINVAL, "bad auv_random_curve_waypoints arguments");
+  auv::k_random_curve_waypoints<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, epoch, length, path_ids, n, waypoints, n_wp);
+  return cuda_check(cudaGetLastError(), "k_random_curve_waypoints");
 }
 
 int auv_fma_probe(float* sink, int blocks, int threads, int iters, void* stream, double* flops_out) {

@@ -212,7 +212,7 @@ __device__ __noinline__ float project_cold_bound(const PathTabs& T, const int nb
 template <int G>
 __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const AuvPathHdr& h, const PathTabs& T,
                                                    const double px, const double py, const int prev_seg,
-                                                   const int lane, const unsigned gm, int& seg_out) {
+                                                   const int lane, const unsigned gm, int& seg_out, int* status = nullptr) {
   constexpr int KB = AUV_PATH_SUPER / G;  // blocks of a superblock per lane
   constexpr int KS = AUV_PATH_BLOCK / G;  // segments of a block per lane
   constexpr int KBB = KB < 8 ? KB : 8;    // ... loaded in batches of at most 8
@@ -281,6 +281,7 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
         cand &= cand - 1;
         const int se = min(nseg, (b + 1) * AUV_PATH_BLOCK);
         const int k0 = b * AUV_PATH_BLOCK + sub * KS;  // this lane's consecutive segments
+        AUV_CHECK(status, b >= 0 && b < nblk && sb < nsb);
         // (screening these in FP32 first was measured slower: far from the path many segments tie within the
         // FP32 error bound, and the divergent FP64 re-evaluation costs more than evaluating all of them)
         double2 va = poly[min(k0, se)];

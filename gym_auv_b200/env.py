@@ -148,6 +148,8 @@ class AUVEnv:
         raise NotImplementedError("rendering is outside the B200 step path (SURVEY.md section 2 #14)")
 
     def _format_obs(self, obs):
+        if isinstance(obs, dict):  # the batched env already split it (AUVVecEnv.observation_dict)
+            return {k: v[0].detach().cpu().numpy().astype(np.float64) for k, v in obs.items()}
         o = obs[0].detach().cpu().numpy().astype(np.float64)
         if self.config.vessel.use_dict_observation:
             R = self.config.vessel.n_sensors

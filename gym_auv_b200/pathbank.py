@@ -220,6 +220,88 @@ class PathBank:
         )
 
 
+class DevicePathBank:
+    """A path bank whose tables are built ON THE GPU (auv_pathbank_build: the three PCHIP rounds of
+    path.py:19-40, polyline, prefix sums, capsules) from host waypoints -- milliseconds for 1024 random
+    curves instead of ~14 s of SciPy -- in fixed-size slots (``vcap`` polyline vertices per path), so that
+    single slots can be rebuilt later (fresh random curves, ``AUVVecEnv.regenerate_paths``).  The host
+    builder ``PathBank`` stays the reference implementation the device tables are tested against."""
+
+    n_knots = N_KNOTS
+
+    def __init__(self, waypoints: Sequence[np.ndarray], vcap: int = 16384):
+        if len(waypoints) == 0:
+            raise ValueError("empty path bank")
+        self.waypoints = [np.asarray(w, dtype=np.float64) for w in waypoints]
+        for w in self.waypoints:
+            if w.ndim != 2 or w.shape[0] != 2 or not (2 <= w.shape[1] <= 8):
+                raise ValueError(f"device-built paths take 2..8 waypoints of shape [2, n], got {w.shape}")
+        self.n_paths = len(self.waypoints)
+        span = PATH_BLOCK * PATH_SUPER
+        self.vcap = (int(vcap) + span - 1) // span * span
+        self._tables = None
+        self._dev = None
+
+    @property
+    def tables(self) -> List[PathTable]:
+        """Host tables (SciPy), built lazily: only scenario generation on the host and the tests need them."""
+        if self._tables is None:
+            self._tables = [build_path(w) for w in self.waypoints]
+        return self._tables
+
+    def waypoint_arrays(self):
+        wp = np.zeros((self.n_paths, 2, 8))
+        nwp = np.zeros(self.n_paths, dtype=np.int32)
+        for i, w in enumerate(self.waypoints):
+            wp[i, :, : w.shape[1]] = w
+            nwp[i] = w.shape[1]
+        return wp, nwp
+
+    def allocate(self, device):
+        import torch
+
+        P, V = self.n_paths, self.vcap
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
+        return dict(
+            hdr=z(P * HDR_DTYPE.itemsize, torch.uint8), poly_xy=z((P * V, 2), torch.float64), poly_cum=z(P * V, torch.float64),
+            poly_f32=z((P * V, 2), torch.float32), blk_chord=z((P * V // PATH_BLOCK, 4), torch.float32),
+            blk_dev=z((P * V // PATH_BLOCK, 2), torch.float32),
+            sb_chord=z((P * V // (PATH_BLOCK * PATH_SUPER), 4), torch.float32),
+            sb_dev=z((P * V // (PATH_BLOCK * PATH_SUPER), 2), torch.float32), pp=z((P, N_KNOTS - 1, PP_W), torch.float64),
+        )
+
+    def build_struct(self, arrays):
+        from . import _lib
+
+        a = arrays
+        return _lib.AuvPathBuild(a["hdr"].data_ptr(), a["poly_xy"].data_ptr(), a["poly_cum"].data_ptr(), a["poly_f32"].data_ptr(),
+                                 a["blk_chord"].data_ptr(), a["blk_dev"].data_ptr(), a["sb_chord"].data_ptr(),
+                                 a["sb_dev"].data_ptr(), a["pp"].data_ptr(), N_KNOTS, self.vcap)
+
+    def device_arrays(self, device):
+        """Allocate the slots and build every path on the device."""
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+
+        lib = _lib.load()
+        arrays = self.allocate(device)
+        wp, nwp = self.waypoint_arrays()
+        d_wp = torch.as_tensor(wp).to(device)
+        d_n = torch.as_tensor(nwp).to(device)
+        status = torch.zeros(1, dtype=torch.int32, device=device)
+        bs = self.build_struct(arrays)
+        with torch.cuda.device(device):
+            stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            _lib.check(lib.auv_pathbank_build(C.c_void_p(d_wp.data_ptr()), C.c_void_p(d_n.data_ptr()), None, self.n_paths,
+                                              C.byref(bs), C.c_void_p(status.data_ptr()), stream), "auv_pathbank_build")
+        if int(status.item()) & _lib.STATUS_PATH_TOO_LONG:
+            raise ValueError(f"a path's 0.1 m polyline has more than vcap={self.vcap} vertices: raise vcap")
+        return arrays
+
+
 def random_curve_waypoints(rng, nwaypoints: int, length: float = 400.0) -> np.ndarray:
     """Waypoints of ``RandomCurveThroughOrigin`` (path.py:96-120): start on a circle of
     radius length/2, end = -start, nwaypoints//2 rounds each inserting two jittered points

@@ -18,7 +18,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from .pathbank import PathBank, PathTable, build_path, random_curve_waypoints
+from .pathbank import DevicePathBank, PathBank, PathTable, build_path, random_curve_waypoints
 
 VESSEL_TRACK_LEN = 9999  # a 10000-point trajectory yields 9999 per-second velocities
 
@@ -278,6 +278,7 @@ def moving_obstacles_template(
     path_length: float = 800.0,
     name: str = "MovingObstaclesNoRules-v0",
     path_period: Optional[int] = None,
+    device_paths: bool = False,
 ) -> ScenarioSet:
     """Path bank + EMPTY obstacle slots for M scenarios: the input of
     ``AUVVecEnv.regenerate_scenarios`` (GPU-side sampling of vessel starts and obstacles).  Only
@@ -288,12 +289,15 @@ def moving_obstacles_template(
     for _ in range(P):
         nwp = int(np.floor(4 * rng.rand() + 2))
         wps.append(random_curve_waypoints(rng, nwp, length=path_length))
-    tables = [build_path(w) for w in wps]
     period, group = _path_layout(M, P, path_period)
     path_id = _path_major_ids(M, P, period, group)
     vessel_init = np.zeros((M, 3))
-    for p in range(P):
-        vessel_init[path_id == p, 0:2] = tables[p](0.0)
+    if device_paths:  # the path tables are built on the GPU too (auv_pathbank_build); vessel starts are generated there
+        tables = None
+    else:
+        tables = [build_path(w) for w in wps]
+        for p in range(P):
+            vessel_init[path_id == p, 0:2] = tables[p](0.0)
     mov_track = np.zeros((M, n_moving, 4), dtype=np.int32)
     mov_track[..., 0] = np.arange(M * n_moving).reshape(M, n_moving)
     mov_track[..., 1] = VESSEL_TRACK_LEN
@@ -303,7 +307,7 @@ def moving_obstacles_template(
         st_pos=np.zeros((M, n_static, 2)), st_radius=np.zeros((M, n_static)), rewarder=rewarder,
         post_generate_update=True, name=name, path_group=group, path_period=period,
     )
-    scn._bank = PathBank(tables)
+    scn._bank = DevicePathBank(wps) if device_paths else PathBank(tables)
     return scn
 
 

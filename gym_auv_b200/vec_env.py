@@ -176,7 +176,7 @@ class AUVVecEnv:
         self._bank = _shared["bank"] if _shared is not None else bank.device_arrays(dev)
         b = self._bank
         self.paths = _lib.AuvPathBank(
-            bank.n_paths, bank.knots.shape[1], b["hdr"].data_ptr(), b["poly_xy"].data_ptr(), b["poly_cum"].data_ptr(),
+            bank.n_paths, getattr(bank, "n_knots", None) or bank.knots.shape[1], b["hdr"].data_ptr(), b["poly_xy"].data_ptr(), b["poly_cum"].data_ptr(),
             b["poly_f32"].data_ptr(), b["blk_chord"].data_ptr(), b["blk_dev"].data_ptr(), b["sb_chord"].data_ptr(), b["sb_dev"].data_ptr(),
             b["pp"].data_ptr(),
         )
@@ -432,6 +432,45 @@ class AUVVecEnv:
         self._build_reset_cache(ids)
         return n
 
+    def regenerate_paths(self, ids: Optional[torch.Tensor] = None, seed: int = 0, epoch: int = 1, length: float = 800.0):
+        """Draw fresh ``RandomCurveThroughOrigin`` paths ON THE GPU (path.py:96-120 waypoints with Philox
+        streams, then ``Path.__init__``'s three PCHIP rounds, polyline and search tables:
+        auv_random_curve_waypoints + auv_pathbank_build) into the listed slots of a device-built bank
+        (default: all).  Scenarios that follow those paths are stale afterwards -- regenerate them
+        (``regenerate_scenarios``) before the next ``reset()``; ``MovingObstacles._generate`` does the same
+        pair of draws per episode (movingobstacles.py:28-95)."""
+        from .pathbank import DevicePathBank
+
+        bank = self.scenarios.bank
+        if not isinstance(bank, DevicePathBank):
+            raise ValueError("regenerate_paths needs a device-built path bank (scenarios built with device_paths=True)")
+        n = bank.n_paths
+        idp = None
+        if ids is not None:
+            ids = ids.to(self.device, torch.int32).contiguous()
+            idp, n = C.c_void_p(ids.data_ptr()), int(ids.numel())
+            if n == 0:
+                return 0
+        wp = torch.zeros((n, 2, 8), dtype=torch.float64, device=self.device)
+        nwp = torch.zeros(n, dtype=torch.int32, device=self.device)
+        bs = bank.build_struct(self._bank)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.auv_random_curve_waypoints(int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, float(length),
+                                                           idp, n, C.c_void_p(wp.data_ptr()), C.c_void_p(nwp.data_ptr()),
+                                                           self._stream()), "auv_random_curve_waypoints")
+            _lib.check(self.lib.auv_pathbank_build(C.c_void_p(wp.data_ptr()), C.c_void_p(nwp.data_ptr()), idp, n, C.byref(bs),
+                                                   C.c_void_p(self._scratch["status"].data_ptr()), self._stream()),
+                       "auv_pathbank_build")
+        # keep the host copy of the waypoints in step (oracle replay / pull_scenarios)
+        hw, hn = wp.cpu().numpy(), nwp.cpu().numpy()
+        slots = range(bank.n_paths) if ids is None else ids.cpu().numpy().tolist()
+        for k, pth in enumerate(slots):
+            bank.waypoints[int(pth)] = hw[k, :, : int(hn[k])].copy()
+            self.scenarios.waypoints[int(pth)] = bank.waypoints[int(pth)]
+        bank._tables = None
+        self.check_status()
+        return n
+
     def refresh_finished(self, seed: int = 0) -> int:
         """Ping-pong scenario refresh for sustained training: with a pool of M = 2 N scenarios env
         e alternates between slots e and e + N at every reset, so the slot it is NOT running is
@@ -527,6 +566,10 @@ class AUVVecEnv:
         st = int(self._scratch["status"].item())
         if st & _lib.STATUS_GEN_GAVE_UP:
             raise RuntimeError("scenario generator: an obstacle slot was still rejected after 100000 draws")
+        if st & _lib.STATUS_BOUNDS:
+            raise RuntimeError("AUV_DEBUG_BOUNDS build: an index check inside a step kernel failed")
+        if st & _lib.STATUS_PATH_TOO_LONG:
+            raise RuntimeError("a generated path's polyline does not fit its slot: raise DevicePathBank(vcap=...)")
         if st & _lib.STATUS_POLY_TOO_LARGE:
             raise RuntimeError(f"a world polygon has more than {_lib.MAX_POLY_VERTS} vertices: split it")
         if st & _lib.STATUS_REC_OVERFLOW:

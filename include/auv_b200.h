@@ -70,6 +70,8 @@ extern "C" {
 #define AUV_MAX_POLY_VERTS 192 /* vertices of one world polygon incl. the closing one */
 #define AUV_STATUS_REC_OVERFLOW 1 /* AuvBatch.status bit: more nearby obstacles than rec_cap */
 #define AUV_STATUS_GEN_GAVE_UP 2  /* scenario generator: an obstacle was placed after 100000 rejections */
+#define AUV_STATUS_PATH_TOO_LONG 8 /* auv_pathbank_build: a path's 0.1 m polyline does not fit its slot (vcap) */
+#define AUV_STATUS_BOUNDS 16 /* -DAUV_DEBUG_BOUNDS builds only: an index check of a step kernel failed */
 #define AUV_STATUS_POLY_TOO_LARGE 4 /* a world polygon has more than AUV_MAX_POLY_VERTS vertices: it was skipped */
 #define AUV_PATH_STAGE_BLOCKS 512 /* paths with at most this many projection blocks (~1.6 km) are searched from a
                                      shared-memory copy of their capsule tables (one bulk async copy per CTA) */
@@ -291,7 +293,8 @@ typedef struct AuvStepOut {
 
 int auv_abi_version(void);
 /* sizeof of the ABI structs, in declaration order (0 AuvConfig, 1 AuvRayTable, 2 AuvPathBank,
- * 3 AuvScenarioPool, 4 AuvBatch, 5 AuvStepOut, 6 AuvGenParams, 7 AuvPathHdr, 8 AuvRefreshScratch) so a binding
+ * 3 AuvScenarioPool, 4 AuvBatch, 5 AuvStepOut, 6 AuvGenParams, 7 AuvPathHdr, 8 AuvRefreshScratch, 9 AuvCompact,
+ * 10 AuvPathBuild) so a binding
  * can verify its layout. */
 int auv_sizeof(int which);
 const char* auv_last_error(void);
@@ -451,6 +454,35 @@ typedef struct AuvRefreshScratch {
 int auv_refresh_finished(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                          const AuvScenarioPool* pool, const AuvBatch* live, AuvBatch* worker, AuvStepOut* worker_out,
                          const AuvRefreshScratch* rs, const AuvGenParams* gp, void* stream);
+/* Device-side construction of path-bank entries: what
+ * gym_auv.objects.path.Path.__init__ (path.py:19-40) computes with SciPy -- three rounds of
+ * chord-length re-parametrisation through PCHIP resampled at 1000 points, the 0.1 m polyline --
+ * plus the tables of AuvPathBank (PPoly piece records, chord-length prefix sums, FP32 polyline,
+ * block / superblock capsules, header), one CTA per path, SciPy's / NumPy's evaluation order with
+ * explicit round-to-nearest operations.  Slot layout: path p owns vertices [p vcap, (p + 1) vcap),
+ * blocks [p vcap / 32, ...), superblocks [p vcap / 512, ...); vcap a multiple of 512.  A polyline that
+ * does not fit raises AUV_STATUS_PATH_TOO_LONG.  waypoints: device [n][2][8] (x row, y row; as passed to
+ * the reference's Path()), n_wp: device [n] (2..8), path_ids: device [n] slots to write, NULL = 0..n-1. */
+typedef struct AuvPathBuild {
+  AuvPathHdr* hdr;
+  double* poly_xy;
+  double* poly_cum;
+  float* poly_f32;
+  float* blk_chord;
+  float* blk_dev;
+  float* sb_chord;
+  float* sb_dev;
+  double* pp;
+  int32_t n_knots; /* 1000 */
+  int32_t vcap;
+} AuvPathBuild;
+int auv_pathbank_build(const double* waypoints, const int32_t* n_wp, const int32_t* path_ids, int n,
+                       const AuvPathBuild* out, int32_t* status, void* stream);
+/* RandomCurveThroughOrigin waypoints (path.py:96-120) with the waypoint count of
+ * MovingObstacles._generate (movingobstacles.py:28-31), Philox streams keyed by (seed; path slot, epoch):
+ * fills waypoints [n][2][8] / n_wp [n] for auv_pathbank_build. */
+int auv_random_curve_waypoints(uint64_t seed, uint32_t epoch, double length, const int32_t* path_ids, int n,
+                               double* waypoints, int32_t* n_wp, void* stream);
 /* Host helper (no GPU work): first wrap and wrap period, in updates, of a constant-velocity
  * VesselObstacle track (obstacles.py:195-215: counter += dt; floor(counter) >= vel_len - 1 wraps the
  * counter to 0 and the position to the track start).  counter0 = waypoint counter right after

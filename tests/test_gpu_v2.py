@@ -4,6 +4,7 @@ global fallback, the warm-started projection, the LiDAR velocity channel of
 simulate_sensor_brute_force (sensor.py:100-137), and oracle samples of the regime that is
 benchmarked (steady state after >= 1000 steps with auto-reset and fresh scenarios)."""
 import dataclasses
+import os
 
 import numpy as np
 import pytest
@@ -322,3 +323,149 @@ def test_dict_observation_views_on_the_batched_env():
         assert torch.equal(o["proprioceptive"], f[:, :6]) and torch.equal(o["lidar"].reshape(16, -1), f[:, 6:])
         assert o["lidar"].data_ptr() == env._out["obs"].data_ptr() + 24  # a view, not a copy
     assert (o["lidar"][:, 1:] != 0).any()
+
+
+def test_device_path_builder_matches_scipy_tables():
+    """auv_pathbank_build (Path.__init__, path.py:19-40, on the GPU) against the host builder
+    (SciPy PCHIP): knots and PPoly coefficients to the last bits, the 0.1 m polyline and its
+    chord-length prefix sums, the header, and capsules that do contain their part of the polyline."""
+    from gym_auv_b200.pathbank import DevicePathBank, PATH_BLOCK, PATH_SUPER, build_path, random_curve_waypoints, HDR_DTYPE
+
+    rng = np.random.RandomState(5)
+    wps = [random_curve_waypoints(rng, int(np.floor(4 * rng.rand() + 2)), 800.0) for _ in range(10)]
+    wps += [np.array([[0.0, 1100.0], [0.0, 1100.0]]), np.array([[25.0, 25.0], [10.0, 200.0]]),
+            np.array([[0.0, 300.0, 300.0, 900.0], [0.0, 0.0, 400.0, 400.0]])]
+    bank = DevicePathBank(wps)
+    arr = bank.device_arrays("cuda:0")
+    torch.cuda.synchronize()
+    hdr = arr["hdr"].cpu().numpy().view(HDR_DTYPE)
+    V = bank.vcap
+    for p, wp in enumerate(wps):
+        ref = build_path(wp)
+        h = hdr[p]
+        n = len(ref.poly)
+        assert h["nseg"] == n - 1 and h["v0"] == p * V
+        assert abs(h["length"] - ref.length) <= 1e-12 * ref.length
+        assert abs(h["end_x"] - ref.end[0]) <= 1e-9 and abs(h["end_y"] - ref.end[1]) <= 1e-9
+        pp = arr["pp"][p].cpu().numpy()
+        assert np.abs(pp[:, 0] - ref.knots[:-1]).max() <= 1e-12 * ref.length
+        assert np.abs(pp[:, 1] - ref.knots[1:]).max() <= 1e-12 * ref.length
+        scale = np.abs(ref.coef).max(axis=(0, 2))
+        assert np.abs(pp[:, 2:6] - ref.coef[:, 0, :]).max() <= 1e-9 * max(1.0, scale[0])
+        assert np.abs(pp[:, 6:10] - ref.coef[:, 1, :]).max() <= 1e-9 * max(1.0, scale[1])
+        poly = arr["poly_xy"][p * V:p * V + n].cpu().numpy()
+        assert np.abs(poly - ref.poly).max() <= 1e-10
+        assert np.abs(arr["poly_cum"][p * V:p * V + n].cpu().numpy() - ref.cum).max() <= 1e-9
+        pf = arr["poly_f32"][p * V:p * V + n].cpu().numpy()
+        assert np.abs(pf - (ref.poly - ref.origin)).max() <= 1e-4
+        # capsules: every covered vertex lies within `dev` of the (rounded) chord
+        rel = ref.poly - np.array([h["ox"], h["oy"]])
+        for span, ck, dk, off in ((PATH_BLOCK, "blk_chord", "blk_dev", h["b0"]), (PATH_BLOCK * PATH_SUPER, "sb_chord", "sb_dev", h["s0"])):
+            nn = (n - 1 + span - 1) // span
+            ch = arr[ck][off:off + nn].cpu().numpy().astype(np.float64)
+            ax = arr[dk][off:off + nn].cpu().numpy().astype(np.float64)
+            for b in range(nn):
+                v = rel[b * span:min((b + 1) * span, n - 1) + 1]
+                w = v - ch[b, :2]
+                t = np.clip((w @ ch[b, 2:]) * ax[b, 0], 0, 1)
+                d = np.linalg.norm(w - t[:, None] * ch[b, 2:], axis=1).max()
+                assert d <= ax[b, 1], (p, span, b, d, ax[b, 1])
+                assert ax[b, 1] <= d + 1e-2  # ... and is not uselessly loose
+
+
+def test_device_built_bank_steps_like_the_host_built_bank():
+    """Same scenarios on a SciPy-built and on a GPU-built path bank: the step agrees to the rounding
+    of the tables (positions 1e-9, arclength 1e-7), done / collision flags identical."""
+    from gym_auv_b200.pathbank import DevicePathBank
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    scn = S.moving_obstacles(64, 6, 6, seed=31, n_paths=4)
+    dscn = dataclasses.replace(scn, _bank=DevicePathBank(scn.waypoints), _world=None)
+    e1 = AUVVecEnv(scn, 64, cfg, test_mode=True, auto_reset=False, debug=True)
+    e2 = AUVVecEnv(dscn, 64, cfg, test_mode=True, auto_reset=False, debug=True)
+    o1, o2 = e1.reset(), e2.reset()
+    assert torch.allclose(o1, o2, atol=1e-6)
+    a = torch.as_tensor(random_actions(50, 64, 8), dtype=torch.float32, device="cuda")
+    for t in range(50):
+        o1, r1, d1, i1 = e1.step(a[t])
+        o2, r2, d2, i2 = e2.step(a[t])
+        assert torch.allclose(o1, o2, atol=1e-6) and torch.allclose(r1, r2, atol=1e-4, rtol=1e-6)
+        assert torch.equal(d1, d2) and torch.equal(i1["collision"], i2["collision"])
+        assert (e1.get_attr("nav")[:, 0] - e2.get_attr("nav")[:, 0]).abs().max() <= 1e-7
+        assert torch.allclose(e1.get_attr("lidar_dist"), e2.get_attr("lidar_dist"), atol=1e-5)
+
+
+def test_fresh_random_paths_on_the_device_replay_through_the_oracle():
+    """regenerate_paths + regenerate_scenarios: a complete MovingObstacles._generate (random curve,
+    vessel start, obstacles -- movingobstacles.py:28-95) on the GPU.  The generated curves have the
+    shape of RandomCurveThroughOrigin (ends on the circle of radius 400, through the origin), and the
+    generated scenarios -- pulled back with their waypoints -- replay through the oracle."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    n = 24
+    scn = S.moving_obstacles_template(n, 6, 5, seed=3, n_paths=n, device_paths=True)
+    env = AUVVecEnv(scn, n, cfg, test_mode=True, auto_reset=False, debug=True)
+    before = [w.copy() for w in scn.bank.waypoints]
+    env.regenerate_paths(seed=77, epoch=2)
+    env.regenerate_scenarios(seed=77, epoch=2)
+    after = scn.bank.waypoints
+    assert all(a.shape[1] in (5, 7) for a in after) and any(not np.array_equal(a, b) for a, b in zip(after, before))
+    for w in after:
+        assert abs(np.hypot(*w[:, 0]) - 400.0) < 1e-9 and np.allclose(w[:, -1], -w[:, 0])
+        assert np.abs(w[:, w.shape[1] // 2]).max() == 0.0  # through the origin
+        assert np.allclose(w[0, 1:-1] - w[1, 1:-1], (w[0, 1:-1] - w[1, 1:-1]))  # (jitter is one scalar per point)
+    host = env.pull_scenarios()
+    acts = random_actions(30, n, 12)
+    ref = rollout_oracle(host, cfg, acts)
+    env.reset()
+    a = torch.as_tensor(acts, dtype=torch.float32, device="cuda")
+    for t in range(30):
+        obs, rew, done, info = env.step(a[t])
+        alive = ref["alive"][t]
+        o = obs.cpu().numpy()
+        assert np.abs(o - ref["obs"][t])[alive].max() <= 1e-4, t
+        assert np.abs(rew.cpu().numpy() - ref["reward"][t])[alive].max() <= 1e-3
+
+
+def test_debug_bounds_build_raises_no_index_violation(tmp_path):
+    """compute-sanitizer is not available on every pool, so the kernels carry their own index checks
+    (-DAUV_DEBUG_BOUNDS: record / ray / vertex-stage / segment / block indices; a violation raises
+    AUV_STATUS_BOUNDS).  The debug library is built here and a crowded rollout -- dense records, several
+    shared-memory rounds, land polygons, auto-reset, host step -- is run through it in a subprocess."""
+    import subprocess
+    import sys
+
+    from gym_auv_b200 import build as B
+
+    lib = str(tmp_path / "libauv_b200_dbg.so")
+    cmd = [os.environ.get("NVCC", "nvcc")] + B.NVCC_FLAGS + ["-DAUV_DEBUG_BOUNDS", "-o", lib, B.SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    prog = r"""
+import numpy as np, torch
+from gym_auv_b200 import lidar_config, scenarios as S
+from gym_auv_b200.vec_env import AUVVecEnv
+cfg = lidar_config(); cfg.episode.max_timesteps = 12
+n = 200
+scn = S.land_scenarios(n, n_polygons=40, n_moving=12, n_static=12, seed=2, n_paths=6, extent=900.0)
+rs = np.random.RandomState(0)
+for m in range(n):
+    for j in range(12):
+        a, d = rs.uniform(0, 2 * np.pi), rs.uniform(10, 140)
+        scn.st_pos[m, j] = scn.vessel_init[m, :2] + d * np.array([np.cos(a), np.sin(a)])
+env = AUVVecEnv(scn, n, cfg, auto_reset=True, debug=True, sector_outputs=True, host_chunks=2)
+env.reset()
+for t in range(40):
+    a = rs.uniform([-1, -0.15], [1, 0.15], size=(n, 2)).astype(np.float32)
+    if t % 2: env.step(torch.as_tensor(a, device="cuda"))
+    else: env.step_host(a)
+env.check_status()
+assert float(env._scratch["rec_cnt"].float().mean()) > 3
+print("bounds ok", int(env._scratch["status"].item()))
+"""
+    env = dict(os.environ, AUV_B200_LIB=lib)
+    out = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, env=env,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and "bounds ok 0" in out.stdout, out.stdout[-1500:] + out.stderr[-3000:]
