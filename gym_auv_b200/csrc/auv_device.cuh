@@ -10,9 +10,9 @@
 // raises AUV_STATUS_BOUNDS in AuvBatch.status (compute-sanitizer is not available on every pool; this build
 // is run once by the GPU tests).  Without the flag the checks compile to nothing.
 #ifdef AUV_DEBUG_BOUNDS
-#define AUV_CHECK(status, cond)                                        \
-  do {                                                                 \
-    if (!(cond) && (status) != nullptr) atomicOr((status), 16);       \
+#define AUV_CHECK(status, cond)                                                              \
+  do {                                                                                       \
+    if (!(cond) && (status) != nullptr) atomicOr((status), 16 | ((__LINE__ & 0x3fff) << 8)); \
   } while (0)
 #else
 #define AUV_CHECK(status, cond) \

@@ -14,7 +14,7 @@ struct S6 {
 
 // nu_dot = M^-1 (tau - D nu - N(nu) nu) and eta_dot = Rz(psi) nu with cos/sin(psi) supplied
 #ifndef AUV_RK_INLINE
-#define AUV_RK_INLINE __noinline__  // the step kernel is instruction-cache bound: six stages share one copy
+#define AUV_RK_INLINE __forceinline__  // (out of line was measured: 0.104 -> 0.126 ms, the S6 structs go through the stack)
 #endif
 __device__ AUV_RK_INLINE S6 state_dot_cs(const S6& s, double cp, double sp, double tau_u, double tau_r) {
   // M = [[25.8,0,0],[0,33.8,1.0948],[0,1.0948,2.76]]   (constants.py:33-36)

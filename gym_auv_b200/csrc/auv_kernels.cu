@@ -312,8 +312,8 @@ __device__ __forceinline__ SlotGeom load_slot(const AuvScenarioPool& pool, const
         g.step_len = (float)(dl2 * inv);
       }
       // obstacles.py:230-262, SURVEY App. A.3: centre = c + R(th)((w/2,0) - c) + pos, c = (5w/18, 0)
-      g.cx = (pos.x - px) + 5.0 * w / 18.0 + (2.0 * w / 9.0) * g.hx;
-      g.cy = (pos.y - py) + (2.0 * w / 9.0) * g.hy;
+      g.cx = (pos.x - px) + w * (5.0 / 18.0) + (w * (2.0 / 9.0)) * g.hx;
+      g.cy = (pos.y - py) + (w * (2.0 / 9.0)) * g.hy;
       g.rho = w * 1.1180339887498949;  // sqrt(5)/2
       g.nv = 6;
     }
@@ -368,7 +368,7 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
             } else if (dc + g.rho - width < range - 1e-6) {
               near = true;  // ... and distance <= dc + rho
             } else {
-              const double bx0 = g.cx - (2.0 * g.geo / 9.0) * g.hx, by0 = g.cy - (2.0 * g.geo / 9.0) * g.hy;
+              const double bx0 = g.cx - (g.geo * (2.0 / 9.0)) * g.hx, by0 = g.cy - (g.geo * (2.0 / 9.0)) * g.hy;
               bool in_dummy;
               const double dist =
                   g.world ? world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + g.vbase, g.nv,
@@ -404,8 +404,8 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
         int lo, hi;
         cull_bounds(g.cx, g.cy, g.rho, psi, R, lo, hi);
         window_from_bounds(lo, hi, R, cfg.cull_mode, wa, wb, allrays);
-        bx0 = g.cx - (2.0 * g.geo / 9.0) * g.hx;
-        by0 = g.cy - (2.0 * g.geo / 9.0) * g.hy;
+        bx0 = g.cx - (g.geo * (2.0 / 9.0)) * g.hx;
+        by0 = g.cy - (g.geo * (2.0 / 9.0)) * g.hy;
         if (g.cx * g.cx + g.cy * g.cy <= g.rho * g.rho) {  // filled boundaries: own-ship inside => range 0
           if (g.pent)
             inside = vessel_inside_pentagon(bx0, by0, g.geo, g.hx, g.hy);
@@ -974,7 +974,8 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
         const float psi_m_pi = (float)(HAND(el, NAV_PSI) - AUV_PI);
         const float ecx = q.ecx, ecy = q.ecy, rho = q.rho;
         const float slack = rho * 1e-5f + 1e-4f;
-        AUV_CHECK(batch.status, tot <= R && lo1 >= 0 && lo1 + n1 <= R && lo2 >= 0 && lo2 + n2 <= R && (ngon || nq <= A.vmax));
+        AUV_CHECK(batch.status, tot <= R && (n1 == 0 || (lo1 >= 0 && lo1 + n1 <= R)) && (n2 == 0 || (lo2 >= 0 && lo2 + n2 <= R)) &&
+                                    (ngon || nq <= A.vmax));
         for (int u = lane; u < tot; u += 32) {
           const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
           AUV_CHECK(batch.status, i >= 0 && i < R && i < rpad);
@@ -1024,7 +1025,10 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
       // are and were all zero are neither computed nor stored
       unsigned* nzrow = use_nz ? sm.nz + el * nzw : nullptr;
       bool nz_dirty = false;
-      if (cnt > 0 || nzrow != nullptr) {
+      // an env with nothing in range whose row is already all zero is done (a quarter of the envs, typically)
+      const bool all_clear = nzrow != nullptr && cnt == 0 && !__any_sync(AUV_FULL, lane < nzw && nzrow[lane] != 0u);
+      if (all_clear) {
+      } else if (cnt > 0 || nzrow != nullptr) {
         const double cpsi = HAND(el, NAV_COSPSI), spsi = HAND(el, NAV_SINPSI);
         const ObstRec* grec = reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
         for (int k0 = 0; k0 < (R + 1) / 2; k0 += 32) {

@@ -74,8 +74,9 @@ __device__ __forceinline__ void pchip_eval2(const AuvPathBank& pb, int pid, doub
                                             PchipOut& o1, PchipOut& o2) {
   const int nk = pb.n_knots;
   const double* __restrict__ base = pb.pp + (long long)pid * (nk - 1) * AUV_PP_W;
-  int j1 = max(0, min(nk - 2, (int)((s1 / L) * (nk - 1))));
-  int j2 = max(0, min(nk - 2, (int)((s2 / L) * (nk - 1))));
+  const double per = (double)(nk - 1) / L;  // pieces per metre: the uniform guess (settled against the record's own knots)
+  int j1 = max(0, min(nk - 2, (int)(s1 * per)));
+  int j2 = max(0, min(nk - 2, (int)(s2 * per)));
   PPiece p1 = pp_load(base, j1), p2 = pp_load(base, j2);
   pp_settle(base, nk, s1, j1, p1);
   pp_settle(base, nk, s2, j2, p2);
@@ -112,6 +113,26 @@ __device__ __forceinline__ float seg_d2_f(float qx, float qy, float2 A, float2 B
   }
   const float cr = wx * ey - wy * ex;
   return cr * cr / len2;
+}
+
+// the same distance as the exact fraction num / den (den > 0): candidates are compared by cross-multiplication,
+// one division for the winner instead of one per segment (FP64 divisions are ~20 instructions each)
+__device__ __forceinline__ void seg_d2_frac(double px, double py, double2 A, double2 B, double& num, double& den) {
+  const double ex = B.x - A.x, ey = B.y - A.y;
+  const double wx = px - A.x, wy = py - A.y;
+  const double len2 = ex * ex + ey * ey;
+  const double t = wx * ex + wy * ey;
+  den = 1.0;
+  if (len2 == 0.0 || t <= 0.0) {
+    num = wx * wx + wy * wy;
+  } else if (t >= len2) {
+    const double zx = px - B.x, zy = py - B.y;
+    num = zx * zx + zy * zy;
+  } else {
+    const double cr = wx * ey - wy * ex;
+    num = cr * cr;
+    den = len2;
+  }
 }
 
 // ---- sub-warp groups: G consecutive lanes (G = 4, 8, 16 or 32) work on one env
@@ -248,7 +269,7 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
   } else {
     ub = project_cold_bound<G>(T, nblk, nsb, qx, qy, pad, lane, gm);  // first step of an episode: out of line
   }
-  double best_d2 = INFINITY;
+  double best_num = INFINITY, best_den = 1.0;  // smallest squared distance so far, as a fraction
   int best_seg = 0x7fffffff;
   // superblocks in windows of 32 (one bit each); the lanes test different superblocks
   for (int w0 = 0; w0 < nsb; w0 += 32) {
@@ -289,10 +310,12 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
         for (int u = 0; u < KS; ++u) {
           const double2 vb = poly[min(k0 + u + 1, se)];
           if (k0 + u < se) {
-            const double d2 = seg_d2(px, py, va, vb);
-            // a lane's segments come in increasing order over the whole search
-            if (d2 < best_d2) {
-              best_d2 = d2;
+            double num, den;
+            seg_d2_frac(px, py, va, vb, num, den);
+            // a lane's segments come in increasing order over the whole search: strictly smaller only
+            if (num * best_den < best_num * den) {
+              best_num = num;
+              best_den = den;
               best_seg = k0 + u;
             }
           }
@@ -303,6 +326,7 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
   }
 #undef AUV_TIGHTEN
 #undef AUV_PRUNED
+  double best_d2 = best_num / best_den;
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) {  // lexicographic (distance, segment) arg-min over the group
     const double od = __shfl_xor_sync(gm, best_d2, o);
@@ -345,7 +369,8 @@ __device__ AUV_NAVIGATE_INLINE void navigate_env(const AuvConfig& cfg, const Auv
   // cross-track error = second row of Rz(-chi) applied to (path(s) - p); cos/sin(chi) are the
   // normalised derivative (no trig needed)
   const double dn = sqrt(d_x * d_x + d_y * d_y);
-  const double cc = dn > 0.0 ? d_x / dn : 1.0, sc = dn > 0.0 ? d_y / dn : 0.0;
+  const double idn = dn > 0.0 ? 1.0 / dn : 0.0;
+  const double cc = dn > 0.0 ? d_x * idn : 1.0, sc = d_y * idn;
   const double y_e = -sc * (p_x - px) + cc * (p_y - py);
   // heading errors feed float32 observations and cos() in the reward: FP32 atan2 (~2e-7 rad)
   const double la_err = princip((double)atan2f((float)ldy, (float)ldx) - psi);

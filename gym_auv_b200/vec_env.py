@@ -13,6 +13,7 @@ PyTorch is used for device memory and streams only; all arithmetic is in
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -292,7 +293,7 @@ class AUVVecEnv:
             self._scratch["rec"].data_ptr(), self._scratch["rec_cnt"].data_ptr(),
             self._scratch["status"].data_ptr(), self.rec_cap, 0,
             s["obst_steps"].data_ptr(), s["prev_seg"].data_ptr(), s["env_pid"].data_ptr(),
-            self._scratch["obs_nz"].data_ptr(),
+            None if os.environ.get("AUV_B200_NO_OBS_NZ") else self._scratch["obs_nz"].data_ptr(),
         )
 
         # ---- outputs
@@ -567,7 +568,8 @@ class AUVVecEnv:
         if st & _lib.STATUS_GEN_GAVE_UP:
             raise RuntimeError("scenario generator: an obstacle slot was still rejected after 100000 draws")
         if st & _lib.STATUS_BOUNDS:
-            raise RuntimeError("AUV_DEBUG_BOUNDS build: an index check inside a step kernel failed")
+            raise RuntimeError("AUV_DEBUG_BOUNDS build: an index check inside a step kernel failed "
+                               f"(source lines OR-ed together: {st >> 8})")
         if st & _lib.STATUS_PATH_TOO_LONG:
             raise RuntimeError("a generated path's polyline does not fit its slot: raise DevicePathBank(vcap=...)")
         if st & _lib.STATUS_POLY_TOO_LARGE:
