@@ -72,7 +72,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-envs", type=int, default=8)
     ap.add_argument("--cpu-sample-steps", type=int, default=400)
-    ap.add_argument("--chunks", type=int, default=4,
+    ap.add_argument("--chunks", type=int, default=2,
                     help="env ranges per step on the pipeline's own streams (auv_step_chunked); 1 = single stream")
     ap.add_argument("--chunk-streams", type=int, default=None)
     ap.add_argument("--host-chunks", type=int, default=4,

@@ -130,6 +130,13 @@ class AuvScenarioPool(C.Structure):
         ("world_circle", _vp),
         ("world_voff", _vp),
         ("world_verts", _vp),
+        ("world_cell_off", _vp),
+        ("world_cell_items", _vp),
+        ("world_grid_x0", C.c_double),
+        ("world_grid_y0", C.c_double),
+        ("world_grid_cell", C.c_double),
+        ("world_grid_nx", C.c_int32),
+        ("world_grid_ny", C.c_int32),
         ("reset_obs", _vp),
         ("reset_max_progress", _vp),
         ("reset_mask", _vp),
@@ -163,7 +170,6 @@ class AuvBatch(C.Structure):
         ("obst_steps", _vp),
         ("prev_seg", _vp),
         ("env_pid", _vp),
-        ("obs_nz", _vp),
     ]
 
 

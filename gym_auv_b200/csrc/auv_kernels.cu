@@ -333,6 +333,24 @@ __device__ __forceinline__ SlotGeom load_slot(const AuvScenarioPool& pool, const
   return g;
 }
 
+// is obstacle slot j within sensor range of the own-ship?  dist(p0, o.boundary) - width < range (vessel.py:266-273):
+// decided from the enclosing circle when it can be, else from the exact boundary distance
+__device__ __forceinline__ bool slot_is_near(const AuvScenarioPool& pool, const AuvBatch& batch,
+                                             const double2* __restrict__ unit64, int e, int scn, int j, double px,
+                                             double py, int n_upd, double range, double width) {
+  const SlotGeom g = load_slot(pool, batch, e, scn, j, px, py, n_upd);
+  if (!g.valid) return false;
+  const double dc = sqrt(g.cx * g.cx + g.cy * g.cy);
+  if (dc - g.rho - width >= range + 1e-6) return false;  // the boundary lies inside the enclosing circle: distance >= dc - rho
+  if (dc + g.rho - width < range - 1e-6) return true;    // ... and distance <= dc + rho
+  const double bx0 = g.cx - (g.geo * (2.0 / 9.0)) * g.hx, by0 = g.cy - (g.geo * (2.0 / 9.0)) * g.hy;
+  bool in_dummy;
+  const double dist = g.world ? world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + g.vbase, g.nv, px,
+                                                       py, in_dummy)
+                              : boundary_distance(g.pent, g.cx, g.cy, bx0, by0, g.geo, g.hx, g.hy, g.nv, unit64);
+  return (dist - width) < range;
+}
+
 // Culling stage for one env by its group of G lanes: the lanes take different obstacle slots
 // (slot j of a 32-slot word belongs to lane j % G), records are emitted in slot order by a
 // ballot prefix.  `store` is false for the padding groups past the end of the env range.
@@ -349,41 +367,48 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
   const double range = cfg.sensor_range, width = cfg.vessel_width;
   ObstRec* rec = reinterpret_cast<ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
   int cnt = 0;
-  for (int base = 0; base < S; base += 32) {
-    unsigned word;
-    unsigned* mw = batch.nearby_mask + (long long)e * batch.mask_words + (base >> 5);
-    if (refresh) {
-      // ---- nearby list: {o : dist(p0, o.boundary) - width < range}   vessel.py:266-273
-      word = 0u;
+  if (refresh) {
+    // ---- nearby list: {o : dist(p0, o.boundary) - width < range}   vessel.py:266-273
+    const int K = pool.k_moving + pool.k_static;
+    const bool grid = pool.world_cell_off != nullptr && pool.n_world > 0;  // world slots through the broad phase
+    const int S_scan = grid ? K : S;
+    for (int base = 0; base < S; base += 32) {
+      unsigned word = 0u;
+      if (base < S_scan) {
 #pragma unroll 1
-      for (int k = 0; k < 32 / G; ++k) {
-        const int j = base + k * G + sub;
-        bool near = false;
-        if (j < S) {
-          const SlotGeom g = load_slot(pool, batch, e, scn, j, px, py, n_upd);
-          if (g.valid) {
-            const double dc = sqrt(g.cx * g.cx + g.cy * g.cy);
-            if (dc - g.rho - width >= range + 1e-6) {
-              near = false;  // the boundary lies inside the enclosing circle: distance >= dc - rho
-            } else if (dc + g.rho - width < range - 1e-6) {
-              near = true;  // ... and distance <= dc + rho
-            } else {
-              const double bx0 = g.cx - (g.geo * (2.0 / 9.0)) * g.hx, by0 = g.cy - (g.geo * (2.0 / 9.0)) * g.hy;
-              bool in_dummy;
-              const double dist =
-                  g.world ? world_polygon_distance(reinterpret_cast<const double2*>(pool.world_verts) + g.vbase, g.nv,
-                                                   px, py, in_dummy)
-                          : boundary_distance(g.pent, g.cx, g.cy, bx0, by0, g.geo, g.hx, g.hy, g.nv, unit64);
-              near = (dist - width) < range;
-            }
+        for (int k = 0; k < 32 / G; ++k) {
+          const int j = base + k * G + sub;
+          const bool near = j < S_scan && slot_is_near(pool, batch, unit64, e, scn, j, px, py, n_upd, range, width);
+          word |= group_ballot<G>(gm, lane, near) << (k * G);
+        }
+      }
+      if (store && sub == 0) batch.nearby_mask[(long long)e * batch.mask_words + (base >> 5)] = word;
+    }
+    if (grid) {
+      // uniform grid over the world's enclosing circles: only the polygons listed in the cells that the
+      // detection disc's bounding box overlaps can be near; the exact test is the same
+      __syncwarp(gm);
+      const double rq = range + width + 1e-3, cell = pool.world_grid_cell;
+      const int ix0 = max(0, (int)floor((px - rq - pool.world_grid_x0) / cell));
+      const int ix1 = min(pool.world_grid_nx - 1, (int)floor((px + rq - pool.world_grid_x0) / cell));
+      const int iy0 = max(0, (int)floor((py - rq - pool.world_grid_y0) / cell));
+      const int iy1 = min(pool.world_grid_ny - 1, (int)floor((py + rq - pool.world_grid_y0) / cell));
+      for (int iy = iy0; iy <= iy1; ++iy)
+        for (int ix = ix0; ix <= ix1; ++ix) {
+          const int c = iy * pool.world_grid_nx + ix;
+          const int i0 = pool.world_cell_off[c], i1 = pool.world_cell_off[c + 1];
+          for (int it = i0 + sub; it < i1; it += G) {
+            const int j = K + pool.world_cell_items[it];
+            if (store && slot_is_near(pool, batch, unit64, e, scn, j, px, py, n_upd, range, width))
+              atomicOr(batch.nearby_mask + (long long)e * batch.mask_words + (j >> 5), 1u << (j & 31));
           }
         }
-        word |= group_ballot<G>(gm, lane, near) << (k * G);
-      }
-      if (store && sub == 0) *mw = word;
-    } else {
-      word = *mw;
     }
+    __syncwarp(gm);
+  }
+  for (int base = 0; base < S; base += 32) {
+    const unsigned* mw = batch.nearby_mask + (long long)e * batch.mask_words + (base >> 5);
+    const unsigned word = refresh ? __ldcg(mw) : *mw;
     // ---- one record per nearby obstacle: lane `sub` takes the (sub + t G)-th set bit of the word
     //      ("by rank"), so the groups of a warp run the expensive window arithmetic together
     if (windows_out != nullptr && store) {
@@ -715,12 +740,10 @@ struct LidarSmem {
   float* pen;       // [E]       sum of w_i (penalty_i - clear penalty) over hit rays
   int* flag;        // [E]       bit 0 collision, bit 1 auto-reset pending
   int* next;        // [E]       scenario the env resets onto
-  unsigned* nz;     // [E][nzw]  non-zero pattern of the envs' observation rows (AuvBatch.obs_nz)
 };
 __host__ __device__ constexpr size_t lidar_smem_bytes_for(int E, int rpad, int vmax, int vel) {
   return (size_t)E * 16 * 8 + (size_t)E * rpad * (vel ? 8 : 4) + AUV_LIDAR_RCAP * sizeof(ObstRec) + AUV_LIDAR_RCAP * 4 +
-         (size_t)(AUV_LIDAR_THREADS / 32) * vmax * 8 + 64 * 8 + 48 * 4 + 32 * 4 + 32 * 4 + 32 * 4 +
-         (size_t)E * 2 * ((rpad + 63) / 64) * 4;
+         (size_t)(AUV_LIDAR_THREADS / 32) * vmax * 8 + 64 * 8 + 48 * 4 + 32 * 4 + 32 * 4 + 32 * 4;
 }
 __device__ __forceinline__ LidarSmem lidar_carve(unsigned char* p, int E, int rpad, int vmax, int vel) {
   LidarSmem s;
@@ -743,8 +766,6 @@ __device__ __forceinline__ LidarSmem lidar_carve(unsigned char* p, int E, int rp
   s.flag = reinterpret_cast<int*>(p);
   p += 32 * 4;
   s.next = reinterpret_cast<int*>(p);
-  p += 32 * 4;
-  s.nz = reinterpret_cast<unsigned*>(p);
   return s;
 }
 
@@ -855,10 +876,6 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
   // ---- phase 1: hand-over lines, unit table, range rows
   for (int k = tid; k < ne * 16; k += AUV_LIDAR_THREADS)
     sm.hand[k] = batch.nav[(long long)(env0 + (k >> 4)) * AUV_NAV_W + NAV_HAND + (k & 15)];
-  const int nzw = 2 * ((R + 63) / 64);
-  const bool use_nz = cfg.use_lidar && batch.obs_nz != nullptr && (A.obs_dim & 1) == 0 && !cfg.sensor_use_velocity_observations;
-  if (use_nz)
-    for (int k = tid; k < ne * nzw; k += AUV_LIDAR_THREADS) sm.nz[k] = batch.obs_nz[(long long)env0 * nzw + k];
   if (cfg.use_lidar) {
     if (tid < 64) {
       const double2 un = reinterpret_cast<const double2*>(A.rays.unit64)[tid];
@@ -1021,52 +1038,18 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
                             : (const void*)(reinterpret_cast<const float*>(sm.sdist) + (size_t)el * rpad);
       float extra = 0.f;
       bool collision = false;
-      // which 64-ray groups of the row hold a non-zero closeness (bit = lane of the float2 pair): groups that
-      // are and were all zero are neither computed nor stored
-      unsigned* nzrow = use_nz ? sm.nz + el * nzw : nullptr;
-      bool nz_dirty = false;
-      // an env with nothing in range whose row is already all zero is done (a quarter of the envs, typically)
-      const bool all_clear = nzrow != nullptr && cnt == 0 && !__any_sync(AUV_FULL, lane < nzw && nzrow[lane] != 0u);
-      if (all_clear) {
-      } else if (cnt > 0 || nzrow != nullptr) {
+      if (cnt > 0) {
         const double cpsi = HAND(el, NAV_COSPSI), spsi = HAND(el, NAV_SINPSI);
         const ObstRec* grec = reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
-        for (int k0 = 0; k0 < (R + 1) / 2; k0 += 32) {
-          const int k = k0 + lane;
-          const int j = k0 >> 5;
+        for (int k = lane; k < (R + 1) / 2; k += 32) {
           float cl2[2] = {0.f, 0.f};
-          bool hit[2] = {false, false};
-          float dd[2] = {rangef, rangef};
-          if (cnt > 0 && k < (R + 1) / 2) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int i = 2 * k + h;
-              if (i < R) {
-                dd[h] = range_get<VEL>(row, i);
-                hit[h] = dd[h] < rangef;
-              }
-            }
-          }
-          const unsigned m0 = __ballot_sync(AUV_FULL, hit[0]), m1 = __ballot_sync(AUV_FULL, hit[1]);
-          if (nzrow != nullptr) {
-            const unsigned p0 = nzrow[2 * j], p1 = nzrow[2 * j + 1];  // warp-uniform
-            if ((m0 | m1 | p0 | p1) == 0u) continue;               // nothing there, nothing was there
-            if (m0 != p0 || m1 != p1) {
-              nz_dirty = true;
-              if (lane == 0) {
-                nzrow[2 * j] = m0;
-                nzrow[2 * j + 1] = m1;
-              }
-            }
-          }
-          if (k >= (R + 1) / 2) continue;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int i = 2 * k + h;
             if (i >= R) continue;
-            const float d = dd[h];
+            const float d = range_get<VEL>(row, i);
             float vxr = 0.f, vyr = 0.f;
-            if (hit[h]) {
+            if (d < rangef) {
               if (cfg.sensor_log_transform)  // log(1 + d) by the hardware log2: |error| < 1e-6 of a value in [0, 5]
                 cl2[h] = 1.f - fminf(fmaxf(__logf(1.f + d) * A.inv_log_range, 0.f), 1.f);
               else
@@ -1102,10 +1085,6 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
         }
         collision = __any_sync(AUV_FULL, collision);
         extra = warp_sum(extra);
-        if (nz_dirty) {  // warp-uniform
-          __syncwarp();
-          if (lane < nzw) batch.obs_nz[(long long)e * nzw + lane] = nzrow[lane];
-        }
       } else {
         if (vec2) {
           float2* o2 = reinterpret_cast<float2*>(obs + 6);
@@ -1285,18 +1264,6 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
     for (int k = lane; k < A.obs_dim; k += 32) {
       if (tobs) tobs[k] = obs[k];
       obs[k] = robs[k];
-    }
-    if (batch.obs_nz != nullptr && cfg.use_lidar) {  // non-zero pattern of the row that was just copied in
-      unsigned* nzrow = batch.obs_nz + (long long)e * nzw;
-      for (int k0 = 0; k0 < (R + 1) / 2; k0 += 32) {
-        const int k = k0 + lane;
-        const bool z0 = 2 * k < R && robs[6 + 2 * k] != 0.f, z1 = 2 * k + 1 < R && robs[6 + 2 * k + 1] != 0.f;
-        const unsigned m0 = __ballot_sync(AUV_FULL, z0), m1 = __ballot_sync(AUV_FULL, z1);
-        if (lane == 0) {
-          nzrow[2 * (k0 >> 5)] = m0;
-          nzrow[2 * (k0 >> 5) + 1] = m1;
-        }
-      }
     }
     if (!A.pool.linear_tracks)
       for (int j = lane; j < km; j += 32) {

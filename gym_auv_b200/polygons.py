@@ -82,6 +82,33 @@ class World:
             c, rad = enclosing_circle(r)
             circ[i] = (c[0], c[1], rad)
         self.circle = circ
+        self._grid = None
+
+    def grid(self, cell: float = 160.0):
+        """Uniform grid over the enclosing circles (AuvScenarioPool.world_cell_*): CSR lists of the
+        polygons whose circle overlaps each cell.  Returns dict(x0, y0, cell, nx, ny, off, items)."""
+        if self._grid is not None and self._grid["cell"] == cell:
+            return self._grid
+        if self.n == 0:
+            return None
+        c = self.circle
+        x0, y0 = float((c[:, 0] - c[:, 2]).min()), float((c[:, 1] - c[:, 2]).min())
+        x1, y1 = float((c[:, 0] + c[:, 2]).max()), float((c[:, 1] + c[:, 2]).max())
+        nx, ny = int(max(1, math.ceil((x1 - x0) / cell))), int(max(1, math.ceil((y1 - y0) / cell)))
+        cells = [[] for _ in range(nx * ny)]
+        for j in range(self.n):
+            ix0 = int(max(0, math.floor((c[j, 0] - c[j, 2] - x0) / cell)))
+            ix1 = int(min(nx - 1, math.floor((c[j, 0] + c[j, 2] - x0) / cell)))
+            iy0 = int(max(0, math.floor((c[j, 1] - c[j, 2] - y0) / cell)))
+            iy1 = int(min(ny - 1, math.floor((c[j, 1] + c[j, 2] - y0) / cell)))
+            for iy in range(iy0, iy1 + 1):
+                for ix in range(ix0, ix1 + 1):
+                    cells[iy * nx + ix].append(j)
+        off = np.zeros(nx * ny + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(v) for v in cells])
+        items = np.array([j for v in cells for j in v], dtype=np.int32) if off[-1] else np.zeros(1, dtype=np.int32)
+        self._grid = dict(x0=x0, y0=y0, cell=float(cell), nx=nx, ny=ny, off=off, items=items)
+        return self._grid
 
 
 def star_polygon(rng, centre, circumradius: float, n_vertices: int) -> np.ndarray:

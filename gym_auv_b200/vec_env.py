@@ -106,6 +106,8 @@ class AUVVecEnv:
                 (sensor.py:100-137): per ray the displacement of the nearest hit obstacle rotated into the
                 ray frame -- it feeds ``max(0, v_y)`` of the Colav penalty (rewarder.py:199-206) and, with
                 ``sensor_use_velocity_observations``, the 2 R velocity channels of the observation
+    world_grid : nearby-list refreshes over a shared world of more than 32 land polygons go through a
+                uniform grid over their enclosing circles instead of testing every polygon (same result)
     compact_host : step_host / step_async send the observations to the host in the lossless compact
                 form (head + hit mask + non-zero closeness values, auv_step_host_compact_submit) and expand
                 them into the dense [N, obs_dim] array with ``host_threads`` host threads; results are
@@ -134,6 +136,7 @@ class AUVVecEnv:
         velocity_mode: str = "zero",
         linear_tracks="auto",
         reset_stride: int = 0,
+        world_grid: bool = True,
         compact_host: bool = True,
         host_threads: Optional[int] = None,
         _shared: Optional[dict] = None,
@@ -224,6 +227,10 @@ class AUVVecEnv:
                 world_circle=t(world.circle, torch.float64), world_voff=t(world.voff, torch.int32),
                 world_verts=t(world.verts, torch.float64),
             )
+            if world_grid and Pw > 32:  # broad phase of the nearby refresh: uniform grid over the enclosing circles
+                g = world.grid(float(self.config.vessel.sensor_range) + 10.0)
+                self._pool.update(world_cell_off=t(g["off"], torch.int32), world_cell_items=t(g["items"], torch.int32))
+                self._pool["world_grid"] = g
         if _shared is None:
             # cached first observation of every scenario (filled by _build_reset_cache)
             self._pool.update(
@@ -241,6 +248,10 @@ class AUVVecEnv:
             p["st_rec"].data_ptr(), wptr("mov_lin"), int(lin is not None), lin["first_wrap"] if lin else 0,
             lin["wrap_period"] if lin else 0, 0,
             wptr("world_circle"), wptr("world_voff"), wptr("world_verts"),
+            wptr("world_cell_off"), wptr("world_cell_items"),
+            p["world_grid"]["x0"] if "world_grid" in p else 0.0, p["world_grid"]["y0"] if "world_grid" in p else 0.0,
+            p["world_grid"]["cell"] if "world_grid" in p else 0.0,
+            p["world_grid"]["nx"] if "world_grid" in p else 0, p["world_grid"]["ny"] if "world_grid" in p else 0,
             p["reset_obs"].data_ptr(), p["reset_max_progress"].data_ptr(), p["reset_mask"].data_ptr(),
         )
         if _shared is None:
@@ -279,8 +290,6 @@ class AUVVecEnv:
         self._scratch = dict(
             rec=torch.zeros((N, self.rec_cap, _lib.REC_BYTES), dtype=torch.uint8, device=dev),
             rec_cnt=z(N, torch.int32), status=z(1, torch.int32),
-            # which closeness entries of the observation buffer are non-zero (all ones = unknown: first step writes all)
-            obs_nz=torch.full((N, 2 * ((max(R, 1) + 63) // 64)), -1, dtype=torch.int32, device=dev),
         )
         s = self._st
         sptr = lambda k: s[k].data_ptr() if k in s else None
@@ -293,7 +302,6 @@ class AUVVecEnv:
             self._scratch["rec"].data_ptr(), self._scratch["rec_cnt"].data_ptr(),
             self._scratch["status"].data_ptr(), self.rec_cap, 0,
             s["obst_steps"].data_ptr(), s["prev_seg"].data_ptr(), s["env_pid"].data_ptr(),
-            None if os.environ.get("AUV_B200_NO_OBS_NZ") else self._scratch["obs_nz"].data_ptr(),
         )
 
         # ---- outputs

@@ -195,6 +195,14 @@ typedef struct AuvScenarioPool {
   const double* world_circle;  /* [n_world][3] cx, cy, rho                              */
   const int32_t* world_voff;   /* [n_world+1] first vertex of each closed ring          */
   const double* world_verts;   /* [total][2]  rings, last vertex repeats the first      */
+  /* broad phase of the nearby-list refresh over the world (vessel.py:266-273 asks every obstacle):
+   * a uniform grid over the enclosing circles -- polygon j is listed in every cell its circle
+   * overlaps; a query visits the cells the own-ship's detection disc overlaps and runs the exact
+   * distance test only on the polygons listed there.  NULL world_cell_off = test every polygon. */
+  const int32_t* world_cell_off;   /* [nx ny + 1] CSR offsets into world_cell_items, cell = iy nx + ix */
+  const int32_t* world_cell_items; /* polygon indices                                       */
+  double world_grid_x0, world_grid_y0, world_grid_cell; /* origin of cell (0, 0) and the cell size */
+  int32_t world_grid_nx, world_grid_ny;
   /* what reset() returns depends on the scenario only: with auto_reset these caches (filled
    * once by running auv_reset + auv_observe(RESET) over the pool) turn the in-step reset of
    * a finished env into a copy */
@@ -242,12 +250,6 @@ typedef struct AuvBatch {
   int32_t* prev_seg;      /* [N] polyline segment the last projection ended on, -1 = none:
                              warm start of the next one (an upper bound only; the search stays exact) */
   int32_t* env_pid;       /* [N] pool.path_id[scn_id[e]], cached by reset                       */
-  uint32_t* obs_nz;       /* [N][2 ceil(n_sensors / 64)] or NULL: which closeness entries of AuvStepOut.obs
-                             are non-zero (internal encoding), initialised to all ones by the caller.
-                             ~85 % of the closeness block is 0 from one step to the next: with this
-                             scratch the casting stage only stores the 64-ray groups that hold, or
-                             held, a non-zero value.  Requires that nobody else writes AuvStepOut.obs
-                             between calls (it is the env's persistent output buffer)              */
 } AuvBatch;
 
 /* Outputs of one step / observe (all optional except obs/reward/done). */

@@ -208,8 +208,7 @@ def test_compact_host_step_is_bit_identical_to_the_dense_copy():
     """step_host / step_async ship head + hit mask + packed non-zero closeness values straight into
     pinned host memory (k_obs_ship) and expand them on the host (auv_compact_expand): the dense array
     they return equals the device observation and the dense D2H copy bit for bit -- through
-    auto-resets (the cached first observation replaces the row) and with the zero-group skipping of
-    the casting stage (obs_nz)."""
+    auto-resets (the cached first observation replaces the row)."""
     from gym_auv_b200.vec_env import AUVVecEnv
 
     cfg = lidar_config()
@@ -469,3 +468,29 @@ print("bounds ok", int(env._scratch["status"].item()))
     out = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, env=env,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0 and "bounds ok 0" in out.stdout, out.stdout[-1500:] + out.stderr[-3000:]
+
+
+def test_world_grid_broad_phase_equals_the_full_scan():
+    """The nearby-list refresh over a shared world of land polygons through the uniform grid over their
+    enclosing circles lists exactly the polygons the full scan lists: bit-identical masks, records,
+    observations over a rollout with several refreshes."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    n = 512
+    scn = S.land_scenarios(n, n_polygons=300, n_moving=3, n_static=3, seed=6, n_paths=8, extent=2500.0)
+    e1 = AUVVecEnv(scn, n, cfg, test_mode=True, auto_reset=False, debug=True, world_grid=True)
+    e2 = AUVVecEnv(scn, n, cfg, test_mode=True, auto_reset=False, debug=True, world_grid=False)
+    assert "world_cell_off" in e1._pool and "world_cell_off" not in e2._pool
+    o1, o2 = e1.reset(), e2.reset()
+    assert torch.equal(o1, o2) and torch.equal(e1._st["nearby_mask"], e2._st["nearby_mask"])
+    assert int(e1._st["nearby_mask"].ne(0).sum()) > 0
+    a = torch.as_tensor(random_actions(55, n, 5), dtype=torch.float32, device="cuda")
+    a[:, :, 0] = a[:, :, 0].abs()
+    for t in range(55):
+        o1, r1, d1, _ = e1.step(a[t])
+        o2, r2, d2, _ = e2.step(a[t])
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+        assert torch.equal(e1._st["nearby_mask"], e2._st["nearby_mask"]), t
+        assert torch.equal(e1._scratch["rec_cnt"], e2._scratch["rec_cnt"])
+    e1.check_status(), e2.check_status()
