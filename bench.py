@@ -75,6 +75,7 @@ def parse():
     ap.add_argument("--chunks", type=int, default=2,
                     help="env ranges per step on the pipeline's own streams (auv_step_chunked); 1 = single stream")
     ap.add_argument("--chunk-streams", type=int, default=None)
+    ap.add_argument("--host-threads", type=int, default=None, help="host threads of auv_compact_expand (default: min(16, cores))")
     ap.add_argument("--host-chunks", type=int, default=4,
                     help="env ranges of the host-buffer step (auv_step_host_chunked): D2H of a range overlaps the next")
     ap.add_argument("--gpu-scenarios", action="store_true", help="(default; kept for old command lines)")
@@ -291,8 +292,13 @@ def run_ours(args):
     N, K, Wm = args.envs, args.steps, max(args.warmup, 3)
     R = cfg.vessel.n_sensors
     fresh = args.workload == "moving" and not args.host_scenarios  # a fresh GPU-generated scenario per episode
+    # host threads of the compact-transfer expansion: the cores this rank may use, shared by the ranks of the box
+    cores_here = len(os.sched_getaffinity(0))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_threads = args.host_threads or max(1, min(16, cores_here // max(local_world, 1)))
     env = AUVVecEnv(scn, N, cfg, device=device, test_mode=False, auto_reset=True, env_offset=0,
-                    chunks=args.chunks, chunk_streams=args.chunk_streams, host_chunks=args.host_chunks)
+                    chunks=args.chunks, chunk_streams=args.chunk_streams, host_chunks=args.host_chunks,
+                    host_threads=host_threads)
     seed = args.seed + 1000 * rank
     scenario_gen = {"where": "host", "scenarios": scn.n_scenarios}
     if fresh:
@@ -499,12 +505,14 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t_a, op=dist.ReduceOp.MAX)
         a_ms = 1e3 * float(t_a.item()) / (ke + 1)
+        expand_ms = 1e3 * sum(g.expand_seconds for g in groups) / (ke + 4 + 1)  # per step of N envs (both groups), incl. warm-up steps
         sync_part = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "host_chunks": e2e["host_chunks"],
                      "call": "AUVVecEnv.step_host (one synchronous call per step)"}
         e2e.update({"value": world * 2 * half * (ke + 1) / float(t_a.item()), "ms_per_step": a_ms, "steps": ke + 1,
                     "mode": "AUVVecEnv.step_async / step_wait, two groups of N/2 envs stepped alternately"
                             + (", fresh scenario per episode" if fresh else ""),
                     "d2h_bytes_per_step": sum(g.d2h_bytes_per_step for g in groups) * world,
+                    "host_expand_ms_per_step": expand_ms, "host_threads": groups[0].host_threads,
                     "host_chunks": groups[0].host_chunks, "sync": sync_part})
         torch.cuda.synchronize()
         for g in groups:

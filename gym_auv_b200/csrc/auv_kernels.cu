@@ -853,7 +853,7 @@ __device__ __forceinline__ void range_min(void* row, int i, float d, int slot) {
 }
 
 #ifndef AUV_LIDAR_MINB
-#define AUV_LIDAR_MINB 4  // 64 registers
+#define AUV_LIDAR_MINB 5  // 48 registers (4 / 5 / 6 CTAs per SM: 0.0807 / 0.0767 / 0.101 ms)
 #endif
 template <bool COUNT, bool VEL>
 __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(const __grid_constant__ LidarArgs A) {

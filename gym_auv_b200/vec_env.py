@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from typing import Dict, Optional
 
 import numpy as np
@@ -341,6 +342,7 @@ class AUVVecEnv:
         import os as _os
 
         self.host_threads = int(host_threads) if host_threads else max(1, min(16, len(_os.sched_getaffinity(0))))
+        self.expand_seconds = 0.0  # host time spent in auv_compact_expand (diagnostic)
         self.chunks = max(1, int(chunks))
         self.host_chunks = max(1, min(64, int(host_chunks))) if host_chunks else self.chunks
         self._pipe = None
@@ -722,9 +724,11 @@ class AUVVecEnv:
         self._async_pending = False
         pin = self._pinned
         if self.compact_host:  # scatter head / mask / packed values into the dense array (host threads)
+            t0 = time.perf_counter()
             _lib.check(self.lib.auv_compact_expand(
                 C.byref(self.cfg), self.num_envs, C.byref(pin["compact"]), C.c_void_p(pin["prev_mask"].ctypes.data),
                 C.c_void_p(pin["obs_dense"].ctypes.data), self.host_threads), "auv_compact_expand")
+            self.expand_seconds += time.perf_counter() - t0
             return pin["obs_dense"], pin["reward"].numpy(), pin["done"].numpy()
         return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy()
 
@@ -742,7 +746,8 @@ class AUVVecEnv:
         return [AUVVecEnv(self.scenarios, n, self.config, device=self.device, test_mode=self.test_mode,
                           auto_reset=bool(self.cfg.auto_reset), cull_mode=self._cull_mode, env_offset=g * n,
                           max_nearby=self._max_nearby, velocity_mode=self._velocity_mode,
-                          reset_stride=self.reset_stride or self.num_envs, _shared=shared, **kw)
+                          reset_stride=self.reset_stride or self.num_envs, host_threads=self.host_threads,
+                          compact_host=self.compact_host, _shared=shared, **kw)
                 for g in range(int(n_groups))]
 
     def step_host_buffers(self):
