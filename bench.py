@@ -610,7 +610,8 @@ def run_ours(args):
                         "note": "side note: the same K steps right after reset() (vessels at their path starts, nearby "
                                 "lists refreshed in lock-step) -- NOT the headline"},
         "e2e": e2e,
-        "gpu_launches": 2 * K * n_ranges(N, env.chunks) + (7 * (K // args.refresh_every) if fresh else 0),
+        # k_vessel_nav + k_nav_cull + k_lidar per env range, 6 kernels + 1 memset per scenario refresh
+        "gpu_launches": 3 * K * n_ranges(N, env.chunks) + (7 * (K // args.refresh_every) if fresh else 0),
         "roofline": roof,
         "episode_stats": stats_timed,
     }
