@@ -82,6 +82,8 @@ def parse():
     ap.add_argument("--host-scenarios", action="store_true",
                     help="sample vessel starts and obstacles with the host generator once (pool of N scenarios, replayed "
                          "on reset) instead of the default: GPU generator, pool of 2N, a fresh scenario per episode")
+    ap.add_argument("--host-paths", action="store_true",
+                    help="build the path bank with SciPy on the host (~14 s for 1024 paths) instead of auv_pathbank_build")
     ap.add_argument("--refresh-every", type=int, default=8,
                     help="steps between auv_refresh_finished calls (fresh scenarios for the envs that finished)")
     ap.add_argument("--preroll-steps", type=int, default=2000,
@@ -153,7 +155,7 @@ def build_workload(args, rank):
     cache = getattr(args, "scenario_cache", None)
     if cache:
         cache = (f"{cache}.{args.workload}.{args.envs}.{args.rays}.{args.n_moving}.{args.n_static}.{args.n_paths}."
-                 f"{args.seed}.{rank}.{int(bool(getattr(args, 'host_scenarios', False)))}")
+                 f"{args.seed}.{rank}.{int(bool(getattr(args, 'host_scenarios', False)))}{int(bool(getattr(args, 'host_paths', False)))}")
         if os.path.exists(cache):
             with open(cache, "rb") as f:
                 return pickle.load(f)
@@ -182,8 +184,10 @@ def _build_workload(args, rank):
                                seed=args.seed + 1000 * rank, n_paths=args.n_paths)
     elif not getattr(args, "host_scenarios", False):
         # pool of 2N slots, path-major within N: env e alternates between slots e and e + N
+        # the path bank is built on the GPU as well (auv_pathbank_build) unless --host-paths asks for SciPy
         scn = S.moving_obstacles_template(2 * args.envs, args.n_moving, args.n_static, seed=args.seed + 1000 * rank,
-                                          n_paths=args.n_paths, path_period=args.envs)
+                                          n_paths=args.n_paths, path_period=args.envs,
+                                          device_paths=not getattr(args, "host_paths", False))
     else:
         scn = S.moving_obstacles(args.envs, args.n_moving, args.n_static, seed=args.seed + 1000 * rank,
                                  n_paths=args.n_paths)
@@ -598,7 +602,7 @@ def run_ours(args):
                    + (f" + {args.n_polygons} shared land polygons" if args.workload == "land" else ""),
                    "envs_per_gpu": N, "rays": R, "obstacles": args.n_moving + args.n_static,
                    "paths": args.n_paths, "l2": "per-step working set (state + records + observations ~%.0f MB, path bank ~%.0f MB) exceeds the 126 MB L2; no explicit flush"
-                   % (N * ALGO_BYTES_PER_ENV_STEP / 1e6, (scn.bank.poly_xy.nbytes * 1.5 + scn.bank.coef.nbytes * 1.5) / 1e6),
+                   % (N * ALGO_BYTES_PER_ENV_STEP / 1e6, sum(v.numel() * v.element_size() for v in env._bank.values()) / 1e6),
                    "phase": "steady state: %d steps after reset(), auto-reset running, timed through AUVVecEnv.step" % (step_no[0] - 3 * K),
                    "auto_reset": True, "dones_per_step": dones_per_step, "records_per_env_step": steady_records,
                    "mean_abs_cross_track_m": cross_track,

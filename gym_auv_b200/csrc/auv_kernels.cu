@@ -994,60 +994,67 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
           continue;
         }
         const bool ngon = !(fl & (OFLAG_PENTAGON | OFLAG_WORLD)) && nq > 16;
-        if (!ngon) {
-          if (nq > A.vmax) {  // a polygon the vertex stage cannot hold: flagged, never silently miscast
-            if (lane == 0 && batch.status != nullptr) atomicOr(batch.status, AUV_STATUS_POLY_TOO_LARGE);
-            continue;
-          }
-          // stage the vertices: vessel-relative, formed in FP64, stored FP32
-          __syncwarp();
-          if (fl & OFLAG_WORLD) {
-            const double px = HAND(el, NAV_X), py = HAND(el, NAV_Y);
-            const double2* wv = reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase;
-            for (int k = lane; k < nq; k += 32) {
-              const double2 w = wv[k];
-              wverts[k] = make_float2((float)(w.x - px), (float)(w.y - py));
-            }
-          } else if (fl & OFLAG_PENTAGON) {
-            if (lane < 6) {
-              double vx, vy;
-              pent_vertex(lane == 5 ? 0 : lane, q.cx, q.cy, q.geo, q.hx, q.hy, vx, vy);
-              wverts[lane] = make_float2((float)vx, (float)vy);
-            }
-          } else {  // small polygonised circle (2 / 4 / 8 sides) incl. the closing vertex
-            const int ne_ = nq - 1, sh = 6 - (31 - __clz(ne_));
-            if (lane < nq) {
-              const double2 un = __ldg(&unit[(lane == ne_ ? 0 : lane) << sh]);
-              wverts[lane] = make_float2((float)(q.cx + q.geo * un.x), (float)(q.cy + q.geo * un.y));
-            }
-          }
-          __syncwarp();
+        if (!ngon && !(fl & OFLAG_WORLD) && nq > A.vmax) {  // cannot happen (pentagon 6, small n-gon <= 9 vertices)
+          if (lane == 0 && batch.status != nullptr) atomicOr(batch.status, AUV_STATUS_POLY_TOO_LARGE);
+          continue;
         }
         const double cpsi = HAND(el, NAV_COSPSI), spsi = HAND(el, NAV_SINPSI);
         const float psi_m_pi = (float)(HAND(el, NAV_PSI) - AUV_PI);
         const float ecx = q.ecx, ecy = q.ecy, rho = q.rho;
         const float slack = rho * 1e-5f + 1e-4f;
-        AUV_CHECK(batch.status, tot <= R && (n1 == 0 || (lo1 >= 0 && lo1 + n1 <= R)) && (n2 == 0 || (lo2 >= 0 && lo2 + n2 <= R)) &&
-                                    (ngon || nq <= A.vmax));
-        for (int u = lane; u < tot; u += 32) {
-          const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
-          AUV_CHECK(batch.status, i >= 0 && i < R && i < rpad);
-          const float cur = range_get<VEL>(row, i);
-          // ray direction in the world frame, formed in FP64 (vessel.py:317)
-          const double2 cs = cos_sin[i];
-          const float c = (float)(cs.x * cpsi - cs.y * spsi), sn = (float)(cs.y * cpsi + cs.x * spsi);
-          const float tc = ecx * c + ecy * sn;
-          const float hc = ecy * c - ecx * sn;
-          if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > cur) continue;
-          float got;
-          if (ngon) {
-            // world angle of ray i; only selects which polygon edge the analytic pick looks at
-            const float theta = fmaf((float)(i + 1), dth_f, psi_m_pi);
-            got = cast_ngon(ecx, ecy, rho, nq - 1, sm.unit, c, sn, theta, tc, hc, cur, rangef);
-          } else {
-            got = cast_chain(wverts, nq, c, sn, cur, rangef);
+        AUV_CHECK(batch.status, tot <= R && (n1 == 0 || (lo1 >= 0 && lo1 + n1 <= R)) && (n2 == 0 || (lo2 >= 0 && lo2 + n2 <= R)));
+        // a world polygon with more vertices than the stage holds is cast chain by chain (consecutive
+        // chains share their end vertex), so land perimeters of any length are supported
+        const int nchain = (!ngon && nq > A.vmax) ? (nq - 2) / (A.vmax - 1) + 1 : 1;
+        for (int ch = 0; ch < nchain; ++ch) {
+          const int v0 = ch * (A.vmax - 1);
+          const int nqc = nchain == 1 ? nq : min(nq - v0, A.vmax);
+          if (!ngon) {
+            // stage the vertices: vessel-relative, formed in FP64, stored FP32
+            __syncwarp();
+            if (fl & OFLAG_WORLD) {
+              const double px = HAND(el, NAV_X), py = HAND(el, NAV_Y);
+              const double2* wv = reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase + v0;
+              for (int k = lane; k < nqc; k += 32) {
+                const double2 w = wv[k];
+                wverts[k] = make_float2((float)(w.x - px), (float)(w.y - py));
+              }
+            } else if (fl & OFLAG_PENTAGON) {
+              if (lane < 6) {
+                double vx, vy;
+                pent_vertex(lane == 5 ? 0 : lane, q.cx, q.cy, q.geo, q.hx, q.hy, vx, vy);
+                wverts[lane] = make_float2((float)vx, (float)vy);
+              }
+            } else {  // small polygonised circle (2 / 4 / 8 sides) incl. the closing vertex
+              const int ne_ = nq - 1, sh = 6 - (31 - __clz(ne_));
+              if (lane < nq) {
+                const double2 un = __ldg(&unit[(lane == ne_ ? 0 : lane) << sh]);
+                wverts[lane] = make_float2((float)(q.cx + q.geo * un.x), (float)(q.cy + q.geo * un.y));
+              }
+            }
+            __syncwarp();
           }
-          if (got < cur) range_min<VEL>(row, i, got, slot);
+          AUV_CHECK(batch.status, ngon || nqc <= A.vmax);
+          for (int u = lane; u < tot; u += 32) {
+            const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
+            AUV_CHECK(batch.status, i >= 0 && i < R && i < rpad);
+            const float cur = range_get<VEL>(row, i);
+            // ray direction in the world frame, formed in FP64 (vessel.py:317)
+            const double2 cs = cos_sin[i];
+            const float c = (float)(cs.x * cpsi - cs.y * spsi), sn = (float)(cs.y * cpsi + cs.x * spsi);
+            const float tc = ecx * c + ecy * sn;
+            const float hc = ecy * c - ecx * sn;
+            if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > cur) continue;
+            float got;
+            if (ngon) {
+              // world angle of ray i; only selects which polygon edge the analytic pick looks at
+              const float theta = fmaf((float)(i + 1), dth_f, psi_m_pi);
+              got = cast_ngon(ecx, ecy, rho, nq - 1, sm.unit, c, sn, theta, tc, hc, cur, rangef);
+            } else {
+              got = cast_chain(wverts, nqc, c, sn, cur, rangef);
+            }
+            if (got < cur) range_min<VEL>(row, i, got, slot);
+          }
         }
       }
       __syncthreads();

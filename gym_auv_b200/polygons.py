@@ -68,8 +68,7 @@ class World:
                 raise ValueError("a polygon needs >= 3 (x, y) vertices")
             if not np.array_equal(r[0], r[-1]):
                 r = np.vstack([r, r[:1]])
-            if len(r) > 192:  # AUV_MAX_POLY_VERTS: one polygon must fit the per-warp vertex stage
-                raise ValueError("a world polygon may have at most 191 distinct vertices; split it")
+            # (any vertex count: the casting stage walks perimeters longer than its vertex stage chain by chain)
             rings.append(r)
         self.rings = rings
         self.n = len(rings)

@@ -494,3 +494,28 @@ def test_world_grid_broad_phase_equals_the_full_scan():
         assert torch.equal(e1._st["nearby_mask"], e2._st["nearby_mask"]), t
         assert torch.equal(e1._scratch["rec_cnt"], e2._scratch["rec_cnt"])
     e1.check_status(), e2.check_status()
+
+
+def test_realworld_scenario_matches_the_reference_episode_on_gpu():
+    """The reference's RealWorldEnv episode (land perimeters incl. one with 230 vertices -- more than
+    one vertex stage --, AIS vessel tracks; tests/golden/make_reference_goldens_realworld.py) through the
+    loaders and the CUDA step, in a batch of identical worlds."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+    from tests.test_realworld import GOLD, build_scenario
+
+    cfg = lidar_config()
+    scn, _, _ = build_scenario(n=40)
+    env = AUVVecEnv(scn, 40, cfg, test_mode=True, auto_reset=False, debug=True)
+    obs0 = env.reset().cpu().numpy()
+    assert np.abs(obs0 - GOLD["obs0"][None, :]).max() <= 1e-4
+    for t, a in enumerate(GOLD["actions"][: len(GOLD["obs"])]):
+        act = torch.as_tensor(np.tile(a, (40, 1)), dtype=torch.float32, device="cuda")
+        obs, rew, done, info = env.step(act)
+        d = env.get_attr("lidar_dist").cpu().numpy()
+        ref = GOLD["dists"][t]
+        assert (np.abs(d - ref[None, :]) <= 1e-4 + 1e-4 * ref[None, :]).all(), t
+        assert np.abs(obs.cpu().numpy() - GOLD["obs"][t][None, :]).max() <= 1e-4
+        assert np.abs(rew.cpu().numpy() - GOLD["reward"][t]).max() <= 1e-4 + 1e-4 * abs(GOLD["reward"][t])
+        assert int(env._scratch["rec_cnt"][0]) == int(GOLD["n_nearby"][t])
+        assert torch.equal(obs[0], obs[39])  # every env of the batch runs the same world
+    env.check_status()
