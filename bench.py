@@ -42,6 +42,20 @@ FLOP_PER_SEG_TEST = 16
 FLOP_PER_RAY = 60
 
 
+def workload_config(args, use_lidar=True):
+    """`config` of the JSON line: what names the workload -- identical for this arm and for `--impl reference`."""
+    R = args.rays if use_lidar else 0
+    default = args.workload == "moving" and args.envs == 65536 and args.rays == 180 and args.n_moving == 16 and args.n_static == 16
+    name = WORKLOAD if default else (
+        f"{args.workload}: {args.envs} envs/GPU x {R} rays x {args.n_moving}+{args.n_static} obstacles"
+        + (f" + {args.n_polygons} shared land polygons" if args.workload == "land" else ""))
+    return {"workload": name, "envs_per_gpu": args.envs, "rays": R, "obstacles": args.n_moving + args.n_static,
+            "paths": args.n_paths, "auto_reset": True,
+            "scenarios": "a fresh scenario of the MovingObstacles distribution for every episode" if args.workload == "moving"
+            else "fixed pool, replayed on reset",
+            "l2": "the per-step working set (state, records, observations, path tables) exceeds the 126 MB L2; no explicit flush"}
+
+
 def n_ranges(n, chunks):
     """env ranges auv_step_chunked cuts n envs into (range size = ceil(n/chunks) rounded up to 64)."""
     if chunks <= 1:
@@ -256,9 +270,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tmax / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{per_step_envs} envs per step on {cores} processes"},
+        "config": workload_config(args),
+        "sample": f"{per_step_envs} envs per step on {cores} processes (a bounded sample of the workload's scenario distribution)",
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{total} env-steps ({per_step_envs} envs x {args.steps} steps), "
+                         "sample": f"{total} env-steps ({per_step_envs} envs x {args.steps} steps on {cores} processes), "
                                    "oracle/sim.py FP64 restatement (Shapely/GEOS not installable)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -597,18 +612,13 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 ray casting on f64 state/culling", "data": "synthetic",
-        "config": {"workload": WORKLOAD if args.workload == "moving" and N == 65536 and R == 180 else
-                   f"{args.workload}: {N} envs/GPU x {R if cfg.vessel.use_lidar else 0} rays x {args.n_moving}+{args.n_static} obstacles"
-                   + (f" + {args.n_polygons} shared land polygons" if args.workload == "land" else ""),
-                   "envs_per_gpu": N, "rays": R, "obstacles": args.n_moving + args.n_static,
-                   "paths": args.n_paths, "l2": "per-step working set (state + records + observations ~%.0f MB, path bank ~%.0f MB) exceeds the 126 MB L2; no explicit flush"
-                   % (N * ALGO_BYTES_PER_ENV_STEP / 1e6, sum(v.numel() * v.element_size() for v in env._bank.values()) / 1e6),
-                   "phase": "steady state: %d steps after reset(), auto-reset running, timed through AUVVecEnv.step" % (step_no[0] - 3 * K),
-                   "auto_reset": True, "dones_per_step": dones_per_step, "records_per_env_step": steady_records,
-                   "mean_abs_cross_track_m": cross_track,
-                   "chunks": env.chunks, "chunk_streams": getattr(env, "chunk_streams", 1),
-                   "scenario_generation": scenario_gen, "setup_s": setup_s,
-                   "host_cores_bound": len(numa_cores)},
+        "config": workload_config(args, bool(cfg.vessel.use_lidar)),
+        "run": {"phase": "steady state: %d steps after reset(), auto-reset running, timed through AUVVecEnv.step" % (step_no[0] - 3 * K),
+                "dones_per_step": dones_per_step, "records_per_env_step": steady_records,
+                "mean_abs_cross_track_m": cross_track, "chunks": env.chunks, "chunk_streams": getattr(env, "chunk_streams", 1),
+                "scenario_generation": scenario_gen, "setup_s": setup_s, "host_cores_bound": len(numa_cores),
+                "working_set_mb": {"per_step_state_and_outputs": N * ALGO_BYTES_PER_ENV_STEP / 1e6,
+                                   "path_bank": sum(v.numel() * v.element_size() for v in env._bank.values()) / 1e6}},
         "clocks": clocks,
         "after_reset": {"value": world * N / (after_reset_ms * 1e-3), "ms_per_step": after_reset_ms,
                         "note": "side note: the same K steps right after reset() (vessels at their path starts, nearby "

@@ -519,3 +519,108 @@ def test_realworld_scenario_matches_the_reference_episode_on_gpu():
         assert int(env._scratch["rec_cnt"][0]) == int(GOLD["n_nearby"][t])
         assert torch.equal(obs[0], obs[39])  # every env of the batch runs the same world
     env.check_status()
+
+
+def test_c_abi_alone_builds_and_steps_a_batch():
+    """a host that only has the C ABI (here: ctypes + raw device allocations, no
+    AUVVecEnv / PathBank / ScenarioSet) builds the path bank from waypoints, samples the scenario pool,
+    fills the reset cache, steps with auto-reset and refreshes finished scenarios -- and gets what
+    AUVVecEnv gets for the same pool."""
+    import ctypes as C
+
+    from gym_auv_b200 import _lib
+    from gym_auv_b200.vec_env import AUVVecEnv, make_auv_config, ray_table
+
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+    P_ = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    N, M, P, Km, Ks, R, V = 96, 192, 6, 5, 4, 180, 16384
+    conf = lidar_config()
+    conf.episode.max_timesteps = 11
+    cfg = make_auv_config(conf, "colav", False, True, "reference")
+    od = lib.auv_obs_dim(C.byref(cfg))
+    # ---- 1. paths
+    wp, nwp, status = z((P, 2, 8), torch.float64), z(P, torch.int32), z(1, torch.int32)
+    _lib.check(lib.auv_random_curve_waypoints(7, 1, 800.0, None, P, P_(wp), P_(nwp), st), "waypoints")
+    pa = dict(hdr=z(P * 64, torch.uint8), poly_xy=z((P * V, 2), torch.float64), poly_cum=z(P * V, torch.float64),
+              poly_f32=z((P * V, 2), torch.float32), blk_chord=z((P * V // 32, 4), torch.float32), blk_dev=z((P * V // 32, 2), torch.float32),
+              sb_chord=z((P * V // 512, 4), torch.float32), sb_dev=z((P * V // 512, 2), torch.float32), pp=z((P, 999, 12), torch.float64))
+    order = ("hdr", "poly_xy", "poly_cum", "poly_f32", "blk_chord", "blk_dev", "sb_chord", "sb_dev", "pp")
+    pb = _lib.AuvPathBuild(*[pa[k].data_ptr() for k in order], 1000, V)
+    _lib.check(lib.auv_pathbank_build(P_(wp), P_(nwp), None, P, C.byref(pb), P_(status), st), "auv_pathbank_build")
+    paths = _lib.AuvPathBank(P, 1000, *[pa[k].data_ptr() for k in order])
+    # ---- 2. scenario pool, sampled on the GPU
+    mw = 1
+    pl = dict(path_id=z(M, torch.int32), vessel_init=z((M, 3), torch.float64), mov_start=z((M, Km, 2), torch.float64),
+              mov_width=z((M, Km), torch.float64), mov_track=z((M, Km, 4), torch.int32), mov_pos0=z((M, Km, 2), torch.float64),
+              mov_disp0=z((M, Km, 2), torch.float64), mov_counter0=z((M, Km), torch.float64), vel_table=z((M * Km, 2), torch.float64),
+              st_pos=z((M, Ks, 2), torch.float64), st_radius=z((M, Ks), torch.float64), st_rec=z((M, Ks, 4), torch.float64),
+              mov_lin=z((M, Km, 8), torch.float64), reset_obs=z((M, od), torch.float32), reset_max_progress=z(M, torch.float64),
+              reset_mask=z((M, mw), torch.int32))
+    first, period = C.c_int32(0), C.c_int32(0)
+    _lib.check(lib.auv_linear_wrap(1.0, 1.1, 9999, C.byref(first), C.byref(period)), "auv_linear_wrap")
+    pool = _lib.AuvScenarioPool(
+        M, Km, Ks, 0, *[pl[k].data_ptr() for k in ("path_id", "vessel_init", "mov_start", "mov_width", "mov_track", "mov_pos0",
+                                                   "mov_disp0", "mov_counter0", "vel_table", "st_pos", "st_radius", "st_rec", "mov_lin")],
+        1, first.value, period.value, 0, None, None, None, None, None, 0.0, 0.0, 0.0, 0, 0,
+        pl["reset_obs"].data_ptr(), pl["reset_max_progress"].data_ptr(), pl["reset_mask"].data_ptr())
+    gp = _lib.AuvGenParams(seed=3, epoch=1, post_generate_update=1, t_step_size=1.0, vessel_width=1.255, init_pos_jitter=50.0,
+                           mov_disp_std=500.0, mov_width_mean=10.0, mov_speed_lo=1.0, mov_speed_hi=3.0, st_disp_std=250.0,
+                           st_radius_mean=30.0, path_group=N // P, path_period=N)
+    _lib.check(lib.auv_generate_moving_obstacles(C.byref(gp), C.byref(paths), C.byref(pool), None, M, P_(status), st), "generate")
+    # ---- ray table (host constants) and batches
+    _, cos_sin, weight, wsum, sector = ray_table(R, 9)
+    k64 = np.arange(64) * (2 * np.pi / 64)
+    rt = dict(cos_sin=torch.as_tensor(cos_sin).to(dev), weight=torch.as_tensor(weight).to(dev), sector=torch.as_tensor(sector).to(dev),
+              unit64=torch.as_tensor(np.stack([np.cos(k64), np.sin(k64)], 1)).to(dev))
+    rays = _lib.AuvRayTable(rt["cos_sin"].data_ptr(), rt["weight"].data_ptr(), rt["sector"].data_ptr(), rt["unit64"].data_ptr(), wsum)
+
+    def make_batch(n):
+        b = dict(scn_id=torch.arange(n, device=dev, dtype=torch.int32), episode=z(n, torch.int32), state=z((6, n), torch.float64),
+                 step_counter=z(n, torch.int32), t_step=z(n, torch.int32), cum_reward=z(n, torch.float64),
+                 max_progress=z(n, torch.float64), cte_sum=z(n, torch.float64), nearby_mask=z((n, mw), torch.int32),
+                 nav=z((n, 24), torch.float64), rec=z((n, Km + Ks, 80), torch.uint8), rec_cnt=z(n, torch.int32),
+                 obst_steps=z(n, torch.int32), prev_seg=torch.full((n,), -1, dtype=torch.int32, device=dev), env_pid=z(n, torch.int32))
+        o = dict(obs=z((n, od), torch.float32), reward=z(n, torch.float32), done=z(n, torch.uint8), stats=z(16, torch.float64))
+        batch = _lib.AuvBatch(n, mw, 0, 0, b["scn_id"].data_ptr(), b["episode"].data_ptr(), b["state"].data_ptr(),
+                              b["step_counter"].data_ptr(), b["t_step"].data_ptr(), b["cum_reward"].data_ptr(),
+                              b["max_progress"].data_ptr(), b["cte_sum"].data_ptr(), b["nearby_mask"].data_ptr(), None, None, None,
+                              b["nav"].data_ptr(), b["rec"].data_ptr(), b["rec_cnt"].data_ptr(), status.data_ptr(), Km + Ks, 0,
+                              b["obst_steps"].data_ptr(), b["prev_seg"].data_ptr(), b["env_pid"].data_ptr())
+        out = _lib.AuvStepOut(o["obs"].data_ptr(), o["reward"].data_ptr(), o["done"].data_ptr(), None, None, None, None, None, None,
+                              None, None, None, o["stats"].data_ptr(), None, None)
+        return b, o, batch, out
+
+    wb, wo, worker, worker_out = make_batch(64)
+    # ---- 3. reset cache, 64 scenarios per call
+    for f0 in range(0, M, 64):
+        _lib.check(lib.auv_reset_cache_fill(C.byref(cfg), C.byref(rays), C.byref(paths), C.byref(pool), C.byref(worker),
+                                            C.byref(worker_out), None, f0, min(64, M - f0), st), "auv_reset_cache_fill")
+    # ---- 4. run
+    b, o, batch, out = make_batch(N)
+    _lib.check(lib.auv_reset(C.byref(cfg), C.byref(pool), C.byref(batch), None, st), "auv_reset")
+    _lib.check(lib.auv_observe(C.byref(cfg), C.byref(rays), C.byref(paths), C.byref(pool), C.byref(batch), C.byref(out), 1, st), "observe")
+    torch.cuda.synchronize()
+    assert torch.equal(o["obs"], pl["reset_obs"][:N])  # the cached first observations are what reset() returns
+    rs = _lib.AuvRefreshScratch(z(N, torch.int32).data_ptr(), z(64, torch.int32).data_ptr(), z(1, torch.int32).data_ptr(), 64, 0)
+    keep = []  # (the scratch tensors above must outlive the calls)
+    seen, ids, cnt = z(N, torch.int32), z(64, torch.int32), z(1, torch.int32)
+    rs = _lib.AuvRefreshScratch(seen.data_ptr(), ids.data_ptr(), cnt.data_ptr(), 64, 0)
+    acts = torch.as_tensor(random_actions(30, N, 1), dtype=torch.float32, device=dev)
+    before = pl["st_pos"].clone()
+    n_done = 0
+    for t in range(30):
+        _lib.check(lib.auv_step(C.byref(cfg), C.byref(rays), C.byref(paths), C.byref(pool), C.byref(batch), P_(acts[t]),
+                                C.byref(out), st), "auv_step")
+        n_done += int(o["done"].sum())
+        assert torch.isfinite(o["obs"]).all() and o["obs"].abs().max() <= 1 and torch.isfinite(o["reward"]).all()
+        if t % 4 == 3:
+            gp.epoch += 1
+            _lib.check(lib.auv_refresh_finished(C.byref(cfg), C.byref(rays), C.byref(paths), C.byref(pool), C.byref(batch),
+                                                C.byref(worker), C.byref(worker_out), C.byref(rs), C.byref(gp), st), "refresh")
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0 and n_done >= 2 * N and float(o["stats"][0]) == n_done
+    assert (pl["st_pos"] != before).any(), "vacated slots were regenerated"
+    assert (b["scn_id"] >= 0).all() and (b["scn_id"] < M).all()

@@ -228,3 +228,36 @@ def test_vec_env_refuses_to_run_without_cuda():
 
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         AUVVecEnv(S.empty_scenario(), 1, Config(), device="cuda:0")
+
+
+def test_parity_harness_counts_steps_inside_the_collision_band():
+    """tests/_parity.compare skips the bit-exact collision / done comparison where the oracle's minimum
+    range is within COLLISION_BAND of the vessel width (FP32 casting may legitimately decide the other
+    way) -- and COUNTS those steps.  Forced case: one step inside the band with flipped flags is
+    skipped and counted, the same flip outside the band fails."""
+    import pytest
+
+    from gym_auv_b200 import lidar_config
+    from tests._parity import COLLISION_BAND, compare
+
+    cfg = lidar_config()
+    w = cfg.vessel.vessel_width
+    T, M, R = 2, 1, cfg.vessel.n_sensors
+
+    def case(min_dist):
+        dists = np.full((T, M, R), 150.0)
+        dists[1, 0, 7] = min_dist
+        ref = dict(alive=np.ones((T, M), bool), state=np.zeros((T, M, 6)), s=np.zeros((T, M)), dists=dists,
+                   min_dist=dists.min(axis=2), collision=np.zeros((T, M), bool), reached=np.zeros((T, M), bool),
+                   done=np.zeros((T, M), bool), reward=np.zeros((T, M)), obs=np.zeros((T, M, 6 + R)), windows=[[{}] * M] * T)
+        gpu = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in ref.items()}
+        gpu["collision"][1, 0] = gpu["done"][1, 0] = True  # the FP32 side saw 1.2549 < width
+        gpu["windows"] = np.zeros((T, M, 1, 2), int)
+        return ref, gpu
+
+    ref, gpu = case(w + 0.5 * COLLISION_BAND)
+    rep = compare(ref, gpu, cfg, "inside the band")
+    assert rep["collision_skipped_in_band"] == 1 and rep["collision_decisive"] == T * M - 1
+    ref, gpu = case(w + 3 * COLLISION_BAND)
+    with pytest.raises(AssertionError):
+        compare(ref, gpu, cfg, "outside the band")
