@@ -89,6 +89,10 @@ def parse():
     ap.add_argument("--chunks", type=int, default=2,
                     help="env ranges per step on the pipeline's own streams (auv_step_chunked); 1 = single stream")
     ap.add_argument("--chunk-streams", type=int, default=None)
+    ap.add_argument("--host-transfer", default="auto", choices=["auto", "delta", "compact", "dense"],
+                    help="how the e2e leg delivers observations to host memory (auto: measures delta and compact, "
+                         "the faster one is e2e.value, the other is listed under e2e.other)")
+    ap.add_argument("--delta-gran", type=int, default=16, help="floats per chunk of the delta transfer (8, 16, 32)")
     ap.add_argument("--host-threads", type=int, default=None, help="host threads of auv_compact_expand (default: min(16, cores))")
     ap.add_argument("--host-chunks", type=int, default=4,
                     help="env ranges of the host-buffer step (auv_step_host_chunked): D2H of a range overlaps the next")
@@ -317,7 +321,8 @@ def run_ours(args):
     host_threads = args.host_threads or max(1, min(16, cores_here // max(local_world, 1)))
     env = AUVVecEnv(scn, N, cfg, device=device, test_mode=False, auto_reset=True, env_offset=0,
                     chunks=args.chunks, chunk_streams=args.chunk_streams, host_chunks=args.host_chunks,
-                    host_threads=host_threads)
+                    host_threads=host_threads, delta_gran=args.delta_gran,
+                    host_transfer=None if args.host_transfer == "auto" else args.host_transfer)
     seed = args.seed + 1000 * rank
     scenario_gen = {"where": "host", "scenarios": scn.n_scenarios}
     if fresh:
@@ -476,7 +481,7 @@ def run_ours(args):
         e2e = {"value": world * N * ke / float(t_e.item()), "unit": UNIT,
                "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
                "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": ke, "ms_per_step": e2e_ms,
-               "host_chunks": env.host_chunks, "compact_transfer": env.compact_host, "host_threads": env.host_threads,
+               "host_chunks": env.host_chunks, "host_transfer": env.host_transfer, "host_threads": env.host_threads,
                "dense_d2h_bytes_per_step": dense_bytes * world,
                "pcie": {"dense_d2h_only_ms_per_step": d2h_ms, "d2h_gbs": dense_bytes / (d2h_ms * 1e-3) / 1e9,
                         "note": "rank-0 link: time of a plain D2H copy of the dense [N, obs_dim] rows alone (what bounded "
@@ -486,9 +491,9 @@ def run_ours(args):
     #      step_async / step_wait (stable-baselines' VecEnv interface) so that one group's
     #      observations travel while the other group is computed.  Same env count, same host
     #      buffers, every step's actions come from host memory and every observation lands there.
-    if e2e is not None and N >= 128:
+    def async_e2e(mode):
         half = N // 2
-        groups = env.groups(2)  # two envs of N/2 sharing this env's device tables
+        groups = env.groups(2, host_transfer=mode, delta_gran=args.delta_gran)  # two envs of N/2 sharing this env's device tables
         for g in groups:
             g.reset()
         ah = [[a[:half].copy() for a in acts_np], [a[half:2 * half].copy() for a in acts_np]]
@@ -508,6 +513,8 @@ def run_ours(args):
         for g in groups:
             g.step_wait()
         refresh_groups(args.refresh_every - 1)  # warm-up of the refresh path (creates its worker batch)
+        for g in groups:
+            g.d2h_bytes_per_step  # (delta transfer: start the byte count at the timed region)
         barrier()
         t0 = time.perf_counter()
         for g, a in zip(groups, ah):
@@ -525,18 +532,29 @@ def run_ours(args):
             dist.all_reduce(t_a, op=dist.ReduceOp.MAX)
         a_ms = 1e3 * float(t_a.item()) / (ke + 1)
         expand_ms = 1e3 * sum(g.expand_seconds for g in groups) / (ke + 4 + 1)  # per step of N envs (both groups), incl. warm-up steps
-        sync_part = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "host_chunks": e2e["host_chunks"],
-                     "call": "AUVVecEnv.step_host (one synchronous call per step)"}
-        e2e.update({"value": world * 2 * half * (ke + 1) / float(t_a.item()), "ms_per_step": a_ms, "steps": ke + 1,
-                    "mode": "AUVVecEnv.step_async / step_wait, two groups of N/2 envs stepped alternately"
-                            + (", fresh scenario per episode" if fresh else ""),
-                    "d2h_bytes_per_step": sum(g.d2h_bytes_per_step for g in groups) * world,
-                    "host_expand_ms_per_step": expand_ms, "host_threads": groups[0].host_threads,
-                    "host_chunks": groups[0].host_chunks, "sync": sync_part})
+        res = {"value": world * 2 * half * (ke + 1) / float(t_a.item()), "ms_per_step": a_ms, "steps": ke + 1,
+               "host_transfer": mode + (f"/{args.delta_gran * 4}B" if mode == "delta" else ""),
+               "d2h_bytes_per_step": sum(g.d2h_bytes_per_step for g in groups) * world,
+               "host_expand_ms_per_step": expand_ms, "host_threads": groups[0].host_threads if mode == "compact" else 0,
+               "host_chunks": groups[0].host_chunks}
         torch.cuda.synchronize()
         for g in groups:
             g.close()
         del groups
+        return res
+
+    if e2e is not None and N >= 128:
+        modes = ["delta", "compact"] if args.host_transfer == "auto" else [args.host_transfer]
+        if not env.compact_host and "compact" in modes and args.host_transfer == "auto":
+            modes.remove("compact")
+        runs = [async_e2e(m) for m in modes]
+        runs.sort(key=lambda r: -r["value"])
+        sync_part = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "host_chunks": e2e["host_chunks"],
+                     "host_transfer": env.host_transfer, "call": "AUVVecEnv.step_host (one synchronous call per step)"}
+        e2e.update(runs[0])
+        e2e.update({"mode": "AUVVecEnv.step_async / step_wait, two groups of N/2 envs stepped alternately"
+                            + (", fresh scenario per episode" if fresh else ""),
+                    "sync": sync_part, "other": runs[1:]})
 
     if rank != 0:
         if world > 1:

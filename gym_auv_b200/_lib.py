@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUV_B200_LIB", os.path.join(_HERE, "libauv_b200.so"))  # override: tuning builds only
-ABI_VERSION = 18
+ABI_VERSION = 19
 REC_BYTES = 80
 MAX_POLY_VERTS = 192
 STATUS_REC_OVERFLOW = 1
@@ -225,6 +225,10 @@ class AuvCompact(C.Structure):
     _fields_ = [("head", _vp), ("mask", _vp), ("vals", _vp), ("counter", _vp), ("words", C.c_int32), ("capacity", C.c_int32)]
 
 
+class AuvDelta(C.Structure):
+    _fields_ = [("obs_host", _vp), ("shadow", _vp), ("shipped", _vp), ("gran", C.c_int32), ("reserved0", C.c_int32)]
+
+
 EXPORTS = [
     "auv_abi_version",
     "auv_sizeof",
@@ -255,6 +259,7 @@ EXPORTS = [
     "auv_reset_cache_fill",
     "auv_refresh_finished",
     "auv_step_host_compact_submit",
+    "auv_step_host_delta_submit",
     "auv_compact_expand",
     "auv_pathbank_build",
     "auv_random_curve_waypoints",
@@ -325,6 +330,10 @@ def load():
         P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, _vp, P(AuvStepOut),
         P(AuvCompact), _vp, _vp, _vp, _vp, C.c_int,
     ]
+    lib.auv_step_host_delta_submit.argtypes = [
+        P(AuvConfig), P(AuvRayTable), P(AuvPathBank), P(AuvScenarioPool), P(AuvBatch), _vp, _vp, P(AuvStepOut),
+        P(AuvDelta), _vp, _vp, _vp, _vp, C.c_int,
+    ]
     lib.auv_compact_expand.argtypes = [P(AuvConfig), C.c_int, P(AuvCompact), _vp, _vp, C.c_int]
     lib.auv_pathbank_build.argtypes = [_vp, _vp, _vp, C.c_int, P(AuvPathBuild), _vp, _vp]
     lib.auv_random_curve_waypoints.argtypes = [C.c_uint64, C.c_uint32, C.c_double, _vp, C.c_int, _vp, _vp, _vp]
@@ -343,7 +352,7 @@ def load():
         raise AuvLibraryError(f"ABI mismatch: library {ver}, binding {ABI_VERSION}; rebuild")
     lib.auv_sizeof.argtypes = [C.c_int]
     for i, st in enumerate([AuvConfig, AuvRayTable, AuvPathBank, AuvScenarioPool, AuvBatch, AuvStepOut, AuvGenParams,
-                            AuvPathHdr, AuvRefreshScratch, AuvCompact, AuvPathBuild]):
+                            AuvPathHdr, AuvRefreshScratch, AuvCompact, AuvPathBuild, AuvDelta]):
         if lib.auv_sizeof(i) != C.sizeof(st):
             raise AuvLibraryError(f"struct layout mismatch for {st.__name__}: C {lib.auv_sizeof(i)} vs ctypes {C.sizeof(st)}")
     _lib = lib

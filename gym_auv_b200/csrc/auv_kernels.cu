@@ -569,6 +569,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // the ~50 capsule tests per env then read shared memory instead of four dependent rounds of
 // global loads.  CTAs with mixed paths (or a path with more than AUV_PATH_STAGE_BLOCKS blocks)
 // search the global tables; the arithmetic is the same.
+#ifndef AUV_LIDAR_GROUPSKIP
+#define AUV_LIDAR_GROUPSKIP 1  // the observation pass computes only the 64-ray groups some record shortened a ray of
+#endif
 #ifndef AUV_NAV_G
 #define AUV_NAV_G 4
 #endif
@@ -776,10 +779,11 @@ struct LidarSmem {
   float* pen;       // [E]       sum of w_i (penalty_i - clear penalty) over hit rays
   int* flag;        // [E]       bit 0 collision, bit 1 auto-reset pending
   int* next;        // [E]       scenario the env resets onto
+  unsigned* grp;    // [E]       bit g: some ray of the 64-ray group g was shortened by an obstacle
 };
 __host__ __device__ constexpr size_t lidar_smem_bytes_for(int E, int rpad, int vmax, int vel) {
   return (size_t)E * 16 * 8 + (size_t)E * rpad * (vel ? 8 : 4) + AUV_LIDAR_RCAP * sizeof(ObstRec) + AUV_LIDAR_RCAP * 4 +
-         (size_t)(AUV_LIDAR_THREADS / 32) * vmax * 8 + 64 * 8 + 48 * 4 + 32 * 4 + 32 * 4 + 32 * 4;
+         (size_t)(AUV_LIDAR_THREADS / 32) * vmax * 8 + 64 * 8 + 48 * 4 + 32 * 4 + 32 * 4 + 32 * 4 + 32 * 4;
 }
 __device__ __forceinline__ LidarSmem lidar_carve(unsigned char* p, int E, int rpad, int vmax, int vel) {
   LidarSmem s;
@@ -802,6 +806,8 @@ __device__ __forceinline__ LidarSmem lidar_carve(unsigned char* p, int E, int rp
   s.flag = reinterpret_cast<int*>(p);
   p += 32 * 4;
   s.next = reinterpret_cast<int*>(p);
+  p += 32 * 4;
+  s.grp = reinterpret_cast<unsigned*>(p);
   return s;
 }
 
@@ -912,6 +918,7 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
   // ---- phase 1: hand-over lines, unit table, range rows
   for (int k = tid; k < ne * 16; k += AUV_LIDAR_THREADS)
     sm.hand[k] = batch.nav[(long long)(env0 + (k >> 4)) * AUV_NAV_W + NAV_HAND + (k & 15)];
+  if (tid < AUV_LIDAR_MAX_ENVS) sm.grp[tid] = 0u;
   if (cfg.use_lidar) {
     if (tid < 64) {
       const double2 un = reinterpret_cast<const double2*>(A.rays.unit64)[tid];
@@ -989,8 +996,15 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
         if (tot == 0) continue;
         void* row = VEL ? (void*)(reinterpret_cast<unsigned long long*>(sm.sdist) + (size_t)el * rpad)
                         : (void*)(reinterpret_cast<float*>(sm.sdist) + (size_t)el * rpad);
+        unsigned gbits = 0u;  // 64-ray groups this lane shortened a ray of
         if (fl & OFLAG_INSIDE) {  // own-ship inside a filled boundary: every candidate ray reads 0
-          for (int u = lane; u < tot; u += 32) range_min<VEL>(row, u < n1 ? lo1 + u : lo2 + (u - n1), 0.f, slot);
+          for (int u = lane; u < tot; u += 32) {
+            const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
+            range_min<VEL>(row, i, 0.f, slot);
+            gbits |= 1u << (i >> 6);
+          }
+          gbits = __reduce_or_sync(AUV_FULL, gbits);
+          if (lane == 0 && gbits) atomicOr(&sm.grp[el], gbits);
           continue;
         }
         const bool ngon = !(fl & (OFLAG_PENTAGON | OFLAG_WORLD)) && nq > 16;
@@ -1053,9 +1067,14 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
             } else {
               got = cast_chain(wverts, nqc, c, sn, cur, rangef);
             }
-            if (got < cur) range_min<VEL>(row, i, got, slot);
+            if (got < cur) {
+              range_min<VEL>(row, i, got, slot);
+              gbits |= 1u << (i >> 6);
+            }
           }
         }
+        gbits = __reduce_or_sync(AUV_FULL, gbits);
+        if (lane == 0 && gbits) atomicOr(&sm.grp[el], gbits);
       }
       __syncthreads();
     }
@@ -1081,10 +1100,26 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
                             : (const void*)(reinterpret_cast<const float*>(sm.sdist) + (size_t)el * rpad);
       float extra = 0.f;
       bool collision = false;
-      if (cnt > 0) {
+      const unsigned gb = sm.grp[el];  // groups of 64 rays (= 32 float2 pairs = one iteration below) with a hit
+      if (cnt > 0 && (gb != 0u || !AUV_LIDAR_GROUPSKIP)) {
         const double cpsi = HAND(el, NAV_COSPSI), spsi = HAND(el, NAV_SINPSI);
         const ObstRec* grec = reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
         for (int k = lane; k < (R + 1) / 2; k += 32) {
+          if (AUV_LIDAR_GROUPSKIP && !((gb >> (k >> 5)) & 1u)) {  // warp-uniform: no ray of this group was shortened -- zeros, nothing to compute
+            if (vec2) {
+              if (2 * k + 1 < R)
+                reinterpret_cast<float2*>(obs + 6)[k] = make_float2(0.f, 0.f);
+              else
+                obs[6 + 2 * k] = 0.f;
+            } else {
+              obs[6 + 2 * k] = 0.f;
+              if (2 * k + 1 < R) obs[6 + 2 * k + 1] = 0.f;
+            }
+            if (vel_obs)
+              for (int h = 0; h < 2; ++h)
+                if (2 * k + h < R) obs[6 + R + 2 * k + h] = obs[6 + 2 * R + 2 * k + h] = 0.f;
+            continue;
+          }
           float cl2[2] = {0.f, 0.f};
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -1401,6 +1436,63 @@ __global__ void __launch_bounds__(AUV_SHIP_THREADS) k_obs_ship(const float* __re
 }
 
 // ------------------------------------------------------------------------------------
+// Delta transfer (auv_step_host_delta_submit): the dense observation array of the caller lives
+// in pinned host memory and keeps its content between steps; `shadow` is the device's copy of
+// what it holds.  A thread owns one 16 B quad of the flat [N * obs_dim] array, a chunk is `g4`
+// consecutive quads (2 / 4 / 8: 32 / 64 / 128 B) of one warp; a chunk is stored -- to the host
+// array and to the shadow -- iff any of its words differs bitwise.  The stores of a chunk are one
+// contiguous, aligned run, so the link sees whole 32 / 64 / 128 B writes.
+// ------------------------------------------------------------------------------------
+#define AUV_DELTA_THREADS 256
+__global__ void __launch_bounds__(AUV_DELTA_THREADS) k_obs_delta(const float* __restrict__ obs, float* __restrict__ shadow,
+                                                                float* __restrict__ obs_h, long long f0, long long f1, int g4,
+                                                                const float* __restrict__ reward,
+                                                                const uint8_t* __restrict__ done, float* __restrict__ reward_h,
+                                                                uint8_t* __restrict__ done_h, int e0, int e1,
+                                                                unsigned long long* __restrict__ shipped) {
+  __shared__ int s_count;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  const long long q = (f0 >> 2) + (long long)blockIdx.x * AUV_DELTA_THREADS + tid;  // f0 is a multiple of 4
+  const long long base = q << 2;
+  const bool full = base + 4 <= f1, part = !full && base < f1;
+  bool changed = false;
+  uint4 cur = make_uint4(0u, 0u, 0u, 0u);
+  if (full) {
+    cur = __ldcs(reinterpret_cast<const uint4*>(obs) + q);
+    const uint4 old = __ldcs(reinterpret_cast<const uint4*>(shadow) + q);
+    changed = (cur.x != old.x) | (cur.y != old.y) | (cur.z != old.z) | (cur.w != old.w);
+  } else if (part) {
+    for (long long i = base; i < f1; ++i) changed |= __float_as_uint(obs[i]) != __float_as_uint(shadow[i]);
+  }
+  const unsigned any = __ballot_sync(AUV_FULL, changed);
+  const unsigned cm = (g4 >= 32 ? 0xffffffffu : ((1u << g4) - 1u)) << (lane & ~(g4 - 1));
+  const bool ship = (any & cm) != 0u;
+  if (ship) {
+    if (full) {
+      reinterpret_cast<uint4*>(obs_h)[q] = cur;
+      reinterpret_cast<uint4*>(shadow)[q] = cur;
+    } else if (part) {
+      for (long long i = base; i < f1; ++i) obs_h[i] = shadow[i] = obs[i];
+    }
+  }
+  if (shipped != nullptr) {
+    const unsigned lead = __ballot_sync(AUV_FULL, ship && (lane & (g4 - 1)) == 0);
+    if (lane == 0 && lead) atomicAdd(&s_count, __popc(lead));
+  }
+  const int e = e0 + blockIdx.x * AUV_DELTA_THREADS + tid;
+  if (e < e1) {
+    reward_h[e] = reward[e];
+    done_h[e] = done[e];
+  }
+  if (shipped != nullptr) {
+    __syncthreads();
+    if (tid == 0 && s_count) atomicAdd(shipped, (unsigned long long)s_count);
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // FP32 FMA peak probe: 8 independent FMA chains per thread
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fma_probe(float* sink, int iters) {
@@ -1461,6 +1553,7 @@ int auv_sizeof(int which) {
     case 8: return (int)sizeof(AuvRefreshScratch);
     case 9: return (int)sizeof(AuvCompact);
     case 10: return (int)sizeof(AuvPathBuild);
+    case 11: return (int)sizeof(AuvDelta);
     default: return AUV_EINVAL;
   }
 }
@@ -1835,11 +1928,23 @@ static int launch_obs_ship(const AuvConfig* cfg, const AuvStepOut* out, const Au
   return cuda_check(cudaGetLastError(), "k_obs_ship");
 }
 
+static int launch_obs_delta(const AuvConfig* cfg, const AuvStepOut* out, const AuvDelta* d, float* reward_host,
+                            uint8_t* done_host, int e0, int cnt, cudaStream_t s) {
+  const long long od = auv_obs_dim(cfg);
+  const long long f0 = od * e0, f1 = od * (e0 + cnt);  // e0 is a multiple of 256 envs: f0 is 1 KB aligned
+  const long long quads = (f1 - f0 + 3) / 4;
+  const long long work = quads > cnt ? quads : cnt;
+  const int blocks = (int)((work + AUV_DELTA_THREADS - 1) / AUV_DELTA_THREADS);
+  auv::k_obs_delta<<<blocks, AUV_DELTA_THREADS, 0, s>>>(out->obs, d->shadow, d->obs_host, f0, f1, d->gran / 4, out->reward,
+                                                       out->done, reward_host, done_host, e0, e0 + cnt, d->shipped);
+  return cuda_check(cudaGetLastError(), "k_obs_delta");
+}
+
 static int enqueue_host_step(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                              const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
                              float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
                              uint8_t* done_host, cudaStream_t s, cudaStream_t ds, AuvPipeline* p, int n_chunks,
-                             const AuvCompact* cb = nullptr) {
+                             const AuvCompact* cb = nullptr, const AuvDelta* dl = nullptr) {
   const int n = batch->n_envs;
   const int cs = chunk_size(n, n_chunks);
   const size_t od = (size_t)auv_obs_dim(cfg);
@@ -1856,13 +1961,15 @@ static int enqueue_host_step(const AuvConfig* cfg, const AuvRayTable* rays, cons
       if (int rc = cuda_check(cudaEventRecord(p->chunk[c], s), "range done")) return rc;
       if (int rc = cuda_check(cudaStreamWaitEvent(ds, p->chunk[c], 0), "copy stream wait")) return rc;
     }
-    if (cb != nullptr) {  // compact transfer: the kernel's own stores into pinned host memory
+    if (dl != nullptr) {  // delta transfer: changed chunks of the dense rows, stored by the kernel
+      if (int rc = launch_obs_delta(cfg, out, dl, reward_host, done_host, e0, cnt, ds)) return rc;
+    } else if (cb != nullptr) {  // compact transfer: the kernel's own stores into pinned host memory
       if (int rc = launch_obs_ship(cfg, out, cb, reward_host, done_host, e0, cnt, ds)) return rc;
     } else if (int rc = cuda_check(cudaMemcpyAsync(obs_host + od * e0, out->obs + od * e0, (size_t)cnt * od * sizeof(float),
                                                    cudaMemcpyDeviceToHost, ds), "D2H obs"))
       return rc;
   }
-  if (cb == nullptr) {
+  if (cb == nullptr && dl == nullptr) {
     if (int rc = cuda_check(cudaMemcpyAsync(reward_host, out->reward, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ds),
                             "D2H reward"))
       return rc;
@@ -1886,7 +1993,7 @@ static int step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, cons
                              const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
                              float* actions_dev, AuvStepOut* out, float* obs_host, float* reward_host,
                              uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks,
-                             const AuvCompact* cb = nullptr) {
+                             const AuvCompact* cb = nullptr, const AuvDelta* dl = nullptr) {
   if (!p) return set_err(AUV_EINVAL, "pipeline is NULL");
   if (n_chunks <= 0 || n_chunks > AUV_PIPE_MAX_CHUNKS) return set_err(AUV_EINVAL, "n_chunks out of range");
   if (int rc = check_observe_args(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP)) return rc;
@@ -1902,6 +2009,7 @@ static int step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, cons
     const void* ptrs[6] = {actions_host, actions_dev, obs_host, reward_host, done_host, (const void*)(size_t)n_chunks};
     key = fnv1a(key, ptrs, sizeof(ptrs));
     if (cb) key = fnv1a(key, cb, sizeof(*cb));
+    if (dl) key = fnv1a(key, dl, sizeof(*dl));
     if (p->graph_state == 0 || key != p->gkey) {
       if (p->gexec) {
         cudaGraphExecDestroy(p->gexec);
@@ -1916,7 +2024,7 @@ static int step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, cons
       int rc = 0;
       if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
         rc = enqueue_host_step(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, obs_host, reward_host,
-                               done_host, cs, ds, p, n_chunks, cb);
+                               done_host, cs, ds, p, n_chunks, cb, dl);
         const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
         if (rc == 0 && ce == cudaSuccess && graph != nullptr &&
             cudaGraphInstantiate(&p->gexec, graph, 0) == cudaSuccess) {
@@ -1934,7 +2042,7 @@ static int step_host_chunked(const AuvConfig* cfg, const AuvRayTable* rays, cons
     if (p->graph_state == 1) return cuda_check(cudaGraphLaunch(p->gexec, s), "cudaGraphLaunch");
   }
   return enqueue_host_step(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, obs_host, reward_host, done_host,
-                           s, ds, p, n_chunks, cb);
+                           s, ds, p, n_chunks, cb, dl);
 }
 
 int auv_step_chunked(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
@@ -1968,6 +2076,20 @@ int auv_step_host_compact_submit(const AuvConfig* cfg, const AuvRayTable* rays, 
     return set_err(AUV_EINVAL, "compact.capacity must be >= n_envs * words * 32");
   return step_host_chunked(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, nullptr, reward_host, done_host,
                            stream, p, n_chunks, cb);
+}
+
+int auv_step_host_delta_submit(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                               const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
+                               float* actions_dev, AuvStepOut* out, const AuvDelta* d, float* reward_host,
+                               uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks) {
+  if (!cfg || !batch || !out || !actions_host || !actions_dev || !d || !reward_host || !done_host)
+    return set_err(AUV_EINVAL, "NULL argument");
+  if (!d->obs_host || !d->shadow) return set_err(AUV_EINVAL, "delta buffers are NULL");
+  if (d->gran != 8 && d->gran != 16 && d->gran != 32) return set_err(AUV_EINVAL, "delta.gran must be 8, 16 or 32");
+  if (((size_t)d->obs_host | (size_t)d->shadow | (size_t)out->obs) & 15u)
+    return set_err(AUV_EINVAL, "delta: obs_host, shadow and out->obs must be 16 B aligned");
+  return step_host_chunked(cfg, rays, paths, pool, batch, actions_host, actions_dev, out, nullptr, reward_host, done_host,
+                           stream, p, n_chunks, nullptr, d);
 }
 
 int auv_compact_expand(const AuvConfig* cfg, int n_envs, const AuvCompact* cb, uint32_t* prev_mask, float* obs_host,

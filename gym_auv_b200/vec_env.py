@@ -113,6 +113,12 @@ class AUVVecEnv:
                 form (head + hit mask + non-zero closeness values, auv_step_host_compact_submit) and expand
                 them into the dense [N, obs_dim] array with ``host_threads`` host threads; results are
                 bit-identical to the dense copy.  Falls back to dense rows with velocity observations.
+    host_transfer : how step_host / step_async deliver the observations: "delta" = the dense [N, obs_dim] array
+                lives in pinned host memory, the device stores only the 64 B chunks of it that changed since the
+                previous step (auv_step_host_delta_submit; no host-side work, every observation layout);
+                "compact" = compact_host; "dense" = plain D2H copy of all rows.  Default: "compact" when
+                compact_host applies, else "dense".  All three are bit-identical.
+    delta_gran : floats per chunk of the delta transfer (8, 16 or 32)
     linear_tracks : "auto" (default) = pools whose moving obstacles all follow constant-velocity tracks
                 (the MovingObstacles family) are stepped with the closed form of the update and keep no
                 per-env obstacle state; False forces the general table-driven update
@@ -140,6 +146,8 @@ class AUVVecEnv:
         world_grid: bool = True,
         compact_host: bool = True,
         host_threads: Optional[int] = None,
+        host_transfer: Optional[str] = None,
+        delta_gran: int = 16,
         _shared: Optional[dict] = None,
     ):
         self.device = torch.device(device)
@@ -339,6 +347,14 @@ class AUVVecEnv:
         self._pinned = None
         self.compact_host = bool(compact_host) and bool(self.config.vessel.use_lidar) and not bool(
             self.config.vessel.sensor_use_velocity_observations)
+        if host_transfer not in (None, "dense", "compact", "delta"):
+            raise ValueError("host_transfer must be 'dense', 'compact' or 'delta'")
+        if host_transfer == "compact" and not self.compact_host:
+            raise ValueError("host_transfer='compact' needs LiDAR observations without velocity channels")
+        self.host_transfer = host_transfer or ("compact" if self.compact_host else "dense")
+        self.compact_host = self.host_transfer == "compact"
+        self.delta_gran = int(delta_gran)
+        self._delta_seen = (0, 0)  # (chunks, steps) at the last d2h_bytes_per_step query
         import os as _os
 
         self.host_threads = int(host_threads) if host_threads else max(1, min(16, len(_os.sched_getaffinity(0))))
@@ -658,7 +674,7 @@ class AUVVecEnv:
     def step_host(self, actions: np.ndarray):
         """NumPy in / NumPy out: the call a CPU-side VecEnv consumer makes (the e2e
         path).  Copies actions H2D and obs/reward/done D2H through pinned buffers."""
-        if self.compact_host:
+        if self.host_transfer != "dense":
             self.step_async(actions)
             return self.step_wait()
         pin = self.step_host_buffers()
@@ -699,7 +715,14 @@ class AUVVecEnv:
         cur = torch.cuda.current_stream(self.device)
         self._async_stream.wait_stream(cur)  # earlier work of this env (reset, step) is ordered before
         with torch.cuda.device(self.device):
-            if self.compact_host:
+            if self.host_transfer == "delta":
+                _lib.check(self.lib.auv_step_host_delta_submit(
+                    cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
+                    C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.byref(pin["delta"]),
+                    C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()),
+                    C.c_void_p(self._async_stream.cuda_stream), self._pipe, max(1, self.host_chunks)),
+                    "auv_step_host_delta_submit")
+            elif self.compact_host:
                 _lib.check(self.lib.auv_step_host_compact_submit(
                     cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
                     C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.byref(pin["compact"]),
@@ -743,11 +766,13 @@ class AUVVecEnv:
             raise ValueError("more groups than envs")
         shared = self._shared_tables()
         kw.setdefault("host_chunks", max(1, self.host_chunks // int(n_groups)))
+        kw.setdefault("host_transfer", self.host_transfer)
+        kw.setdefault("delta_gran", self.delta_gran)
         return [AUVVecEnv(self.scenarios, n, self.config, device=self.device, test_mode=self.test_mode,
                           auto_reset=bool(self.cfg.auto_reset), cull_mode=self._cull_mode, env_offset=g * n,
                           max_nearby=self._max_nearby, velocity_mode=self._velocity_mode,
                           reset_stride=self.reset_stride or self.num_envs, host_threads=self.host_threads,
-                          compact_host=self.compact_host, _shared=shared, **kw)
+                          _shared=shared, **kw)
                 for g in range(int(n_groups))]
 
     def step_host_buffers(self):
@@ -772,6 +797,12 @@ class AUVVecEnv:
                                                p["counter"].data_ptr(), W, N * W * 32)
             else:
                 self._pinned["obs"] = torch.zeros((N, self.obs_dim), dtype=torch.float32).pin_memory()
+                if self.host_transfer == "delta":  # the device's copy of what the host array holds
+                    p = self._pinned
+                    p["shadow"] = torch.zeros((N, self.obs_dim), dtype=torch.float32, device=self.device)
+                    p["shipped"] = torch.zeros(1, dtype=torch.int64, device=self.device)
+                    p["delta"] = _lib.AuvDelta(p["obs"].data_ptr(), p["shadow"].data_ptr(), p["shipped"].data_ptr(),
+                                               self.delta_gran, 0)
         return self._pinned
 
     @property
@@ -786,6 +817,11 @@ class AUVVecEnv:
             p = self._pinned
             nz = int(p["head"].numpy().view(np.int32)[:, 6].sum())
             return self.num_envs * (32 + 4 * p["mask"].shape[1] + 4 + 1) + 4 * nz
+        if self.host_transfer == "delta" and self._pinned is not None:  # average since the previous query
+            chunks, steps = int(self._pinned["shipped"].item()), self.total_steps
+            c0, s0 = self._delta_seen
+            self._delta_seen = (chunks, steps)
+            return self.num_envs * (4 + 1) + int((chunks - c0) * self.delta_gran * 4 / max(1, steps - s0))
         return self.num_envs * (self.obs_dim * 4 + 4 + 1)
 
     def info(self) -> Dict[str, torch.Tensor]:

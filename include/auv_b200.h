@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUV_ABI_VERSION 18
+#define AUV_ABI_VERSION 19
 
 #define AUV_EINVAL (-1)  /* bad argument / NULL pointer / unsupported size */
 #define AUV_ENOTSUP (-2) /* feature not built */
@@ -296,7 +296,7 @@ typedef struct AuvStepOut {
 int auv_abi_version(void);
 /* sizeof of the ABI structs, in declaration order (0 AuvConfig, 1 AuvRayTable, 2 AuvPathBank,
  * 3 AuvScenarioPool, 4 AuvBatch, 5 AuvStepOut, 6 AuvGenParams, 7 AuvPathHdr, 8 AuvRefreshScratch, 9 AuvCompact,
- * 10 AuvPathBuild) so a binding
+ * 10 AuvPathBuild, 11 AuvDelta) so a binding
  * can verify its layout. */
 int auv_sizeof(int which);
 const char* auv_last_error(void);
@@ -384,6 +384,26 @@ int auv_step_host_compact_submit(const AuvConfig* cfg, const AuvRayTable* rays, 
                                  uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks);
 int auv_compact_expand(const AuvConfig* cfg, int n_envs, const AuvCompact* cb, uint32_t* prev_mask, float* obs_host,
                        int n_threads);
+/* Lossless DELTA host step: no host-side work at all.  The caller's dense [N][obs_dim] observation
+ * array lives in PINNED host memory and persists from step to step; the device keeps a shadow copy of
+ * what that array holds.  After each env range is computed, k_obs_delta compares the new rows with
+ * the shadow in chunks of `gran` floats (8, 16 or 32: 32 / 64 / 128 B) and stores ONLY the chunks that
+ * differ -- bitwise -- straight into the host array (and the shadow); reward / done are stored whole.
+ * ~85 % of a row is 0 step after step (rays that read clear), so ~1/4 of the dense bytes cross the
+ * link and the host array is complete the moment the stream drains.  Both arrays must start equal
+ * (e.g. zero-filled).  Works with every observation layout (velocity channels included).  Results
+ * are bit-identical to auv_step_host.  `shipped` accumulates the number of chunks stored. */
+typedef struct AuvDelta {
+  float* obs_host;              /* [N][obs_dim] pinned host, 16 B aligned                  */
+  float* shadow;                /* [N][obs_dim] device, 16 B aligned                       */
+  unsigned long long* shipped;  /* [1] device, cumulative chunks stored (NULL: not counted) */
+  int32_t gran;                 /* floats per chunk: 8, 16 or 32                           */
+  int32_t reserved0;
+} AuvDelta;
+int auv_step_host_delta_submit(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
+                               const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
+                               float* actions_dev, AuvStepOut* out, const AuvDelta* d, float* reward_host,
+                               uint8_t* done_host, void* stream, AuvPipeline* p, int n_chunks);
 /* Per-kernel CUDA-event timing of a step on the launching stream (used by bench.py for the
  * roofline of the dominant kernel).  A timer holds `capacity` slots of 4 events. */
 typedef struct AuvTimer AuvTimer;

@@ -247,6 +247,53 @@ def test_compact_host_step_is_bit_identical_to_the_dense_copy():
     assert (o2[:, 6:] != 0).any() and (o2[:, 6:] == 0).mean() > 0.5
 
 
+@pytest.mark.parametrize("gran,velocity", [(8, False), (16, False), (32, False), (16, True)])
+def test_delta_host_step_is_bit_identical_to_the_dense_copy(gran, velocity):
+    """host_transfer="delta": the dense observation array lives in pinned host memory and the device
+    stores only the chunks that changed since the previous step (k_obs_delta against its shadow copy).
+    The host array equals the device observation bit for bit at every step -- through auto-resets,
+    with an env count that leaves a partial quad at the end, and with the (3, R) velocity layout
+    the compact form does not cover -- while fewer bytes cross the link than the dense copy moves."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    cfg.episode.max_timesteps = 9
+    kw = {}
+    if velocity:
+        cfg.vessel.sensor_use_velocity_observations = True
+        kw["velocity_mode"] = "nearest"
+    n = 301  # n * obs_dim = 301 * 186 is not a multiple of 4: the last quad is partial
+    scn = S.moving_obstacles(n, 6, 6, seed=13, n_paths=5)
+    rs = np.random.RandomState(3)
+    for m in range(0, n, 2):
+        for j in range(6):
+            ang, dist = rs.uniform(0, 2 * np.pi), rs.uniform(20, 100)
+            scn.st_pos[m, j] = scn.vessel_init[m, :2] + dist * np.array([np.cos(ang), np.sin(ang)])
+    dev = AUVVecEnv(scn, n, cfg, auto_reset=True, **kw)
+    dlt = AUVVecEnv(scn, n, cfg, auto_reset=True, host_chunks=2, host_transfer="delta", delta_gran=gran, **kw)
+    assert dlt.host_transfer == "delta" and not dlt.compact_host
+    dev.reset()
+    dlt.reset()
+    acts = random_actions(30, n, 6).astype(np.float32)
+    resets = 0
+    dense_bytes = n * (dev.obs_dim * 4 + 5)
+    for t in range(30):
+        o1, r1, d1, _ = dev.step(torch.as_tensor(acts[t], device="cuda"))
+        if t % 2:
+            dlt.step_async(acts[t])
+            o2, r2, d2 = dlt.step_wait()
+        else:
+            o2, r2, d2 = dlt.step_host(acts[t])
+        torch.cuda.synchronize()
+        assert np.array_equal(o1.cpu().numpy().view(np.uint32), o2.view(np.uint32)), t
+        assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy(), d2)
+        resets += int(d2.sum())
+        if t % 5 == 4:
+            assert 0 < dlt.d2h_bytes_per_step < dense_bytes
+    assert resets > n
+    assert (o2[:, 6:] != 0).any() and (o2[:, 6:] == 0).mean() > 0.5
+
+
 def test_vecenv_adapter_history_and_report(tmp_path):
     """B200VecEnv: the SubprocVecEnv surface scripts/run.py:278-475 drives (NumPy in / out, per-env
     info list with terminal_observation, get_attr('history')) with a fresh GPU-generated scenario per
