@@ -516,6 +516,7 @@ def run_ours(args):
         for g in groups:
             g.d2h_bytes_per_step  # (delta transfer: start the byte count at the timed region)
         barrier()
+        w0 = sum(g.wait_seconds for g in groups)
         t0 = time.perf_counter()
         for g, a in zip(groups, ah):
             g.step_async(a[0])
@@ -536,6 +537,7 @@ def run_ours(args):
                "host_transfer": mode + (f"/{args.delta_gran * 4}B" if mode == "delta" else ""),
                "d2h_bytes_per_step": sum(g.d2h_bytes_per_step for g in groups) * world,
                "host_expand_ms_per_step": expand_ms, "host_threads": groups[0].host_threads if mode == "compact" else 0,
+               "host_blocked_ms_per_step": 1e3 * (sum(g.wait_seconds for g in groups) - w0) / (ke + 1),
                "host_chunks": groups[0].host_chunks}
         torch.cuda.synchronize()
         for g in groups:

@@ -359,6 +359,7 @@ class AUVVecEnv:
 
         self.host_threads = int(host_threads) if host_threads else max(1, min(16, len(_os.sched_getaffinity(0))))
         self.expand_seconds = 0.0  # host time spent in auv_compact_expand (diagnostic)
+        self.wait_seconds = 0.0  # host time spent blocked in step_wait (diagnostic)
         self.chunks = max(1, int(chunks))
         self.host_chunks = max(1, min(64, int(host_chunks))) if host_chunks else self.chunks
         self._pipe = None
@@ -742,7 +743,9 @@ class AUVVecEnv:
     def step_wait(self):
         if not getattr(self, "_async_pending", False):
             raise RuntimeError("step_wait() without a pending step_async()")
+        t0 = time.perf_counter()
         self._async_done.synchronize()
+        self.wait_seconds += time.perf_counter() - t0
         torch.cuda.current_stream(self.device).wait_event(self._async_done)
         self._async_pending = False
         pin = self._pinned
