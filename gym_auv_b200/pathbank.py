@@ -225,11 +225,16 @@ class DevicePathBank:
     path.py:19-40, polyline, prefix sums, capsules) from host waypoints -- milliseconds for 1024 random
     curves instead of ~14 s of SciPy -- in fixed-size slots (``vcap`` polyline vertices per path), so that
     single slots can be rebuilt later (fresh random curves, ``AUVVecEnv.regenerate_paths``).  The host
-    builder ``PathBank`` stays the reference implementation the device tables are tested against."""
+    builder ``PathBank`` stays the reference implementation the device tables are tested against.
+
+    ``vcap``: a PCHIP curve is monotone per coordinate between its knots, so its length is at most the L1
+    length of the waypoint polygon; for ``RandomCurveThroughOrigin(length=800)`` with up to 5 waypoints
+    (movingobstacles.py:30-31) that is < 4.08 x 800 m = 3264 m -> 32642 vertices: the default never overflows
+    for that family (paths of ~1.7 km do occur among a few thousand samples)."""
 
     n_knots = N_KNOTS
 
-    def __init__(self, waypoints: Sequence[np.ndarray], vcap: int = 16384):
+    def __init__(self, waypoints: Sequence[np.ndarray], vcap: int = 32768):
         if len(waypoints) == 0:
             raise ValueError("empty path bank")
         self.waypoints = [np.asarray(w, dtype=np.float64) for w in waypoints]

@@ -261,3 +261,22 @@ def test_parity_harness_counts_steps_inside_the_collision_band():
     ref, gpu = case(w + 3 * COLLISION_BAND)
     with pytest.raises(AssertionError):
         compare(ref, gpu, cfg, "outside the band")
+
+
+def test_device_path_slot_capacity_covers_the_random_curve_family():
+    """DevicePathBank's default slot (vcap vertices at 10 per metre) holds every RandomCurveThroughOrigin
+    (length=800, <= 5 waypoints) curve: PCHIP is monotone per coordinate between knots, so the path length is
+    bounded by the L1 length of the waypoint polygon, which for this family is < 4.08 x length."""
+    from gym_auv_b200.pathbank import DevicePathBank, build_path, random_curve_waypoints
+
+    rng = np.random.RandomState(5)
+    worst = 0.0
+    for k in range(300):
+        w = random_curve_waypoints(rng, int(np.floor(4 * rng.rand() + 2)), length=800.0)
+        l1 = float(np.abs(np.diff(w, axis=1)).sum())
+        assert l1 < 4.08 * 800.0
+        worst = max(worst, l1)
+        if k < 12:
+            assert build_path(w).length <= l1 + 1e-9
+    bank = DevicePathBank([random_curve_waypoints(rng, 5, length=800.0)])
+    assert 10 * 4.08 * 800.0 + 2 <= bank.vcap
