@@ -547,7 +547,8 @@ def run_ours(args):
 
     if e2e is not None and N >= 128:
         modes = ["delta", "compact"] if args.host_transfer == "auto" else [args.host_transfer]
-        if not env.compact_host and "compact" in modes and args.host_transfer == "auto":
+        if "compact" in modes and args.host_transfer == "auto" and (
+                not cfg.vessel.use_lidar or cfg.vessel.sensor_use_velocity_observations):
             modes.remove("compact")
         runs = [async_e2e(m) for m in modes]
         runs.sort(key=lambda r: -r["value"])

@@ -429,15 +429,19 @@ def test_step_host_equals_step():
     cfg = lidar_config()
     scn = S.moving_obstacles(33, 4, 4, seed=12)  # odd batch size on purpose
     e1 = AUVVecEnv(scn, 33, cfg, auto_reset=True)
-    e2 = AUVVecEnv(scn, 33, cfg, auto_reset=True)
-    e1.reset(), e2.reset()
+    e2 = AUVVecEnv(scn, 33, cfg, auto_reset=True, host_transfer="compact")
+    e3 = AUVVecEnv(scn, 33, cfg, auto_reset=True)  # default: delta transfer
+    e1.reset(), e2.reset(), e3.reset()
     acts = random_actions(10, 33, 3).astype(np.float32)
     for t in range(10):
         o1, r1, d1, _ = e1.step(torch.as_tensor(acts[t], device="cuda"))
         o2, r2, d2 = e2.step_host(acts[t])
+        o3, r3, d3 = e3.step_host(acts[t])
         assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
         assert np.array_equal(d1.cpu().numpy(), d2)
+        assert np.array_equal(o2, o3) and np.array_equal(r2, r3) and np.array_equal(d2, d3)
     assert e2.h2d_bytes_per_step == 33 * 8
+    assert e3.host_transfer == "delta" and 33 * 5 < e3.d2h_bytes_per_step < 33 * (186 * 4 + 5)
     nz = int((o2[:, 6:] != 0).sum())  # compact transfer: 32 B head + 6 mask words + reward + done per env, 4 B per non-zero value
     assert e2.compact_host and e2.d2h_bytes_per_step == 33 * (32 + 24 + 5) + 4 * nz < 33 * (186 * 4 + 5)
 

@@ -221,9 +221,10 @@ def test_compact_host_step_is_bit_identical_to_the_dense_copy():
             ang, dist = rs.uniform(0, 2 * np.pi), rs.uniform(20, 100)
             scn.st_pos[m, j] = scn.vessel_init[m, :2] + dist * np.array([np.cos(ang), np.sin(ang)])
     dev = AUVVecEnv(scn, n, cfg, auto_reset=True)
-    cmp_ = AUVVecEnv(scn, n, cfg, auto_reset=True, host_chunks=3, host_threads=3)
+    cmp_ = AUVVecEnv(scn, n, cfg, auto_reset=True, host_chunks=3, host_threads=3, host_transfer="compact")
     dense = AUVVecEnv(scn, n, cfg, auto_reset=True, host_chunks=2, compact_host=False)
-    assert cmp_.compact_host and not dense.compact_host
+    assert cmp_.compact_host and not dense.compact_host and dense.host_transfer == "dense"
+    assert AUVVecEnv(scn, n, cfg).host_transfer == "delta"
     for e in (dev, cmp_, dense):
         e.reset()
     acts = random_actions(30, n, 6).astype(np.float32)
