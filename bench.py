@@ -92,6 +92,8 @@ def parse():
     ap.add_argument("--host-transfer", default="auto", choices=["auto", "delta", "compact", "dense"],
                     help="how the e2e leg delivers observations to host memory (auto: measures delta and compact, "
                          "the faster one is e2e.value, the other is listed under e2e.other)")
+    ap.add_argument("--e2e-groups", type=int, nargs="+", default=[4],
+                    help="env groups of the e2e leg (each value is measured; the fastest run is e2e.value)")
     ap.add_argument("--delta-gran", type=int, default=16, help="floats per chunk of the delta transfer (8, 16, 32)")
     ap.add_argument("--host-threads", type=int, default=None, help="host threads of auv_compact_expand (default: min(16, cores))")
     ap.add_argument("--host-chunks", type=int, default=4,
@@ -491,58 +493,52 @@ def run_ours(args):
     #      step_async / step_wait (stable-baselines' VecEnv interface) so that one group's
     #      observations travel while the other group is computed.  Same env count, same host
     #      buffers, every step's actions come from host memory and every observation lands there.
-    def async_e2e(mode):
-        half = N // 2
-        groups = env.groups(2, host_transfer=mode, delta_gran=args.delta_gran)  # two envs of N/2 sharing this env's device tables
-        for g in groups:
-            g.reset()
-        ah = [[a[:half].copy() for a in acts_np], [a[half:2 * half].copy() for a in acts_np]]
+    def async_e2e(mode, n_groups):
+        ring = env.ring(n_groups, host_transfer=mode, delta_gran=args.delta_gran, host_chunks=1)
+        G, part = len(ring), ring.envs_per_group  # G envs of N/G sharing this env's device tables
+        ring.reset()
+        ah = [[a[g * part:(g + 1) * part].copy() for a in acts_np] for g in range(G)]
+        count = [0] * G
 
-        def refresh_groups(i):
-            if fresh and i % args.refresh_every == args.refresh_every - 1:
-                for g in groups:  # ordered after the group's step on its own stream
-                    with torch.cuda.stream(g._async_stream):
-                        g.refresh_finished_device(seed=seed + 17)
+        def turn_around(g):  # what the consumer does with a finished group: (refresh its vacated scenarios,) next step
+            count[g] += 1
+            if fresh and count[g] % args.refresh_every == 0:
+                with torch.cuda.stream(ring.groups[g]._async_stream):  # ordered after the group's step on its own stream
+                    ring.groups[g].refresh_finished_device(seed=seed + 17)
+            ring.send(g, ah[g][count[g] % 4])
 
-        for g, a in zip(groups, ah):
-            g.step_async(a[0])
-        for i in range(3):  # warm-up (graph capture happens here)
-            for g, a in zip(groups, ah):
-                g.step_wait()
-                g.step_async(a[i % 4])
-        for g in groups:
-            g.step_wait()
-        refresh_groups(args.refresh_every - 1)  # warm-up of the refresh path (creates its worker batch)
-        for g in groups:
-            g.d2h_bytes_per_step  # (delta transfer: start the byte count at the timed region)
+        for g in range(G):
+            ring.send(g, ah[g][0])
+        for _ in range(3 * G):  # warm-up (graph capture happens here)
+            turn_around(ring.recv()[0])
+        ring.drain()
+        for g in range(G):  # warm-up of the refresh path (creates its worker batch)
+            with torch.cuda.stream(ring.groups[g]._async_stream):
+                ring.groups[g].refresh_finished_device(seed=seed + 17)
+            ring.groups[g].d2h_bytes_per_step  # (delta transfer: start the byte count at the timed region)
+        torch.cuda.synchronize()
         barrier()
-        w0 = sum(g.wait_seconds for g in groups)
+        w0 = sum(g.wait_seconds for g in ring.groups)
+        x0 = sum(g.expand_seconds for g in ring.groups)
         t0 = time.perf_counter()
-        for g, a in zip(groups, ah):
-            g.step_async(a[0])
-        for i in range(ke):
-            for g, a in zip(groups, ah):
-                g.step_wait()
-                g.step_async(a[(i + 1) % 4])
-            refresh_groups(i)
-        for g in groups:
-            g.step_wait()
+        for g in range(G):
+            ring.send(g, ah[g][0])
+        for _ in range(ke * G):
+            turn_around(ring.recv()[0])
+        ring.drain()
         dt = time.perf_counter() - t0
         t_a = torch.tensor([dt], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t_a, op=dist.ReduceOp.MAX)
         a_ms = 1e3 * float(t_a.item()) / (ke + 1)
-        expand_ms = 1e3 * sum(g.expand_seconds for g in groups) / (ke + 4 + 1)  # per step of N envs (both groups), incl. warm-up steps
-        res = {"value": world * 2 * half * (ke + 1) / float(t_a.item()), "ms_per_step": a_ms, "steps": ke + 1,
-               "host_transfer": mode + (f"/{args.delta_gran * 4}B" if mode == "delta" else ""),
-               "d2h_bytes_per_step": sum(g.d2h_bytes_per_step for g in groups) * world,
-               "host_expand_ms_per_step": expand_ms, "host_threads": groups[0].host_threads if mode == "compact" else 0,
-               "host_blocked_ms_per_step": 1e3 * (sum(g.wait_seconds for g in groups) - w0) / (ke + 1),
-               "host_chunks": groups[0].host_chunks}
+        res = {"value": world * G * part * (ke + 1) / float(t_a.item()), "ms_per_step": a_ms, "steps": ke + 1,
+               "host_transfer": mode + (f"/{args.delta_gran * 4}B" if mode == "delta" else ""), "groups": G,
+               "d2h_bytes_per_step": sum(g.d2h_bytes_per_step for g in ring.groups) * world,
+               "host_expand_ms_per_step": 1e3 * (sum(g.expand_seconds for g in ring.groups) - x0) / (ke + 1),
+               "host_threads": ring.groups[0].host_threads if mode == "compact" else 0,
+               "host_blocked_ms_per_step": 1e3 * (sum(g.wait_seconds for g in ring.groups) - w0) / (ke + 1)}
         torch.cuda.synchronize()
-        for g in groups:
-            g.close()
-        del groups
+        ring.close()
         return res
 
     if e2e is not None and N >= 128:
@@ -550,12 +546,12 @@ def run_ours(args):
         if "compact" in modes and args.host_transfer == "auto" and (
                 not cfg.vessel.use_lidar or cfg.vessel.sensor_use_velocity_observations):
             modes.remove("compact")
-        runs = [async_e2e(m) for m in modes]
+        runs = [async_e2e(m, g) for m in modes for g in args.e2e_groups]
         runs.sort(key=lambda r: -r["value"])
         sync_part = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "host_chunks": e2e["host_chunks"],
                      "host_transfer": env.host_transfer, "call": "AUVVecEnv.step_host (one synchronous call per step)"}
         e2e.update(runs[0])
-        e2e.update({"mode": "AUVVecEnv.step_async / step_wait, two groups of N/2 envs stepped alternately"
+        e2e.update({"mode": "EnvGroupRing.recv / send over G groups of N/G envs (AUVVecEnv.step_async / step_wait per group)"
                             + (", fresh scenario per episode" if fresh else ""),
                     "sync": sync_part, "other": runs[1:]})
 

@@ -712,31 +712,31 @@ class AUVVecEnv:
             self._async_stream = torch.cuda.Stream(device=self.device)
             self._async_done = torch.cuda.Event()
         pin = self._pinned
-        pin["act"].numpy()[...] = actions
-        cfg, rays, paths, pool, batch = self._refs()
-        cur = torch.cuda.current_stream(self.device)
-        self._async_stream.wait_stream(cur)  # earlier work of this env (reset, step) is ordered before
-        with torch.cuda.device(self.device):
+        if getattr(self, "_async_call", None) is None:  # the argument list never changes: build it once
+            cfg, rays, paths, pool, batch = self._refs()
+            head = (cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()), C.c_void_p(self.actions_dev.data_ptr()),
+                    C.byref(self.out))
+            tail = (C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()),
+                    C.c_void_p(self._async_stream.cuda_stream), self._pipe, max(1, self.host_chunks))
             if self.host_transfer == "delta":
-                _lib.check(self.lib.auv_step_host_delta_submit(
-                    cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
-                    C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.byref(pin["delta"]),
-                    C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()),
-                    C.c_void_p(self._async_stream.cuda_stream), self._pipe, max(1, self.host_chunks)),
-                    "auv_step_host_delta_submit")
+                self._async_call = (self.lib.auv_step_host_delta_submit, head + (C.byref(pin["delta"]),) + tail,
+                                    "auv_step_host_delta_submit")
             elif self.compact_host:
-                _lib.check(self.lib.auv_step_host_compact_submit(
-                    cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
-                    C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.byref(pin["compact"]),
-                    C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()),
-                    C.c_void_p(self._async_stream.cuda_stream), self._pipe, max(1, self.host_chunks)),
-                    "auv_step_host_compact_submit")
+                self._async_call = (self.lib.auv_step_host_compact_submit, head + (C.byref(pin["compact"]),) + tail,
+                                    "auv_step_host_compact_submit")
             else:
-                _lib.check(self.lib.auv_step_host_submit(
-                    cfg, rays, paths, pool, batch, C.c_void_p(pin["act"].data_ptr()),
-                    C.c_void_p(self.actions_dev.data_ptr()), C.byref(self.out), C.c_void_p(pin["obs"].data_ptr()),
-                    C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["done"].data_ptr()),
-                    C.c_void_p(self._async_stream.cuda_stream), self._pipe, max(1, self.host_chunks)), "auv_step_host_submit")
+                self._async_call = (self.lib.auv_step_host_submit, head + (C.c_void_p(pin["obs"].data_ptr()),) + tail,
+                                    "auv_step_host_submit")
+            self._act_np = pin["act"].numpy()
+        self._act_np[...] = actions
+        cur = torch.cuda.current_stream(self.device)
+        if cur != self._async_stream:
+            self._async_stream.wait_stream(cur)  # earlier work of this env (reset, step) is ordered before
+        fn, fargs, name = self._async_call
+        with torch.cuda.device(self.device):
+            rc = fn(*fargs)
+        if rc:
+            _lib.check(rc, name)
         self._async_done.record(self._async_stream)
         self._async_pending = True
         self.total_steps += 1
@@ -778,6 +778,12 @@ class AUVVecEnv:
                           reset_stride=self.reset_stride or self.num_envs, host_threads=self.host_threads,
                           _shared=shared, **kw)
                 for g in range(int(n_groups))]
+
+    def ring(self, n_groups: int = 4, **kw) -> "EnvGroupRing":
+        """The env groups of ``groups(n_groups)`` behind a send / recv interface (the asynchronous mode
+        of batched env pools): ``recv()`` hands out whichever group's step has finished, ``send(g, actions)``
+        submits that group's next step.  See EnvGroupRing."""
+        return EnvGroupRing(self.groups(n_groups, **kw))
 
     def step_host_buffers(self):
         """Pinned host buffers of step_host / step_async (actions in; obs, reward, done out)."""
@@ -912,3 +918,64 @@ class AUVVecEnv:
             self.close()
         except Exception:
             pass
+
+
+class EnvGroupRing:
+    """G env groups stepped out of order: ``send(g, actions)`` submits group g's step (step_async),
+    ``recv()`` returns ``(g, obs, reward, done)`` of the first group whose step has finished and whose
+    results are complete in host memory.  Unlike a fixed ``wait(A); submit(A); wait(B); submit(B)`` loop --
+    which pulls the groups into lock-step (a group that finishes early is only resubmitted after the one
+    before it, so all of them compute at the same time and then queue on the host link together) -- the
+    groups keep whatever phase offset they have, and with G >= 3 the link and the SMs both stay busy
+    while the host turns one group around.  ``start(actions)`` submits the first steps staggered."""
+
+    def __init__(self, groups):
+        self.groups = list(groups)
+        self.pending = []  # group indices in submission order
+        self.spins = 0
+
+    def __len__(self):
+        return len(self.groups)
+
+    @property
+    def envs_per_group(self) -> int:
+        return self.groups[0].num_envs
+
+    def reset(self):
+        return [g.reset() for g in self.groups]
+
+    def send(self, g: int, actions: np.ndarray):
+        self.groups[g].step_async(actions)
+        self.pending.append(g)
+
+    def start(self, actions_per_group):
+        """First submission of every group, each one after the previous group's step has left the SMs
+        (approximated by its completion), so that the groups start spread over the cycle."""
+        for g, a in enumerate(actions_per_group):
+            self.send(g, a)
+            if g + 1 < len(self.groups):
+                self.groups[g]._async_done.synchronize()
+
+    def recv(self):
+        if not self.pending:
+            raise RuntimeError("recv() with no step in flight")
+        t0 = time.perf_counter()
+        while True:
+            for k, g in enumerate(self.pending):
+                if self.groups[g]._async_done.query():
+                    del self.pending[k]
+                    self.groups[g].wait_seconds += time.perf_counter() - t0
+                    obs, rew, done = self.groups[g].step_wait()
+                    return g, obs, rew, done
+            self.spins += 1
+
+    def drain(self):
+        out = []
+        while self.pending:
+            out.append(self.recv())
+        return out
+
+    def close(self):
+        for g in self.groups:
+            g.close()
+        self.groups = []

@@ -295,6 +295,44 @@ def test_delta_host_step_is_bit_identical_to_the_dense_copy(gran, velocity):
     assert (o2[:, 6:] != 0).any() and (o2[:, 6:] == 0).mean() > 0.5
 
 
+def test_env_group_ring_out_of_order_equals_the_whole_env():
+    """EnvGroupRing (send / recv): three groups of n envs stepped in whatever order their steps finish
+    give, step for step, the rows the whole 3n-env batch gives -- through auto-resets, delta transfer."""
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    cfg.episode.max_timesteps = 7
+    n, G, T = 70, 3, 16
+    scn = S.moving_obstacles(G * n, 5, 5, seed=41, n_paths=4)
+    ref = AUVVecEnv(scn, G * n, cfg, auto_reset=True)
+    ring = ref.ring(G)
+    assert len(ring) == G and ring.envs_per_group == n and ring.groups[0].host_transfer == "delta"
+    ref.reset()
+    ring.reset()
+    acts = random_actions(T, G * n, 8).astype(np.float32)
+    want = []
+    for t in range(T):
+        o, r, d, _ = ref.step(torch.as_tensor(acts[t], device="cuda"))
+        want.append((o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()))
+    with pytest.raises(RuntimeError):
+        ring.recv()
+    count = [0] * G
+    for g in (2, 0, 1):
+        ring.send(g, acts[0, g * n:(g + 1) * n])
+    order = []
+    while ring.pending:
+        g, o, r, d = ring.recv()
+        t = count[g]
+        order.append(g)
+        sl = slice(g * n, (g + 1) * n)
+        assert np.array_equal(o, want[t][0][sl]) and np.array_equal(r, want[t][1][sl]) and np.array_equal(d, want[t][2][sl]), (g, t)
+        count[g] += 1
+        if count[g] < T:
+            ring.send(g, acts[count[g], sl])
+    assert count == [T] * G and sum(int(w[2].sum()) for w in want) > G * n
+    ring.close()
+
+
 def test_vecenv_adapter_history_and_report(tmp_path):
     """B200VecEnv: the SubprocVecEnv surface scripts/run.py:278-475 drives (NumPy in / out, per-env
     info list with terminal_observation, get_attr('history')) with a fresh GPU-generated scenario per
