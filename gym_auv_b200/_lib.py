@@ -226,7 +226,7 @@ class AuvCompact(C.Structure):
 
 
 class AuvDelta(C.Structure):
-    _fields_ = [("obs_host", _vp), ("shadow", _vp), ("shipped", _vp), ("gran", C.c_int32), ("reserved0", C.c_int32)]
+    _fields_ = [("obs_host", _vp), ("shadow", _vp), ("shipped", _vp), ("gran", C.c_int32), ("ctas", C.c_int32)]
 
 
 EXPORTS = [

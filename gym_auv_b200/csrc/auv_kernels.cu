@@ -1443,53 +1443,63 @@ __global__ void __launch_bounds__(AUV_SHIP_THREADS) k_obs_ship(const float* __re
 // array and to the shadow -- iff any of its words differs bitwise.  The stores of a chunk are one
 // contiguous, aligned run, so the link sees whole 32 / 64 / 128 B writes.
 // ------------------------------------------------------------------------------------
-#define AUV_DELTA_THREADS 256
-__global__ void __launch_bounds__(AUV_DELTA_THREADS) k_obs_delta(const float* __restrict__ obs, float* __restrict__ shadow,
+#define AUV_DELTA_THREADS 64
+#define AUV_DELTA_UNROLL 2
+// The kernel is bound by the host link, not by the SMs: it runs as a SMALL persistent grid (two
+// CTAs of 64 threads x 40 registers per SM by default: one fits into the registers five k_lidar
+// CTAs leave over) that strides over the range, so that its warps -- stalled on the link's write
+// queue most of the time -- leave the SMs to the step kernels of the next env range / env group
+// running beside it.  (One CTA per 256 quads, the first version, filled every
+// CTA slot of the GPU with stalled warps: the step kernels of the other stream waited for it.)
+__global__ void __launch_bounds__(AUV_DELTA_THREADS, 24) k_obs_delta(const float* __restrict__ obs, float* __restrict__ shadow,
                                                                 float* __restrict__ obs_h, long long f0, long long f1, int g4,
                                                                 const float* __restrict__ reward,
                                                                 const uint8_t* __restrict__ done, float* __restrict__ reward_h,
                                                                 uint8_t* __restrict__ done_h, int e0, int e1,
                                                                 unsigned long long* __restrict__ shipped) {
-  __shared__ int s_count;
-  const int tid = threadIdx.x, lane = tid & 31;
-  if (tid == 0) s_count = 0;
-  __syncthreads();
-  const long long q = (f0 >> 2) + (long long)blockIdx.x * AUV_DELTA_THREADS + tid;  // f0 is a multiple of 4
-  const long long base = q << 2;
-  const bool full = base + 4 <= f1, part = !full && base < f1;
-  bool changed = false;
-  uint4 cur = make_uint4(0u, 0u, 0u, 0u);
-  if (full) {
-    cur = __ldcs(reinterpret_cast<const uint4*>(obs) + q);
-    const uint4 old = __ldcs(reinterpret_cast<const uint4*>(shadow) + q);
-    changed = (cur.x != old.x) | (cur.y != old.y) | (cur.z != old.z) | (cur.w != old.w);
-  } else if (part) {
-    for (long long i = base; i < f1; ++i) changed |= __float_as_uint(obs[i]) != __float_as_uint(shadow[i]);
-  }
-  const unsigned any = __ballot_sync(AUV_FULL, changed);
-  const unsigned cm = (g4 >= 32 ? 0xffffffffu : ((1u << g4) - 1u)) << (lane & ~(g4 - 1));
-  const bool ship = (any & cm) != 0u;
-  if (ship) {
-    if (full) {
-      reinterpret_cast<uint4*>(obs_h)[q] = cur;
-      reinterpret_cast<uint4*>(shadow)[q] = cur;
-    } else if (part) {
-      for (long long i = base; i < f1; ++i) obs_h[i] = shadow[i] = obs[i];
-    }
-  }
-  if (shipped != nullptr) {
-    const unsigned lead = __ballot_sync(AUV_FULL, ship && (lane & (g4 - 1)) == 0);
-    if (lane == 0 && lead) atomicAdd(&s_count, __popc(lead));
-  }
-  const int e = e0 + blockIdx.x * AUV_DELTA_THREADS + tid;
-  if (e < e1) {
+  const int lane = threadIdx.x & 31;
+  const long long nthreads = (long long)gridDim.x * AUV_DELTA_THREADS;
+  const long long gtid = (long long)blockIdx.x * AUV_DELTA_THREADS + threadIdx.x;
+  for (long long e = e0 + gtid; e < e1; e += nthreads) {
     reward_h[e] = reward[e];
     done_h[e] = done[e];
   }
-  if (shipped != nullptr) {
-    __syncthreads();
-    if (tid == 0 && s_count) atomicAdd(shipped, (unsigned long long)s_count);
+  const long long qfull = f1 >> 2, qend = (f1 + 3) >> 2;  // quads wholly inside the range / touched by it (f0 is a multiple of 4)
+  const unsigned cm = (g4 >= 32 ? 0xffffffffu : ((1u << g4) - 1u)) << (lane & ~(g4 - 1));
+  unsigned count = 0u;
+  // qb = the quad of lane 0: the trip count is uniform in the warp
+  for (long long qb = (f0 >> 2) + gtid - lane; qb < qend; qb += nthreads * AUV_DELTA_UNROLL) {
+    uint4 cur[AUV_DELTA_UNROLL], old[AUV_DELTA_UNROLL];
+#pragma unroll
+    for (int u = 0; u < AUV_DELTA_UNROLL; ++u) {
+      const long long q = qb + u * nthreads + lane;
+      cur[u] = old[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (q < qfull) {
+        cur[u] = __ldcs(reinterpret_cast<const uint4*>(obs) + q);
+        old[u] = __ldcs(reinterpret_cast<const uint4*>(shadow) + q);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < AUV_DELTA_UNROLL; ++u) {
+      const long long q = qb + u * nthreads + lane;
+      const bool full = q < qfull, part = !full && q < qend;
+      bool changed = (cur[u].x != old[u].x) | (cur[u].y != old[u].y) | (cur[u].z != old[u].z) | (cur[u].w != old[u].w);
+      if (part)
+        for (long long i = q << 2; i < f1; ++i) changed |= __float_as_uint(obs[i]) != __float_as_uint(shadow[i]);
+      const unsigned any = __ballot_sync(AUV_FULL, changed);
+      const bool ship = (any & cm) != 0u;
+      if (ship) {
+        if (full) {
+          reinterpret_cast<uint4*>(obs_h)[q] = cur[u];
+          reinterpret_cast<uint4*>(shadow)[q] = cur[u];
+        } else if (part) {
+          for (long long i = q << 2; i < f1; ++i) obs_h[i] = shadow[i] = obs[i];
+        }
+      }
+      count += __popc(__ballot_sync(AUV_FULL, ship && (full || part) && (lane & (g4 - 1)) == 0));
+    }
   }
+  if (shipped != nullptr && lane == 0 && count) atomicAdd(shipped, (unsigned long long)count);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1933,10 +1943,20 @@ static int launch_obs_delta(const AuvConfig* cfg, const AuvStepOut* out, const A
   const long long od = auv_obs_dim(cfg);
   const long long f0 = od * e0, f1 = od * (e0 + cnt);  // e0 is a multiple of 256 envs: f0 is 1 KB aligned
   const long long quads = (f1 - f0 + 3) / 4;
-  const long long work = quads > cnt ? quads : cnt;
-  const int blocks = (int)((work + AUV_DELTA_THREADS - 1) / AUV_DELTA_THREADS);
-  auv::k_obs_delta<<<blocks, AUV_DELTA_THREADS, 0, s>>>(out->obs, d->shadow, d->obs_host, f0, f1, d->gran / 4, out->reward,
-                                                       out->done, reward_host, done_host, e0, e0 + cnt, d->shipped);
+  static std::atomic<int> sms[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  int n_sm = sms[dev].load();
+  if (n_sm == 0) {
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    sms[dev].store(n_sm);
+  }
+  long long blocks = d->ctas > 0 ? d->ctas : 2 * n_sm;
+  const long long need = (quads + AUV_DELTA_THREADS - 1) / AUV_DELTA_THREADS;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  auv::k_obs_delta<<<(int)blocks, AUV_DELTA_THREADS, 0, s>>>(out->obs, d->shadow, d->obs_host, f0, f1, d->gran / 4, out->reward,
+                                                            out->done, reward_host, done_host, e0, e0 + cnt, d->shipped);
   return cuda_check(cudaGetLastError(), "k_obs_delta");
 }
 

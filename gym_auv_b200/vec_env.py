@@ -812,7 +812,7 @@ class AUVVecEnv:
                     p["shadow"] = torch.zeros((N, self.obs_dim), dtype=torch.float32, device=self.device)
                     p["shipped"] = torch.zeros(1, dtype=torch.int64, device=self.device)
                     p["delta"] = _lib.AuvDelta(p["obs"].data_ptr(), p["shadow"].data_ptr(), p["shipped"].data_ptr(),
-                                               self.delta_gran, 0)
+                                               self.delta_gran, int(os.environ.get("AUV_B200_DELTA_CTAS", "0")))
         return self._pinned
 
     @property

@@ -398,7 +398,7 @@ typedef struct AuvDelta {
   float* shadow;                /* [N][obs_dim] device, 16 B aligned                       */
   unsigned long long* shipped;  /* [1] device, cumulative chunks stored (NULL: not counted) */
   int32_t gran;                 /* floats per chunk: 8, 16 or 32                           */
-  int32_t reserved0;
+  int32_t ctas;                 /* CTAs of the (link-bound, persistent) kernel; 0 = two per SM */
 } AuvDelta;
 int auv_step_host_delta_submit(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                                const AuvScenarioPool* pool, AuvBatch* batch, const float* actions_host,
