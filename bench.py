@@ -42,13 +42,19 @@ FLOP_PER_SEG_TEST = 16
 FLOP_PER_RAY = 60
 
 
+DENSE_RANGE = 1500.0  # --dense: a sensor range that covers the whole 800 m scenario area
+
+
 def workload_config(args, use_lidar=True):
     """`config` of the JSON line: what names the workload -- identical for this arm and for `--impl reference`."""
     R = args.rays if use_lidar else 0
-    default = args.workload == "moving" and args.envs == 65536 and args.rays == 180 and args.n_moving == 16 and args.n_static == 16
+    dense = bool(getattr(args, "dense", False))
+    default = (args.workload == "moving" and args.envs == 65536 and args.rays == 180 and args.n_moving == 16
+               and args.n_static == 16 and not dense)
     name = WORKLOAD if default else (
         f"{args.workload}: {args.envs} envs/GPU x {R} rays x {args.n_moving}+{args.n_static} obstacles"
-        + (f" + {args.n_polygons} shared land polygons" if args.workload == "land" else ""))
+        + (f" + {args.n_polygons} shared land polygons" if args.workload == "land" else "")
+        + (f", DENSE: sensor range {DENSE_RANGE:.0f} m, every obstacle slot is a record at every step" if dense else ""))
     return {"workload": name, "envs_per_gpu": args.envs, "rays": R, "obstacles": args.n_moving + args.n_static,
             "paths": args.n_paths, "auto_reset": True,
             "scenarios": "a fresh scenario of the MovingObstacles distribution for every episode" if args.workload == "moving"
@@ -92,6 +98,8 @@ def parse():
     ap.add_argument("--host-transfer", default="auto", choices=["auto", "delta", "compact", "dense"],
                     help="how the e2e leg delivers observations to host memory (auto: measures delta and compact, "
                          "the faster one is e2e.value, the other is listed under e2e.other)")
+    ap.add_argument("--dense", action="store_true",
+                    help="stress line: sensor range 1500 m, so all obstacle slots are nearby and cast against at every step")
     ap.add_argument("--e2e-groups", type=int, nargs="+", default=[4],
                     help="env groups of the e2e leg (each value is measured; the fastest run is e2e.value)")
     ap.add_argument("--delta-gran", type=int, default=16, help="floats per chunk of the delta transfer (8, 16, 32)")
@@ -175,7 +183,8 @@ def build_workload(args, rank):
     cache = getattr(args, "scenario_cache", None)
     if cache:
         cache = (f"{cache}.{args.workload}.{args.envs}.{args.rays}.{args.n_moving}.{args.n_static}.{args.n_paths}."
-                 f"{args.seed}.{rank}.{int(bool(getattr(args, 'host_scenarios', False)))}{int(bool(getattr(args, 'host_paths', False)))}")
+                 f"{args.seed}.{rank}.{int(bool(getattr(args, 'host_scenarios', False)))}{int(bool(getattr(args, 'host_paths', False)))}"
+                 f"{int(bool(getattr(args, 'dense', False)))}")
         if os.path.exists(cache):
             with open(cache, "rb") as f:
                 return pickle.load(f)
@@ -199,6 +208,8 @@ def _build_workload(args, rank):
         cfg.vessel.n_sectors = 8
         per_sector = args.rays // 8
     cfg.vessel.n_sensors_per_sector = per_sector
+    if getattr(args, "dense", False):
+        cfg.vessel.sensor_range = DENSE_RANGE
     if getattr(args, "workload", "moving") == "land":
         scn = S.land_scenarios(args.envs, n_polygons=args.n_polygons, n_moving=args.n_moving, n_static=args.n_static,
                                seed=args.seed + 1000 * rank, n_paths=args.n_paths)
@@ -266,8 +277,8 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     small = argparse.Namespace(**vars(args))
-    small.envs = max(cores * 2, 16)
-    small.n_paths = min(args.n_paths, small.envs)
+    small.envs = max(cores * 16, 64)  # seconds of work per process per step, not milliseconds
+    small.n_paths = min(args.n_paths, 64)  # (SciPy builds each path in ~14 ms: untimed set-up)
     small.host_scenarios = True
     cfg, scn = build_workload(small, 0)
     per_step_envs = small.envs

@@ -9,9 +9,12 @@ Constructor signature, return types (``float`` reward, ``bool`` done, ``dict`` i
 the four reference keys), ``seed()``, spaces, and the attributes the reference's driver
 reads (``history, last_episode, total_t_steps, episode, t_step, cumulative_reward,
 config, obstacles, vessel, path, rewarder.params`` -- scripts/run.py:415-426) are kept.
-A scenario plug-in overrides ``_generate()`` and returns a one-scenario ``ScenarioSet``
-(the batched counterpart of setting ``self.vessel/self.path/self.obstacles``,
-environment.py:394-399).  Rendering is out of scope:
+A scenario plug-in overrides ``_generate()`` and returns a ``ScenarioSet`` (the batched
+counterpart of setting ``self.vessel/self.path/self.obstacles``, environment.py:394-399)
+holding one scenario -- or, via ``_generate_block(n)``, the scenarios of the next n episodes:
+the facade keeps ONE AUVVecEnv (device tables, path bank, reset cache) alive for the whole
+block and moves from scenario to scenario with ``reset_envs``; it is rebuilt only when the
+block is used up.  Rendering is out of scope:
 ``renderer`` must be None.
 """
 from __future__ import annotations
@@ -40,6 +43,7 @@ class AUVEnv:
 
     metadata = {"render.modes": []}
     scenario_name = ""
+    block_size = 64  # episodes generated (and uploaded) at a time by families that implement _generate_block
 
     def __init__(
         self,
@@ -73,6 +77,10 @@ class AUVEnv:
         self._seed_counter = 0
         self.seed()
         self._vec = None
+        self._recycle = False
+        self._block_pos = 0
+        self._idx = 0
+        self.vec_env_builds = 0  # how many times the backing AUVVecEnv was (re)built (diagnostic)
         n = cfg.vessel.dense_observation_size + (cfg.vessel.n_lidar_observations if cfg.vessel.use_lidar else 0)
         self.n_observations = n
         self._action_space = Box(low=np.array([-1, -0.15]), high=np.array([1, 0.15]), dtype=np.float32)
@@ -90,6 +98,11 @@ class AUVEnv:
     # -- plug-in hook -------------------------------------------------------------
     def _generate(self) -> S.ScenarioSet:
         raise NotImplementedError
+
+    def _generate_block(self, n: int):
+        """-> (ScenarioSet, recycle).  The scenarios of the next episodes, in order; recycle=True means the
+        set is the same every time (a deterministic scenario) and is simply replayed."""
+        return self._generate(), False
 
     # -- gym contract -------------------------------------------------------------
     @property
@@ -114,13 +127,23 @@ class AUVEnv:
         self.episode += 1
         self.total_t_steps += self.t_step if self._vec is not None else 0
         self.last_reward = 0
-        self.scenario = self._generate()
-        self._vec = AUVVecEnv(self.scenario, 1, self.config, device=self.device, test_mode=self.test_mode,
-                              auto_reset=False, debug=True)
-        self.rewarder = SimpleNamespace(params=dict(REWARDER_PARAMS[self.scenario.rewarder]))
-        self._cte = []
         self._info = dict(collision=False, reached_goal=False, goal_distance=None, progress=0)
-        return self._format_obs(self._vec.reset())
+        if self._vec is None or (self._block_pos >= self.scenario.n_scenarios and not self._recycle):
+            self.scenario, self._recycle = self._generate_block(self.block_size)
+            self._vec = AUVVecEnv(self.scenario, 1, self.config, device=self.device, test_mode=self.test_mode,
+                                  auto_reset=False, debug=True)
+            self.vec_env_builds += 1
+            self.rewarder = SimpleNamespace(params=dict(REWARDER_PARAMS[self.scenario.rewarder]))
+            self._block_pos, self._idx = 1, 0
+            return self._format_obs(self._vec.reset())
+        import torch
+
+        self._idx = self._block_pos % self.scenario.n_scenarios
+        self._block_pos += 1
+        one = torch.ones(1, dtype=torch.uint8, device=self._vec.device)
+        obs = self._vec.reset_envs(one, torch.tensor([self._idx], dtype=torch.int32, device=self._vec.device))
+        self._vec.check_status()
+        return self._format_obs(self._vec._fmt(obs))
 
     def step(self, action):
         import torch
@@ -193,11 +216,11 @@ class AUVEnv:
 
     @property
     def path(self):
-        return self.scenario.bank.tables[int(self.scenario.path_id[0])]
+        return self.scenario.bank.tables[int(self.scenario.path_id[self._idx])]
 
     @property
     def obstacles(self):
-        return self.scenario.describe(0)
+        return self.scenario.describe(self._idx)
 
     def save_latest_episode(self, save_history=True):
         """environment.py:466-489 (path_taken histories are not kept: SURVEY B11)."""
@@ -230,6 +253,14 @@ def scenario_env(name: str, default_config=None):
             if "start_angle" in params:
                 return builder(start_angle=float(self.rng.uniform(-np.deg2rad(5), np.deg2rad(5))))
             return builder()
+
+        def _generate_block(self, n):
+            import inspect
+
+            params = inspect.signature(builder).parameters
+            if "n" in params and "seed" in params:  # random families: the next n episodes in one set
+                return builder(n=int(n), seed=int(self.rng.randint(0, 2**31 - 1))), False
+            return self._generate(), not ({"seed", "start_angle"} & set(params))
 
     _Env.__name__ = name.split("-")[0]
     _Env.default_config = default_config

@@ -541,6 +541,6 @@ SCENARIOS = {
     "TestCrossing1-v0": test_crossing1,
     "DebugScenario-v0": debug_scenario,
     "EmptyScenario-v0": empty_scenario,
-    "MovingObstaclesNoRules-v0": lambda seed=0: moving_obstacles(1, 17, 11, seed=seed),
-    "PathFollowNoObstacles-v0": lambda seed=0: path_follow_no_obstacles(1, seed=seed),
+    "MovingObstaclesNoRules-v0": lambda seed=0, n=1: moving_obstacles(n, 17, 11, seed=seed),
+    "PathFollowNoObstacles-v0": lambda seed=0, n=1: path_follow_no_obstacles(n, seed=seed),
 }

@@ -927,7 +927,7 @@ class EnvGroupRing:
     which pulls the groups into lock-step (a group that finishes early is only resubmitted after the one
     before it, so all of them compute at the same time and then queue on the host link together) -- the
     groups keep whatever phase offset they have, and with G >= 3 the link and the SMs both stay busy
-    while the host turns one group around.  ``start(actions)`` submits the first steps staggered."""
+    while the host turns one group around."""
 
     def __init__(self, groups):
         self.groups = list(groups)
@@ -947,14 +947,6 @@ class EnvGroupRing:
     def send(self, g: int, actions: np.ndarray):
         self.groups[g].step_async(actions)
         self.pending.append(g)
-
-    def start(self, actions_per_group):
-        """First submission of every group, each one after the previous group's step has left the SMs
-        (approximated by its completion), so that the groups start spread over the cycle."""
-        for g, a in enumerate(actions_per_group):
-            self.send(g, a)
-            if g + 1 < len(self.groups):
-                self.groups[g]._async_done.synchronize()
 
     def recv(self):
         if not self.pending:

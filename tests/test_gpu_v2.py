@@ -333,6 +333,46 @@ def test_env_group_ring_out_of_order_equals_the_whole_env():
     ring.close()
 
 
+def test_facade_keeps_one_vec_env_alive_across_episodes():
+    """AUVEnv.reset(): a random family generates the scenarios of the next `block_size` episodes at once
+    and walks through them with reset_envs on ONE AUVVecEnv (device tables, path bank, reset cache built
+    once per block); deterministic scenarios replay their single scenario.  Every episode equals what a
+    freshly built 1-env AUVVecEnv gives on that scenario of the block."""
+    import gym_auv_b200
+    from gym_auv_b200.vec_env import AUVVecEnv
+
+    cfg = lidar_config()
+    env = gym_auv_b200.make("MovingObstaclesNoRules-v0", cfg)
+    env.block_size = 3
+    env._vec = None  # drop the block the constructor generated with the default size
+    env.vec_env_builds = 0
+    acts = random_actions(6, 1, 9).astype(np.float32)
+    firsts = []
+    for ep in range(5):  # 3 episodes on the first block, 2 on the second
+        o = env.reset()
+        if ep % 3 == 0:
+            block = env.scenario
+            assert block.n_scenarios == 3
+        assert env.scenario is block
+        fresh = AUVVecEnv(block, 1, cfg, auto_reset=False, env_offset=ep % 3)  # env 0 sits on scenario ep % 3
+        o_f = fresh.reset()[0].cpu().numpy().astype(np.float64)
+        assert np.array_equal(o, o_f), ep
+        for t in range(6):
+            o, r, d, info = env.step(acts[t, 0])
+            of, rf, df, _ = fresh.step(torch.as_tensor(acts[t], device="cuda"))
+            assert np.array_equal(o, of[0].cpu().numpy().astype(np.float64)) and r == float(rf.item()), (ep, t)
+        assert env.t_step == 6
+        firsts.append(o)
+        assert len(env.obstacles) > 0 and env.path.length > 100
+    assert env.vec_env_builds == 2 and len(env.history) == 4 and env.episode == 6
+    assert not np.array_equal(firsts[0], firsts[1])
+    fixed = gym_auv_b200.make("TestScenario3-v0", cfg)
+    for _ in range(3):
+        fixed.reset()
+        fixed.step([0.5, 0.1])
+    assert fixed.vec_env_builds == 1
+
+
 def test_vecenv_adapter_history_and_report(tmp_path):
     """B200VecEnv: the SubprocVecEnv surface scripts/run.py:278-475 drives (NumPy in / out, per-env
     info list with terminal_observation, get_attr('history')) with a fresh GPU-generated scenario per
