@@ -569,9 +569,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // the ~50 capsule tests per env then read shared memory instead of four dependent rounds of
 // global loads.  CTAs with mixed paths (or a path with more than AUV_PATH_STAGE_BLOCKS blocks)
 // search the global tables; the arithmetic is the same.
-#ifndef AUV_LIDAR_GROUPSKIP
-#define AUV_LIDAR_GROUPSKIP 1  // the observation pass computes only the 64-ray groups some record shortened a ray of
-#endif
 #ifndef AUV_NAV_G
 #define AUV_NAV_G 4
 #endif
@@ -779,11 +776,10 @@ struct LidarSmem {
   float* pen;       // [E]       sum of w_i (penalty_i - clear penalty) over hit rays
   int* flag;        // [E]       bit 0 collision, bit 1 auto-reset pending
   int* next;        // [E]       scenario the env resets onto
-  unsigned* grp;    // [E]       bit g: some ray of the 64-ray group g was shortened by an obstacle
 };
 __host__ __device__ constexpr size_t lidar_smem_bytes_for(int E, int rpad, int vmax, int vel) {
   return (size_t)E * 16 * 8 + (size_t)E * rpad * (vel ? 8 : 4) + AUV_LIDAR_RCAP * sizeof(ObstRec) + AUV_LIDAR_RCAP * 4 +
-         (size_t)(AUV_LIDAR_THREADS / 32) * vmax * 8 + 64 * 8 + 48 * 4 + 32 * 4 + 32 * 4 + 32 * 4 + 32 * 4;
+         (size_t)(AUV_LIDAR_THREADS / 32) * vmax * 8 + 64 * 8 + 48 * 4 + 32 * 4 + 32 * 4 + 32 * 4;
 }
 __device__ __forceinline__ LidarSmem lidar_carve(unsigned char* p, int E, int rpad, int vmax, int vel) {
   LidarSmem s;
@@ -806,8 +802,6 @@ __device__ __forceinline__ LidarSmem lidar_carve(unsigned char* p, int E, int rp
   s.flag = reinterpret_cast<int*>(p);
   p += 32 * 4;
   s.next = reinterpret_cast<int*>(p);
-  p += 32 * 4;
-  s.grp = reinterpret_cast<unsigned*>(p);
   return s;
 }
 
@@ -897,6 +891,40 @@ __device__ __forceinline__ void range_min(void* row, int i, float d, int slot) {
 #ifndef AUV_LIDAR_MINB
 #define AUV_LIDAR_MINB 5  // 48 registers (4 / 5 / 6 CTAs per SM: 0.0807 / 0.0767 / 0.101 ms)
 #endif
+#ifndef AUV_LIDAR_LONG_POLY
+#define AUV_LIDAR_LONG_POLY 1  // 0: tuning builds without the out-of-line long-polygon path (such polygons are flagged)
+#endif
+// A world polygon with more vertices than a warp's vertex stage holds, cast chain by chain
+// (consecutive chains share their end vertex).  Cold: land perimeters of thousands of vertices only.
+template <bool VEL>
+__device__ __noinline__ void cast_long_polygon(const double2* __restrict__ wv, int nq, int vmax, float2* wverts, double px,
+                                               double py, double cpsi, double spsi, const double2* __restrict__ cos_sin,
+                                               float ecx, float ecy, float rho, void* row, int slot, int lane, int n1, int n2,
+                                               int lo1, int lo2, float rangef) {
+  const float slack = rho * 1e-5f + 1e-4f;
+  const int tot = n1 + n2;
+  for (int v0 = 0; v0 < nq - 1; v0 += vmax - 1) {
+    const int nqc = min(nq - v0, vmax);
+    __syncwarp();
+    for (int k = lane; k < nqc; k += 32) {
+      const double2 w = wv[v0 + k];
+      wverts[k] = make_float2((float)(w.x - px), (float)(w.y - py));
+    }
+    __syncwarp();
+    for (int u = lane; u < tot; u += 32) {
+      const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
+      const float cur = range_get<VEL>(row, i);
+      const double2 cs = cos_sin[i];
+      const float c = (float)(cs.x * cpsi - cs.y * spsi), sn = (float)(cs.y * cpsi + cs.x * spsi);
+      const float tc = ecx * c + ecy * sn;
+      const float hc = ecy * c - ecx * sn;
+      if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > cur) continue;
+      const float got = cast_chain(wverts, nqc, c, sn, cur, rangef);
+      if (got < cur) range_min<VEL>(row, i, got, slot);
+    }
+  }
+}
+
 template <bool COUNT, bool VEL>
 __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(const __grid_constant__ LidarArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -918,7 +946,6 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
   // ---- phase 1: hand-over lines, unit table, range rows
   for (int k = tid; k < ne * 16; k += AUV_LIDAR_THREADS)
     sm.hand[k] = batch.nav[(long long)(env0 + (k >> 4)) * AUV_NAV_W + NAV_HAND + (k & 15)];
-  if (tid < AUV_LIDAR_MAX_ENVS) sm.grp[tid] = 0u;
   if (cfg.use_lidar) {
     if (tid < 64) {
       const double2 un = reinterpret_cast<const double2*>(A.rays.unit64)[tid];
@@ -996,85 +1023,73 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
         if (tot == 0) continue;
         void* row = VEL ? (void*)(reinterpret_cast<unsigned long long*>(sm.sdist) + (size_t)el * rpad)
                         : (void*)(reinterpret_cast<float*>(sm.sdist) + (size_t)el * rpad);
-        unsigned gbits = 0u;  // 64-ray groups this lane shortened a ray of
         if (fl & OFLAG_INSIDE) {  // own-ship inside a filled boundary: every candidate ray reads 0
-          for (int u = lane; u < tot; u += 32) {
-            const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
-            range_min<VEL>(row, i, 0.f, slot);
-            gbits |= 1u << (i >> 6);
-          }
-          gbits = __reduce_or_sync(AUV_FULL, gbits);
-          if (lane == 0 && gbits) atomicOr(&sm.grp[el], gbits);
+          for (int u = lane; u < tot; u += 32) range_min<VEL>(row, u < n1 ? lo1 + u : lo2 + (u - n1), 0.f, slot);
           continue;
         }
         const bool ngon = !(fl & (OFLAG_PENTAGON | OFLAG_WORLD)) && nq > 16;
-        if (!ngon && !(fl & OFLAG_WORLD) && nq > A.vmax) {  // cannot happen (pentagon 6, small n-gon <= 9 vertices)
-          if (lane == 0 && batch.status != nullptr) atomicOr(batch.status, AUV_STATUS_POLY_TOO_LARGE);
-          continue;
+        if (!ngon) {
+          if (nq > A.vmax) {
+            // a world polygon with more vertices than the stage holds (land perimeters of any length): cast chain
+            // by chain, out of line -- the hot loop below stays as small as it was without them
+            if (AUV_LIDAR_LONG_POLY && (fl & OFLAG_WORLD))
+              cast_long_polygon<VEL>(reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase, nq, A.vmax, wverts,
+                                     HAND(el, NAV_X), HAND(el, NAV_Y), HAND(el, NAV_COSPSI), HAND(el, NAV_SINPSI), cos_sin,
+                                     q.ecx, q.ecy, q.rho, row, slot, lane, n1, n2, lo1, lo2, rangef);
+            else if (lane == 0 && batch.status != nullptr)  // cannot happen (pentagon 6, small n-gon <= 9 vertices)
+              atomicOr(batch.status, AUV_STATUS_POLY_TOO_LARGE);
+            continue;
+          }
+          // stage the vertices: vessel-relative, formed in FP64, stored FP32
+          __syncwarp();
+          if (fl & OFLAG_WORLD) {
+            const double px = HAND(el, NAV_X), py = HAND(el, NAV_Y);
+            const double2* wv = reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase;
+            for (int k = lane; k < nq; k += 32) {
+              const double2 w = wv[k];
+              wverts[k] = make_float2((float)(w.x - px), (float)(w.y - py));
+            }
+          } else if (fl & OFLAG_PENTAGON) {
+            if (lane < 6) {
+              double vx, vy;
+              pent_vertex(lane == 5 ? 0 : lane, q.cx, q.cy, q.geo, q.hx, q.hy, vx, vy);
+              wverts[lane] = make_float2((float)vx, (float)vy);
+            }
+          } else {  // small polygonised circle (2 / 4 / 8 sides) incl. the closing vertex
+            const int ne_ = nq - 1, sh = 6 - (31 - __clz(ne_));
+            if (lane < nq) {
+              const double2 un = __ldg(&unit[(lane == ne_ ? 0 : lane) << sh]);
+              wverts[lane] = make_float2((float)(q.cx + q.geo * un.x), (float)(q.cy + q.geo * un.y));
+            }
+          }
+          __syncwarp();
         }
         const double cpsi = HAND(el, NAV_COSPSI), spsi = HAND(el, NAV_SINPSI);
         const float psi_m_pi = (float)(HAND(el, NAV_PSI) - AUV_PI);
         const float ecx = q.ecx, ecy = q.ecy, rho = q.rho;
         const float slack = rho * 1e-5f + 1e-4f;
-        AUV_CHECK(batch.status, tot <= R && (n1 == 0 || (lo1 >= 0 && lo1 + n1 <= R)) && (n2 == 0 || (lo2 >= 0 && lo2 + n2 <= R)));
-        // a world polygon with more vertices than the stage holds is cast chain by chain (consecutive
-        // chains share their end vertex), so land perimeters of any length are supported
-        const int nchain = (!ngon && nq > A.vmax) ? (nq - 2) / (A.vmax - 1) + 1 : 1;
-        for (int ch = 0; ch < nchain; ++ch) {
-          const int v0 = ch * (A.vmax - 1);
-          const int nqc = nchain == 1 ? nq : min(nq - v0, A.vmax);
-          if (!ngon) {
-            // stage the vertices: vessel-relative, formed in FP64, stored FP32
-            __syncwarp();
-            if (fl & OFLAG_WORLD) {
-              const double px = HAND(el, NAV_X), py = HAND(el, NAV_Y);
-              const double2* wv = reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase + v0;
-              for (int k = lane; k < nqc; k += 32) {
-                const double2 w = wv[k];
-                wverts[k] = make_float2((float)(w.x - px), (float)(w.y - py));
-              }
-            } else if (fl & OFLAG_PENTAGON) {
-              if (lane < 6) {
-                double vx, vy;
-                pent_vertex(lane == 5 ? 0 : lane, q.cx, q.cy, q.geo, q.hx, q.hy, vx, vy);
-                wverts[lane] = make_float2((float)vx, (float)vy);
-              }
-            } else {  // small polygonised circle (2 / 4 / 8 sides) incl. the closing vertex
-              const int ne_ = nq - 1, sh = 6 - (31 - __clz(ne_));
-              if (lane < nq) {
-                const double2 un = __ldg(&unit[(lane == ne_ ? 0 : lane) << sh]);
-                wverts[lane] = make_float2((float)(q.cx + q.geo * un.x), (float)(q.cy + q.geo * un.y));
-              }
-            }
-            __syncwarp();
+        AUV_CHECK(batch.status, tot <= R && (n1 == 0 || (lo1 >= 0 && lo1 + n1 <= R)) && (n2 == 0 || (lo2 >= 0 && lo2 + n2 <= R)) &&
+                                    (ngon || nq <= A.vmax));
+        for (int u = lane; u < tot; u += 32) {
+          const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
+          AUV_CHECK(batch.status, i >= 0 && i < R && i < rpad);
+          const float cur = range_get<VEL>(row, i);
+          // ray direction in the world frame, formed in FP64 (vessel.py:317)
+          const double2 cs = cos_sin[i];
+          const float c = (float)(cs.x * cpsi - cs.y * spsi), sn = (float)(cs.y * cpsi + cs.x * spsi);
+          const float tc = ecx * c + ecy * sn;
+          const float hc = ecy * c - ecx * sn;
+          if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > cur) continue;
+          float got;
+          if (ngon) {
+            // world angle of ray i; only selects which polygon edge the analytic pick looks at
+            const float theta = fmaf((float)(i + 1), dth_f, psi_m_pi);
+            got = cast_ngon(ecx, ecy, rho, nq - 1, sm.unit, c, sn, theta, tc, hc, cur, rangef);
+          } else {
+            got = cast_chain(wverts, nq, c, sn, cur, rangef);
           }
-          AUV_CHECK(batch.status, ngon || nqc <= A.vmax);
-          for (int u = lane; u < tot; u += 32) {
-            const int i = u < n1 ? lo1 + u : lo2 + (u - n1);
-            AUV_CHECK(batch.status, i >= 0 && i < R && i < rpad);
-            const float cur = range_get<VEL>(row, i);
-            // ray direction in the world frame, formed in FP64 (vessel.py:317)
-            const double2 cs = cos_sin[i];
-            const float c = (float)(cs.x * cpsi - cs.y * spsi), sn = (float)(cs.y * cpsi + cs.x * spsi);
-            const float tc = ecx * c + ecy * sn;
-            const float hc = ecy * c - ecx * sn;
-            if (fabsf(hc) > rho + slack || tc + rho + slack < 0.f || tc - rho - slack > cur) continue;
-            float got;
-            if (ngon) {
-              // world angle of ray i; only selects which polygon edge the analytic pick looks at
-              const float theta = fmaf((float)(i + 1), dth_f, psi_m_pi);
-              got = cast_ngon(ecx, ecy, rho, nq - 1, sm.unit, c, sn, theta, tc, hc, cur, rangef);
-            } else {
-              got = cast_chain(wverts, nqc, c, sn, cur, rangef);
-            }
-            if (got < cur) {
-              range_min<VEL>(row, i, got, slot);
-              gbits |= 1u << (i >> 6);
-            }
-          }
+          if (got < cur) range_min<VEL>(row, i, got, slot);
         }
-        gbits = __reduce_or_sync(AUV_FULL, gbits);
-        if (lane == 0 && gbits) atomicOr(&sm.grp[el], gbits);
       }
       __syncthreads();
     }
@@ -1100,26 +1115,10 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
                             : (const void*)(reinterpret_cast<const float*>(sm.sdist) + (size_t)el * rpad);
       float extra = 0.f;
       bool collision = false;
-      const unsigned gb = sm.grp[el];  // groups of 64 rays (= 32 float2 pairs = one iteration below) with a hit
-      if (cnt > 0 && (gb != 0u || !AUV_LIDAR_GROUPSKIP)) {
+      if (cnt > 0) {
         const double cpsi = HAND(el, NAV_COSPSI), spsi = HAND(el, NAV_SINPSI);
         const ObstRec* grec = reinterpret_cast<const ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
         for (int k = lane; k < (R + 1) / 2; k += 32) {
-          if (AUV_LIDAR_GROUPSKIP && !((gb >> (k >> 5)) & 1u)) {  // warp-uniform: no ray of this group was shortened -- zeros, nothing to compute
-            if (vec2) {
-              if (2 * k + 1 < R)
-                reinterpret_cast<float2*>(obs + 6)[k] = make_float2(0.f, 0.f);
-              else
-                obs[6 + 2 * k] = 0.f;
-            } else {
-              obs[6 + 2 * k] = 0.f;
-              if (2 * k + 1 < R) obs[6 + 2 * k + 1] = 0.f;
-            }
-            if (vel_obs)
-              for (int h = 0; h < 2; ++h)
-                if (2 * k + h < R) obs[6 + R + 2 * k + h] = obs[6 + 2 * R + 2 * k + h] = 0.f;
-            continue;
-          }
           float cl2[2] = {0.f, 0.f};
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
