@@ -11,7 +11,7 @@
 //                      the group): nearby list (every 25 steps), enclosing circles,
 //                      reference-exact ray windows, inside tests -> compact per-env obstacle
 //                      records in HBM                                          latency / FP64
-//   k_lidar<COUNT,VEL> one CTA per 32 consecutive envs, every phase with the mapping that fills
+//   k_lidar<COUNT,VEL,WORLD> one CTA per 32 consecutive envs, every phase with the mapping that fills
 //                      its lanes: hand-over lines + obstacle records -> shared memory; WARP PER
 //                      RECORD over the CTA's flat record list (analytic edge pick for polygonised
 //                      circles, vertices formed on the fly, results merged into the env's range
@@ -925,7 +925,7 @@ __device__ __noinline__ void cast_long_polygon(const double2* __restrict__ wv, i
   }
 }
 
-template <bool COUNT, bool VEL>
+template <bool COUNT, bool VEL, bool WORLD>
 __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(const __grid_constant__ LidarArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NW = AUV_LIDAR_THREADS / 32;
@@ -1027,12 +1027,13 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
           for (int u = lane; u < tot; u += 32) range_min<VEL>(row, u < n1 ? lo1 + u : lo2 + (u - n1), 0.f, slot);
           continue;
         }
-        const bool ngon = !(fl & (OFLAG_PENTAGON | OFLAG_WORLD)) && nq > 16;
+        const bool world = WORLD && (fl & OFLAG_WORLD);  // pools without land polygons run the instantiation without this path
+        const bool ngon = !(fl & OFLAG_PENTAGON) && !world && nq > 16;
         if (!ngon) {
           if (nq > A.vmax) {
             // a world polygon with more vertices than the stage holds (land perimeters of any length): cast chain
             // by chain, out of line -- the hot loop below stays as small as it was without them
-            if (AUV_LIDAR_LONG_POLY && (fl & OFLAG_WORLD))
+            if (AUV_LIDAR_LONG_POLY && world)
               cast_long_polygon<VEL>(reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase, nq, A.vmax, wverts,
                                      HAND(el, NAV_X), HAND(el, NAV_Y), HAND(el, NAV_COSPSI), HAND(el, NAV_SINPSI), cos_sin,
                                      q.ecx, q.ecy, q.rho, row, slot, lane, n1, n2, lo1, lo2, rangef);
@@ -1042,7 +1043,7 @@ __global__ void __launch_bounds__(AUV_LIDAR_THREADS, AUV_LIDAR_MINB) k_lidar(con
           }
           // stage the vertices: vessel-relative, formed in FP64, stored FP32
           __syncwarp();
-          if (fl & OFLAG_WORLD) {
+          if (world) {
             const double px = HAND(el, NAV_X), py = HAND(el, NAV_Y);
             const double2* wv = reinterpret_cast<const double2*>(A.pool.world_verts) + q.vbase;
             for (int k = lane; k < nq; k += 32) {
@@ -1733,9 +1734,11 @@ static int lidar_configure(size_t smem) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
   if (smem <= g_lidar_smem_configured[dev].load(std::memory_order_acquire)) return 0;
-  const void* fns[4] = {(const void*)auv::k_lidar<false, false>, (const void*)auv::k_lidar<true, false>,
-                        (const void*)auv::k_lidar<false, true>, (const void*)auv::k_lidar<true, true>};
-  for (int i = 0; i < 4; ++i)
+  const void* fns[8] = {(const void*)auv::k_lidar<false, false, false>, (const void*)auv::k_lidar<true, false, false>,
+                        (const void*)auv::k_lidar<false, true, false>,  (const void*)auv::k_lidar<true, true, false>,
+                        (const void*)auv::k_lidar<false, false, true>,  (const void*)auv::k_lidar<true, false, true>,
+                        (const void*)auv::k_lidar<false, true, true>,   (const void*)auv::k_lidar<true, true, true>};
+  for (int i = 0; i < 8; ++i)
     if (int rc = cuda_check(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(k_lidar)"))
       return rc;
@@ -1785,10 +1788,20 @@ static int launch_lidar(const AuvConfig* cfg, const AuvRayTable* rays, const Auv
   const int blocks = (cnt + args.envs_per_cta - 1) / args.envs_per_cta;
   cudaStream_t s = (cudaStream_t)stream;
   const bool count = out->seg_tests != nullptr, vel = lidar_velocity(cfg) != 0;
-  if (count && vel) auv::k_lidar<true, true><<<blocks, AUV_LIDAR_THREADS, smem, s>>>(args);
-  else if (count) auv::k_lidar<true, false><<<blocks, AUV_LIDAR_THREADS, smem, s>>>(args);
-  else if (vel) auv::k_lidar<false, true><<<blocks, AUV_LIDAR_THREADS, smem, s>>>(args);
-  else auv::k_lidar<false, false><<<blocks, AUV_LIDAR_THREADS, smem, s>>>(args);
+  const bool world = pool->n_world > 0;  // the instantiation with the land-polygon path only when there is land
+#define AUV_LAUNCH_LIDAR(C, V, W) auv::k_lidar<C, V, W><<<blocks, AUV_LIDAR_THREADS, smem, s>>>(args)
+  if (world) {
+    if (count && vel) AUV_LAUNCH_LIDAR(true, true, true);
+    else if (count) AUV_LAUNCH_LIDAR(true, false, true);
+    else if (vel) AUV_LAUNCH_LIDAR(false, true, true);
+    else AUV_LAUNCH_LIDAR(false, false, true);
+  } else {
+    if (count && vel) AUV_LAUNCH_LIDAR(true, true, false);
+    else if (count) AUV_LAUNCH_LIDAR(true, false, false);
+    else if (vel) AUV_LAUNCH_LIDAR(false, true, false);
+    else AUV_LAUNCH_LIDAR(false, false, false);
+  }
+#undef AUV_LAUNCH_LIDAR
   return cuda_check(cudaGetLastError(), "k_lidar");
 }
 
