@@ -277,6 +277,7 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
     unsigned live = 0u;
 #pragma unroll
     for (int k = 0; k < 32 / G; ++k) {
+      if (k * G >= wn) break;  // (uniform in the group; in the warp too when its envs share a path)
       const int t = k * G + sub;
       const int i = min(w0 + t, nsb - 1);
       const float2 a0 = sba[i];

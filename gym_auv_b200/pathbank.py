@@ -23,7 +23,7 @@ import os
 import numpy as np
 from scipy import interpolate
 
-PATH_BLOCK = 32  # must equal AUV_PATH_BLOCK in include/auv_b200.h
+PATH_BLOCK = int(os.environ.get("AUV_PATH_BLOCK", 32))  # must equal AUV_PATH_BLOCK in include/auv_b200.h (env override: tuning builds only)
 PATH_SUPER = int(os.environ.get("AUV_PATH_SUPER", 16))  # blocks per superblock, AUV_PATH_SUPER (env override: tuning builds only)
 N_KNOTS = 1000
 PP_W = 12  # AUV_PP_W

@@ -61,7 +61,9 @@ extern "C" {
 
 #define AUV_MAX_RAYS 1024
 #define AUV_MAX_OBSTACLES 1024 /* moving + static slots per env */
+#ifndef AUV_PATH_BLOCK
 #define AUV_PATH_BLOCK 32     /* polyline segments per projection block */
+#endif
 #ifndef AUV_PATH_SUPER
 #define AUV_PATH_SUPER 16     /* blocks per projection superblock (8 / 16 / 32 swept: profiles/r1j_variants.txt) */
 #endif
@@ -73,7 +75,9 @@ extern "C" {
 #define AUV_STATUS_PATH_TOO_LONG 8 /* auv_pathbank_build: a path's 0.1 m polyline does not fit its slot (vcap) */
 #define AUV_STATUS_BOUNDS 16 /* -DAUV_DEBUG_BOUNDS builds only: an index check of a step kernel failed */
 #define AUV_STATUS_POLY_TOO_LARGE 4 /* a world polygon has more than AUV_MAX_POLY_VERTS vertices: it was skipped */
-#define AUV_PATH_STAGE_BLOCKS 512 /* paths with at most this many projection blocks (~1.6 km) are searched from a
+#ifndef AUV_PATH_STAGE_BLOCKS
+#define AUV_PATH_STAGE_BLOCKS 512
+#endif                            /* paths with at most this many projection blocks (~1.6 km) are searched from a
                                      shared-memory copy of their capsule tables (one bulk async copy per CTA) */
 #define AUV_PP_W 12           /* doubles per PCHIP piece record in AuvPathBank.pp */
 
