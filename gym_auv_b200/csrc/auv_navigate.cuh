@@ -230,6 +230,10 @@ __device__ __noinline__ float project_cold_bound(const PathTabs& T, const int nb
   return ub;
 }
 
+#ifndef AUV_PROJ_UNROLL
+#define AUV_PROJ_UNROLL 2  // unroll of the FP64 refine over a lane's 8 segments (1 / 4 / 8 measured: see DESIGN 5d)
+#endif
+constexpr int kProjUnroll = AUV_PROJ_UNROLL;
 template <int G>
 __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const AuvPathHdr& h, const PathTabs& T,
                                                    const double px, const double py, const int prev_seg,
@@ -307,7 +311,7 @@ __device__ AUV_PROJECT_INLINE double project_group(const AuvPathBank& pb, const 
         // (screening these in FP32 first was measured slower: far from the path many segments tie within the
         // FP32 error bound, and the divergent FP64 re-evaluation costs more than evaluating all of them)
         double2 va = poly[min(k0, se)];
-#pragma unroll 2
+#pragma unroll kProjUnroll
         for (int u = 0; u < KS; ++u) {
           const double2 vb = poly[min(k0 + u + 1, se)];
           if (k0 + u < se) {
