@@ -351,6 +351,9 @@ __device__ __forceinline__ bool slot_is_near(const AuvScenarioPool& pool, const 
   return (dist - width) < range;
 }
 
+#ifndef AUV_CULL_COOP
+#define AUV_CULL_COOP 1
+#endif
 // Culling stage for one env by its group of G lanes: the lanes take different obstacle slots
 // (slot j of a 32-slot word belongs to lane j % G), records are emitted in slot order by a
 // ballot prefix.  `store` is false for the padding groups past the end of the env range.
@@ -367,11 +370,34 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
   const double range = cfg.sensor_range, width = cfg.vessel_width;
   ObstRec* rec = reinterpret_cast<ObstRec*>(batch.rec) + (long long)e * batch.rec_cap;
   int cnt = 0;
+  // ---- nearby list: {o : dist(p0, o.boundary) - width < range}   vessel.py:266-273
+  // An env refreshes its list every 25 steps; in the desynchronised steady state that is ~1 of the 8 envs of a
+  // warp per step -- but most warps have one.  The warp therefore does its refreshing envs one after the other
+  // with ALL 32 lanes on different slots (one round for 32 slots) instead of leaving each to the 4 lanes of its
+  // group (8 rounds during which the other groups wait).  (AUV_CULL_COOP 0: the per-group version.)
+  const int K = pool.k_moving + pool.k_static;
+  const bool grid = pool.world_cell_off != nullptr && pool.n_world > 0;  // world slots through the broad phase
+  const int S_scan = grid ? K : S;
+#if AUV_CULL_COOP
+  const unsigned rmask = __ballot_sync(AUV_FULL, refresh && sub == 0 && store);
+  for (unsigned rm = rmask; rm; rm &= rm - 1) {  // uniform in the warp
+    const int src = __ffs(rm) - 1;
+    const int eb = __shfl_sync(AUV_FULL, e, src), sb = __shfl_sync(AUV_FULL, scn, src);
+    const int nb = __shfl_sync(AUV_FULL, n_upd, src);
+    const double pxb = __shfl_sync(AUV_FULL, px, src), pyb = __shfl_sync(AUV_FULL, py, src);
+    for (int base = 0; base < S; base += 32) {
+      unsigned word = 0u;
+      if (base < S_scan) {
+        const int j = base + lane;
+        word = __ballot_sync(AUV_FULL, j < S_scan && slot_is_near(pool, batch, unit64, eb, sb, j, pxb, pyb, nb, range, width));
+      }
+      if (lane == src) batch.nearby_mask[(long long)eb * batch.mask_words + (base >> 5)] = word;
+    }
+  }
+  if (rmask) __syncwarp();
+#endif
   if (refresh) {
-    // ---- nearby list: {o : dist(p0, o.boundary) - width < range}   vessel.py:266-273
-    const int K = pool.k_moving + pool.k_static;
-    const bool grid = pool.world_cell_off != nullptr && pool.n_world > 0;  // world slots through the broad phase
-    const int S_scan = grid ? K : S;
+#if !AUV_CULL_COOP
     for (int base = 0; base < S; base += 32) {
       unsigned word = 0u;
       if (base < S_scan) {
@@ -384,6 +410,7 @@ __device__ __forceinline__ void cull_env_group(const AuvConfig& cfg, const AuvSc
       }
       if (store && sub == 0) batch.nearby_mask[(long long)e * batch.mask_words + (base >> 5)] = word;
     }
+#endif
     if (grid) {
       // uniform grid over the world's enclosing circles: only the polygons listed in the cells that the
       // detection disc's bounding box overlaps can be near; the exact test is the same
