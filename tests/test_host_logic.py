@@ -280,3 +280,54 @@ def test_device_path_slot_capacity_covers_the_random_curve_family():
             assert build_path(w).length <= l1 + 1e-9
     bank = DevicePathBank([random_curve_waypoints(rng, 5, length=800.0)])
     assert 10 * 4.08 * 800.0 + 2 <= bank.vcap
+
+
+def test_env_group_ring_hands_out_groups_in_completion_order():
+    """EnvGroupRing.recv returns whichever pending group has finished (not the oldest submission), send appends to
+    the pending list, recv without anything in flight raises -- checked with stand-in groups (no GPU)."""
+    from gym_auv_b200.vec_env import EnvGroupRing
+
+    class Done:
+        def __init__(self):
+            self.ready = False
+
+        def query(self):
+            return self.ready
+
+    class Group:
+        num_envs = 5
+
+        def __init__(self, name):
+            self.name, self._async_done, self.wait_seconds, self.sent = name, Done(), 0.0, []
+
+        def step_async(self, actions):
+            self.sent.append(actions)
+            self._async_done.ready = False
+
+        def step_wait(self):
+            return (self.name, len(self.sent)), "rew", "done"
+
+        def reset(self):
+            return self.name
+
+        def close(self):
+            pass
+
+    groups = [Group("a"), Group("b"), Group("c")]
+    ring = EnvGroupRing(groups)
+    assert len(ring) == 3 and ring.envs_per_group == 5 and ring.reset() == ["a", "b", "c"]
+    with pytest.raises(RuntimeError):
+        ring.recv()
+    for g in range(3):
+        ring.send(g, g)
+    assert ring.pending == [0, 1, 2]
+    groups[2]._async_done.ready = True  # the last submission finishes first
+    g, obs, rew, done = ring.recv()
+    assert g == 2 and obs == ("c", 1) and ring.pending == [0, 1]
+    ring.send(2, "next")
+    groups[0]._async_done.ready = groups[1]._async_done.ready = True
+    assert [ring.recv()[0] for _ in range(2)] == [0, 1]  # both ready: submission order
+    groups[2]._async_done.ready = True
+    assert [r[0] for r in ring.drain()] == [2] and ring.pending == []
+    ring.close()
+    assert ring.groups == []
