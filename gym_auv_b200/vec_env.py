@@ -912,6 +912,7 @@ class AUVVecEnv:
             torch.cuda.synchronize(self.device)
             self.lib.auv_pipeline_destroy(self._pipe)
             self._pipe = None
+            self._async_call = None  # (its argument list holds the destroyed pipeline)
 
     def __del__(self):
         try:
