@@ -212,6 +212,27 @@ def test_bad_arguments_return_error_codes_not_crashes(built_lib):
     assert b"t_step_size" in lib.auv_last_error()
 
 
+def test_delta_host_step_rejects_bad_arguments(built_lib):
+    """auv_step_host_delta_submit validates its AuvDelta before touching the device: NULL buffers, a chunk size
+    other than 8 / 16 / 32 floats and unaligned arrays come back as error codes."""
+    from gym_auv_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.auv_step_host_delta_submit(None, None, None, None, None, None, None, None, None, None, None, None, None, 1) == -1
+    assert b"NULL" in lib.auv_last_error()
+    cfg, batch, out = _lib.AuvConfig(t_step_size=1.0), _lib.AuvBatch(n_envs=4), _lib.AuvStepOut()
+    p = ctypes.c_void_p(64)
+    args = lambda d: (ctypes.byref(cfg), None, None, None, ctypes.byref(batch), p, p, ctypes.byref(out), ctypes.byref(d), p, p,
+                      None, None, 1)
+    assert lib.auv_step_host_delta_submit(*args(_lib.AuvDelta(None, None, None, 16, 0))) == -1
+    assert b"delta buffers" in lib.auv_last_error()
+    assert lib.auv_step_host_delta_submit(*args(_lib.AuvDelta(64, 64, None, 12, 0))) == -1
+    assert b"gran" in lib.auv_last_error()
+    assert lib.auv_step_host_delta_submit(*args(_lib.AuvDelta(64, 72, None, 16, 0))) == -1
+    assert b"aligned" in lib.auv_last_error()
+    assert ctypes.sizeof(_lib.AuvDelta) == lib.auv_sizeof(11) == 32
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "gym_auv_b200")
     for fn in os.listdir(pkg):
