@@ -298,6 +298,98 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def kernel_times(kms):
+    """kms[K][3] = the three intervals of auv_step_timed per step (ms): k_vessel_nav, k_nav_cull, k_lidar.  (A library
+    whose timer still brackets the navigation pair as one interval reports ~0 in the first: the pair is then kept whole.)"""
+    kms = np.asarray(kms, dtype=np.float64)
+    mmm = lambda v: [float(v.min()), float(np.median(v)), float(v.max())]
+    pair = kms[:, 0] + kms[:, 1]
+    out = {"k_lidar": float(kms[:, 2].mean()), "nav_pair": float(pair.mean()),
+           "k_lidar_min_med_max": mmm(kms[:, 2]), "nav_pair_min_med_max": mmm(pair)}
+    if kms[:, 0].mean() > 0.02 * pair.mean():
+        out.update({"k_vessel_nav": float(kms[:, 0].mean()), "k_nav_cull": float(kms[:, 1].mean())})
+    else:
+        out.update({"k_vessel_nav": float(pair.mean()), "k_nav_cull": None})
+    return out
+
+
+def roofline_block(N, R, obs_dim, step_ms, kernel_ms, records_per_step, seg_tests_per_step, k_moving, k_static,
+                   refresh_interval, table_tracks, fp32_peak_tflops, workload):
+    """The `roofline` object of the JSON line: every step kernel with its algorithmic bytes against
+    the measured HBM peak, k_lidar also with the SURVEY 8(d) FLOP count against the FP32 FMA probe; the headline fields
+    are those of the DOMINANT kernel = the single launch with the longest duration in the steady state."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    flops_per_launch = FLOP_PER_SEG_TEST * seg_tests_per_step + FLOP_PER_RAY * R * N
+    lidar_tflops = flops_per_launch / (kernel_ms["k_lidar"] * 1e-3) / 1e12
+    # Algorithmic bytes per launch, steady state, per env:
+    #   k_vessel_nav: reads state 48 + action 8 + counters / ids 44 + the path's header line 64 + the winning polyline
+    #     segment 48, writes state 48 + counters 16 + the arclength 8.
+    #   k_nav_cull: reads state 48 + ids 20 + header 64 + 2 PCHIP piece records 2 x 96 + its obstacle records' sources
+    #     (64 B per nearby moving slot, 32 B per nearby static slot; all slots once per refresh interval), writes the
+    #     navigation record 192 + obs[0..5] 24 + its obstacle records (80 B each).
+    #   k_lidar: reads the hand-over line 128 and its obstacle records (80 B each), writes the closeness part of obs
+    #     4 * (obs_dim - 6), reward / done / info 15, counters 20.
+    rec_per_env = records_per_step / N
+    slot_bytes = (k_moving * 64 + k_static * 32) / max(refresh_interval, 1) + rec_per_env * 48
+    if table_tracks:
+        slot_bytes += k_moving * (80 + 40)  # table-driven tracks: per-env obstacle state read + written every step
+    split = kernel_ms.get("k_nav_cull") is not None
+    nav_bytes = N * (48 + 8 + 44 + 64 + 48 + 48 + 16 + 8)
+    cull_bytes = N * (48 + 20 + 64 + 192 + slot_bytes + 192 + 24) + 80.0 * records_per_step
+    kbytes = {"k_vessel_nav": nav_bytes if split else nav_bytes + cull_bytes,
+              "k_lidar": N * (128 + 4 * (obs_dim - 6) + 15 + 20) + 80.0 * records_per_step}
+    if split:
+        kbytes["k_nav_cull"] = cull_bytes
+    traffic = {}
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if workload == "moving" and N == tr["envs"] and R == tr["rays"]:
+            traffic = {k: tr[k]["dram_bytes_per_launch"] for k in kbytes if k in tr}
+            if not split and "k_nav_cull" in tr:
+                traffic["k_vessel_nav"] = tr["k_vessel_nav"]["dram_bytes_per_launch"] + tr["k_nav_cull"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    kernels = {}
+    for k, nbytes in kbytes.items():
+        gbs = nbytes / (kernel_ms[k] * 1e-3) / 1e9
+        kernels[k] = {"ms_per_launch": kernel_ms[k], "algo_bytes_per_launch": nbytes, "hbm_gbs": gbs,
+                      "hbm_frac": gbs / hbm_peak, "traffic": traffic.get(k)}
+    kernels["k_lidar"].update({"fp32_tflops": lidar_tflops, "fp32_peak_tflops": fp32_peak_tflops,
+                               "fp32_frac": lidar_tflops / fp32_peak_tflops if fp32_peak_tflops else None,
+                               "seg_tests_per_env_step": seg_tests_per_step / N})
+    dominant = max(kernels, key=lambda k: kernels[k]["ms_per_launch"])
+    step_gbs = ALGO_BYTES_PER_ENV_STEP * N / (step_ms * 1e-3) / 1e9
+    if dominant != "k_lidar":
+        roof = {"kernel": dominant if split else "k_vessel_nav + k_nav_cull", "bound": "hbm",
+                "achieved": kernels[dominant]["hbm_gbs"], "peak": hbm_peak,
+                "unit": "GB/s", "frac": kernels[dominant]["hbm_frac"], "traffic": kernels[dominant]["traffic"],
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
+    else:  # SURVEY 8(d): lidar_cast is bound by the FP32 pipe / instruction issue, not by tensor cores or HBM
+        roof = {"kernel": dominant, "bound": "fp32", "achieved": lidar_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                "frac": kernels[dominant]["fp32_frac"], "traffic": kernels[dominant]["traffic"],
+                "peak_source": "FP32 FMA probe measured in this run (no FP32 peak in MEASURED_PEAKS.json)"}
+    roof.update({
+        "ms_per_launch": kernels[dominant]["ms_per_launch"],
+        "algo_bytes_per_launch": kernels[dominant]["algo_bytes_per_launch"],
+        "records_per_env_step": rec_per_env,
+        "kernels": kernels,
+        "kernel_ms": kernel_ms,
+        "note": "dominant kernel = the single launch with the longest duration in the STEADY STATE (CUDA events around "
+                "every kernel of a single-stream run of K steps, auv_step_timed).  k_vessel_nav / k_nav_cull: algorithmic "
+                "bytes against the measured HBM peak; k_lidar: SURVEY 8(d) FLOPs (16 x reference-semantics ray/segment "
+                "tests + 60 x rays) against an FP32 FMA probe; ncu pipe / issue numbers of all three: profiles/.",
+        "step_hbm_view": {"achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
+                          "algo_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                          "note": "whole step (all kernels), SURVEY 8(d) bytes per env-step / timed-region time per step"},
+    })
+    return roof
+
+
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
@@ -431,9 +523,7 @@ def run_ours(args):
     for i in range(K):
         _lib.check(env.lib.auv_timer_read(timer, i, kms[i].ctypes.data_as(C.POINTER(C.c_float))), "auv_timer_read")
     env.lib.auv_timer_destroy(timer)
-    kernel_ms = {"k_vessel_nav": float(kms[:, 1].mean()), "k_lidar": float(kms[:, 2].mean())}
-    kernel_ms["k_lidar_min_med_max"] = [float(kms[:, 2].min()), float(np.median(kms[:, 2])), float(kms[:, 2].max())]
-    kernel_ms["k_vessel_nav_min_med_max"] = [float(kms[:, 1].min()), float(np.median(kms[:, 1])), float(kms[:, 1].max())]
+    kernel_ms = kernel_times(kms)
     kernel_ms["single_stream_ms_per_step"] = serial_ms_per_step
 
     # ---- counting pass (untimed): K more steps with the seg-test counter on
@@ -573,69 +663,10 @@ def run_ours(args):
 
     print(f"[bench] value={value:.4g} ms/step={ms_max / K:.4f} after_reset_ms={after_reset_ms:.4f} kernel_ms={kernel_ms} "
           f"setup_s={setup_s:.1f} e2e={e2e}", file=sys.stderr)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    flops_per_launch = FLOP_PER_SEG_TEST * seg_tests_per_step + FLOP_PER_RAY * (R if cfg.vessel.use_lidar else 0) * N
-    lidar_tflops = flops_per_launch / (kernel_ms["k_lidar"] * 1e-3) / 1e12
-    # Algorithmic bytes per launch of the two step kernels, steady state.
-    #   k_vessel_nav per env: reads state 48 + action 8 + counters / ids 44 + the path's header line 64 +
-    #     2 PCHIP piece records 2 x 96 + the winning polyline segment 48 + its obstacle records' sources
-    #     (64 B per nearby moving slot, 32 B per nearby static slot; all slots once per 25 steps), writes
-    #     state 48 + counters 16 + navigation record 192 + obs[0..5] 24 + its obstacle records (80 B each).
-    #   k_lidar per env: reads the hand-over line 128 and its obstacle records (80 B each), writes the
-    #     closeness part of obs 4*(obs_dim-6), reward/done/info 15, counters 20.
-    Km, Ks = env.k_moving, env.k_static
-    rec_per_env = records_per_step / N
-    slot_bytes = (Km * 64 + Ks * 32) / max(cfg.vessel.sensor_interval_load_obstacles, 1) + rec_per_env * 48
-    if env.linear is None:
-        slot_bytes += Km * (80 + 40)  # table-driven tracks: per-env obstacle state read + written every step
-    kbytes = {
-        "k_vessel_nav": N * (48 + 8 + 44 + 64 + 192 + 48 + slot_bytes + 48 + 16 + 192 + 24) + 80.0 * records_per_step,
-        "k_lidar": N * (128 + 4 * (env.obs_dim - 6) + 15 + 20) + 80.0 * records_per_step,
-    }
-    traffic = {}
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        if args.workload == "moving" and N == tr["envs"] and R == tr["rays"]:
-            traffic = {k: tr[k]["dram_bytes_per_launch"] for k in kbytes}
-    except Exception:
-        pass
-    kernels = {}
-    for k, nbytes in kbytes.items():
-        gbs = nbytes / (kernel_ms[k] * 1e-3) / 1e9
-        kernels[k] = {"ms_per_launch": kernel_ms[k], "algo_bytes_per_launch": nbytes, "hbm_gbs": gbs,
-                      "hbm_frac": gbs / hbm_peak, "traffic": traffic.get(k)}
-    kernels["k_lidar"].update({"fp32_tflops": lidar_tflops, "fp32_peak_tflops": fp32_peak_tflops,
-                               "fp32_frac": lidar_tflops / fp32_peak_tflops if fp32_peak_tflops else None,
-                               "seg_tests_per_env_step": seg_tests_per_step / N})
-    dominant = max(("k_vessel_nav", "k_lidar"), key=lambda k: kernels[k]["ms_per_launch"])
-    step_gbs = ALGO_BYTES_PER_ENV_STEP * N / (ms_max / K * 1e-3) / 1e9
-    if dominant == "k_vessel_nav":
-        roof = {"kernel": dominant, "bound": "hbm", "achieved": kernels[dominant]["hbm_gbs"], "peak": hbm_peak,
-                "unit": "GB/s", "frac": kernels[dominant]["hbm_frac"], "traffic": kernels[dominant]["traffic"],
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
-    else:  # lidar_cast is bound by the FP32 pipe / instruction issue, not by tensor cores or HBM
-        roof = {"kernel": dominant, "bound": "fp32", "achieved": lidar_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                "frac": kernels[dominant]["fp32_frac"], "traffic": kernels[dominant]["traffic"],
-                "peak_source": "FP32 FMA probe measured in this run (no FP32 peak in MEASURED_PEAKS.json)"}
-    roof.update({
-        "ms_per_launch": kernels[dominant]["ms_per_launch"],
-        "algo_bytes_per_launch": kernels[dominant]["algo_bytes_per_launch"],
-        "records_per_env_step": rec_per_env,
-        "kernels": kernels,
-        "kernel_ms": kernel_ms,
-        "note": "dominant kernel of the STEADY STATE (CUDA-event launch durations of a single-stream run of K steps, "
-                "auv_step_timed).  k_vessel_nav: algorithmic bytes against the measured HBM peak; k_lidar: SURVEY 8(d) "
-                "FLOPs (16 x reference-semantics ray/segment tests + 60 x rays) against an FP32 FMA probe; ncu pipe / "
-                "issue numbers of both: profiles/.",
-        "step_hbm_view": {"achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
-                          "algo_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
-                          "note": "whole step (both kernels), SURVEY 8(d) bytes per env-step / timed-region time per step"},
-    })
+    roof = roofline_block(N=N, R=R if cfg.vessel.use_lidar else 0, obs_dim=env.obs_dim, step_ms=ms_max / K, kernel_ms=kernel_ms,
+                          records_per_step=records_per_step, seg_tests_per_step=seg_tests_per_step, k_moving=env.k_moving,
+                          k_static=env.k_static, refresh_interval=cfg.vessel.sensor_interval_load_obstacles,
+                          table_tracks=env.linear is None, fp32_peak_tflops=fp32_peak_tflops, workload=args.workload)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

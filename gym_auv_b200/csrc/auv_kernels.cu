@@ -1726,7 +1726,8 @@ static int nav_configure(size_t smem) {
 
 static int launch_vessel_nav(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                              const AuvScenarioPool* pool, AuvBatch* batch, AuvStepOut* out,
-                             const float* actions, void* stream, int e0 = 0, int cnt = -1, bool with_obstacles = false) {
+                             const float* actions, void* stream, int e0 = 0, int cnt = -1, bool with_obstacles = false,
+                             cudaEvent_t between = nullptr /* recorded between the two launches (auv_step_timed) */) {
   if (cnt < 0) cnt = batch->n_envs - e0;
   const int per_cta = AUV_NAV_THREADS / AUV_NAV_G;  // envs per CTA
   const int blocks = (cnt + per_cta - 1) / per_cta;
@@ -1748,6 +1749,7 @@ static int launch_vessel_nav(const AuvConfig* cfg, const AuvRayTable* rays, cons
     auv::k_vessel_nav<false, false, AUV_NAV_G><<<blocks, AUV_NAV_THREADS, nsm, s>>>(*cfg, *paths, *pool, *batch, unit, win, nullptr, obs, od, e0, e0 + cnt);
   if (AUV_NAV_SPLIT) {
     if (int rc = cuda_check(cudaGetLastError(), "k_vessel_nav")) return rc;
+    if (between != nullptr) cudaEventRecord(between, s);
     auv::k_nav_cull<AUV_NAV_G><<<(cnt + 31) / 32, 128, 0, s>>>(*cfg, *paths, *pool, *batch, unit, win, obs, od, e0, e0 + cnt);
     return cuda_check(cudaGetLastError(), "k_nav_cull");
   }
@@ -2232,8 +2234,10 @@ int auv_step_timed(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathB
   cudaStream_t s = (cudaStream_t)stream;
   cudaEvent_t* e = t->ev + AUV_TIMER_EVENTS * slot;
   cudaEventRecord(e[0], s);
-  cudaEventRecord(e[1], s);  // the obstacle update is fused into k_vessel_nav: slot 0 reads ~0
-  if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, actions, stream, 0, -1, true)) return rc;
+  if (!AUV_NAV_SPLIT) cudaEventRecord(e[1], s);  // one navigation launch: interval 0 reads ~0, interval 1 is the kernel
+  if (int rc = launch_vessel_nav(cfg, rays, paths, pool, batch, out, actions, stream, 0, -1, true,
+                                 AUV_NAV_SPLIT ? e[1] : nullptr))
+    return rc;
   cudaEventRecord(e[2], s);
   if (int rc = launch_lidar(cfg, rays, paths, pool, batch, out, AUV_OBSERVE_STEP, stream)) return rc;
   return cuda_check(cudaEventRecord(e[3], s), "cudaEventRecord");

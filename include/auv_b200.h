@@ -413,11 +413,11 @@ int auv_step_host_delta_submit(const AuvConfig* cfg, const AuvRayTable* rays, co
 typedef struct AuvTimer AuvTimer;
 AuvTimer* auv_timer_create(int capacity);
 void auv_timer_destroy(AuvTimer* t);
-/* auv_step with events recorded around k_obstacle_update, k_vessel_nav and k_lidar. */
+/* auv_step on ONE stream with events recorded around each of its kernels. */
 int auv_step_timed(const AuvConfig* cfg, const AuvRayTable* rays, const AuvPathBank* paths,
                    const AuvScenarioPool* pool, AuvBatch* batch, const float* actions,
                    AuvStepOut* out, void* stream, AuvTimer* t, int slot);
-/* after the stream is synchronised: ms[0..2] = obstacle_update, vessel_nav, lidar */
+/* after the stream is synchronised: ms[0..2] = k_vessel_nav, k_nav_cull, k_lidar */
 int auv_timer_read(AuvTimer* t, int slot, float* ms);
 /* GPU-side scenario generation for the MovingObstacles family:
  * what MovingObstacles._generate (envs/movingobstacles.py:28-95) and helpers.generate_obstacle

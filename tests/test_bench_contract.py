@@ -38,3 +38,38 @@ def test_gpu_arm_fails_loudly_without_cuda():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode != 0 and "no CPU fallback" in (res.stderr + res.stdout)
+
+
+def test_roofline_block_names_the_longest_single_launch():
+    """bench.roofline_block: three step kernels, each with its own CUDA-event interval; the headline roofline is that of
+    the single launch with the longest duration (k_lidar -> FP32 roof, a navigation kernel -> HBM roof); a timer that
+    brackets the navigation pair as one interval keeps the pair whole.  Pure host logic: no GPU, no oracle."""
+    import numpy as np
+
+    import bench
+
+    kms = np.array([[0.052, 0.037, 0.075], [0.054, 0.039, 0.077]], dtype=np.float32)
+    t = bench.kernel_times(kms)
+    assert abs(t["k_vessel_nav"] - 0.053) < 1e-6 and abs(t["k_nav_cull"] - 0.038) < 1e-6 and abs(t["nav_pair"] - 0.091) < 1e-6
+    assert t["k_lidar_min_med_max"][0] <= t["k_lidar"] <= t["k_lidar_min_med_max"][2]
+    kw = dict(N=65536, R=180, obs_dim=186, step_ms=0.164, records_per_step=1.4 * 65536, seg_tests_per_step=1200.0 * 65536,
+              k_moving=16, k_static=16, refresh_interval=25, table_tracks=False, fp32_peak_tflops=64.0, workload="moving")
+    r = bench.roofline_block(kernel_ms=t, **kw)
+    assert r["kernel"] == "k_lidar" and r["bound"] == "fp32" and r["unit"] == "TFLOP/s"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0.2 < r["frac"] < 0.6
+    assert set(r["kernels"]) == {"k_vessel_nav", "k_nav_cull", "k_lidar"}
+    assert all(k["hbm_frac"] > 0 and k["algo_bytes_per_launch"] > 0 for k in r["kernels"].values())
+    assert r["traffic"] is None or r["traffic"] > 0  # profiles/ncu_traffic.json: per launch, like `achieved`
+    # the navigation kernel as the longest launch -> HBM roof
+    slow = dict(t, k_vessel_nav=0.2, nav_pair=0.238)
+    r = bench.roofline_block(kernel_ms=slow, **kw)
+    assert r["kernel"] == "k_vessel_nav" and r["bound"] == "hbm" and r["unit"] == "GB/s" and 0 < r["frac"] < 1
+    # an older timer: interval 0 ~ 0, interval 1 = the pair
+    t2 = bench.kernel_times(np.array([[0.0004, 0.091, 0.075]], dtype=np.float32))
+    assert t2["k_nav_cull"] is None and abs(t2["k_vessel_nav"] - 0.0914) < 1e-5
+    r = bench.roofline_block(kernel_ms=t2, **kw)
+    assert r["kernel"] == "k_vessel_nav + k_nav_cull" and set(r["kernels"]) == {"k_vessel_nav", "k_lidar"}
+    assert r["traffic"] is None or r["traffic"] > 5e7
+    import json
+
+    json.dumps(r)  # serialisable

@@ -46,11 +46,7 @@ for r in raw[2:]:
     key = next(k for k in KERNELS if k in name)
     traffic[key] = {"dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
                     "inst_executed": val("smsp__inst_executed.sum") if "smsp__inst_executed.sum" in h else None}
-# bench.py attributes both navigation launches to "k_vessel_nav" (one CUDA-event interval)
-if "k_nav_cull" in traffic and "k_vessel_nav" in traffic:
-    a, b = traffic["k_vessel_nav"], traffic.pop("k_nav_cull")
-    traffic["k_vessel_nav"] = {k: (a[k] or 0) + (b[k] or 0) for k in a}
-    traffic["k_vessel_nav"]["note"] = "k_vessel_nav + k_nav_cull"
+# (one entry per kernel: bench.py times every launch of the step by its own CUDA-event interval)
 for k in KERNELS:
     f = os.path.join(ROOT, "gpurun_out", f"cs_{tag}_{k}.csv")
     with open(f, "w") as fh:
